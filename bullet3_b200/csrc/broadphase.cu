@@ -1,0 +1,638 @@
+// broadphase.cu -- pair finding on sm_100a.
+//
+// Two algorithms behind the b3GpuBroadphaseInterface contract
+// (b3GpuBroadphaseInterface.h:12-40):
+//   GRID : uniform-grid cell hash (128^3 wrapped, like gridBroadphase.cl:13-21)
+//          -> stable KV radix sort -> cell starts -> 27-cell scan.  Unlike the
+//          reference grid (which silently drops pairs whose AABB is wider than
+//          the fixed 3.0 cell) the cell edge is re-derived
+//          every call from the widest small AABB, so the pair SET equals the
+//          brute-force host twin calculateOverlappingPairsHost
+//          (b3GpuSapBroadphase.cpp:862-981) bit for bit.
+//   SAP  : 1-axis sweep on the axis of largest centre variance
+//          (b3GpuSapBroadphase.cpp:997-1231): FloatFlip keys -> sort -> gather ->
+//          forward sweep.
+// Static ("large") proxies are tested brute force against all small ones
+// (computePairsKernelTwoArrays, sap.cl:66).
+//
+// Pairs are staged per warp in shared memory and flushed with ONE global atomic
+// per >=64 pairs and coalesced 16-byte stores (the reference does one global
+// atomic_add per pair: gridBroadphase.cl:151, sap.cl:296).  No host round trip:
+// axis choice, cell size and pair count stay on the device.
+#include "internal.h"
+
+namespace b3b200
+{
+constexpr int BP_THREADS = 128;
+constexpr int GRID_DIM = 128;
+constexpr int GRID_CELLS = GRID_DIM * GRID_DIM * GRID_DIM;
+constexpr int STAGE_CAP = 96;  // per-warp staging: flush at >= 64
+
+// scalars layout (32-bit words)
+enum
+{
+	SC_MAXEXT_BITS = 0,
+	SC_CELL = 1,
+	SC_INVCELL = 2,
+	SC_AXIS = 3,
+	SC_SUM = 4,   // 3 floats
+	SC_SUM2 = 7,  // 3 floats
+	SC_COUNT = 16
+};
+
+B3_D bool aabbOverlap(const float4& mn1, const float4& mx1, const float4& mn2, const float4& mx2)
+{
+	// b3TestAabbAgainstAabb (shared/b3Aabb.h:45-53): inclusive, NaN => overlapping
+	bool overlap = true;
+	overlap = (mn1.x > mx2.x || mx1.x < mn2.x) ? false : overlap;
+	overlap = (mn1.z > mx2.z || mx1.z < mn2.z) ? false : overlap;
+	overlap = (mn1.y > mx2.y || mx1.y < mn2.y) ? false : overlap;
+	return overlap;
+}
+
+// All 32 lanes must call this together.
+B3_D void stageFlush(int2* stage, int& count, int lane, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+{
+	unsigned int base = 0;
+	if (lane == 0) base = atomicAdd(&ctr[CTR_PAIRS], (unsigned int)count);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	for (int k = lane; k < count; k += 32)
+	{
+		unsigned int dst = base + k;
+		if (dst < (unsigned int)maxPairs)
+		{
+			int2 p = stage[k];
+			b3b200_int4 o;
+			o.x = p.x;
+			o.y = p.y;
+			o.z = -1;  // clearOverlappingPairsKernel (updateAabbsKernel.cl:15) folded in
+			o.w = -1;
+			pairs[dst] = o;
+		}
+	}
+	__syncwarp();
+	count = 0;
+}
+
+B3_D void stagePush(bool hit, int a, int b, int2* stage, int& count, int lane, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+{
+	unsigned int m = __ballot_sync(0xffffffffu, hit);
+	if (m)
+	{
+		if (hit)
+		{
+			int pos = count + __popc(m & ((1u << lane) - 1u));
+			stage[pos] = make_int2(a < b ? a : b, a < b ? b : a);
+		}
+		count += __popc(m);
+		__syncwarp();
+		if (count >= STAGE_CAP - 32) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
+	}
+}
+
+// ---------------------------------------------------------------- parameters
+__global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n, unsigned int* __restrict__ scal)
+{
+	float ext = 0.f;
+	float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
+		float4 mn = __ldg(p), mx = __ldg(p + 1);
+		ext = fmaxf(ext, fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z)));
+		float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
+		sx += cx;
+		sy += cy;
+		sz += cz;
+		qx += cx * cx;
+		qy += cy * cy;
+		qz += cz * cz;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+		sx += __shfl_xor_sync(0xffffffffu, sx, o);
+		sy += __shfl_xor_sync(0xffffffffu, sy, o);
+		sz += __shfl_xor_sync(0xffffffffu, sz, o);
+		qx += __shfl_xor_sync(0xffffffffu, qx, o);
+		qy += __shfl_xor_sync(0xffffffffu, qy, o);
+		qz += __shfl_xor_sync(0xffffffffu, qz, o);
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		atomicMax(&scal[SC_MAXEXT_BITS], __float_as_uint(ext));
+		float* f = reinterpret_cast<float*>(scal);
+		atomicAdd(&f[SC_SUM + 0], sx);
+		atomicAdd(&f[SC_SUM + 1], sy);
+		atomicAdd(&f[SC_SUM + 2], sz);
+		atomicAdd(&f[SC_SUM2 + 0], qx);
+		atomicAdd(&f[SC_SUM2 + 1], qy);
+		atomicAdd(&f[SC_SUM2 + 2], qz);
+	}
+}
+
+__global__ void bpParamsKernel(unsigned int* scal, int n)
+{
+	float* f = reinterpret_cast<float*>(scal);
+	float ext = __uint_as_float(scal[SC_MAXEXT_BITS]);
+	// the cell edge must be >= the widest small AABB for the 27-cell scan to be exact
+	float cell = fmaxf(ext * 1.01f + 1e-6f, 1e-3f);
+	f[SC_CELL] = cell;
+	f[SC_INVCELL] = 1.0f / cell;
+	// axis of largest variance (b3GpuSapBroadphase.cpp:1041-1051)
+	float nn = (float)n;
+	float vx = f[SC_SUM2 + 0] - f[SC_SUM + 0] * f[SC_SUM + 0] / nn;
+	float vy = f[SC_SUM2 + 1] - f[SC_SUM + 1] * f[SC_SUM + 1] / nn;
+	float vz = f[SC_SUM2 + 2] - f[SC_SUM + 2] * f[SC_SUM + 2] / nn;
+	int axis = 0;
+	float best = vx;
+	if (vy > best)
+	{
+		axis = 1;
+		best = vy;
+	}
+	if (vz > best) axis = 2;
+	scal[SC_AXIS] = (unsigned int)axis;
+}
+
+// ---------------------------------------------------------------- grid
+B3_D int3 cellOf(const float4& mn, const float4& mx, float invCell)
+{
+	float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
+	return make_int3((int)floorf(cx * invCell), (int)floorf(cy * invCell), (int)floorf(cz * invCell));
+}
+B3_D unsigned int cellKey(int x, int y, int z)
+{
+	return ((unsigned int)(z & (GRID_DIM - 1)) << 14) | ((unsigned int)(y & (GRID_DIM - 1)) << 7) | (unsigned int)(x & (GRID_DIM - 1));
+}
+
+__global__ void __launch_bounds__(256) gridHashKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
+													  const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float invCell = __uint_as_float(scal[SC_INVCELL]);
+	int idx = smallMap[i];
+	const float4* p = reinterpret_cast<const float4*>(&aabbs[idx]);
+	int3 c = cellOf(__ldg(p), __ldg(p + 1), invCell);
+	keys[i] = cellKey(c.x, c.y, c.z);
+	vals[i] = (unsigned int)idx;
+}
+
+// gather AABBs into sorted order (coalesced 2x128-bit per proxy) and mark cell starts
+__global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restrict__ aabbs, const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals,
+													int n, b3b200_aabb* __restrict__ sorted, int* __restrict__ cellStart)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4* p = reinterpret_cast<const float4*>(&aabbs[vals[i]]);
+	float4 mn = __ldg(p), mx = __ldg(p + 1);
+	float4* q = reinterpret_cast<float4*>(&sorted[i]);
+	q[0] = mn;
+	q[1] = mx;
+	if (cellStart)
+	{
+		unsigned int k = keys[i];
+		if (i == 0 || keys[i - 1] != k) cellStart[k] = i;
+	}
+}
+
+__global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_aabb* __restrict__ sorted, const unsigned int* __restrict__ keys, const int* __restrict__ cellStart,
+																  int n, const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+{
+	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
+	const int lane = threadIdx.x & 31;
+	int2* stage = stageAll[threadIdx.x >> 5];
+	int count = 0;
+	const float invCell = __uint_as_float(scal[SC_INVCELL]);
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool valid = i < n;
+	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
+	int idA = 0;
+	int3 c = make_int3(0, 0, 0);
+	if (valid)
+	{
+		const float4* p = reinterpret_cast<const float4*>(&sorted[i]);
+		mnA = p[0];
+		mxA = p[1];
+		idA = __float_as_int(mnA.w);
+		c = cellOf(mnA, mxA, invCell);
+	}
+	int nb = 0;
+	int j = -1;
+	unsigned int curKey = 0;
+	for (;;)
+	{
+		bool have = false;
+		if (valid)
+		{
+			for (;;)
+			{
+				if (j >= 0)
+				{
+					if (j < n && keys[j] == curKey)
+					{
+						have = true;
+						break;
+					}
+					j = -1;
+				}
+				if (nb >= 27)
+				{
+					valid = false;
+					break;
+				}
+				int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
+				curKey = cellKey(c.x + dx, c.y + dy, c.z + dz);
+				nb++;
+				j = cellStart[curKey];
+			}
+		}
+		bool hit = false;
+		int idB = 0;
+		if (have)
+		{
+			if (j > i)
+			{
+				const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
+				float4 mnB = p[0], mxB = p[1];
+				idB = __float_as_int(mnB.w);
+				hit = aabbOverlap(mnA, mxA, mnB, mxB);
+			}
+			j++;
+		}
+		stagePush(hit, idA, idB, stage, count, lane, pairs, ctr, maxPairs);
+		if (!__any_sync(0xffffffffu, valid)) break;
+	}
+	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
+}
+
+// ---------------------------------------------------------------- SAP
+B3_D unsigned int floatFlip(float f)
+{
+	// flipFloatKernel (sap.cl:353): IEEE-754 -> order-preserving u32
+	unsigned int u = __float_as_uint(f);
+	unsigned int mask = (unsigned int)(-(int)(u >> 31)) | 0x80000000u;
+	return u ^ mask;
+}
+B3_D float axisOf(const float4& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+__global__ void __launch_bounds__(256) sapKeyKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
+													const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int axis = (int)scal[SC_AXIS];
+	int idx = smallMap[i];
+	float4 mn = __ldg(reinterpret_cast<const float4*>(&aabbs[idx]));
+	keys[i] = floatFlip(axisOf(mn, axis));
+	vals[i] = (unsigned int)idx;
+}
+
+__global__ void __launch_bounds__(BP_THREADS) sapSweepKernel(const b3b200_aabb* __restrict__ sorted, int n, const unsigned int* __restrict__ scal,
+															 b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+{
+	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
+	const int lane = threadIdx.x & 31;
+	int2* stage = stageAll[threadIdx.x >> 5];
+	int count = 0;
+	const int axis = (int)scal[SC_AXIS];
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	bool valid = i < n;
+	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
+	int idA = 0;
+	float limit = 0.f;
+	if (valid)
+	{
+		const float4* p = reinterpret_cast<const float4*>(&sorted[i]);
+		mnA = p[0];
+		mxA = p[1];
+		idA = __float_as_int(mnA.w);
+		limit = axisOf(mxA, axis);
+	}
+	int j = i + 1;
+	for (;;)
+	{
+		bool hit = false;
+		int idB = 0;
+		if (valid)
+		{
+			if (j < n)
+			{
+				const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
+				float4 mnB = p[0];
+				// computePairsKernelLocalSharedMemory break test (sap.cl:231-300)
+				if (limit < axisOf(mnB, axis))
+					valid = false;
+				else
+				{
+					float4 mxB = p[1];
+					idB = __float_as_int(mnB.w);
+					hit = aabbOverlap(mnA, mxA, mnB, mxB);
+					j++;
+				}
+			}
+			else
+				valid = false;
+		}
+		stagePush(hit, idA, idB, stage, count, lane, pairs, ctr, maxPairs);
+		if (!__any_sync(0xffffffffu, valid)) break;
+	}
+	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
+}
+
+// ---------------------------------------------------------------- large x small
+__global__ void __launch_bounds__(BP_THREADS) largeSmallKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int nSmall,
+															   const int* __restrict__ largeMap, int nLarge,
+															   b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+{
+	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
+	const int lane = threadIdx.x & 31;
+	int2* stage = stageAll[threadIdx.x >> 5];
+	int count = 0;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = i < nSmall;
+	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
+	int idA = 0;
+	if (valid)
+	{
+		const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
+		mnA = __ldg(p);
+		mxA = __ldg(p + 1);
+		idA = __float_as_int(mnA.w);
+	}
+	for (int l = 0; l < nLarge; l++)
+	{
+		const float4* p = reinterpret_cast<const float4*>(&aabbs[largeMap[l]]);
+		float4 mnB = __ldg(p), mxB = __ldg(p + 1);
+		bool hit = valid && aabbOverlap(mnA, mxA, mnB, mxB);
+		stagePush(hit, idA, __float_as_int(mnB.w), stage, count, lane, pairs, ctr, maxPairs);
+	}
+	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
+}
+
+__global__ void clampPairsKernel(unsigned int* ctr, int maxPairs)
+{
+	if (ctr[CTR_PAIRS] > (unsigned int)maxPairs)
+	{
+		ctr[CTR_PAIRS] = (unsigned int)maxPairs;
+		ctr[CTR_OVERFLOW] |= OVF_PAIRS;
+	}
+}
+
+// ---------------------------------------------------------------- host side
+int Broadphase::init(int kind_, int device_, cudaStream_t stream_, int maxProxies_, int maxPairs_)
+{
+	kind = kind_;
+	device = device_;
+	maxProxies = maxProxies_;
+	maxPairs = maxPairs_;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	if (stream_)
+	{
+		stream = stream_;
+		ownStream = false;
+	}
+	else
+	{
+		B3_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		ownStream = true;
+	}
+	B3_TRY(counters.reserve(CTR_COUNT));
+	B3_CUDA_CHECK(cudaMemsetAsync(counters.ptr, 0, sizeof(unsigned int) * CTR_COUNT, stream));
+	ctr = counters.ptr;
+	B3_TRY(scalars.reserve(SC_COUNT));
+	B3_TRY(pairs.reserve(maxPairs > 0 ? maxPairs : 1));
+	B3_CUDA_CHECK(cudaEventCreate(&ev0));
+	B3_CUDA_CHECK(cudaEventCreate(&ev1));
+	return 0;
+}
+
+void Broadphase::destroy()
+{
+	cudaSetDevice(device);
+	if (stream) cudaStreamSynchronize(stream);
+	if (ev0) cudaEventDestroy(ev0);
+	if (ev1) cudaEventDestroy(ev1);
+	ev0 = ev1 = nullptr;
+	if (ownStream && stream) cudaStreamDestroy(stream);
+	stream = 0;
+	aabbs.release();
+	smallMap.release();
+	largeMap.release();
+	pairs.release();
+	counters.release();
+	keys.release();
+	vals.release();
+	sortedAabbs.release();
+	cellStart.release();
+	scalars.release();
+}
+
+int Broadphase::reset()
+{
+	aabbsCPU.clear();
+	smallIdx.clear();
+	largeIdx.clear();
+	numSmall = numLarge = numAabbs = 0;
+	return 0;
+}
+
+int Broadphase::createProxy(const float* mn, const float* mx, int userPtr, bool large)
+{
+	if ((int)aabbsCPU.size() >= maxProxies)
+	{
+		setLastError("broadphase: exceeding the number of proxies (%d)", maxProxies);
+		return B3B200_ERR_CAPACITY;
+	}
+	// b3GpuSapBroadphase::createProxy / createLargeProxy (b3GpuSapBroadphase.cpp:1233-1264)
+	b3b200_aabb a;
+	a.min[0] = mn[0];
+	a.min[1] = mn[1];
+	a.min[2] = mn[2];
+	a.minIndices[3] = userPtr;
+	a.max[0] = mx[0];
+	a.max[1] = mx[1];
+	a.max[2] = mx[2];
+	a.signedMaxIndices[3] = (int)aabbsCPU.size();
+	(large ? largeIdx : smallIdx).push_back((int)aabbsCPU.size());
+	aabbsCPU.push_back(a);
+	return 0;
+}
+
+int Broadphase::writeAabbs()
+{
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	numAabbs = (int)aabbsCPU.size();
+	numSmall = (int)smallIdx.size();
+	numLarge = (int)largeIdx.size();
+	B3_TRY(aabbs.reserve(numAabbs > 0 ? numAabbs : 1));
+	B3_TRY(smallMap.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(largeMap.reserve(numLarge > 0 ? numLarge : 1));
+	B3_TRY(keys.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(vals.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(sortedAabbs.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(cellStart.reserve(GRID_CELLS));
+	B3_TRY(sortTmp.keysAlt.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(sortTmp.valsAlt.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(sortTmp.blockHist.reserve((size_t)256 * divUp(numSmall > 0 ? numSmall : 1, 2048)));
+	if (numAabbs) B3_CUDA_CHECK(cudaMemcpyAsync(aabbs.ptr, aabbsCPU.data(), sizeof(b3b200_aabb) * numAabbs, cudaMemcpyHostToDevice, stream));
+	if (numSmall) B3_CUDA_CHECK(cudaMemcpyAsync(smallMap.ptr, smallIdx.data(), sizeof(int) * numSmall, cudaMemcpyHostToDevice, stream));
+	if (numLarge) B3_CUDA_CHECK(cudaMemcpyAsync(largeMap.ptr, largeIdx.data(), sizeof(int) * numLarge, cudaMemcpyHostToDevice, stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(stream));
+	return 0;
+}
+
+int Broadphase::calculatePairs(int maxPairsNow)
+{
+	if (maxPairsNow > maxPairs) maxPairsNow = maxPairs;
+	if (maxPairsNow < 0) maxPairsNow = 0;
+	cudaStream_t s = stream;
+	B3_CUDA_CHECK(cudaMemsetAsync(&ctr[CTR_PAIRS], 0, sizeof(unsigned int), s));
+	if (numSmall > 0)
+	{
+		B3_CUDA_CHECK(cudaMemsetAsync(scalars.ptr, 0, sizeof(float) * SC_COUNT, s));
+		int prepBlocks = divUp(numSmall, 256);
+		if (prepBlocks > 592) prepBlocks = 592;
+		bpPrepKernel<<<prepBlocks, 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, reinterpret_cast<unsigned int*>(scalars.ptr));
+		B3_LAUNCH_CHECK();
+		bpParamsKernel<<<1, 1, 0, s>>>(reinterpret_cast<unsigned int*>(scalars.ptr), numSmall);
+		B3_LAUNCH_CHECK();
+		const unsigned int* scal = reinterpret_cast<const unsigned int*>(scalars.ptr);
+		if (kind == B3B200_BP_GRID)
+		{
+			gridHashKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr);
+			B3_LAUNCH_CHECK();
+			B3_TRY(radixSortKV32(s, sortTmp, keys.ptr, vals.ptr, numSmall, 21));
+			B3_CUDA_CHECK(cudaMemsetAsync(cellStart.ptr, 0xff, sizeof(int) * GRID_CELLS, s));
+			gatherKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, keys.ptr, vals.ptr, numSmall, sortedAabbs.ptr, cellStart.ptr);
+			B3_LAUNCH_CHECK();
+			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, keys.ptr, cellStart.ptr, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
+			B3_LAUNCH_CHECK();
+		}
+		else
+		{
+			sapKeyKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr);
+			B3_LAUNCH_CHECK();
+			B3_TRY(radixSortKV32(s, sortTmp, keys.ptr, vals.ptr, numSmall, 32));
+			gatherKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, keys.ptr, vals.ptr, numSmall, sortedAabbs.ptr, nullptr);
+			B3_LAUNCH_CHECK();
+			sapSweepKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
+			B3_LAUNCH_CHECK();
+		}
+		if (numLarge > 0)
+		{
+			largeSmallKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, largeMap.ptr, numLarge, pairs.ptr, ctr, maxPairsNow);
+			B3_LAUNCH_CHECK();
+		}
+	}
+	clampPairsKernel<<<1, 1, 0, s>>>(ctr, maxPairsNow);
+	B3_LAUNCH_CHECK();
+	return 0;
+}
+
+}  // namespace b3b200
+
+using namespace b3b200;
+
+// ------------------------------------------------------------------ C ABI
+extern "C" int b3b200_bp_create(int kind, int device, void* stream, int maxProxies, int maxPairs, b3b200_broadphase** out)
+{
+	if (!out || maxProxies <= 0 || maxPairs < 0 || (kind != B3B200_BP_SAP && kind != B3B200_BP_GRID)) return B3B200_ERR_INVALID;
+	b3b200_broadphase* bp = new b3b200_broadphase();
+	int r = bp->init(kind, device, (cudaStream_t)stream, maxProxies, maxPairs);
+	if (r < 0)
+	{
+		bp->destroy();
+		delete bp;
+		return r;
+	}
+	*out = bp;
+	return 0;
+}
+extern "C" int b3b200_bp_destroy(b3b200_broadphase* bp)
+{
+	if (!bp) return B3B200_ERR_INVALID;
+	bp->destroy();
+	delete bp;
+	return 0;
+}
+extern "C" int b3b200_bp_create_proxy(b3b200_broadphase* bp, const float* mn, const float* mx, int userPtr)
+{
+	if (!bp || !mn || !mx) return B3B200_ERR_INVALID;
+	return bp->createProxy(mn, mx, userPtr, false);
+}
+extern "C" int b3b200_bp_create_large_proxy(b3b200_broadphase* bp, const float* mn, const float* mx, int userPtr)
+{
+	if (!bp || !mn || !mx) return B3B200_ERR_INVALID;
+	return bp->createProxy(mn, mx, userPtr, true);
+}
+extern "C" int b3b200_bp_write_aabbs(b3b200_broadphase* bp)
+{
+	if (!bp) return B3B200_ERR_INVALID;
+	return bp->writeAabbs();
+}
+extern "C" int b3b200_bp_set_aabbs(b3b200_broadphase* bp, const b3b200_aabb* a, int n)
+{
+	if (!bp || !a || n != (int)bp->aabbsCPU.size()) return B3B200_ERR_INVALID;
+	for (int i = 0; i < n; i++) bp->aabbsCPU[i] = a[i];
+	if (n != bp->numAabbs) return bp->writeAabbs();
+	B3_CUDA_CHECK(cudaSetDevice(bp->device));
+	B3_CUDA_CHECK(cudaMemcpyAsync(bp->aabbs.ptr, a, sizeof(b3b200_aabb) * n, cudaMemcpyHostToDevice, bp->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(bp->stream));
+	return 0;
+}
+extern "C" int b3b200_bp_calculate_pairs(b3b200_broadphase* bp, int maxPairs)
+{
+	if (!bp) return B3B200_ERR_INVALID;
+	B3_CUDA_CHECK(cudaSetDevice(bp->device));
+	if (bp->numAabbs != (int)bp->aabbsCPU.size()) B3_TRY(bp->writeAabbs());
+	B3_CUDA_CHECK(cudaEventRecord(bp->ev0, bp->stream));
+	B3_TRY(bp->calculatePairs(maxPairs));
+	B3_CUDA_CHECK(cudaEventRecord(bp->ev1, bp->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(bp->stream));
+	cudaEventElapsedTime(&bp->lastMs, bp->ev0, bp->ev1);
+	return 0;
+}
+extern "C" int b3b200_bp_num_overlap(b3b200_broadphase* bp)
+{
+	if (!bp) return B3B200_ERR_INVALID;
+	unsigned int n = 0;
+	B3_CUDA_CHECK(cudaSetDevice(bp->device));
+	B3_CUDA_CHECK(cudaMemcpyAsync(&n, &bp->ctr[CTR_PAIRS], sizeof(n), cudaMemcpyDeviceToHost, bp->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(bp->stream));
+	return (int)n;
+}
+extern "C" int b3b200_bp_get_pairs(b3b200_broadphase* bp, b3b200_int4* dst, int capacity, int* numPairs)
+{
+	if (!bp || !numPairs || capacity < 0) return B3B200_ERR_INVALID;
+	int n = b3b200_bp_num_overlap(bp);
+	if (n < 0) return n;
+	*numPairs = n;
+	int m = n < capacity ? n : capacity;
+	if (m > 0 && dst)
+	{
+		B3_CUDA_CHECK(cudaMemcpyAsync(dst, bp->pairs.ptr, sizeof(b3b200_int4) * m, cudaMemcpyDeviceToHost, bp->stream));
+		B3_CUDA_CHECK(cudaStreamSynchronize(bp->stream));
+	}
+	return 0;
+}
+extern "C" int b3b200_bp_device_pairs(b3b200_broadphase* bp, void** p)
+{
+	if (!bp || !p) return B3B200_ERR_INVALID;
+	*p = bp->pairs.ptr;
+	return 0;
+}
+extern "C" int b3b200_bp_device_aabbs(b3b200_broadphase* bp, void** p)
+{
+	if (!bp || !p) return B3B200_ERR_INVALID;
+	*p = bp->aabbs.ptr;
+	return 0;
+}
+extern "C" int b3b200_bp_last_ms(b3b200_broadphase* bp, float* ms)
+{
+	if (!bp || !ms) return B3B200_ERR_INVALID;
+	*ms = bp->lastMs;
+	return 0;
+}

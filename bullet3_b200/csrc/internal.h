@@ -1,0 +1,182 @@
+// internal.h -- host-side state behind the C ABI handles.
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "primitives.cuh"
+#include "hull.h"
+
+namespace b3b200
+{
+// device-side counters shared by the stages of one step
+enum Counter
+{
+	CTR_PAIRS = 0,
+	CTR_CONTACTS = 1,
+	CTR_BATCHES = 2,
+	CTR_COLOUR_ROUNDS = 3,
+	CTR_OVERFLOW = 4,
+	CTR_COMPOUND_PAIRS = 5,
+	CTR_CONCAVE_PAIRS = 6,
+	CTR_UNCOLOURED = 7,
+	CTR_COUNT = 16
+};
+enum OverflowBits
+{
+	OVF_PAIRS = 1,
+	OVF_CONTACTS = 2,
+	OVF_BATCHES = 4,
+	OVF_COMPOUND = 8,
+	OVF_CONCAVE = 16
+};
+
+// ------------------------------------------------------------------ broadphase
+// Owns the world-space AABB array (creation order, min.w = user handle) and the
+// pair buffer, like b3GpuSapBroadphase / b3GpuGridBroadphase
+// (b3GpuSapBroadphase.h:14-141, b3GpuGridBroadphase.h:7-78).
+struct Broadphase
+{
+	int kind = B3B200_BP_GRID;
+	int device = 0;
+	cudaStream_t stream = 0;
+	bool ownStream = false;
+	int maxProxies = 0;
+	int maxPairs = 0;
+
+	std::vector<b3b200_aabb> aabbsCPU;  // all proxies, creation order
+	std::vector<int> smallIdx, largeIdx;  // indices into aabbsCPU
+
+	DevBuf<b3b200_aabb> aabbs;
+	DevBuf<int> smallMap, largeMap;
+	int numSmall = 0, numLarge = 0, numAabbs = 0;
+
+	DevBuf<b3b200_int4> pairs;
+	DevBuf<unsigned int> counters;  // CTR_COUNT (own copy when stand-alone; world shares its own)
+	unsigned int* ctr = nullptr;    // -> counters actually used
+
+	// scratch
+	DevBuf<unsigned int> keys, vals;
+	DevBuf<b3b200_aabb> sortedAabbs;
+	DevBuf<int> cellStart;         // 128^3
+	DevBuf<float> scalars;         // [0]=maxExtent bits/cellSize ... see broadphase.cu
+	RadixSortTemp sortTmp;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	float lastMs = 0.f;
+
+	int init(int kind, int device, cudaStream_t stream, int maxProxies, int maxPairs);
+	void destroy();
+	int createProxy(const float* mn, const float* mx, int userPtr, bool large);
+	int writeAabbs();           // host -> device, (re)allocates scratch
+	int calculatePairs(int maxPairsNow);  // async on stream
+	int reset();
+};
+
+// ------------------------------------------------------------------ world
+struct World
+{
+	b3b200_config cfg;
+	int device = 0;
+	cudaStream_t stream = 0;
+	bool ownStream = false;
+	bool uploaded = false;
+	bool aabbsValid = false;  // world AABBs on device match the current poses
+
+	// settings
+	float gravity[3] = {0.f, -9.8f, 0.f};  // b3GpuRigidBodyPipeline.cpp:92
+	float angularDamping = 0.99f;          // b3GpuRigidBodyPipeline.cpp:469
+	int solverKind = B3B200_SOLVER_PGS;
+	int solverIterations = 4;  // b3GpuPgsContactSolver.cpp:1049
+	float clipMinDist = -1e30f, clipMaxDist = 0.02f;  // satClipHullContacts.cl:916-917
+	int static0Index = -1;     // b3GpuNarrowPhase.cpp:861-864
+
+	// host-side shape tables (b3GpuNarrowPhaseInternalData.h:24-86)
+	std::vector<b3b200_collidable> collidables;
+	std::vector<b3b200_aabb> localAabbs;  // per collidable
+	std::vector<b3b200_convex_polyhedron> convex;
+	std::vector<b3b200_float4> vertices, uniqueEdges;
+	std::vector<b3b200_face> faces;
+	std::vector<int> indices;
+	std::vector<b3b200_child_shape> childShapes;
+	std::vector<b3b200_bvh_info> bvhInfos;
+	std::vector<b3b200_bvh_node> bvhNodes;
+	std::vector<b3b200_bvh_subtree> bvhSubtrees;
+	// host-side bodies
+	std::vector<b3b200_rigid_body> bodies;
+	std::vector<b3b200_inertia> inertias;
+
+	// device shape tables
+	DevBuf<b3b200_collidable> dCollidables;
+	DevBuf<b3b200_aabb> dLocalAabbs;
+	DevBuf<b3b200_convex_polyhedron> dConvex;
+	DevBuf<float4> dVertices, dUniqueEdges;
+	DevBuf<b3b200_face> dFaces;
+	DevBuf<int> dIndices;
+	DevBuf<b3b200_child_shape> dChildShapes;
+	DevBuf<b3b200_bvh_info> dBvhInfos;
+	DevBuf<b3b200_bvh_node> dBvhNodes;
+	DevBuf<b3b200_bvh_subtree> dBvhSubtrees;
+
+	// device body state.  AoS (reference layout) is the boundary format; the
+	// step runs on the SoA split below: pose = {pos.xyz, invMass | quat} and
+	// vel = {linVel | angVel}, one 32-byte sector each.
+	int numBodies = 0;
+	DevBuf<b3b200_rigid_body> dBodiesAoS;
+	DevBuf<b3b200_inertia> dInertias;
+	DevBuf<float4> dPose;  // 2 float4 per body
+	DevBuf<float4> dVel;   // 2 float4 per body
+	DevBuf<int> dCollidableIdx;
+	bool soaDirty = false;  // SoA is newer than AoS
+
+	Broadphase bp;
+
+	// narrowphase output
+	DevBuf<b3b200_contact4> dContacts;
+	DevBuf<unsigned int> dCounters;  // CTR_COUNT
+	DevBuf<b3b200_int4> dCompoundPairs;
+	DevBuf<b3b200_int4> dConcavePairs;
+
+	// solver
+	DevBuf<b3b200_constraint4> dConstraints;
+	DevBuf<unsigned long long> dBodyMask;  // colours used per body (2 words / body)
+	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body
+	DevBuf<int> dContactColour;           // colour per contact, -1 = none yet
+	DevBuf<unsigned int> dBatchCount;     // per colour (B3_MAX_BATCHES+1)
+	DevBuf<unsigned int> dBatchOffset;    // exclusive scan
+	DevBuf<unsigned int> dBatchCursor;
+	DevBuf<unsigned int> dGridBarrier;    // software grid barrier state
+	// jacobi
+	DevBuf<unsigned int> dBodyCount, dBodyOffset;
+	DevBuf<float4> dDeltaLin, dDeltaAng;
+	DevBuf<unsigned int> dContactSlot;  // 2 per contact
+
+	int smCount = 148;
+	int coopBlocksPerSm = 1;
+
+	// timing
+	bool timing = false;
+	cudaEvent_t ev[8] = {nullptr};
+	float stageMs[8] = {0.f};
+
+	int init(const b3b200_config* cfg, int device, cudaStream_t stream);
+	void destroy();
+};
+
+constexpr int MAX_BATCHES = 128;  // B3_MAX_NUM_BATCHES (b3Solver.h:33-41)
+
+// stage launchers (each async on w->stream)
+int launchPackSoA(World* w);    // AoS -> SoA
+int launchUnpackSoA(World* w);  // SoA -> AoS
+int launchUpdateAabbs(World* w);
+int launchIntegrate(World* w, float dt, bool alsoAabbs);
+int launchNarrowphase(World* w);
+int launchSolverSetup(World* w);
+int launchSolverIterate(World* w);
+int launchJacobi(World* w);
+
+}  // namespace b3b200
+
+struct b3b200_world : b3b200::World
+{
+};
+struct b3b200_broadphase : b3b200::Broadphase
+{
+};

@@ -1,0 +1,540 @@
+// narrowphase.cu -- contact generation, one warp per overlapping pair.
+//
+// Replaces b3GpuNarrowPhase::computeContacts -> GpuSatCollision::
+// computeConvexConvexContactsGPUSAT (b3GpuNarrowPhase.cpp:751-809,
+// b3ConvexHullContact.cpp:2558-4408: ~12 kernels + 7..15 host round trips per
+// step) with ONE persistent kernel and no host synchronisation.
+//
+// The arithmetic follows the reference's shared CPU headers operation by
+// operation (the oracle the parity tests use):
+//   SAT        b3FindSeparatingAxis / b3TestSepAxis / b3ProjectAxis
+//              (shared/b3FindSeparatingAxis.h:4-195)
+//   clipping   b3ClipHullAgainstHull / b3ClipFaceAgainstHull / b3ClipFace
+//              (shared/b3ContactConvexConvexSAT.h:20-266)
+//   reduction  b3ReduceContacts (shared/b3ReduceContacts.h:4-87)
+// but the work is laid out for a 32-wide warp: lanes own separating-axis
+// candidates (face normals of A, of B, edge x edge), the arg-min over axes is a
+// shuffle reduction that breaks ties towards the lower axis index (== the
+// reference's "first strict minimum" in sequential order), Sutherland-Hodgman
+// clipping runs one polygon edge per lane with ballot-compacted output in
+// shared memory, and the manifold reduction is four more shuffle arg-mins.
+#include "internal.h"
+
+namespace b3b200
+{
+constexpr int NP_THREADS = 128;
+constexpr int NP_WARPS = NP_THREADS / 32;
+constexpr int MAX_POLY = 64;  // b3Config::m_maxVerticesPerFace (b3Config.h:27)
+#define FULL 0xffffffffu
+
+struct HullRef
+{
+	float4 localCenter;
+	int faceOffset, numFaces, numVertices, vertexOffset, uniqueEdgesOffset, numUniqueEdges;
+};
+
+B3_D HullRef loadHull(const b3b200_convex_polyhedron* __restrict__ convex, int shapeIndex)
+{
+	const b3b200_convex_polyhedron* h = &convex[shapeIndex];
+	HullRef r;
+	r.localCenter = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
+	const int4* t = reinterpret_cast<const int4*>(&h->radius);  // radius, faceOffset, numFaces, numVertices
+	int4 a = __ldg(t), b = __ldg(t + 1);                         // vertexOffset, uniqueEdgesOffset, numUniqueEdges, unused
+	r.faceOffset = a.y;
+	r.numFaces = a.z;
+	r.numVertices = a.w;
+	r.vertexOffset = b.x;
+	r.uniqueEdgesOffset = b.y;
+	r.numUniqueEdges = b.z;
+	return r;
+}
+
+// b3ProjectAxis (shared/b3FindSeparatingAxis.h:4-34)
+B3_D void projectAxis(const HullRef& hull, const float4& pos, const float4& orn, const float4& dir, const float4* __restrict__ vertices, float& mn, float& mx)
+{
+	mn = FLT_MAX;
+	mx = -FLT_MAX;
+	const float4 localDir = quatRotate(quatInverse(orn), dir);
+	const float offset = dot3(pos, dir);
+	const float4* v = vertices + hull.vertexOffset;
+	for (int i = 0; i < hull.numVertices; i++)
+	{
+		float dp = dot3(__ldg(&v[i]), localDir);
+		if (dp < mn) mn = dp;
+		if (dp > mx) mx = dp;
+	}
+	if (mn > mx)
+	{
+		float t = mn;
+		mn = mx;
+		mx = t;
+	}
+	mn += offset;
+	mx += offset;
+}
+
+// b3TestSepAxis (shared/b3FindSeparatingAxis.h:36-55)
+B3_D bool testSepAxis(const HullRef& hA, const HullRef& hB, const float4& posA, const float4& ornA, const float4& posB, const float4& ornB,
+					  const float4& axis, const float4* __restrict__ vertices, float& depth)
+{
+	float min0, max0, min1, max1;
+	projectAxis(hA, posA, ornA, axis, vertices, min0, max0);
+	projectAxis(hB, posB, ornB, axis, vertices, min1, max1);
+	if (max0 < min1 || max1 < min0) return false;
+	float d0 = max0 - min1;
+	float d1 = max1 - min0;
+	depth = d0 < d1 ? d0 : d1;
+	return true;
+}
+
+// lexicographic (value, index) arg-min across the warp; index < 0 = "no candidate"
+B3_D void warpArgMin(float& d, int& k)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		float od = __shfl_xor_sync(FULL, d, o);
+		int ok = __shfl_xor_sync(FULL, k, o);
+		if (ok >= 0 && (k < 0 || od < d || (od == d && ok < k)))
+		{
+			d = od;
+			k = ok;
+		}
+	}
+}
+B3_D void warpArgMax(float& d, int& k)
+{
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		float od = __shfl_xor_sync(FULL, d, o);
+		int ok = __shfl_xor_sync(FULL, k, o);
+		if (ok >= 0 && (k < 0 || od > d || (od == d && ok < k)))
+		{
+			d = od;
+			k = ok;
+		}
+	}
+}
+
+B3_D bool almostZero(const float4& v)
+{
+	// b3IsAlmostZero (shared/b3Float4.h:58-63); x > 1e-6 (double) <=> x > 1e-6f for float x
+	return !(fabsf(v.x) > 1e-6f || fabsf(v.y) > 1e-6f || fabsf(v.z) > 1e-6f);
+}
+
+B3_D float4 lerp3(const float4& a, const float4& b, float t)
+{
+	return mk4(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t, 0.f);
+}
+
+// One Sutherland-Hodgman pass (b3ClipFace, shared/b3ContactConvexConvexSAT.h:20-68),
+// one polygon edge per lane, outputs compacted in order.  Returns the new vertex count.
+B3_D int clipFaceWarp(const float4* in, int numIn, const float4& n, float eq, float4* out, int lane)
+{
+	if (numIn < 2) return 0;
+	int numOut = 0;
+	for (int base = 0; base < numIn; base += 32)
+	{
+		int ve = base + lane;
+		int c = 0;
+		float4 o0 = mk4(0, 0, 0), o1 = mk4(0, 0, 0);
+		if (ve < numIn)
+		{
+			float4 first = in[ve == 0 ? numIn - 1 : ve - 1];
+			float4 end = in[ve];
+			float ds = dot3(n, first) + eq;
+			float de = dot3(n, end) + eq;
+			if (ds < 0)
+			{
+				if (de < 0)
+					o0 = end;
+				else
+					o0 = lerp3(first, end, (ds * 1.f / (ds - de)));
+				c = 1;
+			}
+			else if (de < 0)
+			{
+				o0 = lerp3(first, end, (ds * 1.f / (ds - de)));
+				o1 = end;
+				c = 2;
+			}
+		}
+		unsigned int m1 = __ballot_sync(FULL, c >= 1);
+		unsigned int m2 = __ballot_sync(FULL, c == 2);
+		unsigned int lt = (1u << lane) - 1u;
+		int pos = numOut + __popc(m1 & lt) + __popc(m2 & lt);
+		if (c >= 1 && pos < MAX_POLY) out[pos] = o0;
+		if (c == 2 && pos + 1 < MAX_POLY) out[pos + 1] = o1;
+		numOut += __popc(m1) + __popc(m2);
+	}
+	__syncwarp();
+	return numOut < MAX_POLY ? numOut : MAX_POLY;
+}
+
+struct NpArgs
+{
+	const b3b200_int4* pairs;
+	b3b200_int4* pairsOut;
+	unsigned int* ctr;
+	const float4* pose;
+	const int* coll;
+	const b3b200_collidable* collidables;
+	const b3b200_convex_polyhedron* convex;
+	const float4* vertices;
+	const float4* uniqueEdges;
+	const b3b200_face* faces;
+	const int* indices;
+	b3b200_contact4* contacts;
+	int maxContacts;
+	float clipMin, clipMax;
+};
+
+// convex hull vs convex hull: b3ContactConvexConvexSAT (shared/b3ContactConvexConvexSAT.h:407-484)
+B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int shapeA, int shapeB, int childA, int childB,
+						   float4 posA, float4 ornA, float4 posB, float4 ornB, float invMassA, float invMassB,
+						   float4* bufA, float4* bufB, int lane)
+{
+	posA.w = 0.f;
+	posB.w = 0.f;
+	const HullRef hA = loadHull(a.convex, shapeA);
+	const HullRef hB = loadHull(a.convex, shapeB);
+
+	// ---- b3FindSeparatingAxis
+	const float4 c0 = transformPoint(hA.localCenter, posA, ornA);
+	const float4 c1 = transformPoint(hB.localCenter, posB, ornB);
+	const float4 deltaC2 = sub3(c0, c1);
+
+	const int nFA = hA.numFaces, nFB = hB.numFaces, nEA = hA.numUniqueEdges, nEB = hB.numUniqueEdges;
+	const int total = nFA + nFB + nEA * nEB;
+	float bestD = FLT_MAX;
+	int bestK = -1;
+	float4 bestAxis = mk4(0, 0, 0);
+	bool separated = false;
+	for (int k = lane; k < total && !separated; k += 32)
+	{
+		float4 axis;
+		if (k < nFA + nFB)
+		{
+			const bool onA = k < nFA;
+			const b3b200_face* f = onA ? &a.faces[hA.faceOffset + k] : &a.faces[hB.faceOffset + (k - nFA)];
+			float4 normal = __ldg(reinterpret_cast<const float4*>(&f->plane));
+			axis = quatRotate(onA ? ornA : ornB, normal);
+			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+		}
+		else
+		{
+			int e = k - nFA - nFB;
+			int e0 = e / nEB, e1 = e - e0 * nEB;
+			float4 edge0 = quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
+			float4 edge1 = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+			float4 cr = cross3(edge0, edge1);
+			if (almostZero(cr)) continue;
+			axis = normalized3(cr);
+			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+		}
+		float d;
+		if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d))
+		{
+			separated = true;
+			break;
+		}
+		if (d < bestD)
+		{
+			bestD = d;
+			bestK = k;
+			bestAxis = axis;
+		}
+	}
+	if (__any_sync(FULL, separated)) return;
+	const int myK = bestK;
+	warpArgMin(bestD, bestK);
+	if (bestK < 0) return;
+	const int src = __ffs(__ballot_sync(FULL, myK == bestK)) - 1;
+	float4 sep = mk4(__shfl_sync(FULL, bestAxis.x, src), __shfl_sync(FULL, bestAxis.y, src), __shfl_sync(FULL, bestAxis.z, src));
+	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
+
+	// ---- b3ClipHullAgainstHull: incident face of B = most aligned with sep
+	int closestFaceB = -1;
+	{
+		float dmax = -FLT_MAX;
+		for (int f = lane; f < nFB; f += 32)
+		{
+			float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+			float d = dot3(quatRotate(ornB, normal), sep);
+			if (d > dmax)
+			{
+				dmax = d;
+				closestFaceB = f;
+			}
+		}
+		warpArgMax(dmax, closestFaceB);
+	}
+	if (closestFaceB < 0) return;
+	int numVertsIn;
+	{
+		const b3b200_face* polyB = &a.faces[hB.faceOffset + closestFaceB];
+		const int idxOff = __ldg(&polyB->indexOffset);
+		numVertsIn = __ldg(&polyB->numIndices);
+		if (numVertsIn > MAX_POLY) numVertsIn = MAX_POLY;
+		for (int e = lane; e < numVertsIn; e += 32)
+		{
+			float4 b = __ldg(&a.vertices[hB.vertexOffset + __ldg(&a.indices[idxOff + e])]);
+			bufA[e] = transformPoint(b, posB, ornB);
+		}
+		__syncwarp();
+	}
+
+	// ---- b3ClipFaceAgainstHull: reference face of A = least aligned with sep
+	int closestFaceA = -1;
+	{
+		float dmin = FLT_MAX;
+		for (int f = lane; f < nFA; f += 32)
+		{
+			float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
+			float d = dot3(quatRotate(ornA, mk4(normal.x, normal.y, normal.z)), sep);
+			if (d < dmin)
+			{
+				dmin = d;
+				closestFaceA = f;
+			}
+		}
+		warpArgMin(dmin, closestFaceA);
+	}
+	if (closestFaceA < 0) return;
+
+	const b3b200_face* polyA = &a.faces[hA.faceOffset + closestFaceA];
+	const float4 planeA = __ldg(reinterpret_cast<const float4*>(&polyA->plane));
+	const int idxOffA = __ldg(&polyA->indexOffset);
+	const int numVerticesA = __ldg(&polyA->numIndices);
+	const float4 planeNormalA = mk4(planeA.x, planeA.y, planeA.z);
+	const float4 worldPlaneAnormal1 = quatRotate(ornA, planeNormalA);
+
+	float4* pIn = bufA;
+	float4* pOut = bufB;
+	for (int e0 = 0; e0 < numVerticesA; e0++)
+	{
+		const float4 va = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + e0])]);
+		const float4 vb = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + ((e0 + 1) % numVerticesA)])]);
+		const float4 edge0 = sub3(va, vb);
+		const float4 worldEdge0 = quatRotate(ornA, edge0);
+		const float4 planeNormalWS = neg3(cross3(worldEdge0, worldPlaneAnormal1));
+		const float4 worldA1 = transformPoint(va, posA, ornA);
+		const float planeEqWS = -dot3(worldA1, planeNormalWS);
+		int numOut = clipFaceWarp(pIn, numVertsIn, planeNormalWS, planeEqWS, pOut, lane);
+		float4* t = pOut;
+		pOut = pIn;
+		pIn = t;
+		numVertsIn = numOut;
+	}
+
+	// ---- keep points behind the witness face (b3ContactConvexConvexSAT.h:143-173)
+	int numContactsOut = 0;
+	{
+		const float4 planeNormalWS = worldPlaneAnormal1;
+		const float planeEqWS = planeA.w - dot3(planeNormalWS, posA);
+		for (int base = 0; base < numVertsIn; base += 32)
+		{
+			int i = base + lane;
+			bool keep = false;
+			float4 pt = mk4(0, 0, 0);
+			if (i < numVertsIn)
+			{
+				pt = pIn[i];
+				float depth = dot3(planeNormalWS, pt) + planeEqWS;
+				if (depth <= a.clipMin) depth = a.clipMin;
+				if (depth <= a.clipMax)
+				{
+					keep = true;
+					pt.w = depth;
+				}
+			}
+			unsigned int m = __ballot_sync(FULL, keep);
+			if (keep) pOut[numContactsOut + __popc(m & ((1u << lane) - 1u))] = pt;
+			numContactsOut += __popc(m);
+		}
+		__syncwarp();
+	}
+	if (numContactsOut <= 0) return;
+	const float4* pts = pOut;
+
+	// ---- b3ReduceContacts (shared/b3ReduceContacts.h:4-87)
+	int idx0 = 0, idx1 = 1, idx2 = 2, idx3 = 3;
+	int numPoints = numContactsOut;
+	if (numContactsOut > 4)
+	{
+		int nPoints = numContactsOut > 64 ? 64 : numContactsOut;
+		float4 center = mk4(0, 0, 0);
+		for (int i = 0; i < nPoints; i++)
+		{
+			float4 p = pts[i];
+			center.x += p.x;
+			center.y += p.y;
+			center.z += p.z;
+		}
+		{
+			float s = 1.0f / (float)nPoints;
+			center.x *= s;
+			center.y *= s;
+			center.z *= s;
+		}
+		float4 aVector = sub3(pts[0], center);
+		float4 u = cross3(sep, aVector);
+		float4 v = cross3(sep, u);
+		u = normalized3(u);
+		v = normalized3(v);
+		const float4 nu = neg3(u), nv = neg3(v);
+		float minW = FLT_MAX;
+		int minIndex = -1;
+		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
+		int i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+		for (int ie = lane; ie < nPoints; ie += 32)
+		{
+			float4 p = pts[ie];
+			if (p.w < minW)
+			{
+				minW = p.w;
+				minIndex = ie;
+			}
+			float4 r = sub3(p, center);
+			float f = dot3(u, r);
+			if (f < m0)
+			{
+				m0 = f;
+				i0 = ie;
+			}
+			f = dot3(nu, r);
+			if (f < m1)
+			{
+				m1 = f;
+				i1 = ie;
+			}
+			f = dot3(v, r);
+			if (f < m2)
+			{
+				m2 = f;
+				i2 = ie;
+			}
+			f = dot3(nv, r);
+			if (f < m3)
+			{
+				m3 = f;
+				i3 = ie;
+			}
+		}
+		warpArgMin(minW, minIndex);
+		warpArgMin(m0, i0);
+		warpArgMin(m1, i1);
+		warpArgMin(m2, i2);
+		warpArgMin(m3, i3);
+		if (i0 >= 0) idx0 = i0;
+		if (i1 >= 0) idx1 = i1;
+		if (i2 >= 0) idx2 = i2;
+		if (i3 >= 0) idx3 = i3;
+		if (idx0 != minIndex && idx1 != minIndex && idx2 != minIndex && idx3 != minIndex) idx0 = minIndex;
+		numPoints = 4;
+	}
+
+	// ---- append (b3ClipHullHullSingle, shared/b3ContactConvexConvexSAT.h:364-397)
+	unsigned int slot = 0;
+	if (lane == 0) slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	slot = __shfl_sync(FULL, slot, 0);
+	if (slot >= (unsigned int)a.maxContacts) return;  // clamped afterwards, OVF_CONTACTS raised
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	if (lane < 4)
+	{
+		int id = lane == 0 ? idx0 : (lane == 1 ? idx1 : (lane == 2 ? idx2 : idx3));
+		float4 p = lane < numPoints ? pts[id] : mk4(0, 0, 0, 0);
+		cw[lane] = p;
+	}
+	else if (lane == 4)
+	{
+		cw[4] = mk4(sep.x, sep.y, sep.z, (float)numPoints);
+	}
+	else if (lane == 5)
+	{
+		int4 t;
+		t.x = (int)(0u | (45874u << 16));  // restitutionCmp = 0, frictionCmp = 45874
+		t.y = 0;                            // batchIdx
+		t.z = invMassA == 0.f ? -bodyA : bodyA;
+		t.w = invMassB == 0.f ? -bodyB : bodyB;
+		reinterpret_cast<int4*>(c)[5] = t;
+	}
+	else if (lane == 6)
+	{
+		int4 t;
+		t.x = childA;
+		t.y = childB;
+		t.z = 0;
+		t.w = 0;
+		reinterpret_cast<int4*>(c)[6] = t;
+	}
+	if (lane == 0 && pairIndex >= 0) a.pairsOut[pairIndex].z = (int)slot;
+}
+
+__global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a)
+{
+	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	float4* bufA = bufAll[warp][0];
+	float4* bufB = bufAll[warp][1];
+	const int numPairs = (int)a.ctr[CTR_PAIRS];
+	const int warpsTotal = gridDim.x * NP_WARPS;
+	for (int p = blockIdx.x * NP_WARPS + warp; p < numPairs; p += warpsTotal)
+	{
+		const int bodyA = a.pairs[p].x;
+		const int bodyB = a.pairs[p].y;
+		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+		if (cA < 0 || cB < 0) continue;
+		const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
+		if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
+		{
+			float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
+			float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
+			convexConvexWarp(a, p, bodyA, bodyB, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), -1, -1,
+							 posA, ornA, posB, ornB, posA.w, posB.w, bufA, bufB, lane);
+		}
+		__syncwarp();
+	}
+}
+
+__global__ void clampContactsKernel(unsigned int* ctr, int maxContacts)
+{
+	if (ctr[CTR_CONTACTS] > (unsigned int)maxContacts)
+	{
+		ctr[CTR_CONTACTS] = (unsigned int)maxContacts;
+		ctr[CTR_OVERFLOW] |= OVF_CONTACTS;
+	}
+}
+
+int launchNarrowphase(World* w)
+{
+	cudaStream_t s = w->stream;
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
+	NpArgs a;
+	a.pairs = w->bp.pairs.ptr;
+	a.pairsOut = w->bp.pairs.ptr;
+	a.ctr = w->dCounters.ptr;
+	a.pose = w->dPose.ptr;
+	a.coll = w->dCollidableIdx.ptr;
+	a.collidables = w->dCollidables.ptr;
+	a.convex = w->dConvex.ptr;
+	a.vertices = w->dVertices.ptr;
+	a.uniqueEdges = w->dUniqueEdges.ptr;
+	a.faces = w->dFaces.ptr;
+	a.indices = w->dIndices.ptr;
+	a.contacts = w->dContacts.ptr;
+	a.maxContacts = w->cfg.maxContactCapacity;
+	a.clipMin = w->clipMinDist;
+	a.clipMax = w->clipMaxDist;
+	int blocks = w->smCount * 8;
+	narrowphaseKernel<<<blocks, NP_THREADS, 0, s>>>(a);
+	B3_LAUNCH_CHECK();
+	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity);
+	B3_LAUNCH_CHECK();
+	return 0;
+}
+
+}  // namespace b3b200

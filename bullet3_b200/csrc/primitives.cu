@@ -1,0 +1,351 @@
+// primitives.cu -- radix sort / scan / bound search / fill for sm_100a.
+//
+// Radix sort: LSD, 8-bit digits.  Per pass: (1) per-tile digit histogram,
+// (2) one exclusive scan over the digit-major [256][numTiles] table,
+// (3) stable scatter.  Ranking inside a tile is done with __match_any_sync:
+// every warp owns 8 rounds of 32 consecutive keys, peers with the same digit
+// rank themselves with a popc of the lower-lane mask -- no shared-memory
+// atomics, no bank-conflicted counters, and the order (warp, round, lane) is
+// exactly input order, so the sort is stable like b3RadixSort32CL
+// (b3RadixSort32CL.cpp:12-646; its executeHost twin :587-646 is the oracle).
+#include "primitives.cuh"
+
+namespace b3b200
+{
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // 2048 keys per CTA
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rsHistKernel(const KeyT* __restrict__ keys, int n, int shift,
+														   unsigned int* __restrict__ blockHist, int numBlocks)
+{
+	__shared__ unsigned int hist[256];
+	hist[threadIdx.x] = 0;
+	__syncthreads();
+	int base = blockIdx.x * RS_TILE;
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++)
+	{
+		int i = base + r * RS_THREADS + threadIdx.x;
+		if (i < n)
+		{
+			unsigned int d = (unsigned int)(keys[i] >> shift) & 255u;
+			atomicAdd(&hist[d], 1u);
+		}
+	}
+	__syncthreads();
+	blockHist[threadIdx.x * numBlocks + blockIdx.x] = hist[threadIdx.x];
+}
+
+template <typename KeyT, bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS) rsScatterKernel(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
+															  KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut,
+															  int n, int shift, const unsigned int* __restrict__ blockOffsets, int numBlocks)
+{
+	__shared__ unsigned int whist[RS_WARPS][257];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	for (int i = threadIdx.x; i < RS_WARPS * 257; i += RS_THREADS) (&whist[0][0])[i] = 0;
+	__syncthreads();
+
+	const int warpBase = blockIdx.x * RS_TILE + warp * (32 * RS_ITEMS);
+	KeyT key[RS_ITEMS];
+	unsigned int val[RS_ITEMS];
+	unsigned int rank[RS_ITEMS];
+	unsigned int dig[RS_ITEMS];
+	const unsigned int ltMask = (1u << lane) - 1u;
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++)
+	{
+		int i = warpBase + r * 32 + lane;
+		bool valid = i < n;
+		key[r] = valid ? keysIn[i] : (KeyT)0;
+		if (HAS_VALS) val[r] = valid ? valsIn[i] : 0u;
+		dig[r] = valid ? ((unsigned int)(key[r] >> shift) & 255u) : 256u;
+	}
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++)
+	{
+		unsigned int d = dig[r];
+		unsigned int peers = __match_any_sync(0xffffffffu, d);
+		unsigned int before = whist[warp][d];
+		__syncwarp();
+		if ((peers & ltMask) == 0) whist[warp][d] = before + __popc(peers);
+		__syncwarp();
+		rank[r] = before + __popc(peers & ltMask);
+	}
+	__syncthreads();
+	{
+		// thread d turns the per-warp counts of digit d into global write cursors
+		int d = threadIdx.x;
+		unsigned int run = blockOffsets[d * numBlocks + blockIdx.x];
+#pragma unroll
+		for (int w = 0; w < RS_WARPS; w++)
+		{
+			unsigned int t = whist[w][d];
+			whist[w][d] = run;
+			run += t;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < RS_ITEMS; r++)
+	{
+		if (dig[r] < 256u)
+		{
+			unsigned int pos = whist[warp][dig[r]] + rank[r];
+			keysOut[pos] = key[r];
+			if (HAS_VALS) valsOut[pos] = val[r];
+		}
+	}
+}
+
+// single-CTA exclusive scan (tables here are small: 256 x numTiles)
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) scanKernel(const unsigned int* src, unsigned int* dst, int n, unsigned int* total)
+{
+	__shared__ unsigned int warpSums[32];
+	__shared__ unsigned int carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int base = 0; base < n; base += SCAN_THREADS * 4)
+	{
+		int i = base + threadIdx.x * 4;
+		unsigned int v0 = i < n ? src[i] : 0, v1 = i + 1 < n ? src[i + 1] : 0, v2 = i + 2 < n ? src[i + 2] : 0, v3 = i + 3 < n ? src[i + 3] : 0;
+		unsigned int sum = v0 + v1 + v2 + v3;
+		unsigned int incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) warpSums[warp] = incl;
+		__syncthreads();
+		if (warp == 0)
+		{
+			unsigned int w = warpSums[lane];
+			unsigned int wi = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+				if (lane >= o) wi += t;
+			}
+			warpSums[lane] = wi - w;  // exclusive
+		}
+		__syncthreads();
+		unsigned int excl = carry + warpSums[warp] + (incl - sum);
+		if (i < n) dst[i] = excl;
+		if (i + 1 < n) dst[i + 1] = excl + v0;
+		if (i + 2 < n) dst[i + 2] = excl + v0 + v1;
+		if (i + 3 < n) dst[i + 3] = excl + v0 + v1 + v2;
+		__syncthreads();
+		if (threadIdx.x == SCAN_THREADS - 1) carry = excl + sum;
+		__syncthreads();
+	}
+	if (total && threadIdx.x == 0) *total = carry;
+}
+
+int exclusiveScanU32(cudaStream_t s, const unsigned int* src, unsigned int* dst, int n, unsigned int* totalDevice)
+{
+	scanKernel<<<1, SCAN_THREADS, 0, s>>>(src, dst, n, totalDevice);
+	B3_LAUNCH_CHECK();
+	return 0;
+}
+
+template <typename KeyT, bool HAS_VALS>
+static int radixSortImpl(cudaStream_t s, RadixSortTemp& tmp, KeyT* keys, KeyT* keysAlt, unsigned int* vals, unsigned int* valsAlt, int n, int numBits)
+{
+	if (n <= 1) return 0;
+	int numBlocks = divUp(n, RS_TILE);
+	B3_TRY(tmp.blockHist.reserve((size_t)256 * numBlocks));
+	int passes = (numBits + 7) / 8;
+	KeyT* kin = keys;
+	KeyT* kout = keysAlt;
+	unsigned int* vin = vals;
+	unsigned int* vout = valsAlt;
+	for (int p = 0; p < passes; p++)
+	{
+		int shift = p * 8;
+		rsHistKernel<KeyT><<<numBlocks, RS_THREADS, 0, s>>>(kin, n, shift, tmp.blockHist.ptr, numBlocks);
+		B3_LAUNCH_CHECK();
+		scanKernel<<<1, SCAN_THREADS, 0, s>>>(tmp.blockHist.ptr, tmp.blockHist.ptr, 256 * numBlocks, nullptr);
+		B3_LAUNCH_CHECK();
+		rsScatterKernel<KeyT, HAS_VALS><<<numBlocks, RS_THREADS, 0, s>>>(kin, vin, kout, vout, n, shift, tmp.blockHist.ptr, numBlocks);
+		B3_LAUNCH_CHECK();
+		KeyT* t = kin;
+		kin = kout;
+		kout = t;
+		unsigned int* tv = vin;
+		vin = vout;
+		vout = tv;
+	}
+	if (kin != keys)
+	{
+		B3_CUDA_CHECK(cudaMemcpyAsync(keys, kin, sizeof(KeyT) * n, cudaMemcpyDeviceToDevice, s));
+		if (HAS_VALS) B3_CUDA_CHECK(cudaMemcpyAsync(vals, vin, sizeof(unsigned int) * n, cudaMemcpyDeviceToDevice, s));
+	}
+	return 0;
+}
+
+int radixSortKV32(cudaStream_t s, RadixSortTemp& tmp, unsigned int* keys, unsigned int* vals, int n, int numBits)
+{
+	B3_TRY(tmp.keysAlt.reserve(n));
+	B3_TRY(tmp.valsAlt.reserve(n));
+	return radixSortImpl<unsigned int, true>(s, tmp, keys, tmp.keysAlt.ptr, vals, tmp.valsAlt.ptr, n, numBits);
+}
+int radixSortKeys32(cudaStream_t s, RadixSortTemp& tmp, unsigned int* keys, int n, int numBits)
+{
+	B3_TRY(tmp.keysAlt.reserve(n));
+	return radixSortImpl<unsigned int, false>(s, tmp, keys, tmp.keysAlt.ptr, nullptr, nullptr, n, numBits);
+}
+int radixSortKV64(cudaStream_t s, RadixSortTemp& tmp, unsigned long long* keys, unsigned int* vals, int n, int numBits)
+{
+	B3_TRY(tmp.keys64Alt.reserve(n));
+	B3_TRY(tmp.valsAlt.reserve(n));
+	return radixSortImpl<unsigned long long, true>(s, tmp, keys, tmp.keys64Alt.ptr, vals, tmp.valsAlt.ptr, n, numBits);
+}
+
+// ------------------------------------------------------------------ misc kernels
+__global__ void fillKernel(unsigned int* dst, unsigned int value, int n, int offset)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) dst[offset + i] = value;
+}
+
+// b3BoundSearchCL COUNT (b3BoundSearchCL.cpp:74-203): counts[b] = #{i : sorted[i].key == b}
+__global__ void boundCountKernel(const b3b200_sort_data* __restrict__ sorted, int n, unsigned int* __restrict__ lower, unsigned int* __restrict__ upper, int numBuckets)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned int k = sorted[i].key;
+	if (k >= (unsigned int)numBuckets) return;
+	if (i == 0 || sorted[i - 1].key != k) lower[k] = i;
+	if (i == n - 1 || sorted[i + 1].key != k) upper[k] = i + 1;
+}
+__global__ void subKernel(const unsigned int* lower, const unsigned int* upper, unsigned int* counts, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) counts[i] = upper[i] - lower[i];
+}
+
+__global__ void splitSortDataKernel(const b3b200_sort_data* in, unsigned int* k, unsigned int* v, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		k[i] = in[i].key;
+		v[i] = in[i].value;
+	}
+}
+__global__ void joinSortDataKernel(b3b200_sort_data* out, const unsigned int* k, const unsigned int* v, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		out[i].key = k[i];
+		out[i].value = v[i];
+	}
+}
+
+}  // namespace b3b200
+
+using namespace b3b200;
+
+// ------------------------------------------------------------------ C ABI (host buffers)
+extern "C" int b3b200_radix_sort_kv(int device, b3b200_sort_data* data, int n)
+{
+	if (n < 0 || (n > 0 && !data)) return B3B200_ERR_INVALID;
+	if (n == 0) return 0;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<b3b200_sort_data> d;
+	DevBuf<unsigned int> k, v;
+	RadixSortTemp tmp;
+	B3_TRY(d.reserve(n));
+	B3_TRY(k.reserve(n));
+	B3_TRY(v.reserve(n));
+	B3_CUDA_CHECK(cudaMemcpy(d.ptr, data, sizeof(b3b200_sort_data) * n, cudaMemcpyHostToDevice));
+	splitSortDataKernel<<<divUp(n, 256), 256>>>(d.ptr, k.ptr, v.ptr, n);
+	B3_LAUNCH_CHECK();
+	B3_TRY(radixSortKV32(0, tmp, k.ptr, v.ptr, n, 32));
+	joinSortDataKernel<<<divUp(n, 256), 256>>>(d.ptr, k.ptr, v.ptr, n);
+	B3_LAUNCH_CHECK();
+	B3_CUDA_CHECK(cudaMemcpy(data, d.ptr, sizeof(b3b200_sort_data) * n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int b3b200_radix_sort_keys(int device, unsigned int* keys, int n)
+{
+	if (n < 0 || (n > 0 && !keys)) return B3B200_ERR_INVALID;
+	if (n == 0) return 0;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<unsigned int> k;
+	RadixSortTemp tmp;
+	B3_TRY(k.reserve(n));
+	B3_CUDA_CHECK(cudaMemcpy(k.ptr, keys, sizeof(unsigned int) * n, cudaMemcpyHostToDevice));
+	B3_TRY(radixSortKeys32(0, tmp, k.ptr, n, 32));
+	B3_CUDA_CHECK(cudaMemcpy(keys, k.ptr, sizeof(unsigned int) * n, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int b3b200_prefix_scan_u32(int device, const unsigned int* src, unsigned int* dst, int n, unsigned int* sum)
+{
+	if (n < 0 || (n > 0 && (!src || !dst))) return B3B200_ERR_INVALID;
+	if (n == 0)
+	{
+		if (sum) *sum = 0;
+		return 0;
+	}
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<unsigned int> a, b, t;
+	B3_TRY(a.reserve(n));
+	B3_TRY(b.reserve(n));
+	B3_TRY(t.reserve(1));
+	B3_CUDA_CHECK(cudaMemcpy(a.ptr, src, sizeof(unsigned int) * n, cudaMemcpyHostToDevice));
+	B3_TRY(exclusiveScanU32(0, a.ptr, b.ptr, n, t.ptr));
+	B3_CUDA_CHECK(cudaMemcpy(dst, b.ptr, sizeof(unsigned int) * n, cudaMemcpyDeviceToHost));
+	if (sum) B3_CUDA_CHECK(cudaMemcpy(sum, t.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int b3b200_bound_search_count(int device, const b3b200_sort_data* sorted, int n, unsigned int* counts, int numBuckets)
+{
+	if (n < 0 || numBuckets <= 0 || !counts || (n > 0 && !sorted)) return B3B200_ERR_INVALID;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<b3b200_sort_data> d;
+	DevBuf<unsigned int> lo, hi, c;
+	B3_TRY(lo.reserve(numBuckets));
+	B3_TRY(hi.reserve(numBuckets));
+	B3_TRY(c.reserve(numBuckets));
+	B3_CUDA_CHECK(cudaMemset(lo.ptr, 0, sizeof(unsigned int) * numBuckets));
+	B3_CUDA_CHECK(cudaMemset(hi.ptr, 0, sizeof(unsigned int) * numBuckets));
+	if (n > 0)
+	{
+		B3_TRY(d.reserve(n));
+		B3_CUDA_CHECK(cudaMemcpy(d.ptr, sorted, sizeof(b3b200_sort_data) * n, cudaMemcpyHostToDevice));
+		boundCountKernel<<<divUp(n, 256), 256>>>(d.ptr, n, lo.ptr, hi.ptr, numBuckets);
+		B3_LAUNCH_CHECK();
+	}
+	subKernel<<<divUp(numBuckets, 256), 256>>>(lo.ptr, hi.ptr, c.ptr, numBuckets);
+	B3_LAUNCH_CHECK();
+	B3_CUDA_CHECK(cudaMemcpy(counts, c.ptr, sizeof(unsigned int) * numBuckets, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+extern "C" int b3b200_fill_u32(int device, unsigned int* dst, unsigned int value, int n, int offset)
+{
+	if (n < 0 || offset < 0 || (n > 0 && !dst)) return B3B200_ERR_INVALID;
+	if (n == 0) return 0;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<unsigned int> d;
+	B3_TRY(d.reserve((size_t)n + offset));
+	B3_CUDA_CHECK(cudaMemcpy(d.ptr, dst, sizeof(unsigned int) * ((size_t)n + offset), cudaMemcpyHostToDevice));
+	fillKernel<<<divUp(n, 256), 256>>>(d.ptr, value, n, offset);
+	B3_LAUNCH_CHECK();
+	B3_CUDA_CHECK(cudaMemcpy(dst, d.ptr, sizeof(unsigned int) * ((size_t)n + offset), cudaMemcpyDeviceToHost));
+	return 0;
+}

@@ -1,0 +1,625 @@
+// solver.cu -- batched PGS contact solver.
+//
+// Replaces b3GpuPgsContactSolver::solveContacts (b3GpuPgsContactSolver.cpp:568-1103):
+// 6 radix sorts + a serial per-cell batching thread (batchingKernelsNew.cl:144-231)
+// + contact->constraint + 2*I*8 launches of 32 work-groups, with host
+// synchronisation after every phase.  Here:
+//
+//  setup    ONE persistent cooperative kernel:
+//           (1) graph colouring of the contact graph by priority rounds
+//               (Jones-Plassmann): every contact has a 64-bit priority that is a
+//               hash of (bodyA, bodyB, childA, childB); per round each uncoloured
+//               contact posts its priority on its dynamic bodies with atomicMax,
+//               and the contact that is top on both of its bodies takes the
+//               lowest colour not yet used on either body (two 64-bit colour
+//               masks per body = 128 colours = B3_MAX_NUM_BATCHES, b3Solver.h:39).
+//               The result equals a sequential first-fit colouring in
+//               descending priority order, i.e. it is deterministic whatever
+//               order the narrowphase appended the contacts in, and the CPU
+//               oracle reproduces it exactly ("same batching").
+//           (2) colour histogram -> batch offsets,
+//           (3) contact -> constraint rows (setConstraint4,
+//               b3ConvertConstraint4.h:62-148) written straight into batch order.
+//  iterate  ONE persistent cooperative kernel: for every iteration, every batch
+//           in order (grid barrier in between), all normal rows; then the same
+//           for friction -- the order of the reference's global-batch mode
+//           (gUseLargeBatches, solveContactConstraintBatchSizes,
+//           b3GpuPgsContactSolver.cpp:262-311) and of its host twin
+//           (solveContact<false>/solveFriction, b3Solver.cpp:187-329).
+//           Velocities live in the 32-byte-per-body SoA array (8 MB at 256k
+//           bodies: L2-resident across all 2*I*batches phases).
+#include "internal.h"
+
+namespace b3b200
+{
+constexpr int SOLVER_THREADS = 256;
+constexpr int MAX_ROUNDS = 1024;
+
+// ---------------------------------------------------------------- grid barrier
+// bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident
+// (cooperative launch), one thread per CTA spins.
+B3_D void gridBarrier(unsigned int* bar, unsigned int numBlocks)
+{
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		__threadfence();
+		volatile unsigned int* vbar = bar;
+		unsigned int gen = vbar[1];
+		unsigned int arrived = atomicAdd(&bar[0], 1u);
+		if (arrived == numBlocks - 1)
+		{
+			vbar[0] = 0;
+			__threadfence();
+			atomicAdd(&bar[1], 1u);
+		}
+		else
+		{
+			while (vbar[1] == gen)
+			{
+			}
+		}
+		__threadfence();
+	}
+	__syncthreads();
+}
+
+B3_HD unsigned int hashContact(int a, int b, int ca, int cb)
+{
+	unsigned int h = (unsigned int)a * 0x9E3779B1u;
+	h ^= (unsigned int)b * 0x85EBCA77u + 0x165667B1u + (h << 6) + (h >> 2);
+	h ^= (unsigned int)ca * 0xC2B2AE3Du + (h << 6) + (h >> 2);
+	h ^= (unsigned int)cb * 0x27D4EB2Fu + (h << 6) + (h >> 2);
+	h ^= h >> 16;
+	h *= 0x85EBCA6Bu;
+	h ^= h >> 13;
+	h *= 0xC2B2AE35u;
+	h ^= h >> 16;
+	return h;
+}
+
+struct SetupArgs
+{
+	b3b200_contact4* contacts;
+	unsigned int* ctr;
+	const float4* pose;
+	const float4* vel;
+	const b3b200_inertia* inertias;
+	b3b200_constraint4* constraints;
+	unsigned long long* bodyMask;  // 2 per body
+	unsigned long long* bodyPrio;  // 1 per body
+	int* contactColour;
+	unsigned int* batchCount;   // MAX_BATCHES
+	unsigned int* batchOffset;  // MAX_BATCHES + 1
+	unsigned int* batchCursor;  // MAX_BATCHES
+	unsigned int* remaining;    // MAX_ROUNDS
+	unsigned int* bar;
+	int numBodies;
+	int staticIdx;
+	float dt, positionDrift, positionConstraintCoeff;
+};
+
+B3_D float4 matRowMul(const float4& r0, const float4& r1, const float4& r2, const float4& v)
+{
+	return mk4(dot3(r0, v), dot3(r1, v), dot3(r2, v));
+}
+
+// calcJacCoeff (b3ConvertConstraint4.h:50-60)
+B3_D float calcJacCoeff(const float4& angular0, const float4& angular1, float invMass0, const float4* I0, float invMass1, const float4* I1)
+{
+	float jmj0 = invMass0;
+	float jmj1 = dot3(matRowMul(I0[0], I0[1], I0[2], angular0), angular0);
+	float jmj2 = invMass1;
+	float jmj3 = dot3(matRowMul(I1[0], I1[1], I1[2], angular1), angular1);
+	return -1.f / (jmj0 + jmj1 + jmj2 + jmj3);
+}
+B3_D float calcRelVel(const float4& l0, const float4& l1, const float4& a0, const float4& a1, const float4& linVel0, const float4& angVel0,
+					  const float4& linVel1, const float4& angVel1)
+{
+	return dot3(l0, linVel0) + dot3(a0, angVel0) + dot3(l1, linVel1) + dot3(a1, angVel1);
+}
+// b3PlaneSpace1 (b3ConvertConstraint4.h:5-34)
+B3_D void planeSpace1(const float4& n, float4& p, float4& q)
+{
+	if (fabsf(n.z) > 0.70710678f)
+	{
+		float a = n.y * n.y + n.z * n.z;
+		float k = 1.f / sqrtf(a);
+		p = mk4(0.f, -n.z * k, n.y * k);
+		q = mk4(a * k, -n.x * p.z, n.x * p.y);
+	}
+	else
+	{
+		float a = n.x * n.x + n.y * n.y;
+		float k = 1.f / sqrtf(a);
+		p = mk4(-n.y * k, n.x * k, 0.f);
+		q = mk4(-n.z * p.y, n.z * p.x, a * k);
+	}
+}
+
+// setConstraint4 (b3ConvertConstraint4.h:62-148)
+B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict__ src, int colour, b3b200_constraint4* __restrict__ dst)
+{
+	const float4* cw = reinterpret_cast<const float4*>(src);
+	float4 wp[4] = {cw[0], cw[1], cw[2], cw[3]};
+	const float4 nrm = cw[4];
+	const int4 ids = reinterpret_cast<const int4*>(src)[5];
+	const int aIdx = abs(ids.z), bIdx = abs(ids.w);
+	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
+	const float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
+	const float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
+	const float invMassA = posA.w, invMassB = posB.w;
+	// quirk kept from the reference: rows are built with the LOCAL initial inverse inertia
+	// (solverSetup.cl:254,260 / b3Solver.cpp:911,917), solved with the world one.
+	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].initInvInertia);
+	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].initInvInertia);
+	float4 ia[3] = {__ldg(IA), __ldg(IA + 1), __ldg(IA + 2)};
+	float4 ib[3] = {__ldg(IB), __ldg(IB + 1), __ldg(IB + 2)};
+
+	const float dtInv = 1.f / s.dt;
+	const float npoints = nrm.w;
+	float jac[4], bb[4];
+	const float4 n = mk4(nrm.x, nrm.y, nrm.z);
+	const float4 nn = neg3(n);
+#pragma unroll
+	for (int ic = 0; ic < 4; ic++)
+	{
+		float4 r0 = sub3(wp[ic], posA);
+		float4 r1 = sub3(wp[ic], posB);
+		if ((float)ic >= npoints)
+		{
+			jac[ic] = 0.f;
+			bb[ic] = 0.f;
+			continue;
+		}
+		float4 angular0 = cross3(r0, n);
+		float4 angular1 = neg3(cross3(r1, n));
+		jac[ic] = calcJacCoeff(angular0, angular1, invMassA, ia, invMassB, ib);
+		float relVelN = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+		float e = 0.f;
+		float b = e * relVelN;
+		b += (wp[ic].w + s.positionDrift) * s.positionConstraintCoeff * dtInv;
+		bb[ic] = b;
+	}
+	float fjac[2] = {0.f, 0.f};
+	float4 center = mk4(0, 0, 0);
+	if (npoints > 0)
+	{
+		for (int i = 0; (float)i < npoints && i < 4; i++)
+		{
+			center.x += wp[i].x;
+			center.y += wp[i].y;
+			center.z += wp[i].z;
+		}
+		float inv = 1.0f / (float)npoints;
+		center.x *= inv;
+		center.y *= inv;
+		center.z *= inv;
+		float4 t0, t1;
+		planeSpace1(n, t0, t1);
+		float4 r0 = sub3(center, posA), r1 = sub3(center, posB);
+		{
+			float4 a0 = cross3(r0, t0), a1 = neg3(cross3(r1, t0));
+			fjac[0] = calcJacCoeff(a0, a1, invMassA, ia, invMassB, ib);
+		}
+		{
+			float4 a0 = cross3(r0, t1), a1 = neg3(cross3(r1, t1));
+			fjac[1] = calcJacCoeff(a0, a1, invMassA, ia, invMassB, ib);
+		}
+	}
+	float4* dw = reinterpret_cast<float4*>(dst);
+	dw[0] = mk4(nrm.x, nrm.y, nrm.z, 0.7f);
+#pragma unroll
+	for (int i = 0; i < 4; i++) dw[1 + i] = ((float)i < npoints) ? wp[i] : mk4(0, 0, 0, 0);
+	dw[5] = center;
+	dw[6] = mk4(jac[0], jac[1], jac[2], jac[3]);
+	dw[7] = mk4(bb[0], bb[1], bb[2], bb[3]);
+	dw[8] = mk4(0, 0, 0, 0);              // appliedRambdaDt
+	dw[9] = mk4(fjac[0], fjac[1], 0, 0);  // fJacCoeffInv, fAppliedRambdaDt
+	int4 tail;
+	tail.x = aIdx;
+	tail.y = bIdx;
+	tail.z = colour;
+	tail.w = 0;
+	reinterpret_cast<int4*>(dst)[10] = tail;
+}
+
+__global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
+{
+	const unsigned int nBlocks = gridDim.x;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+	const int nContacts = (int)s.ctr[CTR_CONTACTS];
+
+	// ---- phase 0: clear
+	for (int i = tid; i < s.numBodies; i += stride)
+	{
+		s.bodyMask[2 * i] = 0ull;
+		s.bodyMask[2 * i + 1] = 0ull;
+		s.bodyPrio[i] = 0ull;
+	}
+	for (int i = tid; i < nContacts; i += stride) s.contactColour[i] = -1;
+	for (int i = tid; i < MAX_BATCHES; i += stride)
+	{
+		s.batchCount[i] = 0;
+		s.batchCursor[i] = 0;
+	}
+	for (int i = tid; i < MAX_ROUNDS; i += stride) s.remaining[i] = 0;
+	gridBarrier(s.bar, nBlocks);
+
+	// ---- phase 1: colouring rounds
+	int round = 0;
+	for (; round < MAX_ROUNDS; round++)
+	{
+		// claim
+		for (int c = tid; c < nContacts; c += stride)
+		{
+			if (s.contactColour[c] >= 0) continue;
+			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
+			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
+			const int a = abs(ids.z), b = abs(ids.w);
+			const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
+			const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
+			unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
+			if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
+			if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
+		}
+		gridBarrier(s.bar, nBlocks);
+		// colour
+		unsigned int left = 0;
+		for (int c = tid; c < nContacts; c += stride)
+		{
+			if (s.contactColour[c] >= 0) continue;
+			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
+			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
+			const int a = abs(ids.z), b = abs(ids.w);
+			const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
+			const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
+			unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
+			volatile unsigned long long* vp = s.bodyPrio;
+			bool top = (aStatic || vp[a] == prio) && (bStatic || vp[b] == prio);
+			if (!top)
+			{
+				left++;
+				continue;
+			}
+			unsigned long long m0 = 0ull, m1 = 0ull;
+			if (!aStatic)
+			{
+				m0 |= s.bodyMask[2 * a];
+				m1 |= s.bodyMask[2 * a + 1];
+			}
+			if (!bStatic)
+			{
+				m0 |= s.bodyMask[2 * b];
+				m1 |= s.bodyMask[2 * b + 1];
+			}
+			int colour;
+			if (~m0)
+				colour = __ffsll((long long)~m0) - 1;
+			else if (~m1)
+				colour = 64 + __ffsll((long long)~m1) - 1;
+			else
+			{
+				colour = MAX_BATCHES - 1;
+				atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+			}
+			unsigned long long bit = 1ull << (colour & 63);
+			int word = colour >> 6;
+			if (!aStatic)
+			{
+				s.bodyMask[2 * a + word] |= bit;
+				s.bodyPrio[a] = 0ull;
+			}
+			if (!bStatic)
+			{
+				s.bodyMask[2 * b + word] |= bit;
+				s.bodyPrio[b] = 0ull;
+			}
+			s.contactColour[c] = colour;
+			s.contacts[c].batchIdx = colour;
+			atomicAdd(&s.batchCount[colour], 1u);
+		}
+		// block-reduce `left`
+		left = __reduce_add_sync(0xffffffffu, left);
+		if ((threadIdx.x & 31) == 0 && left) atomicAdd(&s.remaining[round], left);
+		gridBarrier(s.bar, nBlocks);
+		volatile unsigned int* vr = s.remaining;
+		if (vr[round] == 0) break;
+	}
+
+	// ---- phase 2: batch offsets (one warp)
+	if (blockIdx.x == 0 && threadIdx.x < 32)
+	{
+		unsigned int run = 0;
+		int numBatches = 0;
+		for (int base = 0; base < MAX_BATCHES; base += 32)
+		{
+			unsigned int v = s.batchCount[base + threadIdx.x];
+			unsigned int incl = v;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+				if ((int)threadIdx.x >= o) incl += t;
+			}
+			s.batchOffset[base + threadIdx.x] = run + incl - v;
+			unsigned int nz = __ballot_sync(0xffffffffu, v != 0);
+			if (nz) numBatches = base + 32 - __clz(nz);
+			run += __shfl_sync(0xffffffffu, incl, 31);
+		}
+		if (threadIdx.x == 0)
+		{
+			s.batchOffset[MAX_BATCHES] = run;
+			s.ctr[CTR_BATCHES] = (unsigned int)numBatches;
+			s.ctr[CTR_COLOUR_ROUNDS] = (unsigned int)(round + 1);
+		}
+	}
+	gridBarrier(s.bar, nBlocks);
+
+	// ---- phase 3: contact -> constraint rows, written in batch order
+	for (int c = tid; c < nContacts; c += stride)
+	{
+		int colour = s.contactColour[c];
+		if (colour < 0) continue;
+		unsigned int slot = s.batchOffset[colour] + atomicAdd(&s.batchCursor[colour], 1u);
+		buildConstraint(s, &s.contacts[c], colour, &s.constraints[slot]);
+	}
+}
+
+// ---------------------------------------------------------------- iterations
+struct IterArgs
+{
+	b3b200_constraint4* constraints;
+	const unsigned int* ctr;
+	const float4* pose;
+	float4* vel;
+	const b3b200_inertia* inertias;
+	const unsigned int* batchOffset;
+	unsigned int* bar;
+	int iterations;
+};
+
+// solveContact<false> (b3Solver.cpp:187-266)
+B3_D void solveNormalRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs)
+{
+	float4* cw = reinterpret_cast<float4*>(cs);
+	const float4 lin = cw[0];
+	const float4 jac = cw[6];
+	const float4 bias = cw[7];
+	float4 applied = cw[8];
+	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
+	const int aIdx = tail.x, bIdx = tail.y;
+	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
+	const float invMassA = posA.w, invMassB = posB.w;
+	float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
+	float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
+	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
+	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
+	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
+	const float4 ib0 = __ldg(IB), ib1 = __ldg(IB + 1), ib2 = __ldg(IB + 2);
+	const float4 n = mk4(lin.x, lin.y, lin.z);
+	const float4 nn = neg3(n);
+	const float jacv[4] = {jac.x, jac.y, jac.z, jac.w};
+	const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
+	float ap[4] = {applied.x, applied.y, applied.z, applied.w};
+#pragma unroll
+	for (int ic = 0; ic < 4; ic++)
+	{
+		if (jacv[ic] == 0.f) continue;
+		const float4 wp = cw[1 + ic];
+		float4 r0 = sub3(wp, posA), r1 = sub3(wp, posB);
+		float4 angular0 = cross3(r0, n);
+		float4 angular1 = neg3(cross3(r1, n));
+		float rambdaDt = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
+		rambdaDt *= jacv[ic];
+		{
+			float prevSum = ap[ic];
+			float updated = prevSum;
+			updated += rambdaDt;
+			updated = fmaxf(updated, 0.f);
+			updated = fminf(updated, FLT_MAX);
+			rambdaDt = updated - prevSum;
+			ap[ic] = updated;
+		}
+		float4 linImp0 = scale3(scale3(n, invMassA), rambdaDt);
+		float4 linImp1 = scale3(scale3(nn, invMassB), rambdaDt);
+		float4 angImp0 = scale3(matRowMul(ia0, ia1, ia2, angular0), rambdaDt);
+		float4 angImp1 = scale3(matRowMul(ib0, ib1, ib2, angular1), rambdaDt);
+		linVelA = add3(linVelA, linImp0);
+		angVelA = add3(angVelA, angImp0);
+		linVelB = add3(linVelB, linImp1);
+		angVelB = add3(angVelB, angImp1);
+	}
+	cw[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
+	if (invMassA != 0.f)
+	{
+		s.vel[2 * aIdx] = linVelA;
+		s.vel[2 * aIdx + 1] = angVelA;
+	}
+	if (invMassB != 0.f)
+	{
+		s.vel[2 * bIdx] = linVelB;
+		s.vel[2 * bIdx + 1] = angVelB;
+	}
+}
+
+// solveFriction (b3Solver.cpp:268-329) with the limits of SolveTask::run (:384-402)
+B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs)
+{
+	float4* cw = reinterpret_cast<float4*>(cs);
+	float4 fr = cw[9];  // fJacCoeffInv[2], fAppliedRambdaDt[2]
+	if (fr.x == 0.f && fr.x == 0.f) return;
+	const float4 lin = cw[0];
+	const float4 center = cw[5];
+	const float4 applied = cw[8];
+	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
+	const int aIdx = tail.x, bIdx = tail.y;
+	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
+	const float invMassA = posA.w, invMassB = posB.w;
+	float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
+	float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
+	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
+	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
+	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
+	const float4 ib0 = __ldg(IB), ib1 = __ldg(IB + 1), ib2 = __ldg(IB + 2);
+
+	float sum = 0.f;
+	sum += applied.x;
+	sum += applied.y;
+	sum += applied.z;
+	sum += applied.w;
+	const float frictionCoeff = 0.7f;
+	const float maxR = frictionCoeff * sum;
+	const float minR = -maxR;
+
+	const float4 n = neg3(mk4(lin.x, lin.y, lin.z));
+	float4 tangent[2];
+	planeSpace1(n, tangent[0], tangent[1]);
+	const float4 r0 = sub3(center, posA), r1 = sub3(center, posB);
+	float fj[2] = {fr.x, fr.y};
+	float fa[2] = {fr.z, fr.w};
+#pragma unroll
+	for (int i = 0; i < 2; i++)
+	{
+		const float4 t = tangent[i];
+		const float4 angular0 = cross3(r0, t);
+		const float4 angular1 = neg3(cross3(r1, t));
+		float rambdaDt = calcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+		rambdaDt *= fj[i];
+		{
+			float prevSum = fa[i];
+			float updated = prevSum;
+			updated += rambdaDt;
+			updated = fmaxf(updated, minR);
+			updated = fminf(updated, maxR);
+			rambdaDt = updated - prevSum;
+			fa[i] = updated;
+		}
+		float4 linImp0 = scale3(scale3(t, invMassA), rambdaDt);
+		float4 linImp1 = scale3(scale3(neg3(t), invMassB), rambdaDt);
+		float4 angImp0 = scale3(matRowMul(ia0, ia1, ia2, angular0), rambdaDt);
+		float4 angImp1 = scale3(matRowMul(ib0, ib1, ib2, angular1), rambdaDt);
+		linVelA = add3(linVelA, linImp0);
+		angVelA = add3(angVelA, angImp0);
+		linVelB = add3(linVelB, linImp1);
+		angVelB = add3(angVelB, angImp1);
+	}
+	{
+		// angular damping for point constraint (b3Solver.cpp:317-328)
+		float4 ab = normalized3(sub3(posB, posA));
+		float4 ac = normalized3(sub3(center, posA));
+		if (dot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
+		{
+			float angNA = dot3(n, angVelA);
+			float angNB = dot3(n, angVelB);
+			angVelA = sub3(angVelA, scale3(n, angNA * 0.1f));
+			angVelB = sub3(angVelB, scale3(n, angNB * 0.1f));
+		}
+	}
+	cw[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
+	if (invMassA != 0.f)
+	{
+		s.vel[2 * aIdx] = linVelA;
+		s.vel[2 * aIdx + 1] = angVelA;
+	}
+	if (invMassB != 0.f)
+	{
+		s.vel[2 * bIdx] = linVelB;
+		s.vel[2 * bIdx + 1] = angVelB;
+	}
+}
+
+__global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s)
+{
+	const unsigned int nBlocks = gridDim.x;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+	const int numBatches = (int)s.ctr[CTR_BATCHES];
+	if (numBatches == 0) return;
+	for (int phase = 0; phase < 2; phase++)
+	{
+		for (int iter = 0; iter < s.iterations; iter++)
+		{
+			for (int b = 0; b < numBatches; b++)
+			{
+				const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
+				for (int i = begin + tid; i < end; i += stride)
+				{
+					if (phase == 0)
+						solveNormalRows(s, &s.constraints[i]);
+					else
+						solveFrictionRows(s, &s.constraints[i]);
+				}
+				gridBarrier(s.bar, nBlocks);
+			}
+		}
+	}
+}
+
+static int coopLaunch(World* w, const void* fn, void* argStruct)
+{
+	int perSm = 0;
+	B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, SOLVER_THREADS, 0));
+	if (perSm < 1)
+	{
+		setLastError("solver kernel does not fit on an SM");
+		return B3B200_ERR_CUDA;
+	}
+	if (perSm > 4) perSm = 4;
+	dim3 grid(w->smCount * perSm), block(SOLVER_THREADS);
+	void* args[] = {argStruct};
+	B3_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, w->stream));
+	g_launchCount++;
+	return 0;
+}
+
+int launchSolverSetup(World* w)
+{
+	SetupArgs s;
+	s.contacts = w->dContacts.ptr;
+	s.ctr = w->dCounters.ptr;
+	s.pose = w->dPose.ptr;
+	s.vel = w->dVel.ptr;
+	s.inertias = w->dInertias.ptr;
+	s.constraints = w->dConstraints.ptr;
+	s.bodyMask = w->dBodyMask.ptr;
+	s.bodyPrio = reinterpret_cast<unsigned long long*>(w->dBodyPrio.ptr);
+	s.contactColour = w->dContactColour.ptr;
+	s.batchCount = w->dBatchCount.ptr;
+	s.batchOffset = w->dBatchOffset.ptr;
+	s.batchCursor = w->dBatchCursor.ptr;
+	s.remaining = w->dBodyCount.ptr;  // MAX_ROUNDS words, see World::init
+	s.bar = w->dGridBarrier.ptr;
+	s.numBodies = w->numBodies;
+	s.staticIdx = w->static0Index;
+	s.dt = 1.f / 60.f;  // the reference solver ignores deltaTime (b3GpuPgsContactSolver.cpp:672)
+	s.positionDrift = 0.005f;
+	s.positionConstraintCoeff = 0.2f;
+	return coopLaunch(w, (const void*)solverSetupKernel, &s);
+}
+
+int launchSolverIterate(World* w)
+{
+	IterArgs s;
+	s.constraints = w->dConstraints.ptr;
+	s.ctr = w->dCounters.ptr;
+	s.pose = w->dPose.ptr;
+	s.vel = w->dVel.ptr;
+	s.inertias = w->dInertias.ptr;
+	s.batchOffset = w->dBatchOffset.ptr;
+	s.bar = w->dGridBarrier.ptr;
+	s.iterations = w->solverIterations;
+	int r = coopLaunch(w, (const void*)solverIterateKernel, &s);
+	w->soaDirty = true;
+	return r;
+}
+
+int launchJacobi(World* w)
+{
+	(void)w;
+	setLastError("Jacobi contact solver: not built yet");
+	return B3B200_ERR_STATE;
+}
+
+}  // namespace b3b200

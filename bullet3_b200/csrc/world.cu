@@ -1,0 +1,786 @@
+// world.cu -- world handle, registration, upload, the step and read-backs:
+// the C ABI of include/b3b200.h.
+#include <stdarg.h>
+#include <string.h>
+#include <math.h>
+#include "internal.h"
+
+namespace b3b200
+{
+static thread_local char g_lastError[512] = "";
+long long g_launchCount = 0;
+
+void setLastError(const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_lastError, sizeof(g_lastError), fmt, ap);
+	va_end(ap);
+}
+
+template <typename T, typename H>
+static int uploadVec(DevBuf<T>& d, const std::vector<H>& h, size_t minCap, cudaStream_t s)
+{
+	static_assert(sizeof(T) == sizeof(H), "layout");
+	size_t n = h.size();
+	B3_TRY(d.reserve(std::max(std::max(n, minCap), (size_t)1)));
+	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(d.ptr, h.data(), n * sizeof(T), cudaMemcpyHostToDevice, s));
+	return 0;
+}
+
+int World::init(const b3b200_config* c, int dev, cudaStream_t st)
+{
+	cfg = *c;
+	device = dev;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	if (st)
+	{
+		stream = st;
+		ownStream = false;
+	}
+	else
+	{
+		B3_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+		ownStream = true;
+	}
+	cudaDeviceProp prop;
+	B3_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+	smCount = prop.multiProcessorCount;
+	B3_TRY(bp.init(B3B200_BP_GRID, device, stream, cfg.maxConvexBodies, cfg.maxBroadphasePairs));
+	B3_TRY(dCounters.reserve(CTR_COUNT));
+	B3_CUDA_CHECK(cudaMemsetAsync(dCounters.ptr, 0, sizeof(unsigned int) * CTR_COUNT, stream));
+	bp.ctr = dCounters.ptr;
+	B3_TRY(dGridBarrier.reserve(4));
+	B3_CUDA_CHECK(cudaMemsetAsync(dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, stream));
+	for (int i = 0; i < 8; i++) B3_CUDA_CHECK(cudaEventCreate(&ev[i]));
+	return 0;
+}
+
+void World::destroy()
+{
+	cudaSetDevice(device);
+	if (stream) cudaStreamSynchronize(stream);
+	for (int i = 0; i < 8; i++)
+		if (ev[i]) cudaEventDestroy(ev[i]);
+	cudaStream_t s = stream;
+	bool own = ownStream;
+	bp.stream = 0;  // shared with the world
+	bp.ownStream = false;
+	bp.destroy();
+	if (own && s) cudaStreamDestroy(s);
+	stream = 0;
+}
+
+// b3TransformAabb (src/Bullet3Geometry/b3AabbUtil.h:182-197), float, scalar path
+static void transformAabbHost(const float* lmn, const float* lmx, float margin, const float* pos, const float* orn, float* outMin, float* outMax)
+{
+	float4 half = mk4(0.5f * (lmx[0] - lmn[0]), 0.5f * (lmx[1] - lmn[1]), 0.5f * (lmx[2] - lmn[2]));
+	half = mk4(half.x + margin, half.y + margin, half.z + margin);
+	float4 lc = mk4(0.5f * (lmx[0] + lmn[0]), 0.5f * (lmx[1] + lmn[1]), 0.5f * (lmx[2] + lmn[2]));
+	float4 q = mk4(orn[0], orn[1], orn[2], orn[3]);
+	Mat3 m = matFromQuat(q);
+	float4 a0 = mk4(fabsf(m.r0.x), fabsf(m.r0.y), fabsf(m.r0.z));
+	float4 a1 = mk4(fabsf(m.r1.x), fabsf(m.r1.y), fabsf(m.r1.z));
+	float4 a2 = mk4(fabsf(m.r2.x), fabsf(m.r2.y), fabsf(m.r2.z));
+	float4 r = matMulVec(m, lc);
+	float c[3] = {r.x + pos[0], r.y + pos[1], r.z + pos[2]};
+	float e[3] = {dot3(half, a0), dot3(half, a1), dot3(half, a2)};
+	for (int i = 0; i < 3; i++)
+	{
+		outMin[i] = c[i] - e[i];
+		outMax[i] = c[i] + e[i];
+	}
+}
+
+static int allocateCollidable(World* w)
+{
+	// b3GpuNarrowPhase::allocateCollidable (b3GpuNarrowPhase.cpp:144-157)
+	if ((int)w->collidables.size() >= w->cfg.maxConvexShapes)
+	{
+		setLastError("allocateCollidable out-of-range %d", w->cfg.maxConvexShapes);
+		return -1;
+	}
+	b3b200_collidable c;
+	memset(&c, 0, sizeof(c));
+	w->collidables.push_back(c);
+	b3b200_aabb a;
+	memset(&a, 0, sizeof(a));
+	w->localAabbs.push_back(a);
+	return (int)w->collidables.size() - 1;
+}
+
+static int registerConvexInternal(World* w, const b3b200_float4* verts, int nV, const b3b200_face* faces, int nF, const int* idx, int nI,
+								  const b3b200_float4* edges, int nE, const b3b200_convex_polyhedron* poly)
+{
+	// b3GpuNarrowPhase::registerConvexHullShapeInternal (b3GpuNarrowPhase.cpp:234-296)
+	if ((int)w->vertices.size() + nV > w->cfg.maxConvexVertices || (int)w->indices.size() + nI > w->cfg.maxConvexIndices ||
+		(int)w->uniqueEdges.size() + nE > w->cfg.maxConvexUniqueEdges || (int)w->convex.size() + 1 > w->cfg.maxConvexShapes)
+	{
+		setLastError("registerConvexHullShape: exceeding shape table capacity");
+		return -1;
+	}
+	b3b200_convex_polyhedron c = *poly;
+	c.numUniqueEdges = nE;
+	c.uniqueEdgesOffset = (int)w->uniqueEdges.size();
+	for (int i = 0; i < nE; i++) w->uniqueEdges.push_back(edges[i]);
+	c.faceOffset = (int)w->faces.size();
+	c.numFaces = nF;
+	for (int i = 0; i < nF; i++)
+	{
+		b3b200_face f = faces[i];
+		int off = (int)w->indices.size();
+		if (f.indexOffset < 0 || f.numIndices < 0 || f.indexOffset + f.numIndices > nI)
+		{
+			setLastError("registerConvexHullShape: face %d indexes outside the index array", i);
+			return -1;
+		}
+		for (int p = 0; p < f.numIndices; p++) w->indices.push_back(idx[f.indexOffset + p]);
+		f.indexOffset = off;
+		w->faces.push_back(f);
+	}
+	c.numVertices = nV;
+	c.vertexOffset = (int)w->vertices.size();
+	for (int i = 0; i < nV; i++) w->vertices.push_back(verts[i]);
+	w->convex.push_back(c);
+	return (int)w->convex.size() - 1;
+}
+
+static void initInertia(World* w, int bodyIndex, float mass, const float* aabbMin, const float* aabbMax)
+{
+	// b3GpuNarrowPhase::registerRigidBody (b3GpuNarrowPhase.cpp:859-903)
+	b3b200_inertia& I = w->inertias[bodyIndex];
+	memset(&I, 0, sizeof(I));
+	if (mass == 0.f) return;
+	float he[3] = {aabbMax[0] - aabbMin[0], aabbMax[1] - aabbMin[1], aabbMax[2] - aabbMin[2]};
+	float lx = 2.f * he[0], ly = 2.f * he[1], lz = 2.f * he[2];
+	float li[3] = {(mass / 12.0f) * (ly * ly + lz * lz), (mass / 12.0f) * (lx * lx + lz * lz), (mass / 12.0f) * (lx * lx + ly * ly)};
+	float inv[3] = {1.f / li[0], 1.f / li[1], 1.f / li[2]};
+	I.initInvInertia.row[0].x = inv[0];
+	I.initInvInertia.row[1].y = inv[1];
+	I.initInvInertia.row[2].z = inv[2];
+	const b3b200_rigid_body& b = w->bodies[bodyIndex];
+	Mat3 m = matFromQuat(mk4(b.quat.x, b.quat.y, b.quat.z, b.quat.w));
+	// m.scaled(inv) * m.transpose()  (b3Matrix3x3.h operator*, tdotx/y/z)
+	float M[3][3] = {{m.r0.x, m.r0.y, m.r0.z}, {m.r1.x, m.r1.y, m.r1.z}, {m.r2.x, m.r2.y, m.r2.z}};
+	float A[3][3];
+	for (int r = 0; r < 3; r++)
+		for (int c = 0; c < 3; c++) A[r][c] = M[r][c] * inv[c];
+	float R[3][3];
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) R[i][j] = M[j][0] * A[i][0] + M[j][1] * A[i][1] + M[j][2] * A[i][2];
+	for (int i = 0; i < 3; i++)
+	{
+		I.invInertiaWorld.row[i].x = R[i][0];
+		I.invInertiaWorld.row[i].y = R[i][1];
+		I.invInertiaWorld.row[i].z = R[i][2];
+		I.invInertiaWorld.row[i].w = 0.f;
+	}
+}
+
+static int syncAoS(World* w)
+{
+	if (w->soaDirty) B3_TRY(launchUnpackSoA(w));
+	return 0;
+}
+
+static int recordStage(World* w, int i)
+{
+	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->ev[i], w->stream));
+	return 0;
+}
+
+static int stepOnce(World* w, float dt)
+{
+	B3_TRY(recordStage(w, 0));
+	if (!w->aabbsValid) B3_TRY(launchUpdateAabbs(w));
+	B3_TRY(recordStage(w, 1));
+	B3_TRY(w->bp.calculatePairs(w->cfg.maxBroadphasePairs));
+	B3_TRY(recordStage(w, 2));
+	B3_TRY(launchNarrowphase(w));
+	B3_TRY(recordStage(w, 3));
+	if (w->solverKind == B3B200_SOLVER_JACOBI)
+	{
+		B3_TRY(launchJacobi(w));
+		B3_TRY(recordStage(w, 4));
+	}
+	else
+	{
+		B3_TRY(launchSolverSetup(w));
+		B3_TRY(recordStage(w, 4));
+		B3_TRY(launchSolverIterate(w));
+	}
+	B3_TRY(recordStage(w, 5));
+	B3_TRY(launchIntegrate(w, dt, true));
+	B3_TRY(recordStage(w, 6));
+	return 0;
+}
+
+}  // namespace b3b200
+
+using namespace b3b200;
+
+#define W_CHECK(w)                         \
+	if (!(w)) return B3B200_ERR_INVALID;   \
+	B3_CUDA_CHECK(cudaSetDevice((w)->device))
+#define W_UPLOADED(w)                                          \
+	W_CHECK(w);                                                \
+	if (!(w)->uploaded)                                        \
+	{                                                          \
+		setLastError("world not uploaded (call b3b200_upload)"); \
+		return B3B200_ERR_STATE;                               \
+	}
+
+extern "C" const char* b3b200_last_error(void) { return g_lastError; }
+extern "C" int b3b200_version(void) { return 100; }
+extern "C" long long b3b200_launch_count(void) { return g_launchCount; }
+
+extern "C" int b3b200_config_default(b3b200_config* c)
+{
+	if (!c) return B3B200_ERR_INVALID;
+	c->maxConvexBodies = 128 * 1024;
+	c->maxVerticesPerFace = 64;
+	c->maxFacesPerShape = 12;
+	c->maxConvexVertices = 8192;
+	c->maxConvexIndices = 81920;
+	c->maxConvexUniqueEdges = 8192;
+	c->maxCompoundChildShapes = 8192;
+	c->maxTriConvexPairCapacity = 256 * 1024;
+	c->maxConvexShapes = c->maxConvexBodies;
+	c->maxBroadphasePairs = 16 * c->maxConvexBodies;
+	c->maxContactCapacity = c->maxBroadphasePairs;
+	c->compoundPairCapacity = 1024 * 1024;
+	return 0;
+}
+
+extern "C" int b3b200_create(const b3b200_config* cfg, int device, void* stream, b3b200_world** out)
+{
+	if (!cfg || !out) return B3B200_ERR_INVALID;
+	if (cfg->maxConvexBodies <= 0 || cfg->maxBroadphasePairs < 0 || cfg->maxContactCapacity < 0) return B3B200_ERR_INVALID;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || device < 0 || device >= count)
+	{
+		setLastError("no CUDA device %d (%s); this library has no CPU fallback", device, e != cudaSuccess ? cudaGetErrorString(e) : "out of range");
+		return B3B200_ERR_CUDA;
+	}
+	b3b200_world* w = new b3b200_world();
+	int r = w->init(cfg, device, (cudaStream_t)stream);
+	if (r < 0)
+	{
+		w->destroy();
+		delete w;
+		return r;
+	}
+	*out = w;
+	return 0;
+}
+
+extern "C" int b3b200_destroy(b3b200_world* w)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->destroy();
+	delete w;
+	return 0;
+}
+
+extern "C" int b3b200_reset(b3b200_world* w)
+{
+	W_CHECK(w);
+	w->collidables.clear();
+	w->localAabbs.clear();
+	w->convex.clear();
+	w->vertices.clear();
+	w->uniqueEdges.clear();
+	w->faces.clear();
+	w->indices.clear();
+	w->childShapes.clear();
+	w->bvhInfos.clear();
+	w->bvhNodes.clear();
+	w->bvhSubtrees.clear();
+	w->bodies.clear();
+	w->inertias.clear();
+	w->numBodies = 0;
+	w->static0Index = -1;
+	w->uploaded = false;
+	w->aabbsValid = false;
+	w->bp.reset();
+	return 0;
+}
+
+extern "C" int b3b200_register_convex(b3b200_world* w, const b3b200_float4* vertices, int numVertices, const b3b200_face* faces, int numFaces,
+									  const int* indices, int numIndices, const b3b200_float4* uniqueEdges, int numUniqueEdges,
+									  const b3b200_convex_polyhedron* poly)
+{
+	if (!w || !vertices || !faces || !indices || !poly || numVertices <= 0 || numFaces <= 0 || numIndices <= 0 || numUniqueEdges < 0 ||
+		(numUniqueEdges > 0 && !uniqueEdges))
+	{
+		setLastError("registerConvexHullShape: invalid argument");
+		return -1;
+	}
+	int ci = allocateCollidable(w);
+	if (ci < 0) return -1;
+	b3b200_collidable& col = w->collidables[ci];
+	col.shapeType = B3B200_SHAPE_CONVEX_HULL;
+	col.shapeIndex = -1;
+	b3b200_convex_polyhedron p = *poly;
+	{
+		// localCenter = vertex average (b3GpuNarrowPhase.cpp:332-337)
+		float cx = 0.f, cy = 0.f, cz = 0.f;
+		for (int i = 0; i < numVertices; i++)
+		{
+			cx += vertices[i].x;
+			cy += vertices[i].y;
+			cz += vertices[i].z;
+		}
+		float s = 1.f / numVertices;
+		p.localCenter.x = cx * s;
+		p.localCenter.y = cy * s;
+		p.localCenter.z = cz * s;
+		p.localCenter.w = 0.f;
+	}
+	int si = registerConvexInternal(w, vertices, numVertices, faces, numFaces, indices, numIndices, uniqueEdges, numUniqueEdges, &p);
+	if (si < 0)
+	{
+		w->collidables.pop_back();
+		w->localAabbs.pop_back();
+		return -1;
+	}
+	w->collidables[ci].shapeIndex = si;
+	// local AABB from the vertices (b3GpuNarrowPhase.cpp:343-365)
+	b3b200_aabb& a = w->localAabbs[ci];
+	float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+	for (int i = 0; i < numVertices; i++)
+	{
+		const float v[3] = {vertices[i].x, vertices[i].y, vertices[i].z};
+		for (int k = 0; k < 3; k++)
+		{
+			if (v[k] < mn[k]) mn[k] = v[k];
+			if (v[k] > mx[k]) mx[k] = v[k];
+		}
+	}
+	for (int k = 0; k < 3; k++)
+	{
+		a.min[k] = mn[k];
+		a.max[k] = mx[k];
+	}
+	a.minIndices[3] = 0;
+	a.signedMaxIndices[3] = 0;
+	return ci;
+}
+
+extern "C" int b3b200_register_convex_points(b3b200_world* w, const float* vertices, int strideInBytes, int numVertices, const float* scaling)
+{
+	if (!w || !vertices || numVertices <= 0 || strideInBytes < 12)
+	{
+		setLastError("registerConvexHullShape: invalid argument");
+		return -1;
+	}
+	static const float one[3] = {1.f, 1.f, 1.f};
+	if (!scaling) scaling = one;
+	std::vector<b3b200_float4> pts(numVertices);
+	const unsigned char* base = (const unsigned char*)vertices;
+	for (int i = 0; i < numVertices; i++)
+	{
+		const float* v = (const float*)(base + (size_t)i * strideInBytes);
+		pts[i].x = v[0] * scaling[0];
+		pts[i].y = v[1] * scaling[1];
+		pts[i].z = v[2] * scaling[2];
+		pts[i].w = 0.f;
+	}
+	HullOut h;
+	if (!buildConvexHull(pts, h))
+	{
+		setLastError("registerConvexHullShape: degenerate point set (need 4 non-coplanar points)");
+		return -1;
+	}
+	return b3b200_register_convex(w, h.vertices.data(), (int)h.vertices.size(), h.faces.data(), (int)h.faces.size(), h.indices.data(),
+								  (int)h.indices.size(), h.uniqueEdges.data(), (int)h.uniqueEdges.size(), &h.poly);
+}
+
+extern "C" int b3b200_register_plane(b3b200_world* w, const float* normal3, float planeConstant)
+{
+	(void)w;
+	(void)normal3;
+	(void)planeConstant;
+	setLastError("registerPlaneShape: not built yet");
+	return -1;
+}
+extern "C" int b3b200_register_sphere(b3b200_world* w, float radius)
+{
+	(void)w;
+	(void)radius;
+	setLastError("registerSphereShape: not built yet");
+	return -1;
+}
+extern "C" int b3b200_register_compound(b3b200_world* w, const b3b200_child_shape* children, int numChildren)
+{
+	(void)w;
+	(void)children;
+	(void)numChildren;
+	setLastError("registerCompoundShape: not built yet");
+	return -1;
+}
+extern "C" int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVertices, const int* triIndices, int numIndices, const float* scaling3)
+{
+	(void)w;
+	(void)vertices;
+	(void)numVertices;
+	(void)triIndices;
+	(void)numIndices;
+	(void)scaling3;
+	setLastError("registerConcaveMesh: not built yet");
+	return -1;
+}
+
+extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex, int userIndex)
+{
+	(void)userIndex;
+	if (!w || !position || !orientation) return -1;
+	if (collidableIndex < 0 || collidableIndex >= (int)w->collidables.size())
+	{
+		setLastError("registerPhysicsInstance using invalid collidableIndex");
+		return -1;
+	}
+	if ((int)w->bodies.size() >= w->cfg.maxConvexBodies)
+	{
+		setLastError("registerRigidBody: exceeding the number of rigid bodies, %d > %d", (int)w->bodies.size(), w->cfg.maxConvexBodies);
+		return -1;
+	}
+	const b3b200_aabb& la = w->localAabbs[collidableIndex];
+	float aabbMin[3], aabbMax[3];
+	transformAabbHost(la.min, la.max, 0.01f, position, orientation, aabbMin, aabbMax);
+	// b3GpuNarrowPhase::registerRigidBody (b3GpuNarrowPhase.cpp:816-908)
+	b3b200_rigid_body b;
+	memset(&b, 0, sizeof(b));
+	b.friction = 1.f;
+	b.restitution = 0.f;
+	b.pos.x = position[0];
+	b.pos.y = position[1];
+	b.pos.z = position[2];
+	b.quat.x = orientation[0];
+	b.quat.y = orientation[1];
+	b.quat.z = orientation[2];
+	b.quat.w = orientation[3];
+	b.collidableIdx = collidableIndex;
+	b.invMass = mass ? 1.f / mass : 0.f;
+	int bodyIndex = (int)w->bodies.size();
+	w->bodies.push_back(b);
+	w->inertias.push_back(b3b200_inertia());
+	if (mass == 0.f && bodyIndex == 0) w->static0Index = 0;
+	initInertia(w, bodyIndex, mass, aabbMin, aabbMax);
+	// createProxy / createLargeProxy (b3GpuRigidBodyPipeline.cpp:648-657)
+	int r = w->bp.createProxy(aabbMin, aabbMax, bodyIndex, mass == 0.f);
+	if (r < 0)
+	{
+		w->bodies.pop_back();
+		w->inertias.pop_back();
+		return -1;
+	}
+	w->uploaded = false;
+	return bodyIndex;
+}
+
+extern "C" int b3b200_upload(b3b200_world* w)
+{
+	W_CHECK(w);
+	cudaStream_t s = w->stream;
+	B3_CUDA_CHECK(cudaStreamSynchronize(s));
+	w->numBodies = (int)w->bodies.size();
+	const size_t nb = std::max(w->numBodies, 1);
+	B3_TRY(uploadVec(w->dCollidables, w->collidables, 0, s));
+	B3_TRY(uploadVec(w->dLocalAabbs, w->localAabbs, 0, s));
+	B3_TRY(uploadVec(w->dConvex, w->convex, 0, s));
+	B3_TRY(uploadVec(w->dVertices, w->vertices, 0, s));
+	B3_TRY(uploadVec(w->dUniqueEdges, w->uniqueEdges, 0, s));
+	B3_TRY(uploadVec(w->dFaces, w->faces, 0, s));
+	B3_TRY(uploadVec(w->dIndices, w->indices, 0, s));
+	B3_TRY(uploadVec(w->dChildShapes, w->childShapes, 0, s));
+	B3_TRY(uploadVec(w->dBvhInfos, w->bvhInfos, 0, s));
+	B3_TRY(uploadVec(w->dBvhNodes, w->bvhNodes, 0, s));
+	B3_TRY(uploadVec(w->dBvhSubtrees, w->bvhSubtrees, 0, s));
+	B3_TRY(uploadVec(w->dBodiesAoS, w->bodies, 0, s));
+	B3_TRY(uploadVec(w->dInertias, w->inertias, 0, s));
+	B3_TRY(w->dPose.reserve(2 * nb));
+	B3_TRY(w->dVel.reserve(2 * nb));
+	B3_TRY(w->dCollidableIdx.reserve(nb));
+	const size_t nc = std::max(w->cfg.maxContactCapacity, 1);
+	B3_TRY(w->dContacts.reserve(nc));
+	B3_TRY(w->dConstraints.reserve(nc));
+	B3_TRY(w->dContactColour.reserve(nc));
+	B3_TRY(w->dBodyMask.reserve(2 * nb));
+	B3_TRY(w->dBodyPrio.reserve(2 * nb));
+	B3_TRY(w->dBatchCount.reserve(MAX_BATCHES + 1));
+	B3_TRY(w->dBatchOffset.reserve(MAX_BATCHES + 1));
+	B3_TRY(w->dBatchCursor.reserve(MAX_BATCHES + 1));
+	B3_TRY(w->dBodyCount.reserve(std::max(nb, (size_t)1024)));
+	B3_TRY(w->bp.writeAabbs());
+	B3_TRY(launchPackSoA(w));
+	B3_CUDA_CHECK(cudaStreamSynchronize(s));
+	w->uploaded = true;
+	w->aabbsValid = false;
+	w->soaDirty = false;
+	return 0;
+}
+
+extern "C" int b3b200_set_gravity(b3b200_world* w, const float* g)
+{
+	if (!w || !g) return B3B200_ERR_INVALID;
+	w->gravity[0] = g[0];
+	w->gravity[1] = g[1];
+	w->gravity[2] = g[2];
+	return 0;
+}
+extern "C" int b3b200_set_solver(b3b200_world* w, int kind, int iterations)
+{
+	if (!w || iterations < 0 || (kind != B3B200_SOLVER_PGS && kind != B3B200_SOLVER_JACOBI)) return B3B200_ERR_INVALID;
+	w->solverKind = kind;
+	w->solverIterations = iterations;
+	return 0;
+}
+extern "C" int b3b200_set_broadphase(b3b200_world* w, int kind)
+{
+	if (!w || (kind != B3B200_BP_SAP && kind != B3B200_BP_GRID)) return B3B200_ERR_INVALID;
+	w->bp.kind = kind;
+	return 0;
+}
+extern "C" int b3b200_set_contact_clip(b3b200_world* w, float minDist, float maxDist)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->clipMinDist = minDist;
+	w->clipMaxDist = maxDist;
+	return 0;
+}
+extern "C" int b3b200_set_angular_damping(b3b200_world* w, float d)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->angularDamping = d;
+	return 0;
+}
+
+extern "C" int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src, int n)
+{
+	W_UPLOADED(w);
+	if (!src || n != w->numBodies) return B3B200_ERR_INVALID;
+	memcpy(w->bodies.data(), src, sizeof(b3b200_rigid_body) * n);
+	B3_CUDA_CHECK(cudaMemcpyAsync(w->dBodiesAoS.ptr, src, sizeof(b3b200_rigid_body) * n, cudaMemcpyHostToDevice, w->stream));
+	B3_TRY(launchPackSoA(w));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	w->aabbsValid = false;
+	return 0;
+}
+
+extern "C" int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, int n)
+{
+	W_UPLOADED(w);
+	if (!dst || n < 0 || n > w->numBodies) return B3B200_ERR_INVALID;
+	B3_TRY(syncAoS(w));
+	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * n, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+extern "C" int b3b200_readback_inertias(b3b200_world* w, b3b200_inertia* dst, int n)
+{
+	W_UPLOADED(w);
+	if (!dst || n < 0 || n > w->numBodies) return B3B200_ERR_INVALID;
+	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dInertias.ptr, sizeof(b3b200_inertia) * n, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+extern "C" int b3b200_num_bodies(b3b200_world* w) { return w ? (int)w->bodies.size() : B3B200_ERR_INVALID; }
+
+extern "C" int b3b200_step(b3b200_world* w, float dt)
+{
+	W_UPLOADED(w);
+	B3_TRY(stepOnce(w, dt));
+	if (w->timing)
+	{
+		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+		for (int i = 0; i < 6; i++) cudaEventElapsedTime(&w->stageMs[i], w->ev[i], w->ev[i + 1]);
+		cudaEventElapsedTime(&w->stageMs[6], w->ev[0], w->ev[6]);
+	}
+	return 0;
+}
+extern "C" int b3b200_step_n(b3b200_world* w, float dt, int n)
+{
+	W_UPLOADED(w);
+	for (int i = 0; i < n; i++) B3_TRY(stepOnce(w, dt));
+	return 0;
+}
+extern "C" int b3b200_synchronize(b3b200_world* w)
+{
+	W_CHECK(w);
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+
+extern "C" int b3b200_update_aabbs(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	return launchUpdateAabbs(w);
+}
+extern "C" int b3b200_find_pairs(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	return w->bp.calculatePairs(w->cfg.maxBroadphasePairs);
+}
+extern "C" int b3b200_compute_contacts(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	return launchNarrowphase(w);
+}
+extern "C" int b3b200_solver_setup(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	return launchSolverSetup(w);
+}
+extern "C" int b3b200_solver_iterate(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	return launchSolverIterate(w);
+}
+extern "C" int b3b200_solve_contacts(b3b200_world* w)
+{
+	W_UPLOADED(w);
+	if (w->solverKind == B3B200_SOLVER_JACOBI) return launchJacobi(w);
+	B3_TRY(launchSolverSetup(w));
+	return launchSolverIterate(w);
+}
+extern "C" int b3b200_integrate(b3b200_world* w, float dt)
+{
+	W_UPLOADED(w);
+	return launchIntegrate(w, dt, false);
+}
+
+static int readCounters(World* w, unsigned int* c)
+{
+	B3_CUDA_CHECK(cudaMemcpyAsync(c, w->dCounters.ptr, sizeof(unsigned int) * CTR_COUNT, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+
+extern "C" int b3b200_get_aabbs(b3b200_world* w, b3b200_aabb* dst, int n)
+{
+	W_UPLOADED(w);
+	if (!dst || n < 0 || n > w->numBodies) return B3B200_ERR_INVALID;
+	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->bp.aabbs.ptr, sizeof(b3b200_aabb) * n, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+extern "C" int b3b200_get_pairs(b3b200_world* w, b3b200_int4* dst, int capacity, int* numPairs)
+{
+	W_UPLOADED(w);
+	if (!numPairs || capacity < 0) return B3B200_ERR_INVALID;
+	unsigned int c[CTR_COUNT];
+	B3_TRY(readCounters(w, c));
+	*numPairs = (int)c[CTR_PAIRS];
+	int m = std::min((int)c[CTR_PAIRS], capacity);
+	if (m > 0 && dst)
+	{
+		B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->bp.pairs.ptr, sizeof(b3b200_int4) * m, cudaMemcpyDeviceToHost, w->stream));
+		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	}
+	return 0;
+}
+extern "C" int b3b200_get_contacts(b3b200_world* w, b3b200_contact4* dst, int capacity, int* numContacts)
+{
+	W_UPLOADED(w);
+	if (!numContacts || capacity < 0) return B3B200_ERR_INVALID;
+	unsigned int c[CTR_COUNT];
+	B3_TRY(readCounters(w, c));
+	*numContacts = (int)c[CTR_CONTACTS];
+	int m = std::min((int)c[CTR_CONTACTS], capacity);
+	if (m > 0 && dst)
+	{
+		B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dContacts.ptr, sizeof(b3b200_contact4) * m, cudaMemcpyDeviceToHost, w->stream));
+		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	}
+	return 0;
+}
+extern "C" int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numContacts)
+{
+	W_UPLOADED(w);
+	if (numContacts < 0 || numContacts > w->cfg.maxContactCapacity || (numContacts > 0 && !src)) return B3B200_ERR_INVALID;
+	if (numContacts) B3_CUDA_CHECK(cudaMemcpyAsync(w->dContacts.ptr, src, sizeof(b3b200_contact4) * numContacts, cudaMemcpyHostToDevice, w->stream));
+	unsigned int n = (unsigned int)numContacts;
+	B3_CUDA_CHECK(cudaMemcpyAsync(&w->dCounters.ptr[CTR_CONTACTS], &n, sizeof(n), cudaMemcpyHostToDevice, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+extern "C" int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, int capacity, int* numConstraints)
+{
+	W_UPLOADED(w);
+	if (!numConstraints || capacity < 0) return B3B200_ERR_INVALID;
+	unsigned int off[MAX_BATCHES + 1];
+	B3_CUDA_CHECK(cudaMemcpyAsync(off, w->dBatchOffset.ptr, sizeof(off), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	int n = (int)off[MAX_BATCHES];
+	*numConstraints = n;
+	int m = std::min(n, capacity);
+	if (m > 0 && dst)
+	{
+		B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dConstraints.ptr, sizeof(b3b200_constraint4) * m, cudaMemcpyDeviceToHost, w->stream));
+		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	}
+	return 0;
+}
+extern "C" int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches)
+{
+	W_UPLOADED(w);
+	if (!numBatches || capacity < 0) return B3B200_ERR_INVALID;
+	unsigned int c[CTR_COUNT];
+	B3_TRY(readCounters(w, c));
+	unsigned int off[MAX_BATCHES + 1];
+	B3_CUDA_CHECK(cudaMemcpyAsync(off, w->dBatchOffset.ptr, sizeof(off), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	int nb = (int)c[CTR_BATCHES];
+	*numBatches = nb;
+	if (batchOffsets)
+		for (int i = 0; i <= nb && i < capacity; i++) batchOffsets[i] = (i == nb) ? (int)off[MAX_BATCHES] : (int)off[i];
+	return 0;
+}
+extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)
+{
+	W_CHECK(w);
+	if (!dst8) return B3B200_ERR_INVALID;
+	unsigned int c[CTR_COUNT];
+	B3_TRY(readCounters(w, c));
+	for (int i = 0; i < 8; i++) dst8[i] = (int)c[i];
+	return 0;
+}
+extern "C" int b3b200_enable_stage_timing(b3b200_world* w, int enable)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->timing = enable != 0;
+	return 0;
+}
+extern "C" int b3b200_stage_timings(b3b200_world* w, float* ms8)
+{
+	if (!w || !ms8) return B3B200_ERR_INVALID;
+	for (int i = 0; i < 8; i++) ms8[i] = w->stageMs[i];
+	return 0;
+}
+extern "C" int b3b200_device_buffer(b3b200_world* w, int which, void** p)
+{
+	W_UPLOADED(w);
+	if (!p) return B3B200_ERR_INVALID;
+	switch (which)
+	{
+		case B3B200_BUF_BODIES:
+			B3_TRY(syncAoS(w));
+			*p = w->dBodiesAoS.ptr;
+			return 0;
+		case B3B200_BUF_AABBS:
+			*p = w->bp.aabbs.ptr;
+			return 0;
+		case B3B200_BUF_PAIRS:
+			*p = w->bp.pairs.ptr;
+			return 0;
+		case B3B200_BUF_CONTACTS:
+			*p = w->dContacts.ptr;
+			return 0;
+		case B3B200_BUF_INERTIAS:
+			*p = w->dInertias.ptr;
+			return 0;
+	}
+	return B3B200_ERR_INVALID;
+}

@@ -1,0 +1,179 @@
+/*
+ * b3b200.h -- C ABI of the B200-native GPU rigid-body step.
+ *
+ * This is the drop-in boundary underneath the reference's C++ class surface
+ * (src/Bullet3OpenCL).  The reference has no FFI layer of its own: callers use
+ * the classes directly (examples/OpenCL/rigidbody/GpuRigidBodyDemo.cpp:129-150,
+ * examples/OpenCL/broadphase/PairBench.cpp:208-379).  The same-named C++
+ * classes under bullet3_b200/csrc/host/ forward to the entry points below, and
+ * each entry point cites the reference method it replaces.
+ *
+ * Conventions: every function returns an int.  Functions that create an index
+ * return the index (>= 0) or -1 on failure, like the reference's register*
+ * methods (b3GpuNarrowPhase.cpp:144-157, 821-825).  All other functions return
+ * 0 on success and a negative B3B200_ERR_* code on failure.  Nothing throws or
+ * aborts; the text of the last failure is available from b3b200_last_error().
+ * All pointers are HOST pointers unless the name says "device".
+ * A world is bound to one device + one stream; worlds are independent of each
+ * other (re-entrant across worlds, not thread-safe per world).
+ */
+#ifndef B3B200_H
+#define B3B200_H
+
+#include "b3b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B3B200_OK 0
+#define B3B200_ERR_INVALID -1  /* bad argument / bad index */
+#define B3B200_ERR_CAPACITY -2 /* a b3Config capacity would be exceeded */
+#define B3B200_ERR_CUDA -3     /* CUDA runtime failure (see b3b200_last_error) */
+#define B3B200_ERR_STATE -4    /* call order violated (e.g. step before upload) */
+
+typedef struct b3b200_world b3b200_world;
+typedef struct b3b200_broadphase b3b200_broadphase;
+
+/* broadphase kinds: b3GpuSapBroadphase (b3GpuSapBroadphase.h:14-141) and
+ * b3GpuGridBroadphase (b3GpuGridBroadphase.h:7-78). */
+#define B3B200_BP_SAP 0
+#define B3B200_BP_GRID 1
+/* contact solver kinds: b3GpuPgsContactSolver (default, b3GpuRigidBodyPipeline.cpp:449)
+ * and b3GpuJacobiContactSolver (gUseJacobi, :389-447). */
+#define B3B200_SOLVER_PGS 0
+#define B3B200_SOLVER_JACOBI 1
+
+const char* b3b200_last_error(void);
+int b3b200_version(void);
+/* number of kernel launches issued by this library since load (all worlds) */
+long long b3b200_launch_count(void);
+
+/* b3Config::b3Config() defaults (b3Config.h:19-36) */
+int b3b200_config_default(b3b200_config* cfg);
+
+/* ------------------------------------------------------------------ world */
+/* replaces: new b3GpuNarrowPhase + new b3Gpu{Sap,Grid}Broadphase + new b3GpuRigidBodyPipeline
+ * (GpuRigidBodyDemo.cpp:129-146; b3GpuRigidBodyPipeline.cpp:65-114).
+ * `stream` is a cudaStream_t (0 = a private non-blocking stream is created). */
+int b3b200_create(const b3b200_config* cfg, int device, void* stream, b3b200_world** out);
+int b3b200_destroy(b3b200_world* w);
+/* b3GpuRigidBodyPipeline::reset + b3GpuNarrowPhase::reset (b3GpuRigidBodyPipeline.cpp:141-150) */
+int b3b200_reset(b3b200_world* w);
+
+/* ---- shapes: b3GpuNarrowPhase::register*Shape (b3GpuNarrowPhase.cpp:159-668) ---- */
+/* registerConvexHullShape(b3ConvexUtility*) :321-368 -- a ready polyhedron.
+ * `poly` supplies localCenter/extents/mC/mE/radius; its offsets/counts are ignored. */
+int b3b200_register_convex(b3b200_world* w,
+						   const b3b200_float4* vertices, int numVertices,
+						   const b3b200_face* faces, int numFaces,
+						   const int* indices, int numIndices,
+						   const b3b200_float4* uniqueEdges, int numUniqueEdges,
+						   const b3b200_convex_polyhedron* poly);
+/* registerConvexHullShape(const float*, stride, n, scaling) :298-319 -- builds the hull */
+int b3b200_register_convex_points(b3b200_world* w, const float* vertices, int strideInBytes,
+								  int numVertices, const float* scaling3);
+/* registerPlaneShape :196-231, registerSphereShape :159-194 */
+int b3b200_register_plane(b3b200_world* w, const float* normal3, float planeConstant);
+int b3b200_register_sphere(b3b200_world* w, float radius);
+/* registerCompoundShape :370-474 -- children reference convex collidables via shapeIndex */
+int b3b200_register_compound(b3b200_world* w, const b3b200_child_shape* children, int numChildren);
+/* registerConcaveMesh :476-498 */
+int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVertices,
+							const int* triIndices, int numIndices, const float* scaling3);
+
+/* ---- bodies ---- */
+/* b3GpuRigidBodyPipeline::registerPhysicsInstance (b3GpuRigidBodyPipeline.cpp:603-669):
+ * world AABB with margin 0.01, registerRigidBody, createProxy / createLargeProxy. */
+int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
+							 const float* orientation, int collidableIndex, int userIndex);
+/* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150) */
+int b3b200_upload(b3b200_world* w);
+/* b3GpuRigidBodyPipeline::setGravity (b3GpuRigidBodyPipeline.cpp:562-565) */
+int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
+int b3b200_set_solver(b3b200_world* w, int kind, int iterations);
+int b3b200_set_broadphase(b3b200_world* w, int kind);
+/* clip window of the convex-convex clipper: the reference kernels use
+ * (-1e30, 0.02) (satClipHullContacts.cl:916-917), the shared CPU header (-1, 0)
+ * (b3ContactConvexConvexSAT.h:320-321).  Default = the kernel constants. */
+int b3b200_set_contact_clip(b3b200_world* w, float minDist, float maxDist);
+int b3b200_set_angular_damping(b3b200_world* w, float damping);
+
+/* overwrite / read the body state (b3RigidBodyData AoS, 80 B each) */
+int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src, int n);
+/* b3GpuNarrowPhase::readbackAllBodiesToCpu + getBodiesCpu (b3GpuNarrowPhase.cpp:965-968, 676-679) */
+int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, int n);
+int b3b200_readback_inertias(b3b200_world* w, b3b200_inertia* dst, int n);
+int b3b200_num_bodies(b3b200_world* w);
+
+/* ---- the step: b3GpuRigidBodyPipeline::stepSimulation (b3GpuRigidBodyPipeline.cpp:221-463) ---- */
+int b3b200_step(b3b200_world* w, float dt);
+/* run `n` steps back to back with no host synchronisation in between */
+int b3b200_step_n(b3b200_world* w, float dt, int n);
+int b3b200_synchronize(b3b200_world* w);
+
+/* per-stage entry points (parity tests call these one at a time) */
+int b3b200_update_aabbs(b3b200_world* w);      /* setupGpuAabbsFull :500-560 */
+int b3b200_find_pairs(b3b200_world* w);        /* bp->calculateOverlappingPairs :260 */
+int b3b200_compute_contacts(b3b200_world* w);  /* np->computeContacts :324 */
+int b3b200_solve_contacts(b3b200_world* w);    /* m_solver2/3->solveContacts :389-460 */
+int b3b200_solver_setup(b3b200_world* w);      /* colouring + contact->constraint only */
+int b3b200_solver_iterate(b3b200_world* w);    /* the iteration loop only */
+int b3b200_integrate(b3b200_world* w, float dt); /* integrate :465-498 */
+
+/* results (device -> host copies; each synchronises the world's stream) */
+int b3b200_get_aabbs(b3b200_world* w, b3b200_aabb* dst, int n);
+int b3b200_get_pairs(b3b200_world* w, b3b200_int4* dst, int capacity, int* numPairs);
+int b3b200_get_contacts(b3b200_world* w, b3b200_contact4* dst, int capacity, int* numContacts);
+int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numContacts);
+/* constraints in solve order (sorted by batch); batchOffsets has numBatches+1 entries */
+int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, int capacity, int* numConstraints);
+int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches);
+/* counters of the last step: [0]=pairs [1]=contacts [2]=batches [3]=colouring rounds
+ * [4]=overflow flags [5]=compound pairs [6]=concave pairs [7]=reserved */
+int b3b200_get_counters(b3b200_world* w, int* dst8);
+/* ms per stage of the last step when timing is enabled:
+ * [0]=aabbs [1]=broadphase [2]=narrowphase [3]=solver setup [4]=solver iterations [5]=integrate [6]=total */
+int b3b200_enable_stage_timing(b3b200_world* w, int enable);
+int b3b200_stage_timings(b3b200_world* w, float* ms8);
+
+/* device pointers with the reference AoS layouts: getBodyBuffer(), getAabbBufferWS(),
+ * getOverlappingPairBuffer(), getContactsGpu() (b3GpuRigidBodyPipeline.cpp:577,
+ * b3GpuBroadphaseInterface.h:29-31, b3GpuNarrowPhase.cpp:713-721) */
+#define B3B200_BUF_BODIES 0
+#define B3B200_BUF_AABBS 1
+#define B3B200_BUF_PAIRS 2
+#define B3B200_BUF_CONTACTS 3
+#define B3B200_BUF_INERTIAS 4
+int b3b200_device_buffer(b3b200_world* w, int which, void** devicePtr);
+
+/* ------------------------------------------------- stand-alone broadphase */
+/* b3GpuBroadphaseInterface (b3GpuBroadphaseInterface.h:12-40) as used by PairBench.cpp:208-379 */
+int b3b200_bp_create(int kind, int device, void* stream, int maxProxies, int maxPairs, b3b200_broadphase** out);
+int b3b200_bp_destroy(b3b200_broadphase* bp);
+int b3b200_bp_create_proxy(b3b200_broadphase* bp, const float* aabbMin3, const float* aabbMax3, int userPtr);
+int b3b200_bp_create_large_proxy(b3b200_broadphase* bp, const float* aabbMin3, const float* aabbMax3, int userPtr);
+int b3b200_bp_write_aabbs(b3b200_broadphase* bp);                       /* writeAabbsToGpu */
+int b3b200_bp_set_aabbs(b3b200_broadphase* bp, const b3b200_aabb* aabbs, int n); /* overwrite all AABBs (host) */
+int b3b200_bp_calculate_pairs(b3b200_broadphase* bp, int maxPairs);     /* calculateOverlappingPairs */
+int b3b200_bp_num_overlap(b3b200_broadphase* bp);                       /* getNumOverlap */
+int b3b200_bp_get_pairs(b3b200_broadphase* bp, b3b200_int4* dst, int capacity, int* numPairs);
+int b3b200_bp_device_pairs(b3b200_broadphase* bp, void** devicePtr);    /* getOverlappingPairBuffer */
+int b3b200_bp_device_aabbs(b3b200_broadphase* bp, void** devicePtr);    /* getAabbBufferWS */
+int b3b200_bp_last_ms(b3b200_broadphase* bp, float* ms);
+
+/* ------------------------------------------------- parallel primitives */
+/* b3RadixSort32CL::execute (b3RadixSort32CL.cpp:12-646): stable LSD sort of
+ * b3SortData{key,value} by key; b3PrefixScanCL::execute (b3PrefixScanCL.cpp:45-119):
+ * exclusive u32 scan, returns the total in *sum;
+ * b3BoundSearchCL::execute COUNT (b3BoundSearchCL.cpp:74-203); b3FillCL (b3FillCL.cpp:41-119). */
+int b3b200_radix_sort_kv(int device, b3b200_sort_data* data, int n);
+int b3b200_radix_sort_keys(int device, unsigned int* keys, int n);
+int b3b200_prefix_scan_u32(int device, const unsigned int* src, unsigned int* dst, int n, unsigned int* sum);
+int b3b200_bound_search_count(int device, const b3b200_sort_data* sorted, int n, unsigned int* counts, int numBuckets);
+int b3b200_fill_u32(int device, unsigned int* dst, unsigned int value, int n, int offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B3B200_H */

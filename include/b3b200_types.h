@@ -1,0 +1,248 @@
+/*
+ * b3b200_types.h -- plain-C POD mirror of the Bullet3 GPU rigid-body ABI.
+ *
+ * Every struct here has the same size and field offsets as the reference
+ * struct it names (verified by the static asserts at the bottom and by
+ * tests/test_abi.py).  The C++ drop-in headers under
+ * bullet3_b200/csrc/host/ typedef these to the reference names.
+ *
+ * Reference layouts (paths relative to the bullet3 tree):
+ *   b3RigidBodyData / b3InertiaData  src/Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h:10-29
+ *   b3Collidable / b3GpuChildShape   src/Bullet3Collision/NarrowPhaseCollision/shared/b3Collidable.h:8-66
+ *   b3ConvexPolyhedronData/b3GpuFace src/Bullet3Collision/NarrowPhaseCollision/shared/b3ConvexPolyhedronData.h:9-34
+ *   b3Aabb / b3SapAabb               src/Bullet3Collision/BroadPhaseCollision/shared/b3Aabb.h:10-22
+ *   b3Int4 (b3BroadphasePair)        src/Bullet3Common/shared/b3Int4.h
+ *   b3Contact4Data                   src/Bullet3Collision/NarrowPhaseCollision/shared/b3Contact4Data.h:8-34
+ *   b3ContactConstraint4             src/Bullet3Dynamics/shared/b3ContactConstraint4.h:8-29
+ *   b3Config                         src/Bullet3Collision/NarrowPhaseCollision/b3Config.h:4-37
+ *   b3QuantizedBvhNodeData           src/Bullet3Collision/NarrowPhaseCollision/shared/b3QuantizedBvhNodeData.h:14-40
+ *   b3BvhSubtreeInfoData             src/Bullet3Collision/NarrowPhaseCollision/shared/b3BvhSubtreeInfoData.h
+ *   b3BvhInfo                        src/Bullet3OpenCL/NarrowphaseCollision/b3BvhInfo.h:6-15
+ */
+#ifndef B3B200_TYPES_H
+#define B3B200_TYPES_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define B3B200_ALIGN16 alignas(16)
+#else
+#define B3B200_ALIGN16 _Alignas(16)
+#endif
+
+typedef struct B3B200_ALIGN16 b3b200_float4
+{
+	float x, y, z, w;
+} b3b200_float4;
+
+typedef struct B3B200_ALIGN16 b3b200_int4
+{
+	int x, y, z, w;
+} b3b200_int4;
+
+typedef struct B3B200_ALIGN16 b3b200_mat3x3
+{
+	b3b200_float4 row[3];
+} b3b200_mat3x3;
+
+enum b3b200_shape_type
+{
+	B3B200_SHAPE_HEIGHT_FIELD = 1,
+	B3B200_SHAPE_CONVEX_HULL = 3,
+	B3B200_SHAPE_PLANE = 4,
+	B3B200_SHAPE_CONCAVE_TRIMESH = 5,
+	B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS = 6,
+	B3B200_SHAPE_SPHERE = 7
+};
+
+typedef struct B3B200_ALIGN16 b3b200_rigid_body
+{
+	b3b200_float4 pos;
+	b3b200_float4 quat;
+	b3b200_float4 linVel;
+	b3b200_float4 angVel;
+	int collidableIdx;
+	float invMass;
+	float restitution;
+	float friction;
+} b3b200_rigid_body;
+
+typedef struct B3B200_ALIGN16 b3b200_inertia
+{
+	b3b200_mat3x3 invInertiaWorld;
+	b3b200_mat3x3 initInvInertia;
+} b3b200_inertia;
+
+typedef struct b3b200_collidable
+{
+	union {
+		int numChildShapes;
+		int bvhIndex;
+	};
+	union {
+		float radius;
+		int compoundBvhIndex;
+	};
+	int shapeType;
+	union {
+		int shapeIndex;
+		float height;
+	};
+} b3b200_collidable;
+
+typedef struct B3B200_ALIGN16 b3b200_child_shape
+{
+	b3b200_float4 childPosition;
+	b3b200_float4 childOrientation;
+	union {
+		int shapeIndex;
+		int capsuleAxis;
+	};
+	union {
+		float radius;
+		int numChildShapes;
+	};
+	union {
+		float height;
+		int collidableShapeIndex;
+	};
+	int shapeType;
+} b3b200_child_shape;
+
+typedef struct B3B200_ALIGN16 b3b200_face
+{
+	b3b200_float4 plane;
+	int indexOffset;
+	int numIndices;
+	int pad1;
+	int pad2;
+} b3b200_face;
+
+typedef struct B3B200_ALIGN16 b3b200_convex_polyhedron
+{
+	b3b200_float4 localCenter;
+	b3b200_float4 extents;
+	b3b200_float4 mC;
+	b3b200_float4 mE;
+	float radius;
+	int faceOffset;
+	int numFaces;
+	int numVertices;
+	int vertexOffset;
+	int uniqueEdgesOffset;
+	int numUniqueEdges;
+	int unused;
+} b3b200_convex_polyhedron;
+
+typedef struct B3B200_ALIGN16 b3b200_aabb
+{
+	union {
+		float min[4];
+		int minIndices[4];
+	};
+	union {
+		float max[4];
+		int signedMaxIndices[4];
+	};
+} b3b200_aabb;
+
+typedef struct B3B200_ALIGN16 b3b200_contact4
+{
+	b3b200_float4 worldPosB[4]; /* xyz = point on B, w = depth */
+	b3b200_float4 worldNormalOnB; /* w = number of points (as float) */
+	unsigned short restitutionCmp;
+	unsigned short frictionCmp;
+	int batchIdx;
+	int bodyAPtrAndSignBit;
+	int bodyBPtrAndSignBit;
+	int childIndexA;
+	int childIndexB;
+	int unused1;
+	int unused2;
+} b3b200_contact4;
+
+typedef struct B3B200_ALIGN16 b3b200_constraint4
+{
+	b3b200_float4 linear; /* normal, w = friction coefficient */
+	b3b200_float4 worldPos[4];
+	b3b200_float4 center;
+	float jacCoeffInv[4];
+	float b[4];
+	float appliedRambdaDt[4];
+	float fJacCoeffInv[2];
+	float fAppliedRambdaDt[2];
+	unsigned int bodyA;
+	unsigned int bodyB;
+	int batchIdx;
+	unsigned int paddings;
+} b3b200_constraint4;
+
+typedef struct b3b200_config
+{
+	int maxConvexBodies;
+	int maxConvexShapes;
+	int maxBroadphasePairs;
+	int maxContactCapacity;
+	int compoundPairCapacity;
+	int maxVerticesPerFace;
+	int maxFacesPerShape;
+	int maxConvexVertices;
+	int maxConvexIndices;
+	int maxConvexUniqueEdges;
+	int maxCompoundChildShapes;
+	int maxTriConvexPairCapacity;
+} b3b200_config;
+
+typedef struct b3b200_bvh_node
+{
+	unsigned short quantizedAabbMin[3];
+	unsigned short quantizedAabbMax[3];
+	int escapeIndexOrTriangleIndex;
+} b3b200_bvh_node;
+
+typedef struct b3b200_bvh_subtree
+{
+	unsigned short quantizedAabbMin[3];
+	unsigned short quantizedAabbMax[3];
+	int rootNodeIndex;
+	int subtreeSize;
+	int padding[3];
+} b3b200_bvh_subtree;
+
+typedef struct B3B200_ALIGN16 b3b200_bvh_info
+{
+	b3b200_float4 aabbMin;
+	b3b200_float4 aabbMax;
+	b3b200_float4 quantization;
+	int numNodes;
+	int numSubTrees;
+	int nodeOffset;
+	int subTreeOffset;
+} b3b200_bvh_info;
+
+typedef struct b3b200_sort_data
+{
+	unsigned int key;
+	unsigned int value;
+} b3b200_sort_data;
+
+#ifdef __cplusplus
+static_assert(sizeof(b3b200_float4) == 16, "abi");
+static_assert(sizeof(b3b200_rigid_body) == 80, "abi");
+static_assert(sizeof(b3b200_inertia) == 96, "abi");
+static_assert(sizeof(b3b200_collidable) == 16, "abi");
+static_assert(sizeof(b3b200_child_shape) == 48, "abi");
+static_assert(sizeof(b3b200_face) == 32, "abi");
+static_assert(sizeof(b3b200_convex_polyhedron) == 96, "abi");
+static_assert(sizeof(b3b200_aabb) == 32, "abi");
+static_assert(sizeof(b3b200_int4) == 16, "abi");
+static_assert(sizeof(b3b200_contact4) == 112, "abi");
+static_assert(sizeof(b3b200_constraint4) == 176, "abi");
+static_assert(sizeof(b3b200_config) == 48, "abi");
+static_assert(sizeof(b3b200_bvh_node) == 16, "abi");
+static_assert(sizeof(b3b200_bvh_subtree) == 32, "abi");
+static_assert(sizeof(b3b200_bvh_info) == 64, "abi");
+static_assert(sizeof(b3b200_sort_data) == 8, "abi");
+#endif
+
+#endif /* B3B200_TYPES_H */
