@@ -156,6 +156,53 @@ B3_HD Mat3 matFromQuat(const float4& q)
 	m.r2 = mk4(xz - wy, yz + wx, 1.0f - (xx + yy), 0.f);
 	return m;
 }
+// b3Matrix3x3::getRotation scalar path (b3Matrix3x3.h:462-490)
+B3_HD float4 quatFromMat(const Mat3& m)
+{
+	const float el[3][3] = {{m.r0.x, m.r0.y, m.r0.z}, {m.r1.x, m.r1.y, m.r1.z}, {m.r2.x, m.r2.y, m.r2.z}};
+	float trace = el[0][0] + el[1][1] + el[2][2];
+	float t0, t1, t2, t3;
+	if (trace > 0.0f)
+	{
+		float s = sqrtf(trace + 1.0f);
+		t3 = (s * 0.5f);
+		s = 0.5f / s;
+		t0 = ((el[2][1] - el[1][2]) * s);
+		t1 = ((el[0][2] - el[2][0]) * s);
+		t2 = ((el[1][0] - el[0][1]) * s);
+	}
+	else if (el[0][0] < el[1][1] ? !(el[1][1] < el[2][2]) : false)
+	{
+		// i = 1, j = 2, k = 0
+		float s = sqrtf(el[1][1] - el[2][2] - el[0][0] + 1.0f);
+		t1 = s * 0.5f;
+		s = 0.5f / s;
+		t3 = (el[0][2] - el[2][0]) * s;
+		t2 = (el[2][1] + el[1][2]) * s;
+		t0 = (el[0][1] + el[1][0]) * s;
+	}
+	else if (el[0][0] < el[1][1] ? true : (el[0][0] < el[2][2]))
+	{
+		// i = 2, j = 0, k = 1
+		float s = sqrtf(el[2][2] - el[0][0] - el[1][1] + 1.0f);
+		t2 = s * 0.5f;
+		s = 0.5f / s;
+		t3 = (el[1][0] - el[0][1]) * s;
+		t0 = (el[0][2] + el[2][0]) * s;
+		t1 = (el[1][2] + el[2][1]) * s;
+	}
+	else
+	{
+		// i = 0, j = 1, k = 2
+		float s = sqrtf(el[0][0] - el[1][1] - el[2][2] + 1.0f);
+		t0 = s * 0.5f;
+		s = 0.5f / s;
+		t3 = (el[2][1] - el[1][2]) * s;
+		t1 = (el[1][0] + el[0][1]) * s;
+		t2 = (el[2][0] + el[0][2]) * s;
+	}
+	return mk4(t0, t1, t2, t3);
+}
 B3_HD float4 matMulVec(const Mat3& m, const float4& v)
 {
 	return mk4(dot3(m.r0, v), dot3(m.r1, v), dot3(m.r2, v), 0.f);

@@ -254,6 +254,12 @@ B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB,
 	float4 sep = mk4(__shfl_sync(FULL, bestAxis.x, src), __shfl_sync(FULL, bestAxis.y, src), __shfl_sync(FULL, bestAxis.z, src));
 	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
 
+	// b3ClipHullHullSingle round-trips both orientations through a b3Transform
+	// (setRotation -> getRotation, shared/b3ContactConvexConvexSAT.h:323-337); the
+	// clipper below sees those re-derived quaternions.
+	ornA = quatFromMat(matFromQuat(ornA));
+	ornB = quatFromMat(matFromQuat(ornB));
+
 	// ---- b3ClipHullAgainstHull: incident face of B = most aligned with sep
 	int closestFaceB = -1;
 	{

@@ -58,6 +58,7 @@ int World::init(const b3b200_config* c, int dev, cudaStream_t st)
 
 void World::destroy()
 {
+	if (device < 0) return;  // host-only world: nothing on a device
 	cudaSetDevice(device);
 	if (stream) cudaStreamSynchronize(stream);
 	for (int i = 0; i < 8; i++)
@@ -219,8 +220,13 @@ static int stepOnce(World* w, float dt)
 
 using namespace b3b200;
 
-#define W_CHECK(w)                         \
-	if (!(w)) return B3B200_ERR_INVALID;   \
+#define W_CHECK(w)                                                              \
+	if (!(w)) return B3B200_ERR_INVALID;                                        \
+	if ((w)->device < 0)                                                        \
+	{                                                                           \
+		setLastError("host-only world (device -1): no GPU work is possible");   \
+		return B3B200_ERR_STATE;                                                \
+	}                                                                           \
 	B3_CUDA_CHECK(cudaSetDevice((w)->device))
 #define W_UPLOADED(w)                                          \
 	W_CHECK(w);                                                \
@@ -256,6 +262,16 @@ extern "C" int b3b200_create(const b3b200_config* cfg, int device, void* stream,
 {
 	if (!cfg || !out) return B3B200_ERR_INVALID;
 	if (cfg->maxConvexBodies <= 0 || cfg->maxBroadphasePairs < 0 || cfg->maxContactCapacity < 0) return B3B200_ERR_INVALID;
+	if (device == -1)
+	{
+		// host-only world: shape/body registration and table queries work, nothing else does
+		b3b200_world* hw = new b3b200_world();
+		hw->cfg = *cfg;
+		hw->device = -1;
+		hw->bp.maxProxies = cfg->maxConvexBodies;
+		*out = hw;
+		return 0;
+	}
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
 	if (e != cudaSuccess || device < 0 || device >= count)
@@ -285,7 +301,7 @@ extern "C" int b3b200_destroy(b3b200_world* w)
 
 extern "C" int b3b200_reset(b3b200_world* w)
 {
-	W_CHECK(w);
+	if (!w) return B3B200_ERR_INVALID;
 	w->collidables.clear();
 	w->localAabbs.clear();
 	w->convex.clear();
@@ -781,6 +797,49 @@ extern "C" int b3b200_device_buffer(b3b200_world* w, int which, void** p)
 		case B3B200_BUF_INERTIAS:
 			*p = w->dInertias.ptr;
 			return 0;
+	}
+	return B3B200_ERR_INVALID;
+}
+
+template <typename T>
+static int copyTable(const std::vector<T>& v, void* dst, int capacity, int* count)
+{
+	*count = (int)v.size();
+	int m = std::min((int)v.size(), capacity);
+	if (dst && m > 0) memcpy(dst, v.data(), sizeof(T) * (size_t)m);
+	return 0;
+}
+extern "C" int b3b200_get_table(b3b200_world* w, int which, void* dst, int capacity, int* count)
+{
+	if (!w || !count || capacity < 0) return B3B200_ERR_INVALID;
+	switch (which)
+	{
+		case B3B200_TBL_COLLIDABLES:
+			return copyTable(w->collidables, dst, capacity, count);
+		case B3B200_TBL_LOCAL_AABBS:
+			return copyTable(w->localAabbs, dst, capacity, count);
+		case B3B200_TBL_CONVEX:
+			return copyTable(w->convex, dst, capacity, count);
+		case B3B200_TBL_VERTICES:
+			return copyTable(w->vertices, dst, capacity, count);
+		case B3B200_TBL_UNIQUE_EDGES:
+			return copyTable(w->uniqueEdges, dst, capacity, count);
+		case B3B200_TBL_FACES:
+			return copyTable(w->faces, dst, capacity, count);
+		case B3B200_TBL_INDICES:
+			return copyTable(w->indices, dst, capacity, count);
+		case B3B200_TBL_CHILD_SHAPES:
+			return copyTable(w->childShapes, dst, capacity, count);
+		case B3B200_TBL_BVH_INFOS:
+			return copyTable(w->bvhInfos, dst, capacity, count);
+		case B3B200_TBL_BVH_NODES:
+			return copyTable(w->bvhNodes, dst, capacity, count);
+		case B3B200_TBL_BVH_SUBTREES:
+			return copyTable(w->bvhSubtrees, dst, capacity, count);
+		case B3B200_TBL_BODIES:
+			return copyTable(w->bodies, dst, capacity, count);
+		case B3B200_TBL_INERTIAS:
+			return copyTable(w->inertias, dst, capacity, count);
 	}
 	return B3B200_ERR_INVALID;
 }

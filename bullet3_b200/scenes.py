@@ -1,0 +1,88 @@
+"""Headless restatements of the reference's demo scene recipes (BASELINE.json configs).
+
+Only the *recipes* (positions, shapes, counts) are restated; bodies are created
+through the C ABI exactly like examples/OpenCL/rigidbody/GpuConvexScene.cpp does
+through b3GpuNarrowPhase / b3GpuRigidBodyPipeline.
+"""
+import numpy as np
+
+IDENT = (0.0, 0.0, 0.0, 1.0)
+
+
+def box_points(hx, hy=None, hz=None):
+    hy = hx if hy is None else hy
+    hz = hx if hz is None else hz
+    return np.array([[sx * hx, sy * hy, sz * hz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float32)
+
+
+def tetra_points(scale=1.0):
+    # tetra_vertices of examples/OpenGLWindow/ShapeData.h:1034 (unit tetrahedron around the origin)
+    return np.array([[0.0, 1.0, 0.0], [1.0, -1.0, 1.0], [-1.0, -1.0, 1.0], [0.0, -1.0, -1.0]], np.float32) * np.float32(scale)
+
+
+def random_hull_points(rng, n, radius_lo=0.5, radius_hi=1.5):
+    """n points on a sphere of random radius (seeded hulls)."""
+    v = rng.normal(size=(n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    r = rng.uniform(radius_lo, radius_hi)
+    return (v * r).astype(np.float32)
+
+
+def random_quat(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return tuple(np.float32(q))
+
+
+def add_ground_box(world, half=400.0, y_top=0.0):
+    """static box like GpuConvexScene::createStaticEnvironment (GpuConvexScene.cpp:280-304)"""
+    col = world.register_convex_points(box_points(half))
+    return world.register_instance(0.0, (0.0, y_top - half, 0.0), IDENT, col)
+
+
+def box_stack(world, nx, ny, nz, half=0.5, spacing=1.0, y0=0.5, mass=1.0, ground=True):
+    """config 1: nx*ny*nz unit boxes at (i, 0.5+j, k) on a static 400-box"""
+    if ground:
+        add_ground_box(world)
+    col = world.register_convex_points(box_points(half))
+    for i in range(nx):
+        for j in range(ny):
+            for k in range(nz):
+                world.register_instance(mass, (i * spacing, y0 + j * spacing, k * spacing), IDENT, col)
+    return col
+
+
+def box_plane_scene(world, nx, ny, nz, ground=True):
+    """config 3: GpuBoxPlaneScene recipe (GpuConvexScene.cpp:163-278): cubes of half-extent 1,
+    pos = (((j+1)&1) + 2.2 i, 1 + 2 j, ((j+1)&1) + 2.2 k)"""
+    if ground:
+        add_ground_box(world)
+    col = world.register_convex_points(box_points(1.0))
+    for i in range(nx):
+        for j in range(ny):
+            for k in range(nz):
+                world.register_instance(1.0, (((j + 1) & 1) + 2.2 * i, 1.0 + 2.0 * j, ((j + 1) & 1) + 2.2 * k), IDENT, col)
+    return col
+
+
+def mixed_convex_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, rotate=True, ground=True, hull_verts=(8, 16)):
+    """config 4 (convex part): mix of tetrahedra, boxes and seeded random hulls dropped on a
+    static ground.  Shapes are instanced (a handful of collidables), bodies get seeded
+    random orientations.  Layout follows the config-3 grid with 2.8 spacing so that the
+    larger hulls start just short of touching."""
+    rng = np.random.default_rng(seed)
+    if ground:
+        add_ground_box(world)
+    shapes = [world.register_convex_points(box_points(1.0)), world.register_convex_points(tetra_points(1.0))]
+    for _ in range(num_hull_shapes):
+        n = int(rng.integers(hull_verts[0], hull_verts[1] + 1))
+        shapes.append(world.register_convex_points(random_hull_points(rng, n, 0.8, 1.3)))
+    kinds = rng.integers(0, len(shapes), size=nx * ny * nz)
+    t = 0
+    for i in range(nx):
+        for j in range(ny):
+            for k in range(nz):
+                q = random_quat(rng) if rotate else IDENT
+                world.register_instance(1.0, (2.8 * i, 1.5 + 2.8 * j, 2.8 * k), q, shapes[int(kinds[t])])
+                t += 1
+    return shapes

@@ -55,7 +55,10 @@ int b3b200_config_default(b3b200_config* cfg);
 /* ------------------------------------------------------------------ world */
 /* replaces: new b3GpuNarrowPhase + new b3Gpu{Sap,Grid}Broadphase + new b3GpuRigidBodyPipeline
  * (GpuRigidBodyDemo.cpp:129-146; b3GpuRigidBodyPipeline.cpp:65-114).
- * `stream` is a cudaStream_t (0 = a private non-blocking stream is created). */
+ * `stream` is a cudaStream_t (0 = a private non-blocking stream is created).
+ * device == -1 creates a HOST-ONLY world: shapes and bodies can be registered and the
+ * tables read back (b3b200_get_table), every call that needs the GPU fails with
+ * B3B200_ERR_STATE.  There is no CPU implementation of the step. */
 int b3b200_create(const b3b200_config* cfg, int device, void* stream, b3b200_world** out);
 int b3b200_destroy(b3b200_world* w);
 /* b3GpuRigidBodyPipeline::reset + b3GpuNarrowPhase::reset (b3GpuRigidBodyPipeline.cpp:141-150) */
@@ -146,6 +149,24 @@ int b3b200_stage_timings(b3b200_world* w, float* ms8);
 #define B3B200_BUF_CONTACTS 3
 #define B3B200_BUF_INERTIAS 4
 int b3b200_device_buffer(b3b200_world* w, int which, void** devicePtr);
+
+/* host-side shape / body tables (b3GpuNarrowPhase::getCollidablesCpu, getInternalData(),
+ * getLocalSpaceAabb: b3GpuNarrowPhase.cpp:676-749, 810-813).  Copies up to capacity
+ * elements into dst (may be NULL to query) and returns the element count in *count. */
+#define B3B200_TBL_COLLIDABLES 0  /* b3b200_collidable */
+#define B3B200_TBL_LOCAL_AABBS 1  /* b3b200_aabb, one per collidable */
+#define B3B200_TBL_CONVEX 2       /* b3b200_convex_polyhedron */
+#define B3B200_TBL_VERTICES 3     /* b3b200_float4 */
+#define B3B200_TBL_UNIQUE_EDGES 4 /* b3b200_float4 */
+#define B3B200_TBL_FACES 5        /* b3b200_face */
+#define B3B200_TBL_INDICES 6      /* int */
+#define B3B200_TBL_CHILD_SHAPES 7 /* b3b200_child_shape */
+#define B3B200_TBL_BVH_INFOS 8    /* b3b200_bvh_info */
+#define B3B200_TBL_BVH_NODES 9    /* b3b200_bvh_node */
+#define B3B200_TBL_BVH_SUBTREES 10 /* b3b200_bvh_subtree */
+#define B3B200_TBL_BODIES 11      /* b3b200_rigid_body (host copy as registered / last written) */
+#define B3B200_TBL_INERTIAS 12    /* b3b200_inertia */
+int b3b200_get_table(b3b200_world* w, int which, void* dst, int capacity, int* count);
 
 /* ------------------------------------------------- stand-alone broadphase */
 /* b3GpuBroadphaseInterface (b3GpuBroadphaseInterface.h:12-40) as used by PairBench.cpp:208-379 */

@@ -1,0 +1,923 @@
+// oracle.cpp -- CPU restatement of the reference's algorithms for the GPU
+// rigid-body step.  TEST INFRASTRUCTURE ONLY: nothing under bullet3_b200/ may
+// link, import or call this file; only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs do, and only as the checker.
+//
+// Parity pinning: oracle/ref_shim.cpp compiles the UNMODIFIED reference sources
+// (b3CpuNarrowPhase's shared headers, b3IntegrateTransforms.h, b3UpdateAabbs.h,
+// b3ConvertConstraint4.h, the brute-force AABB test) into oracle/_ref/libb3ref.so
+// and tests/test_oracle_vs_ref.py checks every function here bit-for-bit against
+// it on seeded inputs.  The reference's own golden vectors for this path are the
+// MPR record/replay counts (not on the default CPU path) -- see DESIGN.md.
+//
+// Plain scalar C++, FP32, compiled with -ffp-contract=off.  Every function
+// cites the reference file:line it restates (paths relative to bullet3/src).
+#include <math.h>
+#include <float.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "../include/b3b200_types.h"
+
+namespace
+{
+struct V3
+{
+	float x, y, z, w;
+};
+inline V3 mk(float x, float y, float z, float w = 0.f)
+{
+	V3 v = {x, y, z, w};
+	return v;
+}
+inline V3 ld(const b3b200_float4& f) { return mk(f.x, f.y, f.z, f.w); }
+inline b3b200_float4 st(const V3& v)
+{
+	b3b200_float4 f = {v.x, v.y, v.z, v.w};
+	return f;
+}
+// Bullet3Common/b3Vector3.h (scalar path)
+inline float dot(const V3& a, const V3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(const V3& a, const V3& b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline V3 add(const V3& a, const V3& b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline V3 sub(const V3& a, const V3& b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline V3 mul(const V3& a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+inline V3 neg(const V3& a) { return mk(-a.x, -a.y, -a.z); }
+inline V3 normalized(const V3& v) { return mul(v, 1.0f / sqrtf(dot(v, v))); }  // b3Vector3.h:802,904
+
+// Bullet3Common/b3Quaternion.h:724-729, 305-310, 868-879
+inline V3 quatMulVec(const V3& q, const V3& w)
+{
+	return mk(q.w * w.x + q.y * w.z - q.z * w.y, q.w * w.y + q.z * w.x - q.x * w.z, q.w * w.z + q.x * w.y - q.y * w.x,
+			  -q.x * w.x - q.y * w.y - q.z * w.z);
+}
+inline V3 quatMul(const V3& a, const V3& b)
+{
+	return mk(a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+			  a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
+}
+inline V3 quatInv(const V3& q) { return mk(-q.x, -q.y, -q.z, q.w); }
+inline V3 quatRotate(const V3& q, const V3& v)
+{
+	V3 t = quatMulVec(q, v);
+	V3 r = quatMul(t, quatInv(q));
+	return mk(r.x, r.y, r.z);
+}
+struct M3
+{
+	V3 r[3];
+};
+// b3Matrix3x3::setRotation (b3Matrix3x3.h:201-262)
+inline M3 matFromQuat(const V3& q)
+{
+	float d = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+	float s = 2.0f / d;
+	float xs = q.x * s, ys = q.y * s, zs = q.z * s;
+	float wx = q.w * xs, wy = q.w * ys, wz = q.w * zs;
+	float xx = q.x * xs, xy = q.x * ys, xz = q.x * zs;
+	float yy = q.y * ys, yz = q.y * zs, zz = q.z * zs;
+	M3 m;
+	m.r[0] = mk(1.0f - (yy + zz), xy - wz, xz + wy);
+	m.r[1] = mk(xy + wz, 1.0f - (xx + zz), yz - wx);
+	m.r[2] = mk(xz - wy, yz + wx, 1.0f - (xx + yy));
+	return m;
+}
+// b3Matrix3x3::getRotation, scalar path (b3Matrix3x3.h:462-490)
+inline V3 quatFromMat(const M3& m)
+{
+	const float el[3][3] = {{m.r[0].x, m.r[0].y, m.r[0].z}, {m.r[1].x, m.r[1].y, m.r[1].z}, {m.r[2].x, m.r[2].y, m.r[2].z}};
+	float trace = el[0][0] + el[1][1] + el[2][2];
+	float temp[4];
+	if (trace > 0.0f)
+	{
+		float s = sqrtf(trace + 1.0f);
+		temp[3] = (s * 0.5f);
+		s = 0.5f / s;
+		temp[0] = ((el[2][1] - el[1][2]) * s);
+		temp[1] = ((el[0][2] - el[2][0]) * s);
+		temp[2] = ((el[1][0] - el[0][1]) * s);
+	}
+	else
+	{
+		int i = el[0][0] < el[1][1] ? (el[1][1] < el[2][2] ? 2 : 1) : (el[0][0] < el[2][2] ? 2 : 0);
+		int j = (i + 1) % 3;
+		int k = (i + 2) % 3;
+		float s = sqrtf(el[i][i] - el[j][j] - el[k][k] + 1.0f);
+		temp[i] = s * 0.5f;
+		s = 0.5f / s;
+		temp[3] = (el[k][j] - el[j][k]) * s;
+		temp[j] = (el[j][i] + el[i][j]) * s;
+		temp[k] = (el[k][i] + el[i][k]) * s;
+	}
+	return mk(temp[0], temp[1], temp[2], temp[3]);
+}
+inline V3 matMul(const M3& m, const V3& v) { return mk(dot(m.r[0], v), dot(m.r[1], v), dot(m.r[2], v)); }
+// b3TransformPoint, C++ path (Bullet3Common/shared/b3Quat.h:18-24 -> b3Transform.h:90-93)
+inline V3 transformPoint(const V3& p, const V3& t, const V3& q) { return add(matMul(matFromQuat(q), p), t); }
+
+struct Hull
+{
+	const b3b200_convex_polyhedron* h;
+	const b3b200_float4* vertices;
+	const b3b200_float4* uniqueEdges;
+	const b3b200_face* faces;
+	const int* indices;
+};
+
+// b3ProjectAxis (Bullet3Collision/NarrowPhaseCollision/shared/b3FindSeparatingAxis.h:4-34)
+void projectAxis(const Hull& hull, const V3& pos, const V3& orn, const V3& dir, float& mn, float& mx)
+{
+	mn = FLT_MAX;
+	mx = -FLT_MAX;
+	V3 localDir = quatRotate(quatInv(orn), dir);
+	float offset = dot(pos, dir);
+	for (int i = 0; i < hull.h->numVertices; i++)
+	{
+		float dp = dot(ld(hull.vertices[hull.h->vertexOffset + i]), localDir);
+		if (dp < mn) mn = dp;
+		if (dp > mx) mx = dp;
+	}
+	if (mn > mx) std::swap(mn, mx);
+	mn += offset;
+	mx += offset;
+}
+// b3TestSepAxis (:36-55)
+bool testSepAxis(const Hull& A, const Hull& B, const V3& posA, const V3& ornA, const V3& posB, const V3& ornB, const V3& axis, float& depth)
+{
+	float min0, max0, min1, max1;
+	projectAxis(A, posA, ornA, axis, min0, max0);
+	projectAxis(B, posB, ornB, axis, min1, max1);
+	if (max0 < min1 || max1 < min0) return false;
+	float d0 = max0 - min1, d1 = max1 - min0;
+	depth = d0 < d1 ? d0 : d1;
+	return true;
+}
+inline bool almostZero(const V3& v)
+{
+	// b3IsAlmostZero (Bullet3Common/shared/b3Float4.h:58-63) -- double literal on purpose
+	if (fabsf(v.x) > 1e-6 || fabsf(v.y) > 1e-6 || fabsf(v.z) > 1e-6) return false;
+	return true;
+}
+// b3FindSeparatingAxis (:57-195)
+bool findSeparatingAxis(const Hull& A, const Hull& B, V3 posA, const V3& ornA, V3 posB, const V3& ornB, V3& sep)
+{
+	posA.w = 0.f;
+	posB.w = 0.f;
+	V3 c0 = transformPoint(ld(A.h->localCenter), posA, ornA);
+	V3 c1 = transformPoint(ld(B.h->localCenter), posB, ornB);
+	V3 deltaC2 = sub(c0, c1);
+	float dmin = FLT_MAX;
+	sep = mk(0, 0, 0);
+	for (int i = 0; i < A.h->numFaces; i++)
+	{
+		V3 n = quatRotate(ornA, ld(A.faces[A.h->faceOffset + i].plane));
+		if (dot(deltaC2, n) < 0) n = mul(n, -1.f);
+		float d;
+		if (!testSepAxis(A, B, posA, ornA, posB, ornB, n, d)) return false;
+		if (d < dmin)
+		{
+			dmin = d;
+			sep = n;
+		}
+	}
+	for (int i = 0; i < B.h->numFaces; i++)
+	{
+		V3 n = quatRotate(ornB, ld(B.faces[B.h->faceOffset + i].plane));
+		if (dot(deltaC2, n) < 0) n = mul(n, -1.f);
+		float d;
+		if (!testSepAxis(A, B, posA, ornA, posB, ornB, n, d)) return false;
+		if (d < dmin)
+		{
+			dmin = d;
+			sep = n;
+		}
+	}
+	for (int e0 = 0; e0 < A.h->numUniqueEdges; e0++)
+	{
+		V3 edge0World = quatRotate(ornA, ld(A.uniqueEdges[A.h->uniqueEdgesOffset + e0]));
+		for (int e1 = 0; e1 < B.h->numUniqueEdges; e1++)
+		{
+			V3 edge1World = quatRotate(ornB, ld(B.uniqueEdges[B.h->uniqueEdgesOffset + e1]));
+			V3 cr = cross(edge0World, edge1World);
+			if (!almostZero(cr))
+			{
+				cr = normalized(cr);
+				if (dot(deltaC2, cr) < 0) cr = mul(cr, -1.f);
+				float dist;
+				if (!testSepAxis(A, B, posA, ornA, posB, ornB, cr, dist)) return false;
+				if (dist < dmin)
+				{
+					dmin = dist;
+					sep = cr;
+				}
+			}
+		}
+	}
+	if (dot(neg(deltaC2), sep) > 0.0f) sep = neg(sep);
+	return true;
+}
+
+const int MAX_VERTS = 1024;  // B3_MAX_VERTS (shared/b3ContactConvexConvexSAT.h:8)
+
+inline V3 lerp3(const V3& a, const V3& b, float t) { return mk(a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t, a.z + (b.z - a.z) * t); }
+// b3ClipFace (shared/b3ContactConvexConvexSAT.h:20-68)
+int clipFace(const V3* in, int numIn, const V3& n, float eq, V3* out)
+{
+	int numOut = 0;
+	if (numIn < 2) return 0;
+	V3 first = in[numIn - 1];
+	float ds = dot(n, first) + eq;
+	for (int ve = 0; ve < numIn; ve++)
+	{
+		V3 end = in[ve];
+		float de = dot(n, end) + eq;
+		if (ds < 0)
+		{
+			if (de < 0)
+				out[numOut++] = end;
+			else
+				out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+		}
+		else if (de < 0)
+		{
+			out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+			out[numOut++] = end;
+		}
+		first = end;
+		ds = de;
+	}
+	return numOut;
+}
+// b3ClipFaceAgainstHull (:70-176)
+int clipFaceAgainstHull(const V3& sep, const Hull& A, const V3& posA, const V3& ornA, V3* vertsB1, int numB1, V3* vertsB2, float minDist, float maxDist,
+						V3* contactsOut, int contactCapacity)
+{
+	int numContactsOut = 0;
+	V3* pIn = vertsB1;
+	V3* pOut = vertsB2;
+	int numIn = numB1;
+	int closestFaceA = -1;
+	{
+		float dmin = FLT_MAX;
+		for (int f = 0; f < A.h->numFaces; f++)
+		{
+			const b3b200_float4& pl = A.faces[A.h->faceOffset + f].plane;
+			V3 n = quatRotate(ornA, mk(pl.x, pl.y, pl.z));
+			float d = dot(n, sep);
+			if (d < dmin)
+			{
+				dmin = d;
+				closestFaceA = f;
+			}
+		}
+	}
+	if (closestFaceA < 0) return 0;
+	const b3b200_face& polyA = A.faces[A.h->faceOffset + closestFaceA];
+	int numVerticesA = polyA.numIndices;
+	for (int e0 = 0; e0 < numVerticesA; e0++)
+	{
+		V3 a = ld(A.vertices[A.h->vertexOffset + A.indices[polyA.indexOffset + e0]]);
+		V3 b = ld(A.vertices[A.h->vertexOffset + A.indices[polyA.indexOffset + ((e0 + 1) % numVerticesA)]]);
+		V3 edge0 = sub(a, b);
+		V3 worldEdge0 = quatRotate(ornA, edge0);
+		V3 worldPlaneAnormal1 = quatRotate(ornA, mk(polyA.plane.x, polyA.plane.y, polyA.plane.z));
+		V3 planeNormalWS = neg(cross(worldEdge0, worldPlaneAnormal1));
+		V3 worldA1 = transformPoint(a, posA, ornA);
+		float planeEqWS = -dot(worldA1, planeNormalWS);
+		int numOut = clipFace(pIn, numIn, planeNormalWS, planeEqWS, pOut);
+		std::swap(pIn, pOut);
+		numIn = numOut;
+	}
+	{
+		V3 planeNormalWS = quatRotate(ornA, mk(polyA.plane.x, polyA.plane.y, polyA.plane.z));
+		float planeEqWS = polyA.plane.w - dot(planeNormalWS, posA);
+		for (int i = 0; i < numIn; i++)
+		{
+			float depth = dot(planeNormalWS, pIn[i]) + planeEqWS;
+			if (depth <= minDist) depth = minDist;
+			if (numContactsOut < contactCapacity)
+			{
+				if (depth <= maxDist) contactsOut[numContactsOut++] = mk(pIn[i].x, pIn[i].y, pIn[i].z, depth);
+			}
+		}
+	}
+	return numContactsOut;
+}
+// b3ClipHullAgainstHull (:178-266)
+int clipHullAgainstHull(const V3& sep, const Hull& A, const Hull& B, const V3& posA, const V3& ornA, const V3& posB, const V3& ornB, V3* vertsB1,
+						V3* vertsB2, float minDist, float maxDist, V3* contactsOut, int contactCapacity)
+{
+	int closestFaceB = -1;
+	float dmax = -FLT_MAX;
+	for (int f = 0; f < B.h->numFaces; f++)
+	{
+		const b3b200_float4& pl = B.faces[B.h->faceOffset + f].plane;
+		V3 n = quatRotate(ornB, mk(pl.x, pl.y, pl.z));
+		float d = dot(n, sep);
+		if (d > dmax)
+		{
+			dmax = d;
+			closestFaceB = f;
+		}
+	}
+	if (closestFaceB < 0) return 0;
+	int numB1 = 0;
+	const b3b200_face& polyB = B.faces[B.h->faceOffset + closestFaceB];
+	for (int e0 = 0; e0 < polyB.numIndices && numB1 < MAX_VERTS; e0++)
+	{
+		V3 b = ld(B.vertices[B.h->vertexOffset + B.indices[polyB.indexOffset + e0]]);
+		vertsB1[numB1++] = transformPoint(b, posB, ornB);
+	}
+	return clipFaceAgainstHull(sep, A, posA, ornA, vertsB1, numB1, vertsB2, minDist, maxDist, contactsOut, contactCapacity);
+}
+// b3ReduceContacts (shared/b3ReduceContacts.h:4-87)
+int reduceContacts(const V3* p, int nPoints, const V3& nearNormal, int idx[4])
+{
+	if (nPoints == 0) return 0;
+	if (nPoints <= 4) return nPoints;
+	if (nPoints > 64) nPoints = 64;
+	V3 center = mk(0, 0, 0);
+	for (int i = 0; i < nPoints; i++) center = add(center, p[i]);
+	center = mul(center, 1.0f / (float)nPoints);
+	V3 aVector = sub(p[0], center);
+	V3 u = cross(nearNormal, aVector);
+	V3 v = cross(nearNormal, u);
+	u = normalized(u);
+	v = normalized(v);
+	float minW = FLT_MAX;
+	int minIndex = -1;
+	float maxDots[4] = {FLT_MIN, FLT_MIN, FLT_MIN, FLT_MIN};
+	for (int ie = 0; ie < nPoints; ie++)
+	{
+		if (p[ie].w < minW)
+		{
+			minW = p[ie].w;
+			minIndex = ie;
+		}
+		V3 r = sub(p[ie], center);
+		float f = dot(u, r);
+		if (f < maxDots[0])
+		{
+			maxDots[0] = f;
+			idx[0] = ie;
+		}
+		f = dot(neg(u), r);
+		if (f < maxDots[1])
+		{
+			maxDots[1] = f;
+			idx[1] = ie;
+		}
+		f = dot(v, r);
+		if (f < maxDots[2])
+		{
+			maxDots[2] = f;
+			idx[2] = ie;
+		}
+		f = dot(neg(v), r);
+		if (f < maxDots[3])
+		{
+			maxDots[3] = f;
+			idx[3] = ie;
+		}
+	}
+	if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
+	return 4;
+}
+
+Hull hullOf(int shapeIndex, const b3b200_convex_polyhedron* convex, const b3b200_float4* vertices, const b3b200_float4* uniqueEdges,
+			const b3b200_face* faces, const int* indices)
+{
+	Hull h = {&convex[shapeIndex], vertices, uniqueEdges, faces, indices};
+	return h;
+}
+
+unsigned int hashContact(int a, int b, int ca, int cb)
+{
+	unsigned int h = (unsigned int)a * 0x9E3779B1u;
+	h ^= (unsigned int)b * 0x85EBCA77u + 0x165667B1u + (h << 6) + (h >> 2);
+	h ^= (unsigned int)ca * 0xC2B2AE3Du + (h << 6) + (h >> 2);
+	h ^= (unsigned int)cb * 0x27D4EB2Fu + (h << 6) + (h >> 2);
+	h ^= h >> 16;
+	h *= 0x85EBCA6Bu;
+	h ^= h >> 13;
+	h *= 0xC2B2AE35u;
+	h ^= h >> 16;
+	return h;
+}
+
+// calcJacCoeff / calcRelVel / b3PlaneSpace1 (Bullet3Dynamics/shared/b3ConvertConstraint4.h:5-60)
+float calcJacCoeff(const V3& angular0, const V3& angular1, float invMass0, const M3& I0, float invMass1, const M3& I1)
+{
+	float jmj0 = invMass0;
+	float jmj1 = dot(matMul(I0, angular0), angular0);
+	float jmj2 = invMass1;
+	float jmj3 = dot(matMul(I1, angular1), angular1);
+	return -1.f / (jmj0 + jmj1 + jmj2 + jmj3);
+}
+float calcRelVel(const V3& l0, const V3& l1, const V3& a0, const V3& a1, const V3& linVel0, const V3& angVel0, const V3& linVel1, const V3& angVel1)
+{
+	return dot(l0, linVel0) + dot(a0, angVel0) + dot(l1, linVel1) + dot(a1, angVel1);
+}
+void planeSpace1(const V3& n, V3& p, V3& q)
+{
+	if (fabsf(n.z) > 0.70710678f)
+	{
+		float a = n.y * n.y + n.z * n.z;
+		float k = 1.f / sqrtf(a);
+		p = mk(0, -n.z * k, n.y * k);
+		q = mk(a * k, -n.x * p.z, n.x * p.y);
+	}
+	else
+	{
+		float a = n.x * n.x + n.y * n.y;
+		float k = 1.f / sqrtf(a);
+		p = mk(-n.y * k, n.x * k, 0);
+		q = mk(-n.z * p.y, n.z * p.x, a * k);
+	}
+}
+M3 ldM(const b3b200_mat3x3& m)
+{
+	M3 r;
+	r.r[0] = ld(m.row[0]);
+	r.r[1] = ld(m.row[1]);
+	r.r[2] = ld(m.row[2]);
+	return r;
+}
+}  // namespace
+
+extern "C" {
+
+// b3ComputeWorldAabb / b3TransformAabb2
+// (Bullet3Collision/NarrowPhaseCollision/shared/b3UpdateAabbs.h:8-33,
+//  Bullet3Collision/BroadPhaseCollision/shared/b3Aabb.h:24-43); max.w carries the
+// intended "is dynamic" flag (the reference reads it out of bounds, SURVEY B#12).
+void orc_update_aabbs(const b3b200_rigid_body* bodies, int n, const b3b200_collidable* collidables, const b3b200_aabb* localAabbs, b3b200_aabb* out)
+{
+	for (int i = 0; i < n; i++)
+	{
+		const b3b200_rigid_body& b = bodies[i];
+		int c = b.collidableIdx;
+		if (c < 0 || collidables[c].shapeIndex < 0) continue;
+		const b3b200_aabb& l = localAabbs[c];
+		V3 lmn = mk(l.min[0], l.min[1], l.min[2]), lmx = mk(l.max[0], l.max[1], l.max[2]);
+		V3 half = mul(sub(lmx, lmn), 0.5f);
+		half = add(half, mk(0.f, 0.f, 0.f));
+		V3 lc = mul(add(lmx, lmn), 0.5f);
+		M3 m = matFromQuat(ld(b.quat));
+		M3 a;
+		for (int r = 0; r < 3; r++) a.r[r] = mk(fabsf(m.r[r].x), fabsf(m.r[r].y), fabsf(m.r[r].z));
+		V3 center = transformPoint(lc, ld(b.pos), ld(b.quat));
+		V3 extent = mk(dot(half, a.r[0]), dot(half, a.r[1]), dot(half, a.r[2]));
+		V3 mn = sub(center, extent), mx = add(center, extent);
+		out[i].min[0] = mn.x;
+		out[i].min[1] = mn.y;
+		out[i].min[2] = mn.z;
+		out[i].minIndices[3] = i;
+		out[i].max[0] = mx.x;
+		out[i].max[1] = mx.y;
+		out[i].max[2] = mx.z;
+		out[i].signedMaxIndices[3] = b.invMass == 0.f ? 0 : 1;
+	}
+}
+
+// b3TestAabbAgainstAabb (shared/b3Aabb.h:45-53)
+static bool aabbOverlap(const b3b200_aabb& a, const b3b200_aabb& b)
+{
+	bool overlap = true;
+	overlap = (a.min[0] > b.max[0] || a.max[0] < b.min[0]) ? false : overlap;
+	overlap = (a.min[2] > b.max[2] || a.max[2] < b.min[2]) ? false : overlap;
+	overlap = (a.min[1] > b.max[1] || a.max[1] < b.min[1]) ? false : overlap;
+	return overlap;
+}
+
+// b3GpuSapBroadphase::calculateOverlappingPairsHost
+// (Bullet3OpenCL/BroadphaseCollision/b3GpuSapBroadphase.cpp:862-981): brute force
+// small x small, then small x large; pairs ordered (min handle, max handle).
+// Returns the number of overlapping pairs (may exceed maxPairs; only maxPairs are stored).
+int orc_brute_force_pairs(const b3b200_aabb* aabbs, const int* smallIdx, int nSmall, const int* largeIdx, int nLarge, b3b200_int4* pairsOut, int maxPairs)
+{
+	int count = 0;
+	for (int i = 0; i < nSmall; i++)
+	{
+		const b3b200_aabb& ai = aabbs[smallIdx[i]];
+		for (int j = i + 1; j < nSmall; j++)
+		{
+			const b3b200_aabb& aj = aabbs[smallIdx[j]];
+			if (aabbOverlap(ai, aj))
+			{
+				int a = ai.minIndices[3], b = aj.minIndices[3];
+				if (count < maxPairs)
+				{
+					pairsOut[count].x = a <= b ? a : b;
+					pairsOut[count].y = a <= b ? b : a;
+					pairsOut[count].z = -1;
+					pairsOut[count].w = -1;
+				}
+				count++;
+			}
+		}
+	}
+	for (int i = 0; i < nSmall; i++)
+	{
+		const b3b200_aabb& ai = aabbs[smallIdx[i]];
+		for (int j = 0; j < nLarge; j++)
+		{
+			const b3b200_aabb& aj = aabbs[largeIdx[j]];
+			if (aabbOverlap(ai, aj))
+			{
+				int a = aj.minIndices[3], b = ai.minIndices[3];
+				if (count < maxPairs)
+				{
+					pairsOut[count].x = a <= b ? a : b;
+					pairsOut[count].y = a <= b ? b : a;
+					pairsOut[count].z = -1;
+					pairsOut[count].w = -1;
+				}
+				count++;
+			}
+		}
+	}
+	return count;
+}
+
+// Same pair set as orc_brute_force_pairs, found with a sort-and-sweep on x so that
+// full-size scenes (256k bodies) finish in seconds.  Checked against the brute
+// force version in tests/test_oracle.py.  Output is sorted lexicographically.
+int orc_sweep_pairs(const b3b200_aabb* aabbs, const int* smallIdx, int nSmall, const int* largeIdx, int nLarge, b3b200_int4* pairsOut, int maxPairs)
+{
+	std::vector<int> order(smallIdx, smallIdx + nSmall);
+	std::sort(order.begin(), order.end(), [&](int a, int b) { return aabbs[a].min[0] < aabbs[b].min[0]; });
+	std::vector<std::pair<int, int> > found;
+	for (int i = 0; i < nSmall; i++)
+	{
+		const b3b200_aabb& ai = aabbs[order[i]];
+		for (int j = i + 1; j < nSmall; j++)
+		{
+			const b3b200_aabb& aj = aabbs[order[j]];
+			if (ai.max[0] < aj.min[0]) break;
+			if (aabbOverlap(ai, aj))
+			{
+				int a = ai.minIndices[3], b = aj.minIndices[3];
+				found.push_back(std::make_pair(a <= b ? a : b, a <= b ? b : a));
+			}
+		}
+		for (int j = 0; j < nLarge; j++)
+		{
+			const b3b200_aabb& aj = aabbs[largeIdx[j]];
+			if (aabbOverlap(ai, aj))
+			{
+				int a = aj.minIndices[3], b = ai.minIndices[3];
+				found.push_back(std::make_pair(a <= b ? a : b, a <= b ? b : a));
+			}
+		}
+	}
+	std::sort(found.begin(), found.end());
+	int count = (int)found.size();
+	for (int i = 0; i < count && i < maxPairs; i++)
+	{
+		pairsOut[i].x = found[i].first;
+		pairsOut[i].y = found[i].second;
+		pairsOut[i].z = -1;
+		pairsOut[i].w = -1;
+	}
+	return count;
+}
+
+// integrateSingleTransform (Bullet3Dynamics/shared/b3IntegrateTransforms.h:5-55):
+// the GPU-path order (position first, then gravity).
+void orc_integrate(b3b200_rigid_body* bodies, int n, float timeStep, float angularDamping, const float* gravity)
+{
+	for (int i = 0; i < n; i++)
+	{
+		b3b200_rigid_body& b = bodies[i];
+		if (b.invMass != 0.f)
+		{
+			float THRESH = (0.25f * 3.14159254f);
+			b.angVel.x *= angularDamping;
+			b.angVel.y *= angularDamping;
+			b.angVel.z *= angularDamping;
+			V3 angvel = ld(b.angVel);
+			float fAngle = sqrtf(dot(angvel, angvel));
+			if (fAngle * timeStep > THRESH) fAngle = THRESH / timeStep;
+			V3 axis;
+			if (fAngle < 0.001f)
+				axis = mul(angvel, 0.5f * timeStep - (timeStep * timeStep * timeStep) * 0.020833333333f * fAngle * fAngle);
+			else
+				axis = mul(angvel, sinf(0.5f * fAngle * timeStep) / fAngle);
+			V3 dorn = mk(axis.x, axis.y, axis.z, cosf(fAngle * timeStep * 0.5f));
+			V3 orn0 = ld(b.quat);
+			V3 pq = quatMul(dorn, orn0);
+			float len2 = pq.x * pq.x + pq.y * pq.y + pq.z * pq.z + pq.w * pq.w;
+			float s = 1.0f / sqrtf(len2);
+			b.quat.x = pq.x * s;
+			b.quat.y = pq.y * s;
+			b.quat.z = pq.z * s;
+			b.quat.w = pq.w * s;
+			b.pos.x += b.linVel.x * timeStep;
+			b.pos.y += b.linVel.y * timeStep;
+			b.pos.z += b.linVel.z * timeStep;
+			b.linVel.x += gravity[0] * timeStep;
+			b.linVel.y += gravity[1] * timeStep;
+			b.linVel.z += gravity[2] * timeStep;
+		}
+	}
+}
+
+// b3ContactConvexConvexSAT + b3ClipHullHullSingle for every convex-convex pair
+// (shared/b3ContactConvexConvexSAT.h:270-484; loop of b3CpuNarrowPhase::computeContacts,
+// Bullet3Collision/NarrowPhaseCollision/b3CpuNarrowPhase.cpp:53-141).
+// minDist/maxDist are the clip window (CPU header: -1, 0; GPU kernels: -1e30, 0.02).
+// pairContactIndex[i] = contact index of pair i or -1.  Returns the contact count.
+int orc_convex_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_rigid_body* bodies, const b3b200_collidable* collidables,
+						const b3b200_convex_polyhedron* convex, const b3b200_float4* vertices, const b3b200_float4* uniqueEdges,
+						const b3b200_face* faces, const int* indices, float minDist, float maxDist, b3b200_contact4* out, int maxContacts,
+						int* pairContactIndex)
+{
+	int nContacts = 0;
+	std::vector<V3> b1(MAX_VERTS), b2(MAX_VERTS), cont(MAX_VERTS);
+	for (int p = 0; p < nPairs; p++)
+	{
+		if (pairContactIndex) pairContactIndex[p] = -1;
+		int bodyA = pairs[p].x, bodyB = pairs[p].y;
+		int cA = bodies[bodyA].collidableIdx, cB = bodies[bodyB].collidableIdx;
+		if (collidables[cA].shapeType != B3B200_SHAPE_CONVEX_HULL || collidables[cB].shapeType != B3B200_SHAPE_CONVEX_HULL) continue;
+		Hull A = hullOf(collidables[cA].shapeIndex, convex, vertices, uniqueEdges, faces, indices);
+		Hull B = hullOf(collidables[cB].shapeIndex, convex, vertices, uniqueEdges, faces, indices);
+		V3 posA = ld(bodies[bodyA].pos), ornA = ld(bodies[bodyA].quat);
+		V3 posB = ld(bodies[bodyB].pos), ornB = ld(bodies[bodyB].quat);
+		posA.w = 0.f;
+		posB.w = 0.f;
+		V3 sep;
+		if (!findSeparatingAxis(A, B, posA, ornA, posB, ornB, sep)) continue;
+		// b3ClipHullHullSingle round-trips both orientations through b3Transform:
+		// trA.setRotation(ornA); trAorn = trA.getRotation()  (shared/b3ContactConvexConvexSAT.h:323-337)
+		V3 ornA2 = quatFromMat(matFromQuat(ornA)), ornB2 = quatFromMat(matFromQuat(ornB));
+		int numContactsOut = clipHullAgainstHull(sep, A, B, posA, ornA2, posB, ornB2, b1.data(), b2.data(), minDist, maxDist, cont.data(), MAX_VERTS);
+		if (numContactsOut <= 0) continue;
+		int idx[4] = {0, 1, 2, 3};
+		int numPoints = reduceContacts(cont.data(), numContactsOut, sep, idx);
+		if (nContacts < maxContacts)
+		{
+			b3b200_contact4& c = out[nContacts];
+			memset(&c, 0, sizeof(c));
+			c.batchIdx = 0;
+			c.bodyAPtrAndSignBit = (bodies[bodyA].invMass == 0) ? -bodyA : bodyA;
+			c.bodyBPtrAndSignBit = (bodies[bodyB].invMass == 0) ? -bodyB : bodyB;
+			c.frictionCmp = 45874;
+			c.restitutionCmp = 0;
+			c.childIndexA = -1;
+			c.childIndexB = -1;
+			for (int k = 0; k < numPoints; k++) c.worldPosB[k] = st(cont[idx[k]]);
+			c.worldNormalOnB = st(mk(sep.x, sep.y, sep.z, (float)numPoints));
+			if (pairContactIndex) pairContactIndex[p] = nContacts;
+			nContacts++;
+		}
+	}
+	return nContacts;
+}
+
+// Graph colouring = sequential first-fit in descending priority order, priority =
+// (hashContact(bodyA, bodyB, childA, childB) << 32) | (index + 1).  This is the
+// batching rule of the new solver (bullet3_b200/csrc/solver.cu); it plays the role
+// of b3GpuPgsContactSolver::sortConstraintByBatch3
+// (Bullet3OpenCL/RigidBody/b3GpuPgsContactSolver.cpp:1385-1529), whose invariant
+// -- no two constraints of a batch share a dynamic body -- it keeps.
+// Returns the number of batches; colours[i] in [0, 128).
+int orc_colour_contacts(const b3b200_contact4* contacts, int n, int numBodies, int staticIdx, int* colours)
+{
+	std::vector<unsigned long long> prio(n);
+	std::vector<int> order(n);
+	for (int i = 0; i < n; i++)
+	{
+		int a = abs(contacts[i].bodyAPtrAndSignBit), b = abs(contacts[i].bodyBPtrAndSignBit);
+		prio[i] = ((unsigned long long)hashContact(a, b, contacts[i].childIndexA, contacts[i].childIndexB) << 32) | (unsigned long long)(i + 1);
+		order[i] = i;
+	}
+	std::sort(order.begin(), order.end(), [&](int x, int y) { return prio[x] > prio[y]; });
+	std::vector<unsigned long long> mask(2 * (size_t)numBodies, 0ull);
+	int numBatches = 0;
+	for (int k = 0; k < n; k++)
+	{
+		int i = order[k];
+		int as = contacts[i].bodyAPtrAndSignBit, bs = contacts[i].bodyBPtrAndSignBit;
+		int a = abs(as), b = abs(bs);
+		bool aStatic = as < 0 || as == staticIdx, bStatic = bs < 0 || bs == staticIdx;
+		unsigned long long m0 = 0, m1 = 0;
+		if (!aStatic)
+		{
+			m0 |= mask[2 * a];
+			m1 |= mask[2 * a + 1];
+		}
+		if (!bStatic)
+		{
+			m0 |= mask[2 * b];
+			m1 |= mask[2 * b + 1];
+		}
+		int colour = 127;
+		if (~m0)
+			colour = __builtin_ctzll(~m0);
+		else if (~m1)
+			colour = 64 + __builtin_ctzll(~m1);
+		unsigned long long bit = 1ull << (colour & 63);
+		if (!aStatic) mask[2 * a + (colour >> 6)] |= bit;
+		if (!bStatic) mask[2 * b + (colour >> 6)] |= bit;
+		colours[i] = colour;
+		if (colour + 1 > numBatches) numBatches = colour + 1;
+	}
+	return numBatches;
+}
+
+// setConstraint4 (Bullet3Dynamics/shared/b3ConvertConstraint4.h:62-148) as driven by
+// b3Solver::convertToConstraints (Bullet3OpenCL/RigidBody/b3Solver.cpp:889-933):
+// rows are built with m_initInvInertia.
+void orc_build_constraints(const b3b200_contact4* contacts, int n, const b3b200_rigid_body* bodies, const b3b200_inertia* inertias, float dt,
+						   float positionDrift, float positionConstraintCoeff, b3b200_constraint4* out)
+{
+	for (int g = 0; g < n; g++)
+	{
+		const b3b200_contact4& src = contacts[g];
+		b3b200_constraint4& dst = out[g];
+		memset(&dst, 0, sizeof(dst));
+		int aIdx = abs(src.bodyAPtrAndSignBit), bIdx = abs(src.bodyBPtrAndSignBit);
+		V3 posA = ld(bodies[aIdx].pos), linVelA = ld(bodies[aIdx].linVel), angVelA = ld(bodies[aIdx].angVel);
+		V3 posB = ld(bodies[bIdx].pos), linVelB = ld(bodies[bIdx].linVel), angVelB = ld(bodies[bIdx].angVel);
+		float invMassA = bodies[aIdx].invMass, invMassB = bodies[bIdx].invMass;
+		M3 IA = ldM(inertias[aIdx].initInvInertia), IB = ldM(inertias[bIdx].initInvInertia);
+		dst.bodyA = aIdx;
+		dst.bodyB = bIdx;
+		float dtInv = 1.f / dt;
+		V3 n3 = mk(src.worldNormalOnB.x, src.worldNormalOnB.y, src.worldNormalOnB.z);
+		float npoints = src.worldNormalOnB.w;
+		dst.linear = st(mk(n3.x, n3.y, n3.z, 0.7f));
+		for (int ic = 0; ic < 4; ic++)
+		{
+			V3 r0 = sub(ld(src.worldPosB[ic]), posA);
+			V3 r1 = sub(ld(src.worldPosB[ic]), posB);
+			if (ic >= npoints)
+			{
+				dst.jacCoeffInv[ic] = 0.f;
+				continue;
+			}
+			V3 angular0 = cross(r0, n3);
+			V3 angular1 = neg(cross(r1, n3));
+			dst.jacCoeffInv[ic] = calcJacCoeff(angular0, angular1, invMassA, IA, invMassB, IB);
+			float relVelN = calcRelVel(n3, neg(n3), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+			float e = 0.f;
+			if (relVelN * relVelN < 0.004f) e = 0.f;
+			dst.b[ic] = e * relVelN;
+			dst.b[ic] += (src.worldPosB[ic].w + positionDrift) * positionConstraintCoeff * dtInv;
+			dst.appliedRambdaDt[ic] = 0.f;
+		}
+		if (npoints > 0)
+		{
+			V3 center = mk(0, 0, 0);
+			for (int i = 0; i < npoints; i++) center = add(center, ld(src.worldPosB[i]));
+			center = mul(center, 1.0f / (float)npoints);
+			V3 t[2];
+			planeSpace1(n3, t[0], t[1]);
+			V3 r0 = sub(center, posA), r1 = sub(center, posB);
+			for (int i = 0; i < 2; i++)
+			{
+				V3 a0 = cross(r0, t[i]), a1 = neg(cross(r1, t[i]));
+				dst.fJacCoeffInv[i] = calcJacCoeff(a0, a1, invMassA, IA, invMassB, IB);
+				dst.fAppliedRambdaDt[i] = 0.f;
+			}
+			dst.center = st(center);
+		}
+		for (int i = 0; i < 4; i++)
+			if (i < npoints)
+				dst.worldPos[i] = src.worldPosB[i];
+			else
+				dst.worldPos[i] = st(mk(0, 0, 0, 0));
+		dst.batchIdx = src.batchIdx;
+	}
+}
+
+// solveContact<false> / solveFriction / SolveTask::run, in the order of the
+// reference's global-batch mode: all iterations of the normal rows batch by batch,
+// then all iterations of the friction rows (Bullet3OpenCL/RigidBody/b3Solver.cpp:187-329,
+// 347-409; b3GpuPgsContactSolver.cpp:262-311).  `constraints` must be sorted by batch,
+// batchOffsets has numBatches+1 entries.
+void orc_solve(b3b200_constraint4* cs, const int* batchOffsets, int numBatches, b3b200_rigid_body* bodies, const b3b200_inertia* inertias, int iterations)
+{
+	for (int phase = 0; phase < 2; phase++)
+		for (int iter = 0; iter < iterations; iter++)
+			for (int bt = 0; bt < numBatches; bt++)
+				for (int i = batchOffsets[bt]; i < batchOffsets[bt + 1]; i++)
+				{
+					b3b200_constraint4& c = cs[i];
+					int aIdx = (int)c.bodyA, bIdx = (int)c.bodyB;
+					b3b200_rigid_body& A = bodies[aIdx];
+					b3b200_rigid_body& B = bodies[bIdx];
+					V3 posA = ld(A.pos), posB = ld(B.pos);
+					V3 linVelA = ld(A.linVel), angVelA = ld(A.angVel), linVelB = ld(B.linVel), angVelB = ld(B.angVel);
+					float invMassA = A.invMass, invMassB = B.invMass;
+					M3 IA = ldM(inertias[aIdx].invInertiaWorld), IB = ldM(inertias[bIdx].invInertiaWorld);
+					V3 lin = ld(c.linear);
+					if (phase == 0)
+					{
+						for (int ic = 0; ic < 4; ic++)
+						{
+							if (c.jacCoeffInv[ic] == 0.f) continue;
+							V3 r0 = sub(ld(c.worldPos[ic]), posA), r1 = sub(ld(c.worldPos[ic]), posB);
+							V3 angular0 = cross(r0, lin), angular1 = neg(cross(r1, lin));
+							float rambdaDt = calcRelVel(lin, neg(lin), angular0, angular1, linVelA, angVelA, linVelB, angVelB) + c.b[ic];
+							rambdaDt *= c.jacCoeffInv[ic];
+							float prevSum = c.appliedRambdaDt[ic];
+							float updated = prevSum;
+							updated += rambdaDt;
+							updated = std::max(updated, 0.f);
+							updated = std::min(updated, FLT_MAX);
+							rambdaDt = updated - prevSum;
+							c.appliedRambdaDt[ic] = updated;
+							V3 linImp0 = mul(mul(lin, invMassA), rambdaDt);
+							V3 linImp1 = mul(mul(neg(lin), invMassB), rambdaDt);
+							V3 angImp0 = mul(matMul(IA, angular0), rambdaDt);
+							V3 angImp1 = mul(matMul(IB, angular1), rambdaDt);
+							linVelA = add(linVelA, linImp0);
+							angVelA = add(angVelA, angImp0);
+							linVelB = add(linVelB, linImp1);
+							angVelB = add(angVelB, angImp1);
+						}
+					}
+					else
+					{
+						if (c.fJacCoeffInv[0] == 0 && c.fJacCoeffInv[0] == 0) continue;
+						float sum = 0;
+						for (int j = 0; j < 4; j++) sum += c.appliedRambdaDt[j];
+						float maxR = 0.7f * sum, minR = -maxR;
+						V3 center = ld(c.center);
+						V3 n = neg(lin);
+						V3 t[2];
+						planeSpace1(n, t[0], t[1]);
+						V3 r0 = sub(center, posA), r1 = sub(center, posB);
+						for (int k = 0; k < 2; k++)
+						{
+							V3 angular0 = cross(r0, t[k]), angular1 = neg(cross(r1, t[k]));
+							float rambdaDt = calcRelVel(t[k], neg(t[k]), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+							rambdaDt *= c.fJacCoeffInv[k];
+							float prevSum = c.fAppliedRambdaDt[k];
+							float updated = prevSum;
+							updated += rambdaDt;
+							updated = std::max(updated, minR);
+							updated = std::min(updated, maxR);
+							rambdaDt = updated - prevSum;
+							c.fAppliedRambdaDt[k] = updated;
+							V3 linImp0 = mul(mul(t[k], invMassA), rambdaDt);
+							V3 linImp1 = mul(mul(neg(t[k]), invMassB), rambdaDt);
+							V3 angImp0 = mul(matMul(IA, angular0), rambdaDt);
+							V3 angImp1 = mul(matMul(IB, angular1), rambdaDt);
+							linVelA = add(linVelA, linImp0);
+							angVelA = add(angVelA, angImp0);
+							linVelB = add(linVelB, linImp1);
+							angVelB = add(angVelB, angImp1);
+						}
+						V3 ab = normalized(sub(posB, posA));
+						V3 ac = normalized(sub(center, posA));
+						if (dot(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
+						{
+							float angNA = dot(n, angVelA), angNB = dot(n, angVelB);
+							angVelA = sub(angVelA, mul(n, angNA * 0.1f));
+							angVelB = sub(angVelB, mul(n, angNB * 0.1f));
+						}
+					}
+					if (invMassA != 0.f)
+					{
+						A.linVel = st(linVelA);
+						A.angVel = st(angVelA);
+					}
+					if (invMassB != 0.f)
+					{
+						B.linVel = st(linVelB);
+						B.angVel = st(angVelB);
+					}
+				}
+}
+
+// b3RadixSort32CL::executeHost (Bullet3OpenCL/ParallelPrimitives/b3RadixSort32CL.cpp:587-646): stable by key
+void orc_radix_sort_kv(b3b200_sort_data* data, int n)
+{
+	std::stable_sort(data, data + n, [](const b3b200_sort_data& a, const b3b200_sort_data& b) { return a.key < b.key; });
+}
+// b3PrefixScanCL::executeHost (b3PrefixScanCL.cpp:105-119): exclusive
+void orc_prefix_scan(const unsigned int* src, unsigned int* dst, int n, unsigned int* sum)
+{
+	unsigned int s = 0;
+	for (int i = 0; i < n; i++)
+	{
+		unsigned int t = src[i];
+		dst[i] = s;
+		s += t;
+	}
+	if (sum) *sum = s;
+}
+// b3BoundSearchCL::executeHost COUNT (b3BoundSearchCL.cpp:159-203)
+void orc_bound_search_count(const b3b200_sort_data* sorted, int n, unsigned int* counts, int numBuckets)
+{
+	for (int i = 0; i < numBuckets; i++) counts[i] = 0;
+	for (int i = 0; i < n; i++)
+		if (sorted[i].key < (unsigned int)numBuckets) counts[sorted[i].key]++;
+}
+
+}  // extern "C"

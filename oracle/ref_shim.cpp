@@ -1,0 +1,221 @@
+// ref_shim.cpp -- thin extern "C" wrappers around the UNMODIFIED reference
+// sources under /root/reference/src, compiled where they lie (see Makefile) into
+// oracle/_ref/libb3ref.so.  TEST INFRASTRUCTURE ONLY.  Nothing here restates an
+// algorithm: every function calls straight into a reference header/function.
+// Used to pin oracle/oracle.cpp (tests/test_oracle_vs_ref.py) and as the
+// "reference" CPU baseline of bench.py.
+#include <string.h>
+#include <stdio.h>
+#include <vector>
+#include "Bullet3Common/b3AlignedObjectArray.h"
+#include "Bullet3Common/b3Vector3.h"
+#include "Bullet3Common/b3Quaternion.h"
+#include "Bullet3Common/b3Logging.h"
+#include "Bullet3Common/b3Scalar.h"
+#define B3_PROFILE(x)
+#include "Bullet3Common/shared/b3Int4.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3Collidable.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3ConvexPolyhedronData.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3ContactConvexConvexSAT.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3UpdateAabbs.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3ConvexUtility.h"
+#include "Bullet3Collision/BroadPhaseCollision/shared/b3Aabb.h"
+#include "Bullet3Dynamics/shared/b3IntegrateTransforms.h"
+#include "Bullet3Dynamics/shared/b3ConvertConstraint4.h"
+
+#include "../include/b3b200_types.h"
+
+static_assert(sizeof(b3RigidBodyData) == sizeof(b3b200_rigid_body), "abi");
+static_assert(sizeof(b3InertiaData) == sizeof(b3b200_inertia), "abi");
+static_assert(sizeof(b3Collidable) == sizeof(b3b200_collidable), "abi");
+static_assert(sizeof(b3ConvexPolyhedronData) == sizeof(b3b200_convex_polyhedron), "abi");
+static_assert(sizeof(b3GpuFace) == sizeof(b3b200_face), "abi");
+static_assert(sizeof(b3Aabb) == sizeof(b3b200_aabb), "abi");
+static_assert(sizeof(b3Contact4Data) == sizeof(b3b200_contact4), "abi");
+static_assert(sizeof(b3ContactConstraint4) == sizeof(b3b200_constraint4), "abi");
+static_assert(sizeof(b3Int4) == sizeof(b3b200_int4), "abi");
+static_assert(sizeof(b3Vector3) == sizeof(b3b200_float4), "abi");
+
+template <typename T, typename S>
+static void fill(b3AlignedObjectArray<T>& dst, const S* src, int n)
+{
+	static_assert(sizeof(T) == sizeof(S), "abi");
+	dst.resize(n);
+	if (n) memcpy(&dst[0], src, sizeof(T) * (size_t)n);
+}
+
+extern "C" {
+
+int ref_sizes(int* out, int n)
+{
+	int s[] = {(int)sizeof(b3RigidBodyData), (int)sizeof(b3InertiaData), (int)sizeof(b3Collidable), (int)sizeof(b3GpuChildShape),
+			   (int)sizeof(b3GpuFace), (int)sizeof(b3ConvexPolyhedronData), (int)sizeof(b3Aabb), (int)sizeof(b3Int4), (int)sizeof(b3Contact4Data),
+			   (int)sizeof(b3ContactConstraint4)};
+	int m = (int)(sizeof(s) / sizeof(s[0]));
+	for (int i = 0; i < m && i < n; i++) out[i] = s[i];
+	return m;
+}
+
+// b3ComputeWorldAabb (shared/b3UpdateAabbs.h:8-33).  The reference reads
+// body[bodyId].m_invMass == bodies[2*bodyId] for max.w, so the body array is
+// padded to 2n here; max.w is not compared by the tests.
+void ref_update_aabbs(const b3b200_rigid_body* bodies, int n, const b3b200_collidable* collidables, const b3b200_aabb* localAabbs, b3b200_aabb* out)
+{
+	std::vector<b3RigidBodyData> padded(2 * (size_t)n + 1);
+	memset(padded.data(), 0, padded.size() * sizeof(b3RigidBodyData));
+	memcpy(padded.data(), bodies, sizeof(b3RigidBodyData) * (size_t)n);
+	for (int i = 0; i < n; i++)
+		b3ComputeWorldAabb(i, padded.data(), (const b3Collidable*)collidables, (const b3Aabb*)localAabbs, (b3Aabb*)out);
+}
+
+// predicate b3TestAabbAgainstAabb (shared/b3Aabb.h:45-53) in the loop structure of
+// b3GpuSapBroadphase::calculateOverlappingPairsHost (b3GpuSapBroadphase.cpp:862-981)
+int ref_brute_force_pairs(const b3b200_aabb* aabbs, const int* smallIdx, int nSmall, const int* largeIdx, int nLarge, b3b200_int4* pairsOut, int maxPairs)
+{
+	const b3Aabb* A = (const b3Aabb*)aabbs;
+	int count = 0;
+	for (int i = 0; i < nSmall; i++)
+		for (int j = i + 1; j < nSmall; j++)
+		{
+			const b3Aabb& a = A[smallIdx[i]];
+			const b3Aabb& b = A[smallIdx[j]];
+			if (b3TestAabbAgainstAabb(a.m_minVec, a.m_maxVec, b.m_minVec, b.m_maxVec))
+			{
+				int x = a.m_minIndices[3], y = b.m_minIndices[3];
+				if (count < maxPairs)
+				{
+					pairsOut[count].x = x <= y ? x : y;
+					pairsOut[count].y = x <= y ? y : x;
+					pairsOut[count].z = -1;
+					pairsOut[count].w = -1;
+				}
+				count++;
+			}
+		}
+	for (int i = 0; i < nSmall; i++)
+		for (int j = 0; j < nLarge; j++)
+		{
+			const b3Aabb& a = A[smallIdx[i]];
+			const b3Aabb& b = A[largeIdx[j]];
+			if (b3TestAabbAgainstAabb(a.m_minVec, a.m_maxVec, b.m_minVec, b.m_maxVec))
+			{
+				int x = b.m_minIndices[3], y = a.m_minIndices[3];
+				if (count < maxPairs)
+				{
+					pairsOut[count].x = x <= y ? x : y;
+					pairsOut[count].y = x <= y ? y : x;
+					pairsOut[count].z = -1;
+					pairsOut[count].w = -1;
+				}
+				count++;
+			}
+		}
+	return count;
+}
+
+// integrateSingleTransform (Bullet3Dynamics/shared/b3IntegrateTransforms.h:5-55)
+void ref_integrate(b3b200_rigid_body* bodies, int n, float dt, float angularDamping, const float* gravity)
+{
+	b3Vector3 g = b3MakeVector3(gravity[0], gravity[1], gravity[2]);
+	for (int i = 0; i < n; i++) integrateSingleTransform((b3RigidBodyData*)bodies, i, dt, angularDamping, g);
+}
+
+// b3ContactConvexConvexSAT (shared/b3ContactConvexConvexSAT.h:407-484), the loop of
+// b3CpuNarrowPhase::computeContacts (b3CpuNarrowPhase.cpp:53-141).  Clip window is the
+// header's own (-1, 0).
+int ref_convex_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_rigid_body* bodies, int nBodies, const b3b200_collidable* collidables,
+						int nCollidables, const b3b200_convex_polyhedron* convex, int nConvex, const b3b200_float4* vertices, int nVerts,
+						const b3b200_float4* uniqueEdges, int nEdges, const b3b200_face* faces, int nFaces, const int* indices, int nIndices,
+						b3b200_contact4* out, int maxContacts, int* pairContactIndex)
+{
+	b3AlignedObjectArray<b3RigidBodyData> rb;
+	b3AlignedObjectArray<b3Collidable> col;
+	b3AlignedObjectArray<b3ConvexPolyhedronData> cv;
+	b3AlignedObjectArray<b3Vector3> vt, ue;
+	b3AlignedObjectArray<b3GpuFace> fc;
+	b3AlignedObjectArray<int> ix;
+	fill(rb, bodies, nBodies);
+	fill(col, collidables, nCollidables);
+	fill(cv, convex, nConvex);
+	fill(vt, vertices, nVerts);
+	fill(ue, uniqueEdges, nEdges);
+	fill(fc, faces, nFaces);
+	fill(ix, indices, nIndices);
+	b3AlignedObjectArray<b3Contact4Data> contacts;
+	contacts.reserve(maxContacts);
+	int numContacts = 0;
+	for (int i = 0; i < nPairs; i++)
+	{
+		int bodyIndexA = pairs[i].x, bodyIndexB = pairs[i].y;
+		int collidableIndexA = rb[bodyIndexA].m_collidableIdx, collidableIndexB = rb[bodyIndexB].m_collidableIdx;
+		int idx = -1;
+		if (col[collidableIndexA].m_shapeType == SHAPE_CONVEX_HULL && col[collidableIndexB].m_shapeType == SHAPE_CONVEX_HULL)
+			idx = b3ContactConvexConvexSAT(i, bodyIndexA, bodyIndexB, collidableIndexA, collidableIndexB, rb, col, cv, vt, ue, ix, fc, contacts,
+										   numContacts, maxContacts);
+		if (pairContactIndex) pairContactIndex[i] = idx;
+	}
+	for (int i = 0; i < numContacts; i++) memcpy(&out[i], &contacts[i], sizeof(b3Contact4Data));
+	return numContacts;
+}
+
+// setConstraint4 (Bullet3Dynamics/shared/b3ConvertConstraint4.h:62-148) driven like
+// b3Solver::convertToConstraints' host branch (b3Solver.cpp:889-933)
+void ref_build_constraints(const b3b200_contact4* contacts, int n, const b3b200_rigid_body* bodies, const b3b200_inertia* inertias, float dt,
+						   float positionDrift, float positionConstraintCoeff, b3b200_constraint4* out)
+{
+	const b3RigidBodyData* gBodies = (const b3RigidBodyData*)bodies;
+	const b3InertiaData* gShapes = (const b3InertiaData*)inertias;
+	for (int gIdx = 0; gIdx < n; gIdx++)
+	{
+		b3Contact4Data c;
+		memcpy(&c, &contacts[gIdx], sizeof(c));
+		int aIdx = abs(c.m_bodyAPtrAndSignBit);
+		int bIdx = abs(c.m_bodyBPtrAndSignBit);
+		b3ContactConstraint4_t cs;
+		memset(&cs, 0, sizeof(cs));
+		setConstraint4(gBodies[aIdx].m_pos, gBodies[aIdx].m_linVel, gBodies[aIdx].m_angVel, gBodies[aIdx].m_invMass, gShapes[aIdx].m_initInvInertia,
+					   gBodies[bIdx].m_pos, gBodies[bIdx].m_linVel, gBodies[bIdx].m_angVel, gBodies[bIdx].m_invMass, gShapes[bIdx].m_initInvInertia, &c, dt,
+					   positionDrift, positionConstraintCoeff, &cs);
+		cs.m_batchIdx = c.m_batchIdx;
+		memcpy(&out[gIdx], &cs, sizeof(cs));
+	}
+}
+
+// b3ConvexUtility::initializePolyhedralFeatures (b3ConvexUtility.cpp:26) -> flat tables,
+// the way b3GpuNarrowPhase::registerConvexHullShapeInternal lays them out
+// (Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.cpp:234-296).  Returns 0 on success.
+int ref_build_hull(const float* points, int n, b3b200_float4* vertsOut, int* nVerts, b3b200_face* facesOut, int* nFaces, int* indicesOut, int* nIndices,
+				   b3b200_float4* edgesOut, int* nEdges, int cap)
+{
+	b3AlignedObjectArray<b3Vector3> verts;
+	for (int i = 0; i < n; i++) verts.push_back(b3MakeVector3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+	b3ConvexUtility util;
+	if (!util.initializePolyhedralFeatures(&verts[0], verts.size(), true)) return -1;
+	if (util.m_vertices.size() > cap || util.m_faces.size() > cap || util.m_uniqueEdges.size() > cap) return -2;
+	*nVerts = util.m_vertices.size();
+	for (int i = 0; i < util.m_vertices.size(); i++) memcpy(&vertsOut[i], &util.m_vertices[i], 16);
+	*nEdges = util.m_uniqueEdges.size();
+	for (int i = 0; i < util.m_uniqueEdges.size(); i++) memcpy(&edgesOut[i], &util.m_uniqueEdges[i], 16);
+	*nFaces = util.m_faces.size();
+	int ni = 0;
+	for (int i = 0; i < util.m_faces.size(); i++)
+	{
+		facesOut[i].plane.x = util.m_faces[i].m_plane[0];
+		facesOut[i].plane.y = util.m_faces[i].m_plane[1];
+		facesOut[i].plane.z = util.m_faces[i].m_plane[2];
+		facesOut[i].plane.w = util.m_faces[i].m_plane[3];
+		facesOut[i].indexOffset = ni;
+		facesOut[i].numIndices = util.m_faces[i].m_indices.size();
+		facesOut[i].pad1 = facesOut[i].pad2 = 0;
+		for (int p = 0; p < util.m_faces[i].m_indices.size(); p++)
+		{
+			if (ni >= cap * 8) return -2;
+			indicesOut[ni++] = util.m_faces[i].m_indices[p];
+		}
+	}
+	*nIndices = ni;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""ctypes access to the CPU oracle (oracle/_build/liboracle.so) and to the compiled
+reference (oracle/_ref/libb3ref.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from bullet3_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libb3ref.so")
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        if not os.path.exists(ORACLE_SO):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
+        _oracle = C.CDLL(ORACLE_SO)
+    return _oracle
+
+
+def ref_available():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(REF_SO)
+    return _ref
+
+
+P = capi.ptr
+
+
+def _arr(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+class Shapes:
+    """flat shape tables + bodies, as both oracle and reference shim consume them"""
+
+    def __init__(self, tables):
+        self.collidables = _arr(tables["collidables"], capi.collidable_t)
+        self.local_aabbs = _arr(tables["local_aabbs"], capi.aabb_t)
+        self.convex = _arr(tables["convex"], capi.convex_t)
+        self.vertices = _arr(tables["vertices"], np.float32).reshape(-1, 4)
+        self.unique_edges = _arr(tables["unique_edges"], np.float32).reshape(-1, 4)
+        self.faces = _arr(tables["faces"], capi.face_t)
+        self.indices = _arr(tables["indices"], np.int32)
+
+
+def update_aabbs(lib, prefix, bodies, shapes):
+    bodies = _arr(bodies, capi.rigid_body_t)
+    out = np.zeros(len(bodies), capi.aabb_t)
+    getattr(lib, prefix + "update_aabbs")(P(bodies), len(bodies), P(shapes.collidables), P(shapes.local_aabbs), P(out))
+    return out
+
+
+def brute_force_pairs(lib, prefix, aabbs, small_idx, large_idx, max_pairs, fn="brute_force_pairs"):
+    aabbs = _arr(aabbs, capi.aabb_t)
+    small_idx = _arr(small_idx, np.int32)
+    large_idx = _arr(large_idx, np.int32)
+    out = np.zeros(max(max_pairs, 1), capi.int4_t)
+    f = getattr(lib, prefix + fn)
+    n = f(P(aabbs), P(small_idx), len(small_idx), P(large_idx), len(large_idx), P(out), int(max_pairs))
+    return n, out[: min(n, max_pairs)]
+
+
+def integrate(lib, prefix, bodies, dt, damping, gravity):
+    bodies = _arr(bodies, capi.rigid_body_t).copy()
+    g = (C.c_float * 3)(*[float(x) for x in gravity])
+    getattr(lib, prefix + "integrate")(P(bodies), len(bodies), C.c_float(dt), C.c_float(damping), g)
+    return bodies
+
+
+def convex_contacts_oracle(pairs, bodies, shapes, clip_min, clip_max, max_contacts):
+    pairs = _arr(pairs, capi.int4_t)
+    bodies = _arr(bodies, capi.rigid_body_t)
+    out = np.zeros(max(max_contacts, 1), capi.contact4_t)
+    pci = np.full(max(len(pairs), 1), -1, np.int32)
+    n = oracle().orc_convex_contacts(P(pairs), len(pairs), P(bodies), P(shapes.collidables), P(shapes.convex), P(shapes.vertices),
+                                     P(shapes.unique_edges), P(shapes.faces), P(shapes.indices), C.c_float(clip_min), C.c_float(clip_max),
+                                     P(out), int(max_contacts), P(pci))
+    return out[:n], pci[: len(pairs)]
+
+
+def convex_contacts_ref(pairs, bodies, shapes, max_contacts):
+    pairs = _arr(pairs, capi.int4_t)
+    bodies = _arr(bodies, capi.rigid_body_t)
+    out = np.zeros(max(max_contacts, 1), capi.contact4_t)
+    pci = np.full(max(len(pairs), 1), -1, np.int32)
+    n = ref().ref_convex_contacts(P(pairs), len(pairs), P(bodies), len(bodies), P(shapes.collidables), len(shapes.collidables),
+                                  P(shapes.convex), len(shapes.convex), P(shapes.vertices), len(shapes.vertices),
+                                  P(shapes.unique_edges), len(shapes.unique_edges), P(shapes.faces), len(shapes.faces),
+                                  P(shapes.indices), len(shapes.indices), P(out), int(max_contacts), P(pci))
+    return out[:n], pci[: len(pairs)]
+
+
+def colour_contacts(contacts, num_bodies, static_idx):
+    contacts = _arr(contacts, capi.contact4_t)
+    colours = np.zeros(max(len(contacts), 1), np.int32)
+    nb = oracle().orc_colour_contacts(P(contacts), len(contacts), int(num_bodies), int(static_idx), P(colours))
+    return nb, colours[: len(contacts)]
+
+
+def build_constraints(lib, prefix, contacts, bodies, inertias, dt=1.0 / 60.0, drift=0.005, coeff=0.2):
+    contacts = _arr(contacts, capi.contact4_t)
+    bodies = _arr(bodies, capi.rigid_body_t)
+    inertias = _arr(inertias, capi.inertia_t)
+    out = np.zeros(max(len(contacts), 1), capi.constraint4_t)
+    getattr(lib, prefix + "build_constraints")(P(contacts), len(contacts), P(bodies), P(inertias), C.c_float(dt), C.c_float(drift),
+                                               C.c_float(coeff), P(out))
+    return out[: len(contacts)]
+
+
+def solve(constraints, batch_offsets, bodies, inertias, iterations):
+    cs = _arr(constraints, capi.constraint4_t).copy()
+    bodies = _arr(bodies, capi.rigid_body_t).copy()
+    inertias = _arr(inertias, capi.inertia_t)
+    off = _arr(batch_offsets, np.int32)
+    oracle().orc_solve(P(cs), P(off), len(off) - 1, P(bodies), P(inertias), int(iterations))
+    return bodies, cs
+
+
+def oracle_pgs_step_velocities(contacts, bodies, inertias, static_idx, iterations):
+    """colour -> sort by batch -> build rows -> solve, all on the CPU oracle"""
+    contacts = _arr(contacts, capi.contact4_t).copy()
+    nb, colours = colour_contacts(contacts, len(bodies), static_idx)
+    contacts["batchIdx"] = colours
+    order = np.argsort(colours, kind="stable")
+    sorted_contacts = contacts[order]
+    counts = np.bincount(colours, minlength=nb)[:nb] if len(colours) else np.zeros(0, np.int64)
+    off = np.zeros(nb + 1, np.int32)
+    off[1:] = np.cumsum(counts)
+    cs = build_constraints(oracle(), "orc_", sorted_contacts, bodies, inertias)
+    out_bodies, cs = solve(cs, off, bodies, inertias, iterations)
+    return out_bodies, cs, off, colours
+
+
+def sorted_pair_set(pairs):
+    """normalise (min,max), sort lexicographically -> (n,2) int array"""
+    if len(pairs) == 0:
+        return np.zeros((0, 2), np.int32)
+    x = np.minimum(pairs["x"], pairs["y"])
+    y = np.maximum(pairs["x"], pairs["y"])
+    xy = np.stack([x, y], axis=1)
+    order = np.lexsort((xy[:, 1], xy[:, 0]))
+    return xy[order]

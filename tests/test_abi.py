@@ -1,0 +1,93 @@
+"""The C-ABI library loads and exports every symbol include/b3b200.h declares;
+POD layouts match the reference.  No GPU needed."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from bullet3_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b3b200.h")).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*|long long)\s+(b3b200_[a-z0-9_]+)\s*\(", src, re.M)))
+
+
+def test_header_symbols_exported():
+    lib = capi.lib()
+    names = declared_symbols()
+    assert len(names) > 50
+    for n in names:
+        assert hasattr(lib, n), "libb3b200.so does not export %s" % n
+    assert sorted(capi.SYMBOLS) == names
+
+
+def test_pod_sizes_match_reference_abi():
+    for name, (dt, size) in capi.ABI_SIZES.items():
+        assert dt.itemsize == size, name
+    assert capi.rigid_body_t.fields["collidableIdx"][1] == 64
+    assert capi.rigid_body_t.fields["invMass"][1] == 68
+    assert capi.contact4_t.fields["worldNormalOnB"][1] == 64
+    assert capi.contact4_t.fields["frictionCmp"][1] == 82
+    assert capi.contact4_t.fields["bodyA"][1] == 88
+    assert capi.contact4_t.fields["childA"][1] == 96
+    assert capi.constraint4_t.fields["jacCoeffInv"][1] == 96
+    assert capi.constraint4_t.fields["fJacCoeffInv"][1] == 144
+    assert capi.constraint4_t.fields["bodyA"][1] == 160
+    assert capi.convex_t.fields["faceOffset"][1] == 68
+    assert capi.convex_t.fields["numUniqueEdges"][1] == 88
+
+
+def test_pod_sizes_match_compiled_reference():
+    import oracle_api
+
+    if not oracle_api.ref_available():
+        pytest.skip("oracle/_ref not built")
+    out = np.zeros(16, np.int32)
+    n = oracle_api.ref().ref_sizes(capi.ptr(out), 16)
+    assert list(out[:n]) == [80, 96, 16, 48, 32, 96, 32, 16, 112, 176]
+
+
+def test_config_default_matches_b3Config():
+    cfg = capi.default_config()
+    assert cfg["maxConvexBodies"][0] == 128 * 1024
+    assert cfg["maxBroadphasePairs"][0] == 16 * 128 * 1024
+    assert cfg["maxContactCapacity"][0] == 16 * 128 * 1024
+    assert cfg["compoundPairCapacity"][0] == 1024 * 1024
+    assert cfg["maxVerticesPerFace"][0] == 64
+    assert cfg["maxTriConvexPairCapacity"][0] == 256 * 1024
+
+
+def test_host_only_world_registers_and_refuses_gpu_work():
+    from bullet3_b200 import scenes
+
+    w = capi.World(capi.default_config(64), device=-1)
+    col = w.register_convex_points(scenes.box_points(0.5))
+    assert col == 0
+    b = w.register_instance(1.0, (0, 1, 0), scenes.IDENT, col)
+    assert b == 0
+    with pytest.raises(capi.B3Error):
+        w.register_instance(1.0, (0, 1, 0), scenes.IDENT, 7)  # bad collidable -> -1 like the reference
+    with pytest.raises(capi.B3Error):
+        w.upload()
+    t = w.tables()
+    assert len(t["vertices"]) == 8 and len(t["faces"]) == 6 and len(t["unique_edges"]) == 3
+    assert t["convex"]["numVertices"][0] == 8
+    w.close()
+
+
+def test_capacity_errors_return_minus_one():
+    from bullet3_b200 import scenes
+
+    w = capi.World(capi.default_config(2), device=-1)
+    col = w.register_convex_points(scenes.box_points(0.5))
+    w.register_instance(1.0, (0, 0, 0), scenes.IDENT, col)
+    w.register_instance(1.0, (0, 2, 0), scenes.IDENT, col)
+    with pytest.raises(capi.B3Error) as e:
+        w.register_instance(1.0, (0, 4, 0), scenes.IDENT, col)
+    assert "exceeding" in str(e.value)
+    w.close()
