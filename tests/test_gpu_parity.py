@@ -1,0 +1,380 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (libb3b200.so),
+against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * broadphase pair set (sorted) and per-pair contact counts: bit-exact
+  * contact points / normals / depths: 1e-5 relative (they are in fact bit-exact)
+  * post-solve velocities after one step, same batching + iteration count: 1e-4 relative
+  * integration: 1e-6 relative (device sinf/cosf vs libm)
+"""
+import numpy as np
+import pytest
+
+import oracle_api as oa
+import pairbench
+from bullet3_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+G = (0.0, -9.8, 0.0)
+
+
+# ------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("n", [0, 1, 31, 256, 257, 2048, 2049, 65537, 1 << 20])
+def test_radix_sort_kv_matches_host_twin(n):
+    rng = np.random.default_rng(n)
+    d = np.zeros(n, capi.sort_data_t)
+    d["key"] = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    if n > 100:
+        d["key"][: n // 2] &= 0xFF  # many duplicates -> stability matters
+    d["value"] = np.arange(n, dtype=np.uint32)
+    g = d.copy()
+    capi.check(capi.lib().b3b200_radix_sort_kv(0, capi.ptr(g), n), "radix_sort_kv")
+    h = d.copy()
+    oa.oracle().orc_radix_sort_kv(capi.ptr(h), n)
+    assert np.array_equal(g["key"], h["key"]) and np.array_equal(g["value"], h["value"])
+
+
+@pytest.mark.parametrize("n", [1, 1000, 300000])
+def test_radix_sort_keys(n):
+    rng = np.random.default_rng(n)
+    k = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    g = k.copy()
+    capi.check(capi.lib().b3b200_radix_sort_keys(0, capi.ptr(g), n), "radix_sort_keys")
+    assert np.array_equal(g, np.sort(k))
+
+
+@pytest.mark.parametrize("n", [1, 2, 1023, 4096, 4097, 262144 + 3])
+def test_prefix_scan_matches_host_twin(n):
+    import ctypes as C
+
+    rng = np.random.default_rng(n)
+    src = rng.integers(0, 1000, n).astype(np.uint32)
+    dst = np.zeros(n, np.uint32)
+    s = C.c_uint(0)
+    capi.check(capi.lib().b3b200_prefix_scan_u32(0, capi.ptr(src), capi.ptr(dst), n, C.byref(s)), "scan")
+    ref = np.zeros(n, np.uint32)
+    s2 = C.c_uint(0)
+    oa.oracle().orc_prefix_scan(capi.ptr(src), capi.ptr(ref), n, C.byref(s2))
+    assert np.array_equal(dst, ref) and s.value == s2.value
+
+
+def test_bound_search_count_and_fill():
+    rng = np.random.default_rng(3)
+    n, buckets = 100000, 256
+    d = np.zeros(n, capi.sort_data_t)
+    d["key"] = np.sort(rng.integers(0, buckets, n).astype(np.uint32))
+    d["value"] = np.arange(n, dtype=np.uint32)
+    c = np.zeros(buckets, np.uint32)
+    capi.check(capi.lib().b3b200_bound_search_count(0, capi.ptr(d), n, capi.ptr(c), buckets), "bound_search")
+    r = np.zeros(buckets, np.uint32)
+    oa.oracle().orc_bound_search_count(capi.ptr(d), n, capi.ptr(r), buckets)
+    assert np.array_equal(c, r) and c.sum() == n
+    a = np.arange(1000, dtype=np.uint32)
+    capi.check(capi.lib().b3b200_fill_u32(0, capi.ptr(a), 7, 100, 50), "fill")
+    assert (a[50:150] == 7).all() and a[49] == 49 and a[150] == 150
+
+
+# ------------------------------------------------------------------ scene helpers
+def gpu_world(n_side=6, seed=0, rotate=True, spacing=1.6, shapes="mixed", max_bodies=8192):
+    rng = np.random.default_rng(seed)
+    w = capi.World(capi.default_config(max_bodies))
+    scenes.add_ground_box(w, 50.0)
+    cols = [w.register_convex_points(scenes.box_points(1.0))]
+    if shapes == "mixed":
+        cols.append(w.register_convex_points(scenes.tetra_points(1.0)))
+        for nv in (6, 9, 12):
+            cols.append(w.register_convex_points(scenes.random_hull_points(rng, nv, 0.8, 1.3)))
+    for i in range(n_side):
+        for j in range(n_side):
+            for k in range(n_side):
+                p = np.array([i, j, k], np.float64) * spacing + (rng.uniform(-0.2, 0.2, 3) if rotate else 0.0)
+                p[1] += 0.9
+                q = scenes.random_quat(rng) if rotate else scenes.IDENT
+                w.register_instance(1.0, tuple(p), q, cols[int(rng.integers(0, len(cols)))])
+    w.upload()
+    t = w.tables()
+    bodies = t["bodies"].copy()
+    rngv = np.random.default_rng(seed + 1)
+    dyn = bodies["invMass"] != 0
+    bodies["linVel"][dyn, :3] = rngv.normal(size=(dyn.sum(), 3)).astype(np.float32)
+    bodies["angVel"][dyn, :3] = rngv.normal(size=(dyn.sum(), 3)).astype(np.float32) * 2
+    w.write_bodies(bodies)
+    return w, oa.Shapes(t), bodies, t["inertias"]
+
+
+def small_large(bodies):
+    return (np.nonzero(bodies["invMass"] != 0)[0].astype(np.int32), np.nonzero(bodies["invMass"] == 0)[0].astype(np.int32))
+
+
+def rel_close(a, b, tol):
+    scale = np.maximum(np.abs(b), 1.0)
+    return np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)) / scale) <= tol
+
+
+# ------------------------------------------------------------------ AABBs + integrate
+@pytest.mark.parametrize("seed", [0, 1])
+def test_update_aabbs_bit_exact(seed):
+    w, sh, bodies, _ = gpu_world(seed=seed)
+    w.update_aabbs()
+    g = w.aabbs()
+    o = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
+    assert np.array_equal(g["min"].view(np.uint32), o["min"].view(np.uint32))
+    assert np.array_equal(g["max"].view(np.uint32), o["max"].view(np.uint32))
+    assert np.array_equal(g["minIndex"], o["minIndex"]) and np.array_equal(g["maxIndex"], o["maxIndex"])
+
+
+def test_integrate_matches_oracle():
+    w, sh, bodies, _ = gpu_world(seed=2)
+    bodies["angVel"][3, :3] = (1e-5, 0, 0)
+    bodies["angVel"][4, :3] = (300.0, 10.0, 0)
+    w.write_bodies(bodies)
+    w.integrate(1 / 60)
+    g = w.bodies()
+    o = oa.integrate(oa.oracle(), "orc_", bodies, 1 / 60, 0.99, G)
+    for f in ("pos", "linVel", "angVel"):
+        assert np.array_equal(g[f][:, :3].view(np.uint32), o[f][:, :3].view(np.uint32)), f
+    assert rel_close(g["quat"], o["quat"], 1e-6)
+    assert np.array_equal(g["collidableIdx"], o["collidableIdx"]) and np.array_equal(g["invMass"], o["invMass"])
+
+
+# ------------------------------------------------------------------ broadphase
+@pytest.mark.parametrize("kind", [capi.BP_GRID, capi.BP_SAP])
+@pytest.mark.parametrize("seed,n_side", [(0, 6), (1, 10)])
+def test_scene_pair_set_bit_exact(kind, seed, n_side):
+    w, sh, bodies, _ = gpu_world(n_side=n_side, seed=seed)
+    w.set_broadphase(kind)
+    w.update_aabbs()
+    w.find_pairs()
+    g = oa.sorted_pair_set(w.pairs())
+    aabbs = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
+    small, large = small_large(bodies)
+    n, o = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 1 << 22)
+    o = oa.sorted_pair_set(o)
+    assert len(o) > 200
+    assert np.array_equal(g, o)
+    assert w.counters()[4] == 0  # no overflow
+
+
+def run_standalone_bp(kind, aabbs, small, large, max_pairs):
+    bp = capi.Broadphase(kind, len(aabbs), max_pairs)
+    is_large = np.zeros(len(aabbs), bool)
+    is_large[large] = True
+    for i in range(len(aabbs)):
+        (bp.create_large_proxy if is_large[i] else bp.create_proxy)(aabbs["min"][i], aabbs["max"][i], int(aabbs["minIndex"][i]))
+    bp.write_aabbs()
+    bp.calculate_pairs(max_pairs)
+    return bp
+
+
+@pytest.mark.parametrize("kind", [capi.BP_GRID, capi.BP_SAP])
+@pytest.mark.parametrize("margin", [0.0, 2.0, 6.0])
+def test_pairbench_64006_pair_set_bit_exact(kind, margin):
+    """config 2: data/64006GPUAABBs.txt parsed as PairBench does.  The raw dump has no overlapping
+    pair at all, so it is also run with every AABB inflated by `margin` per side."""
+    aabbs, small, large = pairbench.load_pairbench_aabbs()
+    aabbs["min"] -= np.float32(margin)
+    aabbs["max"] += np.float32(margin)
+    max_pairs = min(3 * 1024 * 1024, 16 * len(aabbs))  # PairBench.cpp:554-565
+    bp = run_standalone_bp(kind, aabbs, small, large, max_pairs)
+    g = oa.sorted_pair_set(bp.pairs())
+    n, o = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, max_pairs, fn="sweep_pairs")
+    assert n <= max_pairs
+    o = oa.sorted_pair_set(o)
+    assert bp.num_overlap() == n
+    assert np.array_equal(g, o)
+    if margin > 0:
+        assert n > 1000
+
+
+def test_broadphase_edge_cases():
+    # empty
+    bp = capi.Broadphase(capi.BP_GRID, 16, 64)
+    bp.write_aabbs()
+    bp.calculate_pairs(64)
+    assert bp.num_overlap() == 0
+    # two touching unit AABBs => 1 pair (test/b3DynamicBvhBroadphase/main.cpp), inclusive test
+    for kind in (capi.BP_GRID, capi.BP_SAP):
+        bp = capi.Broadphase(kind, 16, 64)
+        bp.create_proxy((0, 0, 0), (1, 1, 1), 5)
+        bp.create_proxy((1, 0, 0), (2, 1, 1), 9)
+        bp.create_proxy((2.5, 0, 0), (3, 1, 1), 11)
+        bp.write_aabbs()
+        bp.calculate_pairs(64)
+        p = bp.pairs()
+        assert len(p) == 1 and (p["x"][0], p["y"][0]) == (5, 9) and p["z"][0] == -1
+    # overflow clamps and keeps going (b3GpuGridBroadphase.cpp:164-168)
+    bp = capi.Broadphase(capi.BP_GRID, 256, 10)
+    for i in range(64):
+        bp.create_proxy((0, 0, 0), (1, 1, 1), i)
+    bp.write_aabbs()
+    bp.calculate_pairs(10)
+    assert bp.num_overlap() == 10
+    # one huge dynamic AABB among small ones stays exact
+    rng = np.random.default_rng(0)
+    a = np.zeros(500, capi.aabb_t)
+    c = rng.uniform(-20, 20, (500, 3)).astype(np.float32)
+    a["min"], a["max"] = c - 0.5, c + 0.5
+    a["min"][7], a["max"][7] = (-30, -1, -30), (30, 1, 30)
+    a["minIndex"] = np.arange(500)
+    small, large = np.arange(500, dtype=np.int32), np.zeros(0, np.int32)
+    n, o = oa.brute_force_pairs(oa.oracle(), "orc_", a, small, large, 1 << 16)
+    for kind in (capi.BP_GRID, capi.BP_SAP):
+        bp = run_standalone_bp(kind, a, small, large, 1 << 16)
+        assert np.array_equal(oa.sorted_pair_set(bp.pairs()), oa.sorted_pair_set(o))
+
+
+# ------------------------------------------------------------------ narrowphase
+def contact_table(contacts):
+    """sort contacts by (|bodyA|, |bodyB|) for order-independent comparison"""
+    order = np.lexsort((np.abs(contacts["bodyB"]), np.abs(contacts["bodyA"])))
+    return contacts[order]
+
+
+def assert_contacts_match(g, o):
+    assert len(g) == len(o)
+    g, o = contact_table(g), contact_table(o)
+    assert np.array_equal(g["bodyA"], o["bodyA"]) and np.array_equal(g["bodyB"], o["bodyB"])
+    # per-pair contact counts: bit-exact
+    assert np.array_equal(g["worldNormalOnB"][:, 3], o["worldNormalOnB"][:, 3])
+    assert rel_close(g["worldNormalOnB"][:, :3], o["worldNormalOnB"][:, :3], 1e-5)
+    npts = o["worldNormalOnB"][:, 3].astype(int)
+    for k in range(4):
+        m = npts > k
+        assert rel_close(g["worldPosB"][m, k], o["worldPosB"][m, k], 1e-5), k
+    assert np.array_equal(g["frictionCmp"], o["frictionCmp"])
+    assert np.array_equal(g["childA"], o["childA"]) and np.array_equal(g["childB"], o["childB"])
+    exact = all(np.array_equal(g["worldPosB"][npts > k, k].view(np.uint32), o["worldPosB"][npts > k, k].view(np.uint32)) for k in range(4))
+    return exact
+
+
+@pytest.mark.parametrize("clip", [(-1e30, 0.02), (-1.0, 0.0)])
+@pytest.mark.parametrize("seed,rotate,shapes,n_side", [(0, True, "mixed", 6), (1, True, "mixed", 8), (2, False, "box", 6), (3, True, "box", 6)])
+def test_convex_contacts_match_oracle(clip, seed, rotate, shapes, n_side):
+    w, sh, bodies, _ = gpu_world(n_side=n_side, seed=seed, rotate=rotate, shapes=shapes, spacing=1.6 if rotate else 1.999)
+    w.set_contact_clip(*clip)
+    w.update_aabbs()
+    w.find_pairs()
+    pairs = w.pairs()
+    w.compute_contacts()
+    g = w.contacts()
+    o, pci = oa.convex_contacts_oracle(pairs, bodies, sh, clip[0], clip[1], 1 << 18)
+    assert len(o) > 100
+    exact = assert_contacts_match(g, o)
+    assert exact, "contact points are expected to be bit-exact (no FMA contraction on either side)"
+    # pairs[i].z = contact index or -1, same pairs
+    pz = w.pairs()["z"]
+    assert np.array_equal(pz >= 0, pci >= 0)
+
+
+def test_resting_stack_contacts_ties():
+    w = capi.World(capi.default_config(2048))
+    scenes.box_stack(w, 6, 6, 6)
+    w.upload()
+    t = w.tables()
+    sh, bodies = oa.Shapes(t), t["bodies"]
+    w.update_aabbs()
+    w.find_pairs()
+    pairs = w.pairs()
+    w.compute_contacts()
+    o, _ = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
+    assert len(o) > 300
+    assert assert_contacts_match(w.contacts(), o)
+
+
+def test_contact_capacity_clamp():
+    cfg = capi.default_config(2048)
+    cfg["maxContactCapacity"] = 50
+    w = capi.World(cfg)
+    scenes.box_stack(w, 6, 6, 6)
+    w.upload()
+    w.update_aabbs()
+    w.find_pairs()
+    w.compute_contacts()
+    c = w.counters()
+    assert c[1] == 50 and (c[4] & 2)
+
+
+# ------------------------------------------------------------------ solver
+@pytest.mark.parametrize("seed,iters", [(0, 4), (1, 10)])
+def test_pgs_solver_matches_oracle(seed, iters):
+    w, sh, bodies, inertias = gpu_world(n_side=7, seed=seed)
+    w.set_solver(capi.SOLVER_PGS, iters)
+    w.update_aabbs()
+    w.find_pairs()
+    w.compute_contacts()
+    contacts = w.contacts()
+    assert len(contacts) > 200
+    w.solver_setup()
+    # --- same batching: the device colouring equals the oracle's first-fit colouring
+    nb, colours = oa.colour_contacts(contacts, len(bodies), 0)
+    g_contacts = w.contacts()
+    assert np.array_equal(g_contacts["batchIdx"], colours)
+    off = w.batches()
+    assert len(off) - 1 == nb and off[-1] == len(contacts)
+    assert np.array_equal(np.diff(off), np.bincount(colours, minlength=nb))
+    # no two constraints of a batch share a dynamic body
+    cs = w.constraints()
+    for b in range(nb):
+        seg = cs[off[b]: off[b + 1]]
+        assert (seg["batchIdx"] == b).all()
+        ids = np.concatenate([seg["bodyA"], seg["bodyB"]])
+        ids = ids[bodies["invMass"][ids] != 0]
+        assert len(ids) == len(np.unique(ids))
+    # --- constraint rows equal the oracle's (order inside a batch is free -> sort by body ids)
+    g_contacts["batchIdx"] = colours
+    o_cs = oa.build_constraints(oa.oracle(), "orc_", g_contacts, bodies, inertias)
+
+    def key(c):
+        return np.lexsort((c["bodyB"], c["bodyA"], c["batchIdx"]))
+
+    gs, os_ = cs[key(cs)], o_cs[key(o_cs)]
+    for f in ("linear", "worldPos", "center", "jacCoeffInv", "b", "fJacCoeffInv"):
+        assert rel_close(gs[f], os_[f], 1e-5), f
+    # --- velocities after the iterations
+    w.solver_iterate()
+    g_bodies = w.bodies()
+    o_bodies, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, iters)
+    assert rel_close(g_bodies["linVel"][:, :3], o_bodies["linVel"][:, :3], 1e-4)
+    assert rel_close(g_bodies["angVel"][:, :3], o_bodies["angVel"][:, :3], 1e-4)
+    moved = np.abs(g_bodies["linVel"][:, :3] - bodies["linVel"][:, :3]).max()
+    assert moved > 0.1  # the solver did something
+
+
+def test_full_step_matches_oracle_pipeline():
+    """one whole b3b200_step == oracle stages chained on the CPU"""
+    w, sh, bodies, inertias = gpu_world(n_side=6, seed=5)
+    w.set_solver(capi.SOLVER_PGS, 4)
+    w.step(1 / 60)
+    g = w.bodies()
+    aabbs = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
+    small, large = small_large(bodies)
+    _, pairs = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 1 << 22)
+    contacts, _ = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
+    solved, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, 4)
+    o = oa.integrate(oa.oracle(), "orc_", solved, 1 / 60, 0.99, G)
+    for f in ("pos", "quat", "linVel", "angVel"):
+        assert rel_close(g[f][:, :3], o[f][:, :3], 1e-4), f
+    # the fused integrate+AABB kernel left valid AABBs for the next step
+    assert rel_close(w.aabbs()["min"], oa.update_aabbs(oa.oracle(), "orc_", g, sh)["min"], 1e-6)
+
+
+def test_trajectory_energy_and_penetration():
+    """chaotic long run: compare statistics, not states (north_star)"""
+    w = capi.World(capi.default_config(4096))
+    scenes.box_plane_scene(w, 8, 6, 8)
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, 10)
+    for _ in range(240):
+        w.step(1 / 60)
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all() and np.isfinite(b["linVel"]).all()
+    # nothing fell through the ground (top at y=0) and the pile came to rest
+    assert b["pos"][dyn, 1].min() > 0.5
+    speed = np.linalg.norm(b["linVel"][dyn, :3], axis=1)
+    assert np.median(speed) < 0.5
+    w.compute_contacts()
+    c = w.contacts()
+    depth = np.concatenate([c["worldPosB"][c["worldNormalOnB"][:, 3] > k, k, 3] for k in range(4)])
+    assert depth.min() > -0.25  # penetration stays small
