@@ -60,7 +60,7 @@ SOLVER_PGS, SOLVER_JACOBI = 0, 1
 SYMBOLS = [
     "b3b200_last_error", "b3b200_version", "b3b200_launch_count", "b3b200_config_default", "b3b200_create", "b3b200_destroy",
     "b3b200_reset", "b3b200_register_convex", "b3b200_register_convex_points", "b3b200_register_plane", "b3b200_register_sphere",
-    "b3b200_register_compound", "b3b200_register_concave", "b3b200_register_instance", "b3b200_upload", "b3b200_set_gravity",
+    "b3b200_register_compound", "b3b200_register_concave", "b3b200_register_instance", "b3b200_register_instances", "b3b200_upload", "b3b200_set_gravity",
     "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
     "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solver_setup",
@@ -201,6 +201,18 @@ class World:
         r = self.L.b3b200_register_instance(self.h, C.c_float(mass), f3(position), f3(orientation), int(collidable), int(user_index))
         if r < 0:
             raise B3Error("register_instance: " + last_error())
+        return r
+
+    def register_instances(self, masses, positions, orientations, collidables):
+        m = np.ascontiguousarray(masses, np.float32)
+        n = len(m)
+        p = np.zeros((n, 4), np.float32)
+        p[:, :3] = np.asarray(positions, np.float32).reshape(n, -1)[:, :3]
+        q = np.ascontiguousarray(np.asarray(orientations, np.float32).reshape(n, 4))
+        c = np.ascontiguousarray(collidables, np.int32)
+        r = self.L.b3b200_register_instances(self.h, n, ptr(m), ptr(p), ptr(q), ptr(c))
+        if r < 0:
+            raise B3Error("register_instances: " + last_error())
         return r
 
     def upload(self):

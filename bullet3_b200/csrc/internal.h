@@ -18,6 +18,7 @@ enum Counter
 	CTR_COMPOUND_PAIRS = 5,
 	CTR_CONCAVE_PAIRS = 6,
 	CTR_UNCOLOURED = 7,
+	CTR_SURVIVORS = 8,
 	CTR_COUNT = 16
 };
 enum OverflowBits
@@ -133,6 +134,7 @@ struct World
 	DevBuf<unsigned int> dCounters;  // CTR_COUNT
 	DevBuf<b3b200_int4> dCompoundPairs;
 	DevBuf<b3b200_int4> dConcavePairs;
+	DevBuf<int> dSurvivors;  // pair indices that passed the quick SAT reject
 
 	// solver
 	DevBuf<b3b200_constraint4> dConstraints;

@@ -479,21 +479,106 @@ B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB,
 	if (lane == 0 && pairIndex >= 0) a.pairsOut[pairIndex].z = (int)slot;
 }
 
-__global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a)
+// ---------------------------------------------------------------- stage 1: quick reject
+// One THREAD per broadphase pair.  For a convex-convex pair it picks the face of A and the
+// face of B that look most likely to separate (largest local-space dot with the centre
+// offset) and runs the reference's own test (b3TestSepAxis, identical arithmetic) on just
+// those two axes.  Both axes are members of b3FindSeparatingAxis' candidate list, so a
+// separation found here is a separation the reference finds too: the reject is exact, not
+// conservative.  Survivors are compacted (one atomic per warp) for the warp-per-pair stage.
+constexpr int CULL_THREADS = 256;
+
+B3_D int bestFace(const NpArgs& a, const HullRef& h, const float4& localDir)
+{
+	int best = 0;
+	float bestDot = -FLT_MAX;
+	for (int f = 0; f < h.numFaces; f++)
+	{
+		float4 n = __ldg(reinterpret_cast<const float4*>(&a.faces[h.faceOffset + f].plane));
+		float d = dot3(n, localDir);
+		if (d > bestDot)
+		{
+			bestDot = d;
+			best = f;
+		}
+	}
+	return best;
+}
+
+__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __restrict__ survivors)
+{
+	const int numPairs = (int)a.ctr[CTR_PAIRS];
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * CULL_THREADS; base < numPairs; base += gridDim.x * CULL_THREADS)
+	{
+		const int p = base + threadIdx.x;
+		bool keep = false;
+		if (p < numPairs)
+		{
+			const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
+			const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+			if (cA >= 0 && cB >= 0)
+			{
+				keep = true;
+				const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
+				if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
+				{
+					float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
+					float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
+					posA.w = 0.f;
+					posB.w = 0.f;
+					const HullRef hA = loadHull(a.convex, __ldg(&a.collidables[cA].shapeIndex));
+					const HullRef hB = loadHull(a.convex, __ldg(&a.collidables[cB].shapeIndex));
+					const float4 c0 = transformPoint(hA.localCenter, posA, ornA);
+					const float4 c1 = transformPoint(hB.localCenter, posB, ornB);
+					const float4 deltaC2 = sub3(c0, c1);
+					{
+						const int f = bestFace(a, hA, quatRotate(quatInverse(ornA), neg3(deltaC2)));
+						float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
+						float4 axis = quatRotate(ornA, normal);
+						if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+						float d;
+						if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d)) keep = false;
+					}
+					if (keep)
+					{
+						const int f = bestFace(a, hB, quatRotate(quatInverse(ornB), deltaC2));
+						float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+						float4 axis = quatRotate(ornB, normal);
+						if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+						float d;
+						if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d)) keep = false;
+					}
+				}
+			}
+		}
+		const unsigned int m = __ballot_sync(FULL, keep);
+		if (m)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(m));
+			slot = __shfl_sync(FULL, slot, 0);
+			if (keep) survivors[slot + __popc(m & ((1u << lane) - 1u))] = p;
+		}
+	}
+}
+
+// ---------------------------------------------------------------- stage 2: one warp per surviving pair
+__global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a, const int* __restrict__ survivors)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
-	const int numPairs = (int)a.ctr[CTR_PAIRS];
+	const int numSurvivors = (int)a.ctr[CTR_SURVIVORS];
 	const int warpsTotal = gridDim.x * NP_WARPS;
-	for (int p = blockIdx.x * NP_WARPS + warp; p < numPairs; p += warpsTotal)
+	for (int s = blockIdx.x * NP_WARPS + warp; s < numSurvivors; s += warpsTotal)
 	{
+		const int p = survivors[s];
 		const int bodyA = a.pairs[p].x;
 		const int bodyB = a.pairs[p].y;
 		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
-		if (cA < 0 || cB < 0) continue;
 		const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
 		if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
 		{
@@ -519,6 +604,7 @@ int launchNarrowphase(World* w)
 {
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, sizeof(unsigned int), s));
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.pairsOut = w->bp.pairs.ptr;
@@ -535,8 +621,10 @@ int launchNarrowphase(World* w)
 	a.maxContacts = w->cfg.maxContactCapacity;
 	a.clipMin = w->clipMinDist;
 	a.clipMax = w->clipMaxDist;
+	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
+	B3_LAUNCH_CHECK();
 	int blocks = w->smCount * 8;
-	narrowphaseKernel<<<blocks, NP_THREADS, 0, s>>>(a);
+	narrowphaseKernel<<<blocks, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
 	B3_LAUNCH_CHECK();
 	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity);
 	B3_LAUNCH_CHECK();

@@ -496,6 +496,18 @@ extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float
 	return bodyIndex;
 }
 
+extern "C" int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4, const float* orientations4,
+										 const int* collidableIndices)
+{
+	if (!w || n < 0 || (n > 0 && (!masses || !positions4 || !orientations4 || !collidableIndices))) return -1;
+	int first = (int)w->bodies.size();
+	w->bodies.reserve(w->bodies.size() + n);
+	w->inertias.reserve(w->inertias.size() + n);
+	for (int i = 0; i < n; i++)
+		if (b3b200_register_instance(w, masses[i], positions4 + 4 * i, orientations4 + 4 * i, collidableIndices[i], 0) < 0) return -1;
+	return first;
+}
+
 extern "C" int b3b200_upload(b3b200_world* w)
 {
 	W_CHECK(w);
@@ -521,6 +533,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(w->dCollidableIdx.reserve(nb));
 	const size_t nc = std::max(w->cfg.maxContactCapacity, 1);
 	B3_TRY(w->dContacts.reserve(nc));
+	B3_TRY(w->dSurvivors.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
 	B3_TRY(w->dConstraints.reserve(nc));
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));

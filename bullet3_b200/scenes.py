@@ -86,3 +86,31 @@ def mixed_convex_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, rotate=T
                 world.register_instance(1.0, (2.8 * i, 1.5 + 2.8 * j, 2.8 * k), q, shapes[int(kinds[t])])
                 t += 1
     return shapes
+
+
+def bench_convex_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, spacing=(2.2, 2.0, 2.2)):
+    """BASELINE.json config 4, convex part, at bench size (64x64x64 = 262 144 bodies): an equal mix of
+    boxes, tetrahedra and `num_hull_shapes` seeded random hulls (8-16 vertices), seeded random
+    orientations, packed on the config-3 lattice so that neighbours touch from the first step,
+    resting on the static 400-box.  Built with one bulk registration call."""
+    rng = np.random.default_rng(seed)
+    add_ground_box(world)
+    shapes = [world.register_convex_points(box_points(0.8)), world.register_convex_points(tetra_points(0.9))]
+    for _ in range(num_hull_shapes):
+        n = int(rng.integers(8, 17))
+        shapes.append(world.register_convex_points(random_hull_points(rng, n, 0.8, 1.1)))
+    n = nx * ny * nz
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.zeros((n, 4), np.float32)
+    pos[:, 0] = (((j + 1) & 1) * 0.5 + spacing[0] * i).reshape(-1)
+    pos[:, 1] = (1.2 + spacing[1] * j).reshape(-1)
+    pos[:, 2] = (((j + 1) & 1) * 0.5 + spacing[2] * k).reshape(-1)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    # kind: 1/3 boxes, 1/3 tetrahedra, 1/3 hulls
+    kind = rng.integers(0, 3, n)
+    hull = rng.integers(0, num_hull_shapes, n) + 2
+    col = np.where(kind == 2, hull, kind)
+    col = np.asarray(shapes, np.int32)[col]
+    world.register_instances(np.ones(n, np.float32), pos, q.astype(np.float32), col)
+    return shapes

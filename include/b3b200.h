@@ -90,6 +90,9 @@ int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVerti
  * world AABB with margin 0.01, registerRigidBody, createProxy / createLargeProxy. */
 int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
 							 const float* orientation, int collidableIndex, int userIndex);
+/* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
+int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4,
+							  const float* orientations4, const int* collidableIndices);
 /* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150) */
 int b3b200_upload(b3b200_world* w);
 /* b3GpuRigidBodyPipeline::setGravity (b3GpuRigidBodyPipeline.cpp:562-565) */
