@@ -29,7 +29,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 60.0
 ITERS = 10
-SETTLE_STEPS = 60  # untimed: lets the lattice drop into contact before anything is measured
+SETTLE_STEPS = 250  # untimed: the 16-layer lattice drops and comes to rest (contacts/body plateaus) before anything is measured
+LAYERS = 16
 
 
 def parse():
@@ -122,7 +123,7 @@ def make_cpu_sample(side, settle_on_gpu):
 
     dev = 0 if settle_on_gpu else -1
     w = capi.World(capi.default_config(side ** 3 + 16), device=dev)
-    scenes.bench_convex_scene(w, side, side, side)
+    scenes.bench_convex_scene(w, *scene_dims(side))
     t = w.tables()
     bodies = t["bodies"]
     if settle_on_gpu:
@@ -209,7 +210,7 @@ def main():
     side = a.bodies_side
     stream = torch.cuda.Stream()
     w = capi.World(capi.default_config(side ** 3 + 16), device=local_rank, stream=stream.cuda_stream)
-    scenes.bench_convex_scene(w, side, side, side)
+    scenes.bench_convex_scene(w, *scene_dims(side))
     w.upload()
     w.set_solver(capi.SOLVER_PGS, ITERS)
     nbodies = w.num_bodies
@@ -314,10 +315,18 @@ def main():
         dist.destroy_process_group()
 
 
+def scene_dims(side):
+    """side^3 bodies laid out as a flat pile of LAYERS layers (64 -> 128 x 16 x 128)"""
+    ny = min(LAYERS, side)
+    nxz = int(round((side ** 3 / ny) ** 0.5))
+    return nxz, ny, nxz
+
+
 def workload_config(a, world_size):
-    return {"workload": "GpuConvexScene-style %d^3 = %d convex bodies (1/3 boxes, 1/3 tetrahedra, 1/3 seeded 8-16-vertex hulls, random orientations) "
-                        "on a static 400-box; batched PGS %d iterations; dt 1/60; grid broadphase; compounds and concave mesh of BASELINE config 4 "
-                        "are not in this scene yet" % (a.bodies_side, a.bodies_side ** 3, ITERS),
+    nx, ny, nz = scene_dims(a.bodies_side)
+    return {"workload": "GpuConvexScene-style pile of %d x %d x %d = %d convex bodies (1/3 boxes, 1/3 tetrahedra, 1/3 seeded 8-16-vertex hulls, "
+                        "random orientations) settled on a static 400-box; batched PGS %d iterations; dt 1/60; grid broadphase; compounds and "
+                        "concave mesh of BASELINE config 4 are not in this scene yet" % (nx, ny, nz, nx * ny * nz, ITERS),
             "worlds_per_gpu": 1, "parallelism": "independent worlds x%d" % world_size,
             "l2": "per-step working set (pairs+contacts+constraints+bodies) exceeds the 126 MB L2; no explicit flush",
             "settle_steps": SETTLE_STEPS}

@@ -32,37 +32,44 @@
 
 namespace b3b200
 {
-constexpr int SOLVER_THREADS = 256;
+constexpr int SOLVER_THREADS = 512;
 constexpr int MAX_ROUNDS = 1024;
 
 // ---------------------------------------------------------------- grid barrier
-// bar[0] = arrival count, bar[1] = generation.  All CTAs are co-resident
-// (cooperative launch), one thread per CTA spins.
-B3_D void gridBarrier(unsigned int* bar, unsigned int numBlocks)
+// One monotonically increasing arrival counter (zeroed by the host before the launch).
+// Thread 0 of every CTA arrives with a gpu-scope RELEASE add and spins with gpu-scope
+// ACQUIRE loads until all CTAs of this generation have arrived; bar.sync on either side
+// extends the ordering to the rest of the CTA (PTX memory model: causality order through
+// the CTA barrier, release/acquire are cumulative).  All CTAs are co-resident
+// (cooperative launch).
+struct GridBarrier
 {
-	__syncthreads();
-	if (threadIdx.x == 0)
+	unsigned int* counter;
+	unsigned int numBlocks;
+	unsigned int target;
+	B3_D void init(unsigned int* c, unsigned int nb)
 	{
-		__threadfence();
-		volatile unsigned int* vbar = bar;
-		unsigned int gen = vbar[1];
-		unsigned int arrived = atomicAdd(&bar[0], 1u);
-		if (arrived == numBlocks - 1)
+		counter = c;
+		numBlocks = nb;
+		target = 0;
+	}
+	B3_D void sync()
+	{
+		target += numBlocks;
+		__syncthreads();
+		if (threadIdx.x == 0)
 		{
-			vbar[0] = 0;
-			__threadfence();
-			atomicAdd(&bar[1], 1u);
-		}
-		else
-		{
-			while (vbar[1] == gen)
+			unsigned int old;
+			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+			unsigned int v = old + 1;
+			while ((int)(v - target) < 0)
 			{
+				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
 			}
 		}
-		__threadfence();
+		__syncthreads();
 	}
-	__syncthreads();
-}
+};
 
 B3_HD unsigned int hashContact(int a, int b, int ca, int cb)
 {
@@ -226,7 +233,8 @@ B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict_
 
 __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 {
-	const unsigned int nBlocks = gridDim.x;
+	GridBarrier bar;
+	bar.init(s.bar, gridDim.x);
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int nContacts = (int)s.ctr[CTR_CONTACTS];
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		s.batchCursor[i] = 0;
 	}
 	for (int i = tid; i < MAX_ROUNDS; i += stride) s.remaining[i] = 0;
-	gridBarrier(s.bar, nBlocks);
+	bar.sync();
 
 	// ---- phase 1: colouring rounds
 	int round = 0;
@@ -264,7 +272,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 			if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
 			if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
 		}
-		gridBarrier(s.bar, nBlocks);
+		bar.sync();
 		// colour
 		unsigned int left = 0;
 		for (int c = tid; c < nContacts; c += stride)
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		// block-reduce `left`
 		left = __reduce_add_sync(0xffffffffu, left);
 		if ((threadIdx.x & 31) == 0 && left) atomicAdd(&s.remaining[round], left);
-		gridBarrier(s.bar, nBlocks);
+		bar.sync();
 		volatile unsigned int* vr = s.remaining;
 		if (vr[round] == 0) break;
 	}
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 			s.ctr[CTR_COLOUR_ROUNDS] = (unsigned int)(round + 1);
 		}
 	}
-	gridBarrier(s.bar, nBlocks);
+	bar.sync();
 
 	// ---- phase 3: contact -> constraint rows, written in batch order
 	for (int c = tid; c < nContacts; c += stride)
@@ -532,7 +540,8 @@ B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ 
 
 __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s)
 {
-	const unsigned int nBlocks = gridDim.x;
+	GridBarrier bar;
+	bar.init(s.bar, gridDim.x);
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int numBatches = (int)s.ctr[CTR_BATCHES];
@@ -551,7 +560,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s
 					else
 						solveFrictionRows(s, &s.constraints[i]);
 				}
-				gridBarrier(s.bar, nBlocks);
+				bar.sync();
 			}
 		}
 	}
@@ -566,9 +575,10 @@ static int coopLaunch(World* w, const void* fn, void* argStruct)
 		setLastError("solver kernel does not fit on an SM");
 		return B3B200_ERR_CUDA;
 	}
-	if (perSm > 4) perSm = 4;
+	if (perSm > 2) perSm = 2;
 	dim3 grid(w->smCount * perSm), block(SOLVER_THREADS);
 	void* args[] = {argStruct};
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
 	B3_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, w->stream));
 	g_launchCount++;
 	return 0;

@@ -774,6 +774,7 @@ extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)
 	unsigned int c[CTR_COUNT];
 	B3_TRY(readCounters(w, c));
 	for (int i = 0; i < 8; i++) dst8[i] = (int)c[i];
+	dst8[7] = (int)c[CTR_SURVIVORS];
 	return 0;
 }
 extern "C" int b3b200_enable_stage_timing(b3b200_world* w, int enable)

@@ -10,7 +10,9 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 bp = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 t0 = time.time()
 w = capi.World(capi.default_config(n * n * n + 16))
-scenes.bench_convex_scene(w, n, n, n)
+ny = int(sys.argv[5]) if len(sys.argv) > 5 else n
+nx = nz = int(round((n * n * n / ny) ** 0.5))
+scenes.bench_convex_scene(w, nx, ny, nz)
 w.upload()
 w.set_solver(capi.SOLVER_PGS, iters)
 w.set_broadphase(bp)
