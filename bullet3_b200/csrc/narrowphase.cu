@@ -30,6 +30,7 @@ constexpr int MAX_POLY = 64;  // b3Config::m_maxVerticesPerFace (b3Config.h:27)
 struct HullRef
 {
 	float4 localCenter;
+	float radius;  // inscribed radius about localCenter (set at registration)
 	int faceOffset, numFaces, numVertices, vertexOffset, uniqueEdgesOffset, numUniqueEdges;
 };
 
@@ -40,6 +41,7 @@ B3_D HullRef loadHull(const b3b200_convex_polyhedron* __restrict__ convex, int s
 	r.localCenter = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
 	const int4* t = reinterpret_cast<const int4*>(&h->radius);  // radius, faceOffset, numFaces, numVertices
 	int4 a = __ldg(t), b = __ldg(t + 1);                         // vertexOffset, uniqueEdgesOffset, numUniqueEdges, unused
+	r.radius = __int_as_float(a.x);
 	r.faceOffset = a.y;
 	r.numFaces = a.z;
 	r.numVertices = a.w;
@@ -193,7 +195,7 @@ struct NpArgs
 // convex hull vs convex hull: b3ContactConvexConvexSAT (shared/b3ContactConvexConvexSAT.h:407-484)
 B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int shapeA, int shapeB, int childA, int childB,
 						   float4 posA, float4 ornA, float4 posB, float4 ornB, float invMassA, float invMassB,
-						   float4* bufA, float4* bufB, int lane)
+						   float4* bufA, float4* bufB, int* queue, int lane)
 {
 	posA.w = 0.f;
 	posB.w = 0.f;
@@ -206,47 +208,126 @@ B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB,
 	const float4 deltaC2 = sub3(c0, c1);
 
 	const int nFA = hA.numFaces, nFB = hB.numFaces, nEA = hA.numUniqueEdges, nEB = hB.numUniqueEdges;
-	const int total = nFA + nFB + nEA * nEB;
+	const int nF = nFA + nFB;
+	const int total = nF + nEA * nEB;
 	float bestD = FLT_MAX;
 	int bestK = -1;
 	float4 bestAxis = mk4(0, 0, 0);
-	bool separated = false;
-	for (int k = lane; k < total && !separated; k += 32)
+
+	// World-space edge directions are rotated once per hull (the same arithmetic the reference
+	// repeats for every pair of edges) and staged in shared memory.
+	const bool staged = nEA <= MAX_POLY && nEB <= MAX_POLY;
+	if (staged)
 	{
-		float4 axis;
-		if (k < nFA + nFB)
+		for (int e = lane; e < nEA + nEB; e += 32)
 		{
-			const bool onA = k < nFA;
-			const b3b200_face* f = onA ? &a.faces[hA.faceOffset + k] : &a.faces[hB.faceOffset + (k - nFA)];
-			float4 normal = __ldg(reinterpret_cast<const float4*>(&f->plane));
-			axis = quatRotate(onA ? ornA : ornB, normal);
-			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+			const bool onA = e < nEA;
+			const float4 ed = __ldg(&a.uniqueEdges[onA ? hA.uniqueEdgesOffset + e : hB.uniqueEdgesOffset + (e - nEA)]);
+			const float4 w = quatRotate(onA ? ornA : ornB, ed);
+			if (onA)
+				bufA[e] = w;
+			else
+				bufB[e - nEA] = w;
 		}
-		else
-		{
-			int e = k - nFA - nFB;
-			int e0 = e / nEB, e1 = e - e0 * nEB;
-			float4 edge0 = quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
-			float4 edge1 = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
-			float4 cr = cross3(edge0, edge1);
-			if (almostZero(cr)) continue;
-			axis = normalized3(cr);
-			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
-		}
-		float d;
-		if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d))
-		{
-			separated = true;
-			break;
-		}
-		if (d < bestD)
-		{
-			bestD = d;
-			bestK = k;
-			bestAxis = axis;
-		}
+		__syncwarp();
 	}
-	if (__any_sync(FULL, separated)) return;
+	// Exact-safe skip for edge x edge axes: with r = inscribed radii about the hull centres, the
+	// overlap depth along a unit axis n is >= rA + rB - |deltaC2 . n|.  An axis whose lower bound
+	// already exceeds the best depth found so far (2e-4 relative safety margin, >> FP32 rounding)
+	// cannot separate and cannot become the strict minimum: the reference's result is unchanged.
+	const float rsum = (hA.radius + hB.radius) * (1.0f - 2e-4f);
+	float curMin = FLT_MAX;  // warp-uniform upper bound of the final minimum depth
+
+	// Candidate axes (index k = position in the reference's sequential order: faces of A, faces
+	// of B, edge pairs) are filtered 32 at a time and compacted into a per-warp queue, so the
+	// expensive projection test always runs with (nearly) all 32 lanes busy.
+	int qn = 0;
+	int next = 0;
+	const unsigned int ltMask = (1u << lane) - 1u;
+	for (;;)
+	{
+		while (qn < 32 && next < total)
+		{
+			const int k = next + lane;
+			bool cand = false;
+			if (k < nF)
+			{
+				const b3b200_face* f = k < nFA ? &a.faces[hA.faceOffset + k] : &a.faces[hB.faceOffset + (k - nFA)];
+				// a face whose normal is bitwise +-equal to an earlier face's gives the identical depth
+				// and can never win the strict "d < dmin" (flag set at registration, world.cu)
+				cand = __ldg(&f->pad1) == 0;
+			}
+			else if (k < total)
+			{
+				const int e = k - nF;
+				const int e0 = e / nEB, e1 = e - e0 * nEB;
+				const float4 edge0 = staged ? bufA[e0] : quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
+				const float4 edge1 = staged ? bufB[e1] : quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+				const float4 cr = cross3(edge0, edge1);
+				cand = !almostZero(cr);
+				const float S = rsum - curMin;
+				if (cand && S > 0.f)
+				{
+					const float dd = dot3(deltaC2, cr);
+					const float len2 = dot3(cr, cr);
+					if (dd * dd < S * S * len2 * 0.999f) cand = false;
+				}
+			}
+			const unsigned int m = __ballot_sync(FULL, cand);
+			if (cand) queue[qn + __popc(m & ltMask)] = k;
+			qn += __popc(m);
+			// do not mix face and edge candidates of different rounds' bounds: nothing to do, bounds only tighten
+			next += 32;
+			__syncwarp();
+		}
+		if (qn == 0) break;
+		const int take = qn < 32 ? qn : 32;
+		bool separated = false;
+		float d = FLT_MAX;
+		if (lane < take)
+		{
+			const int k = queue[lane];
+			float4 axis;
+			if (k < nF)
+			{
+				const bool onA = k < nFA;
+				const b3b200_face* f = onA ? &a.faces[hA.faceOffset + k] : &a.faces[hB.faceOffset + (k - nFA)];
+				axis = quatRotate(onA ? ornA : ornB, __ldg(reinterpret_cast<const float4*>(&f->plane)));
+			}
+			else
+			{
+				const int e = k - nF;
+				const int e0 = e / nEB, e1 = e - e0 * nEB;
+				const float4 edge0 = staged ? bufA[e0] : quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
+				const float4 edge1 = staged ? bufB[e1] : quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+				axis = normalized3(cross3(edge0, edge1));
+			}
+			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+			if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d))
+				separated = true;
+			else if (d < bestD || (d == bestD && k < bestK))
+			{
+				bestD = d;
+				bestK = k;
+				bestAxis = axis;
+			}
+		}
+		if (__any_sync(FULL, separated)) return;
+		{
+			float m = separated ? FLT_MAX : d;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(FULL, m, o));
+			curMin = fminf(curMin, m);
+		}
+		// pop the processed entries
+		const int rest = qn - take;
+		int moved = 0;
+		if (lane < rest) moved = queue[take + lane];
+		__syncwarp();
+		if (lane < rest) queue[lane] = moved;
+		qn = rest;
+		__syncwarp();
+	}
 	const int myK = bestK;
 	warpArgMin(bestD, bestK);
 	if (bestK < 0) return;
@@ -567,10 +648,12 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __re
 __global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a, const int* __restrict__ survivors)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
+	__shared__ int queueAll[NP_WARPS][64];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
+	int* queue = queueAll[warp];
 	const int numSurvivors = (int)a.ctr[CTR_SURVIVORS];
 	const int warpsTotal = gridDim.x * NP_WARPS;
 	for (int s = blockIdx.x * NP_WARPS + warp; s < numSurvivors; s += warpsTotal)
@@ -585,7 +668,7 @@ __global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a, const 
 			float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
 			float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
 			convexConvexWarp(a, p, bodyA, bodyB, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), -1, -1,
-							 posA, ornA, posB, ornB, posA.w, posB.w, bufA, bufB, lane);
+							 posA, ornA, posB, ornB, posA.w, posB.w, bufA, bufB, queue, lane);
 		}
 		__syncwarp();
 	}

@@ -137,7 +137,39 @@ static int registerConvexInternal(World* w, const b3b200_float4* verts, int nV, 
 		}
 		for (int p = 0; p < f.numIndices; p++) w->indices.push_back(idx[f.indexOffset + p]);
 		f.indexOffset = off;
+		// pad1 = 1 when an earlier face of this hull has the bitwise same or exactly negated normal.
+		// Such a face yields the identical SAT depth as the earlier one, so with the reference's strict
+		// "d < dmin" it can never win: the narrowphase skips it (see narrowphase.cu).
+		f.pad1 = 0;
+		for (int j = 0; j < i; j++)
+		{
+			const b3b200_float4& a = faces[j].plane;
+			const b3b200_float4& b = f.plane;
+			bool same = a.x == b.x && a.y == b.y && a.z == b.z;
+			bool opp = a.x == -b.x && a.y == -b.y && a.z == -b.z;
+			if (same || opp)
+			{
+				f.pad1 = 1;
+				break;
+			}
+		}
 		w->faces.push_back(f);
+	}
+	{
+		// radius = inscribed-sphere radius about localCenter (the reference leaves m_radius unset
+		// unless TEST_INTERNAL_OBJECTS is defined, b3ConvexUtility.cpp:427-436).  Rounded down; used
+		// only for the exact-safe lower bound that lets the SAT skip hopeless edge-edge axes.
+		double rin = 1e300;
+		for (int i = 0; i < nF; i++)
+		{
+			const b3b200_float4& pl = faces[i].plane;
+			double nl = sqrt((double)pl.x * pl.x + (double)pl.y * pl.y + (double)pl.z * pl.z);
+			if (nl < 1e-12) continue;
+			double dist = -((double)pl.x * c.localCenter.x + (double)pl.y * c.localCenter.y + (double)pl.z * c.localCenter.z + (double)pl.w) / nl;
+			if (dist < rin) rin = dist;
+		}
+		if (rin > 1e299 || rin < 0) rin = 0;
+		c.radius = (float)(rin * (1.0 - 1e-5));
 	}
 	c.numVertices = nV;
 	c.vertexOffset = (int)w->vertices.size();
