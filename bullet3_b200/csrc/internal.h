@@ -19,6 +19,7 @@ enum Counter
 	CTR_CONCAVE_PAIRS = 6,
 	CTR_UNCOLOURED = 7,
 	CTR_SURVIVORS = 8,
+	CTR_OVERLAPS = 9,
 	CTR_COUNT = 16
 };
 enum OverflowBits
@@ -135,6 +136,8 @@ struct World
 	DevBuf<b3b200_int4> dCompoundPairs;
 	DevBuf<b3b200_int4> dConcavePairs;
 	DevBuf<int> dSurvivors;  // pair indices that passed the quick SAT reject
+	DevBuf<int> dOverlapPairs;  // pair indices with a penetrating SAT result
+	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes
 
 	// solver
 	DevBuf<b3b200_constraint4> dConstraints;

@@ -193,9 +193,10 @@ struct NpArgs
 };
 
 // convex hull vs convex hull: b3ContactConvexConvexSAT (shared/b3ContactConvexConvexSAT.h:407-484)
-B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int shapeA, int shapeB, int childA, int childB,
-						   float4 posA, float4 ornA, float4 posB, float4 ornB, float invMassA, float invMassB,
-						   float4* bufA, float4* bufB, int* queue, int lane)
+// Part 1: b3FindSeparatingAxis.  Returns false when the hulls are separated; otherwise *sepOut is the
+// minimum-penetration axis (the reference's sepNormalWorldSpace).
+B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 ornA, float4 posB, float4 ornB,
+				  float4* bufA, float4* bufB, int* queue, int lane, float4* sepOut)
 {
 	posA.w = 0.f;
 	posB.w = 0.f;
@@ -312,7 +313,7 @@ B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB,
 				bestAxis = axis;
 			}
 		}
-		if (__any_sync(FULL, separated)) return;
+		if (__any_sync(FULL, separated)) return false;
 		{
 			float m = separated ? FLT_MAX : d;
 #pragma unroll
@@ -330,10 +331,25 @@ B3_D void convexConvexWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB,
 	}
 	const int myK = bestK;
 	warpArgMin(bestD, bestK);
-	if (bestK < 0) return;
+	if (bestK < 0) return false;
 	const int src = __ffs(__ballot_sync(FULL, myK == bestK)) - 1;
 	float4 sep = mk4(__shfl_sync(FULL, bestAxis.x, src), __shfl_sync(FULL, bestAxis.y, src), __shfl_sync(FULL, bestAxis.z, src));
 	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
+	*sepOut = sep;
+	return true;
+}
+
+// Part 2: b3ClipHullHullSingle -- clip the incident face of B against the reference face of A, reduce to
+// <= 4 points, append the contact.
+B3_D void clipWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int shapeA, int shapeB, int childA, int childB,
+				   float4 posA, float4 ornA, float4 posB, float4 ornB, float invMassA, float invMassB, const float4 sep,
+				   float4* bufA, float4* bufB, int lane)
+{
+	posA.w = 0.f;
+	posB.w = 0.f;
+	const HullRef hA = loadHull(a.convex, shapeA);
+	const HullRef hB = loadHull(a.convex, shapeB);
+	const int nFA = hA.numFaces, nFB = hB.numFaces;
 
 	// b3ClipHullHullSingle round-trips both orientations through a b3Transform
 	// (setRotation -> getRotation, shared/b3ContactConvexConvexSAT.h:323-337); the
@@ -644,8 +660,11 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __re
 	}
 }
 
-// ---------------------------------------------------------------- stage 2: one warp per surviving pair
-__global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a, const int* __restrict__ survivors)
+// ---------------------------------------------------------------- stage 2: SAT, one warp per surviving pair
+// Small, hot kernel (fits the instruction cache, ~70 registers): finds the minimum-penetration axis
+// and appends (pair, axis) to the overlap list.
+__global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int* __restrict__ survivors, int* __restrict__ overlapPairs,
+															   float4* __restrict__ overlapSep)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
 	__shared__ int queueAll[NP_WARPS][64];
@@ -665,11 +684,43 @@ __global__ void __launch_bounds__(NP_THREADS) narrowphaseKernel(NpArgs a, const 
 		const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
 		if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
 		{
-			float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
-			float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
-			convexConvexWarp(a, p, bodyA, bodyB, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), -1, -1,
-							 posA, ornA, posB, ornB, posA.w, posB.w, bufA, bufB, queue, lane);
+			const float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
+			const float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
+			float4 sep;
+			const bool hit = satWarp(a, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), posA, ornA, posB, ornB, bufA, bufB,
+									 queue, lane, &sep);
+			if (hit && lane == 0)
+			{
+				const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
+				overlapPairs[slot] = p;
+				overlapSep[slot] = sep;
+			}
 		}
+		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------- stage 3: clipping + reduction + append
+__global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int* __restrict__ overlapPairs, const float4* __restrict__ overlapSep)
+{
+	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	float4* bufA = bufAll[warp][0];
+	float4* bufB = bufAll[warp][1];
+	const int numOverlaps = (int)a.ctr[CTR_OVERLAPS];
+	const int warpsTotal = gridDim.x * NP_WARPS;
+	for (int s = blockIdx.x * NP_WARPS + warp; s < numOverlaps; s += warpsTotal)
+	{
+		const int p = overlapPairs[s];
+		const float4 sep = overlapSep[s];
+		const int bodyA = a.pairs[p].x;
+		const int bodyB = a.pairs[p].y;
+		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+		const float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
+		const float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
+		clipWarp(a, p, bodyA, bodyB, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), -1, -1, posA, ornA, posB, ornB,
+				 posA.w, posB.w, mk4(sep.x, sep.y, sep.z), bufA, bufB, lane);
 		__syncwarp();
 	}
 }
@@ -687,7 +738,7 @@ int launchNarrowphase(World* w)
 {
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
-	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.pairsOut = w->bp.pairs.ptr;
@@ -706,8 +757,9 @@ int launchNarrowphase(World* w)
 	a.clipMax = w->clipMaxDist;
 	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
 	B3_LAUNCH_CHECK();
-	int blocks = w->smCount * 8;
-	narrowphaseKernel<<<blocks, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
+	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
+	B3_LAUNCH_CHECK();
+	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity);
 	B3_LAUNCH_CHECK();

@@ -566,6 +566,8 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	const size_t nc = std::max(w->cfg.maxContactCapacity, 1);
 	B3_TRY(w->dContacts.reserve(nc));
 	B3_TRY(w->dSurvivors.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
+	B3_TRY(w->dOverlapPairs.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
+	B3_TRY(w->dOverlapSep.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
 	B3_TRY(w->dConstraints.reserve(nc));
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));
