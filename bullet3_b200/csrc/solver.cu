@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		// claim
 		for (int c = tid; c < nContacts; c += stride)
 		{
-			if (s.contactColour[c] >= 0) continue;
+			if (s.contactColour[c] != -1) continue;
 			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
 			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
 			const int a = abs(ids.z), b = abs(ids.w);
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		unsigned int left = 0;
 		for (int c = tid; c < nContacts; c += stride)
 		{
-			if (s.contactColour[c] >= 0) continue;
+			if (s.contactColour[c] != -1) continue;
 			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
 			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
 			const int a = abs(ids.z), b = abs(ids.w);
@@ -309,8 +309,14 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 				colour = 64 + __ffsll((long long)~m1) - 1;
 			else
 			{
-				colour = MAX_BATCHES - 1;
+				// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
+				// ("batchIdx>=B3_MAX_NUM_BATCHES", b3GpuPgsContactSolver.cpp:1497-1502); here the
+				// contact is left out of this step's solve and the overflow flag is raised.
+				s.contactColour[c] = -2;
+				if (!aStatic) s.bodyPrio[a] = 0ull;
+				if (!bStatic) s.bodyPrio[b] = 0ull;
 				atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+				continue;
 			}
 			unsigned long long bit = 1ull << (colour & 63);
 			int word = colour >> 6;
@@ -343,7 +349,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		int numBatches = 0;
 		for (int base = 0; base < MAX_BATCHES; base += 32)
 		{
-			unsigned int v = s.batchCount[base + threadIdx.x];
+			// every batch is padded to a multiple of 32 slots, so that a warp-row of the iteration
+			// kernels never straddles two batches (padding slots are marked invalid below)
+			const unsigned int raw = s.batchCount[base + threadIdx.x];
+			unsigned int v = (raw + 31u) & ~31u;
 			unsigned int incl = v;
 #pragma unroll
 			for (int o = 1; o < 32; o <<= 1)
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 				if ((int)threadIdx.x >= o) incl += t;
 			}
 			s.batchOffset[base + threadIdx.x] = run + incl - v;
-			unsigned int nz = __ballot_sync(0xffffffffu, v != 0);
+			unsigned int nz = __ballot_sync(0xffffffffu, raw != 0);
 			if (nz) numBatches = base + 32 - __clz(nz);
 			run += __shfl_sync(0xffffffffu, incl, 31);
 		}
@@ -366,6 +375,23 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	bar.sync();
 
 	// ---- phase 3: contact -> constraint rows, written in batch order
+	for (int k = tid; k < MAX_BATCHES * 32; k += stride)
+	{
+		const int bch = k >> 5;
+		const unsigned int slot = s.batchOffset[bch] + s.batchCount[bch] + (unsigned int)(k & 31);
+		if (slot < s.batchOffset[bch + 1])
+		{
+			float4* dw = reinterpret_cast<float4*>(&s.constraints[slot]);
+			dw[6] = mk4(0, 0, 0, 0);
+			dw[9] = mk4(0, 0, 0, 0);
+			int4 tail;
+			tail.x = -1;  // bodyA = 0xffffffff marks a padding slot
+			tail.y = -1;
+			tail.z = -1;
+			tail.w = 0;
+			reinterpret_cast<int4*>(dw)[10] = tail;
+		}
+	}
 	for (int c = tid; c < nContacts; c += stride)
 	{
 		int colour = s.contactColour[c];
@@ -386,6 +412,8 @@ struct IterArgs
 	const unsigned int* batchOffset;
 	unsigned int* bar;
 	int iterations;
+	const unsigned long long* bodyMask;  // colours in use per body (from the setup kernel)
+	unsigned int* seq;                   // per-body progress counter (dataflow kernel)
 };
 
 // solveContact<false> (b3Solver.cpp:187-266)
@@ -398,10 +426,11 @@ B3_D void solveNormalRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs
 	float4 applied = cw[8];
 	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
 	const int aIdx = tail.x, bIdx = tail.y;
+	if (aIdx < 0) return;  // padding slot
 	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
 	const float invMassA = posA.w, invMassB = posB.w;
-	float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
-	float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
+	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
+	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
 	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
 	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
 	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
@@ -442,13 +471,13 @@ B3_D void solveNormalRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs
 	cw[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
 	if (invMassA != 0.f)
 	{
-		s.vel[2 * aIdx] = linVelA;
-		s.vel[2 * aIdx + 1] = angVelA;
+		__stcg(&s.vel[2 * aIdx], linVelA);
+		__stcg(&s.vel[2 * aIdx + 1], angVelA);
 	}
 	if (invMassB != 0.f)
 	{
-		s.vel[2 * bIdx] = linVelB;
-		s.vel[2 * bIdx + 1] = angVelB;
+		__stcg(&s.vel[2 * bIdx], linVelB);
+		__stcg(&s.vel[2 * bIdx + 1], angVelB);
 	}
 }
 
@@ -465,8 +494,8 @@ B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ 
 	const int aIdx = tail.x, bIdx = tail.y;
 	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
 	const float invMassA = posA.w, invMassB = posB.w;
-	float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
-	float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
+	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
+	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
 	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
 	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
 	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
@@ -528,13 +557,13 @@ B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ 
 	cw[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
 	if (invMassA != 0.f)
 	{
-		s.vel[2 * aIdx] = linVelA;
-		s.vel[2 * aIdx + 1] = angVelA;
+		__stcg(&s.vel[2 * aIdx], linVelA);
+		__stcg(&s.vel[2 * aIdx + 1], angVelA);
 	}
 	if (invMassB != 0.f)
 	{
-		s.vel[2 * bIdx] = linVelB;
-		s.vel[2 * bIdx + 1] = angVelB;
+		__stcg(&s.vel[2 * bIdx], linVelB);
+		__stcg(&s.vel[2 * bIdx + 1], angVelB);
 	}
 }
 
@@ -552,8 +581,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s
 		{
 			for (int b = 0; b < numBatches; b++)
 			{
+				// warp-rows are dealt round-robin to the CTAs so that a small batch still uses every SM
 				const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
-				for (int i = begin + tid; i < end; i += stride)
+				const int warpInBlock = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
+				for (int i = begin + ((warpInBlock * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31); i < end; i += stride)
 				{
 					if (phase == 0)
 						solveNormalRows(s, &s.constraints[i]);
@@ -561,6 +592,87 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s
 						solveFrictionRows(s, &s.constraints[i]);
 				}
 				bar.sync();
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------- dataflow iterations
+// Same Gauss-Seidel order as solverIterateKernel, no grid-wide barriers.  Within a body, the
+// constraints touching it are totally ordered by (round, batch); constraints that share no
+// dynamic body commute exactly.  So each constraint only has to wait for ITS two bodies:
+// every dynamic body carries a progress counter seq[b]; constraint c with colour k is the
+// rank(c,b) = popc(mask[b] & below(k))-th user of body b in every round, and may run in round r
+// when seq[b] == r * deg(b) + rank(c,b) for both bodies.  It then solves, publishes the new
+// velocities and bumps both counters (release/acquire at gpu scope).  Threads own constraints
+// i = tid, tid+T, ... of the batch-sorted array and visit them in ascending order each round,
+// which is consistent with the global (round, batch) order, so the earliest unfinished
+// constraint is always runnable: no deadlock as long as all threads are resident
+// (cooperative launch).  Ready lanes solve inside the polling loop, so lanes of one warp never
+// wait for each other at a reconvergence point.
+constexpr int DF_THREADS = 256;
+
+B3_D unsigned int ldRelaxed(const unsigned int* p)
+{
+	unsigned int v;
+	asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+B3_D void fenceAcqRel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+B3_D void stRelease(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+B3_D void rankAndDegree(const unsigned long long* __restrict__ mask, int body, int colour, bool& dyn, unsigned int& rank, unsigned int& deg)
+{
+	const unsigned long long m0 = __ldg(&mask[2 * body]), m1 = __ldg(&mask[2 * body + 1]);
+	const unsigned long long bit = 1ull << (colour & 63);
+	dyn = ((colour < 64 ? m0 : m1) & bit) != 0ull;
+	deg = __popcll(m0) + __popcll(m1);
+	rank = colour < 64 ? __popcll(m0 & (bit - 1ull)) : __popcll(m0) + __popcll(m1 & (bit - 1ull));
+}
+
+__global__ void __launch_bounds__(DF_THREADS) solverIterateDataflowKernel(IterArgs s)
+{
+	const int lane = threadIdx.x & 31;
+	const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
+	const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int nRows = (int)(s.batchOffset[MAX_BATCHES] >> 5);  // batches are padded to multiples of 32
+	const int rounds = 2 * s.iterations;
+	for (int round = 0; round < rounds; round++)
+	{
+		for (int row = warpId; row < nRows; row += warpsTotal)
+		{
+			const int i = row * 32 + lane;
+			const int4 tail = reinterpret_cast<const int4*>(&s.constraints[i])[10];
+			const int a = tail.x, b = tail.y;
+			const bool valid = a >= 0;
+			bool dynA = false, dynB = false;
+			unsigned int expA = 0, expB = 0;
+			if (valid)
+			{
+				unsigned int rank, deg;
+				rankAndDegree(s.bodyMask, a, tail.z, dynA, rank, deg);
+				expA = (unsigned int)round * deg + rank;
+				rankAndDegree(s.bodyMask, b, tail.z, dynB, rank, deg);
+				expB = (unsigned int)round * deg + rank;
+			}
+			// All 32 constraints of a row belong to one batch, hence are mutually independent:
+			// the warp waits until every lane's two bodies have reached this constraint's turn.
+			for (;;)
+			{
+				bool ready = true;
+				if (dynA) ready = ldRelaxed(&s.seq[a]) == expA;
+				if (ready && dynB) ready = ldRelaxed(&s.seq[b]) == expB;
+				if (__all_sync(0xffffffffu, ready)) break;
+			}
+			fenceAcqRel();
+			if (valid)
+			{
+				if (round < s.iterations)
+					solveNormalRows(s, &s.constraints[i]);
+				else
+					solveFrictionRows(s, &s.constraints[i]);
+				if (dynA) stRelease(&s.seq[a], expA + 1u);
+				if (dynB) stRelease(&s.seq[b], expB + 1u);
 			}
 		}
 	}
@@ -620,9 +732,27 @@ int launchSolverIterate(World* w)
 	s.batchOffset = w->dBatchOffset.ptr;
 	s.bar = w->dGridBarrier.ptr;
 	s.iterations = w->solverIterations;
-	int r = coopLaunch(w, (const void*)solverIterateKernel, &s);
+	s.bodyMask = w->dBodyMask.ptr;
+	s.seq = w->dBodyCount.ptr;
 	w->soaDirty = true;
-	return r;
+	if (w->solverDataflow)
+	{
+		// all threads must be co-resident: grid = SMs x occupancy, cooperative launch
+		int perSm = 0;
+		B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)solverIterateDataflowKernel, DF_THREADS, 0));
+		if (perSm < 1)
+		{
+			setLastError("solver kernel does not fit on an SM");
+			return B3B200_ERR_CUDA;
+		}
+		B3_CUDA_CHECK(cudaMemsetAsync(w->dBodyCount.ptr, 0, sizeof(unsigned int) * (size_t)std::max(w->numBodies, 1), w->stream));
+		dim3 grid(w->smCount * perSm), block(DF_THREADS);
+		void* args[] = {&s};
+		B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateDataflowKernel, grid, block, args, 0, w->stream));
+		g_launchCount++;
+		return 0;
+	}
+	return coopLaunch(w, (const void*)solverIterateKernel, &s);
 }
 
 int launchJacobi(World* w)

@@ -568,7 +568,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(w->dSurvivors.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
 	B3_TRY(w->dOverlapPairs.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
 	B3_TRY(w->dOverlapSep.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
-	B3_TRY(w->dConstraints.reserve(nc));
+	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));
 	B3_TRY(w->dBodyPrio.reserve(2 * nb));
@@ -604,6 +604,12 @@ extern "C" int b3b200_set_broadphase(b3b200_world* w, int kind)
 {
 	if (!w || (kind != B3B200_BP_SAP && kind != B3B200_BP_GRID)) return B3B200_ERR_INVALID;
 	w->bp.kind = kind;
+	return 0;
+}
+extern "C" int b3b200_set_solver_dataflow(b3b200_world* w, int enable)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->solverDataflow = enable != 0;
 	return 0;
 }
 extern "C" int b3b200_set_contact_clip(b3b200_world* w, float minDist, float maxDist)

@@ -99,6 +99,9 @@ int b3b200_upload(b3b200_world* w);
 int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
 int b3b200_set_solver(b3b200_world* w, int kind, int iterations);
 int b3b200_set_broadphase(b3b200_world* w, int kind);
+/* PGS iteration kernel: 0 = one grid barrier per batch (default), 1 = barrier-free per-body dataflow ordering (experimental).
+ * Both execute the same Gauss-Seidel order and give bit-identical velocities. */
+int b3b200_set_solver_dataflow(b3b200_world* w, int enable);
 /* clip window of the convex-convex clipper: the reference kernels use
  * (-1e30, 0.02) (satClipHullContacts.cl:916-917), the shared CPU header (-1, 0)
  * (b3ContactConvexConvexSAT.h:320-321).  Default = the kernel constants. */
@@ -132,7 +135,8 @@ int b3b200_get_aabbs(b3b200_world* w, b3b200_aabb* dst, int n);
 int b3b200_get_pairs(b3b200_world* w, b3b200_int4* dst, int capacity, int* numPairs);
 int b3b200_get_contacts(b3b200_world* w, b3b200_contact4* dst, int capacity, int* numContacts);
 int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numContacts);
-/* constraints in solve order (sorted by batch); batchOffsets has numBatches+1 entries */
+/* constraints in solve order (sorted by batch); batchOffsets has numBatches+1 entries.  Every batch is
+ * padded to a multiple of 32 slots; padding slots have batchIdx == -1 and bodyA == 0xffffffff. */
 int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, int capacity, int* numConstraints);
 int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches);
 /* counters of the last step: [0]=pairs [1]=contacts [2]=batches [3]=colouring rounds

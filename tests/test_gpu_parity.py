@@ -296,10 +296,12 @@ def test_contact_capacity_clamp():
 
 
 # ------------------------------------------------------------------ solver
+@pytest.mark.parametrize("dataflow", [True, False])
 @pytest.mark.parametrize("seed,iters", [(0, 4), (1, 10)])
-def test_pgs_solver_matches_oracle(seed, iters):
+def test_pgs_solver_matches_oracle(seed, iters, dataflow):
     w, sh, bodies, inertias = gpu_world(n_side=7, seed=seed)
     w.set_solver(capi.SOLVER_PGS, iters)
+    w.set_solver_dataflow(dataflow)
     w.update_aabbs()
     w.find_pairs()
     w.compute_contacts()
@@ -311,12 +313,14 @@ def test_pgs_solver_matches_oracle(seed, iters):
     g_contacts = w.contacts()
     assert np.array_equal(g_contacts["batchIdx"], colours)
     off = w.batches()
-    assert len(off) - 1 == nb and off[-1] == len(contacts)
-    assert np.array_equal(np.diff(off), np.bincount(colours, minlength=nb))
+    cs_all = w.constraints()
+    assert len(off) - 1 == nb and off[-1] == len(cs_all) and (np.diff(off) % 32 == 0).all()
+    counts = np.array([(cs_all[off[b]: off[b + 1]]["batchIdx"] >= 0).sum() for b in range(nb)])
+    assert np.array_equal(counts, np.bincount(colours, minlength=nb)) and counts.sum() == len(contacts)
     # no two constraints of a batch share a dynamic body
-    cs = w.constraints()
     for b in range(nb):
-        seg = cs[off[b]: off[b + 1]]
+        seg = cs_all[off[b]: off[b + 1]]
+        seg = seg[seg["batchIdx"] >= 0]  # drop the padding slots
         assert (seg["batchIdx"] == b).all()
         ids = np.concatenate([seg["bodyA"], seg["bodyB"]])
         ids = ids[bodies["invMass"][ids] != 0]
@@ -328,6 +332,7 @@ def test_pgs_solver_matches_oracle(seed, iters):
     def key(c):
         return np.lexsort((c["bodyB"], c["bodyA"], c["batchIdx"]))
 
+    cs = cs_all[cs_all["batchIdx"] >= 0]
     gs, os_ = cs[key(cs)], o_cs[key(o_cs)]
     for f in ("linear", "worldPos", "center", "jacCoeffInv", "b", "fJacCoeffInv"):
         assert rel_close(gs[f], os_[f], 1e-5), f
@@ -339,6 +344,22 @@ def test_pgs_solver_matches_oracle(seed, iters):
     assert rel_close(g_bodies["angVel"][:, :3], o_bodies["angVel"][:, :3], 1e-4)
     moved = np.abs(g_bodies["linVel"][:, :3] - bodies["linVel"][:, :3]).max()
     assert moved > 0.1  # the solver did something
+
+
+def test_dataflow_and_barrier_kernels_bit_identical():
+    """the two iteration kernels execute the same Gauss-Seidel order"""
+    out = []
+    for mode in (True, False):
+        w, sh, bodies, inertias = gpu_world(n_side=10, seed=7)
+        w.set_solver(capi.SOLVER_PGS, 10)
+        w.set_solver_dataflow(mode)
+        w.update_aabbs()
+        w.find_pairs()
+        w.compute_contacts()
+        w.solve_contacts()
+        out.append(w.bodies())
+    for f in ("linVel", "angVel"):
+        assert np.array_equal(out[0][f].view(np.uint32), out[1][f].view(np.uint32)), f
 
 
 def test_full_step_matches_oracle_pipeline():

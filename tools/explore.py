@@ -16,6 +16,7 @@ scenes.bench_convex_scene(w, nx, ny, nz)
 w.upload()
 w.set_solver(capi.SOLVER_PGS, iters)
 w.set_broadphase(bp)
+w.set_solver_dataflow(int(os.environ.get('DATAFLOW', '1')))
 print("setup %.1fs bodies=%d" % (time.time() - t0, w.num_bodies), flush=True)
 w.enable_stage_timing(True)
 for s in range(steps):
