@@ -1,0 +1,35 @@
+// b3GpuRigidBodyPipeline with the reference's public surface
+// (src/Bullet3OpenCL/RigidBody/b3GpuRigidBodyPipeline.h:25-68) on top of the C ABI (include/b3b200.h).
+#ifndef B3_GPU_RIGIDBODY_PIPELINE_H
+#define B3_GPU_RIGIDBODY_PIPELINE_H
+#include "Bullet3OpenCL/Initialize/b3OpenCLInclude.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
+#include "Bullet3Common/b3AlignedObjectArray.h"
+
+class b3GpuRigidBodyPipeline
+{
+protected:
+	class b3GpuNarrowPhase* m_np;
+	class b3B200BroadphaseBase* m_bp;
+	b3Config m_config;
+
+public:
+	b3GpuRigidBodyPipeline(cl_context ctx, cl_device_id device, cl_command_queue q, class b3GpuNarrowPhase* narrowphase,
+						   class b3GpuBroadphaseInterface* broadphaseSap, struct b3DynamicBvhBroadphase* broadphaseDbvt, const b3Config& config);
+	virtual ~b3GpuRigidBodyPipeline();
+
+	void stepSimulation(float deltaTime);
+	void integrate(float timeStep);
+	void setupGpuAabbsFull();
+	// declared but never defined in the reference; here it forwards to the narrowphase
+	int registerConvexPolyhedron(class b3ConvexUtility* convex);
+	int registerPhysicsInstance(float mass, const float* position, const float* orientation, int collisionShapeIndex, int userData, bool writeInstanceToGpu);
+	void writeAllInstancesToGpu();
+	void setGravity(const float* grav);
+	void reset();
+	// B200 additions: solver selection (the reference uses the global gUseJacobi) and iteration count
+	void setSolver(bool jacobi, int iterations);
+	cl_mem getBodyBuffer();
+	int getNumBodies() const;
+};
+#endif

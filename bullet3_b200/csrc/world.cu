@@ -480,23 +480,14 @@ extern "C" int b3b200_register_concave(b3b200_world* w, const float* vertices, i
 	return -1;
 }
 
-extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex, int userIndex)
+static int registerBodyCommon(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex,
+							  const float* aabbMin, const float* aabbMax)
 {
-	(void)userIndex;
-	if (!w || !position || !orientation) return -1;
-	if (collidableIndex < 0 || collidableIndex >= (int)w->collidables.size())
-	{
-		setLastError("registerPhysicsInstance using invalid collidableIndex");
-		return -1;
-	}
 	if ((int)w->bodies.size() >= w->cfg.maxConvexBodies)
 	{
 		setLastError("registerRigidBody: exceeding the number of rigid bodies, %d > %d", (int)w->bodies.size(), w->cfg.maxConvexBodies);
 		return -1;
 	}
-	const b3b200_aabb& la = w->localAabbs[collidableIndex];
-	float aabbMin[3], aabbMax[3];
-	transformAabbHost(la.min, la.max, 0.01f, position, orientation, aabbMin, aabbMax);
 	// b3GpuNarrowPhase::registerRigidBody (b3GpuNarrowPhase.cpp:816-908)
 	b3b200_rigid_body b;
 	memset(&b, 0, sizeof(b));
@@ -526,6 +517,33 @@ extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float
 	}
 	w->uploaded = false;
 	return bodyIndex;
+}
+
+extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex, int userIndex)
+{
+	(void)userIndex;
+	if (!w || !position || !orientation) return -1;
+	if (collidableIndex < 0 || collidableIndex >= (int)w->collidables.size())
+	{
+		setLastError("registerPhysicsInstance using invalid collidableIndex");
+		return -1;
+	}
+	const b3b200_aabb& la = w->localAabbs[collidableIndex];
+	float aabbMin[3], aabbMax[3];
+	transformAabbHost(la.min, la.max, 0.01f, position, orientation, aabbMin, aabbMax);
+	return registerBodyCommon(w, mass, position, orientation, collidableIndex, aabbMin, aabbMax);
+}
+
+extern "C" int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const float* position, const float* orientation,
+									const float* aabbMin3, const float* aabbMax3)
+{
+	if (!w || !position || !orientation || !aabbMin3 || !aabbMax3) return -1;
+	if (collidableIndex < 0 || collidableIndex >= (int)w->collidables.size())
+	{
+		setLastError("registerRigidBody using invalid collidableIndex");
+		return -1;
+	}
+	return registerBodyCommon(w, mass, position, orientation, collidableIndex, aabbMin3, aabbMax3);
 }
 
 extern "C" int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4, const float* orientations4,
@@ -896,4 +914,13 @@ extern "C" int b3b200_get_table(b3b200_world* w, int which, void* dst, int capac
 			return copyTable(w->inertias, dst, capacity, count);
 	}
 	return B3B200_ERR_INVALID;
+}
+
+extern "C" int b3b200_device_to_host(void* dstHost, const void* srcDevice, unsigned long long bytes, int device)
+{
+	if (!dstHost || !srcDevice) return B3B200_ERR_INVALID;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	B3_CUDA_CHECK(cudaDeviceSynchronize());
+	B3_CUDA_CHECK(cudaMemcpy(dstHost, srcDevice, (size_t)bytes, cudaMemcpyDeviceToHost));
+	return 0;
 }

@@ -90,6 +90,11 @@ int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVerti
  * world AABB with margin 0.01, registerRigidBody, createProxy / createLargeProxy. */
 int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
 							 const float* orientation, int collidableIndex, int userIndex);
+/* b3GpuNarrowPhase::registerRigidBody (b3GpuNarrowPhase.cpp:816-908) with a caller-supplied world AABB (used for the
+ * box-approximated inertia, :876-897).  Unlike the reference this also creates the broadphase proxy, because the world
+ * keeps AABB index == body index. */
+int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const float* position, const float* orientation,
+						 const float* aabbMin3, const float* aabbMax3);
 /* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
 int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4,
 							  const float* orientations4, const int* collidableIndices);
@@ -189,6 +194,9 @@ int b3b200_bp_get_pairs(b3b200_broadphase* bp, b3b200_int4* dst, int capacity, i
 int b3b200_bp_device_pairs(b3b200_broadphase* bp, void** devicePtr);    /* getOverlappingPairBuffer */
 int b3b200_bp_device_aabbs(b3b200_broadphase* bp, void** devicePtr);    /* getAabbBufferWS */
 int b3b200_bp_last_ms(b3b200_broadphase* bp, float* ms);
+
+/* plain device -> host copy of a buffer obtained from b3b200_device_buffer / b3b200_bp_device_* (synchronous) */
+int b3b200_device_to_host(void* dstHost, const void* srcDevice, unsigned long long bytes, int device);
 
 /* ------------------------------------------------- parallel primitives */
 /* b3RadixSort32CL::execute (b3RadixSort32CL.cpp:12-646): stable LSD sort of
