@@ -109,7 +109,16 @@ void b3B200BroadphaseBase::calculateOverlappingPairs(int maxPairs)
 	if (b3b200_bp_calculate_pairs(m_bp, maxPairs) < 0) reportError("calculateOverlappingPairs");
 	m_numOverlap = b3b200_bp_num_overlap(m_bp);
 }
-int b3B200BroadphaseBase::getNumOverlap() { return m_numOverlap; }
+int b3B200BroadphaseBase::getNumOverlap()
+{
+	if (m_world)
+	{
+		// the pipeline's step finds the pairs; the count lives in the world's device counters
+		int c[8];
+		if (b3b200_get_counters(m_world, c) == 0) m_numOverlap = c[0];
+	}
+	return m_numOverlap;
+}
 cl_mem b3B200BroadphaseBase::getAabbBufferWS()
 {
 	void* p = 0;
@@ -146,7 +155,7 @@ b3AlignedObjectArray<b3SapAabb>& b3B200BroadphaseBase::getAllAabbsCPU()
 }
 b3OpenCLArray<b3Int4>& b3B200BroadphaseBase::getOverlappingPairsGPU()
 {
-	m_pairsGPU.setView(getOverlappingPairBuffer(), m_numOverlap, m_device);
+	m_pairsGPU.setView(getOverlappingPairBuffer(), getNumOverlap(), m_device);
 	return m_pairsGPU;
 }
 

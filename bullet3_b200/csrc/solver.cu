@@ -755,11 +755,4 @@ int launchSolverIterate(World* w)
 	return coopLaunch(w, (const void*)solverIterateKernel, &s);
 }
 
-int launchJacobi(World* w)
-{
-	(void)w;
-	setLastError("Jacobi contact solver: not built yet");
-	return B3B200_ERR_STATE;
-}
-
 }  // namespace b3b200

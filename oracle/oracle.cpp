@@ -895,6 +895,208 @@ void orc_solve(b3b200_constraint4* cs, const int* batchOffsets, int numBatches, 
 				}
 }
 
+// Mass-splitting Jacobi contact solver, GPU order: per iteration contacts, average, friction, average;
+// then the averaged delta is added to the body velocities.
+// (Bullet3OpenCL/RigidBody/b3GpuJacobiContactSolver.cpp:699-869; kernels/solverUtils.cl:
+//  CountBodiesKernel :392-414, setConstraint4/ContactToConstraintSplitKernel :836-967,
+//  SolveContactJacobiKernel :527-651, AverageVelocitiesKernel :428-456,
+//  SolveFrictionJacobiKernel :654-811, UpdateBodyVelocitiesKernel :815-833.)
+// Split slots are handed out in contact-index order (the reference's atomic order is arbitrary).
+void orc_jacobi_solve(const b3b200_contact4* contacts, int n, b3b200_rigid_body* bodies, int numBodies, const b3b200_inertia* inertias, int staticIdx,
+					  int iterations, float dt, float positionDrift, float positionConstraintCoeff)
+{
+	std::vector<unsigned int> bodyCount(numBodies, 0), bodyOffset(numBodies, 0);
+	std::vector<int> slotA(n, 0), slotB(n, 0);
+	for (int i = 0; i < n; i++)
+	{
+		int pa = contacts[i].bodyAPtrAndSignBit, pb = contacts[i].bodyBPtrAndSignBit;
+		if (!((pa < 0) || (pa == staticIdx))) slotA[i] = (int)bodyCount[abs(pa)]++;
+		if (!((pb < 0) || (pb == staticIdx))) slotB[i] = (int)bodyCount[abs(pb)]++;
+	}
+	unsigned int total = 0;
+	for (int i = 0; i < numBodies; i++)
+	{
+		bodyOffset[i] = total;
+		total += bodyCount[i];
+	}
+	std::vector<b3b200_constraint4> cs(n);
+	for (int g = 0; g < n; g++)
+	{
+		const b3b200_contact4& src = contacts[g];
+		b3b200_constraint4& dst = cs[g];
+		memset(&dst, 0, sizeof(dst));
+		int aIdx = abs(src.bodyAPtrAndSignBit), bIdx = abs(src.bodyBPtrAndSignBit);
+		V3 posA = ld(bodies[aIdx].pos), linVelA = ld(bodies[aIdx].linVel), angVelA = ld(bodies[aIdx].angVel);
+		V3 posB = ld(bodies[bIdx].pos), linVelB = ld(bodies[bIdx].linVel), angVelB = ld(bodies[bIdx].angVel);
+		float invMassA = bodies[aIdx].invMass, invMassB = bodies[bIdx].invMass;
+		M3 IA = ldM(inertias[aIdx].invInertiaWorld), IB = ldM(inertias[bIdx].invInertiaWorld);
+		float countA = invMassA != 0.f ? (float)bodyCount[aIdx] : 1, countB = invMassB != 0.f ? (float)bodyCount[bIdx] : 1;
+		auto jac = [&](const V3& a0, const V3& a1) {
+			float jmj0 = invMassA, jmj1 = dot(matMul(IA, a0), a0), jmj2 = invMassB, jmj3 = dot(matMul(IB, a1), a1);
+			return -1.f / ((jmj0 + jmj1) * countA + (jmj2 + jmj3) * countB);
+		};
+		dst.bodyA = aIdx;
+		dst.bodyB = bIdx;
+		float dtInv = 1.f / dt;
+		V3 n3 = mk(src.worldNormalOnB.x, src.worldNormalOnB.y, src.worldNormalOnB.z);
+		float npoints = src.worldNormalOnB.w;
+		dst.linear = st(mk(n3.x, n3.y, n3.z, 0.7f));
+		for (int ic = 0; ic < 4; ic++)
+		{
+			V3 r0 = sub(ld(src.worldPosB[ic]), posA), r1 = sub(ld(src.worldPosB[ic]), posB);
+			if (ic >= npoints) continue;
+			V3 a0 = cross(r0, n3), a1 = neg(cross(r1, n3));
+			dst.jacCoeffInv[ic] = jac(a0, a1);
+			float relVelN = calcRelVel(n3, neg(n3), a0, a1, linVelA, angVelA, linVelB, angVelB);
+			float e = 0.f;
+			dst.b[ic] = e * relVelN;
+			dst.b[ic] += (src.worldPosB[ic].w + positionDrift) * positionConstraintCoeff * dtInv;
+		}
+		if (npoints > 0)
+		{
+			V3 center = mk(0, 0, 0);
+			for (int i = 0; i < npoints; i++) center = add(center, ld(src.worldPosB[i]));
+			center = mul(center, 1.0f / (float)npoints);
+			V3 t[2];
+			planeSpace1(neg(n3), t[0], t[1]);
+			V3 r0 = sub(center, posA), r1 = sub(center, posB);
+			for (int i = 0; i < 2; i++) dst.fJacCoeffInv[i] = jac(cross(r0, t[i]), neg(cross(r1, t[i])));
+			dst.center = st(center);
+		}
+		for (int i = 0; i < 4; i++)
+			if (i < npoints) dst.worldPos[i] = src.worldPosB[i];
+	}
+	std::vector<V3> dLin(total + 1, mk(0, 0, 0)), dAng(total + 1, mk(0, 0, 0));
+	auto average = [&]() {
+		for (int i = 0; i < numBodies; i++)
+		{
+			if (!bodies[i].invMass) continue;
+			int off = (int)bodyOffset[i], count = (int)bodyCount[i];
+			float factor = 1.f / ((float)count);
+			V3 avL = mk(0, 0, 0), avA = mk(0, 0, 0);
+			for (int j = 0; j < count; j++)
+			{
+				avL = add(avL, mul(dLin[off + j], factor));
+				avA = add(avA, mul(dAng[off + j], factor));
+			}
+			for (int j = 0; j < count; j++)
+			{
+				dLin[off + j] = avL;
+				dAng[off + j] = avA;
+			}
+		}
+	};
+	for (int iter = 0; iter < iterations; iter++)
+	{
+		for (int phase = 0; phase < 2; phase++)
+		{
+			for (int i = 0; i < n; i++)
+			{
+				b3b200_constraint4& c = cs[i];
+				int aIdx = (int)c.bodyA, bIdx = (int)c.bodyB;
+				V3 posA = ld(bodies[aIdx].pos), linVelA = ld(bodies[aIdx].linVel), angVelA = ld(bodies[aIdx].angVel);
+				V3 posB = ld(bodies[bIdx].pos), linVelB = ld(bodies[bIdx].linVel), angVelB = ld(bodies[bIdx].angVel);
+				float invMassA = bodies[aIdx].invMass, invMassB = bodies[bIdx].invMass;
+				M3 IA = ldM(inertias[aIdx].invInertiaWorld), IB = ldM(inertias[bIdx].invInertiaWorld);
+				int splitA = (int)bodyOffset[aIdx] + slotA[i], splitB = (int)bodyOffset[bIdx] + slotB[i];
+				V3 dLA = mk(0, 0, 0), dAA = mk(0, 0, 0), dLB = mk(0, 0, 0), dAB = mk(0, 0, 0);
+				if (invMassA)
+				{
+					dLA = dLin[splitA];
+					dAA = dAng[splitA];
+				}
+				if (invMassB)
+				{
+					dLB = dLin[splitB];
+					dAB = dAng[splitB];
+				}
+				V3 lin = ld(c.linear);
+				if (phase == 0)
+				{
+					for (int ic = 0; ic < 4; ic++)
+					{
+						if (c.jacCoeffInv[ic] == 0.f) continue;
+						V3 r0 = sub(ld(c.worldPos[ic]), posA), r1 = sub(ld(c.worldPos[ic]), posB);
+						V3 a0 = cross(r0, lin), a1 = neg(cross(r1, lin));
+						float rambdaDt = calcRelVel(lin, neg(lin), a0, a1, add(linVelA, dLA), add(angVelA, dAA), add(linVelB, dLB), add(angVelB, dAB)) + c.b[ic];
+						rambdaDt *= c.jacCoeffInv[ic];
+						float prevSum = c.appliedRambdaDt[ic];
+						float updated = prevSum + rambdaDt;
+						updated = std::max(updated, 0.f);
+						updated = std::min(updated, FLT_MAX);
+						rambdaDt = updated - prevSum;
+						c.appliedRambdaDt[ic] = updated;
+						if (invMassA)
+						{
+							dLA = add(dLA, mul(mul(lin, invMassA), rambdaDt));
+							dAA = add(dAA, mul(matMul(IA, a0), rambdaDt));
+						}
+						if (invMassB)
+						{
+							dLB = add(dLB, mul(mul(neg(lin), invMassB), rambdaDt));
+							dAB = add(dAB, mul(matMul(IB, a1), rambdaDt));
+						}
+					}
+				}
+				else
+				{
+					if (c.fJacCoeffInv[0] == 0 && c.fJacCoeffInv[0] == 0) continue;
+					float sum = 0;
+					for (int j = 0; j < 4; j++) sum += c.appliedRambdaDt[j];
+					float maxR = 0.7f * sum, minR = -maxR;
+					V3 center = ld(c.center);
+					V3 nn = neg(lin);
+					V3 t[2];
+					planeSpace1(nn, t[0], t[1]);
+					V3 r0 = sub(center, posA), r1 = sub(center, posB);
+					for (int k = 0; k < 2; k++)
+					{
+						V3 a0 = cross(r0, t[k]), a1 = neg(cross(r1, t[k]));
+						float rambdaDt = calcRelVel(t[k], neg(t[k]), a0, a1, add(linVelA, dLA), add(angVelA, dAA), add(linVelB, dLB), add(angVelB, dAB));
+						rambdaDt *= c.fJacCoeffInv[k];
+						float prevSum = c.fAppliedRambdaDt[k];
+						float updated = prevSum + rambdaDt;
+						updated = std::max(updated, minR);
+						updated = std::min(updated, maxR);
+						rambdaDt = updated - prevSum;
+						c.fAppliedRambdaDt[k] = updated;
+						dLA = add(dLA, mul(mul(t[k], invMassA), rambdaDt));
+						dLB = add(dLB, mul(mul(neg(t[k]), invMassB), rambdaDt));
+						dAA = add(dAA, mul(matMul(IA, a0), rambdaDt));
+						dAB = add(dAB, mul(matMul(IB, a1), rambdaDt));
+					}
+					V3 ab = normalized(sub(posB, posA)), ac = normalized(sub(center, posA));
+					if (dot(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
+					{
+						float angNA = dot(nn, angVelA), angNB = dot(nn, angVelB);
+						dAA = sub(dAA, mul(nn, angNA * 0.1f));
+						dAB = sub(dAB, mul(nn, angNB * 0.1f));
+					}
+				}
+				if (invMassA)
+				{
+					dLin[splitA] = dLA;
+					dAng[splitA] = dAA;
+				}
+				if (invMassB)
+				{
+					dLin[splitB] = dLB;
+					dAng[splitB] = dAB;
+				}
+			}
+			average();
+		}
+	}
+	if (iterations > 0)
+		for (int i = 0; i < numBodies; i++)
+			if (bodies[i].invMass && bodyCount[i])
+			{
+				int off = (int)bodyOffset[i];
+				bodies[i].linVel = st(add(ld(bodies[i].linVel), dLin[off]));
+				bodies[i].angVel = st(add(ld(bodies[i].angVel), dAng[off]));
+			}
+}
+
 // b3RadixSort32CL::executeHost (Bullet3OpenCL/ParallelPrimitives/b3RadixSort32CL.cpp:587-646): stable by key
 void orc_radix_sort_kv(b3b200_sort_data* data, int n)
 {

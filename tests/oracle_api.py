@@ -153,3 +153,12 @@ def sorted_pair_set(pairs):
     xy = np.stack([x, y], axis=1)
     order = np.lexsort((xy[:, 1], xy[:, 0]))
     return xy[order]
+
+
+def jacobi_solve(contacts, bodies, inertias, static_idx, iterations, dt=1.0 / 60.0, drift=0.005, coeff=0.99):
+    contacts = _arr(contacts, capi.contact4_t)
+    bodies = _arr(bodies, capi.rigid_body_t).copy()
+    inertias = _arr(inertias, capi.inertia_t)
+    oracle().orc_jacobi_solve(P(contacts), len(contacts), P(bodies), len(bodies), P(inertias), int(static_idx), int(iterations),
+                              C.c_float(dt), C.c_float(drift), C.c_float(coeff))
+    return bodies

@@ -346,6 +346,43 @@ def test_pgs_solver_matches_oracle(seed, iters, dataflow):
     assert moved > 0.1  # the solver did something
 
 
+@pytest.mark.parametrize("seed,iters", [(0, 7), (3, 8)])
+def test_jacobi_solver_matches_oracle(seed, iters):
+    """config 3 solver: mass-splitting Jacobi, GPU kernel order (solverUtils.cl)"""
+    w, sh, bodies, inertias = gpu_world(n_side=7, seed=seed)
+    w.set_solver(capi.SOLVER_JACOBI, iters)
+    w.update_aabbs()
+    w.find_pairs()
+    w.compute_contacts()
+    contacts = w.contacts()
+    assert len(contacts) > 200
+    w.solve_contacts()
+    g = w.bodies()
+    o = oa.jacobi_solve(contacts, bodies, inertias, 0, iters)
+    assert rel_close(g["linVel"][:, :3], o["linVel"][:, :3], 1e-4)
+    assert rel_close(g["angVel"][:, :3], o["angVel"][:, :3], 1e-4)
+    assert np.abs(g["linVel"][:, :3] - bodies["linVel"][:, :3]).max() > 0.1
+    # static bodies untouched
+    st = bodies["invMass"] == 0
+    assert np.array_equal(g["linVel"][st], bodies["linVel"][st])
+
+
+def test_jacobi_box_plane_scene_settles():
+    """config 3 recipe (GpuBoxPlaneScene), reduced: boxes on the ground, Jacobi 8 iterations, SAP broadphase"""
+    w = capi.World(capi.default_config(4096))
+    scenes.box_plane_scene(w, 8, 4, 8)
+    w.upload()
+    w.set_solver(capi.SOLVER_JACOBI, 8)
+    w.set_broadphase(capi.BP_SAP)
+    for _ in range(200):
+        w.step(1 / 60)
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all()
+    assert b["pos"][dyn, 1].min() > 0.8
+    assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 0.5
+
+
 def test_dataflow_and_barrier_kernels_bit_identical():
     """the two iteration kernels execute the same Gauss-Seidel order"""
     out = []
