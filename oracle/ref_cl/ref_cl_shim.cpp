@@ -1,0 +1,241 @@
+// ref_cl_shim.cpp -- extern "C" access to the reference's own HOST TWINS inside src/Bullet3OpenCL
+// (compiled unmodified, -DB3_USE_CLEW, against the host-memory fake OpenCL of fake_cl.cpp).
+// TEST INFRASTRUCTURE ONLY; nothing here restates an algorithm.
+//   refcl_pairs_host        b3GpuSapBroadphase::calculateOverlappingPairsHost   (b3GpuSapBroadphase.cpp:862-981)
+//   refcl_pgs_solve         b3Solver::convertToConstraints (gConvertConstraintOnCpu) + solveContactConstraintHost
+//                           (b3Solver.cpp:889-933, 468-637)
+//   refcl_radix_sort / scan / bound_search   the executeHost twins of ParallelPrimitives
+//   refcl_np_*              b3GpuNarrowPhase + GpuSatCollision built with -DCHECK_ON_HOST: shape registration
+//                           (incl. the compound / mesh BVH builders) and the host contact loop
+//                           (b3ConvexHullContact.cpp:2595-2748)
+#include <string.h>
+#include <stdio.h>
+#include "Bullet3OpenCL/Initialize/b3OpenCLInclude.h"
+#include "Bullet3OpenCL/ParallelPrimitives/b3OpenCLArray.h"
+#include "Bullet3OpenCL/ParallelPrimitives/b3RadixSort32CL.h"
+#include "Bullet3OpenCL/ParallelPrimitives/b3PrefixScanCL.h"
+#include "Bullet3OpenCL/ParallelPrimitives/b3BoundSearchCL.h"
+#include "Bullet3OpenCL/BroadphaseCollision/b3GpuSapBroadphase.h"
+#include "Bullet3OpenCL/RigidBody/b3Solver.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhaseInternalData.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3Contact4.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h"
+#include "Bullet3Dynamics/shared/b3ContactConstraint4.h"
+#include "../../include/b3b200_types.h"
+
+extern "C" void b3ref_cl_init();
+extern bool gConvertConstraintOnCpu;  // b3Solver.cpp:20
+
+static cl_context CTX = 0;
+static cl_device_id DEV = 0;
+static cl_command_queue Q = 0;
+static void init()
+{
+	static bool done = false;
+	if (!done) b3ref_cl_init();
+	done = true;
+}
+
+extern "C" {
+
+int refcl_pairs_host(const b3b200_aabb* aabbs, int n, const unsigned char* isLarge, b3b200_int4* pairsOut, int maxPairs)
+{
+	init();
+	b3GpuSapBroadphase bp(CTX, DEV, Q);
+	for (int i = 0; i < n; i++)
+	{
+		b3Vector3 mn = b3MakeVector3(aabbs[i].min[0], aabbs[i].min[1], aabbs[i].min[2]);
+		b3Vector3 mx = b3MakeVector3(aabbs[i].max[0], aabbs[i].max[1], aabbs[i].max[2]);
+		if (isLarge[i])
+			bp.createLargeProxy(mn, mx, aabbs[i].minIndices[3], 1, 1);
+		else
+			bp.createProxy(mn, mx, aabbs[i].minIndices[3], 1, 1);
+	}
+	bp.writeAabbsToGpu();
+	bp.calculateOverlappingPairsHost(maxPairs);
+	b3AlignedObjectArray<b3Int4> host;
+	bp.getOverlappingPairsGPU().copyToHost(host);
+	for (int i = 0; i < host.size() && i < maxPairs; i++) memcpy(&pairsOut[i], &host[i], 16);
+	return host.size();
+}
+
+// contacts must be sorted by batch; batchSizes[b] = number of contacts in batch b
+int refcl_pgs_solve(const b3b200_contact4* contacts, int n, const int* batchSizes, int numBatches, b3b200_rigid_body* bodies, int numBodies,
+					const b3b200_inertia* inertias, int iterations, float dt, b3b200_constraint4* constraintsOut)
+{
+	init();
+	if (numBatches >= B3_MAX_NUM_BATCHES) return -1;
+	b3Solver solver(CTX, DEV, Q, n > 512 ? n : 512);
+	b3OpenCLArray<b3RigidBodyData> bodyBuf(CTX, Q);
+	b3OpenCLArray<b3InertiaData> shapeBuf(CTX, Q);
+	b3OpenCLArray<b3Contact4> contactBuf(CTX, Q);
+	b3OpenCLArray<b3GpuConstraint4> constraintBuf(CTX, Q);
+	bodyBuf.resize(numBodies);
+	shapeBuf.resize(numBodies);
+	contactBuf.resize(n);
+	bodyBuf.copyFromHostPointer((const b3RigidBodyData*)bodies, numBodies, 0, true);
+	shapeBuf.copyFromHostPointer((const b3InertiaData*)inertias, numBodies, 0, true);
+	contactBuf.copyFromHostPointer((const b3Contact4*)contacts, n, 0, true);
+	b3SolverBase::ConstraintCfg cfg(dt);
+	gConvertConstraintOnCpu = true;
+	solver.convertToConstraints(&bodyBuf, &shapeBuf, &contactBuf, &constraintBuf, 0, n, cfg);
+	if (constraintsOut) constraintBuf.copyToHostPointer((b3GpuConstraint4*)constraintsOut, n, 0, true);
+	// one spatial cell (index 0) holding every constraint; its batches are the global batches
+	b3AlignedObjectArray<unsigned int> counts, offsets;
+	counts.resize(B3_SOLVER_N_CELLS);
+	offsets.resize(B3_SOLVER_N_CELLS);
+	for (int i = 0; i < B3_SOLVER_N_CELLS; i++)
+	{
+		counts[i] = 0;
+		offsets[i] = 0;
+	}
+	counts[0] = n;
+	solver.m_numConstraints->copyFromHost(counts);
+	solver.m_offsets->copyFromHost(offsets);
+	b3AlignedObjectArray<int> bs;
+	bs.resize(B3_SOLVER_N_CELLS * B3_MAX_NUM_BATCHES);
+	for (int i = 0; i < bs.size(); i++) bs[i] = 0;
+	for (int b = 0; b < numBatches; b++) bs[b] = batchSizes[b];
+	solver.m_nIterations = iterations;
+	solver.solveContactConstraintHost(&bodyBuf, &shapeBuf, &constraintBuf, 0, n, numBatches, &bs);
+	bodyBuf.copyToHostPointer((b3RigidBodyData*)bodies, numBodies, 0, true);
+	return 0;
+}
+
+void refcl_radix_sort(b3b200_sort_data* data, int n)
+{
+	init();
+	b3RadixSort32CL sorter(CTX, DEV, Q);
+	b3AlignedObjectArray<b3SortData> a;
+	a.resize(n);
+	if (n) memcpy(&a[0], data, sizeof(b3SortData) * (size_t)n);
+	sorter.executeHost(a);
+	if (n) memcpy(data, &a[0], sizeof(b3SortData) * (size_t)n);
+}
+
+void refcl_prefix_scan(const unsigned int* src, unsigned int* dst, int n, unsigned int* sum)
+{
+	init();
+	b3PrefixScanCL scan(CTX, DEV, Q, n + 16);
+	b3AlignedObjectArray<unsigned int> a, b;
+	a.resize(n);
+	b.resize(n);
+	if (n) memcpy(&a[0], src, 4 * (size_t)n);
+	scan.executeHost(a, b, n, sum);
+	if (n) memcpy(dst, &b[0], 4 * (size_t)n);
+}
+
+void refcl_bound_search_count(const b3b200_sort_data* sorted, int n, unsigned int* counts, int numBuckets)
+{
+	init();
+	b3BoundSearchCL search(CTX, DEV, Q, numBuckets);
+	b3AlignedObjectArray<b3SortData> a;
+	b3AlignedObjectArray<unsigned int> c;
+	a.resize(n);
+	c.resize(numBuckets);
+	if (n) memcpy(&a[0], sorted, sizeof(b3SortData) * (size_t)n);
+	for (int i = 0; i < numBuckets; i++) c[i] = 0;
+	search.executeHost(a, n, c, numBuckets, b3BoundSearchCL::COUNT);
+	memcpy(counts, &c[0], 4 * (size_t)numBuckets);
+}
+
+// ------------------------------------------------------------------ narrowphase (CHECK_ON_HOST build)
+struct RefNp
+{
+	b3GpuNarrowPhase* np;
+	b3Config cfg;
+};
+
+void* refcl_np_create(const b3b200_config* cfg)
+{
+	init();
+	RefNp* r = new RefNp;
+	memcpy(&r->cfg, cfg, sizeof(b3Config));
+	r->np = new b3GpuNarrowPhase(CTX, DEV, Q, r->cfg);
+	return r;
+}
+void refcl_np_destroy(void* h)
+{
+	RefNp* r = (RefNp*)h;
+	delete r->np;
+	delete r;
+}
+int refcl_np_register_convex_points(void* h, const float* pts, int n, const float* scaling)
+{
+	return ((RefNp*)h)->np->registerConvexHullShape(pts, 12, n, scaling);
+}
+int refcl_np_register_plane(void* h, const float* normal, float c) { return ((RefNp*)h)->np->registerPlaneShape(b3MakeVector3(normal[0], normal[1], normal[2]), c); }
+int refcl_np_register_sphere(void* h, float radius) { return ((RefNp*)h)->np->registerSphereShape(radius); }
+int refcl_np_register_compound(void* h, const b3b200_child_shape* children, int n)
+{
+	b3AlignedObjectArray<b3GpuChildShape> ch;
+	ch.resize(n);
+	memcpy(&ch[0], children, sizeof(b3GpuChildShape) * (size_t)n);
+	return ((RefNp*)h)->np->registerCompoundShape(&ch);
+}
+int refcl_np_register_concave(void* h, const float* verts, int nv, const int* idx, int ni, const float* scaling)
+{
+	b3AlignedObjectArray<b3Vector3> v;
+	b3AlignedObjectArray<int> i;
+	for (int k = 0; k < nv; k++) v.push_back(b3MakeVector3(verts[3 * k], verts[3 * k + 1], verts[3 * k + 2]));
+	for (int k = 0; k < ni; k++) i.push_back(idx[k]);
+	return ((RefNp*)h)->np->registerConcaveMesh(&v, &i, scaling);
+}
+int refcl_np_register_body(void* h, int collidable, float mass, const float* pos, const float* orn, const float* aabbMin, const float* aabbMax)
+{
+	return ((RefNp*)h)->np->registerRigidBody(collidable, mass, pos, orn, aabbMin, aabbMax, false);
+}
+// host contact loop on caller-supplied pairs and world AABBs; returns the contact count
+int refcl_np_compute_contacts(void* h, const b3b200_rigid_body* bodies, int numBodies, const b3b200_int4* pairs, int numPairs, const b3b200_aabb* aabbsWS,
+							  b3b200_contact4* out, int maxContacts, b3b200_int4* pairsOut)
+{
+	RefNp* r = (RefNp*)h;
+	b3GpuNarrowPhaseInternalData* d = r->np->getInternalData();
+	// take the caller's body state
+	for (int i = 0; i < numBodies && i < d->m_bodyBufferCPU->size(); i++) memcpy(&d->m_bodyBufferCPU->at(i), &bodies[i], sizeof(b3RigidBodyData));
+	r->np->writeAllBodiesToGpu();
+	b3OpenCLArray<b3Int4> pairBuf(CTX, Q);
+	b3OpenCLArray<b3SapAabb> aabbBuf(CTX, Q);
+	pairBuf.resize(numPairs);
+	aabbBuf.resize(numBodies);
+	pairBuf.copyFromHostPointer((const b3Int4*)pairs, numPairs, 0, true);
+	aabbBuf.copyFromHostPointer((const b3SapAabb*)aabbsWS, numBodies, 0, true);
+	r->np->computeContacts(pairBuf.getBufferCL(), numPairs, aabbBuf.getBufferCL(), numBodies);
+	int n = r->np->getNumContactsGpu();
+	b3AlignedObjectArray<b3Contact4> host;
+	d->m_pBufContactBuffersGPU[d->m_currentContactBuffer]->copyToHost(host);
+	for (int i = 0; i < n && i < maxContacts; i++) memcpy(&out[i], &host[i], sizeof(b3Contact4));
+	if (pairsOut) pairBuf.copyToHostPointer((b3Int4*)pairsOut, numPairs, 0, true);
+	return n;
+}
+// flat shape tables as the reference built them (b3GpuNarrowPhaseInternalData.h:24-86)
+int refcl_np_get_table(void* h, int which, void* dst, int capacity, int* count)
+{
+	b3GpuNarrowPhaseInternalData* d = ((RefNp*)h)->np->getInternalData();
+	const void* src = 0;
+	int n = 0, sz = 0;
+	switch (which)
+	{
+		case 0: src = d->m_collidablesCPU.size() ? &d->m_collidablesCPU[0] : 0; n = d->m_collidablesCPU.size(); sz = sizeof(b3Collidable); break;
+		case 1: src = d->m_localShapeAABBCPU->size() ? &d->m_localShapeAABBCPU->at(0) : 0; n = d->m_localShapeAABBCPU->size(); sz = sizeof(b3SapAabb); break;
+		case 2: src = d->m_convexPolyhedra.size() ? &d->m_convexPolyhedra[0] : 0; n = d->m_convexPolyhedra.size(); sz = sizeof(b3ConvexPolyhedronData); break;
+		case 3: src = d->m_convexVertices.size() ? &d->m_convexVertices[0] : 0; n = d->m_convexVertices.size(); sz = 16; break;
+		case 4: src = d->m_uniqueEdges.size() ? &d->m_uniqueEdges[0] : 0; n = d->m_uniqueEdges.size(); sz = 16; break;
+		case 5: src = d->m_convexFaces.size() ? &d->m_convexFaces[0] : 0; n = d->m_convexFaces.size(); sz = sizeof(b3GpuFace); break;
+		case 6: src = d->m_convexIndices.size() ? &d->m_convexIndices[0] : 0; n = d->m_convexIndices.size(); sz = 4; break;
+		case 7: src = d->m_cpuChildShapes.size() ? &d->m_cpuChildShapes[0] : 0; n = d->m_cpuChildShapes.size(); sz = sizeof(b3GpuChildShape); break;
+		case 8: src = d->m_bvhInfoCPU.size() ? &d->m_bvhInfoCPU[0] : 0; n = d->m_bvhInfoCPU.size(); sz = sizeof(b3BvhInfo); break;
+		case 9: src = d->m_treeNodesCPU.size() ? &d->m_treeNodesCPU[0] : 0; n = d->m_treeNodesCPU.size(); sz = sizeof(b3QuantizedBvhNode); break;
+		case 10: src = d->m_subTreesCPU.size() ? &d->m_subTreesCPU[0] : 0; n = d->m_subTreesCPU.size(); sz = sizeof(b3BvhSubtreeInfo); break;
+		case 11: src = d->m_bodyBufferCPU->size() ? &d->m_bodyBufferCPU->at(0) : 0; n = ((RefNp*)h)->np->getNumRigidBodies(); sz = sizeof(b3RigidBodyData); break;
+		case 12: src = d->m_inertiaBufferCPU->size() ? &d->m_inertiaBufferCPU->at(0) : 0; n = ((RefNp*)h)->np->getNumRigidBodies(); sz = sizeof(b3InertiaData); break;
+		default: return -1;
+	}
+	*count = n;
+	int m = n < capacity ? n : capacity;
+	if (dst && m > 0 && src) memcpy(dst, src, (size_t)sz * m);
+	return 0;
+}
+}

@@ -162,3 +162,40 @@ def jacobi_solve(contacts, bodies, inertias, static_idx, iterations, dt=1.0 / 60
     oracle().orc_jacobi_solve(P(contacts), len(contacts), P(bodies), len(bodies), P(inertias), int(static_idx), int(iterations),
                               C.c_float(dt), C.c_float(drift), C.c_float(coeff))
     return bodies
+
+
+# ---------------------------------------------------------------- reference host twins of src/Bullet3OpenCL (fake OpenCL build)
+REFCL_SO = os.path.join(ROOT, "oracle", "_ref", "libb3refcl.so")
+_refcl = None
+
+
+def refcl_available():
+    return os.path.exists(REFCL_SO)
+
+
+def refcl():
+    global _refcl
+    if _refcl is None:
+        _refcl = C.CDLL(REFCL_SO, mode=C.RTLD_GLOBAL)
+        _refcl.refcl_np_create.restype = C.c_void_p
+    return _refcl
+
+
+def refcl_pairs_host(aabbs, large_idx, max_pairs):
+    aabbs = _arr(aabbs, capi.aabb_t)
+    is_large = np.zeros(len(aabbs), np.uint8)
+    is_large[np.asarray(large_idx, np.int64)] = 1
+    out = np.zeros(max(max_pairs, 1), capi.int4_t)
+    n = refcl().refcl_pairs_host(P(aabbs), len(aabbs), P(is_large), P(out), int(max_pairs))
+    return n, out[: min(n, max_pairs)]
+
+
+def refcl_pgs_solve(sorted_contacts, batch_sizes, bodies, inertias, iterations, dt=1.0 / 60.0):
+    contacts = _arr(sorted_contacts, capi.contact4_t)
+    bs = _arr(batch_sizes, np.int32)
+    bodies = _arr(bodies, capi.rigid_body_t).copy()
+    inertias = _arr(inertias, capi.inertia_t)
+    cs = np.zeros(max(len(contacts), 1), capi.constraint4_t)
+    rc = refcl().refcl_pgs_solve(P(contacts), len(contacts), P(bs), len(bs), P(bodies), len(bodies), P(inertias), int(iterations), C.c_float(dt), P(cs))
+    assert rc == 0
+    return bodies, cs[: len(contacts)]
