@@ -128,6 +128,7 @@ struct World
 	DevBuf<float4> dVel;   // 2 float4 per body
 	DevBuf<int> dCollidableIdx;
 	bool soaDirty = false;  // SoA is newer than AoS
+	bool hasPlanes = false;  // any SHAPE_PLANE collidable registered (enables the primitive-contact kernel)
 
 	Broadphase bp;
 
@@ -136,8 +137,8 @@ struct World
 	DevBuf<unsigned int> dCounters;  // CTR_COUNT
 	DevBuf<b3b200_int4> dCompoundPairs;
 	DevBuf<b3b200_int4> dConcavePairs;
-	DevBuf<int> dSurvivors;  // pair indices that passed the quick SAT reject
-	DevBuf<int> dOverlapPairs;  // pair indices with a penetrating SAT result
+	DevBuf<int4> dSurvivors;     // work items (pair, childA, childB, 0) that passed the quick SAT reject
+	DevBuf<int4> dOverlapPairs;  // work items with a penetrating SAT result
 	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes
 
 	// solver
@@ -167,6 +168,10 @@ struct World
 };
 
 constexpr int MAX_BATCHES = 128;  // B3_MAX_NUM_BATCHES (b3Solver.h:33-41)
+
+// host helpers shared by world.cu / shapes.cu
+void transformAabbHost(const float* lmn, const float* lmx, float margin, const float* pos, const float* orn, float* outMin, float* outMax);
+int allocateCollidable(World* w);
 
 // stage launchers (each async on w->stream)
 int launchPackSoA(World* w);    // AoS -> SoA

@@ -187,10 +187,46 @@ struct NpArgs
 	const float4* uniqueEdges;
 	const b3b200_face* faces;
 	const int* indices;
+	const b3b200_child_shape* childShapes;
 	b3b200_contact4* contacts;
 	int maxContacts;
+	int maxWorkItems;
 	float clipMin, clipMax;
 };
+
+// One side of a (child) pair: the convex hull and its world transform.  For a child of a compound the
+// transform is composed exactly like the reference kernels do (sat.cl:836-862,
+// b3ConvexHullContact.cpp:1806-1832): pos' = quatRotate(orn, childPos) + pos, orn' = orn * childOrn.
+struct Side
+{
+	int shape;
+	float4 pos, orn;
+	float invMass;
+};
+B3_D bool resolveSide(const NpArgs& a, int body, int child, Side& s)
+{
+	float4 pos = a.pose[2 * body], orn = a.pose[2 * body + 1];
+	s.invMass = pos.w;
+	int coll;
+	if (child >= 0)
+	{
+		const b3b200_child_shape* ch = &a.childShapes[child];
+		const float4 cp = __ldg(reinterpret_cast<const float4*>(&ch->childPosition));
+		const float4 co = __ldg(reinterpret_cast<const float4*>(&ch->childOrientation));
+		const float4 r = quatRotate(orn, cp);
+		pos = mk4(r.x + pos.x, r.y + pos.y, r.z + pos.z, 0.f);
+		orn = quatMul(orn, co);
+		coll = __ldg(&ch->shapeIndex);
+	}
+	else
+		coll = a.coll[body];
+	if (coll < 0 || __ldg(&a.collidables[coll].shapeType) != B3B200_SHAPE_CONVEX_HULL) return false;
+	s.shape = __ldg(&a.collidables[coll].shapeIndex);
+	pos.w = 0.f;
+	s.pos = pos;
+	s.orn = orn;
+	return true;
+}
 
 // convex hull vs convex hull: b3ContactConvexConvexSAT (shared/b3ContactConvexConvexSAT.h:407-484)
 // Part 1: b3FindSeparatingAxis.  Returns false when the hulls are separated; otherwise *sepOut is the
@@ -577,12 +613,15 @@ B3_D void clipWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int sha
 }
 
 // ---------------------------------------------------------------- stage 1: quick reject
-// One THREAD per broadphase pair.  For a convex-convex pair it picks the face of A and the
-// face of B that look most likely to separate (largest local-space dot with the centre
-// offset) and runs the reference's own test (b3TestSepAxis, identical arithmetic) on just
-// those two axes.  Both axes are members of b3FindSeparatingAxis' candidate list, so a
-// separation found here is a separation the reference finds too: the reject is exact, not
-// conservative.  Survivors are compacted (one atomic per warp) for the warp-per-pair stage.
+// One THREAD per broadphase pair.  Convex-convex pairs and every child pair of compound shapes
+// (compound x compound, compound x convex) become work items (pair, childA, childB).  For each
+// it picks the face of A and the face of B that look most likely to separate (largest
+// local-space dot with the centre offset) and runs the reference's own test (b3TestSepAxis,
+// identical arithmetic) on just those two axes.  Both axes are members of b3FindSeparatingAxis'
+// candidate list, so a separation found here is a separation the reference finds too: the reject
+// is exact, not conservative.  Surviving items are appended for the warp-per-item stage.
+// The reference culls child pairs with a tree-vs-tree walk of two quantized BVHs
+// (findCompoundPairsKernel, sat.cl:947-1301); any conservative cull gives the same contacts.
 constexpr int CULL_THREADS = 256;
 
 B3_D int bestFace(const NpArgs& a, const HullRef& h, const float4& localDir)
@@ -602,7 +641,36 @@ B3_D int bestFace(const NpArgs& a, const HullRef& h, const float4& localDir)
 	return best;
 }
 
-__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __restrict__ survivors)
+// true = the pair may touch (keep it)
+B3_D bool quickTest(const NpArgs& a, const Side& A, const Side& B)
+{
+	const HullRef hA = loadHull(a.convex, A.shape);
+	const HullRef hB = loadHull(a.convex, B.shape);
+	const float4 c0 = transformPoint(hA.localCenter, A.pos, A.orn);
+	const float4 c1 = transformPoint(hB.localCenter, B.pos, B.orn);
+	const float4 deltaC2 = sub3(c0, c1);
+#pragma unroll 1
+	for (int which = 0; which < 2; which++)
+	{
+		const HullRef& h = which == 0 ? hA : hB;
+		const float4 orn = which == 0 ? A.orn : B.orn;
+		const int f = bestFace(a, h, quatRotate(quatInverse(orn), which == 0 ? neg3(deltaC2) : deltaC2));
+		float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[h.faceOffset + f].plane));
+		float4 axis = quatRotate(orn, normal);
+		if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+		float d;
+		if (!testSepAxis(hA, hB, A.pos, A.orn, B.pos, B.orn, axis, a.vertices, d)) return false;
+	}
+	return true;
+}
+
+B3_D void pushItem(const NpArgs& a, int4* __restrict__ items, int p, int ca, int cb)
+{
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_SURVIVORS], 1u);
+	if (slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, ca, cb, 0);
+}
+
+__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
 	const int lane = threadIdx.x & 31;
@@ -616,35 +684,34 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __re
 			const int cA = a.coll[bodyA], cB = a.coll[bodyB];
 			if (cA >= 0 && cB >= 0)
 			{
-				keep = true;
 				const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
 				if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
 				{
-					float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
-					float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
-					posA.w = 0.f;
-					posB.w = 0.f;
-					const HullRef hA = loadHull(a.convex, __ldg(&a.collidables[cA].shapeIndex));
-					const HullRef hB = loadHull(a.convex, __ldg(&a.collidables[cB].shapeIndex));
-					const float4 c0 = transformPoint(hA.localCenter, posA, ornA);
-					const float4 c1 = transformPoint(hB.localCenter, posB, ornB);
-					const float4 deltaC2 = sub3(c0, c1);
+					Side A, B;
+					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B)) keep = quickTest(a, A, B);
+				}
+				else if ((typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeA == B3B200_SHAPE_CONVEX_HULL) &&
+						 (typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeB == B3B200_SHAPE_CONVEX_HULL))
+				{
+					// at least one compound: expand to child pairs (two static bodies never collide, sat.cl:975-978)
+					if (!(a.pose[2 * bodyA].w == 0.f && a.pose[2 * bodyB].w == 0.f))
 					{
-						const int f = bestFace(a, hA, quatRotate(quatInverse(ornA), neg3(deltaC2)));
-						float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
-						float4 axis = quatRotate(ornA, normal);
-						if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
-						float d;
-						if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d)) keep = false;
-					}
-					if (keep)
-					{
-						const int f = bestFace(a, hB, quatRotate(quatInverse(ornB), deltaC2));
-						float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
-						float4 axis = quatRotate(ornB, normal);
-						if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
-						float d;
-						if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, axis, a.vertices, d)) keep = false;
+						const bool compA = typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS, compB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
+						const int firstA = compA ? __ldg(&a.collidables[cA].shapeIndex) : -1, nA = compA ? __ldg(&a.collidables[cA].numChildShapes) : 1;
+						const int firstB = compB ? __ldg(&a.collidables[cB].shapeIndex) : -1, nB = compB ? __ldg(&a.collidables[cB].numChildShapes) : 1;
+						for (int i = 0; i < nA; i++)
+						{
+							Side A;
+							const int ca = compA ? firstA + i : -1;
+							if (!resolveSide(a, bodyA, ca, A)) continue;
+							for (int j = 0; j < nB; j++)
+							{
+								Side B;
+								const int cb = compB ? firstB + j : -1;
+								if (!resolveSide(a, bodyB, cb, B)) continue;
+								if (quickTest(a, A, B)) pushItem(a, items, p, ca, cb);
+							}
+						}
 					}
 				}
 			}
@@ -655,15 +722,16 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int* __re
 			unsigned int slot = 0;
 			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(m));
 			slot = __shfl_sync(FULL, slot, 0);
-			if (keep) survivors[slot + __popc(m & ((1u << lane) - 1u))] = p;
+			slot += __popc(m & ((1u << lane) - 1u));
+			if (keep && slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, -1, -1, 0);
 		}
 	}
 }
 
-// ---------------------------------------------------------------- stage 2: SAT, one warp per surviving pair
-// Small, hot kernel (fits the instruction cache, ~70 registers): finds the minimum-penetration axis
-// and appends (pair, axis) to the overlap list.
-__global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int* __restrict__ survivors, int* __restrict__ overlapPairs,
+// ---------------------------------------------------------------- stage 2: SAT, one warp per work item
+// Small, hot kernel (fits the instruction cache, ~85 registers): finds the minimum-penetration axis
+// and appends (item, axis) to the overlap list.
+__global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4* __restrict__ items, int4* __restrict__ overlapItems,
 															   float4* __restrict__ overlapSep)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
@@ -673,26 +741,22 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int* 
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
 	int* queue = queueAll[warp];
-	const int numSurvivors = (int)a.ctr[CTR_SURVIVORS];
+	int numItems = (int)a.ctr[CTR_SURVIVORS];
+	if (numItems > a.maxWorkItems) numItems = a.maxWorkItems;
 	const int warpsTotal = gridDim.x * NP_WARPS;
-	for (int s = blockIdx.x * NP_WARPS + warp; s < numSurvivors; s += warpsTotal)
+	for (int s = blockIdx.x * NP_WARPS + warp; s < numItems; s += warpsTotal)
 	{
-		const int p = survivors[s];
-		const int bodyA = a.pairs[p].x;
-		const int bodyB = a.pairs[p].y;
-		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
-		const int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
-		if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
+		const int4 it = items[s];
+		const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+		Side A, B;
+		if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
 		{
-			const float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
-			const float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
 			float4 sep;
-			const bool hit = satWarp(a, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), posA, ornA, posB, ornB, bufA, bufB,
-									 queue, lane, &sep);
+			const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, queue, lane, &sep);
 			if (hit && lane == 0)
 			{
 				const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
-				overlapPairs[slot] = p;
+				overlapItems[slot] = it;
 				overlapSep[slot] = sep;
 			}
 		}
@@ -701,7 +765,7 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int* 
 }
 
 // ---------------------------------------------------------------- stage 3: clipping + reduction + append
-__global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int* __restrict__ overlapPairs, const float4* __restrict__ overlapSep)
+__global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int4* __restrict__ overlapItems, const float4* __restrict__ overlapSep)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
 	const int lane = threadIdx.x & 31;
@@ -712,16 +776,199 @@ __global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int* __
 	const int warpsTotal = gridDim.x * NP_WARPS;
 	for (int s = blockIdx.x * NP_WARPS + warp; s < numOverlaps; s += warpsTotal)
 	{
-		const int p = overlapPairs[s];
+		const int4 it = overlapItems[s];
 		const float4 sep = overlapSep[s];
-		const int bodyA = a.pairs[p].x;
-		const int bodyB = a.pairs[p].y;
-		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
-		const float4 posA = a.pose[2 * bodyA], ornA = a.pose[2 * bodyA + 1];
-		const float4 posB = a.pose[2 * bodyB], ornB = a.pose[2 * bodyB + 1];
-		clipWarp(a, p, bodyA, bodyB, __ldg(&a.collidables[cA].shapeIndex), __ldg(&a.collidables[cB].shapeIndex), -1, -1, posA, ornA, posB, ornB,
-				 posA.w, posB.w, mk4(sep.x, sep.y, sep.z), bufA, bufB, lane);
+		const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+		Side A, B;
+		if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
+			clipWarp(a, it.x, bodyA, bodyB, A.shape, B.shape, it.y, it.z, A.pos, A.orn, B.pos, B.orn, A.invMass, B.invMass, mk4(sep.x, sep.y, sep.z), bufA, bufB, lane);
 		__syncwarp();
+	}
+}
+
+// ---------------------------------------------------------------- primitives: plane x convex, plane x compound
+// One THREAD per broadphase pair that involves a plane.  Restates the reference's host twins
+// computeContactPlaneConvex / computeContactPlaneCompound (b3ConvexHullContact.cpp:1272-1395,
+// 2182-2320; device version primitiveContacts.cl:584-726) operation by operation, including the
+// b3Transform inverse/compose arithmetic (b3Transform.h:90-93,183-197; b3Matrix3x3.h operator*).
+B3_D Mat3 matTranspose(const Mat3& m)
+{
+	Mat3 t;
+	t.r0 = mk4(m.r0.x, m.r1.x, m.r2.x);
+	t.r1 = mk4(m.r0.y, m.r1.y, m.r2.y);
+	t.r2 = mk4(m.r0.z, m.r1.z, m.r2.z);
+	return t;
+}
+// b3Matrix3x3 operator*(m1, m2): row i = (m2.tdotx(m1[i]), m2.tdoty(m1[i]), m2.tdotz(m1[i]))
+B3_D Mat3 matMul(const Mat3& m1, const Mat3& m2)
+{
+	Mat3 r;
+	r.r0 = mk4(m2.r0.x * m1.r0.x + m2.r1.x * m1.r0.y + m2.r2.x * m1.r0.z, m2.r0.y * m1.r0.x + m2.r1.y * m1.r0.y + m2.r2.y * m1.r0.z,
+			   m2.r0.z * m1.r0.x + m2.r1.z * m1.r0.y + m2.r2.z * m1.r0.z);
+	r.r1 = mk4(m2.r0.x * m1.r1.x + m2.r1.x * m1.r1.y + m2.r2.x * m1.r1.z, m2.r0.y * m1.r1.x + m2.r1.y * m1.r1.y + m2.r2.y * m1.r1.z,
+			   m2.r0.z * m1.r1.x + m2.r1.z * m1.r1.y + m2.r2.z * m1.r1.z);
+	r.r2 = mk4(m2.r0.x * m1.r2.x + m2.r1.x * m1.r2.y + m2.r2.x * m1.r2.z, m2.r0.y * m1.r2.x + m2.r1.y * m1.r2.y + m2.r2.y * m1.r2.z,
+			   m2.r0.z * m1.r2.x + m2.r1.z * m1.r2.y + m2.r2.z * m1.r2.z);
+	return r;
+}
+
+constexpr int MAX_PLANE_CONVEX_POINTS = 64;
+
+B3_D void planeConvexThread(const NpArgs& a, int pairIndex, int planeBody, int convexBody, int child, const Side& B)
+{
+	const float4 posA = a.pose[2 * planeBody], ornA = a.pose[2 * planeBody + 1];
+	const float invMassA = posA.w;
+	const int cA = a.coll[planeBody];
+	const float4 planeEq = __ldg(reinterpret_cast<const float4*>(&a.faces[__ldg(&a.collidables[cA].shapeIndex)].plane));
+	const float4 planeNormal = mk4(planeEq.x, planeEq.y, planeEq.z);
+	const float4 planeNormalWorld = quatRotate(ornA, planeNormal);
+	const float planeConstant = planeEq.w;
+	const HullRef hB = loadHull(a.convex, B.shape);
+	const Mat3 Mb = matFromQuat(B.orn), Ma = matFromQuat(ornA);
+	const Mat3 MbT = matTranspose(Mb), MaT = matTranspose(Ma);
+	// planeInConvex.getBasis() = convexWorldTransform.inverse().basis * planeTransform.basis
+	const Mat3 pic = matMul(MbT, Ma);
+	const float4 planeNormalInConvex = matMulVec(pic, neg3(planeNormal));
+	// planeTransform.inverse(): basis MaT, origin MaT * (-posA)
+	const float4 invOriginA = matMulVec(MaT, neg3(mk4(posA.x, posA.y, posA.z)));
+	float maxDot = -1e30f;
+	float4 pts[MAX_PLANE_CONVEX_POINTS];
+	int numPoints = 0;
+	for (int i = 0; i < hB.numVertices; i++)
+	{
+		const float4 vtx = __ldg(&a.vertices[hB.vertexOffset + i]);
+		const float curDot = dot3(vtx, planeNormalInConvex);
+		if (curDot > maxDot)
+		{
+			maxDot = curDot;
+			if (numPoints == MAX_PLANE_CONVEX_POINTS) numPoints--;  // make sure the deepest point is always included
+		}
+		if (numPoints < MAX_PLANE_CONVEX_POINTS)
+		{
+			const float4 r = matMulVec(Mb, vtx);
+			float4 vtxWorld = mk4(r.x + B.pos.x, r.y + B.pos.y, r.z + B.pos.z);
+			const float4 q = matMulVec(MaT, vtxWorld);
+			const float4 vtxInPlane = mk4(q.x + invOriginA.x, q.y + invOriginA.y, q.z + invOriginA.z);
+			const float dist = dot3(planeNormal, vtxInPlane) - planeConstant;
+			if (dist < 0.f)
+			{
+				vtxWorld.w = dist;
+				pts[numPoints++] = vtxWorld;
+			}
+		}
+	}
+	int idx[4] = {0, 1, 2, 3};
+	int numReduced = numPoints;
+	if (numPoints > 4)
+	{
+		// extractManifoldSequentialGlobal (b3ConvexHullContact.cpp:418-501) == b3ReduceContacts
+		const int nP = numPoints > 64 ? 64 : numPoints;
+		float4 center = mk4(0, 0, 0);
+		for (int i = 0; i < nP; i++) center = add3(center, pts[i]);
+		center = scale3(center, 1.0f / (float)nP);
+		const float4 aVector = sub3(pts[0], center);
+		float4 u = cross3(planeNormalInConvex, aVector);
+		float4 v = cross3(planeNormalInConvex, u);
+		u = normalized3(u);
+		v = normalized3(v);
+		float minW = FLT_MAX;
+		int minIndex = -1;
+		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
+		for (int ie = 0; ie < nP; ie++)
+		{
+			if (pts[ie].w < minW)
+			{
+				minW = pts[ie].w;
+				minIndex = ie;
+			}
+			const float4 r = sub3(pts[ie], center);
+			float f = dot3(u, r);
+			if (f < m0)
+			{
+				m0 = f;
+				idx[0] = ie;
+			}
+			f = dot3(neg3(u), r);
+			if (f < m1)
+			{
+				m1 = f;
+				idx[1] = ie;
+			}
+			f = dot3(v, r);
+			if (f < m2)
+			{
+				m2 = f;
+				idx[2] = ie;
+			}
+			f = dot3(neg3(v), r);
+			if (f < m3)
+			{
+				m3 = f;
+				idx[3] = ie;
+			}
+		}
+		if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
+		numReduced = 4;
+	}
+	if (numReduced <= 0) return;
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return;
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	for (int i = 0; i < 4; i++) cw[i] = i < numReduced ? pts[idx[i]] : mk4(0, 0, 0, 0);
+	cw[4] = mk4(-planeNormalWorld.x, -planeNormalWorld.y, -planeNormalWorld.z, (float)numReduced);
+	int4 t;
+	t.x = (int)(0u | (45874u << 16));  // setFrictionCoeff(0.7) -> (unsigned short)(0.7 * 0xffff)
+	t.y = pairIndex;                   // m_batchIdx = pairIndex
+	t.z = invMassA == 0.f ? -planeBody : planeBody;
+	t.w = B.invMass == 0.f ? -convexBody : convexBody;
+	reinterpret_cast<int4*>(c)[5] = t;
+	int4 t2;
+	t2.x = -1;
+	t2.y = child;  // child shape of the compound this contact belongs to (-1 for a plain hull)
+	t2.z = 0;
+	t2.w = 0;
+	reinterpret_cast<int4*>(c)[6] = t2;
+	a.pairsOut[pairIndex].z = (int)slot;
+}
+
+__global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
+{
+	const int numPairs = (int)a.ctr[CTR_PAIRS];
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < numPairs; p += gridDim.x * blockDim.x)
+	{
+		int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
+		int cA = a.coll[bodyA], cB = a.coll[bodyB];
+		if (cA < 0 || cB < 0) continue;
+		int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
+		if (typeB == B3B200_SHAPE_PLANE && typeA != B3B200_SHAPE_PLANE)
+		{
+			// the plane is always passed first (b3ConvexHullContact.cpp:2668-2690)
+			int t = bodyA;
+			bodyA = bodyB;
+			bodyB = t;
+			t = cA;
+			cA = cB;
+			cB = t;
+			t = typeA;
+			typeA = typeB;
+			typeB = t;
+		}
+		if (typeA != B3B200_SHAPE_PLANE) continue;
+		if (typeB == B3B200_SHAPE_CONVEX_HULL)
+		{
+			Side B;
+			if (resolveSide(a, bodyB, -1, B)) planeConvexThread(a, p, bodyA, bodyB, -1, B);
+		}
+		else if (typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS)
+		{
+			const int first = __ldg(&a.collidables[cB].shapeIndex), n = __ldg(&a.collidables[cB].numChildShapes);
+			for (int cI = 0; cI < n; cI++)
+			{
+				Side B;
+				if (resolveSide(a, bodyB, first + cI, B)) planeConvexThread(a, p, bodyA, bodyB, first + cI, B);
+			}
+		}
 	}
 }
 
@@ -751,10 +998,17 @@ int launchNarrowphase(World* w)
 	a.uniqueEdges = w->dUniqueEdges.ptr;
 	a.faces = w->dFaces.ptr;
 	a.indices = w->dIndices.ptr;
+	a.childShapes = w->dChildShapes.ptr;
 	a.contacts = w->dContacts.ptr;
 	a.maxContacts = w->cfg.maxContactCapacity;
+	a.maxWorkItems = (int)w->dSurvivors.cap;
 	a.clipMin = w->clipMinDist;
 	a.clipMax = w->clipMaxDist;
+	if (w->hasPlanes)
+	{
+		npPrimitiveKernel<<<w->smCount * 8, 128, 0, s>>>(a);
+		B3_LAUNCH_CHECK();
+	}
 	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
 	B3_LAUNCH_CHECK();
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);

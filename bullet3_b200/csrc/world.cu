@@ -73,7 +73,7 @@ void World::destroy()
 }
 
 // b3TransformAabb (src/Bullet3Geometry/b3AabbUtil.h:182-197), float, scalar path
-static void transformAabbHost(const float* lmn, const float* lmx, float margin, const float* pos, const float* orn, float* outMin, float* outMax)
+void transformAabbHost(const float* lmn, const float* lmx, float margin, const float* pos, const float* orn, float* outMin, float* outMax)
 {
 	float4 half = mk4(0.5f * (lmx[0] - lmn[0]), 0.5f * (lmx[1] - lmn[1]), 0.5f * (lmx[2] - lmn[2]));
 	half = mk4(half.x + margin, half.y + margin, half.z + margin);
@@ -93,7 +93,7 @@ static void transformAabbHost(const float* lmn, const float* lmx, float margin, 
 	}
 }
 
-static int allocateCollidable(World* w)
+int allocateCollidable(World* w)
 {
 	// b3GpuNarrowPhase::allocateCollidable (b3GpuNarrowPhase.cpp:144-157)
 	if ((int)w->collidables.size() >= w->cfg.maxConvexShapes)
@@ -445,41 +445,6 @@ extern "C" int b3b200_register_convex_points(b3b200_world* w, const float* verti
 								  (int)h.indices.size(), h.uniqueEdges.data(), (int)h.uniqueEdges.size(), &h.poly);
 }
 
-extern "C" int b3b200_register_plane(b3b200_world* w, const float* normal3, float planeConstant)
-{
-	(void)w;
-	(void)normal3;
-	(void)planeConstant;
-	setLastError("registerPlaneShape: not built yet");
-	return -1;
-}
-extern "C" int b3b200_register_sphere(b3b200_world* w, float radius)
-{
-	(void)w;
-	(void)radius;
-	setLastError("registerSphereShape: not built yet");
-	return -1;
-}
-extern "C" int b3b200_register_compound(b3b200_world* w, const b3b200_child_shape* children, int numChildren)
-{
-	(void)w;
-	(void)children;
-	(void)numChildren;
-	setLastError("registerCompoundShape: not built yet");
-	return -1;
-}
-extern "C" int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVertices, const int* triIndices, int numIndices, const float* scaling3)
-{
-	(void)w;
-	(void)vertices;
-	(void)numVertices;
-	(void)triIndices;
-	(void)numIndices;
-	(void)scaling3;
-	setLastError("registerConcaveMesh: not built yet");
-	return -1;
-}
-
 static int registerBodyCommon(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex,
 							  const float* aabbMin, const float* aabbMax)
 {
@@ -583,9 +548,14 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(w->dCollidableIdx.reserve(nb));
 	const size_t nc = std::max(w->cfg.maxContactCapacity, 1);
 	B3_TRY(w->dContacts.reserve(nc));
-	B3_TRY(w->dSurvivors.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
-	B3_TRY(w->dOverlapPairs.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
-	B3_TRY(w->dOverlapSep.reserve(std::max(w->cfg.maxBroadphasePairs, 1)));
+	// work items: one per convex pair + child pairs of compounds (b3Config::m_compoundPairCapacity)
+	const size_t nItems = (size_t)std::max(w->cfg.maxBroadphasePairs, 1) + (w->childShapes.empty() ? 0 : (size_t)std::max(w->cfg.compoundPairCapacity, 0));
+	B3_TRY(w->dSurvivors.reserve(nItems));
+	B3_TRY(w->dOverlapPairs.reserve(nItems));
+	B3_TRY(w->dOverlapSep.reserve(nItems));
+	w->hasPlanes = false;
+	for (size_t i = 0; i < w->collidables.size(); i++)
+		if (w->collidables[i].shapeType == B3B200_SHAPE_PLANE) w->hasPlanes = true;
 	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));

@@ -114,3 +114,19 @@ def bench_convex_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, spacing=
     col = np.asarray(shapes, np.int32)[col]
     world.register_instances(np.ones(n, np.float32), pos, q.astype(np.float32), col)
     return shapes
+
+
+def compound_children(child_collidable, offsets, orientations=None):
+    """b3GpuChildShape records for registerCompoundShape (children must be convex-hull collidables)"""
+    from . import capi
+
+    ch = np.zeros(len(offsets), capi.child_shape_t)
+    for i, o in enumerate(offsets):
+        ch["childPosition"][i, :3] = o
+        ch["childOrientation"][i] = IDENT if orientations is None else orientations[i]
+        ch["shapeIndex"][i] = child_collidable
+        ch["shapeType"][i] = capi.SHAPE_CONVEX_HULL
+    return ch
+
+
+L_OFFSETS = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)]  # 3-box "L" (SURVEY 8(d) config 4)

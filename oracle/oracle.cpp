@@ -677,6 +677,189 @@ int orc_convex_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_rigid
 	return nContacts;
 }
 
+// ---------------------------------------------------------------------------------------------
+// General contact loop: convex x convex, compound children (x compound / x convex), plane x convex,
+// plane x compound -- the dispatch of the reference's host loop
+// (Bullet3OpenCL/NarrowphaseCollision/b3ConvexHullContact.cpp:2655-2724).
+namespace
+{
+struct SideO
+{
+	int shape;
+	V3 pos, orn;
+	float invMass;
+};
+// child transform composition: sat.cl:836-862 / b3ConvexHullContact.cpp:1806-1832
+bool resolveSide(const b3b200_rigid_body* bodies, const b3b200_collidable* collidables, const b3b200_child_shape* children, int body, int child, SideO& s)
+{
+	V3 pos = ld(bodies[body].pos), orn = ld(bodies[body].quat);
+	s.invMass = bodies[body].invMass;
+	int coll;
+	if (child >= 0)
+	{
+		V3 cp = ld(children[child].childPosition), co = ld(children[child].childOrientation);
+		V3 r = quatRotate(orn, cp);
+		pos = mk(r.x + pos.x, r.y + pos.y, r.z + pos.z);
+		orn = quatMul(orn, co);
+		coll = children[child].shapeIndex;
+	}
+	else
+		coll = bodies[body].collidableIdx;
+	if (coll < 0 || collidables[coll].shapeType != B3B200_SHAPE_CONVEX_HULL) return false;
+	s.shape = collidables[coll].shapeIndex;
+	pos.w = 0.f;
+	s.pos = pos;
+	s.orn = orn;
+	return true;
+}
+M3 transposeM(const M3& m)
+{
+	M3 t;
+	t.r[0] = mk(m.r[0].x, m.r[1].x, m.r[2].x);
+	t.r[1] = mk(m.r[0].y, m.r[1].y, m.r[2].y);
+	t.r[2] = mk(m.r[0].z, m.r[1].z, m.r[2].z);
+	return t;
+}
+// b3Matrix3x3 operator* (Bullet3Common/b3Matrix3x3.h: tdotx/tdoty/tdotz of m2 with the rows of m1)
+M3 mulM(const M3& m1, const M3& m2)
+{
+	M3 r;
+	for (int i = 0; i < 3; i++)
+		r.r[i] = mk(m2.r[0].x * m1.r[i].x + m2.r[1].x * m1.r[i].y + m2.r[2].x * m1.r[i].z, m2.r[0].y * m1.r[i].x + m2.r[1].y * m1.r[i].y + m2.r[2].y * m1.r[i].z,
+					m2.r[0].z * m1.r[i].x + m2.r[1].z * m1.r[i].y + m2.r[2].z * m1.r[i].z);
+	return r;
+}
+}  // namespace
+
+extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_rigid_body* bodies, const b3b200_collidable* collidables,
+							const b3b200_convex_polyhedron* convex, const b3b200_float4* vertices, const b3b200_float4* uniqueEdges, const b3b200_face* faces,
+							const int* indices, const b3b200_child_shape* children, float minDist, float maxDist, b3b200_contact4* out, int maxContacts)
+{
+	int nContacts = 0;
+	std::vector<V3> b1(MAX_VERTS), b2(MAX_VERTS), cont(MAX_VERTS);
+	auto convexPair = [&](int bodyA, int bodyB, int childA, int childB, const SideO& A, const SideO& B) {
+		Hull hA = hullOf(A.shape, convex, vertices, uniqueEdges, faces, indices);
+		Hull hB = hullOf(B.shape, convex, vertices, uniqueEdges, faces, indices);
+		V3 sep;
+		if (!findSeparatingAxis(hA, hB, A.pos, A.orn, B.pos, B.orn, sep)) return;
+		V3 ornA2 = quatFromMat(matFromQuat(A.orn)), ornB2 = quatFromMat(matFromQuat(B.orn));
+		int n = clipHullAgainstHull(sep, hA, hB, A.pos, ornA2, B.pos, ornB2, b1.data(), b2.data(), minDist, maxDist, cont.data(), MAX_VERTS);
+		if (n <= 0) return;
+		int idx[4] = {0, 1, 2, 3};
+		int numPoints = reduceContacts(cont.data(), n, sep, idx);
+		if (nContacts >= maxContacts) return;
+		b3b200_contact4& c = out[nContacts++];
+		memset(&c, 0, sizeof(c));
+		c.bodyAPtrAndSignBit = (A.invMass == 0) ? -bodyA : bodyA;
+		c.bodyBPtrAndSignBit = (B.invMass == 0) ? -bodyB : bodyB;
+		c.frictionCmp = 45874;
+		c.childIndexA = childA;
+		c.childIndexB = childB;
+		for (int k = 0; k < numPoints; k++) c.worldPosB[k] = st(cont[idx[k]]);
+		c.worldNormalOnB = st(mk(sep.x, sep.y, sep.z, (float)numPoints));
+	};
+	// computeContactPlaneConvex (b3ConvexHullContact.cpp:1272-1395) for one hull
+	auto planeConvex = [&](int pairIndex, int planeBody, int convexBody, int child, const SideO& B) {
+		V3 posA = ld(bodies[planeBody].pos), ornA = ld(bodies[planeBody].quat);
+		int cA = bodies[planeBody].collidableIdx;
+		V3 planeEq = ld(faces[collidables[cA].shapeIndex].plane);
+		V3 planeNormal = mk(planeEq.x, planeEq.y, planeEq.z);
+		V3 planeNormalWorld = quatRotate(ornA, planeNormal);
+		float planeConstant = planeEq.w;
+		const b3b200_convex_polyhedron& hB = convex[B.shape];
+		M3 Mb = matFromQuat(B.orn), Ma = matFromQuat(ornA);
+		M3 MbT = transposeM(Mb), MaT = transposeM(Ma);
+		M3 pic = mulM(MbT, Ma);
+		V3 planeNormalInConvex = matMul(pic, neg(planeNormal));
+		V3 invOriginA = matMul(MaT, neg(mk(posA.x, posA.y, posA.z)));
+		float maxDot = -1e30f;
+		V3 pts[64];
+		int numPoints = 0;
+		for (int i = 0; i < hB.numVertices; i++)
+		{
+			V3 vtx = ld(vertices[hB.vertexOffset + i]);
+			float curDot = dot(vtx, planeNormalInConvex);
+			if (curDot > maxDot)
+			{
+				maxDot = curDot;
+				if (numPoints == 64) numPoints--;
+			}
+			if (numPoints < 64)
+			{
+				V3 vtxWorld = add(matMul(Mb, vtx), mk(B.pos.x, B.pos.y, B.pos.z));
+				V3 vtxInPlane = add(matMul(MaT, vtxWorld), invOriginA);
+				float dist = dot(planeNormal, vtxInPlane) - planeConstant;
+				if (dist < 0.f)
+				{
+					vtxWorld.w = dist;
+					pts[numPoints++] = vtxWorld;
+				}
+			}
+		}
+		int idx[4] = {0, 1, 2, 3};
+		int numReduced = numPoints;
+		if (numPoints > 4) numReduced = reduceContacts(pts, numPoints, planeNormalInConvex, idx);  // extractManifoldSequentialGlobal :418-501
+		if (numReduced <= 0 || nContacts >= maxContacts) return;
+		b3b200_contact4& c = out[nContacts++];
+		memset(&c, 0, sizeof(c));
+		c.worldNormalOnB = st(mk(-planeNormalWorld.x, -planeNormalWorld.y, -planeNormalWorld.z, (float)numReduced));
+		c.frictionCmp = 45874;
+		c.batchIdx = pairIndex;
+		c.bodyAPtrAndSignBit = bodies[planeBody].invMass == 0 ? -planeBody : planeBody;
+		c.bodyBPtrAndSignBit = bodies[convexBody].invMass == 0 ? -convexBody : convexBody;
+		c.childIndexA = -1;
+		c.childIndexB = child;
+		for (int i = 0; i < numReduced; i++) c.worldPosB[i] = st(pts[idx[i]]);
+	};
+	for (int p = 0; p < nPairs; p++)
+	{
+		int bodyA = pairs[p].x, bodyB = pairs[p].y;
+		int cA = bodies[bodyA].collidableIdx, cB = bodies[bodyB].collidableIdx;
+		int typeA = collidables[cA].shapeType, typeB = collidables[cB].shapeType;
+		const bool hullA = typeA == B3B200_SHAPE_CONVEX_HULL, hullB = typeB == B3B200_SHAPE_CONVEX_HULL;
+		const bool compA = typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS, compB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
+		if (hullA && hullB)
+		{
+			SideO A, B;
+			if (resolveSide(bodies, collidables, children, bodyA, -1, A) && resolveSide(bodies, collidables, children, bodyB, -1, B)) convexPair(bodyA, bodyB, -1, -1, A, B);
+		}
+		else if ((hullA || compA) && (hullB || compB))
+		{
+			if (bodies[bodyA].invMass == 0 && bodies[bodyB].invMass == 0) continue;
+			int firstA = compA ? collidables[cA].shapeIndex : -1, nA = compA ? collidables[cA].numChildShapes : 1;
+			int firstB = compB ? collidables[cB].shapeIndex : -1, nB = compB ? collidables[cB].numChildShapes : 1;
+			for (int i = 0; i < nA; i++)
+				for (int j = 0; j < nB; j++)
+				{
+					SideO A, B;
+					int ca = compA ? firstA + i : -1, cb = compB ? firstB + j : -1;
+					if (resolveSide(bodies, collidables, children, bodyA, ca, A) && resolveSide(bodies, collidables, children, bodyB, cb, B)) convexPair(bodyA, bodyB, ca, cb, A, B);
+				}
+		}
+		else if (typeA == B3B200_SHAPE_PLANE || typeB == B3B200_SHAPE_PLANE)
+		{
+			int planeBody = typeA == B3B200_SHAPE_PLANE ? bodyA : bodyB, other = typeA == B3B200_SHAPE_PLANE ? bodyB : bodyA;
+			int cO = bodies[other].collidableIdx, typeO = collidables[cO].shapeType;
+			if (typeO == B3B200_SHAPE_CONVEX_HULL)
+			{
+				SideO B;
+				if (resolveSide(bodies, collidables, children, other, -1, B)) planeConvex(p, planeBody, other, -1, B);
+			}
+			else if (typeO == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS)
+			{
+				// computeContactPlaneCompound (b3ConvexHullContact.cpp:2182-2320)
+				for (int c = 0; c < collidables[cO].numChildShapes; c++)
+				{
+					SideO B;
+					int child = collidables[cO].shapeIndex + c;
+					if (resolveSide(bodies, collidables, children, other, child, B)) planeConvex(p, planeBody, other, child, B);
+				}
+			}
+		}
+	}
+	return nContacts;
+}
+
 // Graph colouring = sequential first-fit in descending priority order, priority =
 // (hashContact(bodyA, bodyB, childA, childB) << 32) | (index + 1).  This is the
 // batching rule of the new solver (bullet3_b200/csrc/solver.cu); it plays the role

@@ -54,6 +54,7 @@ class Shapes:
         self.unique_edges = _arr(tables["unique_edges"], np.float32).reshape(-1, 4)
         self.faces = _arr(tables["faces"], capi.face_t)
         self.indices = _arr(tables["indices"], np.int32)
+        self.child_shapes = _arr(tables.get("child_shapes", np.zeros(0, capi.child_shape_t)), capi.child_shape_t)
 
 
 def update_aabbs(lib, prefix, bodies, shapes):
@@ -199,3 +200,60 @@ def refcl_pgs_solve(sorted_contacts, batch_sizes, bodies, inertias, iterations, 
     rc = refcl().refcl_pgs_solve(P(contacts), len(contacts), P(bs), len(bs), P(bodies), len(bodies), P(inertias), int(iterations), C.c_float(dt), P(cs))
     assert rc == 0
     return bodies, cs[: len(contacts)]
+
+
+def contacts_oracle(pairs, bodies, shapes, clip_min, clip_max, max_contacts):
+    """general contact loop: convex, compound children, planes"""
+    pairs = _arr(pairs, capi.int4_t)
+    bodies = _arr(bodies, capi.rigid_body_t)
+    out = np.zeros(max(max_contacts, 1), capi.contact4_t)
+    ch = shapes.child_shapes if len(shapes.child_shapes) else np.zeros(1, capi.child_shape_t)
+    n = oracle().orc_contacts(P(pairs), len(pairs), P(bodies), P(shapes.collidables), P(shapes.convex), P(shapes.vertices), P(shapes.unique_edges),
+                              P(shapes.faces), P(shapes.indices), P(ch), C.c_float(clip_min), C.c_float(clip_max), P(out), int(max_contacts))
+    return out[:n]
+
+
+class RefNarrowphase:
+    """the reference b3GpuNarrowPhase (CHECK_ON_HOST build over the fake OpenCL)"""
+
+    def __init__(self, cfg):
+        self.L = refcl()
+        self.h = C.c_void_p(self.L.refcl_np_create(P(cfg)))
+
+    def close(self):
+        if self.h:
+            self.L.refcl_np_destroy(self.h)
+            self.h = None
+
+    def register_convex_points(self, pts, scaling=(1.0, 1.0, 1.0)):
+        pts = _arr(pts, np.float32).reshape(-1, 3)
+        sc = (C.c_float * 4)(*[float(x) for x in scaling], 1.0)
+        return self.L.refcl_np_register_convex_points(self.h, P(pts), len(pts), sc)
+
+    def register_plane(self, normal, constant):
+        n = (C.c_float * 3)(*[float(x) for x in normal])
+        return self.L.refcl_np_register_plane(self.h, n, C.c_float(constant))
+
+    def register_compound(self, children):
+        children = _arr(children, capi.child_shape_t)
+        return self.L.refcl_np_register_compound(self.h, P(children), len(children))
+
+    def register_body(self, collidable, mass, pos, orn, aabb_min, aabb_max):
+        f = lambda v, n: (C.c_float * n)(*[float(x) for x in list(v)[:n]])
+        return self.L.refcl_np_register_body(self.h, int(collidable), C.c_float(mass), f(list(pos) + [0], 4), f(orn, 4), f(aabb_min, 3), f(aabb_max, 3))
+
+    def table(self, which, dt):
+        n = C.c_int(0)
+        self.L.refcl_np_get_table(self.h, which, None, 0, C.byref(n))
+        out = np.zeros(n.value, dt)
+        if n.value:
+            self.L.refcl_np_get_table(self.h, which, P(out), n.value, C.byref(n))
+        return out
+
+    def compute_contacts(self, bodies, pairs, aabbs, max_contacts):
+        bodies = _arr(bodies, capi.rigid_body_t)
+        pairs = _arr(pairs, capi.int4_t)
+        aabbs = _arr(aabbs, capi.aabb_t)
+        out = np.zeros(max(max_contacts, 1), capi.contact4_t)
+        n = self.L.refcl_np_compute_contacts(self.h, P(bodies), len(bodies), P(pairs), len(pairs), P(aabbs), P(out), int(max_contacts), None)
+        return out[:n]

@@ -436,3 +436,65 @@ def test_trajectory_energy_and_penetration():
     c = w.contacts()
     depth = np.concatenate([c["worldPosB"][c["worldNormalOnB"][:, 3] > k, k, 3] for k in range(4)])
     assert depth.min() > -0.25  # penetration stays small
+
+
+# ------------------------------------------------------------------ planes and compounds
+def shapes_world(seed=0, n=400, plane=True):
+    rng = np.random.default_rng(seed)
+    w = capi.World(capi.default_config(4096))
+    box = w.register_convex_points(scenes.box_points(0.5))
+    hull = w.register_convex_points(scenes.random_hull_points(rng, 10, 0.6, 0.9))
+    ell = w.register_compound(scenes.compound_children(box, scenes.L_OFFSETS))
+    if plane:
+        pl = w.register_plane((0, 1, 0), 0.0)
+        w.register_instance(0.0, (0, 0, 0), scenes.IDENT, pl)
+    else:
+        scenes.add_ground_box(w, 50.0)
+    kinds = [box, hull, ell]
+    side = 6.0
+    for i in range(n):
+        p = (rng.uniform(-side, side), rng.uniform(0.1, 4.0), rng.uniform(-side, side))
+        w.register_instance(1.0, p, scenes.random_quat(rng), kinds[int(rng.integers(0, 3))])
+    w.upload()
+    t = w.tables()
+    return w, oa.Shapes(t), t["bodies"], t["inertias"]
+
+
+def contact_sort(c):
+    return c[np.lexsort((c["worldPosB"][:, 0, 0], c["childB"], c["childA"], np.abs(c["bodyB"]), np.abs(c["bodyA"])))]
+
+
+@pytest.mark.parametrize("seed,plane", [(0, True), (1, True), (2, False)])
+def test_plane_and_compound_contacts_match_oracle(seed, plane):
+    w, sh, bodies, _ = shapes_world(seed, plane=plane)
+    w.update_aabbs()
+    w.find_pairs()
+    pairs = w.pairs()
+    w.compute_contacts()
+    g = contact_sort(w.contacts())
+    o = contact_sort(oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18))
+    assert len(o) > 200 and len(g) == len(o)
+    for f in ("bodyA", "bodyB", "childA", "childB", "frictionCmp"):
+        assert np.array_equal(g[f], o[f]), f
+    assert np.array_equal(g["worldNormalOnB"].view(np.uint32), o["worldNormalOnB"].view(np.uint32))
+    npts = o["worldNormalOnB"][:, 3].astype(int)
+    for k in range(4):
+        m = npts > k
+        assert np.array_equal(g["worldPosB"][m, k].view(np.uint32), o["worldPosB"][m, k].view(np.uint32)), k
+    types = sh.collidables["shapeType"][bodies["collidableIdx"]]
+    ta, tb = types[np.abs(o["bodyA"])], types[np.abs(o["bodyB"])]
+    assert ((ta == capi.SHAPE_COMPOUND) & (tb == capi.SHAPE_COMPOUND)).any() and ((ta == capi.SHAPE_COMPOUND) ^ (tb == capi.SHAPE_COMPOUND)).any()
+    if plane:
+        assert (ta == capi.SHAPE_PLANE).sum() > 10
+
+
+def test_compound_scene_steps_and_rests_on_plane():
+    w, sh, bodies, _ = shapes_world(3, n=120)  # random, initially interpenetrating pile
+    w.set_solver(capi.SOLVER_PGS, 10)
+    for _ in range(480):
+        w.step(1 / 60)
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all()
+    assert b["pos"][dyn, 1].min() > -0.3  # nothing fell through the plane
+    assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 1.0

