@@ -20,6 +20,7 @@ enum Counter
 	CTR_UNCOLOURED = 7,
 	CTR_SURVIVORS = 8,
 	CTR_OVERLAPS = 9,
+	CTR_HALO = 10,
 	CTR_COUNT = 16
 };
 enum OverflowBits
@@ -127,6 +128,7 @@ struct World
 	DevBuf<float4> dPose;  // 2 float4 per body
 	DevBuf<float4> dVel;   // 2 float4 per body
 	DevBuf<int> dCollidableIdx;
+	DevBuf<int> dGhostGlobalId;  // slab mode: global id mirrored by each ghost slot (-1 = parked / owned)
 	bool soaDirty = false;  // SoA is newer than AoS
 	bool hasPlanes = false;  // any SHAPE_PLANE collidable registered (enables the primitive-contact kernel)
 

@@ -195,6 +195,18 @@ int b3b200_bp_device_pairs(b3b200_broadphase* bp, void** devicePtr);    /* getOv
 int b3b200_bp_device_aabbs(b3b200_broadphase* bp, void** devicePtr);    /* getAabbBufferWS */
 int b3b200_bp_last_ms(b3b200_broadphase* bp, float* ms);
 
+/* ------------------------------------------------- multi-GPU: spatial slab decomposition (no reference counterpart)
+ * A rank owns bodies [0, numOwned) of its world; the trailing bodies are ghost slots mirroring the neighbours'
+ * boundary bodies.  pack selects the owned dynamic bodies whose world AABB reaches into [lo, hi] along `axis` and writes
+ * b3b200_halo_record_size()-byte records (pose, velocity, inverse inertias, collidable, global id) into a DEVICE buffer;
+ * the caller ships it to the neighbour (NCCL send/recv); unpack scatters received records into the ghost slots
+ * [firstGhostSlot, firstGhostSlot + numGhostSlots) and parks the unused ones.  See bullet3_b200/slab.py. */
+int b3b200_halo_record_size(void);
+int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, int numOwned, int globalIdBase, int rank, void* dstDevice,
+					 int capacity, int* countOut);
+int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int count, int firstGhostSlot, int numGhostSlots);
+int b3b200_halo_ghost_ids(b3b200_world* w, int* dst, int n);
+
 /* plain device -> host copy of a buffer obtained from b3b200_device_buffer / b3b200_bp_device_* (synchronous) */
 int b3b200_device_to_host(void* dstHost, const void* srcDevice, unsigned long long bytes, int device);
 

@@ -1,0 +1,20 @@
+"""Slab decomposition over 2 GPUs against the single-GPU step (skipped on a one-GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_slab_two_gpus_matches_single():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29517",
+           os.path.join(ROOT, "tools", "slab_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=540)
+    assert out.returncode == 0 and "SLAB OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
