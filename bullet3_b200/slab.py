@@ -127,11 +127,11 @@ class SlabWorld:
         # ghost slots: dynamic bodies parked far away until the first exchange fills them
         if n_ghost_slots:
             park = np.zeros((n_ghost_slots, 3), np.float32)
-            park[:, 0] = 1.0e6 + 8.0 * np.arange(n_ghost_slots)
+            park[:, 0] = 1.0e6 + 1024.0 * np.arange(n_ghost_slots)
             park[:, 1] = -1.0e6
             park[:, 2] = 1.0e6
             q0 = np.tile(np.array([0, 0, 0, 1], np.float32), (n_ghost_slots, 1))
-            self.world.register_instances(np.ones(n_ghost_slots, np.float32), park, q0, np.full(n_ghost_slots, cols[0], np.int32))
+            self.world.register_instances(np.ones(n_ghost_slots, np.float32), park, q0, np.full(n_ghost_slots, cols[int(slot[0])], np.int32))
         self.world.upload()
         self.num_owned = self.n_static + self.n_owned_dyn
         self.first_ghost = self.num_owned
