@@ -103,6 +103,12 @@ struct World
 	std::vector<b3b200_bvh_info> bvhInfos;
 	std::vector<b3b200_bvh_node> bvhNodes;
 	std::vector<b3b200_bvh_subtree> bvhSubtrees;
+	// concave trimeshes: this build's own acceleration structure (shapes.cu): a binary AABB tree per mesh with
+	// exact float boxes.  Node = 2 x float4 {min.xyz, bits(left child | first triangle slot)}, {max.xyz, bits(0 |
+	// triangle count)}; children of a node are adjacent; leaves index meshTris (original triangle numbers).
+	std::vector<b3b200_float4> meshNodes;
+	std::vector<int> meshTris;
+	std::vector<b3b200_int4> meshInfos;  // per bvhInfos entry: {first node (in nodes), node count, first slot in meshTris, triangle count}
 	// host-side bodies
 	std::vector<b3b200_rigid_body> bodies;
 	std::vector<b3b200_inertia> inertias;
@@ -118,6 +124,9 @@ struct World
 	DevBuf<b3b200_bvh_info> dBvhInfos;
 	DevBuf<b3b200_bvh_node> dBvhNodes;
 	DevBuf<b3b200_bvh_subtree> dBvhSubtrees;
+	DevBuf<float4> dMeshNodes;
+	DevBuf<int> dMeshTris;
+	DevBuf<int4> dMeshInfos;
 
 	// device body state.  AoS (reference layout) is the boundary format; the
 	// step runs on the SoA split below: pose = {pos.xyz, invMass | quat} and
@@ -130,6 +139,7 @@ struct World
 	DevBuf<int> dCollidableIdx;
 	DevBuf<int> dGhostGlobalId;  // slab mode: global id mirrored by each ghost slot (-1 = parked / owned)
 	bool soaDirty = false;  // SoA is newer than AoS
+	bool hasConcave = false;  // any SHAPE_CONCAVE_TRIMESH collidable registered (enables the concave kernels)
 	bool hasPlanes = false;  // any SHAPE_PLANE collidable registered (enables the primitive-contact kernel)
 
 	Broadphase bp;
@@ -138,7 +148,7 @@ struct World
 	DevBuf<b3b200_contact4> dContacts;
 	DevBuf<unsigned int> dCounters;  // CTR_COUNT
 	DevBuf<b3b200_int4> dCompoundPairs;
-	DevBuf<b3b200_int4> dConcavePairs;
+	DevBuf<int4> dConcavePairs;  // (pair, triangle, child shape of B or -1, 0) work items of the concave path
 	DevBuf<int4> dSurvivors;     // work items (pair, childA, childB, 0) that passed the quick SAT reject
 	DevBuf<int4> dOverlapPairs;  // work items with a penetrating SAT result
 	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes
@@ -181,6 +191,7 @@ int launchUnpackSoA(World* w);  // SoA -> AoS
 int launchUpdateAabbs(World* w);
 int launchIntegrate(World* w, float dt, bool alsoAabbs);
 int launchNarrowphase(World* w);
+int launchConcave(World* w);  // concave.cu; called by launchNarrowphase when a trimesh is registered
 int launchSolverSetup(World* w);
 int launchSolverIterate(World* w);
 int launchJacobi(World* w);

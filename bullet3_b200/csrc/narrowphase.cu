@@ -1015,6 +1015,7 @@ int launchNarrowphase(World* w)
 	B3_LAUNCH_CHECK();
 	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
+	if (w->hasConcave) B3_TRY(launchConcave(w));
 	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity);
 	B3_LAUNCH_CHECK();
 	return 0;

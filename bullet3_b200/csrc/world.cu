@@ -344,6 +344,9 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->childShapes.clear();
 	w->bvhInfos.clear();
 	w->bvhNodes.clear();
+	w->meshNodes.clear();
+	w->meshTris.clear();
+	w->meshInfos.clear();
 	w->bvhSubtrees.clear();
 	w->bodies.clear();
 	w->inertias.clear();
@@ -541,6 +544,9 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(uploadVec(w->dBvhInfos, w->bvhInfos, 0, s));
 	B3_TRY(uploadVec(w->dBvhNodes, w->bvhNodes, 0, s));
 	B3_TRY(uploadVec(w->dBvhSubtrees, w->bvhSubtrees, 0, s));
+	B3_TRY(uploadVec(w->dMeshNodes, w->meshNodes, 0, s));
+	B3_TRY(uploadVec(w->dMeshTris, w->meshTris, 0, s));
+	B3_TRY(uploadVec(w->dMeshInfos, w->meshInfos, 0, s));
 	B3_TRY(uploadVec(w->dBodiesAoS, w->bodies, 0, s));
 	B3_TRY(uploadVec(w->dInertias, w->inertias, 0, s));
 	B3_TRY(w->dPose.reserve(2 * nb));
@@ -554,8 +560,13 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(w->dOverlapPairs.reserve(nItems));
 	B3_TRY(w->dOverlapSep.reserve(nItems));
 	w->hasPlanes = false;
+	w->hasConcave = false;
 	for (size_t i = 0; i < w->collidables.size(); i++)
+	{
 		if (w->collidables[i].shapeType == B3B200_SHAPE_PLANE) w->hasPlanes = true;
+		if (w->collidables[i].shapeType == B3B200_SHAPE_CONCAVE_TRIMESH) w->hasConcave = true;
+	}
+	if (w->hasConcave) B3_TRY(w->dConcavePairs.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
 	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));

@@ -130,3 +130,23 @@ def compound_children(child_collidable, offsets, orientations=None):
 
 
 L_OFFSETS = [(0.0, 0.0, 0.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0)]  # 3-box "L" 
+
+
+def heightfield_mesh(nx, nz, cell=1.0, amplitude=2.0, freq=0.1, x0=None, z0=None):
+    """config 4's synthetic concave ground: an nx x nz quad grid, two triangles per quad,
+    h = amplitude * sin(freq x) * cos(freq z).  Returns (vertices (V,3) f32, triangle indices (T*3,) i32)."""
+    x0 = -0.5 * nx * cell if x0 is None else x0
+    z0 = -0.5 * nz * cell if z0 is None else z0
+    xs = x0 + cell * np.arange(nx + 1, dtype=np.float64)
+    zs = z0 + cell * np.arange(nz + 1, dtype=np.float64)
+    X, Z = np.meshgrid(xs, zs, indexing="ij")
+    Y = amplitude * np.sin(freq * X) * np.cos(freq * Z)
+    verts = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    i, k = np.meshgrid(np.arange(nx), np.arange(nz), indexing="ij")
+    v00 = (i * (nz + 1) + k).reshape(-1)
+    v01 = v00 + 1
+    v10 = v00 + (nz + 1)
+    v11 = v10 + 1
+    # counter-clockwise seen from +y: normals point up
+    tris = np.stack([np.stack([v00, v01, v11], 1), np.stack([v00, v11, v10], 1)], 1).reshape(-1, 3)
+    return verts, tris.astype(np.int32).reshape(-1)

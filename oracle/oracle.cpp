@@ -860,6 +860,278 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 	return nContacts;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Concave trimesh x convex / compound child: the host twins the reference runs when
+// bvhTraversalKernelGPU / findConcaveSeparatingAxisKernelGPU / reduceConcaveContactsOnGPU are off and
+// clipConcaveFacesAndFindContactsCPU is on (b3ConvexHullContact.cpp:3513-3569, 3700-3770, 3850-3885, 3951-4003):
+//   candidates  b3BvhTraversal (shared/b3BvhTraversal.h:11-122) followed by the exact triangle-AABB test at the top of
+//               b3FindConcaveSeparatingAxisKernel (shared/b3FindConcaveSatAxis.h:606-610): the quantized tree only
+//               over-approximates, so the active set is "triangle AABB (mesh-local!) overlaps the body's world AABB"
+//   SAT         b3FindConcaveSeparatingAxisKernel (:551-795): 5-face triangle prism, faces of A, faces of B, all edges
+//   clip        b3FindClippingFaces (:417-505) + clipFacesAndFindContactsKernel (shared/b3ClipFaces.h:66-169)
+//   reduce      b3NewContactReductionKernel (shared/b3NewContactReduction.h:93-173)
+// Contacts come out in (pair, triangle, child) order; the reference's order is its tree's.
+namespace
+{
+bool satOneSided(const Hull& A, const Hull& B, V3 posA, const V3& ornA, V3 posB, const V3& ornB, const V3& deltaC2, V3& sep, float& dmin)
+{
+	// b3FindSeparatingAxis of b3FindConcaveSatAxis.h:59-125: only the face normals of A
+	posA.w = 0.f;
+	posB.w = 0.f;
+	for (int i = 0; i < A.h->numFaces; i++)
+	{
+		V3 n = quatRotate(ornA, ld(A.faces[A.h->faceOffset + i].plane));
+		if (dot(deltaC2, n) < 0) n = mul(n, -1.f);
+		float d;
+		if (!testSepAxis(A, B, posA, ornA, posB, ornB, n, d)) return false;
+		if (d < dmin)
+		{
+			dmin = d;
+			sep = n;
+		}
+	}
+	if (dot(neg(deltaC2), sep) > 0.0f) sep = neg(sep);
+	return true;
+}
+bool satEdgeEdge(const Hull& A, const Hull& B, V3 posA, const V3& ornA, V3 posB, const V3& ornB, const V3& deltaC2, V3& sep, float& dmin)
+{
+	// b3FindSeparatingAxisEdgeEdge (:292-415) with searchAllEdgeEdge = true
+	posA.w = 0.f;
+	posB.w = 0.f;
+	for (int e0 = 0; e0 < A.h->numUniqueEdges; e0++)
+	{
+		V3 edge0World = quatRotate(ornA, ld(A.uniqueEdges[A.h->uniqueEdgesOffset + e0]));
+		for (int e1 = 0; e1 < B.h->numUniqueEdges; e1++)
+		{
+			V3 edge1World = quatRotate(ornB, ld(B.uniqueEdges[B.h->uniqueEdgesOffset + e1]));
+			V3 cr = cross(edge0World, edge1World);
+			if (!almostZero(cr))
+			{
+				cr = normalized(cr);
+				if (dot(deltaC2, cr) < 0) cr = mul(cr, -1.f);
+				float dist;
+				if (!testSepAxis(A, B, posA, ornA, posB, ornB, cr, dist)) return false;
+				if (dist < dmin)
+				{
+					dmin = dist;
+					sep = cr;
+				}
+			}
+		}
+	}
+	if (dot(neg(deltaC2), sep) > 0.0f) sep = neg(sep);
+	return true;
+}
+// clipFaceGlobal (shared/b3ClipFaces.h:21-64): like b3ClipFace but without the numVertsIn < 2 early-out
+int clipFaceGlobal(const V3* in, int numIn, const V3& n, float eq, V3* out)
+{
+	int numOut = 0;
+	if (numIn <= 0) return 0;  // the reference would read pVtxIn[-1]; it never gets here with 0 vertices and a non-empty loop
+	V3 first = in[numIn - 1];
+	float ds = dot(n, first) + eq;
+	for (int ve = 0; ve < numIn; ve++)
+	{
+		V3 end = in[ve];
+		float de = dot(n, end) + eq;
+		if (ds < 0)
+		{
+			if (de < 0)
+				out[numOut++] = end;
+			else
+				out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+		}
+		else if (de < 0)
+		{
+			out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+			out[numOut++] = end;
+		}
+		first = end;
+		ds = de;
+	}
+	return numOut;
+}
+}  // namespace
+
+extern "C" int orc_concave_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_rigid_body* bodies, const b3b200_collidable* collidables,
+									const b3b200_convex_polyhedron* convex, const b3b200_float4* vertices, const b3b200_float4* uniqueEdges,
+									const b3b200_face* faces, const int* indices, const b3b200_child_shape* children, const b3b200_aabb* aabbs,
+									b3b200_contact4* out, int maxContacts, int* numCandidatesOut)
+{
+	const int CAP = 64;  // vertexFaceCapacity (b3ConvexHullContact.cpp:3481)
+	int nContacts = 0, nCand = 0;
+	for (int p = 0; p < nPairs; p++)
+	{
+		int bodyA = pairs[p].x, bodyB = pairs[p].y;
+		int cA = bodies[bodyA].collidableIdx, cB = bodies[bodyB].collidableIdx;
+		if (bodies[bodyA].invMass == 0 && bodies[bodyB].invMass == 0) continue;
+		if (collidables[cA].shapeType != B3B200_SHAPE_CONCAVE_TRIMESH) continue;  // only with the mesh as A (b3BvhTraversal.h:35)
+		int typeB = collidables[cB].shapeType;
+		if (typeB != B3B200_SHAPE_CONVEX_HULL && typeB != B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS) continue;
+		const b3b200_convex_polyhedron& mesh = convex[collidables[cA].shapeIndex];
+		int nChildren = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS ? collidables[cB].numChildShapes : 1;
+		for (int f = 0; f < mesh.numFaces; f++)
+		{
+			const b3b200_face face = faces[mesh.faceOffset + f];
+			b3b200_float4 vA[3];
+			V3 localCenter = mk(0, 0, 0);
+			float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+			for (int i = 0; i < 3; i++)
+			{
+				vA[i] = vertices[mesh.vertexOffset + indices[face.indexOffset + i]];
+				localCenter = add(localCenter, ld(vA[i]));
+				const float c[3] = {vA[i].x, vA[i].y, vA[i].z};
+				for (int k = 0; k < 3; k++)
+				{
+					mn[k] = c[k] < mn[k] ? c[k] : mn[k];
+					mx[k] = c[k] > mx[k] ? c[k] : mx[k];
+				}
+			}
+			const b3b200_aabb& bb = aabbs[bodyB];
+			bool overlap = true;
+			for (int k = 0; k < 3; k++)
+				if (mn[k] > bb.max[k] || mx[k] < bb.min[k]) overlap = false;
+			if (!overlap) continue;
+			for (int ch = 0; ch < nChildren; ch++)
+			{
+				nCand++;
+				// the triangle as a 5-face convex (front, back, three edge planes)
+				b3b200_convex_polyhedron tri;
+				memset(&tri, 0, sizeof(tri));
+				tri.numVertices = 3;
+				tri.numUniqueEdges = 3;
+				tri.numFaces = 5;
+				b3b200_float4 eA[3] = {st(sub(ld(vA[1]), ld(vA[0]))), st(sub(ld(vA[2]), ld(vA[1]))), st(sub(ld(vA[0]), ld(vA[2])))};
+				V3 normal = mk(face.plane.x, face.plane.y, face.plane.z);
+				b3b200_face fA[5];
+				int iA[12] = {0, 1, 2, 2, 1, 0, 0, 0, 0, 0, 0, 0};
+				memset(fA, 0, sizeof(fA));
+				fA[0].plane = st(mk(normal.x, normal.y, normal.z, face.plane.w));
+				fA[0].indexOffset = 0;
+				fA[0].numIndices = 3;
+				fA[1].plane = st(mk(-normal.x, -normal.y, -normal.z, dot(normal, ld(vA[0]))));
+				fA[1].indexOffset = 3;
+				fA[1].numIndices = 3;
+				int cur = 6, prev = 2;
+				for (int i = 0; i < 3; i++)
+				{
+					V3 v0 = ld(vA[i]), v1 = ld(vA[prev]);
+					V3 en = normalized(cross(normal, sub(v1, v0)));
+					fA[2 + i].plane = st(mk(en.x, en.y, en.z, -dot(en, v0)));
+					fA[2 + i].numIndices = 2;
+					fA[2 + i].indexOffset = cur;
+					iA[cur++] = i;
+					iA[cur++] = prev;
+					prev = i;
+				}
+				tri.localCenter = st(mul(localCenter, 1.f / 3.f));
+				Hull A = {&tri, vA, eA, fA, iA};
+				V3 posA = ld(bodies[bodyA].pos), ornA = ld(bodies[bodyA].quat);
+				V3 posB = ld(bodies[bodyB].pos), ornB = ld(bodies[bodyB].quat);
+				posA.w = 0.f;
+				posB.w = 0.f;
+				int shapeIndexB = collidables[cB].shapeIndex;
+				if (typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS)
+				{
+					int child = collidables[cB].shapeIndex + ch;
+					V3 newPos = transformPoint(ld(children[child].childPosition), posB, ornB);
+					ornB = quatMul(ornB, ld(children[child].childOrientation));
+					posB = newPos;
+					shapeIndexB = collidables[children[child].shapeIndex].shapeIndex;
+				}
+				Hull B = hullOf(shapeIndexB, convex, vertices, uniqueEdges, faces, indices);
+				V3 c0 = transformPoint(ld(tri.localCenter), posA, ornA);
+				V3 c1 = transformPoint(ld(B.h->localCenter), posB, ornB);
+				V3 deltaC2 = sub(c0, c1);
+				float dmin = FLT_MAX;
+				V3 sep = mk(1, 2, 3, 4);
+				if (!satOneSided(A, B, posA, ornA, posB, ornB, deltaC2, sep, dmin)) continue;
+				if (!satOneSided(B, A, posB, ornB, posA, ornA, deltaC2, sep, dmin)) continue;
+				if (!satEdgeEdge(A, B, posA, ornA, posB, ornB, deltaC2, sep, dmin)) continue;
+				// b3FindClippingFaces
+				V3 b1[CAP], b2[CAP], a1[CAP];
+				int closestFaceB = -1;
+				float dmax = -FLT_MAX;
+				for (int fb = 0; fb < B.h->numFaces; fb++)
+				{
+					const b3b200_float4& pl = B.faces[B.h->faceOffset + fb].plane;
+					float d = dot(quatRotate(ornB, mk(pl.x, pl.y, pl.z)), sep);
+					if (d > dmax)
+					{
+						dmax = d;
+						closestFaceB = fb;
+					}
+				}
+				int numB = 0;
+				{
+					const b3b200_face& polyB = B.faces[B.h->faceOffset + closestFaceB];
+					for (int e0 = 0; e0 < polyB.numIndices && numB < CAP; e0++)
+						b1[numB++] = transformPoint(ld(B.vertices[B.h->vertexOffset + B.indices[polyB.indexOffset + e0]]), posB, ornB);
+				}
+				int closestFaceA = -1;
+				V3 worldNormalA = mk(0, 0, 0);
+				{
+					float dm = FLT_MAX;
+					for (int fa = 0; fa < 5; fa++)
+					{
+						V3 n = quatRotate(ornA, mk(fA[fa].plane.x, fA[fa].plane.y, fA[fa].plane.z));
+						float d = dot(n, sep);
+						if (d < dm)
+						{
+							dm = d;
+							closestFaceA = fa;
+							worldNormalA = n;
+						}
+					}
+				}
+				int numA = fA[closestFaceA].numIndices;
+				for (int e0 = 0; e0 < numA; e0++) a1[e0] = transformPoint(ld(vA[iA[fA[closestFaceA].indexOffset + e0]]), posA, ornA);
+				// clipFacesAndFindContactsKernel
+				const float minDist = -1e30f, maxDist = 0.02f;
+				V3* pIn = b1;
+				V3* pOut = b2;
+				int numIn = numB;
+				for (int e0 = 0; e0 < numA; e0++)
+				{
+					V3 aw = a1[e0], bw = a1[(e0 + 1) % numA];
+					V3 worldEdge0 = sub(aw, bw);
+					V3 planeNormalWS = neg(cross(worldEdge0, worldNormalA));
+					float planeEqWS = -dot(aw, planeNormalWS);
+					int numOut = clipFaceGlobal(pIn, numIn, planeNormalWS, planeEqWS, pOut);
+					std::swap(pIn, pOut);
+					numIn = numOut;
+				}
+				int numLocal = 0;
+				{
+					float planeEqWS = -dot(worldNormalA, a1[0]);
+					for (int i = 0; i < numIn; i++)
+					{
+						float depth = dot(worldNormalA, pIn[i]) + planeEqWS;
+						if (depth <= minDist) depth = minDist;
+						if (depth <= maxDist) pOut[numLocal++] = mk(pIn[i].x, pIn[i].y, pIn[i].z, depth);
+					}
+				}
+				if (numLocal <= 0) continue;
+				// b3NewContactReductionKernel
+				int idx[4] = {0, 1, 2, 3};
+				int nReduced = reduceContacts(pOut, numLocal, neg(sep), idx);  // b3ExtractManifoldSequentialGlobal == b3ReduceContacts arithmetic
+				if (nContacts >= maxContacts) continue;
+				b3b200_contact4& c = out[nContacts++];
+				memset(&c, 0, sizeof(c));
+				c.frictionCmp = 45874;
+				c.batchIdx = f;  // the reference stores the concave-pair index (tree order); the triangle index is the stable equivalent
+				c.bodyAPtrAndSignBit = bodies[bodyA].invMass == 0 ? -bodyA : bodyA;
+				c.bodyBPtrAndSignBit = bodies[bodyB].invMass == 0 ? -bodyB : bodyB;
+				c.childIndexA = -1;
+				c.childIndexB = -1;
+				for (int k = 0; k < nReduced; k++) c.worldPosB[k] = st(pOut[idx[k]]);
+				c.worldNormalOnB = st(mk(sep.x, sep.y, sep.z, (float)nReduced));
+			}
+		}
+	}
+	if (numCandidatesOut) *numCandidatesOut = nCand;
+	return nContacts;
+}
+
 // Graph colouring = sequential first-fit in descending priority order, priority =
 // (hashContact(bodyA, bodyB, childA, childB) << 32) | (index + 1).  This is the
 // batching rule of the new solver (bullet3_b200/csrc/solver.cu); it plays the role

@@ -25,6 +25,8 @@
 #include "Bullet3Dynamics/shared/b3ContactConstraint4.h"
 #include "../../include/b3b200_types.h"
 
+extern bool bvhTraversalKernelGPU, findConcaveSeparatingAxisKernelGPU, clipConcaveFacesAndFindContactsCPU, reduceConcaveContactsOnGPU;
+
 extern "C" void b3ref_cl_init();
 extern bool gConvertConstraintOnCpu;  // b3Solver.cpp:20
 extern int g_fakeClLaunchIsNoop, g_fakeClLaunches;
@@ -175,6 +177,14 @@ int refcl_np_register_compound(void* h, const b3b200_child_shape* children, int 
 	ch.resize(n);
 	memcpy(&ch[0], children, sizeof(b3GpuChildShape) * (size_t)n);
 	return ((RefNp*)h)->np->registerCompoundShape(&ch);
+}
+// route the concave stages through their host twins (file-scope switches of b3ConvexHullContact.cpp:20-24)
+void refcl_concave_host_twins(int on)
+{
+	bvhTraversalKernelGPU = !on;
+	findConcaveSeparatingAxisKernelGPU = !on;
+	clipConcaveFacesAndFindContactsCPU = on != 0;
+	reduceConcaveContactsOnGPU = !on;
 }
 int refcl_np_register_concave(void* h, const float* verts, int nv, const int* idx, int ni, const float* scaling)
 {

@@ -257,3 +257,31 @@ class RefNarrowphase:
         out = np.zeros(max(max_contacts, 1), capi.contact4_t)
         n = self.L.refcl_np_compute_contacts(self.h, P(bodies), len(bodies), P(pairs), len(pairs), P(aabbs), P(out), int(max_contacts), None)
         return out[:n]
+
+
+def concave_contacts_oracle(pairs, bodies, shapes, aabbs, max_contacts):
+    """trimesh x convex / compound-child contacts (host twins of the concave leg); returns (contacts, num_candidates)"""
+    pairs = _arr(pairs, capi.int4_t)
+    bodies = _arr(bodies, capi.rigid_body_t)
+    aabbs = _arr(aabbs, capi.aabb_t)
+    out = np.zeros(max(max_contacts, 1), capi.contact4_t)
+    ch = shapes.child_shapes if len(shapes.child_shapes) else np.zeros(1, capi.child_shape_t)
+    ncand = C.c_int(0)
+    n = oracle().orc_concave_contacts(P(pairs), len(pairs), P(bodies), P(shapes.collidables), P(shapes.convex), P(shapes.vertices), P(shapes.unique_edges),
+                                      P(shapes.faces), P(shapes.indices), P(ch), P(aabbs), P(out), int(max_contacts), C.byref(ncand))
+    return out[:n], ncand.value
+
+
+def _ref_register_concave(self, vertices, tri_indices, scaling=(1.0, 1.0, 1.0)):
+    v = _arr(vertices, np.float32).reshape(-1, 3)
+    i = _arr(tri_indices, np.int32).reshape(-1)
+    sc = (C.c_float * 4)(*[float(x) for x in scaling], 1.0)
+    return self.L.refcl_np_register_concave(self.h, P(v), len(v), P(i), len(i), sc)
+
+
+def _ref_concave_host_twins(self, on=True):
+    self.L.refcl_concave_host_twins(int(bool(on)))
+
+
+RefNarrowphase.register_concave = _ref_register_concave
+RefNarrowphase.concave_host_twins = _ref_concave_host_twins

@@ -498,3 +498,78 @@ def test_compound_scene_steps_and_rests_on_plane():
     assert np.isfinite(b["pos"]).all()
     assert b["pos"][dyn, 1].min() > -0.3  # nothing fell through the plane
     assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 1.0
+
+
+# ------------------------------------------------------------------ concave trimesh
+def concave_world(seed=0, n=600, nq=24, amplitude=1.5, freq=0.5, drop=0.9, lo=-0.2):
+    rng = np.random.default_rng(seed)
+    cfg = capi.default_config(4096)
+    cfg["maxTriConvexPairCapacity"] = 1 << 18
+    w = capi.World(cfg)
+    verts, tris = scenes.heightfield_mesh(nq, nq, cell=1.0, amplitude=amplitude, freq=freq)
+    mesh = w.register_concave(verts, tris)
+    w.register_instance(0.0, (0, 0, 0), scenes.IDENT, mesh)  # the mesh must be the lower body index (b3BvhTraversal.h:35)
+    box = w.register_convex_points(scenes.box_points(0.5))
+    hull = w.register_convex_points(scenes.random_hull_points(rng, 12, 0.5, 0.8))
+    tet = w.register_convex_points(scenes.tetra_points(0.6))
+    ell = w.register_compound(scenes.compound_children(box, scenes.L_OFFSETS))
+    kinds = [box, hull, tet, ell]
+    half = 0.5 * nq - 1.5
+    for i in range(n):
+        x, z = rng.uniform(-half, half, 2)
+        h = amplitude * np.sin(freq * x) * np.cos(freq * z)
+        w.register_instance(1.0, (x, h + rng.uniform(lo, drop), z), scenes.random_quat(rng), kinds[int(rng.integers(0, 4))])
+    w.upload()
+    t = w.tables()
+    return w, oa.Shapes(t), t["bodies"]
+
+
+def full_sort(c):
+    keys = tuple(c["worldPosB"][:, k, j] for k in range(4) for j in range(4)) + tuple(c["worldNormalOnB"][:, j] for j in range(4))
+    return c[np.lexsort(keys + (c["childB"], c["childA"], np.abs(c["bodyB"]), np.abs(c["bodyA"])))]
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_concave_contacts_match_oracle(seed):
+    w, sh, bodies = concave_world(seed)
+    w.update_aabbs()
+    w.find_pairs()
+    pairs = w.pairs()
+    aabbs = w.aabbs()
+    w.compute_contacts()
+    g = w.contacts()
+    assert w.counters()[4] == 0
+    o_mesh, ncand = oa.concave_contacts_oracle(pairs, bodies, sh, aabbs, 1 << 18)
+    o_rest = oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
+    assert len(o_mesh) > 300 and ncand > len(o_mesh)
+    is_mesh = np.abs(g["bodyA"]) == 0
+    gm, gr = full_sort(g[is_mesh]), full_sort(g[~is_mesh])
+    om, orr = full_sort(o_mesh), full_sort(o_rest)
+    assert len(gm) == len(om) and len(gr) == len(orr)
+    for a, b in ((gm, om), (gr, orr)):
+        for f in ("bodyA", "bodyB", "childA", "childB", "frictionCmp"):
+            assert np.array_equal(a[f], b[f]), f
+        assert np.array_equal(a["worldNormalOnB"].view(np.uint32), b["worldNormalOnB"].view(np.uint32))
+        npts = b["worldNormalOnB"][:, 3].astype(int)
+        for k in range(4):
+            m = npts > k
+            assert np.array_equal(a["worldPosB"][m, k].view(np.uint32), b["worldPosB"][m, k].view(np.uint32)), k
+    types = sh.collidables["shapeType"][bodies["collidableIdx"]]
+    assert (types[np.abs(om["bodyB"])] == capi.SHAPE_COMPOUND).sum() > 20  # compound children against triangles are covered
+
+
+def test_concave_scene_settles_on_the_heightfield():
+    w, sh, bodies = concave_world(5, n=400, drop=4.0, lo=1.0)  # every body starts above the (zero-thickness) surface
+    w.set_solver(capi.SOLVER_PGS, 10)
+    for _ in range(420):
+        w.step(1 / 60)
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all()
+    x, z = b["pos"][dyn, 0], b["pos"][dyn, 2]
+    inside = (np.abs(x) < 11) & (np.abs(z) < 11)
+    ground = 1.5 * np.sin(0.5 * x) * np.cos(0.5 * z)
+    assert inside.sum() > 200
+    above = (b["pos"][dyn, 1][inside] - ground[inside]) > -0.35
+    assert above.mean() > 0.97, above.mean()  # a zero-thickness mesh cannot recover a body squeezed through by the pile; nearly all must rest on it
+    assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)[inside]) < 1.0
