@@ -3,10 +3,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--bodies-side S]
 
-Workload (BASELINE.json metric: "bodies*steps/s and ms/step (256k convex)"): the
-GpuConvexScene-style scene at 64^3 = 262 144 dynamic convex bodies (boxes, tetrahedra,
-seeded random hulls, seeded random orientations) on a static 400-box, batched PGS with
-10 iterations, dt = 1/60.  A "step" is one b3GpuRigidBodyPipeline::stepSimulation.
+Workload (BASELINE.json metric: "bodies*steps/s and ms/step (256k convex)", configs[3]): the
+GpuConvexScene-style scene at 64^3 = 262 144 dynamic bodies (boxes, tetrahedra, seeded random
+8-32-vertex hulls, three-box compounds, seeded random orientations) settled on a concave
+heightfield trimesh (256 x 256 quads), batched PGS with 10 iterations, dt = 1/60.
+A "step" is one b3GpuRigidBodyPipeline::stepSimulation.
 N > 1 (torchrun): every rank steps its own independent copy of the scene (batched
 independent worlds, no data-path collective) -> "scaling": "weak".
 
@@ -108,10 +109,18 @@ def cpu_pipeline_step(oa, lib, prefix, bodies, sh, inertias, iters):
     large = np.nonzero(bodies["invMass"] == 0)[0].astype(np.int32)
     # pair finding: sort-and-sweep port (the reference's host twin is O(N^2) brute force)
     _, pairs = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 16 * len(bodies), fn="sweep_pairs")
+    cap = 24 * len(bodies)
     if prefix == "ref_":
-        contacts, _ = oa.convex_contacts_ref(pairs, bodies, sh, 16 * len(bodies))
+        # convex x convex through the compiled reference header path; compound children and the trimesh through the port
+        hull = sh.collidables["shapeType"][bodies["collidableIdx"]] == 3
+        both = hull[pairs["x"]] & hull[pairs["y"]]
+        c1, _ = oa.convex_contacts_ref(pairs[both], bodies, sh, cap)
+        c2 = oa.contacts_oracle(pairs[~both], bodies, sh, -1e30, 0.02, cap)
     else:
-        contacts, _ = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 16 * len(bodies))
+        c1 = oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.02, cap)
+        c2 = c1[:0]
+    c3, _ = oa.concave_contacts_oracle(pairs, bodies, sh, aabbs, cap)
+    contacts = np.concatenate([c1, c2, c3])
     solved, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, iters)
     return oa.integrate(lib, prefix, solved, DT, 0.99, (0.0, -9.8, 0.0)), len(pairs), len(contacts)
 
@@ -122,8 +131,8 @@ def make_cpu_sample(side, settle_on_gpu):
     import oracle_api as oa
 
     dev = 0 if settle_on_gpu else -1
-    w = capi.World(capi.default_config(side ** 3 + 16), device=dev)
-    scenes.bench_convex_scene(w, *scene_dims(side))
+    w = capi.World(bench_config(capi, side), device=dev)
+    scenes.bench_config4_scene(w, *scene_dims(side))
     t = w.tables()
     bodies = t["bodies"]
     if settle_on_gpu:
@@ -167,8 +176,8 @@ def run_cpu_arm(side, threads, steps, warmup, use_ref, settle_on_gpu):
     el = run(steps)
     value = n * steps * threads / el
     desc = ("%s: %d independent %d-body sample worlds of the bench recipe (one per thread), %d steps each: "
-            "AABBs, sweep pair finding, SAT+clip contacts, coloured PGS %d it., integrate; %d pairs / %d contacts per world" %
-            ("compiled reference (oracle/_ref: b3UpdateAabbs/b3ContactConvexConvexSAT/b3IntegrateTransforms) + oracle-port solver" if use_ref
+            "AABBs, sweep pair finding, SAT+clip contacts (hulls, compound children, trimesh), coloured PGS %d it., integrate; %d pairs / %d contacts per world" %
+            ("compiled reference (oracle/_ref: b3UpdateAabbs/b3ContactConvexConvexSAT/b3IntegrateTransforms) + oracle-port compound/trimesh contacts and solver" if use_ref
              else "oracle port", threads, n, steps, ITERS, stats[0][0], stats[0][1]))
     return value, el / steps * 1e3, desc, ("reference" if use_ref else "port")
 
@@ -209,8 +218,8 @@ def main():
 
     side = a.bodies_side
     stream = torch.cuda.Stream()
-    w = capi.World(capi.default_config(side ** 3 + 16), device=local_rank, stream=stream.cuda_stream)
-    scenes.bench_convex_scene(w, *scene_dims(side))
+    w = capi.World(bench_config(capi, side), device=local_rank, stream=stream.cuda_stream)
+    scenes.bench_config4_scene(w, *scene_dims(side))
     w.upload()
     w.set_solver(capi.SOLVER_PGS, ITERS)
     nbodies = w.num_bodies
@@ -315,6 +324,17 @@ def main():
         dist.destroy_process_group()
 
 
+def bench_config(capi, side):
+    """b3Config for the bench scene: 16 pairs / contacts per body like the reference, child-pair and triangle-pair capacities sized for it"""
+    n = side ** 3 + 16
+    cfg = capi.default_config(n)
+    cfg["compoundPairCapacity"] = max(1 << 20, 24 * n)
+    cfg["maxTriConvexPairCapacity"] = max(1 << 18, 4 * n)
+    cfg["maxConvexVertices"] = 1 << 17  # the 257 x 257 heightfield vertices share the vertex / index tables with the hulls
+    cfg["maxConvexIndices"] = 1 << 20
+    return cfg
+
+
 def scene_dims(side):
     """side^3 bodies laid out as a flat pile of LAYERS layers (64 -> 128 x 16 x 128)"""
     ny = min(LAYERS, side)
@@ -324,9 +344,9 @@ def scene_dims(side):
 
 def workload_config(a, world_size):
     nx, ny, nz = scene_dims(a.bodies_side)
-    return {"workload": "GpuConvexScene-style pile of %d x %d x %d = %d convex bodies (1/3 boxes, 1/3 tetrahedra, 1/3 seeded 8-16-vertex hulls, "
-                        "random orientations) settled on a static 400-box; batched PGS %d iterations; dt 1/60; grid broadphase; compounds and "
-                        "concave mesh of BASELINE config 4 are not in this scene yet" % (nx, ny, nz, nx * ny * nz, ITERS),
+    return {"workload": "BASELINE configs[3] (GpuConvexScene): pile of %d x %d x %d = %d bodies (1/4 boxes, 1/4 tetrahedra, 1/4 seeded 8-32-vertex "
+                        "hulls, 1/4 three-box compounds, random orientations) settled on a concave heightfield trimesh (256 x 256 quads at full "
+                        "size); batched PGS %d iterations; dt 1/60; grid broadphase" % (nx, ny, nz, nx * ny * nz, ITERS),
             "worlds_per_gpu": 1, "parallelism": "independent worlds x%d" % world_size,
             "l2": "per-step working set (pairs+contacts+constraints+bodies) exceeds the 126 MB L2; no explicit flush",
             "settle_steps": SETTLE_STEPS}

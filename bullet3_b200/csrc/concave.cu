@@ -244,6 +244,116 @@ __global__ void __launch_bounds__(256) concaveCullKernel(CcArgs a, int4* __restr
 	}
 }
 
+// stage 1b: exact quick reject, one THREAD per (pair, triangle, child) item.  Tests three members of the reference's
+// own axis list with its own arithmetic -- the triangle normal, the edge plane of the triangle that faces B most, and
+// the face of B that faces the triangle most -- so an item dropped here is one the full SAT would drop too.
+__global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items)
+{
+	int numRaw = (int)a.ctr[CTR_CONCAVE_PAIRS];
+	if (numRaw > a.maxItems) numRaw = a.maxItems;
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * blockDim.x; base < numRaw; base += gridDim.x * blockDim.x)
+	{
+		const int r = base + threadIdx.x;
+		bool keep = false;
+		int4 it = make_int4(0, 0, 0, 0);
+		if (r < numRaw)
+		{
+			it = rawItems[r];
+			const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+			const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+			float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
+			const float4 ornA = a.pose[2 * bodyA + 1];
+			float4 ornB = a.pose[2 * bodyB + 1];
+			posA.w = 0.f;
+			posB.w = 0.f;
+			const b3b200_convex_polyhedron* cvA = &a.convex[__ldg(&a.collidables[cA].shapeIndex)];
+			const b3b200_face* faceA = &a.faces[__ldg(&cvA->faceOffset) + it.y];
+			const float4 plane = __ldg(reinterpret_cast<const float4*>(&faceA->plane));
+			const int idxOffA = __ldg(&faceA->indexOffset), vOffA = __ldg(&cvA->vertexOffset);
+			float4 vA[3];
+#pragma unroll
+			for (int i = 0; i < 3; i++) vA[i] = __ldg(&a.vertices[vOffA + __ldg(&a.indices[idxOffA + i])]);
+			const float4 normal = mk4(plane.x, plane.y, plane.z);
+			int shapeB;
+			if (it.z >= 0)
+			{
+				const b3b200_child_shape* ch = &a.childShapes[it.z];
+				const float4 np = transformPoint(__ldg(reinterpret_cast<const float4*>(&ch->childPosition)), posB, ornB);
+				ornB = quatMul(ornB, __ldg(reinterpret_cast<const float4*>(&ch->childOrientation)));
+				posB = np;
+				shapeB = __ldg(&a.collidables[__ldg(&ch->shapeIndex)].shapeIndex);
+			}
+			else
+				shapeB = __ldg(&a.collidables[cB].shapeIndex);
+			const HullRef hB = loadHull(a.convex, shapeB);
+			float4 localCenter = add3(add3(vA[0], vA[1]), vA[2]);
+			localCenter = scale3(localCenter, 1.f / 3.f);
+			const float4 deltaC2 = sub3(transformPoint(localCenter, posA, ornA), transformPoint(hB.localCenter, posB, ornB));
+			keep = true;
+#pragma unroll 1
+			for (int which = 0; which < 3 && keep; which++)
+			{
+				float4 axis;
+				if (which == 0)
+					axis = quatRotate(ornA, normal);
+				else if (which == 1)
+				{
+					// edge plane i: normalized(cross(normal, v[prev] - v[i])); pick the one pointing at B most
+					const float4 toB = quatRotate(quatInverse(ornA), neg3(deltaC2));
+					float best = -FLT_MAX;
+					float4 bestN = mk4(0, 0, 0);
+					int prev = 2;
+#pragma unroll
+					for (int i = 0; i < 3; i++)
+					{
+						const float4 en = normalized3(cross3(normal, sub3(vA[prev], vA[i])));
+						const float d = dot3(en, toB);
+						if (d > best)
+						{
+							best = d;
+							bestN = en;
+						}
+						prev = i;
+					}
+					axis = quatRotate(ornA, bestN);
+				}
+				else
+				{
+					const float4 toA = quatRotate(quatInverse(ornB), deltaC2);
+					int bf = 0;
+					float best = -FLT_MAX;
+					for (int f = 0; f < hB.numFaces; f++)
+					{
+						const float4 n = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+						const float d = dot3(n, toA);
+						if (d > best)
+						{
+							best = d;
+							bf = f;
+						}
+					}
+					axis = quatRotate(ornB, __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + bf].plane)));
+				}
+				if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+				float minT, maxT, minH, maxH;
+				projectTri(vA, posA, ornA, axis, minT, maxT);
+				projectHull(hB, posB, ornB, axis, a.vertices, minH, maxH);
+				if (maxT < minH || maxH < minT) keep = false;
+			}
+		}
+		const unsigned int m = __ballot_sync(FULL, keep);
+		if (m)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_CONCAVE_SURVIVORS], (unsigned int)__popc(m));
+			slot = __shfl_sync(FULL, slot, 0);
+			slot += __popc(m & ((1u << lane) - 1u));
+			if (keep) items[slot] = it;  // survivors <= raw items <= capacity
+		}
+	}
+}
+
 __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, const int4* __restrict__ items)
 {
 	__shared__ float4 bufAll[CC_WARPS][2][CC_MAX_POLY];
@@ -251,8 +361,7 @@ __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, con
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
-	int numItems = (int)a.ctr[CTR_CONCAVE_PAIRS];
-	if (numItems > a.maxItems) numItems = a.maxItems;
+	const int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
 	const int warpsTotal = gridDim.x * CC_WARPS;
 	for (int s = blockIdx.x * CC_WARPS + warp; s < numItems; s += warpsTotal)
 	{
@@ -591,6 +700,7 @@ int launchConcave(World* w)
 {
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_PAIRS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_SURVIVORS], 0, sizeof(unsigned int), s));
 	CcArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.ctr = w->dCounters.ptr;
@@ -614,7 +724,9 @@ int launchConcave(World* w)
 	B3_LAUNCH_CHECK();
 	clampConcaveKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, a.maxItems);
 	B3_LAUNCH_CHECK();
-	concaveContactKernel<<<w->smCount * 8, CC_THREADS, 0, s>>>(a, w->dConcavePairs.ptr);
+	concaveQuickKernel<<<w->smCount * 4, 256, 0, s>>>(a, w->dConcavePairs.ptr, w->dConcaveSurvivors.ptr);
+	B3_LAUNCH_CHECK();
+	concaveContactKernel<<<w->smCount * 8, CC_THREADS, 0, s>>>(a, w->dConcaveSurvivors.ptr);
 	B3_LAUNCH_CHECK();
 	return 0;
 }

@@ -21,6 +21,7 @@ enum Counter
 	CTR_SURVIVORS = 8,
 	CTR_OVERLAPS = 9,
 	CTR_HALO = 10,
+	CTR_CONCAVE_SURVIVORS = 11,
 	CTR_COUNT = 16
 };
 enum OverflowBits
@@ -149,6 +150,7 @@ struct World
 	DevBuf<unsigned int> dCounters;  // CTR_COUNT
 	DevBuf<b3b200_int4> dCompoundPairs;
 	DevBuf<int4> dConcavePairs;  // (pair, triangle, child shape of B or -1, 0) work items of the concave path
+	DevBuf<int4> dConcaveSurvivors;  // ... that passed the quick reject
 	DevBuf<int4> dSurvivors;     // work items (pair, childA, childB, 0) that passed the quick SAT reject
 	DevBuf<int4> dOverlapPairs;  // work items with a penetrating SAT result
 	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes

@@ -25,6 +25,8 @@ namespace b3b200
 constexpr int NP_THREADS = 128;
 constexpr int NP_WARPS = NP_THREADS / 32;
 constexpr int MAX_POLY = 64;  // b3Config::m_maxVerticesPerFace (b3Config.h:27)
+constexpr int SAT_EDGES = 96;  // world-space edge directions staged per hull (a 32-vertex triangulated hull has 90)
+constexpr int SUP_K = 4;       // support vertices per hull for the tight edge-axis bound
 #define FULL 0xffffffffu
 
 struct HullRef
@@ -232,7 +234,7 @@ B3_D bool resolveSide(const NpArgs& a, int body, int child, Side& s)
 // Part 1: b3FindSeparatingAxis.  Returns false when the hulls are separated; otherwise *sepOut is the
 // minimum-penetration axis (the reference's sepNormalWorldSpace).
 B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 ornA, float4 posB, float4 ornB,
-				  float4* bufA, float4* bufB, int* queue, int lane, float4* sepOut)
+				  float4* bufA, float4* bufB, float4* sup, int* queue, int lane, float4* sepOut)
 {
 	posA.w = 0.f;
 	posB.w = 0.f;
@@ -253,7 +255,7 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 
 	// World-space edge directions are rotated once per hull (the same arithmetic the reference
 	// repeats for every pair of edges) and staged in shared memory.
-	const bool staged = nEA <= MAX_POLY && nEB <= MAX_POLY;
+	const bool staged = nEA <= SAT_EDGES && nEB <= SAT_EDGES;
 	if (staged)
 	{
 		for (int e = lane; e < nEA + nEB; e += 32)
@@ -274,6 +276,53 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 	// cannot separate and cannot become the strict minimum: the reference's result is unchanged.
 	const float rsum = (hA.radius + hB.radius) * (1.0f - 2e-4f);
 	float curMin = FLT_MAX;  // warp-uniform upper bound of the final minimum depth
+
+	// Tighter exact-safe skip for hull pairs with many edge pairs.  The support of a hull along n is at least the
+	// largest projection of ANY subset of its vertices, so with a_k / b_k = SUP_K vertices of A / B (relative to the
+	// hull centres c0 / c1) the overlap along an oriented unit axis n (deltaC2 . n >= 0) obeys
+	//     maxB - minA >= max_k(b_k . n) - min_k(a_k . n) - deltaC2 . n      maxA - minB >= deltaC2 . n + rA + rB
+	// The subset is the SUP_K vertices of each hull that reach furthest towards the other hull, which are the
+	// supports for the axes that matter (those roughly along deltaC2).  An axis whose lower bound exceeds the best
+	// depth so far by more than `supEps` (>> the FP32 error of either evaluation) cannot separate and cannot become
+	// the strict minimum, so the reference's result is unchanged.
+	const bool tight = nEA * nEB >= 64;
+	const float supEps = 1e-3f + 1e-6f * (fabsf(posA.x) + fabsf(posA.y) + fabsf(posA.z) + fabsf(posB.x) + fabsf(posB.y) + fabsf(posB.z));
+	if (tight)
+	{
+#pragma unroll 1
+		for (int side = 0; side < 2; side++)
+		{
+			const HullRef& h = side == 0 ? hA : hB;
+			const float4 orn = side == 0 ? ornA : ornB;
+			const float4 dirL = quatRotate(quatInverse(orn), side == 0 ? neg3(deltaC2) : deltaC2);
+			const int nv = h.numVertices < 64 ? h.numVertices : 64;
+			unsigned long long taken = 0ull;
+			for (int kk = 0; kk < SUP_K; kk++)
+			{
+				float best = -FLT_MAX;
+				int bi = -1;
+				for (int i = lane; i < nv; i += 32)
+				{
+					if ((taken >> i) & 1ull) continue;
+					const float sc = dot3(__ldg(&a.vertices[h.vertexOffset + i]), dirL);
+					if (sc > best)
+					{
+						best = sc;
+						bi = i;
+					}
+				}
+				warpArgMax(best, bi);
+				if (bi < 0) bi = 0;  // fewer than SUP_K vertices: repeat one (still a valid subset)
+				taken |= 1ull << bi;
+				if (lane == 0)
+				{
+					const float4 v = __ldg(&a.vertices[h.vertexOffset + bi]);
+					sup[side * SUP_K + kk] = quatRotate(orn, sub3(v, h.localCenter));
+				}
+			}
+		}
+		__syncwarp();
+	}
 
 	// Candidate axes (index k = position in the reference's sequential order: faces of A, faces
 	// of B, edge pairs) are filtered 32 at a time and compacted into a per-warp queue, so the
@@ -308,6 +357,25 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 					const float dd = dot3(deltaC2, cr);
 					const float len2 = dot3(cr, cr);
 					if (dd * dd < S * S * len2 * 0.999f) cand = false;
+					if (cand && tight)
+					{
+						float mnA = FLT_MAX, mxA = -FLT_MAX, mnB = FLT_MAX, mxB = -FLT_MAX;
+#pragma unroll
+						for (int kk = 0; kk < SUP_K; kk++)
+						{
+							const float pa = dot3(sup[kk], cr), pb = dot3(sup[SUP_K + kk], cr);
+							mnA = fminf(mnA, pa);
+							mxA = fmaxf(mxA, pa);
+							mnB = fminf(mnB, pb);
+							mxB = fmaxf(mxB, pb);
+						}
+						const float m = sqrtf(len2);
+						const float ddAbs = fabsf(dd);
+						// oriented axis = +-cr / m with deltaC2 . axis >= 0
+						const float l1 = (dd < 0.f ? (mxA - mnB) : (mxB - mnA)) - ddAbs;
+						const float l2 = ddAbs + rsum * m;
+						if (fminf(l1, l2) > (curMin + supEps) * m) cand = false;
+					}
 				}
 			}
 			const unsigned int m = __ballot_sync(FULL, cand);
@@ -670,7 +738,45 @@ B3_D void pushItem(const NpArgs& a, int4* __restrict__ items, int p, int ca, int
 	if (slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, ca, cb, 0);
 }
 
-__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items)
+// conservative world-space bounding sphere of one side: centre = hull centre, radius = circumscribed radius about it
+// (stored in the convex entry's unused word at registration, world.cu)
+B3_D float4 boundSphere(const NpArgs& a, const Side& s, float& radius)
+{
+	const b3b200_convex_polyhedron* h = &a.convex[s.shape];
+	radius = __int_as_float(__ldg(&h->unused));
+	return transformPoint(__ldg(reinterpret_cast<const float4*>(&h->localCenter)), s.pos, s.orn);
+}
+
+// stage 1b: the exact quick reject for the raw child items of compound pairs, one THREAD per item
+__global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items)
+{
+	int numRaw = (int)a.ctr[CTR_COMPOUND_PAIRS];
+	if (numRaw > a.maxWorkItems) numRaw = a.maxWorkItems;
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * CULL_THREADS; base < numRaw; base += gridDim.x * CULL_THREADS)
+	{
+		const int r = base + threadIdx.x;
+		bool keep = false;
+		int4 it = make_int4(0, 0, 0, 0);
+		if (r < numRaw)
+		{
+			it = rawItems[r];
+			Side A, B;
+			if (resolveSide(a, a.pairs[it.x].x, it.y, A) && resolveSide(a, a.pairs[it.x].y, it.z, B)) keep = quickTest(a, A, B);
+		}
+		const unsigned int m = __ballot_sync(FULL, keep);
+		if (m)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(m));
+			slot = __shfl_sync(FULL, slot, 0);
+			slot += __popc(m & ((1u << lane) - 1u));
+			if (keep && slot < (unsigned int)a.maxWorkItems) items[slot] = it;
+		}
+	}
+}
+
+__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
 	const int lane = threadIdx.x & 31;
@@ -699,17 +805,27 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 						const bool compA = typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS, compB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
 						const int firstA = compA ? __ldg(&a.collidables[cA].shapeIndex) : -1, nA = compA ? __ldg(&a.collidables[cA].numChildShapes) : 1;
 						const int firstB = compB ? __ldg(&a.collidables[cB].shapeIndex) : -1, nB = compB ? __ldg(&a.collidables[cB].numChildShapes) : 1;
+						// child pairs whose bounding spheres (about the hulls' AABB centres mC, radius |mE|) touch go to the
+						// raw child-item queue; npChildCullKernel runs the exact quick reject on them, one thread each
 						for (int i = 0; i < nA; i++)
 						{
 							Side A;
 							const int ca = compA ? firstA + i : -1;
 							if (!resolveSide(a, bodyA, ca, A)) continue;
+							float rA;
+							const float4 sA = boundSphere(a, A, rA);
 							for (int j = 0; j < nB; j++)
 							{
 								Side B;
 								const int cb = compB ? firstB + j : -1;
 								if (!resolveSide(a, bodyB, cb, B)) continue;
-								if (quickTest(a, A, B)) pushItem(a, items, p, ca, cb);
+								float rB;
+								const float4 sB = boundSphere(a, B, rB);
+								const float4 d = sub3(sA, sB);
+								const float rr = (rA + rB) * 1.001f + 1e-3f;
+								if (dot3(d, d) > rr * rr) continue;
+								const unsigned int slot = atomicAdd(&a.ctr[CTR_COMPOUND_PAIRS], 1u);
+								if (slot < (unsigned int)a.maxWorkItems) rawItems[slot] = make_int4(p, ca, cb, 0);
 							}
 						}
 					}
@@ -734,12 +850,14 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4* __restrict__ items, int4* __restrict__ overlapItems,
 															   float4* __restrict__ overlapSep)
 {
-	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
+	__shared__ float4 bufAll[NP_WARPS][2][SAT_EDGES];
+	__shared__ float4 supAll[NP_WARPS][2 * SUP_K];
 	__shared__ int queueAll[NP_WARPS][64];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
+	float4* sup = supAll[warp];
 	int* queue = queueAll[warp];
 	int numItems = (int)a.ctr[CTR_SURVIVORS];
 	if (numItems > a.maxWorkItems) numItems = a.maxWorkItems;
@@ -752,7 +870,7 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4*
 		if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
 		{
 			float4 sep;
-			const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, queue, lane, &sep);
+			const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, sup, queue, lane, &sep);
 			if (hit && lane == 0)
 			{
 				const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
@@ -972,13 +1090,15 @@ __global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
 	}
 }
 
-__global__ void clampContactsKernel(unsigned int* ctr, int maxContacts)
+__global__ void clampContactsKernel(unsigned int* ctr, int maxContacts, int maxWorkItems)
 {
 	if (ctr[CTR_CONTACTS] > (unsigned int)maxContacts)
 	{
 		ctr[CTR_CONTACTS] = (unsigned int)maxContacts;
 		ctr[CTR_OVERFLOW] |= OVF_CONTACTS;
 	}
+	// work items (child pairs of compounds + surviving pairs) beyond the queue capacity were dropped: say so
+	if (ctr[CTR_COMPOUND_PAIRS] > (unsigned int)maxWorkItems || ctr[CTR_SURVIVORS] > (unsigned int)maxWorkItems) ctr[CTR_OVERFLOW] |= OVF_COMPOUND;
 }
 
 int launchNarrowphase(World* w)
@@ -986,6 +1106,7 @@ int launchNarrowphase(World* w)
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.pairsOut = w->bp.pairs.ptr;
@@ -1009,14 +1130,20 @@ int launchNarrowphase(World* w)
 		npPrimitiveKernel<<<w->smCount * 8, 128, 0, s>>>(a);
 		B3_LAUNCH_CHECK();
 	}
-	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr);
+	// the overlap list is not live yet: it doubles as the raw child-item queue of compound pairs
+	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr);
 	B3_LAUNCH_CHECK();
+	if (!w->childShapes.empty())
+	{
+		npChildCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dSurvivors.ptr);
+		B3_LAUNCH_CHECK();
+	}
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	if (w->hasConcave) B3_TRY(launchConcave(w));
-	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity);
+	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity, a.maxWorkItems);
 	B3_LAUNCH_CHECK();
 	return 0;
 }

@@ -170,6 +170,16 @@ static int registerConvexInternal(World* w, const b3b200_float4* verts, int nV, 
 		}
 		if (rin > 1e299 || rin < 0) rin = 0;
 		c.radius = (float)(rin * (1.0 - 1e-5));
+		// m_unused (b3ConvexPolyhedronData.h:33) carries the bits of the circumscribed radius about localCenter, rounded
+		// up: the conservative bounding sphere the child-pair cull of compounds uses (narrowphase.cu)
+		double rout = 0.0;
+		for (int i = 0; i < nV; i++)
+		{
+			const double dx = (double)verts[i].x - c.localCenter.x, dy = (double)verts[i].y - c.localCenter.y, dz = (double)verts[i].z - c.localCenter.z;
+			rout = std::max(rout, sqrt(dx * dx + dy * dy + dz * dz));
+		}
+		const float routF = (float)(rout * (1.0 + 1e-5)) + 1e-6f;
+		memcpy(&c.unused, &routF, sizeof(float));
 	}
 	c.numVertices = nV;
 	c.vertexOffset = (int)w->vertices.size();
@@ -566,7 +576,11 @@ extern "C" int b3b200_upload(b3b200_world* w)
 		if (w->collidables[i].shapeType == B3B200_SHAPE_PLANE) w->hasPlanes = true;
 		if (w->collidables[i].shapeType == B3B200_SHAPE_CONCAVE_TRIMESH) w->hasConcave = true;
 	}
-	if (w->hasConcave) B3_TRY(w->dConcavePairs.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
+	if (w->hasConcave)
+	{
+		B3_TRY(w->dConcavePairs.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
+		B3_TRY(w->dConcaveSurvivors.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
+	}
 	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
 	B3_TRY(w->dContactColour.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));

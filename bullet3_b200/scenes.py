@@ -150,3 +150,41 @@ def heightfield_mesh(nx, nz, cell=1.0, amplitude=2.0, freq=0.1, x0=None, z0=None
     # counter-clockwise seen from +y: normals point up
     tris = np.stack([np.stack([v00, v01, v11], 1), np.stack([v00, v11, v10], 1)], 1).reshape(-1, 3)
     return verts, tris.astype(np.int32).reshape(-1)
+
+
+def bench_config4_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, hull_verts=(8, 32), spacing=(2.2, 2.0, 2.2), mesh_quads=None):
+    """BASELINE.json config 4: a pile of nx*ny*nz bodies -- 1/4 boxes, 1/4 tetrahedra, 1/4 seeded random hulls
+    (`hull_verts` vertices on a sphere), 1/4 three-box "L" compounds -- with seeded random orientations on the config-3
+    lattice, dropped on a synthetic concave heightfield trimesh h = 2 sin(0.1 x) cos(0.1 z) that extends 10 % beyond the
+    pile (256 x 256 quads = 131 072 triangles at bench size).  Body 0 is the mesh (it has to be the lower body index of
+    its pairs, b3BvhTraversal.h:35).  Returns the list of collidables."""
+    rng = np.random.default_rng(seed)
+    wx, wz = spacing[0] * nx, spacing[2] * nz
+    if mesh_quads is None:
+        mesh_quads = int(min(256, max(8, 2 * max(nx, nz))))
+    cell = 1.2 * max(wx, wz) / mesh_quads
+    verts, tris = heightfield_mesh(mesh_quads, mesh_quads, cell=cell, amplitude=2.0, freq=0.1, x0=0.5 * wx - 0.5 * mesh_quads * cell,
+                                   z0=0.5 * wz - 0.5 * mesh_quads * cell)
+    mesh = world.register_concave(verts, tris)
+    world.register_instance(0.0, (0.0, 0.0, 0.0), IDENT, mesh)
+    box = world.register_convex_points(box_points(0.8))
+    tet = world.register_convex_points(tetra_points(0.9))
+    hulls = []
+    for _ in range(num_hull_shapes):
+        n = int(rng.integers(hull_verts[0], hull_verts[1] + 1))
+        hulls.append(world.register_convex_points(random_hull_points(rng, n, 0.8, 1.1)))
+    small_box = world.register_convex_points(box_points(0.4))
+    ell = world.register_compound(compound_children(small_box, [(-0.4, -0.4, 0.0), (0.4, -0.4, 0.0), (-0.4, 0.4, 0.0)]))
+    n = nx * ny * nz
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.zeros((n, 4), np.float32)
+    pos[:, 0] = (((j + 1) & 1) * 0.5 + spacing[0] * i).reshape(-1)
+    pos[:, 1] = (3.4 + spacing[1] * j).reshape(-1)
+    pos[:, 2] = (((j + 1) & 1) * 0.5 + spacing[2] * k).reshape(-1)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    kind = rng.integers(0, 4, n)
+    hull = np.asarray(hulls, np.int32)[rng.integers(0, num_hull_shapes, n)]
+    col = np.where(kind == 0, box, np.where(kind == 1, tet, np.where(kind == 2, hull, ell))).astype(np.int32)
+    world.register_instances(np.ones(n, np.float32), pos, q.astype(np.float32), col)
+    return [mesh, box, tet] + hulls + [small_box, ell]
