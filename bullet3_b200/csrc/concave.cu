@@ -362,7 +362,9 @@ __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, con
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
 	const int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
+	// static striding: a dynamic cursor (as in satKernel) measured 2.7x slower here
 	const int warpsTotal = gridDim.x * CC_WARPS;
+	{
 	for (int s = blockIdx.x * CC_WARPS + warp; s < numItems; s += warpsTotal)
 	{
 		__syncwarp();
@@ -683,6 +685,7 @@ __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, con
 		}
 		else if (lane == 6)
 			reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);  // child indices are not recorded on this path (:143-144)
+	}
 	}
 }
 

@@ -22,6 +22,9 @@ enum Counter
 	CTR_OVERLAPS = 9,
 	CTR_HALO = 10,
 	CTR_CONCAVE_SURVIVORS = 11,
+	CTR_CURSOR_SAT = 12,  // dynamic work distribution cursors of the warp-per-item kernels (12..14 are cleared together)
+	CTR_CURSOR_CLIP = 13,
+	CTR_CURSOR_CONCAVE = 14,
 	CTR_COUNT = 16
 };
 enum OverflowBits

@@ -27,6 +27,7 @@ constexpr int NP_WARPS = NP_THREADS / 32;
 constexpr int MAX_POLY = 64;  // b3Config::m_maxVerticesPerFace (b3Config.h:27)
 constexpr int SAT_EDGES = 96;  // world-space edge directions staged per hull (a 32-vertex triangulated hull has 90)
 constexpr int SUP_K = 4;       // support vertices per hull for the tight edge-axis bound
+constexpr int WORK_CHUNK = 4;  // items a warp claims per atomic in the warp-per-item kernels
 #define FULL 0xffffffffu
 
 struct HullRef
@@ -249,6 +250,7 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 	const int nFA = hA.numFaces, nFB = hB.numFaces, nEA = hA.numUniqueEdges, nEB = hB.numUniqueEdges;
 	const int nF = nFA + nFB;
 	const int total = nF + nEA * nEB;
+	const float invNEB = 1.0f / (float)(nEB > 0 ? nEB : 1);
 	float bestD = FLT_MAX;
 	int bestK = -1;
 	float4 bestAxis = mk4(0, 0, 0);
@@ -285,7 +287,7 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 	// supports for the axes that matter (those roughly along deltaC2).  An axis whose lower bound exceeds the best
 	// depth so far by more than `supEps` (>> the FP32 error of either evaluation) cannot separate and cannot become
 	// the strict minimum, so the reference's result is unchanged.
-	const bool tight = nEA * nEB >= 64;
+	const bool tight = nEA * nEB >= 128;
 	const float supEps = 1e-3f + 1e-6f * (fabsf(posA.x) + fabsf(posA.y) + fabsf(posA.z) + fabsf(posB.x) + fabsf(posB.y) + fabsf(posB.z));
 	if (tight)
 	{
@@ -346,7 +348,7 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 			else if (k < total)
 			{
 				const int e = k - nF;
-				const int e0 = e / nEB, e1 = e - e0 * nEB;
+				const int e0 = __float2int_rz(((float)e + 0.5f) * invNEB), e1 = e - e0 * nEB;  // == e / nEB (exact for these ranges), without the integer division
 				const float4 edge0 = staged ? bufA[e0] : quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
 				const float4 edge1 = staged ? bufB[e1] : quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
 				const float4 cr = cross3(edge0, edge1);
@@ -402,7 +404,7 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 			else
 			{
 				const int e = k - nF;
-				const int e0 = e / nEB, e1 = e - e0 * nEB;
+				const int e0 = __float2int_rz(((float)e + 0.5f) * invNEB), e1 = e - e0 * nEB;
 				const float4 edge0 = staged ? bufA[e0] : quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
 				const float4 edge1 = staged ? bufB[e1] : quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
 				axis = normalized3(cross3(edge0, edge1));
@@ -861,24 +863,33 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4*
 	int* queue = queueAll[warp];
 	int numItems = (int)a.ctr[CTR_SURVIVORS];
 	if (numItems > a.maxWorkItems) numItems = a.maxWorkItems;
-	const int warpsTotal = gridDim.x * NP_WARPS;
-	for (int s = blockIdx.x * NP_WARPS + warp; s < numItems; s += warpsTotal)
+	// Item cost varies by three orders of magnitude (box x box: 15 axes, two 32-vertex hulls: ~3000), so warps claim
+	// items dynamically, WORK_CHUNK at a time, instead of striding.
+	for (;;)
 	{
-		const int4 it = items[s];
-		const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
-		Side A, B;
-		if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
+		int base = 0;
+		if (lane == 0) base = (int)atomicAdd(&a.ctr[CTR_CURSOR_SAT], (unsigned int)WORK_CHUNK);
+		base = __shfl_sync(FULL, base, 0);
+		if (base >= numItems) break;
+		const int end = base + WORK_CHUNK < numItems ? base + WORK_CHUNK : numItems;
+		for (int s = base; s < end; s++)
 		{
-			float4 sep;
-			const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, sup, queue, lane, &sep);
-			if (hit && lane == 0)
+			const int4 it = items[s];
+			const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+			Side A, B;
+			if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
 			{
-				const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
-				overlapItems[slot] = it;
-				overlapSep[slot] = sep;
+				float4 sep;
+				const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, sup, queue, lane, &sep);
+				if (hit && lane == 0)
+				{
+					const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
+					overlapItems[slot] = it;
+					overlapSep[slot] = sep;
+				}
 			}
+			__syncwarp();
 		}
-		__syncwarp();
 	}
 }
 
@@ -891,16 +902,23 @@ __global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int4* _
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
 	const int numOverlaps = (int)a.ctr[CTR_OVERLAPS];
-	const int warpsTotal = gridDim.x * NP_WARPS;
-	for (int s = blockIdx.x * NP_WARPS + warp; s < numOverlaps; s += warpsTotal)
+	for (;;)
 	{
-		const int4 it = overlapItems[s];
-		const float4 sep = overlapSep[s];
-		const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
-		Side A, B;
-		if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
-			clipWarp(a, it.x, bodyA, bodyB, A.shape, B.shape, it.y, it.z, A.pos, A.orn, B.pos, B.orn, A.invMass, B.invMass, mk4(sep.x, sep.y, sep.z), bufA, bufB, lane);
-		__syncwarp();
+		int base = 0;
+		if (lane == 0) base = (int)atomicAdd(&a.ctr[CTR_CURSOR_CLIP], (unsigned int)WORK_CHUNK);
+		base = __shfl_sync(FULL, base, 0);
+		if (base >= numOverlaps) break;
+		const int end = base + WORK_CHUNK < numOverlaps ? base + WORK_CHUNK : numOverlaps;
+		for (int s = base; s < end; s++)
+		{
+			const int4 it = overlapItems[s];
+			const float4 sep = overlapSep[s];
+			const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+			Side A, B;
+			if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
+				clipWarp(a, it.x, bodyA, bodyB, A.shape, B.shape, it.y, it.z, A.pos, A.orn, B.pos, B.orn, A.invMass, B.invMass, mk4(sep.x, sep.y, sep.z), bufA, bufB, lane);
+			__syncwarp();
+		}
 	}
 }
 
@@ -1107,6 +1125,7 @@ int launchNarrowphase(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 3 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.pairsOut = w->bp.pairs.ptr;
