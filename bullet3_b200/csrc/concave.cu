@@ -111,8 +111,8 @@ B3_D void projectHull(const HullRef& hull, const float4& pos, const float4& orn,
 	for (int i = 0; i < hull.numVertices; i++)
 	{
 		const float dp = dot3(__ldg(&v[i]), localDir);
-		if (dp < mn) mn = dp;
-		if (dp > mx) mx = dp;
+		mn = fminf(mn, dp);  // == "if (dp < mn) mn = dp" up to the sign of a zero, which nothing downstream observes
+		mx = fmaxf(mx, dp);
 	}
 	if (mn > mx)
 	{
@@ -134,8 +134,8 @@ B3_D void projectTri(const float4 (&vA)[3], const float4& pos, const float4& orn
 	for (int i = 0; i < 3; i++)
 	{
 		const float dp = dot3(vA[i], localDir);
-		if (dp < mn) mn = dp;
-		if (dp > mx) mx = dp;
+		mn = fminf(mn, dp);
+		mx = fmaxf(mx, dp);
 	}
 	mn += offset;
 	mx += offset;

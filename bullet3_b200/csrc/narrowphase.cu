@@ -26,7 +26,7 @@ constexpr int NP_THREADS = 128;
 constexpr int NP_WARPS = NP_THREADS / 32;
 constexpr int MAX_POLY = 64;  // b3Config::m_maxVerticesPerFace (b3Config.h:27)
 constexpr int SAT_EDGES = 96;  // world-space edge directions staged per hull (a 32-vertex triangulated hull has 90)
-constexpr int SUP_K = 4;       // support vertices per hull for the tight edge-axis bound
+constexpr int SUP_K = 2;      // support vertices per hull for the tight edge-axis bound
 constexpr int WORK_CHUNK = 4;  // items a warp claims per atomic in the warp-per-item kernels
 #define FULL 0xffffffffu
 
@@ -65,8 +65,10 @@ B3_D void projectAxis(const HullRef& hull, const float4& pos, const float4& orn,
 	for (int i = 0; i < hull.numVertices; i++)
 	{
 		float dp = dot3(__ldg(&v[i]), localDir);
-		if (dp < mn) mn = dp;
-		if (dp > mx) mx = dp;
+		// "if (dp < mn) mn = dp" as one FMNMX: same value (only the sign of a zero can differ, which no later
+		// operation on mn / mx observes)
+		mn = fminf(mn, dp);
+		mx = fmaxf(mx, dp);
 	}
 	if (mn > mx)
 	{

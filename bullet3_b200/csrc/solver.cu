@@ -33,6 +33,8 @@
 namespace b3b200
 {
 constexpr int SOLVER_THREADS = 512;
+constexpr int TAIL_ROWS = SOLVER_THREADS;  // batches up to one row per thread are cheaper to solve in one CTA (measured 1.7 us
+                                           // per phase) than to pay a grid barrier for (3.5 us); two rows per thread cost 5.5 us
 constexpr int MAX_ROUNDS = 1024;
 
 // ---------------------------------------------------------------- grid barrier
@@ -52,6 +54,32 @@ struct GridBarrier
 		counter = c;
 		numBlocks = nb;
 		target = 0;
+	}
+	// split form: arrive() publishes this CTA's writes and signals, wait() blocks until every CTA has arrived;
+	// independent loads may be issued in between
+	unsigned int seen;
+	B3_D void arrive()
+	{
+		target += numBlocks;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			unsigned int old;
+			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+			seen = old + 1;
+		}
+	}
+	B3_D void wait()
+	{
+		if (threadIdx.x == 0)
+		{
+			unsigned int v = seen;
+			while ((int)(v - target) < 0)
+			{
+				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+			}
+		}
+		__syncthreads();
 	}
 	B3_D void sync()
 	{
@@ -567,34 +595,284 @@ B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ 
 	}
 }
 
+// Everything a row needs that no other thread writes during the solve: the row itself (its lambdas are only ever
+// written by the thread that owns the row: the row -> thread mapping is the same in every iteration and phase), the
+// two body positions / inverse masses and inverse inertias.  It is loaded BEFORE the grid barrier of the previous
+// batch is waited for, so that after the barrier only the velocity loads are on the critical path.
+struct RowData
+{
+	float4 lin, wp0, wp1, wp2, wp3, center, jac, bias, applied, fr;
+	float4 posA, posB;
+	float4 ia0, ia1, ia2, ib0, ib1, ib2;
+	int aIdx, bIdx;
+};
+
+template <int PHASE>
+B3_D void loadRow(const IterArgs& s, const b3b200_constraint4* __restrict__ cs, RowData& r)
+{
+	const float4* cw = reinterpret_cast<const float4*>(cs);
+	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
+	r.aIdx = tail.x;
+	r.bIdx = tail.y;
+	r.lin = cw[0];
+	r.applied = cw[8];
+	if (PHASE == 0)
+	{
+		r.wp0 = cw[1];
+		r.wp1 = cw[2];
+		r.wp2 = cw[3];
+		r.wp3 = cw[4];
+		r.jac = cw[6];
+		r.bias = cw[7];
+	}
+	else
+	{
+		r.center = cw[5];
+		r.fr = cw[9];
+	}
+	if (r.aIdx < 0) return;  // padding slot
+	r.posA = s.pose[2 * r.aIdx];
+	r.posB = s.pose[2 * r.bIdx];
+	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[r.aIdx].invInertiaWorld);
+	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[r.bIdx].invInertiaWorld);
+	r.ia0 = __ldg(IA);
+	r.ia1 = __ldg(IA + 1);
+	r.ia2 = __ldg(IA + 2);
+	r.ib0 = __ldg(IB);
+	r.ib1 = __ldg(IB + 1);
+	r.ib2 = __ldg(IB + 2);
+}
+
+// solveContact<false> (b3Solver.cpp:187-266) on preloaded row data; same operation order as solveNormalRows
+B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
+{
+	const int aIdx = r.aIdx, bIdx = r.bIdx;
+	if (aIdx < 0) return;
+	const float invMassA = r.posA.w, invMassB = r.posB.w;
+	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
+	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
+	const float4 n = mk4(r.lin.x, r.lin.y, r.lin.z);
+	const float4 nn = neg3(n);
+	const float jacv[4] = {r.jac.x, r.jac.y, r.jac.z, r.jac.w};
+	const float bv[4] = {r.bias.x, r.bias.y, r.bias.z, r.bias.w};
+	float ap[4] = {r.applied.x, r.applied.y, r.applied.z, r.applied.w};
+#pragma unroll
+	for (int ic = 0; ic < 4; ic++)
+	{
+		if (jacv[ic] == 0.f) continue;
+		const float4 wp = ic == 0 ? r.wp0 : (ic == 1 ? r.wp1 : (ic == 2 ? r.wp2 : r.wp3));
+		float4 r0 = sub3(wp, r.posA), r1 = sub3(wp, r.posB);
+		float4 angular0 = cross3(r0, n);
+		float4 angular1 = neg3(cross3(r1, n));
+		float rambdaDt = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
+		rambdaDt *= jacv[ic];
+		{
+			float prevSum = ap[ic];
+			float updated = prevSum;
+			updated += rambdaDt;
+			updated = fmaxf(updated, 0.f);
+			updated = fminf(updated, FLT_MAX);
+			rambdaDt = updated - prevSum;
+			ap[ic] = updated;
+		}
+		float4 linImp0 = scale3(scale3(n, invMassA), rambdaDt);
+		float4 linImp1 = scale3(scale3(nn, invMassB), rambdaDt);
+		float4 angImp0 = scale3(matRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
+		float4 angImp1 = scale3(matRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
+		linVelA = add3(linVelA, linImp0);
+		angVelA = add3(angVelA, angImp0);
+		linVelB = add3(linVelB, linImp1);
+		angVelB = add3(angVelB, angImp1);
+	}
+	reinterpret_cast<float4*>(cs)[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
+	if (invMassA != 0.f)
+	{
+		__stcg(&s.vel[2 * aIdx], linVelA);
+		__stcg(&s.vel[2 * aIdx + 1], angVelA);
+	}
+	if (invMassB != 0.f)
+	{
+		__stcg(&s.vel[2 * bIdx], linVelB);
+		__stcg(&s.vel[2 * bIdx + 1], angVelB);
+	}
+}
+
+// solveFriction (b3Solver.cpp:268-329) on preloaded row data; same operation order as solveFrictionRows
+B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
+{
+	const float4 fr = r.fr;
+	if (fr.x == 0.f && fr.x == 0.f) return;
+	const int aIdx = r.aIdx, bIdx = r.bIdx;
+	const float4 posA = r.posA, posB = r.posB;
+	const float invMassA = posA.w, invMassB = posB.w;
+	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
+	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
+	float sum = 0.f;
+	sum += r.applied.x;
+	sum += r.applied.y;
+	sum += r.applied.z;
+	sum += r.applied.w;
+	const float frictionCoeff = 0.7f;
+	const float maxR = frictionCoeff * sum;
+	const float minR = -maxR;
+	const float4 n = neg3(mk4(r.lin.x, r.lin.y, r.lin.z));
+	float4 tangent[2];
+	planeSpace1(n, tangent[0], tangent[1]);
+	const float4 r0 = sub3(r.center, posA), r1 = sub3(r.center, posB);
+	float fj[2] = {fr.x, fr.y};
+	float fa[2] = {fr.z, fr.w};
+#pragma unroll
+	for (int i = 0; i < 2; i++)
+	{
+		const float4 t = tangent[i];
+		const float4 angular0 = cross3(r0, t);
+		const float4 angular1 = neg3(cross3(r1, t));
+		float rambdaDt = calcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+		rambdaDt *= fj[i];
+		{
+			float prevSum = fa[i];
+			float updated = prevSum;
+			updated += rambdaDt;
+			updated = fmaxf(updated, minR);
+			updated = fminf(updated, maxR);
+			rambdaDt = updated - prevSum;
+			fa[i] = updated;
+		}
+		float4 linImp0 = scale3(scale3(t, invMassA), rambdaDt);
+		float4 linImp1 = scale3(scale3(neg3(t), invMassB), rambdaDt);
+		float4 angImp0 = scale3(matRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
+		float4 angImp1 = scale3(matRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
+		linVelA = add3(linVelA, linImp0);
+		angVelA = add3(angVelA, angImp0);
+		linVelB = add3(linVelB, linImp1);
+		angVelB = add3(angVelB, angImp1);
+	}
+	{
+		// angular damping for point constraint (b3Solver.cpp:317-328)
+		float4 ab = normalized3(sub3(posB, posA));
+		float4 ac = normalized3(sub3(r.center, posA));
+		if (dot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
+		{
+			float angNA = dot3(n, angVelA);
+			float angNB = dot3(n, angVelB);
+			angVelA = sub3(angVelA, scale3(n, angNA * 0.1f));
+			angVelB = sub3(angVelB, scale3(n, angNB * 0.1f));
+		}
+	}
+	reinterpret_cast<float4*>(cs)[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
+	if (invMassA != 0.f)
+	{
+		__stcg(&s.vel[2 * aIdx], linVelA);
+		__stcg(&s.vel[2 * aIdx + 1], angVelA);
+	}
+	if (invMassB != 0.f)
+	{
+		__stcg(&s.vel[2 * bIdx], linVelB);
+		__stcg(&s.vel[2 * bIdx + 1], angVelB);
+	}
+}
+
+template <int PHASE>
+B3_D void iteratePhase(const IterArgs& s, GridBarrier& bar, int numBatches, int tailStart, int stride, int firstOffset)
+{
+	RowData pre;
+	bool havePre = false;
+	if (tailStart > 0)
+	{
+		const int i0 = (int)s.batchOffset[0] + firstOffset;
+		if (i0 < (int)s.batchOffset[1])
+		{
+			loadRow<PHASE>(s, &s.constraints[i0], pre);
+			havePre = true;
+		}
+	}
+	for (int iter = 0; iter < s.iterations; iter++)
+	{
+		for (int b = 0; b < tailStart; b++)
+		{
+			// warp-rows are dealt round-robin to the CTAs so that a small batch still uses every SM
+			const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
+			for (int i = begin + firstOffset; i < end; i += stride)
+			{
+				if (!havePre) loadRow<PHASE>(s, &s.constraints[i], pre);
+				havePre = false;
+				if (PHASE == 0)
+					solveNormalPre(s, &s.constraints[i], pre);
+				else
+					solveFrictionPre(s, &s.constraints[i], pre);
+			}
+			bar.arrive();
+			// while the other CTAs arrive: fetch this thread's first row of the next grid-wide batch
+			{
+				int nb = b + 1;
+				bool more = true;
+				if (nb == tailStart)
+				{
+					nb = 0;
+					more = tailStart == numBatches && iter + 1 < s.iterations;  // with a tail, batch 0 is prefetched after it
+				}
+				if (more)
+				{
+					const int i2 = (int)s.batchOffset[nb] + firstOffset;
+					if (i2 < (int)s.batchOffset[nb + 1])
+					{
+						loadRow<PHASE>(s, &s.constraints[i2], pre);
+						havePre = true;
+					}
+				}
+			}
+			bar.wait();
+		}
+		if (tailStart < numBatches)
+		{
+			// The colouring leaves a long tail of small batches (a few hundred rows each).  A grid barrier costs more
+			// than solving one of them, so CTA 0 runs the whole tail alone, batch after batch in the same order,
+			// separated by __syncthreads(); everybody meets at ONE grid barrier afterwards.
+			if (blockIdx.x == 0)
+			{
+				for (int b = tailStart; b < numBatches; b++)
+				{
+					const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
+					for (int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x)
+					{
+						RowData r;
+						loadRow<PHASE>(s, &s.constraints[i], r);
+						if (PHASE == 0)
+							solveNormalPre(s, &s.constraints[i], r);
+						else
+							solveFrictionPre(s, &s.constraints[i], r);
+					}
+					__syncthreads();
+				}
+			}
+			bar.arrive();
+			if (tailStart > 0 && iter + 1 < s.iterations)
+			{
+				const int i2 = (int)s.batchOffset[0] + firstOffset;
+				if (i2 < (int)s.batchOffset[1])
+				{
+					loadRow<PHASE>(s, &s.constraints[i2], pre);
+					havePre = true;
+				}
+			}
+			bar.wait();
+		}
+	}
+}
+
 __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s)
 {
 	GridBarrier bar;
 	bar.init(s.bar, gridDim.x);
-	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int numBatches = (int)s.ctr[CTR_BATCHES];
 	if (numBatches == 0) return;
-	for (int phase = 0; phase < 2; phase++)
-	{
-		for (int iter = 0; iter < s.iterations; iter++)
-		{
-			for (int b = 0; b < numBatches; b++)
-			{
-				// warp-rows are dealt round-robin to the CTAs so that a small batch still uses every SM
-				const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
-				const int warpInBlock = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
-				for (int i = begin + ((warpInBlock * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31); i < end; i += stride)
-				{
-					if (phase == 0)
-						solveNormalRows(s, &s.constraints[i]);
-					else
-						solveFrictionRows(s, &s.constraints[i]);
-				}
-				bar.sync();
-			}
-		}
-	}
+	const int firstOffset = (((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31);
+	// tail = the trailing run of batches with at most TAIL_ROWS rows each (solved by CTA 0 alone, see iteratePhase)
+	int tailStart = numBatches;
+	while (tailStart > 0 && (int)(s.batchOffset[tailStart] - s.batchOffset[tailStart - 1]) <= TAIL_ROWS) tailStart--;
+	iteratePhase<0>(s, bar, numBatches, tailStart, stride, firstOffset);
+	iteratePhase<1>(s, bar, numBatches, tailStart, stride, firstOffset);
 }
 
 // ---------------------------------------------------------------- dataflow iterations
