@@ -178,6 +178,7 @@ struct World
 	// timing
 	bool timing = false;
 	cudaEvent_t ev[8] = {nullptr};
+	cudaEvent_t evSat[2] = {nullptr, nullptr};  // around satKernel -> stageMs[7]
 	float stageMs[8] = {0.f};
 
 	int init(const b3b200_config* cfg, int device, cudaStream_t stream);

@@ -1159,8 +1159,10 @@ int launchNarrowphase(World* w)
 		npChildCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dSurvivors.ptr);
 		B3_LAUNCH_CHECK();
 	}
+	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[0], s));  // stage_timings()[7] = this kernel alone
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
+	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[1], s));
 	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	if (w->hasConcave) B3_TRY(launchConcave(w));

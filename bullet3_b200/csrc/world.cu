@@ -53,6 +53,7 @@ int World::init(const b3b200_config* c, int dev, cudaStream_t st)
 	B3_TRY(dGridBarrier.reserve(4));
 	B3_CUDA_CHECK(cudaMemsetAsync(dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, stream));
 	for (int i = 0; i < 8; i++) B3_CUDA_CHECK(cudaEventCreate(&ev[i]));
+	for (int i = 0; i < 2; i++) B3_CUDA_CHECK(cudaEventCreate(&evSat[i]));
 	return 0;
 }
 
@@ -63,6 +64,8 @@ void World::destroy()
 	if (stream) cudaStreamSynchronize(stream);
 	for (int i = 0; i < 8; i++)
 		if (ev[i]) cudaEventDestroy(ev[i]);
+	for (int i = 0; i < 2; i++)
+		if (evSat[i]) cudaEventDestroy(evSat[i]);
 	cudaStream_t s = stream;
 	bool own = ownStream;
 	bp.stream = 0;  // shared with the world
@@ -679,6 +682,11 @@ extern "C" int b3b200_step(b3b200_world* w, float dt)
 		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
 		for (int i = 0; i < 6; i++) cudaEventElapsedTime(&w->stageMs[i], w->ev[i], w->ev[i + 1]);
 		cudaEventElapsedTime(&w->stageMs[6], w->ev[0], w->ev[6]);
+		if (cudaEventElapsedTime(&w->stageMs[7], w->evSat[0], w->evSat[1]) != cudaSuccess)
+		{
+			w->stageMs[7] = 0.f;  // no SAT launch was recorded in this step
+			cudaGetLastError();
+		}
 	}
 	return 0;
 }

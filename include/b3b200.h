@@ -81,7 +81,8 @@ int b3b200_register_plane(b3b200_world* w, const float* normal3, float planeCons
 int b3b200_register_sphere(b3b200_world* w, float radius);
 /* registerCompoundShape :370-474 -- children reference convex collidables via shapeIndex */
 int b3b200_register_compound(b3b200_world* w, const b3b200_child_shape* children, int numChildren);
-/* registerConcaveMesh :476-498 */
+/* registerConcaveMesh (b3GpuNarrowPhase.cpp:521-605) + registerConcaveMeshShape (:607-668): triangles become the faces of
+ * one convex-table entry; this build adds its own float AABB tree instead of the quantized b3OptimizedBvh */
 int b3b200_register_concave(b3b200_world* w, const float* vertices, int numVertices,
 							const int* triIndices, int numIndices, const float* scaling3);
 
@@ -145,7 +146,7 @@ int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numCont
 int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, int capacity, int* numConstraints);
 int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches);
 /* counters of the last step: [0]=pairs [1]=contacts [2]=batches [3]=colouring rounds
- * [4]=overflow flags [5]=compound pairs [6]=concave pairs [7]=reserved */
+ * [4]=overflow flags [5]=raw compound child pairs [6]=raw (pair, triangle, child) items [7]=SAT work items */
 int b3b200_get_counters(b3b200_world* w, int* dst8);
 /* ms per stage of the last step when timing is enabled:
  * [0]=aabbs [1]=broadphase [2]=narrowphase [3]=solver setup [4]=solver iterations [5]=integrate [6]=total */
