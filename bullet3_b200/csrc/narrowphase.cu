@@ -1070,6 +1070,182 @@ B3_D void planeConvexThread(const NpArgs& a, int pairIndex, int planeBody, int c
 	a.pairsOut[pairIndex].z = (int)slot;
 }
 
+// one-point contact of the sphere paths (m_childIndexA/B = -1)
+B3_D void appendOnePoint(const NpArgs& a, int pairIndex, int bodyA, int bodyB, const float4& normalOnB, const float4& pointWithDepth)
+{
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return;
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	cw[0] = pointWithDepth;
+	cw[1] = cw[2] = cw[3] = mk4(0, 0, 0, 0);
+	cw[4] = mk4(normalOnB.x, normalOnB.y, normalOnB.z, 1.f);
+	int4 t;
+	t.x = (int)(0u | (45874u << 16));
+	t.y = pairIndex;
+	t.z = a.pose[2 * bodyA].w == 0.f ? -bodyA : bodyA;
+	t.w = a.pose[2 * bodyB].w == 0.f ? -bodyB : bodyB;
+	reinterpret_cast<int4*>(c)[5] = t;
+	reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);
+	a.pairsOut[pairIndex].z = (int)slot;
+}
+
+// computeContactSphereConvex, host twin (b3ConvexHullContact.cpp:2323-2470; signedDistanceFromPointToPlane :342-349,
+// IsPointInPolygon :362-416), operation by operation.  A = sphere, B = convex hull.
+B3_D void sphereConvexThread(const NpArgs& a, int pairIndex, int sphereBody, int convexBody)
+{
+	const float radius = __ldg(&a.collidables[a.coll[sphereBody]].radius);
+	const float4 spherePos1 = a.pose[2 * sphereBody];
+	const float4 pos = a.pose[2 * convexBody], quat = a.pose[2 * convexBody + 1];
+	const Mat3 basis = matFromQuat(quat), inv = matTranspose(basis);
+	const float4 invOrigin = matMulVec(inv, neg3(mk4(pos.x, pos.y, pos.z)));
+	const float4 spherePos = add3(matMulVec(inv, spherePos1), invOrigin);
+	const HullRef h = loadHull(a.convex, __ldg(&a.collidables[a.coll[convexBody]].shapeIndex));
+	float4 closestPnt = mk4(0, 0, 0), localHitNormal = mk4(0, 0, 0);
+	float minDist = -1000000.f;
+	bool bCollide = true;
+	for (int f = 0; f < h.numFaces; f++)
+	{
+		const b3b200_face* face = &a.faces[h.faceOffset + f];
+		const float4 pl = __ldg(reinterpret_cast<const float4*>(&face->plane));
+		const float4 n = mk4(pl.x, pl.y, pl.z);
+		float dist = dot3(n, spherePos) + pl.w;
+		const float4 pntReturn = sub3(spherePos, scale3(n, dist));
+		if (dist > radius)
+		{
+			bCollide = false;
+			break;
+		}
+		if (dist > 0)
+		{
+			bool inPoly = true;
+			float4 outP = mk4(0, 0, 0);
+			const int numIdx = __ldg(&face->numIndices), idxOff = __ldg(&face->indexOffset);
+			if (numIdx < 2)
+				inPoly = false;
+			else
+			{
+				float4 b = __ldg(&a.vertices[h.vertexOffset + __ldg(&a.indices[idxOff + numIdx - 1])]);
+				for (int i = 0; i != numIdx; ++i)
+				{
+					const float4 av = b;
+					b = __ldg(&a.vertices[h.vertexOffset + __ldg(&a.indices[idxOff + i])]);
+					const float4 ab = sub3(b, av), ap = sub3(spherePos, av);
+					const float4 v = cross3(ab, n);
+					if (dot3(ap, v) > 0.f)
+					{
+						const float ab_m2 = dot3(ab, ab);
+						const float rt = ab_m2 != 0.f ? dot3(ab, ap) / ab_m2 : 0.f;
+						if (rt <= 0.f)
+							outP = av;
+						else if (rt >= 1.f)
+							outP = b;
+						else
+						{
+							const float s = 1.f - rt;
+							outP = mk4(s * av.x + rt * b.x, s * av.y + rt * b.y, s * av.z + rt * b.z);
+						}
+						inPoly = false;
+						break;
+					}
+				}
+			}
+			if (inPoly)
+			{
+				if (dist > minDist)
+				{
+					minDist = dist;
+					closestPnt = pntReturn;
+					localHitNormal = n;
+				}
+			}
+			else
+			{
+				const float4 tmp = sub3(spherePos, outP);
+				const float l2 = dot3(tmp, tmp);
+				if (l2 < radius * radius)
+				{
+					dist = sqrtf(l2);
+					if (dist > minDist)
+					{
+						minDist = dist;
+						closestPnt = outP;
+						localHitNormal = scale3(tmp, 1.0f / dist);
+					}
+				}
+				else
+				{
+					bCollide = false;
+					break;
+				}
+			}
+		}
+		else if (dist > minDist)
+		{
+			minDist = dist;
+			closestPnt = pntReturn;
+			localHitNormal = n;
+		}
+	}
+	if (bCollide && minDist > -10000)
+	{
+		const float4 normalOnSurfaceB1 = matMulVec(basis, localHitNormal);
+		float4 pOnB1 = add3(matMulVec(basis, closestPnt), mk4(pos.x, pos.y, pos.z));
+		const float actualDepth = minDist - radius;
+		if (actualDepth < 0)
+		{
+			pOnB1.w = actualDepth;
+			appendOnePoint(a, pairIndex, sphereBody, convexBody, normalOnSurfaceB1, pOnB1);
+		}
+	}
+}
+
+// computeContactPlaneSphere (kernels/primitiveContacts.cl:728-790).  The reference has no host twin of it.
+B3_D void planeSphereThread(const NpArgs& a, int pairIndex, int planeBody, int sphereBody)
+{
+	const float4 planeEq = __ldg(reinterpret_cast<const float4*>(&a.faces[__ldg(&a.collidables[a.coll[planeBody]].shapeIndex)].plane));
+	const float radius = __ldg(&a.collidables[a.coll[sphereBody]].radius);
+	float4 posA = a.pose[2 * planeBody], posB = a.pose[2 * sphereBody];
+	const float4 ornA = a.pose[2 * planeBody + 1], ornB = a.pose[2 * sphereBody + 1];
+	posA.w = 0.f;
+	posB.w = 0.f;
+	const float4 planeNormal = mk4(planeEq.x, planeEq.y, planeEq.z);
+	const float planeConstant = planeEq.w;
+	const float4 invOrnA = quatInverse(ornA), invPosA = quatRotate(invOrnA, neg3(posA));
+	const float4 cipOrn = quatMul(invOrnA, ornB), cipPos = add3(quatRotate(invOrnA, posB), invPosA);
+	const float4 picOrn = quatMul(quatInverse(ornB), ornA);
+	const float4 vtx = scale3(quatRotate(picOrn, neg3(planeNormal)), radius);
+	const float4 vtxInPlane = add3(quatRotate(cipOrn, vtx), cipPos);
+	const float distance = dot3(planeNormal, vtxInPlane) - planeConstant;
+	if (distance < 0.f)
+	{
+		const float4 projected = sub3(vtxInPlane, scale3(planeNormal, distance));
+		const float4 world = add3(quatRotate(ornA, projected), posA);
+		const float4 normalOnSurfaceB = quatRotate(ornA, planeNormal);
+		float4 pOnB = add3(world, scale3(normalOnSurfaceB, distance));
+		pOnB.w = distance;
+		appendOnePoint(a, pairIndex, planeBody, sphereBody, neg3(normalOnSurfaceB), pOnB);
+	}
+}
+
+// sphere x sphere (kernels/primitiveContacts.cl:926-972).  The reference has no host twin of it.
+B3_D void sphereSphereThread(const NpArgs& a, int pairIndex, int bodyA, int bodyB)
+{
+	const float radiusA = __ldg(&a.collidables[a.coll[bodyA]].radius), radiusB = __ldg(&a.collidables[a.coll[bodyB]].radius);
+	const float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
+	const float4 diff = sub3(posA, posB);
+	const float len = sqrtf(dot3(diff, diff));
+	if (len <= (radiusA + radiusB))
+	{
+		const float dist = len - (radiusA + radiusB);
+		float4 normalOnSurfaceB = mk4(1.f, 0.f, 0.f);
+		if (len > 0.00001f) normalOnSurfaceB = mk4(diff.x / len, diff.y / len, diff.z / len);
+		float4 contactPosB = add3(mk4(posB.x, posB.y, posB.z), scale3(normalOnSurfaceB, radiusB));
+		contactPosB.w = dist;
+		appendOnePoint(a, pairIndex, bodyA, bodyB, normalOnSurfaceB, contactPosB);
+	}
+}
+
 __global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
@@ -1079,6 +1255,16 @@ __global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
 		int cA = a.coll[bodyA], cB = a.coll[bodyB];
 		if (cA < 0 || cB < 0) continue;
 		int typeA = __ldg(&a.collidables[cA].shapeType), typeB = __ldg(&a.collidables[cB].shapeType);
+		if (typeA != B3B200_SHAPE_PLANE && typeB != B3B200_SHAPE_PLANE && (typeA == B3B200_SHAPE_SPHERE || typeB == B3B200_SHAPE_SPHERE))
+		{
+			if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_SPHERE)
+				sphereSphereThread(a, p, bodyA, bodyB);
+			else if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_CONVEX_HULL)
+				sphereConvexThread(a, p, bodyA, bodyB);
+			else if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_SPHERE)
+				sphereConvexThread(a, p, bodyB, bodyA);
+			continue;
+		}
 		if (typeB == B3B200_SHAPE_PLANE && typeA != B3B200_SHAPE_PLANE)
 		{
 			// the plane is always passed first (b3ConvexHullContact.cpp:2668-2690)
@@ -1107,6 +1293,8 @@ __global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
 				if (resolveSide(a, bodyB, first + cI, B)) planeConvexThread(a, p, bodyA, bodyB, first + cI, B);
 			}
 		}
+		else if (typeB == B3B200_SHAPE_SPHERE)
+			planeSphereThread(a, p, bodyA, bodyB);
 	}
 }
 

@@ -576,7 +576,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	w->hasConcave = false;
 	for (size_t i = 0; i < w->collidables.size(); i++)
 	{
-		if (w->collidables[i].shapeType == B3B200_SHAPE_PLANE) w->hasPlanes = true;
+		if (w->collidables[i].shapeType == B3B200_SHAPE_PLANE || w->collidables[i].shapeType == B3B200_SHAPE_SPHERE) w->hasPlanes = true;  // primitives kernel
 		if (w->collidables[i].shapeType == B3B200_SHAPE_CONCAVE_TRIMESH) w->hasConcave = true;
 	}
 	if (w->hasConcave)

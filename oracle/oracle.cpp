@@ -811,6 +811,170 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 		c.childIndexB = child;
 		for (int i = 0; i < numReduced; i++) c.worldPosB[i] = st(pts[idx[i]]);
 	};
+	auto onePoint = [&](int pairIndex, int bodyA, int bodyB, const V3& normalOnB, const V3& pointWithDepth) {
+		if (nContacts >= maxContacts) return;
+		b3b200_contact4& c = out[nContacts++];
+		memset(&c, 0, sizeof(c));
+		c.worldNormalOnB = st(mk(normalOnB.x, normalOnB.y, normalOnB.z, 1.f));
+		c.frictionCmp = 45874;
+		c.batchIdx = pairIndex;
+		c.bodyAPtrAndSignBit = bodies[bodyA].invMass == 0 ? -bodyA : bodyA;
+		c.bodyBPtrAndSignBit = bodies[bodyB].invMass == 0 ? -bodyB : bodyB;
+		c.childIndexA = -1;
+		c.childIndexB = -1;
+		c.worldPosB[0] = st(pointWithDepth);
+	};
+	// computeContactSphereConvex, host twin (b3ConvexHullContact.cpp:2323-2470; signedDistanceFromPointToPlane :342-349,
+	// IsPointInPolygon :362-416).  A = sphere, B = convex hull.
+	auto sphereConvex = [&](int pairIndex, int sphereBody, int convexBody) {
+		const float radius = collidables[bodies[sphereBody].collidableIdx].radius;
+		V3 spherePos1 = ld(bodies[sphereBody].pos);
+		V3 pos = ld(bodies[convexBody].pos), quat = ld(bodies[convexBody].quat);
+		M3 basis = matFromQuat(quat), inv = transposeM(basis);
+		V3 invOrigin = matMul(inv, neg(mk(pos.x, pos.y, pos.z)));
+		V3 spherePos = add(matMul(inv, spherePos1), invOrigin);
+		const b3b200_convex_polyhedron& h = convex[collidables[bodies[convexBody].collidableIdx].shapeIndex];
+		V3 closestPnt = mk(0, 0, 0), localHitNormal = mk(0, 0, 0);
+		float minDist = -1000000.f;
+		bool bCollide = true;
+		for (int f = 0; f < h.numFaces; f++)
+		{
+			const b3b200_face& face = faces[h.faceOffset + f];
+			V3 n = mk(face.plane.x, face.plane.y, face.plane.z);
+			float dist = dot(n, spherePos) + face.plane.w;
+			V3 pntReturn = sub(spherePos, mul(n, dist));
+			if (dist > radius)
+			{
+				bCollide = false;
+				break;
+			}
+			if (dist > 0)
+			{
+				// IsPointInPolygon
+				bool inPoly = true;
+				V3 outP = mk(0, 0, 0);
+				if (face.numIndices < 2)
+					inPoly = false;
+				else
+				{
+					V3 b = ld(vertices[h.vertexOffset + indices[face.indexOffset + face.numIndices - 1]]);
+					for (int i = 0; i != face.numIndices; ++i)
+					{
+						V3 a = b;
+						b = ld(vertices[h.vertexOffset + indices[face.indexOffset + i]]);
+						V3 ab = sub(b, a), ap = sub(spherePos, a);
+						V3 v = cross(ab, n);
+						if (dot(ap, v) > 0.f)
+						{
+							float ab_m2 = dot(ab, ab);
+							float rt = ab_m2 != 0.f ? dot(ab, ap) / ab_m2 : 0.f;
+							if (rt <= 0.f)
+								outP = a;
+							else if (rt >= 1.f)
+								outP = b;
+							else
+							{
+								float s = 1.f - rt;
+								outP = mk(s * a.x + rt * b.x, s * a.y + rt * b.y, s * a.z + rt * b.z);
+							}
+							inPoly = false;
+							break;
+						}
+					}
+				}
+				if (inPoly)
+				{
+					if (dist > minDist)
+					{
+						minDist = dist;
+						closestPnt = pntReturn;
+						localHitNormal = n;
+					}
+				}
+				else
+				{
+					V3 tmp = sub(spherePos, outP);
+					float l2 = dot(tmp, tmp);
+					if (l2 < radius * radius)
+					{
+						dist = sqrtf(l2);
+						if (dist > minDist)
+						{
+							minDist = dist;
+							closestPnt = outP;
+							localHitNormal = mul(tmp, 1.0f / dist);
+						}
+					}
+					else
+					{
+						bCollide = false;
+						break;
+					}
+				}
+			}
+			else if (dist > minDist)
+			{
+				minDist = dist;
+				closestPnt = pntReturn;
+				localHitNormal = n;
+			}
+		}
+		if (bCollide && minDist > -10000)
+		{
+			V3 normalOnSurfaceB1 = matMul(basis, localHitNormal);
+			V3 pOnB1 = add(matMul(basis, closestPnt), mk(pos.x, pos.y, pos.z));
+			float actualDepth = minDist - radius;
+			if (actualDepth < 0)
+			{
+				pOnB1.w = actualDepth;
+				onePoint(pairIndex, sphereBody, convexBody, normalOnSurfaceB1, pOnB1);
+			}
+		}
+	};
+	// computeContactPlaneSphere (kernels/primitiveContacts.cl:728-790; device only -- no host twin: parity unpinned)
+	auto planeSphere = [&](int pairIndex, int planeBody, int sphereBody) {
+		V3 planeEq = ld(faces[collidables[bodies[planeBody].collidableIdx].shapeIndex].plane);
+		const float radius = collidables[bodies[sphereBody].collidableIdx].radius;
+		V3 posA = ld(bodies[planeBody].pos), ornA = ld(bodies[planeBody].quat);
+		V3 posB = ld(bodies[sphereBody].pos), ornB = ld(bodies[sphereBody].quat);
+		posA.w = 0.f;
+		posB.w = 0.f;
+		V3 planeNormal = mk(planeEq.x, planeEq.y, planeEq.z);
+		const float planeConstant = planeEq.w;
+		// trInverse / trMul
+		V3 invOrnA = quatInv(ornA), invPosA = quatRotate(invOrnA, neg(posA));
+		V3 cipOrn = quatMul(invOrnA, ornB), cipPos = add(quatRotate(invOrnA, posB), invPosA);
+		V3 invOrnB = quatInv(ornB);
+		V3 picOrn = quatMul(invOrnB, ornA);
+		V3 vtx = mul(quatRotate(picOrn, neg(planeNormal)), radius);
+		V3 vtxInPlane = add(quatRotate(cipOrn, vtx), cipPos);
+		float distance = dot(planeNormal, vtxInPlane) - planeConstant;
+		if (distance < 0.f)
+		{
+			V3 projected = sub(vtxInPlane, mul(planeNormal, distance));
+			V3 world = add(quatRotate(ornA, projected), posA);
+			V3 normalOnSurfaceB = quatRotate(ornA, planeNormal);
+			V3 pOnB = add(world, mul(normalOnSurfaceB, distance));
+			pOnB.w = distance;
+			onePoint(pairIndex, planeBody, sphereBody, neg(normalOnSurfaceB), pOnB);
+		}
+	};
+	// sphere x sphere (kernels/primitiveContacts.cl:926-972; device only: parity unpinned)
+	auto sphereSphere = [&](int pairIndex, int bodyA, int bodyB) {
+		const float radiusA = collidables[bodies[bodyA].collidableIdx].radius, radiusB = collidables[bodies[bodyB].collidableIdx].radius;
+		V3 posA = ld(bodies[bodyA].pos), posB = ld(bodies[bodyB].pos);
+		V3 diff = sub(posA, posB);
+		float len = sqrtf(dot(diff, diff));
+		if (len <= (radiusA + radiusB))
+		{
+			float dist = len - (radiusA + radiusB);
+			V3 normalOnSurfaceB = mk(1.f, 0.f, 0.f);
+			if (len > 0.00001f) normalOnSurfaceB = mk(diff.x / len, diff.y / len, diff.z / len);
+			V3 contactPosB = add(posB, mul(normalOnSurfaceB, radiusB));
+			contactPosB.w = dist;
+			onePoint(pairIndex, bodyA, bodyB, normalOnSurfaceB, contactPosB);
+		}
+	};
 	for (int p = 0; p < nPairs; p++)
 	{
 		int bodyA = pairs[p].x, bodyB = pairs[p].y;
@@ -855,6 +1019,19 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 					if (resolveSide(bodies, collidables, children, other, child, B)) planeConvex(p, planeBody, other, child, B);
 				}
 			}
+			else if (typeO == B3B200_SHAPE_SPHERE)
+				planeSphere(p, planeBody, other);
+		}
+		else if (typeA == B3B200_SHAPE_SPHERE || typeB == B3B200_SHAPE_SPHERE)
+		{
+			if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_SPHERE)
+				sphereSphere(p, bodyA, bodyB);
+			else if (typeA == B3B200_SHAPE_SPHERE && hullB)
+				sphereConvex(p, bodyA, bodyB);
+			else if (hullA && typeB == B3B200_SHAPE_SPHERE)
+				sphereConvex(p, bodyB, bodyA);
+			// sphere x compound / trimesh: device kernels only in the reference (findConcaveSphereContactsKernel,
+			// processCompoundPairsPrimitivesKernel); not built
 		}
 	}
 	return nContacts;

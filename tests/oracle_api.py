@@ -285,3 +285,10 @@ def _ref_concave_host_twins(self, on=True):
 
 RefNarrowphase.register_concave = _ref_register_concave
 RefNarrowphase.concave_host_twins = _ref_concave_host_twins
+
+
+def _ref_register_sphere(self, radius):
+    return self.L.refcl_np_register_sphere(self.h, C.c_float(radius))
+
+
+RefNarrowphase.register_sphere = _ref_register_sphere
