@@ -3,7 +3,9 @@
 // Replaces b3GpuNarrowPhase::computeContacts -> GpuSatCollision::
 // computeConvexConvexContactsGPUSAT (b3GpuNarrowPhase.cpp:751-809,
 // b3ConvexHullContact.cpp:2558-4408: ~12 kernels + 7..15 host round trips per
-// step) with ONE persistent kernel and no host synchronisation.
+// step) with a short chain of kernels (quick reject -> SAT -> clip, plus the primitive and
+// trimesh kernels when such shapes exist) connected by device-side work queues and counters,
+// without any host synchronisation.
 //
 // The arithmetic follows the reference's shared CPU headers operation by
 // operation (the oracle the parity tests use):

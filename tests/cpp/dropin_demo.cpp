@@ -10,7 +10,85 @@
 #include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
 #include "Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h"
 
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3Collidable.h"
+
 static const float cube[8 * 3] = {-1, -1, -1, -1, -1, 1, -1, 1, -1, -1, 1, 1, 1, -1, -1, 1, -1, 1, 1, 1, -1, 1, 1, 1};
+
+// GpuConcaveScene / GpuCompoundScene-style caller code (examples/OpenCL/rigidbody/ConcaveScene.cpp:150-260,
+// GpuCompoundScene.cpp:60-160): a trimesh ground (body 0), three-box compounds, hulls and spheres dropped on it.
+static bool meshScene(bool useUniformGrid)
+{
+	cl_context ctx = 0;
+	cl_device_id dev = 0;
+	cl_command_queue q = 0;
+	b3Config config;
+	b3GpuNarrowPhase* np = new b3GpuNarrowPhase(ctx, dev, q, config);
+	b3GpuBroadphaseInterface* bp = useUniformGrid ? (b3GpuBroadphaseInterface*)new b3GpuGridBroadphase(ctx, dev, q) : (b3GpuBroadphaseInterface*)new b3GpuSapBroadphase(ctx, dev, q);
+	b3GpuRigidBodyPipeline* pipe = new b3GpuRigidBodyPipeline(ctx, dev, q, np, bp, 0, config);
+	const int Q = 24;
+	b3AlignedObjectArray<b3Vector3> verts;
+	b3AlignedObjectArray<int> idx;
+	for (int i = 0; i <= Q; i++)
+		for (int k = 0; k <= Q; k++)
+		{
+			float x = (float)i - 0.5f * Q, z = (float)k - 0.5f * Q;
+			verts.push_back(b3MakeVector3(x, 0.8f * sinf(0.4f * x) * cosf(0.4f * z), z));
+		}
+	for (int i = 0; i < Q; i++)
+		for (int k = 0; k < Q; k++)
+		{
+			int v00 = i * (Q + 1) + k, v01 = v00 + 1, v10 = v00 + Q + 1, v11 = v10 + 1;
+			int t[6] = {v00, v01, v11, v00, v11, v10};
+			for (int j = 0; j < 6; j++) idx.push_back(t[j]);
+		}
+	float one[4] = {1, 1, 1, 1}, orn[4] = {0, 0, 0, 1}, origin[4] = {0, 0, 0, 0};
+	int meshShape = np->registerConcaveMesh(&verts, &idx, one);
+	int meshBody = pipe->registerPhysicsInstance(0.f, origin, orn, meshShape, 0, false);
+	float half[4] = {0.4f, 0.4f, 0.4f, 1};
+	int smallBox = np->registerConvexHullShape(cube, 3 * sizeof(float), 8, half);
+	b3AlignedObjectArray<b3GpuChildShape> children;
+	const float offs[3][3] = {{-0.4f, -0.4f, 0}, {0.4f, -0.4f, 0}, {-0.4f, 0.4f, 0}};
+	for (int c = 0; c < 3; c++)
+	{
+		b3GpuChildShape ch;
+		ch.m_childPosition = b3MakeVector3(offs[c][0], offs[c][1], offs[c][2]);
+		ch.m_childOrientation = b3Quaternion(0, 0, 0, 1);
+		ch.m_shapeIndex = smallBox;
+		ch.m_shapeType = SHAPE_CONVEX_HULL;
+		children.push_back(ch);
+	}
+	int compound = np->registerCompoundShape(&children);
+	int sphere = np->registerSphereShape(0.5f);
+	int shapes[2] = {smallBox, compound};  // (sphere x trimesh is not built: spheres would fall through)
+	int n = 0;
+	for (int i = 0; i < 6; i++)
+		for (int k = 0; k < 6; k++)
+			for (int j = 0; j < 2; j++)
+			{
+				float pos[4] = {-7.5f + 3.f * i, 2.5f + 1.6f * j, -7.5f + 3.f * k, 0};
+				if (pipe->registerPhysicsInstance(1.f, pos, orn, shapes[(i + k + j) % 2], n, false) >= 0) n++;
+			}
+	pipe->writeAllInstancesToGpu();
+	np->writeAllBodiesToGpu();
+	bp->writeAabbsToGpu();
+	for (int s = 0; s < 240; s++) pipe->stepSimulation(1.f / 60.f);
+	np->readbackAllBodiesToCpu();
+	const b3RigidBodyData* b = np->getBodiesCpu();
+	int resting = 0;
+	for (int i = 1; i < pipe->getNumBodies(); i++)
+	{
+		float ground = 0.8f * sinf(0.4f * b[i].m_pos.x) * cosf(0.4f * b[i].m_pos.z);
+		if (fabsf(b[i].m_pos.x) < 12 && fabsf(b[i].m_pos.z) < 12 && b[i].m_pos.y > ground - 0.2f && b[i].m_pos.y < ground + 3.f) resting++;
+	}
+	printf("mesh scene: shapes mesh=%d box=%d compound=%d sphere=%d, bodies=%d, contacts=%d, resting on the mesh=%d\n", meshShape, smallBox, compound, sphere,
+		   pipe->getNumBodies(), np->getNumContactsGpu(), resting);
+	bool ok = meshShape >= 0 && meshBody == 0 && compound > smallBox && sphere > compound && pipe->getNumBodies() == n + 1 && np->getNumContactsGpu() >= n / 2 &&
+			  resting >= (9 * n) / 10;
+	delete pipe;
+	delete bp;
+	delete np;
+	return ok;
+}
 
 int main(int argc, char** argv)
 {
@@ -81,6 +159,7 @@ int main(int argc, char** argv)
 	delete pipe;
 	delete bp;
 	delete np;
+	ok = meshScene(useUniformGrid) && ok;
 	printf(ok ? "DROPIN OK\n" : "DROPIN FAILED\n");
 	return ok ? 0 : 1;
 }
