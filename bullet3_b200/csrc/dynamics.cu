@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(DYN_THREADS) packSoAKernel(const b3b200_rigid_
 }
 
 __global__ void __launch_bounds__(DYN_THREADS) unpackSoAKernel(b3b200_rigid_body* __restrict__ aos, int n, const float4* __restrict__ pose,
-															   const float4* __restrict__ vel)
+															   const float4* __restrict__ vel, const int* __restrict__ coll)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(DYN_THREADS) unpackSoAKernel(b3b200_rigid_body
 	p[1] = pose[2 * i + 1];
 	p[2] = vel[2 * i];
 	p[3] = vel[2 * i + 1];
+	// collidable index and inverse mass only change through the halo path (ghost slots); keep the AoS view in step
+	aos[i].collidableIdx = coll[i];
+	aos[i].invMass = pose[2 * i].w;
 }
 
 B3_D void computeWorldAabb(const float4& pos, const float4& quat, const float4& lmn, const float4& lmx, float4& outMin, float4& outMax)
@@ -153,7 +156,7 @@ int launchUnpackSoA(World* w)
 {
 	int n = w->numBodies;
 	if (n == 0) return 0;
-	unpackSoAKernel<<<divUp(n, DYN_THREADS), DYN_THREADS, 0, w->stream>>>(w->dBodiesAoS.ptr, n, w->dPose.ptr, w->dVel.ptr);
+	unpackSoAKernel<<<divUp(n, DYN_THREADS), DYN_THREADS, 0, w->stream>>>(w->dBodiesAoS.ptr, n, w->dPose.ptr, w->dVel.ptr, w->dCollidableIdx.ptr);
 	B3_LAUNCH_CHECK();
 	w->soaDirty = false;
 	return 0;

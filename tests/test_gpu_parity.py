@@ -633,3 +633,86 @@ def test_spheres_and_boxes_settle_on_plane():
     assert np.isfinite(b["pos"]).all()
     assert b["pos"][dyn, 1].min() > 0.1  # nothing sank into the plane (spheres rest at radius - drift; the random hull is flat)
     assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 1.0
+
+
+# ------------------------------------------------------------------ halo records (slab mode), two worlds on ONE device
+def test_halo_pack_unpack_between_two_worlds():
+    """b3b200_halo_pack on one world -> device buffer -> b3b200_halo_unpack into the ghost slots of another world:
+    the ghosts carry the owner's state bit for bit, produce the same pairs as the original bodies would, and unused
+    ghost slots stay parked."""
+    import ctypes as C
+    import torch
+
+    rng = np.random.default_rng(0)
+    n, n_ghost = 300, 256
+    pos = np.stack([rng.uniform(-6, 6, n), rng.uniform(0.6, 3.0, n), rng.uniform(-3, 3, n)], 1).astype(np.float32)
+    quat = np.array([scenes.random_quat(rng) for _ in range(n)], np.float32)
+    left = pos[:, 0] < 0
+
+    def make(owned_mask):
+        w = capi.World(capi.default_config(2048))
+        scenes.add_ground_box(w, 50.0)
+        box = w.register_convex_points(scenes.box_points(0.5))
+        hull = w.register_convex_points(scenes.random_hull_points(np.random.default_rng(5), 10, 0.5, 0.7))
+        cols = np.where(np.arange(n) % 2 == 0, box, hull).astype(np.int32)
+        idx = np.nonzero(owned_mask)[0]
+        w.register_instances(np.ones(len(idx), np.float32), pos[idx], quat[idx], cols[idx])
+        park = np.zeros((n_ghost, 3), np.float32)
+        park[:, 0] = 1.0e6 + 1024.0 * np.arange(n_ghost)
+        park[:, 1] = -1.0e6
+        w.register_instances(np.ones(n_ghost, np.float32), park, np.tile(np.array(scenes.IDENT, np.float32), (n_ghost, 1)), np.full(n_ghost, box, np.int32))
+        w.upload()
+        return w, idx
+
+    wl, idl = make(left)
+    wr, idr = make(~left)
+    L = capi.lib()
+    rec = L.b3b200_halo_record_size()
+    buf = torch.zeros(n_ghost * rec, dtype=torch.uint8, device="cuda")
+    cnt = C.c_int(0)
+    margin = 1.5
+    # bodies of the left world whose AABB reaches x >= -margin go to the right world's ghost slots
+    capi.check(L.b3b200_halo_pack(wl.h, 0, C.c_float(-margin), C.c_float(3.0e38), 1 + len(idl), 1000 - 1, 0, C.c_void_p(buf.data_ptr()), n_ghost, C.byref(cnt)), "pack")
+    aabbs_l = wl.aabbs()
+    want = np.nonzero(aabbs_l["max"][1: 1 + len(idl), 0] >= -margin)[0]
+    assert cnt.value == len(want) and 5 < cnt.value < n_ghost
+    first_ghost = 1 + len(idr)
+    capi.check(L.b3b200_halo_unpack(wr.h, C.c_void_p(buf.data_ptr()), cnt.value, first_ghost, n_ghost), "unpack")
+    gids = np.zeros(wr.num_bodies, np.int32)
+    capi.check(L.b3b200_halo_ghost_ids(wr.h, capi.ptr(gids), len(gids)), "ghost ids")
+    got = gids[first_ghost: first_ghost + cnt.value]
+    assert sorted(got.tolist()) == sorted((1000 + want).tolist())
+    assert np.all(gids[first_ghost + cnt.value: first_ghost + n_ghost] == -1)
+    br, bl = wr.bodies(), wl.bodies()
+    for slot, gid in enumerate(got):
+        src = bl[1 + (gid - 1000)]
+        dst = br[first_ghost + slot]
+        for f in ("pos", "quat", "linVel", "angVel"):
+            assert np.array_equal(np.asarray(src[f])[:3].view(np.uint32), np.asarray(dst[f])[:3].view(np.uint32)), f
+        assert src["collidableIdx"] == dst["collidableIdx"] and src["invMass"] == dst["invMass"]
+    parked = br[first_ghost + cnt.value:]
+    assert np.all(parked["invMass"] == 0) and np.all(parked["pos"][:, 0] >= 1.0e6)
+    # pairs of the right world = pairs of a world holding the right bodies + the mirrored left bodies
+    wr.update_aabbs()
+    wr.find_pairs()
+    pr = wr.pairs()
+    ids = np.full(wr.num_bodies, -5, np.int64)
+    ids[0] = -1
+    ids[1: 1 + len(idr)] = idr
+    ids[first_ghost: first_ghost + cnt.value] = idl[got - 1000]
+    have = set(tuple(sorted((int(ids[a]), int(ids[b])))) for a, b in zip(pr["x"], pr["y"]))
+    assert all(-5 not in p for p in have)
+    keep = np.concatenate([idr, idl[want]])
+    wf = capi.World(capi.default_config(2048))
+    scenes.add_ground_box(wf, 50.0)
+    box = wf.register_convex_points(scenes.box_points(0.5))
+    hull = wf.register_convex_points(scenes.random_hull_points(np.random.default_rng(5), 10, 0.5, 0.7))
+    cols = np.where(np.arange(n) % 2 == 0, box, hull).astype(np.int32)
+    wf.register_instances(np.ones(len(keep), np.float32), pos[keep], quat[keep], cols[keep])
+    wf.upload()
+    wf.update_aabbs()
+    wf.find_pairs()
+    pf = wf.pairs()
+    idf = np.concatenate([[-1], keep]).astype(np.int64)
+    ref = set(tuple(sorted((int(idf[a]), int(idf[b])))) for a, b in zip(pf["x"], pf["y"]))
+    assert have == ref and len(ref) > 100
