@@ -85,7 +85,8 @@ __global__ void haloUnpackKernel(float4* __restrict__ pose, float4* __restrict__
 	else
 	{
 		// parked: static, far away, one slot per 1024 units so that parked ghosts never overlap anything
-		pose[2 * i] = mk4(1.0e6f + 1024.0f * (float)k, -1.0e6f, 1.0e6f, 0.f);
+		// (indexed by the absolute body slot: the parked slots of the left and of the right neighbour must not coincide)
+		pose[2 * i] = mk4(1.0e6f + 1024.0f * (float)i, -1.0e6f, 1.0e6f, 0.f);
 		pose[2 * i + 1] = mk4(0.f, 0.f, 0.f, 1.f);
 		vel[2 * i] = mk4(0, 0, 0, 0);
 		vel[2 * i + 1] = mk4(0, 0, 0, 0);
