@@ -3,7 +3,7 @@
 // Replaces the concave leg of GpuSatCollision::computeConvexConvexContactsGPUSAT
 // (b3ConvexHullContact.cpp:3481-4040: bvhTraversalKernel, findConcaveSeparatingAxis*Kernel, clipFacesAndFindContacts,
 // newContactReductionKernel + 6 host round trips) with two launches and no host synchronisation:
-//   concaveCullKernel     one thread per broadphase pair whose A is a trimesh: walks this build's float AABB tree
+//   concaveCullKernel     one thread per broadphase pair whose A is a trimesh (listed by npCullKernel): walks this build's float AABB tree
 //                         (shapes.cu) with B's world AABB and emits (pair, triangle, child) work items for every
 //                         triangle whose exact AABB overlaps -- the same active set as the reference's quantized
 //                         b3BvhTraversal (shared/b3BvhTraversal.h:11-122) followed by the exact triangle-AABB test at
@@ -52,6 +52,7 @@ struct CcArgs
 struct HullRef
 {
 	float4 localCenter;
+	float radius;  // inscribed radius about localCenter (set at registration, world.cu)
 	int faceOffset, numFaces, numVertices, vertexOffset, uniqueEdgesOffset, numUniqueEdges;
 };
 B3_D HullRef loadHull(const b3b200_convex_polyhedron* __restrict__ convex, int shapeIndex)
@@ -61,6 +62,7 @@ B3_D HullRef loadHull(const b3b200_convex_polyhedron* __restrict__ convex, int s
 	r.localCenter = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
 	const int4* t = reinterpret_cast<const int4*>(&h->radius);  // radius, faceOffset, numFaces, numVertices
 	const int4 a = __ldg(t), b = __ldg(t + 1);                   // vertexOffset, uniqueEdgesOffset, numUniqueEdges, unused
+	r.radius = __int_as_float(a.x);
 	r.faceOffset = a.y;
 	r.numFaces = a.z;
 	r.numVertices = a.w;
@@ -184,11 +186,51 @@ B3_D int clipFaceGlobalWarp(const float4* in, int numIn, const float4& n, float 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) concaveCullKernel(CcArgs a, int4* __restrict__ items)
+constexpr int CULL_WARPS = 8;    // warps per CTA of concaveCullKernel
+constexpr int CULL_QUEUE = 256;  // frontier capacity per warp
+
+// serial walk of one subtree by one lane (only used when a warp's frontier queue overflows): appends the overlapping
+// leaves' triangles through `emit`
+template <typename Emit>
+B3_D void walkSubtree(const CcArgs& a, const int4& mesh, int root, const float4& qmn, const float4& qmx, Emit emit)
 {
-	const int numPairs = (int)a.ctr[CTR_PAIRS];
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < numPairs; p += gridDim.x * blockDim.x)
+	int stack[48];
+	int sp = 0;
+	stack[sp++] = root;
+	while (sp)
 	{
+		const int node = stack[--sp];
+		const float4 n0 = __ldg(&a.meshNodes[2 * (mesh.x + node)]), n1 = __ldg(&a.meshNodes[2 * (mesh.x + node) + 1]);
+		if (n0.x > qmx.x || n1.x < qmn.x || n0.y > qmx.y || n1.y < qmn.y || n0.z > qmx.z || n1.z < qmn.z) continue;
+		const int count = __float_as_int(n1.w), first = __float_as_int(n0.w);
+		if (count == 0)
+		{
+			if (sp + 2 <= 48)
+			{
+				stack[sp++] = first + 1;
+				stack[sp++] = first;
+			}
+			continue;
+		}
+		for (int t = 0; t < count; t++) emit(first + t);
+	}
+}
+
+// One WARP per trimesh pair (listed by npCullKernel, narrowphase.cu): level-synchronous walk of the mesh tree with a
+// per-warp frontier queue in shared memory -- 32 nodes are tested per step instead of one dependent load chain per
+// thread -- then the triangles of the overlapping leaves are tested one per lane.
+__global__ void __launch_bounds__(CULL_WARPS * 32) concaveCullKernel(CcArgs a, const int* __restrict__ meshPairs, int maxMeshPairs, int4* __restrict__ items)
+{
+	__shared__ int queueAll[CULL_WARPS][2][CULL_QUEUE];
+	__shared__ int leafAll[CULL_WARPS][CULL_QUEUE];  // first triangle slot | (count << 28)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned int lt = (1u << lane) - 1u;
+	int numMeshPairs = (int)a.ctr[CTR_MESH_PAIRS];
+	if (numMeshPairs > maxMeshPairs) numMeshPairs = maxMeshPairs;
+	for (int q = blockIdx.x * CULL_WARPS + warp; q < numMeshPairs; q += gridDim.x * CULL_WARPS)
+	{
+		__syncwarp();
+		const int p = meshPairs[q];
 		const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
 		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
 		if (cA < 0 || cB < 0) continue;
@@ -202,27 +244,14 @@ __global__ void __launch_bounds__(256) concaveCullKernel(CcArgs a, int4* __restr
 		const float4 qmn = *reinterpret_cast<const float4*>(a.aabbs[bodyB].min), qmx = *reinterpret_cast<const float4*>(a.aabbs[bodyB].max);
 		const int firstChild = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS ? __ldg(&a.collidables[cB].shapeIndex) : -1;
 		const int numChildren = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS ? __ldg(&a.collidables[cB].numChildShapes) : 1;
-		int stack[48];
-		int sp = 0;
-		stack[sp++] = 0;
-		while (sp)
-		{
-			const int node = stack[--sp];
-			const float4 n0 = __ldg(&a.meshNodes[2 * (mesh.x + node)]), n1 = __ldg(&a.meshNodes[2 * (mesh.x + node) + 1]);
-			if (n0.x > qmx.x || n1.x < qmn.x || n0.y > qmx.y || n1.y < qmn.y || n0.z > qmx.z || n1.z < qmn.z) continue;
-			const int count = __float_as_int(n1.w), first = __float_as_int(n0.w);
-			if (count == 0)
+
+		// exact triangle-AABB test + emission of one triangle slot (b3FindConcaveSatAxis.h:606-610)
+		auto testAndEmit = [&](int triSlot, bool valid) {
+			bool hit = false;
+			int tri = 0;
+			if (valid)
 			{
-				if (sp + 2 <= 48)
-				{
-					stack[sp++] = first + 1;
-					stack[sp++] = first;
-				}
-				continue;
-			}
-			for (int t = 0; t < count; t++)
-			{
-				const int tri = __ldg(&a.meshTris[mesh.z + first + t]);
+				tri = __ldg(&a.meshTris[mesh.z + triSlot]);
 				const int idxOff = __ldg(&a.faces[faceOffset + tri].indexOffset);
 				float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
 				for (int i = 0; i < 3; i++)
@@ -235,10 +264,126 @@ __global__ void __launch_bounds__(256) concaveCullKernel(CcArgs a, int4* __restr
 					mx[1] = fmaxf(mx[1], v.y);
 					mx[2] = fmaxf(mx[2], v.z);
 				}
-				if (mn[0] > qmx.x || mx[0] < qmn.x || mn[2] > qmx.z || mx[2] < qmn.z || mn[1] > qmx.y || mx[1] < qmn.y) continue;
-				const unsigned int slot = atomicAdd(&a.ctr[CTR_CONCAVE_PAIRS], (unsigned int)numChildren);
-				for (int c = 0; c < numChildren; c++)
-					if (slot + c < (unsigned int)a.maxItems) items[slot + c] = make_int4(p, tri, firstChild < 0 ? -1 : firstChild + c, 0);
+				hit = !(mn[0] > qmx.x || mx[0] < qmn.x || mn[2] > qmx.z || mx[2] < qmn.z || mn[1] > qmx.y || mx[1] < qmn.y);
+			}
+			const unsigned int m = __ballot_sync(FULL, hit);
+			if (m)
+			{
+				unsigned int slot = 0;
+				if (lane == 0) slot = atomicAdd(&a.ctr[CTR_CONCAVE_PAIRS], (unsigned int)(__popc(m) * numChildren));
+				slot = __shfl_sync(FULL, slot, 0) + (unsigned int)(__popc(m & lt) * numChildren);
+				if (hit)
+					for (int c = 0; c < numChildren; c++)
+						if (slot + c < (unsigned int)a.maxItems) items[slot + c] = make_int4(p, tri, firstChild < 0 ? -1 : firstChild + c, 0);
+			}
+		};
+
+		int* cur = queueAll[warp][0];
+		int* nxt = queueAll[warp][1];
+		int* leaves = leafAll[warp];
+		int n = 1, numLeaves = 0;
+		if (lane == 0) cur[0] = 0;
+		__syncwarp();
+		while (n > 0)
+		{
+			int nn = 0;
+			for (int base = 0; base < n; base += 32)
+			{
+				const int i = base + lane;
+				int kind = 0;  // 0 = nothing, 1 = internal (push 2 children), 2 = leaf
+				int first = 0, count = 0;
+				if (i < n)
+				{
+					const int node = cur[i];
+					const float4 n0 = __ldg(&a.meshNodes[2 * (mesh.x + node)]), n1 = __ldg(&a.meshNodes[2 * (mesh.x + node) + 1]);
+					if (!(n0.x > qmx.x || n1.x < qmn.x || n0.y > qmx.y || n1.y < qmn.y || n0.z > qmx.z || n1.z < qmn.z))
+					{
+						count = __float_as_int(n1.w);
+						first = __float_as_int(n0.w);
+						kind = count == 0 ? 1 : 2;
+					}
+				}
+				const unsigned int mi = __ballot_sync(FULL, kind == 1), ml = __ballot_sync(FULL, kind == 2);
+				const int pi = nn + 2 * __popc(mi & lt), pl = numLeaves + __popc(ml & lt);
+				bool spilled = false;
+				if (kind == 1)
+				{
+					if (pi + 2 <= CULL_QUEUE)
+					{
+						nxt[pi] = first;
+						nxt[pi + 1] = first + 1;
+					}
+					else
+						spilled = true;
+				}
+				else if (kind == 2)
+				{
+					if (pl < CULL_QUEUE)
+						leaves[pl] = first | (count << 28);
+					else
+						spilled = true;
+				}
+				nn = min(nn + 2 * __popc(mi), CULL_QUEUE);
+				numLeaves = min(numLeaves + __popc(ml), CULL_QUEUE);
+				// a full queue (a very large box over a fine mesh): the lanes that could not push walk their subtree alone
+				if (__any_sync(FULL, spilled))
+				{
+					if (spilled)
+					{
+						auto emitSerial = [&](int triSlot) {
+							const int tri = __ldg(&a.meshTris[mesh.z + triSlot]);
+							const int idxOff = __ldg(&a.faces[faceOffset + tri].indexOffset);
+							float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+							for (int v3 = 0; v3 < 3; v3++)
+							{
+								const float4 v = __ldg(&a.vertices[vertexOffset + __ldg(&a.indices[idxOff + v3])]);
+								mn[0] = fminf(mn[0], v.x);
+								mn[1] = fminf(mn[1], v.y);
+								mn[2] = fminf(mn[2], v.z);
+								mx[0] = fmaxf(mx[0], v.x);
+								mx[1] = fmaxf(mx[1], v.y);
+								mx[2] = fmaxf(mx[2], v.z);
+							}
+							if (mn[0] > qmx.x || mx[0] < qmn.x || mn[2] > qmx.z || mx[2] < qmn.z || mn[1] > qmx.y || mx[1] < qmn.y) return;
+							const unsigned int slot = atomicAdd(&a.ctr[CTR_CONCAVE_PAIRS], (unsigned int)numChildren);
+							for (int c = 0; c < numChildren; c++)
+								if (slot + c < (unsigned int)a.maxItems) items[slot + c] = make_int4(p, tri, firstChild < 0 ? -1 : firstChild + c, 0);
+						};
+						if (kind == 1)
+						{
+							walkSubtree(a, mesh, first, qmn, qmx, emitSerial);
+							walkSubtree(a, mesh, first + 1, qmn, qmx, emitSerial);
+						}
+						else
+							for (int t = 0; t < count; t++) emitSerial(first + t);
+					}
+					__syncwarp();
+				}
+			}
+			__syncwarp();
+			int* t = cur;
+			cur = nxt;
+			nxt = t;
+			n = nn;
+			// the leaf list is drained whenever it may not take another level's worth
+			if (numLeaves > CULL_QUEUE / 2 || n == 0)
+			{
+				for (int base = 0; base < numLeaves * 4; base += 32)
+				{
+					const int idx = base + lane;
+					bool valid = false;
+					int triSlot = 0;
+					if (idx < numLeaves * 4)
+					{
+						const int e = leaves[idx >> 2];
+						const int cnt = (int)((unsigned int)e >> 28), f0 = e & 0x0fffffff;
+						valid = (idx & 3) < cnt;
+						triSlot = f0 + (idx & 3);
+					}
+					testAndEmit(triSlot, valid);
+				}
+				numLeaves = 0;
+				__syncwarp();
 			}
 		}
 	}
@@ -429,50 +574,112 @@ __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, con
 		int bestK = -1;
 		float4 bestAxis = mk4(0, 0, 0);
 		bool separated = false;
-		for (int k = lane; k < total && !separated; k += 32)
+		// Exact-safe skip for the later rounds of hulls with many axes (same argument as satWarp, narrowphase.cu): along
+		// an oriented unit axis n (deltaC2 . n >= 0, the triangle lies "ahead" of B) the overlap is
+		//     min(maxT - minH, maxH - minT)  >=  min(maxT - c1.n + rB,  max_k(b_k . n) + c1.n - minT)
+		// with the triangle's projection exact (3 vertices), rB the inscribed radius of B and b_k the two vertices of B
+		// (relative to its centre c1) that reach furthest towards the triangle.  An axis whose bound exceeds the best
+		// depth of the previous rounds by more than supEps can neither separate nor become the strict minimum.
+		const bool tight = total > 32;
+		const float supEps = 1e-3f + 1e-6f * (fabsf(posA.x) + fabsf(posA.y) + fabsf(posA.z) + fabsf(posB.x) + fabsf(posB.y) + fabsf(posB.z));
+		float4 sup0 = mk4(0, 0, 0), sup1 = mk4(0, 0, 0);
+		if (tight)
 		{
-			float4 axis;
-			if (k < 5)
+			const float4 dirL = quatRotate(quatInverse(ornB), deltaC2);
+			const int nv = hB.numVertices < 64 ? hB.numVertices : 64;
+			int taken = -1;
+#pragma unroll 1
+			for (int kk = 0; kk < 2; kk++)
 			{
-				if (k == 1) continue;  // -normal: the oriented axis and its depth are identical to face 0's, never a strict minimum
-				axis = quatRotate(ornA, triN[k]);
+				float best = -FLT_MAX;
+				int bi = -1;
+				for (int i = lane; i < nv; i += 32)
+				{
+					if (i == taken) continue;
+					const float sc = dot3(__ldg(&a.vertices[hB.vertexOffset + i]), dirL);
+					if (sc > best)
+					{
+						best = sc;
+						bi = i;
+					}
+				}
+				warpArgMax(best, bi);
+				if (bi < 0) bi = 0;
+				const float4 sv = quatRotate(ornB, sub3(__ldg(&a.vertices[hB.vertexOffset + bi]), hB.localCenter));
+				if (kk == 0)
+					sup0 = sv;
+				else
+					sup1 = sv;
+				taken = bi;
 			}
-			else if (k < 5 + nFB)
+		}
+		float curMin = FLT_MAX;  // warp-wide best depth of the finished rounds
+		for (int base = 0; base < total; base += 32)
+		{
+			const int k = base + lane;
+			float d = FLT_MAX;
+			bool sepHere = false;
+			do
 			{
-				const b3b200_face* f = &a.faces[hB.faceOffset + (k - 5)];
-				if (__ldg(&f->pad1) != 0) continue;  // bitwise +-duplicate of an earlier face normal (flag set at registration)
-				axis = quatRotate(ornB, __ldg(reinterpret_cast<const float4*>(&f->plane)));
-			}
-			else
-			{
-				const int e = k - 5 - nFB;
-				const int e0 = e / nEB, e1 = e - e0 * nEB;
-				const float4 edgeA = e0 == 0 ? sub3(vA[1], vA[0]) : (e0 == 1 ? sub3(vA[2], vA[1]) : sub3(vA[0], vA[2]));
-				const float4 edge0World = quatRotate(ornA, edgeA);
-				const float4 edge1World = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
-				const float4 cr = cross3(edge0World, edge1World);
-				if (almostZero(cr)) continue;
-				axis = normalized3(cr);
-			}
-			if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
-			float minT, maxT, minH, maxH;
-			projectTri(vA, posA, ornA, axis, minT, maxT);
-			projectHull(hB, posB, ornB, axis, a.vertices, minH, maxH);
-			if (maxT < minH || maxH < minT)
+				if (k >= total) break;
+				float4 axis;
+				if (k < 5)
+				{
+					if (k == 1) break;  // -normal: the oriented axis and its depth are identical to face 0's, never a strict minimum
+					axis = quatRotate(ornA, triN[k]);
+				}
+				else if (k < 5 + nFB)
+				{
+					const b3b200_face* f = &a.faces[hB.faceOffset + (k - 5)];
+					if (__ldg(&f->pad1) != 0) break;  // bitwise +-duplicate of an earlier face normal (flag set at registration)
+					axis = quatRotate(ornB, __ldg(reinterpret_cast<const float4*>(&f->plane)));
+				}
+				else
+				{
+					const int e = k - 5 - nFB;
+					const int e0 = e / nEB, e1 = e - e0 * nEB;
+					const float4 edgeA = e0 == 0 ? sub3(vA[1], vA[0]) : (e0 == 1 ? sub3(vA[2], vA[1]) : sub3(vA[0], vA[2]));
+					const float4 edge0World = quatRotate(ornA, edgeA);
+					const float4 edge1World = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+					const float4 cr = cross3(edge0World, edge1World);
+					if (almostZero(cr)) break;
+					axis = normalized3(cr);
+				}
+				if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+				float minT, maxT, minH, maxH;
+				projectTri(vA, posA, ornA, axis, minT, maxT);
+				if (tight && curMin < FLT_MAX)
+				{
+					const float c1n = dot3(c1, axis);
+					const float l1 = fmaxf(dot3(sup0, axis), dot3(sup1, axis)) + c1n - minT;
+					const float l2 = maxT - c1n + hB.radius * (1.0f - 2e-4f);
+					if (fminf(l1, l2) > curMin + supEps) break;
+				}
+				projectHull(hB, posB, ornB, axis, a.vertices, minH, maxH);
+				if (maxT < minH || maxH < minT)
+				{
+					sepHere = true;
+					break;
+				}
+				const float d0 = maxT - minH, d1 = maxH - minT;
+				d = d0 < d1 ? d0 : d1;
+				if (d < bestD)
+				{
+					bestD = d;
+					bestK = k;
+					bestAxis = axis;
+				}
+			} while (false);
+			if (__any_sync(FULL, sepHere))
 			{
 				separated = true;
 				break;
 			}
-			const float d0 = maxT - minH, d1 = maxH - minT;
-			const float d = d0 < d1 ? d0 : d1;
-			if (d < bestD)
-			{
-				bestD = d;
-				bestK = k;
-				bestAxis = axis;
-			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) d = fminf(d, __shfl_xor_sync(FULL, d, o));
+			curMin = fminf(curMin, d);
 		}
-		if (__any_sync(FULL, separated)) continue;
+		if (separated) continue;
 		const int myK = bestK;
 		warpArgMin(bestD, bestK);
 		if (bestK < 0) continue;
@@ -723,7 +930,7 @@ int launchConcave(World* w)
 	a.contacts = w->dContacts.ptr;
 	a.maxContacts = w->cfg.maxContactCapacity;
 	a.maxItems = (int)w->dConcavePairs.cap;
-	concaveCullKernel<<<w->smCount * 4, 256, 0, s>>>(a, w->dConcavePairs.ptr);
+	concaveCullKernel<<<w->smCount * 8, CULL_WARPS * 32, 0, s>>>(a, reinterpret_cast<const int*>(w->dConcaveSurvivors.ptr), (int)(w->dConcaveSurvivors.cap * 4), w->dConcavePairs.ptr);
 	B3_LAUNCH_CHECK();
 	clampConcaveKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, a.maxItems);
 	B3_LAUNCH_CHECK();

@@ -25,6 +25,7 @@ enum Counter
 	CTR_CURSOR_SAT = 12,  // dynamic work distribution cursors of the warp-per-item kernels (12..14 are cleared together)
 	CTR_CURSOR_CLIP = 13,
 	CTR_CURSOR_CONCAVE = 14,
+	CTR_MESH_PAIRS = 15,  // broadphase pairs with a trimesh as A (listed by npCullKernel)
 	CTR_COUNT = 16
 };
 enum OverflowBits

@@ -782,7 +782,8 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 	}
 }
 
-__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems)
+__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems, int* __restrict__ meshPairs,
+															 int maxMeshPairs)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
 	const int lane = threadIdx.x & 31;
@@ -835,6 +836,14 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 							}
 						}
 					}
+				}
+				else if (meshPairs && typeA == B3B200_SHAPE_CONCAVE_TRIMESH &&
+						 (typeB == B3B200_SHAPE_CONVEX_HULL || typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS))
+				{
+					// trimesh (as A, b3BvhTraversal.h:35) x hull / compound: listed for concaveCullKernel, which then
+					// need not scan all pairs again
+					const unsigned int slot = atomicAdd(&a.ctr[CTR_MESH_PAIRS], 1u);
+					if (slot < (unsigned int)maxMeshPairs) meshPairs[slot] = p;
 				}
 			}
 		}
@@ -1317,7 +1326,7 @@ int launchNarrowphase(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
-	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 3 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 4 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors, CTR_MESH_PAIRS
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.pairsOut = w->bp.pairs.ptr;
@@ -1342,7 +1351,9 @@ int launchNarrowphase(World* w)
 		B3_LAUNCH_CHECK();
 	}
 	// the overlap list is not live yet: it doubles as the raw child-item queue of compound pairs
-	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr);
+	// (the survivor list of the trimesh path is not live yet either: it doubles as the list of trimesh pairs)
+	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->hasConcave ? reinterpret_cast<int*>(w->dConcaveSurvivors.ptr) : nullptr,
+														 w->hasConcave ? (int)(w->dConcaveSurvivors.cap * 4) : 0);
 	B3_LAUNCH_CHECK();
 	if (!w->childShapes.empty())
 	{

@@ -838,6 +838,15 @@ extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)
 	dst8[7] = (int)c[CTR_SURVIVORS];
 	return 0;
 }
+extern "C" int b3b200_get_work_counters(b3b200_world* w, int* dst, int n)
+{
+	W_CHECK(w);
+	if (!dst || n < 0 || n > CTR_COUNT) return B3B200_ERR_INVALID;
+	unsigned int c[CTR_COUNT];
+	B3_TRY(readCounters(w, c));
+	for (int i = 0; i < n; i++) dst[i] = (int)c[i];
+	return 0;
+}
 extern "C" int b3b200_enable_stage_timing(b3b200_world* w, int enable)
 {
 	if (!w) return B3B200_ERR_INVALID;
