@@ -297,8 +297,8 @@ class World:
         return out
 
     def work_counters(self):
-        out = np.zeros(16, np.int32)
-        check(self.L.b3b200_get_work_counters(self.h, ptr(out), 16), "get_work_counters")
+        out = np.zeros(24, np.int32)
+        check(self.L.b3b200_get_work_counters(self.h, ptr(out), 24), "get_work_counters")
         return out
 
     def pairs(self):

@@ -26,7 +26,8 @@ enum Counter
 	CTR_CURSOR_CLIP = 13,
 	CTR_CURSOR_CONCAVE = 14,
 	CTR_MESH_PAIRS = 15,  // broadphase pairs with a trimesh as A (listed by npCullKernel)
-	CTR_COUNT = 16
+	CTR_SMALL_ITEMS = 16,  // small x small hull items (thread-per-item kernel)
+	CTR_COUNT = 24
 };
 enum OverflowBits
 {
@@ -156,6 +157,7 @@ struct World
 	DevBuf<int4> dConcavePairs;  // (pair, triangle, child shape of B or -1, 0) work items of the concave path
 	DevBuf<int4> dConcaveSurvivors;  // ... that passed the quick reject
 	DevBuf<int4> dSurvivors;     // work items (pair, childA, childB, 0) that passed the quick SAT reject
+	DevBuf<int4> dSmallItems;    // ... of which both hulls are small (boxes, tetrahedra): thread-per-item kernel
 	DevBuf<int4> dOverlapPairs;  // work items with a penetrating SAT result
 	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes
 

@@ -686,6 +686,274 @@ B3_D void clipWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int sha
 	if (lane == 0 && pairIndex >= 0) a.pairsOut[pairIndex].z = (int)slot;
 }
 
+// ---------------------------------------------------------------- small pairs: one THREAD per item
+// Pairs of small hulls (boxes, tetrahedra, the box children of compounds: <= 8 vertices, <= 6 faces, <= 6 edge
+// directions each, i.e. at most 48 axes over 16 vertices) leave most lanes of a warp idle in satKernel / clipKernel.
+// They are queued separately and handled like the reference does it on the CPU: one thread runs b3FindSeparatingAxis,
+// b3ClipHullAgainstHull and b3ReduceContacts serially, in the reference's statement order (shared/
+// b3FindSeparatingAxis.h:57-195, shared/b3ContactConvexConvexSAT.h:20-266, 270-405, shared/b3ReduceContacts.h:4-87),
+// so that 32 pairs share a warp.
+constexpr int SMALL_VERTS = 8, SMALL_FACES = 6, SMALL_EDGES = 6;
+constexpr int SMALL_POLY = 16;  // a face of <= 8 vertices clipped by <= 8 planes
+
+B3_D bool isSmallHull(const NpArgs& a, int shape)
+{
+	const HullRef h = loadHull(a.convex, shape);
+	return h.numVertices <= SMALL_VERTS && h.numFaces <= SMALL_FACES && h.numUniqueEdges <= SMALL_EDGES;
+}
+
+// b3ClipFace (shared/b3ContactConvexConvexSAT.h:20-68)
+B3_D int clipFaceSerial(const float4* in, int numIn, const float4& n, float eq, float4* out)
+{
+	int numOut = 0;
+	if (numIn < 2) return 0;
+	float4 first = in[numIn - 1];
+	float ds = dot3(n, first) + eq;
+	for (int ve = 0; ve < numIn; ve++)
+	{
+		const float4 end = in[ve];
+		const float de = dot3(n, end) + eq;
+		if (ds < 0)
+		{
+			if (de < 0)
+			{
+				if (numOut < SMALL_POLY) out[numOut++] = end;
+			}
+			else if (numOut < SMALL_POLY)
+				out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+		}
+		else if (de < 0)
+		{
+			if (numOut < SMALL_POLY) out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+			if (numOut < SMALL_POLY) out[numOut++] = end;
+		}
+		first = end;
+		ds = de;
+	}
+	return numOut;
+}
+
+B3_D void smallPairThread(const NpArgs& a, const int4 it)
+{
+	const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+	Side A, B;
+	if (!resolveSide(a, bodyA, it.y, A) || !resolveSide(a, bodyB, it.z, B)) return;
+	float4 posA = A.pos, posB = B.pos;
+	posA.w = 0.f;
+	posB.w = 0.f;
+	const float4 ornA = A.orn, ornB = B.orn;
+	const HullRef hA = loadHull(a.convex, A.shape), hB = loadHull(a.convex, B.shape);
+
+	// ---- b3FindSeparatingAxis
+	const float4 c0 = transformPoint(hA.localCenter, posA, ornA);
+	const float4 c1 = transformPoint(hB.localCenter, posB, ornB);
+	const float4 deltaC2 = sub3(c0, c1);
+	float dmin = FLT_MAX;
+	float4 sep = mk4(0, 0, 0);
+#pragma unroll 1
+	for (int side = 0; side < 2; side++)
+	{
+		const HullRef& h = side ? hB : hA;
+		const float4 orn = side ? ornB : ornA;
+		for (int i = 0; i < h.numFaces; i++)
+		{
+			const b3b200_face* f = &a.faces[h.faceOffset + i];
+			if (__ldg(&f->pad1) != 0) continue;  // +-duplicate of an earlier normal: identical depth, never the strict minimum
+			float4 n = quatRotate(orn, __ldg(reinterpret_cast<const float4*>(&f->plane)));
+			if (dot3(deltaC2, n) < 0) n = mk4(n.x * -1.f, n.y * -1.f, n.z * -1.f);
+			float d;
+			if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, n, a.vertices, d)) return;
+			if (d < dmin)
+			{
+				dmin = d;
+				sep = n;
+			}
+		}
+	}
+	{
+		float4 edgeB[SMALL_EDGES];
+		for (int e1 = 0; e1 < hB.numUniqueEdges; e1++) edgeB[e1] = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+		for (int e0 = 0; e0 < hA.numUniqueEdges; e0++)
+		{
+			const float4 edge0World = quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
+			for (int e1 = 0; e1 < hB.numUniqueEdges; e1++)
+			{
+				float4 cr = cross3(edge0World, edgeB[e1]);
+				if (almostZero(cr)) continue;
+				cr = normalized3(cr);
+				if (dot3(deltaC2, cr) < 0) cr = mk4(cr.x * -1.f, cr.y * -1.f, cr.z * -1.f);
+				float dist;
+				if (!testSepAxis(hA, hB, posA, ornA, posB, ornB, cr, a.vertices, dist)) return;
+				if (dist < dmin)
+				{
+					dmin = dist;
+					sep = cr;
+				}
+			}
+		}
+	}
+	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
+
+	// ---- b3ClipHullHullSingle: orientations round-trip through b3Transform (:323-337)
+	const float4 ornA2 = quatFromMat(matFromQuat(ornA)), ornB2 = quatFromMat(matFromQuat(ornB));
+	float4 bufA[SMALL_POLY], bufB[SMALL_POLY];
+	// b3ClipHullAgainstHull: incident face of B
+	int closestFaceB = -1;
+	{
+		float dmax = -FLT_MAX;
+		for (int f = 0; f < hB.numFaces; f++)
+		{
+			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+			const float d = dot3(quatRotate(ornB2, normal), sep);
+			if (d > dmax)
+			{
+				dmax = d;
+				closestFaceB = f;
+			}
+		}
+	}
+	if (closestFaceB < 0) return;
+	int numVertsIn;
+	{
+		const b3b200_face* polyB = &a.faces[hB.faceOffset + closestFaceB];
+		const int idxOff = __ldg(&polyB->indexOffset);
+		numVertsIn = __ldg(&polyB->numIndices);
+		if (numVertsIn > SMALL_POLY) numVertsIn = SMALL_POLY;
+		for (int e = 0; e < numVertsIn; e++) bufA[e] = transformPoint(__ldg(&a.vertices[hB.vertexOffset + __ldg(&a.indices[idxOff + e])]), posB, ornB2);
+	}
+	// b3ClipFaceAgainstHull: reference face of A
+	int closestFaceA = -1;
+	{
+		float dm = FLT_MAX;
+		for (int f = 0; f < hA.numFaces; f++)
+		{
+			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
+			const float d = dot3(quatRotate(ornA2, mk4(normal.x, normal.y, normal.z)), sep);
+			if (d < dm)
+			{
+				dm = d;
+				closestFaceA = f;
+			}
+		}
+	}
+	if (closestFaceA < 0) return;
+	const b3b200_face* polyA = &a.faces[hA.faceOffset + closestFaceA];
+	const float4 planeA = __ldg(reinterpret_cast<const float4*>(&polyA->plane));
+	const int idxOffA = __ldg(&polyA->indexOffset);
+	const int numVerticesA = __ldg(&polyA->numIndices);
+	const float4 worldPlaneAnormal1 = quatRotate(ornA2, mk4(planeA.x, planeA.y, planeA.z));
+	float4* pIn = bufA;
+	float4* pOut = bufB;
+	for (int e0 = 0; e0 < numVerticesA; e0++)
+	{
+		const float4 va = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + e0])]);
+		const float4 vb = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + ((e0 + 1) % numVerticesA)])]);
+		const float4 worldEdge0 = quatRotate(ornA2, sub3(va, vb));
+		const float4 planeNormalWS = neg3(cross3(worldEdge0, worldPlaneAnormal1));
+		const float4 worldA1 = transformPoint(va, posA, ornA2);
+		const float planeEqWS = -dot3(worldA1, planeNormalWS);
+		const int numOut = clipFaceSerial(pIn, numVertsIn, planeNormalWS, planeEqWS, pOut);
+		float4* t = pOut;
+		pOut = pIn;
+		pIn = t;
+		numVertsIn = numOut;
+	}
+	int numContactsOut = 0;
+	{
+		const float planeEqWS = planeA.w - dot3(worldPlaneAnormal1, posA);
+		for (int i = 0; i < numVertsIn; i++)
+		{
+			float4 pt = pIn[i];
+			float depth = dot3(worldPlaneAnormal1, pt) + planeEqWS;
+			if (depth <= a.clipMin) depth = a.clipMin;
+			if (depth <= a.clipMax)
+			{
+				pt.w = depth;
+				pOut[numContactsOut++] = pt;
+			}
+		}
+	}
+	if (numContactsOut <= 0) return;
+	const float4* pts = pOut;
+
+	// ---- b3ReduceContacts
+	int idx[4] = {0, 1, 2, 3};
+	int numPoints = numContactsOut;
+	if (numContactsOut > 4)
+	{
+		const int nP = numContactsOut;
+		float4 center = mk4(0, 0, 0);
+		for (int i = 0; i < nP; i++) center = add3(center, pts[i]);
+		center = scale3(center, 1.0f / (float)nP);
+		const float4 aVector = sub3(pts[0], center);
+		float4 u = cross3(sep, aVector);
+		float4 v = cross3(sep, u);
+		u = normalized3(u);
+		v = normalized3(v);
+		float minW = FLT_MAX;
+		int minIndex = -1;
+		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
+		for (int ie = 0; ie < nP; ie++)
+		{
+			if (pts[ie].w < minW)
+			{
+				minW = pts[ie].w;
+				minIndex = ie;
+			}
+			const float4 r = sub3(pts[ie], center);
+			float f = dot3(u, r);
+			if (f < m0)
+			{
+				m0 = f;
+				idx[0] = ie;
+			}
+			f = dot3(neg3(u), r);
+			if (f < m1)
+			{
+				m1 = f;
+				idx[1] = ie;
+			}
+			f = dot3(v, r);
+			if (f < m2)
+			{
+				m2 = f;
+				idx[2] = ie;
+			}
+			f = dot3(neg3(v), r);
+			if (f < m3)
+			{
+				m3 = f;
+				idx[3] = ie;
+			}
+		}
+		if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
+		numPoints = 4;
+	}
+
+	// ---- append
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return;
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	for (int i = 0; i < 4; i++) cw[i] = i < numPoints ? pts[idx[i]] : mk4(0, 0, 0, 0);
+	cw[4] = mk4(sep.x, sep.y, sep.z, (float)numPoints);
+	int4 t;
+	t.x = (int)(0u | (45874u << 16));
+	t.y = 0;
+	t.z = A.invMass == 0.f ? -bodyA : bodyA;
+	t.w = B.invMass == 0.f ? -bodyB : bodyB;
+	reinterpret_cast<int4*>(c)[5] = t;
+	reinterpret_cast<int4*>(c)[6] = make_int4(it.y, it.z, 0, 0);
+	a.pairsOut[it.x].z = (int)slot;
+}
+
+__global__ void __launch_bounds__(128) smallPairKernel(NpArgs a, const int4* __restrict__ smallItems)
+{
+	int numItems = (int)a.ctr[CTR_SMALL_ITEMS];
+	if (numItems > a.maxWorkItems) numItems = a.maxWorkItems;
+	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < numItems; s += gridDim.x * blockDim.x) smallPairThread(a, smallItems[s]);
+}
+
 // ---------------------------------------------------------------- stage 1: quick reject
 // One THREAD per broadphase pair.  Convex-convex pairs and every child pair of compound shapes
 // (compound x compound, compound x convex) become work items (pair, childA, childB).  For each
@@ -744,6 +1012,28 @@ B3_D void pushItem(const NpArgs& a, int4* __restrict__ items, int p, int ca, int
 	if (slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, ca, cb, 0);
 }
 
+// warp-aggregated append of the kept items: small x small hull pairs go to the thread-per-item list, the rest to the
+// warp-per-item list
+B3_D void pushClassified(const NpArgs& a, bool keep, bool small, const int4& it, int4* __restrict__ items, int4* __restrict__ smallItems, int lane)
+{
+	const unsigned int mg = __ballot_sync(FULL, keep && !small), ms = __ballot_sync(FULL, keep && small);
+	const unsigned int lt = (1u << lane) - 1u;
+	if (mg)
+	{
+		unsigned int slot = 0;
+		if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(mg));
+		slot = __shfl_sync(FULL, slot, 0) + __popc(mg & lt);
+		if (keep && !small && slot < (unsigned int)a.maxWorkItems) items[slot] = it;
+	}
+	if (ms)
+	{
+		unsigned int slot = 0;
+		if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SMALL_ITEMS], (unsigned int)__popc(ms));
+		slot = __shfl_sync(FULL, slot, 0) + __popc(ms & lt);
+		if (keep && small && slot < (unsigned int)a.maxWorkItems) smallItems[slot] = it;
+	}
+}
+
 // conservative world-space bounding sphere of one side: centre = hull centre, radius = circumscribed radius about it
 // (stored in the convex entry's unused word at registration, world.cu)
 B3_D float4 boundSphere(const NpArgs& a, const Side& s, float& radius)
@@ -754,7 +1044,8 @@ B3_D float4 boundSphere(const NpArgs& a, const Side& s, float& radius)
 }
 
 // stage 1b: the exact quick reject for the raw child items of compound pairs, one THREAD per item
-__global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items)
+__global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items,
+																  int4* __restrict__ smallItems)
 {
 	int numRaw = (int)a.ctr[CTR_COMPOUND_PAIRS];
 	if (numRaw > a.maxWorkItems) numRaw = a.maxWorkItems;
@@ -762,35 +1053,31 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 	for (int base = blockIdx.x * CULL_THREADS; base < numRaw; base += gridDim.x * CULL_THREADS)
 	{
 		const int r = base + threadIdx.x;
-		bool keep = false;
+		bool keep = false, small = false;
 		int4 it = make_int4(0, 0, 0, 0);
 		if (r < numRaw)
 		{
 			it = rawItems[r];
 			Side A, B;
-			if (resolveSide(a, a.pairs[it.x].x, it.y, A) && resolveSide(a, a.pairs[it.x].y, it.z, B)) keep = quickTest(a, A, B);
+			if (resolveSide(a, a.pairs[it.x].x, it.y, A) && resolveSide(a, a.pairs[it.x].y, it.z, B))
+			{
+				keep = quickTest(a, A, B);
+				small = keep && isSmallHull(a, A.shape) && isSmallHull(a, B.shape);
+			}
 		}
-		const unsigned int m = __ballot_sync(FULL, keep);
-		if (m)
-		{
-			unsigned int slot = 0;
-			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(m));
-			slot = __shfl_sync(FULL, slot, 0);
-			slot += __popc(m & ((1u << lane) - 1u));
-			if (keep && slot < (unsigned int)a.maxWorkItems) items[slot] = it;
-		}
+		pushClassified(a, keep, small, it, items, smallItems, lane);
 	}
 }
 
 __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems, int* __restrict__ meshPairs,
-															 int maxMeshPairs)
+															 int maxMeshPairs, int4* __restrict__ smallItems)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
 	const int lane = threadIdx.x & 31;
 	for (int base = blockIdx.x * CULL_THREADS; base < numPairs; base += gridDim.x * CULL_THREADS)
 	{
 		const int p = base + threadIdx.x;
-		bool keep = false;
+		bool keep = false, small = false;
 		if (p < numPairs)
 		{
 			const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
@@ -801,7 +1088,11 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 				if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_CONVEX_HULL)
 				{
 					Side A, B;
-					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B)) keep = quickTest(a, A, B);
+					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B))
+					{
+						keep = quickTest(a, A, B);
+						small = keep && isSmallHull(a, A.shape) && isSmallHull(a, B.shape);
+					}
 				}
 				else if ((typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeA == B3B200_SHAPE_CONVEX_HULL) &&
 						 (typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeB == B3B200_SHAPE_CONVEX_HULL))
@@ -847,15 +1138,7 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 				}
 			}
 		}
-		const unsigned int m = __ballot_sync(FULL, keep);
-		if (m)
-		{
-			unsigned int slot = 0;
-			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(m));
-			slot = __shfl_sync(FULL, slot, 0);
-			slot += __popc(m & ((1u << lane) - 1u));
-			if (keep && slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, -1, -1, 0);
-		}
+		pushClassified(a, keep, small, make_int4(p, -1, -1, 0), items, smallItems, lane);
 	}
 }
 
@@ -1326,6 +1609,7 @@ int launchNarrowphase(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SMALL_ITEMS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 4 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors, CTR_MESH_PAIRS
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
@@ -1353,13 +1637,15 @@ int launchNarrowphase(World* w)
 	// the overlap list is not live yet: it doubles as the raw child-item queue of compound pairs
 	// (the survivor list of the trimesh path is not live yet either: it doubles as the list of trimesh pairs)
 	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->hasConcave ? reinterpret_cast<int*>(w->dConcaveSurvivors.ptr) : nullptr,
-														 w->hasConcave ? (int)(w->dConcaveSurvivors.cap * 4) : 0);
+														 w->hasConcave ? (int)(w->dConcaveSurvivors.cap * 4) : 0, w->dSmallItems.ptr);
 	B3_LAUNCH_CHECK();
 	if (!w->childShapes.empty())
 	{
-		npChildCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dSurvivors.ptr);
+		npChildCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dSurvivors.ptr, w->dSmallItems.ptr);
 		B3_LAUNCH_CHECK();
 	}
+	smallPairKernel<<<w->smCount * 16, 128, 0, s>>>(a, w->dSmallItems.ptr);
+	B3_LAUNCH_CHECK();
 	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[0], s));  // stage_timings()[7] = this kernel alone
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();

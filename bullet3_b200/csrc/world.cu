@@ -570,6 +570,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	// work items: one per convex pair + child pairs of compounds (b3Config::m_compoundPairCapacity)
 	const size_t nItems = (size_t)std::max(w->cfg.maxBroadphasePairs, 1) + (w->childShapes.empty() ? 0 : (size_t)std::max(w->cfg.compoundPairCapacity, 0));
 	B3_TRY(w->dSurvivors.reserve(nItems));
+	B3_TRY(w->dSmallItems.reserve(nItems));
 	B3_TRY(w->dOverlapPairs.reserve(nItems));
 	B3_TRY(w->dOverlapSep.reserve(nItems));
 	w->hasPlanes = false;

@@ -148,9 +148,9 @@ int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* nu
 /* counters of the last step: [0]=pairs [1]=contacts [2]=batches [3]=colouring rounds
  * [4]=overflow flags [5]=raw compound child pairs [6]=raw (pair, triangle, child) items [7]=SAT work items */
 int b3b200_get_counters(b3b200_world* w, int* dst8);
-/* all 16 raw device counters of the last step (diagnostics; no reference counterpart): [0..7] as above except [7] =
+/* the raw device counters of the last step (n <= 24) (diagnostics; no reference counterpart): [0..7] as above except [7] =
  * uncoloured contacts, [8] = SAT work items, [9] = overlapping items, [10] = halo records, [11] = triangle items that
- * passed the quick reject, [12..14] = work cursors */
+ * passed the quick reject, [12..14] = work cursors, [15] = trimesh pairs, [16] = small x small hull items */
 int b3b200_get_work_counters(b3b200_world* w, int* dst, int n);
 /* ms per stage of the last step when timing is enabled:
  * [0]=aabbs [1]=broadphase [2]=narrowphase [3]=solver setup [4]=solver iterations [5]=integrate [6]=total */
