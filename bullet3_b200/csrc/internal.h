@@ -166,6 +166,7 @@ struct World
 	DevBuf<unsigned long long> dBodyMask;  // colours used per body (2 words / body)
 	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body
 	DevBuf<int> dContactColour;           // colour per contact, -1 = none yet
+	DevBuf<unsigned int> dColourList;     // 2 x maxContacts: compacted uncoloured contacts (ping-pong)
 	DevBuf<unsigned int> dBatchCount;     // per colour (B3_MAX_BATCHES+1)
 	DevBuf<unsigned int> dBatchOffset;    // exclusive scan
 	DevBuf<unsigned int> dBatchCursor;

@@ -36,6 +36,7 @@ constexpr int SOLVER_THREADS = 512;
 constexpr int TAIL_ROWS = SOLVER_THREADS;  // batches up to one row per thread are cheaper to solve in one CTA (measured 1.7 us
                                            // per phase) than to pay a grid barrier for (3.5 us); two rows per thread cost 5.5 us
 constexpr int MAX_ROUNDS = 1024;
+constexpr int TAIL_COLOUR = 2048;  // colouring rounds with at most this many contacts left run in CTA 0 alone
 
 // ---------------------------------------------------------------- grid barrier
 // One monotonically increasing arrival counter (zeroed by the host before the launch).
@@ -44,6 +45,10 @@ constexpr int MAX_ROUNDS = 1024;
 // extends the ordering to the rest of the CTA (PTX memory model: causality order through
 // the CTA barrier, release/acquire are cumulative).  All CTAs are co-resident
 // (cooperative launch).
+// MEASURED CAVEAT: the acquire by thread 0 does not stop the OTHER threads' plain loads from hitting
+// stale lines in the SM's L1 (body colour masks read with ld.global gave invalid colourings in ~30 %
+// of the runs once the rounds became short).  Every value another CTA may have written during this
+// kernel is therefore read with ld.global.cg (__ldcg), volatile or an atomic -- never a plain load.
 struct GridBarrier
 {
 	unsigned int* counter;
@@ -128,6 +133,8 @@ struct SetupArgs
 	unsigned int* batchOffset;  // MAX_BATCHES + 1
 	unsigned int* batchCursor;  // MAX_BATCHES
 	unsigned int* remaining;    // MAX_ROUNDS
+	unsigned int* colourList;   // 2 x colourListStride: uncoloured contacts of the current / next round
+	int colourListStride;
 	unsigned int* bar;
 	int numBodies;
 	int staticIdx;
@@ -259,6 +266,83 @@ B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict_
 	reinterpret_cast<int4*>(dst)[10] = tail;
 }
 
+// One colouring round, step 1: an uncoloured contact posts its priority on its dynamic bodies.
+B3_D void colourClaim(const SetupArgs& s, int c)
+{
+	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
+	const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
+	const int a = abs(ids.z), b = abs(ids.w);
+	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
+	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
+	const unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
+	if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
+	if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
+}
+
+// Step 2: the contact that is top on both of its bodies takes the lowest colour free on both.  Returns true when the
+// contact stays uncoloured for the next round.
+B3_D bool colourTry(const SetupArgs& s, int c)
+{
+	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
+	const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
+	const int a = abs(ids.z), b = abs(ids.w);
+	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
+	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
+	const unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
+	volatile unsigned long long* vp = s.bodyPrio;
+	const bool top = (aStatic || vp[a] == prio) && (bStatic || vp[b] == prio);
+	if (!top) return true;
+	// (masks written by other CTAs in earlier rounds: read through L2)
+	unsigned long long m0 = 0ull, m1 = 0ull;
+	if (!aStatic)
+	{
+		m0 |= __ldcg(&s.bodyMask[2 * a]);
+		m1 |= __ldcg(&s.bodyMask[2 * a + 1]);
+	}
+	if (!bStatic)
+	{
+		m0 |= __ldcg(&s.bodyMask[2 * b]);
+		m1 |= __ldcg(&s.bodyMask[2 * b + 1]);
+	}
+	int colour = -2;
+	if (~m0)
+		colour = __ffsll((long long)~m0) - 1;
+	else if (~m1)
+		colour = 64 + __ffsll((long long)~m1) - 1;
+	if (colour < 0)
+	{
+		// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
+		// ("batchIdx>=B3_MAX_NUM_BATCHES", b3GpuPgsContactSolver.cpp:1497-1502); here the
+		// contact is left out of this step's solve and the overflow flag is raised.
+		s.contactColour[c] = -2;
+		if (!aStatic) s.bodyPrio[a] = 0ull;
+		if (!bStatic) s.bodyPrio[b] = 0ull;
+		atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+		return false;
+	}
+	const unsigned long long bit = 1ull << (colour & 63);
+	const int word = colour >> 6;
+	if (!aStatic)
+	{
+		__stcg(&s.bodyMask[2 * a + word], __ldcg(&s.bodyMask[2 * a + word]) | bit);
+		s.bodyPrio[a] = 0ull;
+	}
+	if (!bStatic)
+	{
+		__stcg(&s.bodyMask[2 * b + word], __ldcg(&s.bodyMask[2 * b + word]) | bit);
+		s.bodyPrio[b] = 0ull;
+	}
+	s.contactColour[c] = colour;
+	s.contacts[c].batchIdx = colour;
+	atomicAdd(&s.batchCount[colour], 1u);
+	return false;
+}
+
+#ifdef B3_SETUP_TIMING
+#define B3_PROBE(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); printf("setup %s %llu round %d\n", tag, t, round); } } while (0)
+#else
+#define B3_PROBE(tag)
+#endif
 __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 {
 	GridBarrier bar;
@@ -266,6 +350,8 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int nContacts = (int)s.ctr[CTR_CONTACTS];
+	int round = 0;
+	B3_PROBE("start");
 
 	// ---- phase 0: clear
 	for (int i = tid; i < s.numBodies; i += stride)
@@ -283,93 +369,78 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	for (int i = tid; i < MAX_ROUNDS; i += stride) s.remaining[i] = 0;
 	bar.sync();
 
+	B3_PROBE("cleared");
 	// ---- phase 1: colouring rounds
-	int round = 0;
+	// Round 0 walks all contacts; every later round walks the compacted list of the contacts the previous round left
+	// uncoloured (ping-pong halves of colourList; remaining[round] is both the list length and the stop criterion).
+	// Once the list is short (<= TAIL_COLOUR) CTA 0 finishes the remaining rounds alone between __syncthreads():
+	// two grid barriers per round cost more than such a round.
+	int count = nContacts;
+	const unsigned int* cur = nullptr;
+	const int lane = threadIdx.x & 31;
+	__shared__ unsigned int sNext;
 	for (; round < MAX_ROUNDS; round++)
 	{
-		// claim
-		for (int c = tid; c < nContacts; c += stride)
-		{
-			if (s.contactColour[c] != -1) continue;
-			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
-			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
-			const int a = abs(ids.z), b = abs(ids.w);
-			const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
-			const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
-			unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
-			if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
-			if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
-		}
+		for (int i = tid; i < count; i += stride) colourClaim(s, cur ? (int)__ldcg(&cur[i]) : i);
 		bar.sync();
-		// colour
-		unsigned int left = 0;
-		for (int c = tid; c < nContacts; c += stride)
+		unsigned int* nxt = s.colourList + (size_t)(round & 1) * (size_t)s.colourListStride;
+		for (int base = tid - lane; base < count; base += stride)
 		{
-			if (s.contactColour[c] != -1) continue;
-			const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
-			const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
-			const int a = abs(ids.z), b = abs(ids.w);
-			const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
-			const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
-			unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
-			volatile unsigned long long* vp = s.bodyPrio;
-			bool top = (aStatic || vp[a] == prio) && (bStatic || vp[b] == prio);
-			if (!top)
+			const int i = base + lane;
+			const int c = i < count ? (cur ? (int)__ldcg(&cur[i]) : i) : 0;
+			const bool left = i < count && colourTry(s, c);
+			// the still uncoloured contacts of this warp go to the next round's list
+			const unsigned int m = __ballot_sync(0xffffffffu, left);
+			if (m)
 			{
-				left++;
-				continue;
+				unsigned int slot = 0;
+				if (lane == 0) slot = atomicAdd(&s.remaining[round], (unsigned int)__popc(m));
+				slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+				if (left) nxt[slot] = (unsigned int)c;
 			}
-			unsigned long long m0 = 0ull, m1 = 0ull;
-			if (!aStatic)
-			{
-				m0 |= s.bodyMask[2 * a];
-				m1 |= s.bodyMask[2 * a + 1];
-			}
-			if (!bStatic)
-			{
-				m0 |= s.bodyMask[2 * b];
-				m1 |= s.bodyMask[2 * b + 1];
-			}
-			int colour;
-			if (~m0)
-				colour = __ffsll((long long)~m0) - 1;
-			else if (~m1)
-				colour = 64 + __ffsll((long long)~m1) - 1;
-			else
-			{
-				// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
-				// ("batchIdx>=B3_MAX_NUM_BATCHES", b3GpuPgsContactSolver.cpp:1497-1502); here the
-				// contact is left out of this step's solve and the overflow flag is raised.
-				s.contactColour[c] = -2;
-				if (!aStatic) s.bodyPrio[a] = 0ull;
-				if (!bStatic) s.bodyPrio[b] = 0ull;
-				atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-				continue;
-			}
-			unsigned long long bit = 1ull << (colour & 63);
-			int word = colour >> 6;
-			if (!aStatic)
-			{
-				s.bodyMask[2 * a + word] |= bit;
-				s.bodyPrio[a] = 0ull;
-			}
-			if (!bStatic)
-			{
-				s.bodyMask[2 * b + word] |= bit;
-				s.bodyPrio[b] = 0ull;
-			}
-			s.contactColour[c] = colour;
-			s.contacts[c].batchIdx = colour;
-			atomicAdd(&s.batchCount[colour], 1u);
 		}
-		// block-reduce `left`
-		left = __reduce_add_sync(0xffffffffu, left);
-		if ((threadIdx.x & 31) == 0 && left) atomicAdd(&s.remaining[round], left);
 		bar.sync();
 		volatile unsigned int* vr = s.remaining;
-		if (vr[round] == 0) break;
+		count = (int)vr[round];
+		cur = nxt;
+		if (count == 0) break;
+		if (count <= TAIL_COLOUR)
+		{
+			if (blockIdx.x == 0)
+			{
+				while (count > 0 && round + 1 < MAX_ROUNDS)
+				{
+					round++;
+					for (int i = threadIdx.x; i < count; i += blockDim.x) colourClaim(s, (int)__ldcg(&cur[i]));
+					if (threadIdx.x == 0) sNext = 0;
+					__syncthreads();
+					nxt = s.colourList + (size_t)(round & 1) * (size_t)s.colourListStride;
+					for (int base = (int)threadIdx.x - lane; base < count; base += blockDim.x)
+					{
+						const int i = base + lane;
+						const int c = i < count ? (int)__ldcg(&cur[i]) : 0;
+						const bool left = i < count && colourTry(s, c);
+						const unsigned int m = __ballot_sync(0xffffffffu, left);
+						if (m)
+						{
+							unsigned int slot = 0;
+							if (lane == 0) slot = atomicAdd(&sNext, (unsigned int)__popc(m));
+							slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+							if (left) nxt[slot] = (unsigned int)c;
+						}
+					}
+					__syncthreads();
+					count = (int)sNext;
+					cur = nxt;
+					__syncthreads();
+				}
+			}
+			bar.sync();
+			break;
+		}
 	}
 
+	B3_PROBE("coloured");
 	// ---- phase 2: batch offsets (one warp)
 	if (blockIdx.x == 0 && threadIdx.x < 32)
 	{
@@ -379,7 +450,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		{
 			// every batch is padded to a multiple of 32 slots, so that a warp-row of the iteration
 			// kernels never straddles two batches (padding slots are marked invalid below)
-			const unsigned int raw = s.batchCount[base + threadIdx.x];
+			const unsigned int raw = __ldcg(&s.batchCount[base + threadIdx.x]);  // cross-CTA data after a grid barrier: always through L2
 			unsigned int v = (raw + 31u) & ~31u;
 			unsigned int incl = v;
 #pragma unroll
@@ -402,12 +473,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	}
 	bar.sync();
 
+	B3_PROBE("offsets");
 	// ---- phase 3: contact -> constraint rows, written in batch order
 	for (int k = tid; k < MAX_BATCHES * 32; k += stride)
 	{
 		const int bch = k >> 5;
-		const unsigned int slot = s.batchOffset[bch] + s.batchCount[bch] + (unsigned int)(k & 31);
-		if (slot < s.batchOffset[bch + 1])
+		const unsigned int slot = __ldcg(&s.batchOffset[bch]) + __ldcg(&s.batchCount[bch]) + (unsigned int)(k & 31);
+		if (slot < __ldcg(&s.batchOffset[bch + 1]))
 		{
 			float4* dw = reinterpret_cast<float4*>(&s.constraints[slot]);
 			dw[6] = mk4(0, 0, 0, 0);
@@ -422,11 +494,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	}
 	for (int c = tid; c < nContacts; c += stride)
 	{
-		int colour = s.contactColour[c];
+		int colour = __ldcg(&s.contactColour[c]);
 		if (colour < 0) continue;
-		unsigned int slot = s.batchOffset[colour] + atomicAdd(&s.batchCursor[colour], 1u);
+		unsigned int slot = __ldcg(&s.batchOffset[colour]) + atomicAdd(&s.batchCursor[colour], 1u);
 		buildConstraint(s, &s.contacts[c], colour, &s.constraints[slot]);
 	}
+	B3_PROBE("built(block0 thread0 only)");
 }
 
 // ---------------------------------------------------------------- iterations
@@ -990,6 +1063,8 @@ int launchSolverSetup(World* w)
 	s.batchOffset = w->dBatchOffset.ptr;
 	s.batchCursor = w->dBatchCursor.ptr;
 	s.remaining = w->dBodyCount.ptr;  // MAX_ROUNDS words, see World::init
+	s.colourList = w->dColourList.ptr;
+	s.colourListStride = (int)(w->dColourList.cap / 2);
 	s.bar = w->dGridBarrier.ptr;
 	s.numBodies = w->numBodies;
 	s.staticIdx = w->static0Index;

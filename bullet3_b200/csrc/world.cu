@@ -587,6 +587,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	}
 	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
 	B3_TRY(w->dContactColour.reserve(nc));
+	B3_TRY(w->dColourList.reserve(2 * nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));
 	B3_TRY(w->dBodyPrio.reserve(2 * nb));
 	B3_TRY(w->dBatchCount.reserve(MAX_BATCHES + 1));
