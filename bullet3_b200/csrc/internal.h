@@ -145,6 +145,7 @@ struct World
 	DevBuf<int> dCollidableIdx;
 	DevBuf<int> dGhostGlobalId;  // slab mode: global id mirrored by each ghost slot (-1 = parked / owned)
 	bool soaDirty = false;  // SoA is newer than AoS
+	bool hostBodiesStale = false;  // the host mirror `bodies` is older than the device AoS (after b3b200_write_bodies)
 	bool hasConcave = false;  // any SHAPE_CONCAVE_TRIMESH collidable registered (enables the concave kernels)
 	bool hasPlanes = false;  // any SHAPE_PLANE collidable registered (enables the primitive-contact kernel)
 

@@ -544,6 +544,14 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	W_CHECK(w);
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaStreamSynchronize(s));
+	if (w->hostBodiesStale && w->numBodies > 0 && w->dBodiesAoS.ptr)
+	{
+		// bodies written with b3b200_write_bodies live on the device only: bring them back before the tables are re-sent
+		if (w->soaDirty) B3_TRY(launchUnpackSoA(w));
+		B3_CUDA_CHECK(cudaMemcpyAsync(w->bodies.data(), w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * (size_t)w->numBodies, cudaMemcpyDeviceToHost, s));
+		B3_CUDA_CHECK(cudaStreamSynchronize(s));
+	}
+	w->hostBodiesStale = false;
 	w->numBodies = (int)w->bodies.size();
 	const size_t nb = std::max(w->numBodies, 1);
 	B3_TRY(uploadVec(w->dCollidables, w->collidables, 0, s));
@@ -648,7 +656,8 @@ extern "C" int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src
 {
 	W_UPLOADED(w);
 	if (!src || n != w->numBodies) return B3B200_ERR_INVALID;
-	memcpy(w->bodies.data(), src, sizeof(b3b200_rigid_body) * n);
+	// the host mirror (get_table) is refreshed lazily: copying 80 B x N on the host here cost more than the transfer
+	w->hostBodiesStale = true;
 	B3_CUDA_CHECK(cudaMemcpyAsync(w->dBodiesAoS.ptr, src, sizeof(b3b200_rigid_body) * n, cudaMemcpyHostToDevice, w->stream));
 	B3_TRY(launchPackSoA(w));
 	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
@@ -923,6 +932,15 @@ extern "C" int b3b200_get_table(b3b200_world* w, int which, void* dst, int capac
 		case B3B200_TBL_BVH_SUBTREES:
 			return copyTable(w->bvhSubtrees, dst, capacity, count);
 		case B3B200_TBL_BODIES:
+			if (w->hostBodiesStale && w->device >= 0 && w->uploaded)
+			{
+				// "last written": the AoS buffer as b3b200_write_bodies left it is not kept on the host any more
+				B3_CUDA_CHECK(cudaSetDevice(w->device));
+				B3_TRY(syncAoS(w));
+				B3_CUDA_CHECK(cudaMemcpyAsync(w->bodies.data(), w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * w->bodies.size(), cudaMemcpyDeviceToHost, w->stream));
+				B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+				w->hostBodiesStale = false;
+			}
 			return copyTable(w->bodies, dst, capacity, count);
 		case B3B200_TBL_INERTIAS:
 			return copyTable(w->inertias, dst, capacity, count);

@@ -181,7 +181,7 @@ int b3b200_device_buffer(b3b200_world* w, int which, void** devicePtr);
 #define B3B200_TBL_BVH_INFOS 8    /* b3b200_bvh_info */
 #define B3B200_TBL_BVH_NODES 9    /* b3b200_bvh_node */
 #define B3B200_TBL_BVH_SUBTREES 10 /* b3b200_bvh_subtree */
-#define B3B200_TBL_BODIES 11      /* b3b200_rigid_body (host copy as registered / last written) */
+#define B3B200_TBL_BODIES 11      /* b3b200_rigid_body (as registered; after b3b200_write_bodies: the current device state) */
 #define B3B200_TBL_INERTIAS 12    /* b3b200_inertia */
 int b3b200_get_table(b3b200_world* w, int which, void* dst, int capacity, int* count);
 
