@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) concaveCullKernel(CcArgs a, c
 		if (cA < 0 || cB < 0) continue;
 		if (__ldg(&a.collidables[cA].shapeType) != B3B200_SHAPE_CONCAVE_TRIMESH) continue;  // only with the mesh as A (b3BvhTraversal.h:35)
 		const int typeB = __ldg(&a.collidables[cB].shapeType);
-		if (typeB != B3B200_SHAPE_CONVEX_HULL && typeB != B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS) continue;
+		if (typeB != B3B200_SHAPE_CONVEX_HULL && typeB != B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS && typeB != B3B200_SHAPE_SPHERE) continue;
 		if (a.pose[2 * bodyA].w == 0.f && a.pose[2 * bodyB].w == 0.f) continue;
 		const int4 mesh = __ldg(&a.meshInfos[__ldg(&a.collidables[cA].bvhIndex)]);
 		const b3b200_convex_polyhedron* cv = &a.convex[__ldg(&a.collidables[cA].shapeIndex)];
@@ -389,6 +389,105 @@ __global__ void __launch_bounds__(CULL_WARPS * 32) concaveCullKernel(CcArgs a, c
 	}
 }
 
+// computeContactSphereTriangle (kernels/primitiveContacts.cl:1162-1300, called by findConcaveSphereContactsKernel
+// :1305-1373; the reference has no host twin of it).  The sphere is "A" of the contact, the mesh "B".
+B3_D void sphereTriangleThread(const CcArgs& a, const int4& it, int meshBody, int sphereBody, int cMesh, int cSphere)
+{
+	const float radius = __ldg(&a.collidables[cSphere].radius);
+	float4 pos = a.pose[2 * meshBody];
+	const float4 quat = a.pose[2 * meshBody + 1];
+	const float invMassMesh = pos.w;
+	pos.w = 0.f;
+	float4 spherePos2 = a.pose[2 * sphereBody];
+	const float invMassSphere = spherePos2.w;
+	spherePos2.w = 0.f;
+	const b3b200_convex_polyhedron* cv = &a.convex[__ldg(&a.collidables[cMesh].shapeIndex)];
+	const int idxOff = __ldg(&a.faces[__ldg(&cv->faceOffset) + it.y].indexOffset), vOff = __ldg(&cv->vertexOffset);
+	const float4 v0 = __ldg(&a.vertices[vOff + __ldg(&a.indices[idxOff])]);
+	const float4 v1 = __ldg(&a.vertices[vOff + __ldg(&a.indices[idxOff + 1])]);
+	const float4 v2 = __ldg(&a.vertices[vOff + __ldg(&a.indices[idxOff + 2])]);
+	const float4 invOrn = quatInverse(quat), invPos = quatRotate(invOrn, neg3(pos));
+	const float4 sphereCenter = add3(quatRotate(invOrn, spherePos2), invPos);
+	float4 normal = normalized3(cross3(sub3(v1, v0), sub3(v2, v0)));
+	float distanceFromPlane = dot3(sub3(sphereCenter, v0), normal);
+	if (distanceFromPlane < 0.f)
+	{
+		distanceFromPlane *= -1.f;
+		normal = scale3(normal, -1.f);
+	}
+	bool hasContact = false;
+	float4 contactPoint = mk4(0, 0, 0);
+	if (distanceFromPlane < radius)
+	{
+		const float4 e1 = sub3(v1, v0), e2 = sub3(v2, v1), e3 = sub3(v0, v2);
+		const float r1 = dot3(cross3(e1, normal), sub3(sphereCenter, v0));
+		const float r2 = dot3(cross3(e2, normal), sub3(sphereCenter, v1));
+		const float r3 = dot3(cross3(e3, normal), sub3(sphereCenter, v2));
+		if ((r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0))
+		{
+			hasContact = true;
+			contactPoint = sub3(sphereCenter, scale3(normal, distanceFromPlane));
+		}
+		else
+		{
+#pragma unroll
+			for (int i = 0; i < 3; i++)
+			{
+				const float4 from = i == 0 ? v0 : (i == 1 ? v1 : v2), to = i == 0 ? v1 : (i == 1 ? v2 : v0);
+				float4 diff = sub3(sphereCenter, from);
+				const float4 v = sub3(to, from);
+				float t = dot3(v, diff);
+				if (t > 0)
+				{
+					const float dotVV = dot3(v, v);
+					if (t < dotVV)
+					{
+						t /= dotVV;
+						diff = sub3(diff, scale3(v, t));
+					}
+					else
+					{
+						t = 1;
+						diff = sub3(diff, v);
+					}
+				}
+				else
+					t = 0;
+				const float4 nearest = add3(from, scale3(v, t));
+				if (dot3(diff, diff) < radius * radius)
+				{
+					hasContact = true;
+					contactPoint = nearest;
+				}
+			}
+		}
+	}
+	if (!hasContact) return;
+	const float4 contactToCenter = sub3(sphereCenter, contactPoint);
+	const float minDist = sqrtf(dot3(contactToCenter, contactToCenter));
+	if (!(minDist > FLT_EPSILON)) return;
+	const float4 hitNormal = normalized3(contactToCenter);
+	const float4 normalOnSurfaceB1 = quatRotate(quat, neg3(hitNormal));
+	float4 pOnB1 = add3(quatRotate(quat, contactPoint), pos);
+	const float actualDepth = minDist - radius;
+	if (!(actualDepth <= 0.f) || !(dot3(normalOnSurfaceB1, normalOnSurfaceB1) > FLT_EPSILON)) return;
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return;
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	pOnB1.w = actualDepth;
+	cw[0] = pOnB1;
+	cw[1] = cw[2] = cw[3] = mk4(0, 0, 0, 0);
+	cw[4] = mk4(-normalOnSurfaceB1.x, -normalOnSurfaceB1.y, -normalOnSurfaceB1.z, 1.f);
+	int4 t5;
+	t5.x = (int)(0u | (45874u << 16));
+	t5.y = it.y;
+	t5.z = invMassSphere == 0.f ? -sphereBody : sphereBody;
+	t5.w = invMassMesh == 0.f ? -meshBody : meshBody;
+	reinterpret_cast<int4*>(c)[5] = t5;
+	reinterpret_cast<int4*>(c)[6] = make_int4(-1, it.y, 0, 0);  // m_childIndexB = faceIndex (:1290)
+}
+
 // stage 1b: exact quick reject, one THREAD per (pair, triangle, child) item.  Tests three members of the reference's
 // own axis list with its own arithmetic -- the triangle normal, the edge plane of the triangle that faces B most, and
 // the face of B that faces the triangle most -- so an item dropped here is one the full SAT would drop too.
@@ -407,6 +506,13 @@ __global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* 
 			it = rawItems[r];
 			const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
 			const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+			if (__ldg(&a.collidables[cB].shapeType) == B3B200_SHAPE_SPHERE)
+			{
+				sphereTriangleThread(a, it, bodyA, bodyB, cA, cB);  // one-point contact, finished here
+				it = make_int4(0, 0, 0, 0);
+			}
+			else
+			{
 			float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
 			const float4 ornA = a.pose[2 * bodyA + 1];
 			float4 ornB = a.pose[2 * bodyB + 1];
@@ -485,6 +591,7 @@ __global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* 
 				projectTri(vA, posA, ornA, axis, minT, maxT);
 				projectHull(hB, posB, ornB, axis, a.vertices, minH, maxH);
 				if (maxT < minH || maxH < minT) keep = false;
+			}
 			}
 		}
 		const unsigned int m = __ballot_sync(FULL, keep);

@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 					}
 				}
 				else if (meshPairs && typeA == B3B200_SHAPE_CONCAVE_TRIMESH &&
-						 (typeB == B3B200_SHAPE_CONVEX_HULL || typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS))
+						 (typeB == B3B200_SHAPE_CONVEX_HULL || typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeB == B3B200_SHAPE_SPHERE))
 				{
 					// trimesh (as A, b3BvhTraversal.h:35) x hull / compound: listed for concaveCullKernel, which then
 					// need not scan all pairs again
@@ -1365,7 +1365,7 @@ B3_D void planeConvexThread(const NpArgs& a, int pairIndex, int planeBody, int c
 }
 
 // one-point contact of the sphere paths (m_childIndexA/B = -1)
-B3_D void appendOnePoint(const NpArgs& a, int pairIndex, int bodyA, int bodyB, const float4& normalOnB, const float4& pointWithDepth)
+B3_D void appendOnePoint(const NpArgs& a, int pairIndex, int bodyA, int bodyB, const float4& normalOnB, const float4& pointWithDepth, int childB = -1)
 {
 	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
 	if (slot >= (unsigned int)a.maxContacts) return;
@@ -1380,21 +1380,23 @@ B3_D void appendOnePoint(const NpArgs& a, int pairIndex, int bodyA, int bodyB, c
 	t.z = a.pose[2 * bodyA].w == 0.f ? -bodyA : bodyA;
 	t.w = a.pose[2 * bodyB].w == 0.f ? -bodyB : bodyB;
 	reinterpret_cast<int4*>(c)[5] = t;
-	reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);
+	reinterpret_cast<int4*>(c)[6] = make_int4(-1, childB, 0, 0);
 	a.pairsOut[pairIndex].z = (int)slot;
 }
 
 // computeContactSphereConvex, host twin (b3ConvexHullContact.cpp:2323-2470; signedDistanceFromPointToPlane :342-349,
 // IsPointInPolygon :362-416), operation by operation.  A = sphere, B = convex hull.
-B3_D void sphereConvexThread(const NpArgs& a, int pairIndex, int sphereBody, int convexBody)
+B3_D void sphereConvexThread(const NpArgs& a, int pairIndex, int sphereBody, int convexBody, int child)
 {
 	const float radius = __ldg(&a.collidables[a.coll[sphereBody]].radius);
 	const float4 spherePos1 = a.pose[2 * sphereBody];
-	const float4 pos = a.pose[2 * convexBody], quat = a.pose[2 * convexBody + 1];
+	Side side;
+	if (!resolveSide(a, convexBody, child, side)) return;  // child >= 0: that child shape of a compound
+	const float4 pos = side.pos, quat = side.orn;
 	const Mat3 basis = matFromQuat(quat), inv = matTranspose(basis);
 	const float4 invOrigin = matMulVec(inv, neg3(mk4(pos.x, pos.y, pos.z)));
 	const float4 spherePos = add3(matMulVec(inv, spherePos1), invOrigin);
-	const HullRef h = loadHull(a.convex, __ldg(&a.collidables[a.coll[convexBody]].shapeIndex));
+	const HullRef h = loadHull(a.convex, side.shape);
 	float4 closestPnt = mk4(0, 0, 0), localHitNormal = mk4(0, 0, 0);
 	float minDist = -1000000.f;
 	bool bCollide = true;
@@ -1489,7 +1491,7 @@ B3_D void sphereConvexThread(const NpArgs& a, int pairIndex, int sphereBody, int
 		if (actualDepth < 0)
 		{
 			pOnB1.w = actualDepth;
-			appendOnePoint(a, pairIndex, sphereBody, convexBody, normalOnSurfaceB1, pOnB1);
+			appendOnePoint(a, pairIndex, sphereBody, convexBody, normalOnSurfaceB1, pOnB1, child);
 		}
 	}
 }
@@ -1554,9 +1556,18 @@ __global__ void __launch_bounds__(128) npPrimitiveKernel(NpArgs a)
 			if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_SPHERE)
 				sphereSphereThread(a, p, bodyA, bodyB);
 			else if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_CONVEX_HULL)
-				sphereConvexThread(a, p, bodyA, bodyB);
+				sphereConvexThread(a, p, bodyA, bodyB, -1);
 			else if (typeA == B3B200_SHAPE_CONVEX_HULL && typeB == B3B200_SHAPE_SPHERE)
-				sphereConvexThread(a, p, bodyB, bodyA);
+				sphereConvexThread(a, p, bodyB, bodyA, -1);
+			else if ((typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS) ||
+					 (typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS && typeB == B3B200_SHAPE_SPHERE))
+			{
+				// processCompoundPairsPrimitivesKernel (kernels/primitiveContacts.cl:975-1097): every child against the sphere
+				const bool compIsB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
+				const int sphereBody = compIsB ? bodyA : bodyB, compBody = compIsB ? bodyB : bodyA, cC = compIsB ? cB : cA;
+				const int first = __ldg(&a.collidables[cC].shapeIndex), n = __ldg(&a.collidables[cC].numChildShapes);
+				for (int cI = 0; cI < n; cI++) sphereConvexThread(a, p, sphereBody, compBody, first + cI);
+			}
 			continue;
 		}
 		if (typeB == B3B200_SHAPE_PLANE && typeA != B3B200_SHAPE_PLANE)

@@ -826,14 +826,18 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 	};
 	// computeContactSphereConvex, host twin (b3ConvexHullContact.cpp:2323-2470; signedDistanceFromPointToPlane :342-349,
 	// IsPointInPolygon :362-416).  A = sphere, B = convex hull.
-	auto sphereConvex = [&](int pairIndex, int sphereBody, int convexBody) {
+	// child >= 0: the convex is that child shape of a compound (processCompoundPairsPrimitivesKernel,
+	// kernels/primitiveContacts.cl:975-1097, composes the child transform and calls the same routine)
+	auto sphereConvex = [&](int pairIndex, int sphereBody, int convexBody, int child) {
 		const float radius = collidables[bodies[sphereBody].collidableIdx].radius;
 		V3 spherePos1 = ld(bodies[sphereBody].pos);
-		V3 pos = ld(bodies[convexBody].pos), quat = ld(bodies[convexBody].quat);
+		SideO side;
+		if (!resolveSide(bodies, collidables, children, convexBody, child, side)) return;
+		V3 pos = side.pos, quat = side.orn;
 		M3 basis = matFromQuat(quat), inv = transposeM(basis);
 		V3 invOrigin = matMul(inv, neg(mk(pos.x, pos.y, pos.z)));
 		V3 spherePos = add(matMul(inv, spherePos1), invOrigin);
-		const b3b200_convex_polyhedron& h = convex[collidables[bodies[convexBody].collidableIdx].shapeIndex];
+		const b3b200_convex_polyhedron& h = convex[side.shape];
 		V3 closestPnt = mk(0, 0, 0), localHitNormal = mk(0, 0, 0);
 		float minDist = -1000000.f;
 		bool bCollide = true;
@@ -928,6 +932,7 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 			{
 				pOnB1.w = actualDepth;
 				onePoint(pairIndex, sphereBody, convexBody, normalOnSurfaceB1, pOnB1);
+				if (child >= 0) out[nContacts - 1].childIndexB = child;
 			}
 		}
 	};
@@ -1027,11 +1032,16 @@ extern "C" int orc_contacts(const b3b200_int4* pairs, int nPairs, const b3b200_r
 			if (typeA == B3B200_SHAPE_SPHERE && typeB == B3B200_SHAPE_SPHERE)
 				sphereSphere(p, bodyA, bodyB);
 			else if (typeA == B3B200_SHAPE_SPHERE && hullB)
-				sphereConvex(p, bodyA, bodyB);
+				sphereConvex(p, bodyA, bodyB, -1);
 			else if (hullA && typeB == B3B200_SHAPE_SPHERE)
-				sphereConvex(p, bodyB, bodyA);
-			// sphere x compound / trimesh: device kernels only in the reference (findConcaveSphereContactsKernel,
-			// processCompoundPairsPrimitivesKernel); not built
+				sphereConvex(p, bodyB, bodyA, -1);
+			else if ((typeA == B3B200_SHAPE_SPHERE && compB) || (compA && typeB == B3B200_SHAPE_SPHERE))
+			{
+				const int sphereBody = compB ? bodyA : bodyB, compBody = compB ? bodyB : bodyA;
+				const int cC = bodies[compBody].collidableIdx;
+				for (int c = 0; c < collidables[cC].numChildShapes; c++) sphereConvex(p, sphereBody, compBody, collidables[cC].shapeIndex + c);
+			}
+			// sphere x trimesh: orc_concave_contacts
 		}
 	}
 	return nContacts;
@@ -1143,7 +1153,7 @@ extern "C" int orc_concave_contacts(const b3b200_int4* pairs, int nPairs, const 
 		if (bodies[bodyA].invMass == 0 && bodies[bodyB].invMass == 0) continue;
 		if (collidables[cA].shapeType != B3B200_SHAPE_CONCAVE_TRIMESH) continue;  // only with the mesh as A (b3BvhTraversal.h:35)
 		int typeB = collidables[cB].shapeType;
-		if (typeB != B3B200_SHAPE_CONVEX_HULL && typeB != B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS) continue;
+		if (typeB != B3B200_SHAPE_CONVEX_HULL && typeB != B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS && typeB != B3B200_SHAPE_SPHERE) continue;
 		const b3b200_convex_polyhedron& mesh = convex[collidables[cA].shapeIndex];
 		int nChildren = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS ? collidables[cB].numChildShapes : 1;
 		for (int f = 0; f < mesh.numFaces; f++)
@@ -1168,6 +1178,98 @@ extern "C" int orc_concave_contacts(const b3b200_int4* pairs, int nPairs, const 
 			for (int k = 0; k < 3; k++)
 				if (mn[k] > bb.max[k] || mx[k] < bb.min[k]) overlap = false;
 			if (!overlap) continue;
+			if (typeB == B3B200_SHAPE_SPHERE)
+			{
+				// computeContactSphereTriangle (kernels/primitiveContacts.cl:1162-1300, called by
+				// findConcaveSphereContactsKernel :1305-1373; device only: parity unpinned).  "A" of the contact is the sphere.
+				nCand++;
+				const float radius = collidables[cB].radius;
+				V3 pos = ld(bodies[bodyA].pos), quat = ld(bodies[bodyA].quat);
+				pos.w = 0.f;
+				V3 spherePos2 = ld(bodies[bodyB].pos);
+				spherePos2.w = 0.f;
+				V3 invOrn = quatInv(quat), invPos = quatRotate(invOrn, neg(pos));
+				V3 sphereCenter = add(quatRotate(invOrn, spherePos2), invPos);
+				V3 v0 = ld(vA[0]), v1 = ld(vA[1]), v2 = ld(vA[2]);
+				V3 normal = normalized(cross(sub(v1, v0), sub(v2, v0)));
+				float distanceFromPlane = dot(sub(sphereCenter, v0), normal);
+				if (distanceFromPlane < 0.f)
+				{
+					distanceFromPlane *= -1.f;
+					normal = mul(normal, -1.f);
+				}
+				bool hasContact = false;
+				V3 contactPoint = mk(0, 0, 0);
+				if (distanceFromPlane < radius)
+				{
+					// pointInTriangle (:1100-1133)
+					V3 e1 = sub(v1, v0), e2 = sub(v2, v1), e3 = sub(v0, v2);
+					float r1 = dot(cross(e1, normal), sub(sphereCenter, v0));
+					float r2 = dot(cross(e2, normal), sub(sphereCenter, v1));
+					float r3 = dot(cross(e3, normal), sub(sphereCenter, v2));
+					if ((r1 > 0 && r2 > 0 && r3 > 0) || (r1 <= 0 && r2 <= 0 && r3 <= 0))
+					{
+						hasContact = true;
+						contactPoint = sub(sphereCenter, mul(normal, distanceFromPlane));
+					}
+					else
+					{
+						const V3 tv[3] = {v0, v1, v2};
+						for (int i = 0; i < 3; i++)
+						{
+							// segmentSqrDistance (:1136-1159)
+							V3 from = tv[i], to = tv[(i + 1) % 3];
+							V3 diff = sub(sphereCenter, from), v = sub(to, from);
+							float t = dot(v, diff);
+							if (t > 0)
+							{
+								float dotVV = dot(v, v);
+								if (t < dotVV)
+								{
+									t /= dotVV;
+									diff = sub(diff, mul(v, t));
+								}
+								else
+								{
+									t = 1;
+									diff = sub(diff, v);
+								}
+							}
+							else
+								t = 0;
+							V3 nearest = add(from, mul(v, t));
+							if (dot(diff, diff) < radius * radius)
+							{
+								hasContact = true;
+								contactPoint = nearest;
+							}
+						}
+					}
+				}
+				if (!hasContact) continue;
+				V3 contactToCenter = sub(sphereCenter, contactPoint);
+				float minDist = sqrtf(dot(contactToCenter, contactToCenter));
+				if (!(minDist > FLT_EPSILON)) continue;
+				V3 hitNormal = normalized(contactToCenter);
+				V3 normalOnSurfaceB1 = quatRotate(quat, neg(hitNormal));
+				V3 pOnB1 = add(quatRotate(quat, contactPoint), pos);
+				float actualDepth = minDist - radius;
+				if (actualDepth <= 0.f && dot(normalOnSurfaceB1, normalOnSurfaceB1) > FLT_EPSILON && nContacts < maxContacts)
+				{
+					b3b200_contact4& c = out[nContacts++];
+					memset(&c, 0, sizeof(c));
+					c.frictionCmp = 45874;
+					c.batchIdx = f;
+					c.bodyAPtrAndSignBit = bodies[bodyB].invMass == 0 ? -bodyB : bodyB;  // the sphere
+					c.bodyBPtrAndSignBit = bodies[bodyA].invMass == 0 ? -bodyA : bodyA;  // the mesh
+					c.childIndexA = -1;
+					c.childIndexB = f;
+					pOnB1.w = actualDepth;
+					c.worldPosB[0] = st(pOnB1);
+					c.worldNormalOnB = st(mk(-normalOnSurfaceB1.x, -normalOnSurfaceB1.y, -normalOnSurfaceB1.z, 1.f));
+				}
+				continue;
+			}
 			for (int ch = 0; ch < nChildren; ch++)
 			{
 				nCand++;

@@ -513,12 +513,13 @@ def concave_world(seed=0, n=600, nq=24, amplitude=1.5, freq=0.5, drop=0.9, lo=-0
     hull = w.register_convex_points(scenes.random_hull_points(rng, 12, 0.5, 0.8))
     tet = w.register_convex_points(scenes.tetra_points(0.6))
     ell = w.register_compound(scenes.compound_children(box, scenes.L_OFFSETS))
-    kinds = [box, hull, tet, ell]
+    ball = w.register_sphere(0.5)
+    kinds = [box, hull, tet, ell, ball]
     half = 0.5 * nq - 1.5
     for i in range(n):
         x, z = rng.uniform(-half, half, 2)
         h = amplitude * np.sin(freq * x) * np.cos(freq * z)
-        w.register_instance(1.0, (x, h + rng.uniform(lo, drop), z), scenes.random_quat(rng), kinds[int(rng.integers(0, 4))])
+        w.register_instance(1.0, (x, h + rng.uniform(lo, drop), z), scenes.random_quat(rng), kinds[int(rng.integers(0, 5))])
     w.upload()
     t = w.tables()
     return w, oa.Shapes(t), t["bodies"]
@@ -542,7 +543,7 @@ def test_concave_contacts_match_oracle(seed):
     o_mesh, ncand = oa.concave_contacts_oracle(pairs, bodies, sh, aabbs, 1 << 18)
     o_rest = oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
     assert len(o_mesh) > 300 and ncand > len(o_mesh)
-    is_mesh = np.abs(g["bodyA"]) == 0
+    is_mesh = (np.abs(g["bodyA"]) == 0) | (np.abs(g["bodyB"]) == 0)  # (sphere x trimesh contacts carry the sphere as A)
     gm, gr = full_sort(g[is_mesh]), full_sort(g[~is_mesh])
     om, orr = full_sort(o_mesh), full_sort(o_rest)
     assert len(gm) == len(om) and len(gr) == len(orr)
@@ -556,6 +557,7 @@ def test_concave_contacts_match_oracle(seed):
             assert np.array_equal(a["worldPosB"][m, k].view(np.uint32), b["worldPosB"][m, k].view(np.uint32)), k
     types = sh.collidables["shapeType"][bodies["collidableIdx"]]
     assert (types[np.abs(om["bodyB"])] == capi.SHAPE_COMPOUND).sum() > 20  # compound children against triangles are covered
+    assert (types[np.abs(om["bodyA"])] == capi.SHAPE_SPHERE).sum() > 10  # and sphere x triangle
 
 
 def test_concave_scene_settles_on_the_heightfield():
@@ -583,14 +585,15 @@ def sphere_world(seed=0, n=500, plane=True):
     hull = w.register_convex_points(scenes.random_hull_points(rng, 12, 0.5, 0.8))
     s1 = w.register_sphere(0.45)
     s2 = w.register_sphere(0.8)
+    ell = w.register_compound(scenes.compound_children(box, scenes.L_OFFSETS))
     if plane:
         w.register_instance(0.0, (0, 0, 0), scenes.IDENT, w.register_plane((0, 1, 0), 0.0))
     else:
         scenes.add_ground_box(w, 50.0)
-    kinds = [box, hull, s1, s2]
+    kinds = [box, hull, s1, s2, ell]
     for i in range(n):
         p = (rng.uniform(-5, 5), rng.uniform(0.0, 3.5), rng.uniform(-5, 5))
-        w.register_instance(1.0, p, scenes.random_quat(rng), kinds[int(rng.integers(0, 4))])
+        w.register_instance(1.0, p, scenes.random_quat(rng), kinds[int(rng.integers(0, 5))])
     w.upload()
     t = w.tables()
     return w, oa.Shapes(t), t["bodies"]
@@ -619,6 +622,7 @@ def test_sphere_contacts_match_oracle(seed, plane):
     ta, tb = types[np.abs(o["bodyA"])], types[np.abs(o["bodyB"])]
     sp = capi.SHAPE_SPHERE
     assert ((ta == sp) & (tb == sp)).sum() > 20 and ((ta == sp) ^ (tb == sp)).sum() > 50
+    assert (((ta == sp) & (tb == capi.SHAPE_COMPOUND)) | ((ta == capi.SHAPE_COMPOUND) & (tb == sp))).sum() > 10  # sphere x compound child
     if plane:
         assert ((ta == capi.SHAPE_PLANE) & (tb == sp)).sum() > 5
 
