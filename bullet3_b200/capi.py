@@ -39,6 +39,8 @@ config_t = np.dtype([(n, "i4") for n in (
     "maxConvexBodies", "maxConvexShapes", "maxBroadphasePairs", "maxContactCapacity", "compoundPairCapacity",
     "maxVerticesPerFace", "maxFacesPerShape", "maxConvexVertices", "maxConvexIndices", "maxConvexUniqueEdges",
     "maxCompoundChildShapes", "maxTriConvexPairCapacity")])
+joint_t = np.dtype([("constraintType", "i4"), ("rbA", "i4"), ("rbB", "i4"), ("breakingImpulseThreshold", "f4"), ("pivotInA", "f4", 4), ("pivotInB", "f4", 4),
+                    ("relTargetAB", "f4", 4), ("flags", "i4"), ("uid", "i4"), ("padding", "i4", 2)])
 sort_data_t = np.dtype([("key", "u4"), ("value", "u4")])
 bvh_node_t = np.dtype([("qmin", "u2", 3), ("qmax", "u2", 3), ("escapeIndexOrTriangleIndex", "i4")])
 bvh_subtree_t = np.dtype([("qmin", "u2", 3), ("qmax", "u2", 3), ("rootNodeIndex", "i4"), ("subtreeSize", "i4"), ("padding", "i4", 3)])
@@ -63,7 +65,8 @@ SYMBOLS = [
     "b3b200_register_compound", "b3b200_register_concave", "b3b200_register_instance", "b3b200_register_body", "b3b200_register_instances", "b3b200_upload", "b3b200_set_gravity",
     "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_solver_dataflow", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
-    "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solver_setup",
+    "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solve_joints", "b3b200_create_p2p_constraint", "b3b200_create_fixed_constraint", "b3b200_remove_constraint",
+    "b3b200_num_constraints", "b3b200_get_joints", "b3b200_solver_setup",
     "b3b200_solver_iterate", "b3b200_integrate", "b3b200_get_aabbs", "b3b200_get_pairs", "b3b200_get_contacts", "b3b200_set_contacts",
     "b3b200_get_constraints", "b3b200_get_batches", "b3b200_get_counters", "b3b200_get_work_counters", "b3b200_enable_stage_timing", "b3b200_stage_timings",
     "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
@@ -295,6 +298,42 @@ class World:
         out = np.zeros(8, np.int32)
         check(self.L.b3b200_get_counters(self.h, ptr(out)), "get_counters")
         return out
+
+    # ---- joints
+    def create_p2p_constraint(self, body_a, body_b, pivot_a, pivot_b, breaking_threshold=1e30):
+        fa = (C.c_float * 3)(*[float(x) for x in pivot_a[:3]])
+        fb = (C.c_float * 3)(*[float(x) for x in pivot_b[:3]])
+        r = self.L.b3b200_create_p2p_constraint(self.h, int(body_a), int(body_b), fa, fb, C.c_float(breaking_threshold))
+        if r < 0:
+            raise B3Error("create_p2p_constraint: " + last_error())
+        return r
+
+    def create_fixed_constraint(self, body_a, body_b, pivot_a, pivot_b, rel_target_ab, breaking_threshold=1e30):
+        fa = (C.c_float * 3)(*[float(x) for x in pivot_a[:3]])
+        fb = (C.c_float * 3)(*[float(x) for x in pivot_b[:3]])
+        fq = (C.c_float * 4)(*[float(x) for x in rel_target_ab[:4]])
+        r = self.L.b3b200_create_fixed_constraint(self.h, int(body_a), int(body_b), fa, fb, fq, C.c_float(breaking_threshold))
+        if r < 0:
+            raise B3Error("create_fixed_constraint: " + last_error())
+        return r
+
+    def remove_constraint(self, uid):
+        check(self.L.b3b200_remove_constraint(self.h, int(uid)), "remove_constraint")
+
+    @property
+    def num_constraints(self):
+        return check(self.L.b3b200_num_constraints(self.h), "num_constraints")
+
+    def joints(self):
+        n = C.c_int(0)
+        check(self.L.b3b200_get_joints(self.h, None, 0, C.byref(n)), "get_joints")
+        out = np.zeros(n.value, joint_t)
+        if n.value:
+            check(self.L.b3b200_get_joints(self.h, ptr(out), n.value, C.byref(n)), "get_joints")
+        return out
+
+    def solve_joints(self):
+        check(self.L.b3b200_solve_joints(self.h), "solve_joints")
 
     def work_counters(self):
         out = np.zeros(24, np.int32)

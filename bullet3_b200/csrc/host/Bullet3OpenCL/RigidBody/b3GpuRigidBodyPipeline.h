@@ -25,6 +25,12 @@ public:
 	int registerConvexPolyhedron(class b3ConvexUtility* convex);
 	int registerPhysicsInstance(float mass, const float* position, const float* orientation, int collisionShapeIndex, int userData, bool writeInstanceToGpu);
 	void writeAllInstancesToGpu();
+	// joints (b3GpuRigidBodyPipeline.h:28-34 of the reference); solved before the contacts, broken joints get flags = 0
+	int createPoint2PointConstraint(int bodyA, int bodyB, const float* pivotInA, const float* pivotInB, float breakingThreshold);
+	int createFixedConstraint(int bodyA, int bodyB, const float* pivotInA, const float* pivotInB, const float* relTargetAB, float breakingThreshold);
+	void removeConstraintByUid(int uid);
+	void copyConstraintsToHost();
+	int getNumConstraints() const;
 	void setGravity(const float* grav);
 	void reset();
 	// B200 additions: solver selection (the reference uses the global gUseJacobi) and iteration count

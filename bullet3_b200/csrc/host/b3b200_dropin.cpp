@@ -407,6 +407,17 @@ int b3GpuRigidBodyPipeline::registerPhysicsInstance(float mass, const float* pos
 	return r;
 }
 void b3GpuRigidBodyPipeline::writeAllInstancesToGpu() { checked(b3b200_upload(m_np->m_world), "writeAllInstancesToGpu"); }
+int b3GpuRigidBodyPipeline::createPoint2PointConstraint(int bodyA, int bodyB, const float* pivotInA, const float* pivotInB, float breakingThreshold)
+{
+	return checked(b3b200_create_p2p_constraint(m_np->m_world, bodyA, bodyB, pivotInA, pivotInB, breakingThreshold), "createPoint2PointConstraint");
+}
+int b3GpuRigidBodyPipeline::createFixedConstraint(int bodyA, int bodyB, const float* pivotInA, const float* pivotInB, const float* relTargetAB, float breakingThreshold)
+{
+	return checked(b3b200_create_fixed_constraint(m_np->m_world, bodyA, bodyB, pivotInA, pivotInB, relTargetAB, breakingThreshold), "createFixedConstraint");
+}
+void b3GpuRigidBodyPipeline::removeConstraintByUid(int uid) { checked(b3b200_remove_constraint(m_np->m_world, uid), "removeConstraintByUid"); }
+void b3GpuRigidBodyPipeline::copyConstraintsToHost() { checked(b3b200_get_joints(m_np->m_world, 0, 0, 0), "copyConstraintsToHost"); }
+int b3GpuRigidBodyPipeline::getNumConstraints() const { return b3b200_num_constraints(m_np->m_world); }
 void b3GpuRigidBodyPipeline::setGravity(const float* g) { b3b200_set_gravity(m_np->m_world, g); }
 void b3GpuRigidBodyPipeline::reset() { m_np->reset(); }
 void b3GpuRigidBodyPipeline::setSolver(bool jacobi, int iterations) { b3b200_set_solver(m_np->m_world, jacobi ? B3B200_SOLVER_JACOBI : B3B200_SOLVER_PGS, iterations); }

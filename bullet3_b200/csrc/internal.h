@@ -115,6 +115,12 @@ struct World
 	std::vector<b3b200_float4> meshNodes;
 	std::vector<int> meshTris;
 	std::vector<b3b200_int4> meshInfos;  // per bvhInfos entry: {first node (in nodes), node count, first slot in meshTris, triangle count}
+	// joints (b3GpuRigidBodyPipeline: m_cpuConstraints / m_gpuConstraints, m_constraintUid)
+	std::vector<b3b200_generic_constraint> joints;
+	int jointUid = 0;
+	bool jointsDirty = false;         // host copy newer than the device copy
+	bool jointBatchesDirty = false;   // constraint set changed: rebuild the batches (b3GpuPgsConstraintSolver::recomputeBatches)
+	std::vector<int> jointOrder, jointBatchOffset;
 	// host-side bodies
 	std::vector<b3b200_rigid_body> bodies;
 	std::vector<b3b200_inertia> inertias;
@@ -172,6 +178,10 @@ struct World
 	DevBuf<unsigned int> dBatchOffset;    // exclusive scan
 	DevBuf<unsigned int> dBatchCursor;
 	DevBuf<unsigned int> dGridBarrier;    // software grid barrier state
+	// joints
+	DevBuf<b3b200_generic_constraint> dJoints;
+	DevBuf<int> dJointOrder, dJointBatchOffset, dJointNumRows;
+	DevBuf<float4> dJointRows, dJointDelta;
 	// jacobi
 	DevBuf<unsigned int> dBodyCount, dBodyOffset;
 	DevBuf<float4> dDeltaLin, dDeltaAng;
@@ -203,6 +213,7 @@ int launchUpdateAabbs(World* w);
 int launchIntegrate(World* w, float dt, bool alsoAabbs);
 int launchNarrowphase(World* w);
 int launchConcave(World* w);  // concave.cu; called by launchNarrowphase when a trimesh is registered
+int launchSolveJoints(World* w);  // joints.cu
 int launchSolverSetup(World* w);
 int launchSolverIterate(World* w);
 int launchJacobi(World* w);

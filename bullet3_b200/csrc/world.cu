@@ -244,6 +244,8 @@ static int stepOnce(World* w, float dt)
 	B3_TRY(recordStage(w, 2));
 	B3_TRY(launchNarrowphase(w));
 	B3_TRY(recordStage(w, 3));
+	// joints first, then contacts (b3GpuRigidBodyPipeline.cpp:361-374 before :389-460)
+	if (!w->joints.empty()) B3_TRY(launchSolveJoints(w));
 	if (w->solverKind == B3B200_SOLVER_JACOBI)
 	{
 		B3_TRY(launchJacobi(w));
@@ -363,6 +365,10 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->bvhSubtrees.clear();
 	w->bodies.clear();
 	w->inertias.clear();
+	w->joints.clear();
+	w->jointUid = 0;
+	w->jointsDirty = false;
+	w->jointBatchesDirty = false;
 	w->numBodies = 0;
 	w->static0Index = -1;
 	w->uploaded = false;

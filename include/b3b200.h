@@ -101,6 +101,17 @@ int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const
 							  const float* orientations4, const int* collidableIndices);
 /* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150) */
 int b3b200_upload(b3b200_world* w);
+
+/* ---- joints: b3GpuRigidBodyPipeline::createPoint2PointConstraint / createFixedConstraint / removeConstraintByUid /
+ * copyConstraintsToHost (b3GpuRigidBodyPipeline.cpp:158-218, 593-596).  They take effect at the next step; like in the
+ * reference the joints are solved before the contacts (4 iterations, ERP 0.2, dt 1/60), a joint whose applied impulse
+ * reaches its breaking threshold is disabled (flags = 0).  create_* return the uid (>= 0) or -1. */
+int b3b200_create_p2p_constraint(b3b200_world* w, int bodyA, int bodyB, const float* pivotInA3, const float* pivotInB3, float breakingThreshold);
+int b3b200_create_fixed_constraint(b3b200_world* w, int bodyA, int bodyB, const float* pivotInA3, const float* pivotInB3, const float* relTargetAB4,
+								   float breakingThreshold);
+int b3b200_remove_constraint(b3b200_world* w, int uid);
+int b3b200_num_constraints(b3b200_world* w);
+int b3b200_get_joints(b3b200_world* w, b3b200_generic_constraint* dst, int capacity, int* count);
 /* b3GpuRigidBodyPipeline::setGravity (b3GpuRigidBodyPipeline.cpp:562-565) */
 int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
 int b3b200_set_solver(b3b200_world* w, int kind, int iterations);
@@ -132,6 +143,7 @@ int b3b200_update_aabbs(b3b200_world* w);      /* setupGpuAabbsFull :500-560 */
 int b3b200_find_pairs(b3b200_world* w);        /* bp->calculateOverlappingPairs :260 */
 int b3b200_compute_contacts(b3b200_world* w);  /* np->computeContacts :324 */
 int b3b200_solve_contacts(b3b200_world* w);    /* m_solver2/3->solveContacts :389-460 */
+int b3b200_solve_joints(b3b200_world* w);      /* m_gpuSolver->solveJoints :361-374 (b3GpuPgsConstraintSolver.cpp:927-942) */
 int b3b200_solver_setup(b3b200_world* w);      /* colouring + contact->constraint only */
 int b3b200_solver_iterate(b3b200_world* w);    /* the iteration loop only */
 int b3b200_integrate(b3b200_world* w, float dt); /* integrate :465-498 */

@@ -220,6 +220,24 @@ typedef struct B3B200_ALIGN16 b3b200_bvh_info
 	int subTreeOffset;
 } b3b200_bvh_info;
 
+/* b3GpuGenericConstraint (src/Bullet3OpenCL/RigidBody/b3GpuGenericConstraint.h:73-127), 80 bytes */
+#define B3B200_CONSTRAINT_P2P 3   /* B3_GPU_POINT2POINT_CONSTRAINT_TYPE */
+#define B3B200_CONSTRAINT_FIXED 4 /* B3_GPU_FIXED_CONSTRAINT_TYPE */
+#define B3B200_CONSTRAINT_FLAG_ENABLED 1
+typedef struct B3B200_ALIGN16 b3b200_generic_constraint
+{
+	int constraintType;
+	int rbA;
+	int rbB;
+	float breakingImpulseThreshold;
+	b3b200_float4 pivotInA;
+	b3b200_float4 pivotInB;
+	b3b200_float4 relTargetAB;
+	int flags;
+	int uid;
+	int padding[2];
+} b3b200_generic_constraint;
+
 typedef struct b3b200_sort_data
 {
 	unsigned int key;
@@ -243,6 +261,7 @@ static_assert(sizeof(b3b200_bvh_node) == 16, "abi");
 static_assert(sizeof(b3b200_bvh_subtree) == 32, "abi");
 static_assert(sizeof(b3b200_bvh_info) == 64, "abi");
 static_assert(sizeof(b3b200_sort_data) == 8, "abi");
+static_assert(sizeof(b3b200_generic_constraint) == 80, "abi");
 #endif
 
 #endif /* B3B200_TYPES_H */

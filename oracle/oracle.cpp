@@ -1857,3 +1857,185 @@ void orc_bound_search_count(const b3b200_sort_data* sorted, int n, unsigned int*
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Joints: b3GpuPgsConstraintSolver::solveJoints, host twins (b3GpuPgsConstraintSolver.cpp: setup :346-541,
+// sortConstraintByBatch3 :778-905, iterations :664-735 with resolveSingleConstraintRowGeneric2 :575-604, finish
+// :959-1050) + getInfo2Point2Point (b3GpuGenericConstraint.cpp:39-116) and, for the fixed joint, the device-only
+// getInfo2FixedOrientation (kernels/jointSolver.cl:546-628).  4 iterations, dt = 1/60, ERP 0.2, CFM 0, damping 1
+// (:927-942, b3ContactSolverInfo.h:66-74).  The reference's host twin only works for ONE constraint (its
+// batchConstraints[] are never initialised on that path), which is what it is pinned against.
+extern "C" void orc_solve_joints(b3b200_rigid_body* bodies, int numBodies, const b3b200_inertia* inertias, b3b200_generic_constraint* cs, int n)
+{
+	struct Row
+	{
+		V3 normal, rel1, rel2, angA, angB;
+		float jacDiagABInv, rhs, cfm, lower, upper, applied;
+		int bodyA, bodyB;
+	};
+	const float fps = 60.f, erp = 0.2f, cfm = 0.f, damping = 1.0f;
+	const int iterations = 4;
+	std::vector<V3> dLin(numBodies, mk(0, 0, 0)), dAng(numBodies, mk(0, 0, 0));
+	std::vector<std::vector<Row> > rows(n);
+	for (int i = 0; i < n; i++)
+	{
+		const b3b200_generic_constraint& c = cs[i];
+		int nr = 0;
+		if (c.flags & B3B200_CONSTRAINT_FLAG_ENABLED) nr = c.constraintType == B3B200_CONSTRAINT_P2P ? 3 : (c.constraintType == B3B200_CONSTRAINT_FIXED ? 6 : 0);
+		if (!nr) continue;
+		const b3b200_rigid_body& rbA = bodies[c.rbA];
+		const b3b200_rigid_body& rbB = bodies[c.rbB];
+		M3 mA = matFromQuat(ld(rbA.quat)), mB = matFromQuat(ld(rbB.quat));
+		V3 a1 = matMul(mA, mk(c.pivotInA.x, c.pivotInA.y, c.pivotInA.z)), a2 = matMul(mB, mk(c.pivotInB.x, c.pivotInB.y, c.pivotInB.z));
+		V3 a1n = neg(a1);
+		const float k = fps * erp;
+		V3 normals[6], rel1[6], rel2[6];
+		float rhs[6];
+		const V3 J1[3] = {mk(0.f, -a1n.z, a1n.y), mk(a1n.z, 0.f, -a1n.x), mk(-a1n.y, a1n.x, 0.f)};
+		const V3 J2[3] = {mk(0.f, -a2.z, a2.y), mk(a2.z, 0.f, -a2.x), mk(-a2.y, a2.x, 0.f)};
+		const float pa[3] = {rbA.pos.x, rbA.pos.y, rbA.pos.z}, pb[3] = {rbB.pos.x, rbB.pos.y, rbB.pos.z};
+		const float a1v[3] = {a1.x, a1.y, a1.z}, a2v[3] = {a2.x, a2.y, a2.z};
+		for (int j = 0; j < 3; j++)
+		{
+			normals[j] = mk(j == 0 ? 1.f : 0.f, j == 1 ? 1.f : 0.f, j == 2 ? 1.f : 0.f);
+			rel1[j] = J1[j];
+			rel2[j] = J2[j];
+			rhs[j] = k * (a2v[j] + pb[j] - a1v[j] - pa[j]);
+		}
+		if (nr == 6)
+		{
+			V3 ornA = ld(rbA.quat), ornB = ld(rbB.quat);
+			V3 qrelCur = quatMul(ornA, quatInv(ornB));
+			V3 q0 = ld(c.relTargetAB);
+			V3 dq = mk(q0.x - qrelCur.x, q0.y - qrelCur.y, q0.z - qrelCur.z, q0.w - qrelCur.w);
+			V3 sq = mk(q0.x + qrelCur.x, q0.y + qrelCur.y, q0.z + qrelCur.z, q0.w + qrelCur.w);
+			float dd = dq.x * dq.x + dq.y * dq.y + dq.z * dq.z + dq.w * dq.w, ss = sq.x * sq.x + sq.y * sq.y + sq.z * sq.z + sq.w * sq.w;
+			V3 orn1 = dd < ss ? qrelCur : mk(-qrelCur.x, -qrelCur.y, -qrelCur.z, -qrelCur.w);
+			V3 dorn = quatMul(orn1, quatInv(q0));
+			if (dorn.w >= 1.f) dorn.w = 1.f;
+			float x = dorn.w;
+			if (x < -1.f) x = -1.f;
+			if (x > 1.f) x = 1.f;
+			float angle = 2.f * acosf(x);
+			V3 axis = mk(dorn.x, dorn.y, dorn.z);
+			float len = dot(axis, axis);
+			if (len < FLT_EPSILON * FLT_EPSILON)
+				axis = mk(1.f, 0.f, 0.f);
+			else
+			{
+				float sl = sqrtf(len);
+				axis = mk(axis.x / sl, axis.y / sl, axis.z / sl);
+			}
+			V3 diff = mul(axis, -angle);
+			const float dv[3] = {diff.x, diff.y, diff.z};
+			for (int j = 0; j < 3; j++)
+			{
+				normals[3 + j] = mk(0, 0, 0);
+				rel1[3 + j] = mk(j == 0 ? 1.f : 0.f, j == 1 ? 1.f : 0.f, j == 2 ? 1.f : 0.f);
+				rel2[3 + j] = mk(j == 0 ? -1.f : 0.f, j == 1 ? -1.f : 0.f, j == 2 ? -1.f : 0.f);
+				rhs[3 + j] = k * dv[j];
+			}
+		}
+		M3 IA = ldM(inertias[c.rbA].invInertiaWorld), IB = ldM(inertias[c.rbB].invInertiaWorld);
+		for (int j = 0; j < nr; j++)
+		{
+			Row r;
+			r.lower = -FLT_MAX;
+			r.upper = FLT_MAX;
+			if (r.upper >= c.breakingImpulseThreshold) r.upper = c.breakingImpulseThreshold;
+			if (r.lower <= -c.breakingImpulseThreshold) r.lower = -c.breakingImpulseThreshold;
+			r.normal = normals[j];
+			r.rel1 = rel1[j];
+			r.rel2 = rel2[j];
+			r.angA = matMul(IA, rel1[j]);
+			r.angB = matMul(IB, rel2[j]);
+			V3 iMJlA = mul(normals[j], rbA.invMass), iMJlB = mul(normals[j], rbB.invMass);
+			float sum = dot(iMJlA, normals[j]);
+			sum += dot(r.angA, rel1[j]);
+			sum += dot(iMJlB, normals[j]);
+			sum += dot(r.angB, rel2[j]);
+			r.jacDiagABInv = fabsf(sum) > FLT_EPSILON ? 1.f / sum : 0.f;
+			float vel1Dotn = dot(normals[j], ld(rbA.linVel)) + dot(rel1[j], ld(rbA.angVel));
+			float vel2Dotn = -dot(normals[j], ld(rbB.linVel)) + dot(rel2[j], ld(rbB.angVel));
+			float relVel = vel1Dotn + vel2Dotn;
+			float velocityError = 0.f - relVel * damping;
+			r.rhs = rhs[j] * r.jacDiagABInv + velocityError * r.jacDiagABInv;
+			r.cfm = cfm;
+			r.applied = 0.f;
+			r.bodyA = c.rbA;
+			r.bodyB = c.rbB;
+			rows[i].push_back(r);
+		}
+	}
+	// sortConstraintByBatch3, simdWidth = n + 1
+	std::vector<int> order(n), batchOffset(1, 0);
+	for (int i = 0; i < n; i++) order[i] = i;
+	{
+		std::vector<char> used(numBodies, 0);
+		int numValid = 0;
+		while (numValid < n)
+		{
+			std::fill(used.begin(), used.end(), 0);
+			for (int i = numValid; i < n; i++)
+			{
+				const b3b200_generic_constraint& c = cs[order[i]];
+				bool aStatic = bodies[c.rbA].invMass == 0.f, bStatic = bodies[c.rbB].invMass == 0.f;
+				bool unavailable = !aStatic && used[c.rbA];
+				if (!unavailable) unavailable = !bStatic && used[c.rbB];
+				if (unavailable) continue;
+				if (!aStatic) used[c.rbA] = 1;
+				if (!bStatic) used[c.rbB] = 1;
+				std::swap(order[i], order[numValid]);
+				numValid++;
+			}
+			batchOffset.push_back(numValid);
+		}
+	}
+	for (int it = 0; it < iterations; it++)
+		for (size_t b = 0; b + 1 < batchOffset.size(); b++)
+			for (int s = batchOffset[b]; s < batchOffset[b + 1]; s++)
+			{
+				int ci = order[s];
+				if (!(cs[ci].flags & B3B200_CONSTRAINT_FLAG_ENABLED)) continue;
+				for (size_t j = 0; j < rows[ci].size(); j++)
+				{
+					Row& r = rows[ci][j];
+					float invMassA = bodies[r.bodyA].invMass, invMassB = bodies[r.bodyB].invMass;
+					float deltaImpulse = r.rhs - r.applied * r.cfm;
+					float deltaVel1Dotn = dot(r.normal, dLin[r.bodyA]) + dot(r.rel1, dAng[r.bodyA]);
+					float deltaVel2Dotn = -dot(r.normal, dLin[r.bodyB]) + dot(r.rel2, dAng[r.bodyB]);
+					deltaImpulse -= deltaVel1Dotn * r.jacDiagABInv;
+					deltaImpulse -= deltaVel2Dotn * r.jacDiagABInv;
+					float sum = r.applied + deltaImpulse;
+					if (sum < r.lower)
+					{
+						deltaImpulse = r.lower - r.applied;
+						r.applied = r.lower;
+					}
+					else if (sum > r.upper)
+					{
+						deltaImpulse = r.upper - r.applied;
+						r.applied = r.upper;
+					}
+					else
+						r.applied = sum;
+					dLin[r.bodyA] = add(dLin[r.bodyA], mul(mul(r.normal, invMassA), deltaImpulse));
+					dAng[r.bodyA] = add(dAng[r.bodyA], mul(r.angA, deltaImpulse));
+					dLin[r.bodyB] = add(dLin[r.bodyB], mul(mul(neg(r.normal), invMassB), deltaImpulse));
+					dAng[r.bodyB] = add(dAng[r.bodyB], mul(r.angB, deltaImpulse));
+				}
+			}
+	for (int i = 0; i < n; i++)
+		for (size_t j = 0; j < rows[i].size(); j++)
+			if (fabsf(rows[i][j].applied) >= cs[i].breakingImpulseThreshold) cs[i].flags = 0;
+	for (int i = 0; i < numBodies; i++)
+	{
+		if (bodies[i].invMass == 0.f) continue;
+		bodies[i].linVel.x += dLin[i].x;
+		bodies[i].linVel.y += dLin[i].y;
+		bodies[i].linVel.z += dLin[i].z;
+		bodies[i].angVel.x += dAng[i].x;
+		bodies[i].angVel.y += dAng[i].y;
+		bodies[i].angVel.z += dAng[i].z;
+	}
+}

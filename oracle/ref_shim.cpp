@@ -24,6 +24,8 @@
 #include "Bullet3Dynamics/shared/b3IntegrateTransforms.h"
 #include "Bullet3Dynamics/shared/b3ConvertConstraint4.h"
 
+#include "Bullet3Dynamics/ConstraintSolver/b3PgsJacobiSolver.h"
+#include "Bullet3Dynamics/ConstraintSolver/b3Point2PointConstraint.h"
 #include "../include/b3b200_types.h"
 
 static_assert(sizeof(b3RigidBodyData) == sizeof(b3b200_rigid_body), "abi");
@@ -216,6 +218,29 @@ int ref_build_hull(const float* points, int n, b3b200_float4* vertsOut, int* nVe
 	}
 	*nIndices = ni;
 	return 0;
+}
+
+
+// The reference's CPU joint path: b3PgsJacobiSolver::solveContacts with b3Point2PointConstraint objects -- what
+// b3GpuRigidBodyPipeline::stepSimulation itself calls for b3TypedConstraint joints (b3GpuRigidBodyPipeline.cpp:375-385) and
+// what b3GpuPgsConstraintSolver::solveJoints was ported from (same 4 iterations, dt 1/60, ERP 0.2).  Joints are solved
+// sequentially in index order.  Only P2P joints (type 3) are taken; returns how many were solved.
+int ref_solve_joints_p2p(b3b200_rigid_body* bodies, b3b200_inertia* inertias, int numBodies, const b3b200_generic_constraint* cs, int n)
+{
+	std::vector<b3TypedConstraint*> joints;
+	for (int i = 0; i < n; i++)
+	{
+		if (cs[i].constraintType != 3 || !(cs[i].flags & 1)) continue;
+		b3Point2PointConstraint* p = new b3Point2PointConstraint(cs[i].rbA, cs[i].rbB, b3MakeVector3(cs[i].pivotInA.x, cs[i].pivotInA.y, cs[i].pivotInA.z),
+																 b3MakeVector3(cs[i].pivotInB.x, cs[i].pivotInB.y, cs[i].pivotInB.z));
+		p->setBreakingImpulseThreshold(cs[i].breakingImpulseThreshold);
+		joints.push_back(p);
+	}
+	b3PgsJacobiSolver solver(true);
+	if (!joints.empty()) solver.solveContacts(numBodies, (b3RigidBodyData*)bodies, (b3InertiaData*)inertias, 0, 0, (int)joints.size(), &joints[0]);
+	int solved = (int)joints.size();
+	for (size_t i = 0; i < joints.size(); i++) delete joints[i];
+	return solved;
 }
 
 }  // extern "C"

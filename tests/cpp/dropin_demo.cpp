@@ -71,7 +71,16 @@ static bool meshScene(bool useUniformGrid)
 	pipe->writeAllInstancesToGpu();
 	np->writeAllBodiesToGpu();
 	bp->writeAabbsToGpu();
+	// GpuTetraScene-style joints (examples/OpenCL/rigidbody/GpuConvexScene.cpp:411-583): tie two neighbours together,
+	// and one deliberately weak joint that has to break
+	float pivA[3] = {0.6f, 0, 0}, pivB[3] = {-0.6f, 0, 0};
+	int uid0 = pipe->createPoint2PointConstraint(1, 2, pivA, pivB, 1e30f);
+	float far[3] = {-8.f, 0, 0};
+	int uid1 = pipe->createPoint2PointConstraint(3, 4, pivA, far, 0.001f);
 	for (int s = 0; s < 240; s++) pipe->stepSimulation(1.f / 60.f);
+	pipe->copyConstraintsToHost();
+	pipe->removeConstraintByUid(uid1);
+	bool jointsOk = uid0 == 0 && uid1 == 1 && pipe->getNumConstraints() == 1;
 	np->readbackAllBodiesToCpu();
 	const b3RigidBodyData* b = np->getBodiesCpu();
 	int resting = 0;
@@ -83,7 +92,7 @@ static bool meshScene(bool useUniformGrid)
 	printf("mesh scene: shapes mesh=%d box=%d compound=%d sphere=%d, bodies=%d, contacts=%d, resting on the mesh=%d\n", meshShape, smallBox, compound, sphere,
 		   pipe->getNumBodies(), np->getNumContactsGpu(), resting);
 	bool ok = meshShape >= 0 && meshBody == 0 && compound > smallBox && sphere > compound && pipe->getNumBodies() == n + 1 && np->getNumContactsGpu() >= n / 2 &&
-			  resting >= (9 * n) / 10;
+			  resting >= (9 * n) / 10 && jointsOk;
 	delete pipe;
 	delete bp;
 	delete np;

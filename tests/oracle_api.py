@@ -292,3 +292,21 @@ def _ref_register_sphere(self, radius):
 
 
 RefNarrowphase.register_sphere = _ref_register_sphere
+
+
+def solve_joints_oracle(bodies, inertias, joints):
+    """b3GpuPgsConstraintSolver::solveJoints restated (orc_solve_joints); returns (bodies, joints) after the solve"""
+    b = _arr(bodies, capi.rigid_body_t).copy()
+    j = _arr(joints, capi.joint_t).copy()
+    inert = _arr(inertias, capi.inertia_t)
+    oracle().orc_solve_joints(P(b), len(b), P(inert), P(j), len(j))
+    return b, j
+
+
+def solve_joints_ref(bodies, inertias, joints):
+    """the reference's CPU joint path (b3PgsJacobiSolver + b3Point2PointConstraint, sequential in index order)"""
+    b = _arr(bodies, capi.rigid_body_t).copy()
+    j = _arr(joints, capi.joint_t)
+    inert = _arr(inertias, capi.inertia_t).copy()
+    ref().ref_solve_joints_p2p(P(b), P(inert), len(b), P(j), len(j))
+    return b

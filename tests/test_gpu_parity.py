@@ -720,3 +720,89 @@ def test_halo_pack_unpack_between_two_worlds():
     idf = np.concatenate([[-1], keep]).astype(np.int64)
     ref = set(tuple(sorted((int(idf[a]), int(idf[b])))) for a, b in zip(pf["x"], pf["y"]))
     assert have == ref and len(ref) > 100
+
+
+# ------------------------------------------------------------------ joints
+def joint_world(seed=0, n=40):
+    rng = np.random.default_rng(seed)
+    w = capi.World(capi.default_config(1024))
+    box = w.register_convex_points(scenes.box_points(0.5))
+    w.register_instance(0.0, (0, 10, 0), scenes.IDENT, box)  # a static anchor high above
+    for i in range(n):
+        w.register_instance(1.0 + 0.05 * i, (rng.uniform(-8, 8), rng.uniform(6, 14), rng.uniform(-8, 8)), scenes.random_quat(rng), box)
+    w.upload()
+    b = w.bodies()
+    b["linVel"][1:, :3] = rng.uniform(-1, 1, (n, 3))
+    b["angVel"][1:, :3] = rng.uniform(-1, 1, (n, 3))
+    w.write_bodies(b)
+    return w, rng
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_joint_solver_matches_oracle(seed):
+    """P2P and fixed joints in chains and stars (several batches): velocities after solve_joints against the oracle's
+    restatement of b3GpuPgsConstraintSolver::solveJoints with the same batches"""
+    w, rng = joint_world(seed)
+    n = w.num_bodies - 1
+    for i in range(1, n):  # a chain
+        w.create_p2p_constraint(i, i + 1, rng.uniform(-0.5, 0.5, 3), rng.uniform(-0.5, 0.5, 3))
+    for i in range(1, n, 5):  # some hang on the static anchor
+        w.create_p2p_constraint(0, i, (0, 0, 0), (0, 0.5, 0))
+    for i in range(2, n, 7):  # fixed joints across the chain
+        w.create_fixed_constraint(i, (i + 3) % n + 1, (0.5, 0, 0), (-0.5, 0, 0), scenes.random_quat(rng))
+    assert w.num_constraints > 40
+    bodies, inertias, joints = w.bodies(), w.inertias(), w.joints()
+    w.solve_joints()
+    g = w.bodies()
+    ob, oj = oa.solve_joints_oracle(bodies, inertias, joints)
+    for f in ("linVel", "angVel"):
+        assert rel_close(g[f][:, :3], ob[f][:, :3], 1e-4), f
+    assert np.array_equal(w.joints()["flags"], oj["flags"])
+    assert not np.allclose(g["linVel"], bodies["linVel"])
+
+
+def test_joint_breaking_and_removal():
+    w, rng = joint_world(3, n=6)
+    weak = w.create_p2p_constraint(1, 2, (0.5, 0, 0), (-2.5, 0, 0), breaking_threshold=0.01)  # far apart: breaks at once
+    strong = w.create_p2p_constraint(3, 4, (0.5, 0, 0), (-0.5, 0, 0))
+    assert (weak, strong) == (0, 1) and w.num_constraints == 2
+    w.solve_joints()
+    j = w.joints()
+    assert j["flags"][j["uid"] == weak][0] == 0 and j["flags"][j["uid"] == strong][0] == 1
+    w.remove_constraint(weak)
+    assert w.num_constraints == 1 and w.joints()["uid"][0] == strong
+    third = w.create_p2p_constraint(5, 6, (0, 0, 0), (0, 0, 0))
+    assert third == 2  # uids keep counting (m_constraintUid)
+    w.solve_joints()
+    assert np.all(w.joints()["flags"] == 1)
+
+
+def test_pendulum_chain_holds_under_gravity():
+    """a chain of boxes hanging from a static anchor through P2P joints, full steps: the pivots stay together"""
+    w = capi.World(capi.default_config(256))
+    box = w.register_convex_points(scenes.box_points(0.25))
+    w.register_instance(0.0, (0, 20, 0), scenes.IDENT, box)
+    n = 10
+    for i in range(n):
+        w.register_instance(1.0, (0.8 * (i + 1), 20, 0), scenes.IDENT, box)
+    w.upload()
+    for i in range(n):
+        w.create_p2p_constraint(i, i + 1, (0.4, 0, 0), (-0.4, 0, 0))
+    w.set_solver(capi.SOLVER_PGS, 4)
+    for _ in range(240):
+        w.step(1 / 60)
+    b = w.bodies()
+    assert np.isfinite(b["pos"]).all()
+    gaps = []
+    for i in range(n):
+        pa = b["pos"][i, :3] + oa_rotate(b["quat"][i], np.array([0.4, 0, 0]))
+        pb = b["pos"][i + 1, :3] + oa_rotate(b["quat"][i + 1], np.array([-0.4, 0, 0]))
+        gaps.append(np.linalg.norm(pa - pb))
+    assert max(gaps) < 0.25, gaps  # Baumgarte-stabilised joints: small drift only
+    assert b["pos"][1:, 1].min() < 15  # and the chain swung down
+
+
+def oa_rotate(q, v):
+    x, y, z, w_ = [float(t) for t in q]
+    u = np.array([x, y, z])
+    return v + 2 * np.cross(u, np.cross(u, v) + w_ * v)
