@@ -39,6 +39,8 @@ config_t = np.dtype([(n, "i4") for n in (
     "maxConvexBodies", "maxConvexShapes", "maxBroadphasePairs", "maxContactCapacity", "compoundPairCapacity",
     "maxVerticesPerFace", "maxFacesPerShape", "maxConvexVertices", "maxConvexIndices", "maxConvexUniqueEdges",
     "maxCompoundChildShapes", "maxTriConvexPairCapacity")])
+ray_info_t = np.dtype([("from", "f4", 4), ("to", "f4", 4)])
+ray_hit_t = np.dtype([("hitFraction", "f4"), ("hitBody", "i4"), ("hitResult1", "i4"), ("hitResult2", "i4"), ("hitPoint", "f4", 4), ("hitNormal", "f4", 4)])
 joint_t = np.dtype([("constraintType", "i4"), ("rbA", "i4"), ("rbB", "i4"), ("breakingImpulseThreshold", "f4"), ("pivotInA", "f4", 4), ("pivotInB", "f4", 4),
                     ("relTargetAB", "f4", 4), ("flags", "i4"), ("uid", "i4"), ("padding", "i4", 2)])
 sort_data_t = np.dtype([("key", "u4"), ("value", "u4")])
@@ -66,7 +68,7 @@ SYMBOLS = [
     "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_solver_dataflow", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
     "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solve_joints", "b3b200_create_p2p_constraint", "b3b200_create_fixed_constraint", "b3b200_remove_constraint",
-    "b3b200_num_constraints", "b3b200_get_joints", "b3b200_solver_setup",
+    "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_solver_setup",
     "b3b200_solver_iterate", "b3b200_integrate", "b3b200_get_aabbs", "b3b200_get_pairs", "b3b200_get_contacts", "b3b200_set_contacts",
     "b3b200_get_constraints", "b3b200_get_batches", "b3b200_get_counters", "b3b200_get_work_counters", "b3b200_enable_stage_timing", "b3b200_stage_timings",
     "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
@@ -334,6 +336,19 @@ class World:
 
     def solve_joints(self):
         check(self.L.b3b200_solve_joints(self.h), "solve_joints")
+
+    def cast_rays(self, ray_from, ray_to, max_fraction=1.0):
+        """returns ray_hit_t array; hitBody = -1 where nothing was hit"""
+        f = np.asarray(ray_from, np.float32).reshape(-1, 3)
+        t = np.asarray(ray_to, np.float32).reshape(-1, 3)
+        rays = np.zeros(len(f), ray_info_t)
+        rays["from"][:, :3] = f
+        rays["to"][:, :3] = t
+        hits = np.zeros(len(f), ray_hit_t)
+        hits["hitFraction"] = max_fraction
+        hits["hitBody"] = -1
+        check(self.L.b3b200_cast_rays(self.h, ptr(rays), len(rays), ptr(hits)), "cast_rays")
+        return hits
 
     def work_counters(self):
         out = np.zeros(24, np.int32)

@@ -5,6 +5,7 @@
 #include "Bullet3OpenCL/Initialize/b3OpenCLInclude.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
 #include "Bullet3Common/b3AlignedObjectArray.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3RaycastInfo.h"
 
 class b3GpuRigidBodyPipeline
 {
@@ -31,6 +32,8 @@ public:
 	void removeConstraintByUid(int uid);
 	void copyConstraintsToHost();
 	int getNumConstraints() const;
+	// b3GpuRigidBodyPipeline.h:63 of the reference; hitResults[i].m_hitFraction is the caller's cap on entry (b3GpuRaycast.cpp:182)
+	void castRays(const b3AlignedObjectArray<b3RayInfo>& rays, b3AlignedObjectArray<b3RayHit>& hitResults);
 	void setGravity(const float* grav);
 	void reset();
 	// B200 additions: solver selection (the reference uses the global gUseJacobi) and iteration count

@@ -418,6 +418,12 @@ int b3GpuRigidBodyPipeline::createFixedConstraint(int bodyA, int bodyB, const fl
 void b3GpuRigidBodyPipeline::removeConstraintByUid(int uid) { checked(b3b200_remove_constraint(m_np->m_world, uid), "removeConstraintByUid"); }
 void b3GpuRigidBodyPipeline::copyConstraintsToHost() { checked(b3b200_get_joints(m_np->m_world, 0, 0, 0), "copyConstraintsToHost"); }
 int b3GpuRigidBodyPipeline::getNumConstraints() const { return b3b200_num_constraints(m_np->m_world); }
+void b3GpuRigidBodyPipeline::castRays(const b3AlignedObjectArray<b3RayInfo>& rays, b3AlignedObjectArray<b3RayHit>& hitResults)
+{
+	static_assert(sizeof(b3RayInfo) == sizeof(b3b200_ray_info) && sizeof(b3RayHit) == sizeof(b3b200_ray_hit), "ray records are the reference's PODs");
+	if (!rays.size()) return;
+	checked(b3b200_cast_rays(m_np->m_world, (const b3b200_ray_info*)&rays[0], rays.size(), (b3b200_ray_hit*)&hitResults[0]), "castRays");
+}
 void b3GpuRigidBodyPipeline::setGravity(const float* g) { b3b200_set_gravity(m_np->m_world, g); }
 void b3GpuRigidBodyPipeline::reset() { m_np->reset(); }
 void b3GpuRigidBodyPipeline::setSolver(bool jacobi, int iterations) { b3b200_set_solver(m_np->m_world, jacobi ? B3B200_SOLVER_JACOBI : B3B200_SOLVER_PGS, iterations); }

@@ -182,6 +182,9 @@ struct World
 	DevBuf<b3b200_generic_constraint> dJoints;
 	DevBuf<int> dJointOrder, dJointBatchOffset, dJointNumRows;
 	DevBuf<float4> dJointRows, dJointDelta;
+	// raycast
+	DevBuf<float4> dRays, dRayHits;
+	DevBuf<unsigned long long> dRayBest;
 	// jacobi
 	DevBuf<unsigned int> dBodyCount, dBodyOffset;
 	DevBuf<float4> dDeltaLin, dDeltaAng;

@@ -112,6 +112,14 @@ int b3b200_create_fixed_constraint(b3b200_world* w, int bodyA, int bodyB, const 
 int b3b200_remove_constraint(b3b200_world* w, int uid);
 int b3b200_num_constraints(b3b200_world* w);
 int b3b200_get_joints(b3b200_world* w, b3b200_generic_constraint* dst, int capacity, int* count);
+
+/* ---- b3GpuRigidBodyPipeline::castRays (b3GpuRigidBodyPipeline.cpp:671-680 -> b3GpuRaycast::castRays,
+ * src/Bullet3OpenCL/Raycast/b3GpuRaycast.cpp:249-373; result semantics of its host twin castRaysHost :160-246): for
+ * every ray the closest hit with hitFraction < the value the caller stored in hits[i].hitFraction (normally 1);
+ * convex hulls and spheres are tested, other shape types are ignored like in the reference; the hit normal of a hull
+ * is the face normal in the hull's LOCAL frame (reference quirk).  rays / hits are HOST arrays of numRays entries;
+ * hits of rays that hit nothing are left untouched. */
+int b3b200_cast_rays(b3b200_world* w, const b3b200_ray_info* rays, int numRays, b3b200_ray_hit* hits);
 /* b3GpuRigidBodyPipeline::setGravity (b3GpuRigidBodyPipeline.cpp:562-565) */
 int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
 int b3b200_set_solver(b3b200_world* w, int kind, int iterations);

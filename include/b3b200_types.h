@@ -238,6 +238,23 @@ typedef struct B3B200_ALIGN16 b3b200_generic_constraint
 	int padding[2];
 } b3b200_generic_constraint;
 
+/* b3RayInfo / b3RayHit (src/Bullet3Collision/NarrowPhaseCollision/b3RaycastInfo.h:7-23) */
+typedef struct B3B200_ALIGN16 b3b200_ray_info
+{
+	b3b200_float4 from;
+	b3b200_float4 to;
+} b3b200_ray_info;
+
+typedef struct B3B200_ALIGN16 b3b200_ray_hit
+{
+	float hitFraction;
+	int hitBody;
+	int hitResult1;
+	int hitResult2;
+	b3b200_float4 hitPoint;
+	b3b200_float4 hitNormal;
+} b3b200_ray_hit;
+
 typedef struct b3b200_sort_data
 {
 	unsigned int key;
@@ -262,6 +279,8 @@ static_assert(sizeof(b3b200_bvh_subtree) == 32, "abi");
 static_assert(sizeof(b3b200_bvh_info) == 64, "abi");
 static_assert(sizeof(b3b200_sort_data) == 8, "abi");
 static_assert(sizeof(b3b200_generic_constraint) == 80, "abi");
+static_assert(sizeof(b3b200_ray_info) == 32, "abi");
+static_assert(sizeof(b3b200_ray_hit) == 48, "abi");
 #endif
 
 #endif /* B3B200_TYPES_H */

@@ -2039,3 +2039,96 @@ extern "C" void orc_solve_joints(b3b200_rigid_body* bodies, int numBodies, const
 		bodies[i].angVel.z += dAng[i].z;
 	}
 }
+
+// ---------------------------------------------------------------------------------------------
+// b3GpuRaycast::castRaysHost (src/Bullet3OpenCL/Raycast/b3GpuRaycast.cpp:160-246) with rayConvex (:123-158) and
+// sphere_intersect (:99-121).  One deliberate difference: the reference's SHAPE_SPHERE case has no `break` and falls
+// through into the convex test with the sphere collidable's shape index; that accident is not restated.
+extern "C" void orc_cast_rays(const b3b200_ray_info* rays, int numRays, b3b200_ray_hit* hits, const b3b200_rigid_body* bodies, int numBodies,
+							  const b3b200_collidable* collidables, const b3b200_convex_polyhedron* convex, const b3b200_face* faces)
+{
+	for (int r = 0; r < numRays; r++)
+	{
+		V3 rayFrom = ld(rays[r].from), rayTo = ld(rays[r].to);
+		float hitFraction = hits[r].hitFraction;
+		int hitBodyIndex = -1;
+		V3 hitNormal = mk(0, 0, 0);
+		for (int b = 0; b < numBodies; b++)
+		{
+			const b3b200_collidable& col = collidables[bodies[b].collidableIdx];
+			V3 pos = ld(bodies[b].pos);
+			if (col.shapeType == B3B200_SHAPE_SPHERE)
+			{
+				float radius = col.radius;
+				V3 rs = sub(rayFrom, pos), rayDir = sub(rayTo, rayFrom);
+				float A = dot(rayDir, rayDir), B = dot(rs, rayDir), C = dot(rs, rs) - (radius * radius);
+				float D = B * B - A * C;
+				if (D > 0.0f)
+				{
+					float t = (-B - sqrtf(D)) / A;
+					if ((t >= 0.0f) && (t < hitFraction))
+					{
+						hitFraction = t;
+						hitBodyIndex = b;
+						float s = 1.0f - t;
+						V3 hp = mk(s * rayFrom.x + t * rayTo.x, s * rayFrom.y + t * rayTo.y, s * rayFrom.z + t * rayTo.z);
+						hitNormal = normalized(sub(hp, pos));
+					}
+				}
+			}
+			else if (col.shapeType == B3B200_SHAPE_CONVEX_HULL)
+			{
+				M3 basis = matFromQuat(ld(bodies[b].quat)), inv = transposeM(basis);
+				V3 invOrigin = matMul(inv, neg(mk(pos.x, pos.y, pos.z)));
+				V3 fromL = add(matMul(inv, rayFrom), invOrigin), toL = add(matMul(inv, rayTo), invOrigin);
+				const b3b200_convex_polyhedron& poly = convex[col.shapeIndex];
+				float exitFraction = hitFraction, enterFraction = -0.1f;
+				V3 curHitNormal = mk(0, 0, 0);
+				bool hit = true;
+				for (int i = 0; i < poly.numFaces && hit; i++)
+				{
+					const b3b200_float4& pl = faces[poly.faceOffset + i].plane;
+					V3 n = mk(pl.x, pl.y, pl.z);
+					float fromPlaneDist = dot(fromL, n) + pl.w, toPlaneDist = dot(toL, n) + pl.w;
+					if (fromPlaneDist < 0.f)
+					{
+						if (toPlaneDist >= 0.f)
+						{
+							float fraction = fromPlaneDist / (fromPlaneDist - toPlaneDist);
+							if (exitFraction > fraction) exitFraction = fraction;
+						}
+					}
+					else
+					{
+						if (toPlaneDist < 0.f)
+						{
+							float fraction = fromPlaneDist / (fromPlaneDist - toPlaneDist);
+							if (enterFraction <= fraction)
+							{
+								enterFraction = fraction;
+								curHitNormal = n;
+							}
+						}
+						else
+							hit = false;
+					}
+					if (exitFraction <= enterFraction) hit = false;
+				}
+				if (hit && !(enterFraction < 0.f))
+				{
+					hitFraction = enterFraction;
+					hitNormal = curHitNormal;
+					hitBodyIndex = b;
+				}
+			}
+		}
+		if (hitBodyIndex >= 0)
+		{
+			float s = 1.0f - hitFraction;
+			hits[r].hitFraction = hitFraction;
+			hits[r].hitPoint = st(mk(s * rayFrom.x + hitFraction * rayTo.x, s * rayFrom.y + hitFraction * rayTo.y, s * rayFrom.z + hitFraction * rayTo.z));
+			hits[r].hitNormal = st(hitNormal);
+			hits[r].hitBody = hitBodyIndex;
+		}
+	}
+}

@@ -5,6 +5,7 @@
 //   refcl_pgs_solve         b3Solver::convertToConstraints (gConvertConstraintOnCpu) + solveContactConstraintHost
 //                           (b3Solver.cpp:889-933, 468-637)
 //   refcl_radix_sort / scan / bound_search   the executeHost twins of ParallelPrimitives
+//   refcl_cast_rays_host    b3GpuRaycast::castRaysHost (b3GpuRaycast.cpp:173-246) on the shapes/bodies of a refcl_np handle
 //   refcl_np_*              b3GpuNarrowPhase + GpuSatCollision built with -DCHECK_ON_HOST: shape registration
 //                           (incl. the compound / mesh BVH builders) and the host contact loop
 //                           (b3ConvexHullContact.cpp:2595-2748)
@@ -19,6 +20,7 @@
 #include "Bullet3OpenCL/RigidBody/b3Solver.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhaseInternalData.h"
+#include "Bullet3OpenCL/Raycast/b3GpuRaycast.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3Contact4.h"
 #include "Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h"
@@ -250,5 +252,22 @@ int refcl_np_get_table(void* h, int which, void* dst, int capacity, int* count)
 	int m = n < capacity ? n : capacity;
 	if (dst && m > 0 && src) memcpy(dst, src, (size_t)sz * m);
 	return 0;
+}
+// b3GpuRaycast::castRaysHost over the bodies and shape tables of this narrowphase (the caller's body state is taken first)
+void refcl_cast_rays_host(void* h, const b3b200_rigid_body* bodies, int numBodies, const b3b200_ray_info* rays, int numRays, b3b200_ray_hit* hits)
+{
+	RefNp* r = (RefNp*)h;
+	b3GpuNarrowPhaseInternalData* d = r->np->getInternalData();
+	for (int i = 0; i < numBodies && i < d->m_bodyBufferCPU->size(); i++) memcpy(&d->m_bodyBufferCPU->at(i), &bodies[i], sizeof(b3RigidBodyData));
+	b3AlignedObjectArray<b3RayInfo> in;
+	b3AlignedObjectArray<b3RayHit> out;
+	in.resize(numRays);
+	out.resize(numRays);
+	if (numRays) memcpy(&in[0], rays, sizeof(b3RayInfo) * (size_t)numRays);
+	if (numRays) memcpy(&out[0], hits, sizeof(b3RayHit) * (size_t)numRays);
+	static b3GpuRaycast* rc = 0;
+	if (!rc) rc = new b3GpuRaycast(CTX, DEV, Q);
+	rc->castRaysHost(in, out, numBodies, &d->m_bodyBufferCPU->at(0), d->m_collidablesCPU.size(), &d->m_collidablesCPU[0], d);
+	if (numRays) memcpy(hits, &out[0], sizeof(b3RayHit) * (size_t)numRays);
 }
 }

@@ -89,6 +89,30 @@ static bool meshScene(bool useUniformGrid)
 		float ground = 0.8f * sinf(0.4f * b[i].m_pos.x) * cosf(0.4f * b[i].m_pos.z);
 		if (fabsf(b[i].m_pos.x) < 12 && fabsf(b[i].m_pos.z) < 12 && b[i].m_pos.y > ground - 0.2f && b[i].m_pos.y < ground + 3.f) resting++;
 	}
+	// picking rays straight down on every box body (GpuRigidBodyDemo-style mouse pick, b3GpuRigidBodyPipeline::castRays): the box
+	// under the ray, or one resting on top of it, must be reported; compounds and the mesh are skipped like in the reference
+	b3AlignedObjectArray<b3RayInfo> rays;
+	b3AlignedObjectArray<b3RayHit> hits;
+	b3AlignedObjectArray<int> target;
+	for (int i = 1; i < pipe->getNumBodies(); i++)
+	{
+		if (np->getCollidablesCpu()[b[i].m_collidableIdx].m_shapeType != SHAPE_CONVEX_HULL) continue;
+		b3RayInfo r;
+		r.m_from = b3MakeVector3(b[i].m_pos.x, 50.f, b[i].m_pos.z);
+		r.m_to = b3MakeVector3(b[i].m_pos.x, -50.f, b[i].m_pos.z);
+		b3RayHit h;
+		h.m_hitFraction = 1.f;
+		h.m_hitBody = -1;
+		rays.push_back(r);
+		hits.push_back(h);
+		target.push_back(i);
+	}
+	pipe->castRays(rays, hits);
+	int picked = 0;
+	for (int i = 0; i < rays.size(); i++)
+		if (hits[i].m_hitBody > 0 && hits[i].m_hitPoint.y >= b[target[i]].m_pos.y && hits[i].m_hitFraction < 0.5f) picked++;
+	printf("mesh scene: %d picking rays, %d hit a box at or above their target\n", rays.size(), picked);
+	jointsOk = jointsOk && rays.size() > 0 && picked == rays.size();
 	printf("mesh scene: shapes mesh=%d box=%d compound=%d sphere=%d, bodies=%d, contacts=%d, resting on the mesh=%d\n", meshShape, smallBox, compound, sphere,
 		   pipe->getNumBodies(), np->getNumContactsGpu(), resting);
 	bool ok = meshShape >= 0 && meshBody == 0 && compound > smallBox && sphere > compound && pipe->getNumBodies() == n + 1 && np->getNumContactsGpu() >= n / 2 &&

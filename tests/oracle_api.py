@@ -310,3 +310,34 @@ def solve_joints_ref(bodies, inertias, joints):
     inert = _arr(inertias, capi.inertia_t).copy()
     ref().ref_solve_joints_p2p(P(b), P(inert), len(b), P(j), len(j))
     return b
+
+
+def make_rays(ray_from, ray_to, max_fraction=1.0):
+    f = np.asarray(ray_from, np.float32).reshape(-1, 3)
+    t = np.asarray(ray_to, np.float32).reshape(-1, 3)
+    rays = np.zeros(len(f), capi.ray_info_t)
+    rays["from"][:, :3] = f
+    rays["to"][:, :3] = t
+    hits = np.zeros(len(f), capi.ray_hit_t)
+    hits["hitFraction"] = max_fraction
+    hits["hitBody"] = -1
+    return rays, hits
+
+
+def cast_rays_oracle(ray_from, ray_to, bodies, shapes, max_fraction=1.0):
+    """b3GpuRaycast::castRaysHost restated (orc_cast_rays): closest hit over all bodies, first body wins ties"""
+    rays, hits = make_rays(ray_from, ray_to, max_fraction)
+    b = _arr(bodies, capi.rigid_body_t)
+    oracle().orc_cast_rays(P(rays), len(rays), P(hits), P(b), len(b), P(shapes.collidables), P(shapes.convex), P(shapes.faces))
+    return hits
+
+
+def _ref_cast_rays(self, ray_from, ray_to, bodies, max_fraction=1.0):
+    """the reference's own b3GpuRaycast::castRaysHost on this narrowphase's shapes"""
+    rays, hits = make_rays(ray_from, ray_to, max_fraction)
+    b = _arr(bodies, capi.rigid_body_t)
+    self.L.refcl_cast_rays_host(self.h, P(b), len(b), P(rays), len(rays), P(hits))
+    return hits
+
+
+RefNarrowphase.cast_rays = _ref_cast_rays

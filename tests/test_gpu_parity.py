@@ -806,3 +806,85 @@ def oa_rotate(q, v):
     x, y, z, w_ = [float(t) for t in q]
     u = np.array([x, y, z])
     return v + 2 * np.cross(u, np.cross(u, v) + w_ * v)
+
+
+# ------------------------------------------------------------------ raycast (b3GpuRigidBodyPipeline::castRays)
+def ray_bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_hits_equal(g, o):
+    assert np.array_equal(g["hitBody"], o["hitBody"])
+    assert np.array_equal(ray_bits(g["hitFraction"]), ray_bits(o["hitFraction"]))
+    hit = o["hitBody"] >= 0
+    assert np.array_equal(ray_bits(g["hitPoint"][hit, :3]), ray_bits(o["hitPoint"][hit, :3]))
+    assert np.array_equal(ray_bits(g["hitNormal"][hit, :3]), ray_bits(o["hitNormal"][hit, :3]))
+
+
+@pytest.mark.parametrize("seed,plane", [(0, True), (1, False)])
+def test_cast_rays_match_oracle(seed, plane):
+    """hulls + spheres are hit, planes / compounds are skipped like the reference's `default:` case"""
+    w, sh, bodies = sphere_world(seed, n=700, plane=plane)
+    rng = np.random.default_rng(50 + seed)
+    n = 5000
+    frm = rng.uniform(-6, 6, (n, 3)).astype(np.float32)
+    to = rng.uniform(-6, 6, (n, 3)).astype(np.float32)
+    frm[:, 1] = rng.uniform(0.2, 6, n)
+    to[:, 1] = rng.uniform(0.2, 4, n)
+    g = w.cast_rays(frm, to)
+    o = oa.cast_rays_oracle(frm, to, bodies, sh)
+    assert (o["hitBody"] >= 0).sum() > n // 4 and (o["hitBody"] < 0).sum() > n // 20
+    assert_hits_equal(g, o)
+    # capped rays: hits beyond the cap leave the record untouched
+    g2 = w.cast_rays(frm, to, max_fraction=0.3)
+    o2 = oa.cast_rays_oracle(frm, to, bodies, sh, max_fraction=0.3)
+    assert_hits_equal(g2, o2)
+    assert np.all(g2["hitFraction"][g2["hitBody"] < 0] == np.float32(0.3))
+
+
+def test_cast_rays_after_stepping_and_edge_cases():
+    w, sh, bodies = sphere_world(2, n=400, plane=True)
+    assert len(w.cast_rays(np.zeros((0, 3)), np.zeros((0, 3)))) == 0
+    for _ in range(20):
+        w.step(1 / 60)
+    b = w.bodies()
+    rng = np.random.default_rng(9)
+    # vertical picking rays from above: every ray over a hull / sphere body must report the topmost one
+    frm = np.stack([rng.uniform(-5, 5, 3000), np.full(3000, 30.0), rng.uniform(-5, 5, 3000)], 1).astype(np.float32)
+    to = frm.copy()
+    to[:, 1] = -1.0
+    g = w.cast_rays(frm, to)
+    o = oa.cast_rays_oracle(frm, to, b, sh)
+    assert (o["hitBody"] >= 0).sum() > 500
+    assert_hits_equal(g, o)
+    # degenerate ray (from == to) hits nothing
+    z = w.cast_rays(frm[:4], frm[:4])
+    assert np.all(z["hitBody"] == -1)
+
+
+def test_cast_rays_many_bodies_chunked():
+    """more bodies than one candidate chunk (2048) and ties between coincident bodies -> lowest index wins"""
+    rng = np.random.default_rng(3)
+    w = capi.World(capi.default_config(8192))
+    box = w.register_convex_points(scenes.box_points(0.4))
+    sph = w.register_sphere(0.4)
+    for i in range(5000):
+        p = (rng.uniform(-20, 20), rng.uniform(0, 10), rng.uniform(-20, 20))
+        w.register_instance(1.0, p, scenes.random_quat(rng), box if i % 3 else sph)
+    # exact duplicates of the first 50 bodies, placed after them
+    t0 = w.tables()["bodies"]
+    for i in range(50):
+        w.register_instance(1.0, tuple(t0["pos"][i, :3]), tuple(t0["quat"][i]), box if i % 3 else sph)
+    w.upload()
+    t = w.tables()
+    sh, bodies = oa.Shapes(t), t["bodies"]
+    n = 4000
+    frm = rng.uniform(-22, 22, (n, 3)).astype(np.float32)
+    to = rng.uniform(-22, 22, (n, 3)).astype(np.float32)
+    # aim a block of rays straight at the duplicated bodies
+    to[:50] = bodies["pos"][:50, :3]
+    frm[:50] = bodies["pos"][:50, :3] + np.float32([0, 15, 0])
+    g = w.cast_rays(frm, to)
+    o = oa.cast_rays_oracle(frm, to, bodies, sh)
+    assert (o["hitBody"][:50] >= 0).all() and (o["hitBody"][:50] < 5000).all()
+    assert_hits_equal(g, o)
