@@ -75,6 +75,7 @@ SYMBOLS = [
     "b3b200_bp_write_aabbs", "b3b200_bp_set_aabbs", "b3b200_bp_calculate_pairs", "b3b200_bp_num_overlap", "b3b200_bp_get_pairs",
     "b3b200_bp_device_pairs", "b3b200_bp_device_aabbs", "b3b200_bp_last_ms", "b3b200_radix_sort_kv", "b3b200_radix_sort_keys",
     "b3b200_prefix_scan_u32", "b3b200_bound_search_count", "b3b200_fill_u32",
+    "b3b200_register_concave_obj", "b3b200_checkpoint_save", "b3b200_checkpoint_load", "b3b200_copy_transforms",
 ]
 
 _lib = None
@@ -199,6 +200,15 @@ class World:
         r = self.L.b3b200_register_concave(self.h, ptr(v), len(v), ptr(i), len(i), sc)
         if r < 0:
             raise B3Error("register_concave: " + last_error())
+        return r
+
+    def register_concave_obj(self, path, shift=(0.0, 0.0, 0.0), scaling=(1.0, 1.0, 1.0)):
+        """Wavefront .obj -> trimesh collidable (ConcaveScene::createConcaveMesh recipe)"""
+        sh = (C.c_float * 3)(*[float(x) for x in shift])
+        sc = (C.c_float * 3)(*[float(x) for x in scaling])
+        r = self.L.b3b200_register_concave_obj(self.h, str(path).encode(), sh, sc)
+        if r < 0:
+            raise B3Error("register_concave_obj: " + last_error())
         return r
 
     # ---- bodies
@@ -416,6 +426,16 @@ class World:
 
     def tables(self):
         return {k: self.table(k) for k in self.TABLES}
+
+    def checkpoint_save(self, path):
+        check(self.L.b3b200_checkpoint_save(self.h, str(path).encode()), "checkpoint_save")
+
+    def checkpoint_load(self, path):
+        check(self.L.b3b200_checkpoint_load(self.h, str(path).encode()), "checkpoint_load")
+
+    def copy_transforms(self, dst_device_ptr, num_nodes):
+        """copyTransformsToVBOKernel: (pos.xyz, 1) then orientations into a device buffer of 2 * num_nodes float4"""
+        check(self.L.b3b200_copy_transforms(self.h, C.c_void_p(int(dst_device_ptr)), int(num_nodes)), "copy_transforms")
 
     def device_buffer(self, which):
         p = C.c_void_p()

@@ -1013,9 +1013,8 @@ __global__ void clampConcaveKernel(unsigned int* ctr, int maxItems)
 }
 }  // namespace
 
-int launchConcave(World* w)
+int launchConcave(World* w, cudaStream_t s)
 {
-	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_PAIRS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_SURVIVORS], 0, sizeof(unsigned int), s));
 	CcArgs a;

@@ -1640,9 +1640,21 @@ int launchNarrowphase(World* w)
 	a.maxWorkItems = (int)w->dSurvivors.cap;
 	a.clipMin = w->clipMinDist;
 	a.clipMax = w->clipMaxDist;
+	// Branches (they share no buffer; contacts are appended through one atomic counter):
+	//   P  npPrimitiveKernel                       (pairs only)
+	//   C  trimesh chain                           (after npCullKernel listed the trimesh pairs)
+	//   S  smallPairKernel                         (after both cull kernels filled the small-item list)
+	//   M  satKernel -> clipKernel on `s`          (after npChildCullKernel released the raw queue = overlap list)
+	const bool fork = w->npOverlap;
+	cudaStream_t sP = fork ? w->npStream[0] : s, sC = fork ? w->npStream[1] : s, sS = fork ? w->npStream[2] : s;
+	if (fork)
+	{
+		B3_CUDA_CHECK(cudaEventRecord(w->evNpFork[0], s));  // counters cleared, pairs final
+		B3_CUDA_CHECK(cudaStreamWaitEvent(sP, w->evNpFork[0], 0));
+	}
 	if (w->hasPlanes)
 	{
-		npPrimitiveKernel<<<w->smCount * 8, 128, 0, s>>>(a);
+		npPrimitiveKernel<<<w->smCount * 8, 128, 0, sP>>>(a);
 		B3_LAUNCH_CHECK();
 	}
 	// the overlap list is not live yet: it doubles as the raw child-item queue of compound pairs
@@ -1650,20 +1662,40 @@ int launchNarrowphase(World* w)
 	npCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->hasConcave ? reinterpret_cast<int*>(w->dConcaveSurvivors.ptr) : nullptr,
 														 w->hasConcave ? (int)(w->dConcaveSurvivors.cap * 4) : 0, w->dSmallItems.ptr);
 	B3_LAUNCH_CHECK();
+	if (w->hasConcave && fork)
+	{
+		B3_CUDA_CHECK(cudaEventRecord(w->evNpFork[1], s));
+		B3_CUDA_CHECK(cudaStreamWaitEvent(sC, w->evNpFork[1], 0));
+		B3_TRY(launchConcave(w, sC));
+	}
 	if (!w->childShapes.empty())
 	{
 		npChildCullKernel<<<w->smCount * 8, CULL_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dSurvivors.ptr, w->dSmallItems.ptr);
 		B3_LAUNCH_CHECK();
 	}
-	smallPairKernel<<<w->smCount * 16, 128, 0, s>>>(a, w->dSmallItems.ptr);
+	if (fork)
+	{
+		B3_CUDA_CHECK(cudaEventRecord(w->evNpFork[0], s));
+		B3_CUDA_CHECK(cudaStreamWaitEvent(sS, w->evNpFork[0], 0));
+	}
+	smallPairKernel<<<w->smCount * 16, 128, 0, sS>>>(a, w->dSmallItems.ptr);
 	B3_LAUNCH_CHECK();
-	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[0], s));  // stage_timings()[7] = this kernel alone
+	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[0], s));  // stage_timings()[7] = this kernel (alone only without the forks)
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[1], s));
 	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
-	if (w->hasConcave) B3_TRY(launchConcave(w));
+	if (w->hasConcave && !fork) B3_TRY(launchConcave(w, s));
+	if (fork)
+	{
+		cudaStream_t side[3] = {sP, sC, sS};
+		for (int i = 0; i < 3; i++)
+		{
+			B3_CUDA_CHECK(cudaEventRecord(w->evNpJoin[i], side[i]));
+			B3_CUDA_CHECK(cudaStreamWaitEvent(s, w->evNpJoin[i], 0));
+		}
+	}
 	clampContactsKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, w->cfg.maxContactCapacity, a.maxWorkItems);
 	B3_LAUNCH_CHECK();
 	return 0;

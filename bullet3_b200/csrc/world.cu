@@ -54,6 +54,10 @@ int World::init(const b3b200_config* c, int dev, cudaStream_t st)
 	B3_CUDA_CHECK(cudaMemsetAsync(dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, stream));
 	for (int i = 0; i < 8; i++) B3_CUDA_CHECK(cudaEventCreate(&ev[i]));
 	for (int i = 0; i < 2; i++) B3_CUDA_CHECK(cudaEventCreate(&evSat[i]));
+	for (int i = 0; i < 3; i++) B3_CUDA_CHECK(cudaStreamCreateWithFlags(&npStream[i], cudaStreamNonBlocking));
+	for (int i = 0; i < 2; i++) B3_CUDA_CHECK(cudaEventCreateWithFlags(&evNpFork[i], cudaEventDisableTiming));
+	for (int i = 0; i < 3; i++) B3_CUDA_CHECK(cudaEventCreateWithFlags(&evNpJoin[i], cudaEventDisableTiming));
+	if (const char* e = getenv("B3B200_NP_OVERLAP")) npOverlap = atoi(e) != 0;
 	return 0;
 }
 
@@ -66,6 +70,18 @@ void World::destroy()
 		if (ev[i]) cudaEventDestroy(ev[i]);
 	for (int i = 0; i < 2; i++)
 		if (evSat[i]) cudaEventDestroy(evSat[i]);
+	for (int i = 0; i < 3; i++)
+	{
+		if (npStream[i]) cudaStreamSynchronize(npStream[i]), cudaStreamDestroy(npStream[i]);
+		if (evNpJoin[i]) cudaEventDestroy(evNpJoin[i]);
+		npStream[i] = nullptr;
+		evNpJoin[i] = nullptr;
+	}
+	for (int i = 0; i < 2; i++)
+	{
+		if (evNpFork[i]) cudaEventDestroy(evNpFork[i]);
+		evNpFork[i] = nullptr;
+	}
 	cudaStream_t s = stream;
 	bool own = ownStream;
 	bp.stream = 0;  // shared with the world

@@ -232,6 +232,19 @@ int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, int numOwned
 int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int count, int firstGhostSlot, int numGhostSlots);
 int b3b200_halo_ghost_ids(b3b200_world* w, int* dst, int n);
 
+/* ---- the callers' data formats either side of the step ----
+ * Wavefront .obj -> trimesh collidable the way ConcaveScene::createConcaveMesh feeds registerConcaveMesh
+ * (examples/OpenCL/rigidbody/ConcaveScene.cpp:28-109, 111-158): one fresh vertex per face corner, polygons as fans,
+ * vertex = (p + shift) * scaling.  shift3 / scaling3 may be NULL.  Returns the collidable index or -1. */
+int b3b200_register_concave_obj(b3b200_world* w, const char* path, const float* shift3, const float* scaling3);
+/* body buffer + inertias + joints to / from a file.  load needs a world with the same shapes and body count. */
+int b3b200_checkpoint_save(b3b200_world* w, const char* path);
+int b3b200_checkpoint_load(b3b200_world* w, const char* path);
+/* copyTransformsToVBOKernel (examples/OpenCL/rigidbody/GpuRigidBodyDemo.cpp:52-60): dst[i] = (pos.xyz, 1),
+ * dst[i + numNodes] = orientation, for bodies [0, numNodes); dstDevice is a DEVICE pointer of 2 * numNodes float4
+ * (e.g. a mapped graphics-interop buffer); asynchronous on the world's stream. */
+int b3b200_copy_transforms(b3b200_world* w, void* dstDevice, int numNodes);
+
 /* plain device -> host copy of a buffer obtained from b3b200_device_buffer / b3b200_bp_device_* (synchronous) */
 int b3b200_device_to_host(void* dstHost, const void* srcDevice, unsigned long long bytes, int device);
 

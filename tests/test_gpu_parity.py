@@ -888,3 +888,70 @@ def test_cast_rays_many_bodies_chunked():
     o = oa.cast_rays_oracle(frm, to, bodies, sh)
     assert (o["hitBody"][:50] >= 0).all() and (o["hitBody"][:50] < 5000).all()
     assert_hits_equal(g, o)
+
+
+# ------------------------------------------------------------------ checkpoint / render interop
+def jointed_world(n):
+    w, _ = joint_world(0, n=n)
+    for i in range(1, n, 3):
+        w.create_p2p_constraint(i, i + 1 if i + 1 <= n else 0, (0.4, 0, 0), (-0.4, 0, 0), 50.0 if i % 2 else 1e30)
+    w.create_fixed_constraint(0, 1, (0, -1, 0), (0, 1, 0), (0, 0, 0, 1))
+    return w
+
+
+def test_checkpoint_roundtrip_restores_bodies_inertias_and_joints(tmp_path):
+    w = jointed_world(40)
+    w.set_solver(capi.SOLVER_PGS, 4)
+    for _ in range(30):
+        w.step(1 / 60)
+    path = tmp_path / "state.b3cp"
+    w.checkpoint_save(path)
+    saved_b, saved_j = w.bodies().copy(), w.joints().copy()
+    saved_i = w.inertias().copy()
+    for _ in range(20):
+        w.step(1 / 60)
+    assert not np.array_equal(w.bodies()["pos"], saved_b["pos"])
+    # restore into the same world and into a freshly built twin
+    w2 = jointed_world(40)
+    w2.remove_constraint(0)  # the file carries the joint set, whatever the target had
+    for target in (w, w2):
+        target.checkpoint_load(path)
+        assert np.array_equal(target.bodies().view(np.uint8), saved_b.view(np.uint8))
+        assert np.array_equal(target.inertias().view(np.uint8), saved_i.view(np.uint8))
+        assert np.array_equal(target.joints().view(np.uint8), saved_j.view(np.uint8))
+    # both continue from the same state: one more step of the (joint + contact) pipeline gives the same bodies
+    w.set_solver(capi.SOLVER_PGS, 4)
+    w2.set_solver(capi.SOLVER_PGS, 4)
+    w.step(1 / 60)
+    w2.step(1 / 60)
+    a, b = w.bodies(), w2.bodies()
+    assert rel_close(a["pos"], b["pos"], 1e-5) and rel_close(a["linVel"], b["linVel"], 1e-4)
+    # a world of another size refuses the file
+    w3 = jointed_world(12)
+    with pytest.raises(capi.B3Error):
+        w3.checkpoint_load(path)
+    with pytest.raises(capi.B3Error):
+        w.checkpoint_load(tmp_path / "missing.b3cp")
+
+
+def test_copy_transforms_matches_body_buffer():
+    import torch
+
+    w, sh, bodies, inert = gpu_world(6, 1)
+    for _ in range(5):
+        w.step(1 / 60)
+    n = len(bodies)
+    out = torch.full((2 * n, 4), -7.0, dtype=torch.float32, device="cuda:0")
+    w.copy_transforms(out.data_ptr(), n)
+    w.synchronize()
+    o = out.cpu().numpy()
+    b = w.bodies()
+    assert np.array_equal(o[:n, :3].view(np.uint32), b["pos"][:, :3].view(np.uint32))
+    assert np.all(o[:n, 3] == 1.0)
+    assert np.array_equal(o[n:].view(np.uint32), b["quat"].view(np.uint32))
+    # a prefix only: the rest of the buffer is untouched
+    out.fill_(-7.0)
+    w.copy_transforms(out.data_ptr(), 10)
+    w.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[10:20].view(np.uint32), b["quat"][:10].view(np.uint32)) and np.all(o[20:] == -7.0)

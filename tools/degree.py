@@ -15,3 +15,14 @@ ids = ids[inv[ids] != 0]
 deg = np.bincount(ids, minlength=len(b))
 print("contacts", len(c), "max degree", deg.max(), "batches", len(w.batches()) - 1)
 print("degree histogram", np.bincount(deg)[:40].tolist())
+# the same with all manifolds of one body pair merged into one group (one colour per pair instead of per manifold)
+a, bb = np.abs(c["bodyA"]).astype(np.int64), np.abs(c["bodyB"]).astype(np.int64)
+key = np.minimum(a, bb) * (1 << 32) + np.maximum(a, bb)
+uk, cnt = np.unique(key, return_counts=True)
+ga, gb = (uk >> 32).astype(np.int64), (uk & 0xFFFFFFFF).astype(np.int64)
+gid = np.concatenate([ga, gb])
+gid = gid[inv[gid] != 0]
+gdeg = np.bincount(gid, minlength=len(b))
+print("pair groups", len(uk), "max group degree", gdeg.max(), "group size histogram", np.bincount(cnt)[:40].tolist(), "max group", cnt.max())
+print("group degree histogram", np.bincount(gdeg)[:40].tolist())
+print("batch sizes", np.diff(w.batches()).tolist())
