@@ -68,7 +68,7 @@ SYMBOLS = [
     "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_solver_dataflow", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
     "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solve_joints", "b3b200_create_p2p_constraint", "b3b200_create_fixed_constraint", "b3b200_remove_constraint",
-    "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_solver_setup",
+    "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_set_ray_accel", "b3b200_solver_setup",
     "b3b200_solver_iterate", "b3b200_integrate", "b3b200_get_aabbs", "b3b200_get_pairs", "b3b200_get_contacts", "b3b200_set_contacts",
     "b3b200_get_constraints", "b3b200_get_batches", "b3b200_get_counters", "b3b200_get_work_counters", "b3b200_enable_stage_timing", "b3b200_stage_timings",
     "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
@@ -359,6 +359,9 @@ class World:
         hits["hitBody"] = -1
         check(self.L.b3b200_cast_rays(self.h, ptr(rays), len(rays), ptr(hits)), "cast_rays")
         return hits
+
+    def set_ray_accel(self, mode):
+        check(self.L.b3b200_set_ray_accel(self.h, int(mode)), "set_ray_accel")
 
     def work_counters(self):
         out = np.zeros(24, np.int32)

@@ -185,6 +185,11 @@ struct World
 	// raycast
 	DevBuf<float4> dRays, dRayHits;
 	DevBuf<unsigned long long> dRayBest;
+	// per-call linear BVH of the ray path (raycast.cu): Morton keys / order, leaf + chunk + super boxes, centre bounds
+	DevBuf<unsigned int> dRayKeys, dRayOrder, dRayBounds;
+	DevBuf<float4> dRayTree;
+	RadixSortTemp raySortTmp;
+	int rayAccel = -1;
 	// jacobi
 	DevBuf<unsigned int> dBodyCount, dBodyOffset;
 	DevBuf<float4> dDeltaLin, dDeltaAng;

@@ -120,6 +120,10 @@ int b3b200_get_joints(b3b200_world* w, b3b200_generic_constraint* dst, int capac
  * is the face normal in the hull's LOCAL frame (reference quirk).  rays / hits are HOST arrays of numRays entries;
  * hits of rays that hit nothing are left untouched. */
 int b3b200_cast_rays(b3b200_world* w, const b3b200_ray_info* rays, int numRays, b3b200_ray_hit* hits);
+/* how cast_rays culls: -1 (default) = per call: a linear BVH over the Morton-sorted bodies, rebuilt for the call (the role of
+ * b3GpuParallelLinearBvh), when there are >= 64 rays and >= 4096 dynamic bodies, else brute force over the world AABBs;
+ * 0 = always brute force; 1 = always the tree.  The results are identical. */
+int b3b200_set_ray_accel(b3b200_world* w, int mode);
 /* b3GpuRigidBodyPipeline::setGravity (b3GpuRigidBodyPipeline.cpp:562-565) */
 int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
 int b3b200_set_solver(b3b200_world* w, int kind, int iterations);

@@ -831,15 +831,19 @@ def test_cast_rays_match_oracle(seed, plane):
     to = rng.uniform(-6, 6, (n, 3)).astype(np.float32)
     frm[:, 1] = rng.uniform(0.2, 6, n)
     to[:, 1] = rng.uniform(0.2, 4, n)
-    g = w.cast_rays(frm, to)
     o = oa.cast_rays_oracle(frm, to, bodies, sh)
     assert (o["hitBody"] >= 0).sum() > n // 4 and (o["hitBody"] < 0).sum() > n // 20
-    assert_hits_equal(g, o)
-    # capped rays: hits beyond the cap leave the record untouched
-    g2 = w.cast_rays(frm, to, max_fraction=0.3)
     o2 = oa.cast_rays_oracle(frm, to, bodies, sh, max_fraction=0.3)
-    assert_hits_equal(g2, o2)
-    assert np.all(g2["hitFraction"][g2["hitBody"] < 0] == np.float32(0.3))
+    o3 = oa.cast_rays_oracle(frm, to, bodies, sh, max_fraction=1.7)
+    for accel in (0, 1):  # brute force over the world AABBs / linear BVH: same answers
+        w.set_ray_accel(accel)
+        assert_hits_equal(w.cast_rays(frm, to), o)
+        # capped rays: hits beyond the cap leave the record untouched
+        g2 = w.cast_rays(frm, to, max_fraction=0.3)
+        assert_hits_equal(g2, o2)
+        assert np.all(g2["hitFraction"][g2["hitBody"] < 0] == np.float32(0.3))
+        # a cap beyond the end point extends the ray like in the reference (t is only compared with the cap)
+        assert_hits_equal(w.cast_rays(frm, to, max_fraction=1.7), o3)
 
 
 def test_cast_rays_after_stepping_and_edge_cases():
@@ -853,10 +857,11 @@ def test_cast_rays_after_stepping_and_edge_cases():
     frm = np.stack([rng.uniform(-5, 5, 3000), np.full(3000, 30.0), rng.uniform(-5, 5, 3000)], 1).astype(np.float32)
     to = frm.copy()
     to[:, 1] = -1.0
-    g = w.cast_rays(frm, to)
     o = oa.cast_rays_oracle(frm, to, b, sh)
     assert (o["hitBody"] >= 0).sum() > 500
-    assert_hits_equal(g, o)
+    for accel in (0, 1):
+        w.set_ray_accel(accel)
+        assert_hits_equal(w.cast_rays(frm, to), o)
     # degenerate ray (from == to) hits nothing
     z = w.cast_rays(frm[:4], frm[:4])
     assert np.all(z["hitBody"] == -1)
@@ -884,10 +889,11 @@ def test_cast_rays_many_bodies_chunked():
     # aim a block of rays straight at the duplicated bodies
     to[:50] = bodies["pos"][:50, :3]
     frm[:50] = bodies["pos"][:50, :3] + np.float32([0, 15, 0])
-    g = w.cast_rays(frm, to)
     o = oa.cast_rays_oracle(frm, to, bodies, sh)
     assert (o["hitBody"][:50] >= 0).all() and (o["hitBody"][:50] < 5000).all()
-    assert_hits_equal(g, o)
+    for accel in (-1, 0, 1):
+        w.set_ray_accel(accel)
+        assert_hits_equal(w.cast_rays(frm, to), o)
 
 
 # ------------------------------------------------------------------ checkpoint / render interop

@@ -26,7 +26,8 @@ rng = np.random.default_rng(0)
 frm = np.tile(np.float32([(lo[0] + hi[0]) / 2, hi[1] + 40.0, (lo[2] + hi[2]) / 2]), (nrays, 1))
 to = rng.uniform(lo, hi, (nrays, 3)).astype(np.float32)
 to = frm + (to - frm) * 1.5
-for rep in range(3):
+for rep in range(6):
+    w.set_ray_accel(0 if rep < 2 else 1)
     t0 = time.perf_counter()
     h = w.cast_rays(frm, to)
     dt = time.perf_counter() - t0
