@@ -33,7 +33,8 @@
 namespace b3b200
 {
 constexpr int SOLVER_THREADS = 512;
-constexpr int TAIL_ROWS = SOLVER_THREADS;  // batches up to one row per thread are cheaper to solve in one CTA (measured 1.7 us
+constexpr int ITER_THREADS = 512;
+constexpr int TAIL_ROWS = ITER_THREADS;  // batches up to one row per thread are cheaper to solve in one CTA (measured 1.7 us
                                            // per phase) than to pay a grid barrier for (3.5 us); two rows per thread cost 5.5 us
 constexpr int MAX_ROUNDS = 1024;
 constexpr int TAIL_COLOUR = 2048;  // colouring rounds with at most this many contacts left run in CTA 0 alone
@@ -517,161 +518,28 @@ struct IterArgs
 	unsigned int* seq;                   // per-body progress counter (dataflow kernel)
 };
 
-// solveContact<false> (b3Solver.cpp:187-266)
-B3_D void solveNormalRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs)
+// Iteration arithmetic: explicit FMAs.  This file is built with --fmad=false, so the only fused operations are the
+// ones written here and every kernel that inlines these helpers (barrier kernel, its one-CTA tail, dataflow kernel)
+// produces the same bits for the same Gauss-Seidel order.  (The oracle evaluates the reference's unfused expressions;
+// the bar for velocities is 1e-4 relative.)
+B3_D float fdot3(const float4& a, const float4& b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
+B3_D float4 fcross3(const float4& a, const float4& b)
 {
-	float4* cw = reinterpret_cast<float4*>(cs);
-	const float4 lin = cw[0];
-	const float4 jac = cw[6];
-	const float4 bias = cw[7];
-	float4 applied = cw[8];
-	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
-	const int aIdx = tail.x, bIdx = tail.y;
-	if (aIdx < 0) return;  // padding slot
-	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
-	const float invMassA = posA.w, invMassB = posB.w;
-	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
-	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
-	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
-	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
-	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
-	const float4 ib0 = __ldg(IB), ib1 = __ldg(IB + 1), ib2 = __ldg(IB + 2);
-	const float4 n = mk4(lin.x, lin.y, lin.z);
-	const float4 nn = neg3(n);
-	const float jacv[4] = {jac.x, jac.y, jac.z, jac.w};
-	const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
-	float ap[4] = {applied.x, applied.y, applied.z, applied.w};
-#pragma unroll
-	for (int ic = 0; ic < 4; ic++)
-	{
-		if (jacv[ic] == 0.f) continue;
-		const float4 wp = cw[1 + ic];
-		float4 r0 = sub3(wp, posA), r1 = sub3(wp, posB);
-		float4 angular0 = cross3(r0, n);
-		float4 angular1 = neg3(cross3(r1, n));
-		float rambdaDt = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
-		rambdaDt *= jacv[ic];
-		{
-			float prevSum = ap[ic];
-			float updated = prevSum;
-			updated += rambdaDt;
-			updated = fmaxf(updated, 0.f);
-			updated = fminf(updated, FLT_MAX);
-			rambdaDt = updated - prevSum;
-			ap[ic] = updated;
-		}
-		float4 linImp0 = scale3(scale3(n, invMassA), rambdaDt);
-		float4 linImp1 = scale3(scale3(nn, invMassB), rambdaDt);
-		float4 angImp0 = scale3(matRowMul(ia0, ia1, ia2, angular0), rambdaDt);
-		float4 angImp1 = scale3(matRowMul(ib0, ib1, ib2, angular1), rambdaDt);
-		linVelA = add3(linVelA, linImp0);
-		angVelA = add3(angVelA, angImp0);
-		linVelB = add3(linVelB, linImp1);
-		angVelB = add3(angVelB, angImp1);
-	}
-	cw[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
-	if (invMassA != 0.f)
-	{
-		__stcg(&s.vel[2 * aIdx], linVelA);
-		__stcg(&s.vel[2 * aIdx + 1], angVelA);
-	}
-	if (invMassB != 0.f)
-	{
-		__stcg(&s.vel[2 * bIdx], linVelB);
-		__stcg(&s.vel[2 * bIdx + 1], angVelB);
-	}
+	return mk4(__fmaf_rn(a.y, b.z, -(a.z * b.y)), __fmaf_rn(a.z, b.x, -(a.x * b.z)), __fmaf_rn(a.x, b.y, -(a.y * b.x)));
+}
+B3_D float4 fmatRowMul(const float4& r0, const float4& r1, const float4& r2, const float4& v) { return mk4(fdot3(r0, v), fdot3(r1, v), fdot3(r2, v)); }
+// v + (dir * k) * s
+B3_D float4 faddScaled(const float4& v, const float4& dir, float k, float s)
+{
+	return mk4(__fmaf_rn(dir.x * k, s, v.x), __fmaf_rn(dir.y * k, s, v.y), __fmaf_rn(dir.z * k, s, v.z));
+}
+B3_D float4 faddScaled1(const float4& v, const float4& dir, float s) { return mk4(__fmaf_rn(dir.x, s, v.x), __fmaf_rn(dir.y, s, v.y), __fmaf_rn(dir.z, s, v.z)); }
+B3_D float fcalcRelVel(const float4& l0, const float4& l1, const float4& a0, const float4& a1, const float4& linVel0, const float4& angVel0,
+					   const float4& linVel1, const float4& angVel1)
+{
+	return fdot3(l0, linVel0) + fdot3(a0, angVel0) + fdot3(l1, linVel1) + fdot3(a1, angVel1);
 }
 
-// solveFriction (b3Solver.cpp:268-329) with the limits of SolveTask::run (:384-402)
-B3_D void solveFrictionRows(const IterArgs& s, b3b200_constraint4* __restrict__ cs)
-{
-	float4* cw = reinterpret_cast<float4*>(cs);
-	float4 fr = cw[9];  // fJacCoeffInv[2], fAppliedRambdaDt[2]
-	if (fr.x == 0.f && fr.x == 0.f) return;
-	const float4 lin = cw[0];
-	const float4 center = cw[5];
-	const float4 applied = cw[8];
-	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
-	const int aIdx = tail.x, bIdx = tail.y;
-	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
-	const float invMassA = posA.w, invMassB = posB.w;
-	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
-	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
-	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[aIdx].invInertiaWorld);
-	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[bIdx].invInertiaWorld);
-	const float4 ia0 = __ldg(IA), ia1 = __ldg(IA + 1), ia2 = __ldg(IA + 2);
-	const float4 ib0 = __ldg(IB), ib1 = __ldg(IB + 1), ib2 = __ldg(IB + 2);
-
-	float sum = 0.f;
-	sum += applied.x;
-	sum += applied.y;
-	sum += applied.z;
-	sum += applied.w;
-	const float frictionCoeff = 0.7f;
-	const float maxR = frictionCoeff * sum;
-	const float minR = -maxR;
-
-	const float4 n = neg3(mk4(lin.x, lin.y, lin.z));
-	float4 tangent[2];
-	planeSpace1(n, tangent[0], tangent[1]);
-	const float4 r0 = sub3(center, posA), r1 = sub3(center, posB);
-	float fj[2] = {fr.x, fr.y};
-	float fa[2] = {fr.z, fr.w};
-#pragma unroll
-	for (int i = 0; i < 2; i++)
-	{
-		const float4 t = tangent[i];
-		const float4 angular0 = cross3(r0, t);
-		const float4 angular1 = neg3(cross3(r1, t));
-		float rambdaDt = calcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
-		rambdaDt *= fj[i];
-		{
-			float prevSum = fa[i];
-			float updated = prevSum;
-			updated += rambdaDt;
-			updated = fmaxf(updated, minR);
-			updated = fminf(updated, maxR);
-			rambdaDt = updated - prevSum;
-			fa[i] = updated;
-		}
-		float4 linImp0 = scale3(scale3(t, invMassA), rambdaDt);
-		float4 linImp1 = scale3(scale3(neg3(t), invMassB), rambdaDt);
-		float4 angImp0 = scale3(matRowMul(ia0, ia1, ia2, angular0), rambdaDt);
-		float4 angImp1 = scale3(matRowMul(ib0, ib1, ib2, angular1), rambdaDt);
-		linVelA = add3(linVelA, linImp0);
-		angVelA = add3(angVelA, angImp0);
-		linVelB = add3(linVelB, linImp1);
-		angVelB = add3(angVelB, angImp1);
-	}
-	{
-		// angular damping for point constraint (b3Solver.cpp:317-328)
-		float4 ab = normalized3(sub3(posB, posA));
-		float4 ac = normalized3(sub3(center, posA));
-		if (dot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
-		{
-			float angNA = dot3(n, angVelA);
-			float angNB = dot3(n, angVelB);
-			angVelA = sub3(angVelA, scale3(n, angNA * 0.1f));
-			angVelB = sub3(angVelB, scale3(n, angNB * 0.1f));
-		}
-	}
-	cw[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
-	if (invMassA != 0.f)
-	{
-		__stcg(&s.vel[2 * aIdx], linVelA);
-		__stcg(&s.vel[2 * aIdx + 1], angVelA);
-	}
-	if (invMassB != 0.f)
-	{
-		__stcg(&s.vel[2 * bIdx], linVelB);
-		__stcg(&s.vel[2 * bIdx + 1], angVelB);
-	}
-}
-
-// Everything a row needs that no other thread writes during the solve: the row itself (its lambdas are only ever
-// written by the thread that owns the row: the row -> thread mapping is the same in every iteration and phase), the
-// two body positions / inverse masses and inverse inertias.  It is loaded BEFORE the grid barrier of the previous
-// batch is waited for, so that after the barrier only the velocity loads are on the critical path.
 struct RowData
 {
 	float4 lin, wp0, wp1, wp2, wp3, center, jac, bias, applied, fr;
@@ -735,9 +603,9 @@ B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs,
 		if (jacv[ic] == 0.f) continue;
 		const float4 wp = ic == 0 ? r.wp0 : (ic == 1 ? r.wp1 : (ic == 2 ? r.wp2 : r.wp3));
 		float4 r0 = sub3(wp, r.posA), r1 = sub3(wp, r.posB);
-		float4 angular0 = cross3(r0, n);
-		float4 angular1 = neg3(cross3(r1, n));
-		float rambdaDt = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
+		float4 angular0 = fcross3(r0, n);
+		float4 angular1 = neg3(fcross3(r1, n));
+		float rambdaDt = fcalcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
 		rambdaDt *= jacv[ic];
 		{
 			float prevSum = ap[ic];
@@ -748,14 +616,10 @@ B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs,
 			rambdaDt = updated - prevSum;
 			ap[ic] = updated;
 		}
-		float4 linImp0 = scale3(scale3(n, invMassA), rambdaDt);
-		float4 linImp1 = scale3(scale3(nn, invMassB), rambdaDt);
-		float4 angImp0 = scale3(matRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
-		float4 angImp1 = scale3(matRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
-		linVelA = add3(linVelA, linImp0);
-		angVelA = add3(angVelA, angImp0);
-		linVelB = add3(linVelB, linImp1);
-		angVelB = add3(angVelB, angImp1);
+		linVelA = faddScaled(linVelA, n, invMassA, rambdaDt);
+		angVelA = faddScaled1(angVelA, fmatRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
+		linVelB = faddScaled(linVelB, nn, invMassB, rambdaDt);
+		angVelB = faddScaled1(angVelB, fmatRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
 	}
 	reinterpret_cast<float4*>(cs)[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
 	if (invMassA != 0.f)
@@ -770,7 +634,7 @@ B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs,
 	}
 }
 
-// solveFriction (b3Solver.cpp:268-329) on preloaded row data; same operation order as solveFrictionRows
+// solveFriction (b3Solver.cpp:268-329) on preloaded row data; explicit FMAs (see fdot3)
 B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
 {
 	const float4 fr = r.fr;
@@ -798,9 +662,9 @@ B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ c
 	for (int i = 0; i < 2; i++)
 	{
 		const float4 t = tangent[i];
-		const float4 angular0 = cross3(r0, t);
-		const float4 angular1 = neg3(cross3(r1, t));
-		float rambdaDt = calcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
+		const float4 angular0 = fcross3(r0, t);
+		const float4 angular1 = neg3(fcross3(r1, t));
+		float rambdaDt = fcalcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
 		rambdaDt *= fj[i];
 		{
 			float prevSum = fa[i];
@@ -811,25 +675,21 @@ B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ c
 			rambdaDt = updated - prevSum;
 			fa[i] = updated;
 		}
-		float4 linImp0 = scale3(scale3(t, invMassA), rambdaDt);
-		float4 linImp1 = scale3(scale3(neg3(t), invMassB), rambdaDt);
-		float4 angImp0 = scale3(matRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
-		float4 angImp1 = scale3(matRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
-		linVelA = add3(linVelA, linImp0);
-		angVelA = add3(angVelA, angImp0);
-		linVelB = add3(linVelB, linImp1);
-		angVelB = add3(angVelB, angImp1);
+		linVelA = faddScaled(linVelA, t, invMassA, rambdaDt);
+		angVelA = faddScaled1(angVelA, fmatRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
+		linVelB = faddScaled(linVelB, neg3(t), invMassB, rambdaDt);
+		angVelB = faddScaled1(angVelB, fmatRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
 	}
 	{
 		// angular damping for point constraint (b3Solver.cpp:317-328)
 		float4 ab = normalized3(sub3(posB, posA));
 		float4 ac = normalized3(sub3(r.center, posA));
-		if (dot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
+		if (fdot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
 		{
-			float angNA = dot3(n, angVelA);
-			float angNB = dot3(n, angVelB);
-			angVelA = sub3(angVelA, scale3(n, angNA * 0.1f));
-			angVelB = sub3(angVelB, scale3(n, angNB * 0.1f));
+			float angNA = fdot3(n, angVelA);
+			float angNB = fdot3(n, angVelB);
+			angVelA = faddScaled1(angVelA, n, -(angNA * 0.1f));
+			angVelB = faddScaled1(angVelB, n, -(angNB * 0.1f));
 		}
 	}
 	reinterpret_cast<float4*>(cs)[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
@@ -933,7 +793,8 @@ B3_D void iteratePhase(const IterArgs& s, GridBarrier& bar, int numBatches, int 
 	}
 }
 
-__global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s)
+template <int THREADS, int MIN_BLOCKS>
+B3_D void solverIterateBody(const IterArgs& s)
 {
 	GridBarrier bar;
 	bar.init(s.bar, gridDim.x);
@@ -943,10 +804,14 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverIterateKernel(IterArgs s
 	const int firstOffset = (((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31);
 	// tail = the trailing run of batches with at most TAIL_ROWS rows each (solved by CTA 0 alone, see iteratePhase)
 	int tailStart = numBatches;
-	while (tailStart > 0 && (int)(s.batchOffset[tailStart] - s.batchOffset[tailStart - 1]) <= TAIL_ROWS) tailStart--;
+	while (tailStart > 0 && (int)(s.batchOffset[tailStart] - s.batchOffset[tailStart - 1]) <= (int)blockDim.x) tailStart--;
 	iteratePhase<0>(s, bar, numBatches, tailStart, stride, firstOffset);
 	iteratePhase<1>(s, bar, numBatches, tailStart, stride, firstOffset);
 }
+
+__global__ void __launch_bounds__(ITER_THREADS) solverIterateKernel(IterArgs s) { solverIterateBody<ITER_THREADS, 1>(s); }
+// (measured: 2 CTAs per SM of 384 / 512 threads, i.e. 80 / 64 registers with part of the prefetched row spilled, take 2.74 /
+// 3.17 ms against 2.39 ms for this 128-register, one-CTA-per-SM version on the bench scene)
 
 // ---------------------------------------------------------------- dataflow iterations
 // Same Gauss-Seidel order as solverIterateKernel, no grid-wide barriers.  Within a body, the
@@ -970,6 +835,7 @@ B3_D unsigned int ldRelaxed(const unsigned int* p)
 	return v;
 }
 B3_D void fenceAcqRel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+B3_D void stRelaxed(unsigned int* p, unsigned int v) { asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 B3_D void stRelease(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 B3_D void rankAndDegree(const unsigned long long* __restrict__ mask, int body, int colour, bool& dyn, unsigned int& rank, unsigned int& deg)
@@ -981,65 +847,89 @@ B3_D void rankAndDegree(const unsigned long long* __restrict__ mask, int body, i
 	rank = colour < 64 ? __popcll(m0 & (bit - 1ull)) : __popcll(m0) + __popcll(m1 & (bit - 1ull));
 }
 
-__global__ void __launch_bounds__(DF_THREADS) solverIterateDataflowKernel(IterArgs s)
+// One THREAD owns the slots i = tid, tid + T, ... of the batch-sorted array and walks them in ascending order every round.
+// A lane whose two bodies have reached its row's turn solves it at once, inside the polling loop; the other lanes of the
+// warp keep polling (independent thread scheduling), nobody waits at a reconvergence point.  The row, the positions and
+// the inertias are fetched when the thread moves on to the slot (only this thread ever writes the row), so when the
+// counters match only the velocities are still to be loaded.
+template <int PHASE>
+B3_D void dataflowRounds(const IterArgs& s, int tid, int T, int nSlots, int roundBegin, int roundEnd)
 {
-	const int lane = threadIdx.x & 31;
-	const int warpsTotal = (gridDim.x * blockDim.x) >> 5;
-	const int warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const int nRows = (int)(s.batchOffset[MAX_BATCHES] >> 5);  // batches are padded to multiples of 32
-	const int rounds = 2 * s.iterations;
-	for (int round = 0; round < rounds; round++)
+	int round = roundBegin, i = tid;
+	bool have = false, valid = false, dynA = false, dynB = false;
+	unsigned int expA = 0, expB = 0;
+	RowData pre;
+	while (round < roundEnd)
 	{
-		for (int row = warpId; row < nRows; row += warpsTotal)
+		if (!have)
 		{
-			const int i = row * 32 + lane;
-			const int4 tail = reinterpret_cast<const int4*>(&s.constraints[i])[10];
-			const int a = tail.x, b = tail.y;
-			const bool valid = a >= 0;
-			bool dynA = false, dynB = false;
-			unsigned int expA = 0, expB = 0;
+			loadRow<PHASE>(s, &s.constraints[i], pre);
+			valid = pre.aIdx >= 0;
 			if (valid)
 			{
+				const int colour = reinterpret_cast<const int4*>(&s.constraints[i])[10].z;
 				unsigned int rank, deg;
-				rankAndDegree(s.bodyMask, a, tail.z, dynA, rank, deg);
+				rankAndDegree(s.bodyMask, pre.aIdx, colour, dynA, rank, deg);
 				expA = (unsigned int)round * deg + rank;
-				rankAndDegree(s.bodyMask, b, tail.z, dynB, rank, deg);
+				rankAndDegree(s.bodyMask, pre.bIdx, colour, dynB, rank, deg);
 				expB = (unsigned int)round * deg + rank;
 			}
-			// All 32 constraints of a row belong to one batch, hence are mutually independent:
-			// the warp waits until every lane's two bodies have reached this constraint's turn.
-			for (;;)
-			{
-				bool ready = true;
-				if (dynA) ready = ldRelaxed(&s.seq[a]) == expA;
-				if (ready && dynB) ready = ldRelaxed(&s.seq[b]) == expB;
-				if (__all_sync(0xffffffffu, ready)) break;
-			}
-			fenceAcqRel();
+			have = true;
+		}
+		bool ready = true;
+		if (valid)
+		{
+			if (dynA) ready = ldRelaxed(&s.seq[pre.aIdx]) == expA;
+			if (ready && dynB) ready = ldRelaxed(&s.seq[pre.bIdx]) == expB;
+		}
+		if (ready)
+		{
 			if (valid)
 			{
-				if (round < s.iterations)
-					solveNormalRows(s, &s.constraints[i]);
+				// No acquire fence here: it would invalidate the whole L1 (CCTL.IVALL) once per row.  Everything another
+				// thread writes (velocities, counters) is read with strong gpu-scope loads served by L2, and those loads
+				// are only issued once the branch on the counter values has resolved.
+				if (PHASE == 0)
+					solveNormalPre(s, &s.constraints[i], pre);
 				else
-					solveFrictionRows(s, &s.constraints[i]);
-				if (dynA) stRelease(&s.seq[a], expA + 1u);
-				if (dynB) stRelease(&s.seq[b], expB + 1u);
+					solveFrictionPre(s, &s.constraints[i], pre);
+				if (dynA || dynB) __threadfence();  // the velocity stores are performed before either counter moves
+				if (dynA) stRelaxed(&s.seq[pre.aIdx], expA + 1u);
+				if (dynB) stRelaxed(&s.seq[pre.bIdx], expB + 1u);
+			}
+			have = false;
+			i += T;
+			if (i >= nSlots)
+			{
+				i = tid;
+				round++;
 			}
 		}
 	}
 }
 
-static int coopLaunch(World* w, const void* fn, void* argStruct)
+__global__ void __launch_bounds__(DF_THREADS) solverIterateDataflowKernel(IterArgs s)
+{
+	const int T = gridDim.x * blockDim.x;
+	// consecutive lanes own consecutive slots; warps are dealt round-robin to the CTAs like in the barrier kernel
+	const int tid = (((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31);
+	const int nSlots = (int)s.batchOffset[MAX_BATCHES];  // batches are padded to multiples of 32
+	if (tid >= nSlots) return;
+	dataflowRounds<0>(s, tid, T, nSlots, 0, s.iterations);
+	dataflowRounds<1>(s, tid, T, nSlots, s.iterations, 2 * s.iterations);
+}
+
+static int coopLaunch(World* w, const void* fn, void* argStruct, int threads = SOLVER_THREADS)
 {
 	int perSm = 0;
-	B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, SOLVER_THREADS, 0));
+	B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, threads, 0));
 	if (perSm < 1)
 	{
 		setLastError("solver kernel does not fit on an SM");
 		return B3B200_ERR_CUDA;
 	}
 	if (perSm > 2) perSm = 2;
-	dim3 grid(w->smCount * perSm), block(SOLVER_THREADS);
+	dim3 grid(w->smCount * perSm), block(threads);
 	void* args[] = {argStruct};
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
 	B3_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, w->stream));
@@ -1105,7 +995,7 @@ int launchSolverIterate(World* w)
 		g_launchCount++;
 		return 0;
 	}
-	return coopLaunch(w, (const void*)solverIterateKernel, &s);
+	return coopLaunch(w, (const void*)solverIterateKernel, &s, ITER_THREADS);
 }
 
 }  // namespace b3b200
