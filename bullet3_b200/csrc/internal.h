@@ -133,6 +133,7 @@ struct World
 	DevBuf<b3b200_face> dFaces;
 	DevBuf<int> dIndices;
 	DevBuf<b3b200_child_shape> dChildShapes;
+	DevBuf<float4> dChildSpheres;  // bounding sphere of every child hull in its compound's frame (built at upload)
 	DevBuf<b3b200_bvh_info> dBvhInfos;
 	DevBuf<b3b200_bvh_node> dBvhNodes;
 	DevBuf<b3b200_bvh_subtree> dBvhSubtrees;

@@ -195,6 +195,7 @@ struct NpArgs
 	const b3b200_face* faces;
 	const int* indices;
 	const b3b200_child_shape* childShapes;
+	const float4* childSpheres;  // per child shape: bounding-sphere centre in the compound's frame, radius in w (< 0: not a hull)
 	b3b200_contact4* contacts;
 	int maxContacts;
 	int maxWorkItems;
@@ -1090,7 +1091,12 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 					Side A, B;
 					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B))
 					{
-						keep = quickTest(a, A, B);
+						// bounding spheres first (conservative, like the child pairs below), then the exact quick reject
+						float rA, rB;
+						const float4 sA = boundSphere(a, A, rA), sB = boundSphere(a, B, rB);
+						const float4 d = sub3(sA, sB);
+						const float rr = (rA + rB) * 1.001f + 1e-3f;
+						keep = dot3(d, d) <= rr * rr && quickTest(a, A, B);
 						small = keep && isSmallHull(a, A.shape) && isSmallHull(a, B.shape);
 					}
 				}
@@ -1103,27 +1109,39 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 						const bool compA = typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS, compB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
 						const int firstA = compA ? __ldg(&a.collidables[cA].shapeIndex) : -1, nA = compA ? __ldg(&a.collidables[cA].numChildShapes) : 1;
 						const int firstB = compB ? __ldg(&a.collidables[cB].shapeIndex) : -1, nB = compB ? __ldg(&a.collidables[cB].numChildShapes) : 1;
-						// child pairs whose bounding spheres (about the hulls' AABB centres mC, radius |mE|) touch go to the
-						// raw child-item queue; npChildCullKernel runs the exact quick reject on them, one thread each
+						// child pairs whose bounding spheres touch go to the raw child-item queue; npChildCullKernel runs the exact
+						// quick reject on them, one thread each.  The spheres come from a per-child table in the compound's
+						// frame (world.cu), so a child costs one matrix-vector product here instead of a composed transform.
+						const float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
+						const Mat3 mA = matFromQuat(a.pose[2 * bodyA + 1]), mB = matFromQuat(a.pose[2 * bodyB + 1]);
+						float4 loneA = mk4(0, 0, 0, -1.f), loneB = mk4(0, 0, 0, -1.f);
+						if (!compA)
+						{
+							const b3b200_convex_polyhedron* h = &a.convex[__ldg(&a.collidables[cA].shapeIndex)];
+							loneA = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
+							loneA.w = __int_as_float(__ldg(&h->unused));
+						}
+						if (!compB)
+						{
+							const b3b200_convex_polyhedron* h = &a.convex[__ldg(&a.collidables[cB].shapeIndex)];
+							loneB = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
+							loneB.w = __int_as_float(__ldg(&h->unused));
+						}
 						for (int i = 0; i < nA; i++)
 						{
-							Side A;
-							const int ca = compA ? firstA + i : -1;
-							if (!resolveSide(a, bodyA, ca, A)) continue;
-							float rA;
-							const float4 sA = boundSphere(a, A, rA);
+							const float4 lA = compA ? __ldg(&a.childSpheres[firstA + i]) : loneA;
+							if (lA.w < 0.f) continue;
+							const float4 sA = add3(matMulVec(mA, lA), posA);
 							for (int j = 0; j < nB; j++)
 							{
-								Side B;
-								const int cb = compB ? firstB + j : -1;
-								if (!resolveSide(a, bodyB, cb, B)) continue;
-								float rB;
-								const float4 sB = boundSphere(a, B, rB);
+								const float4 lB = compB ? __ldg(&a.childSpheres[firstB + j]) : loneB;
+								if (lB.w < 0.f) continue;
+								const float4 sB = add3(matMulVec(mB, lB), posB);
 								const float4 d = sub3(sA, sB);
-								const float rr = (rA + rB) * 1.001f + 1e-3f;
+								const float rr = (lA.w + lB.w) * 1.001f + 2e-3f;
 								if (dot3(d, d) > rr * rr) continue;
 								const unsigned int slot = atomicAdd(&a.ctr[CTR_COMPOUND_PAIRS], 1u);
-								if (slot < (unsigned int)a.maxWorkItems) rawItems[slot] = make_int4(p, ca, cb, 0);
+								if (slot < (unsigned int)a.maxWorkItems) rawItems[slot] = make_int4(p, compA ? firstA + i : -1, compB ? firstB + j : -1, 0);
 							}
 						}
 					}
@@ -1635,6 +1653,7 @@ int launchNarrowphase(World* w)
 	a.faces = w->dFaces.ptr;
 	a.indices = w->dIndices.ptr;
 	a.childShapes = w->dChildShapes.ptr;
+	a.childSpheres = w->dChildSpheres.ptr;
 	a.contacts = w->dContacts.ptr;
 	a.maxContacts = w->cfg.maxContactCapacity;
 	a.maxWorkItems = (int)w->dSurvivors.cap;

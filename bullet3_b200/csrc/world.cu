@@ -584,6 +584,28 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(uploadVec(w->dFaces, w->faces, 0, s));
 	B3_TRY(uploadVec(w->dIndices, w->indices, 0, s));
 	B3_TRY(uploadVec(w->dChildShapes, w->childShapes, 0, s));
+	{
+		// conservative bounding sphere per child hull, in the compound's frame: centre = childPos + R(childOrn) * hull centre,
+		// radius = the hull's circumscribed radius (convex entry's unused word), padded; w < 0 marks a child that is not a hull
+		std::vector<float4> spheres(w->childShapes.size());
+		for (size_t k = 0; k < w->childShapes.size(); k++)
+		{
+			const b3b200_child_shape& ch = w->childShapes[k];
+			float4 sp = make_float4(0.f, 0.f, 0.f, -1.f);
+			const int ci = ch.shapeIndex;
+			if (ci >= 0 && ci < (int)w->collidables.size() && w->collidables[ci].shapeType == B3B200_SHAPE_CONVEX_HULL)
+			{
+				const b3b200_convex_polyhedron& cv = w->convex[w->collidables[ci].shapeIndex];
+				float r;
+				memcpy(&r, &cv.unused, sizeof(float));
+				const float4 lc = quatRotate(mk4(ch.childOrientation.x, ch.childOrientation.y, ch.childOrientation.z, ch.childOrientation.w),
+											 mk4(cv.localCenter.x, cv.localCenter.y, cv.localCenter.z));
+				sp = make_float4(lc.x + ch.childPosition.x, lc.y + ch.childPosition.y, lc.z + ch.childPosition.z, r * 1.0001f + 1e-5f);
+			}
+			spheres[k] = sp;
+		}
+		B3_TRY(uploadVec(w->dChildSpheres, spheres, 0, s));
+	}
 	B3_TRY(uploadVec(w->dBvhInfos, w->bvhInfos, 0, s));
 	B3_TRY(uploadVec(w->dBvhNodes, w->bvhNodes, 0, s));
 	B3_TRY(uploadVec(w->dBvhSubtrees, w->bvhSubtrees, 0, s));
