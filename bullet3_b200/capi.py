@@ -75,7 +75,7 @@ SYMBOLS = [
     "b3b200_bp_write_aabbs", "b3b200_bp_set_aabbs", "b3b200_bp_calculate_pairs", "b3b200_bp_num_overlap", "b3b200_bp_get_pairs",
     "b3b200_bp_device_pairs", "b3b200_bp_device_aabbs", "b3b200_bp_last_ms", "b3b200_radix_sort_kv", "b3b200_radix_sort_keys",
     "b3b200_prefix_scan_u32", "b3b200_bound_search_count", "b3b200_fill_u32",
-    "b3b200_register_concave_obj", "b3b200_checkpoint_save", "b3b200_checkpoint_load", "b3b200_copy_transforms",
+    "b3b200_solve_contacts_device", "b3b200_register_concave_obj", "b3b200_checkpoint_save", "b3b200_checkpoint_load", "b3b200_copy_transforms",
 ]
 
 _lib = None
@@ -429,6 +429,11 @@ class World:
 
     def tables(self):
         return {k: self.table(k) for k in self.TABLES}
+
+    def solve_contacts_device(self, num_bodies, bodies_ptr, inertias_ptr, num_contacts, contacts_ptr, static0_index):
+        """the stand-alone solver entry (b3GpuPgsContactSolver / b3GpuJacobiContactSolver::solveContacts) on caller-owned buffers"""
+        check(self.L.b3b200_solve_contacts_device(self.h, int(num_bodies), C.c_void_p(int(bodies_ptr)), C.c_void_p(int(inertias_ptr)), int(num_contacts),
+                                                  C.c_void_p(int(contacts_ptr)), int(static0_index)), "solve_contacts_device")
 
     def checkpoint_save(self, path):
         check(self.L.b3b200_checkpoint_save(self.h, str(path).encode()), "checkpoint_save")

@@ -8,7 +8,10 @@
 #include <stdio.h>
 #include "Bullet3OpenCL/RigidBody/b3GpuRigidBodyPipeline.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuPgsContactSolver.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuJacobiContactSolver.h"
 #include "Bullet3OpenCL/BroadphaseCollision/b3GpuSapBroadphase.h"
+#include <vector>
 #include "Bullet3OpenCL/BroadphaseCollision/b3GpuGridBroadphase.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3ConvexUtility.h"
 #include "Bullet3Common/b3Logging.h"
@@ -429,3 +432,71 @@ void b3GpuRigidBodyPipeline::reset() { m_np->reset(); }
 void b3GpuRigidBodyPipeline::setSolver(bool jacobi, int iterations) { b3b200_set_solver(m_np->m_world, jacobi ? B3B200_SOLVER_JACOBI : B3B200_SOLVER_PGS, iterations); }
 cl_mem b3GpuRigidBodyPipeline::getBodyBuffer() { return m_np->getBodiesGpu(); }
 int b3GpuRigidBodyPipeline::getNumBodies() const { return m_np->getNumRigidBodies(); }
+
+// ------------------------------------------------------------------ stand-alone contact solvers
+// The solver kernels work on a world's buffers, so each solver object keeps a private scratch world with enough body and
+// contact slots (placeholder bodies; grown on demand) and runs b3b200_solve_contacts_device on the caller's buffers.
+b3B200ContactSolverBase::b3B200ContactSolverBase(cl_device_id device, cl_command_queue q, int pairCapacity, int kind, int iterations)
+	: m_scratch(0), m_device(b3b200DeviceOrdinal(device)), m_pairCapacity(pairCapacity), m_bodyCapacity(0), m_contactCapacity(0), m_kind(kind), m_iterations(iterations), m_queue(q)
+{
+}
+b3B200ContactSolverBase::~b3B200ContactSolverBase()
+{
+	if (m_scratch) b3b200_destroy(m_scratch);
+}
+bool b3B200ContactSolverBase::ensureScratch(int numBodies, int numContacts)
+{
+	if (m_scratch && numBodies <= m_bodyCapacity && numContacts <= m_contactCapacity) return true;
+	if (m_scratch) b3b200_destroy(m_scratch);
+	m_scratch = 0;
+	b3b200_config cfg;
+	b3b200_config_default(&cfg);
+	m_bodyCapacity = numBodies + numBodies / 4 + 16;
+	m_contactCapacity = numContacts + numContacts / 4 + 16;
+	if (m_contactCapacity < m_pairCapacity) m_contactCapacity = m_pairCapacity;
+	cfg.maxConvexBodies = m_bodyCapacity;
+	cfg.maxContactCapacity = m_contactCapacity;
+	cfg.maxBroadphasePairs = 1024;  // the scratch world never finds pairs
+	cfg.compoundPairCapacity = 0;
+	cfg.maxTriConvexPairCapacity = 0;
+	if (b3b200_create(&cfg, m_device, m_queue, &m_scratch) < 0) return reportError("contact solver scratch world"), false;
+	const int shape = b3b200_register_sphere(m_scratch, 0.5f);
+	std::vector<float> mass((size_t)m_bodyCapacity, 1.f), pos((size_t)m_bodyCapacity * 4, 0.f), orn((size_t)m_bodyCapacity * 4, 0.f);
+	std::vector<int> col((size_t)m_bodyCapacity, shape);
+	for (int i = 0; i < m_bodyCapacity; i++)
+	{
+		pos[4 * (size_t)i] = 4.f * (float)i;
+		orn[4 * (size_t)i + 3] = 1.f;
+	}
+	if (shape < 0 || b3b200_register_instances(m_scratch, m_bodyCapacity, &mass[0], &pos[0], &orn[0], &col[0]) < 0 || b3b200_upload(m_scratch) < 0)
+	{
+		reportError("contact solver scratch world");
+		b3b200_destroy(m_scratch);
+		m_scratch = 0;
+		return false;
+	}
+	return true;
+}
+void b3B200ContactSolverBase::solve(int numBodies, cl_mem bodyBuf, cl_mem inertiaBuf, int numContacts, cl_mem contactBuf, int static0Index)
+{
+	if (numBodies <= 0 || numContacts <= 0) return;  // b3GpuPgsContactSolver.cpp:1105 / b3GpuJacobiContactSolver.cpp:701: nothing to do
+	if (!ensureScratch(numBodies, numContacts)) return;
+	b3b200_set_solver(m_scratch, m_kind, m_iterations);
+	checked(b3b200_solve_contacts_device(m_scratch, numBodies, bodyBuf, inertiaBuf, numContacts, contactBuf, static0Index), "solveContacts");
+}
+b3GpuPgsContactSolver::b3GpuPgsContactSolver(cl_context, cl_device_id device, cl_command_queue q, int pairCapacity)
+	: b3B200ContactSolverBase(device, q, pairCapacity, B3B200_SOLVER_PGS, 4)
+{
+}
+void b3GpuPgsContactSolver::solveContacts(int numBodies, cl_mem bodyBuf, cl_mem inertiaBuf, int numContacts, cl_mem contactBuf, const b3Config&, int static0Index)
+{
+	solve(numBodies, bodyBuf, inertiaBuf, numContacts, contactBuf, static0Index);
+}
+b3GpuJacobiContactSolver::b3GpuJacobiContactSolver(cl_context, cl_device_id device, cl_command_queue q, int pairCapacity)
+	: b3B200ContactSolverBase(device, q, pairCapacity, B3B200_SOLVER_JACOBI, b3JacobiSolverInfo().m_numIterations)
+{
+}
+void b3GpuJacobiContactSolver::solveContacts(int numBodies, cl_mem bodyBuf, cl_mem inertiaBuf, int numContacts, cl_mem contactBuf, const b3Config&, int static0Index)
+{
+	solve(numBodies, bodyBuf, inertiaBuf, numContacts, contactBuf, static0Index);
+}

@@ -841,6 +841,46 @@ extern "C" int b3b200_get_contacts(b3b200_world* w, b3b200_contact4* dst, int ca
 	}
 	return 0;
 }
+// b3GpuPgsContactSolver::solveContacts / b3GpuJacobiContactSolver::solveContacts (b3GpuPgsContactSolver.cpp:568-1103,
+// b3GpuJacobiContactSolver.cpp:699-869) on CALLER-OWNED buffers with the reference AoS layouts.  `w` is only the scratch
+// context (solver kind, iteration count, work buffers): the first numBodies body slots, the inertias and the contact
+// buffer are overwritten, the solve runs, and the bodies (velocities updated) are copied back.  The pointers may be
+// device or host pointers (cudaMemcpyDefault).
+extern "C" int b3b200_solve_contacts_device(b3b200_world* w, int numBodies, void* bodies, const void* inertias, int numContacts, const void* contacts,
+											int static0Index)
+{
+	W_UPLOADED(w);
+	if (numBodies < 0 || numBodies > w->numBodies || numContacts < 0 || numContacts > w->cfg.maxContactCapacity) return B3B200_ERR_INVALID;
+	if ((numBodies > 0 && (!bodies || !inertias)) || (numContacts > 0 && !contacts)) return B3B200_ERR_INVALID;
+	if (numBodies == 0) return 0;
+	cudaStream_t s = w->stream;
+	B3_TRY(syncAoS(w));
+	B3_CUDA_CHECK(cudaMemcpyAsync(w->dBodiesAoS.ptr, bodies, sizeof(b3b200_rigid_body) * (size_t)numBodies, cudaMemcpyDefault, s));
+	B3_CUDA_CHECK(cudaMemcpyAsync(w->dInertias.ptr, inertias, sizeof(b3b200_inertia) * (size_t)numBodies, cudaMemcpyDefault, s));
+	if (numContacts) B3_CUDA_CHECK(cudaMemcpyAsync(w->dContacts.ptr, contacts, sizeof(b3b200_contact4) * (size_t)numContacts, cudaMemcpyDefault, s));
+	const unsigned int n = (unsigned int)numContacts;
+	B3_CUDA_CHECK(cudaMemcpyAsync(&w->dCounters.ptr[CTR_CONTACTS], &n, sizeof(n), cudaMemcpyHostToDevice, s));
+	w->hostBodiesStale = true;
+	w->aabbsValid = false;
+	B3_TRY(launchPackSoA(w));
+	const int saved = w->static0Index;
+	w->static0Index = static0Index;
+	int rc = 0;
+	if (w->solverKind == B3B200_SOLVER_JACOBI)
+		rc = launchJacobi(w);
+	else
+	{
+		rc = launchSolverSetup(w);
+		if (rc == 0) rc = launchSolverIterate(w);
+	}
+	w->static0Index = saved;
+	if (rc) return rc;
+	B3_TRY(syncAoS(w));
+	B3_CUDA_CHECK(cudaMemcpyAsync(bodies, w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * (size_t)numBodies, cudaMemcpyDefault, s));
+	B3_CUDA_CHECK(cudaStreamSynchronize(s));
+	return 0;
+}
+
 extern "C" int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numContacts)
 {
 	W_UPLOADED(w);

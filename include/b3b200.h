@@ -236,6 +236,14 @@ int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, int numOwned
 int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int count, int firstGhostSlot, int numGhostSlots);
 int b3b200_halo_ghost_ids(b3b200_world* w, int* dst, int n);
 
+/* b3GpuPgsContactSolver::solveContacts / b3GpuJacobiContactSolver::solveContacts(numBodies, bodyBuf, inertiaBuf, numContacts,
+ * contactBuf, config, static0Index) (b3GpuPgsContactSolver.h:34, b3GpuJacobiContactSolver.h:47) on caller-owned buffers
+ * with the reference AoS layouts (device or host pointers).  `w` is the scratch context: an uploaded world with at least
+ * numBodies body slots, whose solver kind / iteration count apply and whose own body state is overwritten.  On return
+ * the velocities in `bodies` are the solved ones. */
+int b3b200_solve_contacts_device(b3b200_world* w, int numBodies, void* bodies, const void* inertias, int numContacts, const void* contacts,
+								 int static0Index);
+
 /* ---- the callers' data formats either side of the step ----
  * Wavefront .obj -> trimesh collidable the way ConcaveScene::createConcaveMesh feeds registerConcaveMesh
  * (examples/OpenCL/rigidbody/ConcaveScene.cpp:28-109, 111-158): one fresh vertex per face corner, polygons as fans,

@@ -7,6 +7,8 @@
 #include "Bullet3OpenCL/BroadphaseCollision/b3GpuGridBroadphase.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuRigidBodyPipeline.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuPgsContactSolver.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuJacobiContactSolver.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
 #include "Bullet3Collision/NarrowPhaseCollision/shared/b3RigidBodyData.h"
 
@@ -188,6 +190,39 @@ int main(int argc, char** argv)
 	printf("standalone pairs=%d\n", bp2->getNumOverlap());
 	ok = ok && bp2->getNumOverlap() == 4 && pairs.size() == 4;
 	delete bp2;
+
+	// the stand-alone solver classes on the pipeline's own device buffers, the way b3GpuRigidBodyPipeline::stepSimulation
+	// calls them (b3GpuRigidBodyPipeline.cpp:396-421): every box is pushed down at 1 m/s, the solver has to stop the pile
+	for (int pass = 0; pass < 2; pass++)
+	{
+		float down[3] = {0, -1, 0}, zero[3] = {0, 0, 0};
+		for (int i = 1; i < pipe->getNumBodies(); i++) np->setObjectVelocityCpu(down, zero, i);
+		np->writeAllBodiesToGpu();
+		if (pass == 0)
+		{
+			b3GpuPgsContactSolver pgs(ctx, dev, q, config.m_maxBroadphasePairs);
+			pgs.setNumIterations(20);
+			pgs.solveContacts(np->getNumRigidBodies(), np->getBodiesGpu(), np->getBodyInertiasGpu(), np->getNumContactsGpu(), np->getContactsGpu(), config, np->getStatic0Index());
+		}
+		else
+		{
+			b3GpuJacobiContactSolver jac(ctx, dev, q, config.m_maxBroadphasePairs);
+			jac.setNumIterations(40);
+			jac.solveContacts(np->getNumRigidBodies(), np->getBodiesGpu(), np->getBodyInertiasGpu(), np->getNumContactsGpu(), np->getContactsGpu(), config, np->getStatic0Index());
+		}
+		np->readbackAllBodiesToCpu();
+		const b3RigidBodyData* bb = np->getBodiesCpu();
+		double sumVy = 0;
+		bool finite = true;
+		for (int i = 1; i < pipe->getNumBodies(); i++)
+		{
+			sumVy += bb[i].m_linVel.y;
+			finite = finite && bb[i].m_linVel.y == bb[i].m_linVel.y;
+		}
+		const double meanVy = sumVy / (pipe->getNumBodies() - 1);
+		printf("standalone %s solver: mean vertical velocity %.3f after the solve (was -1)\n", pass == 0 ? "PGS" : "Jacobi", meanVy);
+		ok = ok && finite && meanVy > -0.5;
+	}
 
 	delete pipe;
 	delete bp;

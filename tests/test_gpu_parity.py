@@ -961,3 +961,39 @@ def test_copy_transforms_matches_body_buffer():
     w.synchronize()
     o = out.cpu().numpy()
     assert np.array_equal(o[10:20].view(np.uint32), b["quat"][:10].view(np.uint32)) and np.all(o[20:] == -7.0)
+
+
+def test_standalone_solver_entry_on_device_buffers_matches_world_solve():
+    """b3GpuPgsContactSolver / b3GpuJacobiContactSolver::solveContacts as a stand-alone entry: a scratch world solves another
+    world's device buffers in place and gives the velocities that world's own solve gives"""
+    for kind, iters in ((capi.SOLVER_PGS, 6), (capi.SOLVER_JACOBI, 7)):
+        w, sh, bodies, inertias = gpu_world(n_side=8, seed=11)
+        w.set_solver(kind, iters)
+        w.update_aabbs()
+        w.find_pairs()
+        w.compute_contacts()
+        start = w.bodies()
+        ncontacts = len(w.contacts())
+        assert ncontacts > 300
+        w.solve_contacts()
+        own = w.bodies()
+        assert not np.array_equal(own["linVel"], start["linVel"])
+        w.write_bodies(start)  # back to the pre-solve state; the contact buffer is untouched
+        scratch = capi.World(capi.default_config(2048))
+        sphere = scratch.register_sphere(0.5)
+        for i in range(len(start) + 5):
+            scratch.register_instance(1.0, (4.0 * i, 0, 0), scenes.IDENT, sphere)
+        scratch.upload()
+        scratch.set_solver(kind, iters)
+        scratch.solve_contacts_device(len(start), w.device_buffer(0), w.device_buffer(4), ncontacts, w.device_buffer(3), 0)
+        got = w.bodies()
+        for f in ("linVel", "angVel"):
+            if kind == capi.SOLVER_PGS:
+                assert np.array_equal(got[f].view(np.uint32), own[f].view(np.uint32)), f
+            else:  # the Jacobi kernels accumulate the split velocities with float atomics: equal up to summation order
+                assert rel_close(got[f], own[f], 1e-4), f
+        assert np.array_equal(got["pos"].view(np.uint32), start["pos"].view(np.uint32))
+        # host pointers work too (cudaMemcpyDefault)
+        hb, hi, hc = start.copy(), w.inertias(), w.contacts()
+        scratch.solve_contacts_device(len(hb), hb.ctypes.data, hi.ctypes.data, len(hc), hc.ctypes.data, 0)
+        assert rel_close(hb["linVel"], own["linVel"], 1e-4 if kind == capi.SOLVER_JACOBI else 0.0)
