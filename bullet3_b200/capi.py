@@ -71,7 +71,7 @@ SYMBOLS = [
     "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_set_ray_accel", "b3b200_solver_setup",
     "b3b200_solver_iterate", "b3b200_integrate", "b3b200_get_aabbs", "b3b200_get_pairs", "b3b200_get_contacts", "b3b200_set_contacts",
     "b3b200_get_constraints", "b3b200_get_batches", "b3b200_get_counters", "b3b200_get_work_counters", "b3b200_enable_stage_timing", "b3b200_stage_timings",
-    "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
+    "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_halo_set_ids", "b3b200_halo_emigrate", "b3b200_halo_adopt", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
     "b3b200_bp_write_aabbs", "b3b200_bp_set_aabbs", "b3b200_bp_calculate_pairs", "b3b200_bp_num_overlap", "b3b200_bp_get_pairs",
     "b3b200_bp_device_pairs", "b3b200_bp_device_aabbs", "b3b200_bp_last_ms", "b3b200_radix_sort_kv", "b3b200_radix_sort_keys",
     "b3b200_prefix_scan_u32", "b3b200_bound_search_count", "b3b200_fill_u32",

@@ -151,6 +151,8 @@ struct World
 	DevBuf<float4> dVel;   // 2 float4 per body
 	DevBuf<int> dCollidableIdx;
 	DevBuf<int> dGhostGlobalId;  // slab mode: global id mirrored by each ghost slot (-1 = parked / owned)
+	DevBuf<int> dHaloSlots;  // slot lists of emigrate / adopt
+	bool haloIdsSet = false;  // dGhostGlobalId holds the global id of every slot (b3b200_halo_set_ids)
 	bool soaDirty = false;  // SoA is newer than AoS
 	bool hostBodiesStale = false;  // the host mirror `bodies` is older than the device AoS (after b3b200_write_bodies)
 	bool hasConcave = false;  // any SHAPE_CONCAVE_TRIMESH collidable registered (enables the concave kernels)

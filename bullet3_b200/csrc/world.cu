@@ -385,6 +385,7 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->jointUid = 0;
 	w->jointsDirty = false;
 	w->jointBatchesDirty = false;
+	w->haloIdsSet = false;
 	w->numBodies = 0;
 	w->static0Index = -1;
 	w->uploaded = false;

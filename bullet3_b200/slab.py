@@ -9,7 +9,9 @@ Two modes, as BASELINE.json's north_star names them:
   (b3b200_halo_pack), exchanged with the left/right neighbour by NCCL send/recv over NVLink
   (torch.distributed.batch_isend_irecv on CUDA staging tensors) and scattered into the ghost slots
   (b3b200_halo_unpack).  Contacts between an owned body and a ghost are solved on both ranks; the owner's
-  state wins at the next exchange.
+  state wins at the next exchange.  With `spare_slots` > 0 ownership follows the bodies: a body whose centre has left
+  the slab by more than `hysteresis` is handed to the neighbour (b3b200_halo_emigrate / b3b200_halo_adopt, same
+  records and the same count-then-payload exchange) before the halo exchange of that step.
 
 The reference has no multi-device code; none of this has a reference counterpart.
 """
@@ -92,10 +94,12 @@ class SlabWorld:
         shapes:     callable(world) -> list of collidable indices (same order on every rank)
         static:     list of (position, orientation, shape_slot) replicated on every rank
         pos, quat:  (N,3|4) / (N,4) arrays of the dynamic bodies (identical on every rank)
+        lin_vel:    optional (N,3) initial linear velocities
         shape_slot: (N,) index into the list returned by `shapes`
     """
 
-    def __init__(self, scene, rank, world_size, device, stream, max_ghosts, margin=3.0, pairs_per_body=16):
+    def __init__(self, scene, rank, world_size, device, stream, max_ghosts, margin=3.0, pairs_per_body=16, spare_slots=0, hysteresis=0.25,
+                 max_migrants=4096):
         import torch
 
         self.torch = torch
@@ -115,7 +119,10 @@ class SlabWorld:
         self.has_left, self.has_right = rank > 0, rank < world_size - 1
         self.max_ghosts = int(max_ghosts)
         n_ghost_slots = self.max_ghosts * (int(self.has_left) + int(self.has_right))
-        n_bodies = self.n_static + self.n_owned_dyn + n_ghost_slots
+        self.spare_slots = int(spare_slots) if world_size > 1 else 0
+        self.hysteresis = float(hysteresis)
+        self.max_migrants = int(max_migrants)
+        n_bodies = self.n_static + self.n_owned_dyn + self.spare_slots + n_ghost_slots
         cfg = capi.default_config(n_bodies + 16, pairs_per_body)
         self.world = capi.World(cfg, device=device, stream=stream)
         cols = scene["shapes"](self.world)
@@ -124,23 +131,42 @@ class SlabWorld:
         quat = np.asarray(scene["quat"], np.float32)
         slot = np.asarray(scene["shape_slot"])
         self.world.register_instances(np.ones(len(mine), np.float32), pos[mine], quat[mine], np.asarray(cols, np.int32)[slot[mine]])
-        # ghost slots: dynamic bodies parked far away until the first exchange fills them
-        if n_ghost_slots:
-            park = np.zeros((n_ghost_slots, 3), np.float32)
-            park[:, 0] = 1.0e6 + 1024.0 * np.arange(n_ghost_slots)
+        # spare owned slots (for bodies that migrate in) and ghost slots: dynamic bodies parked far away until they are filled
+        n_parked = self.spare_slots + n_ghost_slots
+        first_parked = self.n_static + self.n_owned_dyn
+        if n_parked:
+            park = np.zeros((n_parked, 3), np.float32)
+            park[:, 0] = 1.0e6 + 1024.0 * (first_parked + np.arange(n_parked))
             park[:, 1] = -1.0e6
             park[:, 2] = 1.0e6
-            q0 = np.tile(np.array([0, 0, 0, 1], np.float32), (n_ghost_slots, 1))
-            self.world.register_instances(np.ones(n_ghost_slots, np.float32), park, q0, np.full(n_ghost_slots, cols[int(slot[0])], np.int32))
+            q0 = np.tile(np.array([0, 0, 0, 1], np.float32), (n_parked, 1))
+            self.world.register_instances(np.ones(n_parked, np.float32), park, q0, np.full(n_parked, cols[int(slot[0])], np.int32))
         self.world.upload()
-        self.num_owned = self.n_static + self.n_owned_dyn
+        self.num_owned = self.n_static + self.n_owned_dyn + self.spare_slots  # the owned REGION of the slot array
         self.first_ghost = self.num_owned
+        self.free_slots = list(range(first_parked, first_parked + self.spare_slots))[::-1]
+        if scene.get("lin_vel") is not None and self.n_owned_dyn:
+            b = self.world.bodies()
+            b["linVel"][self.n_static: first_parked, :3] = np.asarray(scene["lin_vel"], np.float32)[mine]
+            self.world.write_bodies(b)
+        if self.spare_slots:
+            # spare slots start out static (parked) so that no stage treats them as bodies; every slot gets its global id
+            b = self.world.bodies()
+            b["invMass"][first_parked: first_parked + self.spare_slots] = 0.0
+            self.world.write_bodies(b)
+            ids = np.full(n_bodies, -1, np.int32)
+            ids[self.n_static: first_parked] = self.global_first + np.arange(self.n_owned_dyn)
+            capi.check(capi.lib().b3b200_halo_set_ids(self.world.h, capi.ptr(ids), n_bodies), "halo_set_ids")
         dev = torch.device("cuda", device)
         self.send = {s: torch.zeros(self.max_ghosts * HALO_RECORD, dtype=torch.uint8, device=dev) for s in ("left", "right")}
         self.recv = {s: torch.zeros(self.max_ghosts * HALO_RECORD, dtype=torch.uint8, device=dev) for s in ("left", "right")}
         self.cnt_send = {s: torch.zeros(1, dtype=torch.int32, device=dev) for s in ("left", "right")}
         self.cnt_recv = {s: torch.zeros(1, dtype=torch.int32, device=dev) for s in ("left", "right")}
+        if self.spare_slots:
+            self.mig_send = {s: torch.zeros(self.max_migrants * HALO_RECORD, dtype=torch.uint8, device=dev) for s in ("left", "right")}
+            self.mig_recv = {s: torch.zeros(self.max_migrants * HALO_RECORD, dtype=torch.uint8, device=dev) for s in ("left", "right")}
         self.halo_bytes = 0
+        self.migrated_out = self.migrated_in = 0
         assert capi.lib().b3b200_halo_record_size() == HALO_RECORD
 
     def _pack(self, side):
@@ -171,16 +197,54 @@ class SlabWorld:
         self.halo_bytes = sum(counts.values()) * HALO_RECORD
         return counts, rc
 
+    def migrate(self):
+        """hand the bodies whose centre left this slab (by more than the hysteresis) to the neighbour on that side"""
+        if not self.spare_slots:
+            return {}, {}
+        torch = self.torch
+        sides = [s for s, has in (("left", self.has_left), ("right", self.has_right)) if has]
+        peer = {"left": self.rank - 1, "right": self.rank + 1}
+        lo, hi = float(self.boundaries[self.rank]), float(self.boundaries[self.rank + 1])
+        big = 3.0e38
+        counts = {}
+        for s in sides:
+            a, b = (-big, lo - self.hysteresis) if s == "left" else (hi + self.hysteresis, big)
+            n = C.c_int(0)
+            slots = np.zeros(self.max_migrants, np.int32)
+            capi.check(capi.lib().b3b200_halo_emigrate(self.world.h, 0, C.c_float(a), C.c_float(b), int(self.num_owned), int(self.rank),
+                                                       C.c_void_p(self.mig_send[s].data_ptr()), self.max_migrants, capi.ptr(slots), C.byref(n)), "halo_emigrate")
+            counts[s] = n.value
+            self.free_slots.extend(int(x) for x in slots[: n.value])
+        rc = exchange_buffers(sides, peer, counts, self.mig_send, self.mig_recv, self.cnt_send, self.cnt_recv, HALO_RECORD)
+        torch.cuda.current_stream().synchronize()
+        for s in sides:
+            if rc[s] > len(self.free_slots):
+                raise capi.B3Error("slab migration: %d bodies arrive, %d spare slots left" % (rc[s], len(self.free_slots)))
+            slots = np.array([self.free_slots.pop() for _ in range(rc[s])], np.int32)
+            if rc[s]:
+                capi.check(capi.lib().b3b200_halo_adopt(self.world.h, C.c_void_p(self.mig_recv[s].data_ptr()), rc[s], capi.ptr(slots)), "halo_adopt")
+        self.migrated_out += sum(counts.values())
+        self.migrated_in += sum(rc.values())
+        return counts, rc
+
     def step(self, dt=1.0 / 60.0):
         self.world.step(dt)
+        self.migrate()
         self.exchange()
 
     def global_ids(self):
         """global id of every local body (-1 for static and parked ghost slots)"""
-        ids = np.full(self.world.num_bodies, -1, np.int64)
-        ids[self.n_static: self.num_owned] = self.global_first + np.arange(self.n_owned_dyn)
         n = self.world.num_bodies
         g = np.zeros(n, np.int32)
         capi.check(capi.lib().b3b200_halo_ghost_ids(self.world.h, capi.ptr(g), n), "halo_ghost_ids")
+        if self.spare_slots:
+            return g.astype(np.int64)  # every slot carries its id (b3b200_halo_set_ids)
+        ids = np.full(n, -1, np.int64)
+        ids[self.n_static: self.num_owned] = self.global_first + np.arange(self.n_owned_dyn)
         ids[self.first_ghost:] = g[self.first_ghost:]
         return ids
+
+    def owned_ids(self):
+        """global ids of the dynamic bodies this rank owns right now"""
+        g = self.global_ids()[self.n_static: self.num_owned]
+        return g[g >= 0]

@@ -235,6 +235,14 @@ int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, int numOwned
 					 int capacity, int* countOut);
 int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int count, int firstGhostSlot, int numGhostSlots);
 int b3b200_halo_ghost_ids(b3b200_world* w, int* dst, int n);
+/* Migration.  set_ids gives every body slot its global id (n = number of bodies; -1 = none) -- pack then sends these.
+ * emigrate moves out the owned dynamic bodies whose CENTRE along `axis` lies in [lo, hi] (a range outside the slab): their
+ * records go to dstDevice, their slots are freed (parked, static, id -1) and listed in slotsOut (host, `capacity` ints).
+ * adopt writes `count` received records into the free slots the caller lists (host array). */
+int b3b200_halo_set_ids(b3b200_world* w, const int* ids, int n);
+int b3b200_halo_emigrate(b3b200_world* w, int axis, float lo, float hi, int numOwned, int rank, void* dstDevice, int capacity, int* slotsOut,
+						 int* countOut);
+int b3b200_halo_adopt(b3b200_world* w, const void* srcDevice, int count, const int* slots);
 
 /* b3GpuPgsContactSolver::solveContacts / b3GpuJacobiContactSolver::solveContacts(numBodies, bodyBuf, inertiaBuf, numContacts,
  * contactBuf, config, static0Index) (b3GpuPgsContactSolver.h:34, b3GpuJacobiContactSolver.h:47) on caller-owned buffers

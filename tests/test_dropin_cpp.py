@@ -16,7 +16,9 @@ def test_dropin_library_exports_reference_classes():
     out = subprocess.run(["nm", "-DC", LIB], capture_output=True, text=True).stdout
     for sym in ("b3GpuRigidBodyPipeline::stepSimulation(float)", "b3GpuRigidBodyPipeline::registerPhysicsInstance(",
                 "b3GpuNarrowPhase::registerConvexHullShape(float const*, int, int, float const*)", "b3GpuNarrowPhase::readbackAllBodiesToCpu()",
-                "b3B200BroadphaseBase::calculateOverlappingPairs(int)", "b3GpuRigidBodyPipeline::getBodyBuffer()"):
+                "b3B200BroadphaseBase::calculateOverlappingPairs(int)", "b3GpuRigidBodyPipeline::getBodyBuffer()",
+                "b3GpuRigidBodyPipeline::castRays(", "b3GpuRigidBodyPipeline::createPoint2PointConstraint(", "b3GpuPgsContactSolver::solveContacts(",
+                "b3GpuJacobiContactSolver::solveContacts("):
         assert sym in out, sym
 
 

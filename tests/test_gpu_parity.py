@@ -997,3 +997,85 @@ def test_standalone_solver_entry_on_device_buffers_matches_world_solve():
         hb, hi, hc = start.copy(), w.inertias(), w.contacts()
         scratch.solve_contacts_device(len(hb), hb.ctypes.data, hi.ctypes.data, len(hc), hc.ctypes.data, 0)
         assert rel_close(hb["linVel"], own["linVel"], 1e-4 if kind == capi.SOLVER_JACOBI else 0.0)
+
+
+def test_halo_emigrate_adopt_between_two_worlds():
+    """migration on one GPU: the bodies of world A whose centre lies beyond x = 0 are handed to free slots of world B;
+    B then holds their exact state under the same global ids, A's slots are parked and id-less, nothing else moves"""
+    import ctypes as C
+    import torch
+
+    rng = np.random.default_rng(1)
+    n, spare = 200, 160
+
+    def make(num_real):
+        w = capi.World(capi.default_config(1024))
+        scenes.add_ground_box(w, 50.0)
+        box = w.register_convex_points(scenes.box_points(0.5))
+        tet = w.register_convex_points(scenes.tetra_points(0.6))
+        for i in range(num_real):
+            p = (rng.uniform(-6, 6), rng.uniform(0.6, 3.0), rng.uniform(-3, 3))
+            w.register_instance(1.0 + 0.01 * i, p, scenes.random_quat(rng), box if i % 2 else tet)
+        for k in range(spare):
+            w.register_instance(1.0, (1.0e6 + 1024.0 * (1 + num_real + k), -1.0e6, 1.0e6), scenes.IDENT, box)
+        w.upload()
+        b = w.bodies()
+        b["invMass"][1 + num_real:] = 0.0
+        b["linVel"][1: 1 + num_real, :3] = rng.normal(size=(num_real, 3))
+        b["angVel"][1: 1 + num_real, :3] = rng.normal(size=(num_real, 3))
+        w.write_bodies(b)
+        return w
+
+    wa, wb = make(n), make(40)
+    L = capi.lib()
+    ids_a = np.full(wa.num_bodies, -1, np.int32)
+    ids_a[1: 1 + n] = 5000 + np.arange(n)
+    ids_b = np.full(wb.num_bodies, -1, np.int32)
+    ids_b[1: 41] = 9000 + np.arange(40)
+    capi.check(L.b3b200_halo_set_ids(wa.h, capi.ptr(ids_a), len(ids_a)), "set_ids")
+    capi.check(L.b3b200_halo_set_ids(wb.h, capi.ptr(ids_b), len(ids_b)), "set_ids")
+    before_a, before_b, inert_a = wa.bodies(), wb.bodies(), wa.inertias()
+    want = np.nonzero(before_a["pos"][1: 1 + n, 0] >= 0.0)[0] + 1
+    rec = L.b3b200_halo_record_size()
+    buf = torch.zeros(spare * rec, dtype=torch.uint8, device="cuda")
+    slots = np.zeros(spare, np.int32)
+    cnt = C.c_int(0)
+    capi.check(L.b3b200_halo_emigrate(wa.h, 0, C.c_float(0.0), C.c_float(3.0e38), wa.num_bodies, 0, C.c_void_p(buf.data_ptr()), spare, capi.ptr(slots), C.byref(cnt)), "emigrate")
+    assert cnt.value == len(want) and 40 < cnt.value < spare
+    assert sorted(slots[: cnt.value].tolist()) == want.tolist()
+    after_a = wa.bodies()
+    gone = np.zeros(wa.num_bodies, bool)
+    gone[want] = True
+    assert np.all(after_a["invMass"][gone] == 0) and np.all(after_a["pos"][gone, 0] >= 1.0e6)
+    assert np.array_equal(after_a[~gone].view(np.uint8), before_a[~gone].view(np.uint8))
+    ga = np.zeros(wa.num_bodies, np.int32)
+    capi.check(L.b3b200_halo_ghost_ids(wa.h, capi.ptr(ga), len(ga)), "ids")
+    assert np.all(ga[gone] == -1) and np.array_equal(ga[~gone], ids_a[~gone])
+    # a second call finds nothing left to move
+    capi.check(L.b3b200_halo_emigrate(wa.h, 0, C.c_float(0.0), C.c_float(3.0e38), wa.num_bodies, 0, C.c_void_p(buf.data_ptr() + 0), spare, capi.ptr(np.zeros(spare, np.int32)), C.byref(C.c_int(0))), "emigrate")
+    # adopt into B's free slots (any order the caller likes)
+    free = np.arange(41, 41 + cnt.value, dtype=np.int32)[::-1].copy()
+    capi.check(L.b3b200_halo_adopt(wb.h, C.c_void_p(buf.data_ptr()), cnt.value, capi.ptr(free)), "adopt")
+    after_b, inert_b = wb.bodies(), wb.inertias()
+    gb = np.zeros(wb.num_bodies, np.int32)
+    capi.check(L.b3b200_halo_ghost_ids(wb.h, capi.ptr(gb), len(gb)), "ids")
+    for k in range(cnt.value):
+        src, dst = int(slots[k]), int(free[k])
+        assert gb[dst] == ids_a[src]
+        for f in ("pos", "quat", "linVel", "angVel"):
+            assert np.array_equal(np.asarray(before_a[src][f])[:3].view(np.uint32), np.asarray(after_b[dst][f])[:3].view(np.uint32)), f
+        assert before_a[src]["invMass"] == after_b[dst]["invMass"] and before_a[src]["collidableIdx"] == after_b[dst]["collidableIdx"]
+        assert np.array_equal(inert_a[src: src + 1].view(np.uint8), inert_b[dst: dst + 1].view(np.uint8))
+    untouched = np.ones(wb.num_bodies, bool)
+    untouched[free] = False
+    assert np.array_equal(after_b[untouched].view(np.uint8), before_b[untouched].view(np.uint8))
+    # the adopted bodies take part in B's step like any other body
+    wb.step(1 / 60)
+    assert np.isfinite(wb.bodies()["pos"]).all() and wb.counters()[0] > 0
+    # capacity overflow is reported, the bodies that did not fit stay
+    wc = make(n)
+    capi.check(L.b3b200_halo_set_ids(wc.h, capi.ptr(ids_a), len(ids_a)), "set_ids")
+    small = 8
+    rc = L.b3b200_halo_emigrate(wc.h, 0, C.c_float(-3.0e38), C.c_float(3.0e38), wc.num_bodies, 0, C.c_void_p(buf.data_ptr()), small, capi.ptr(slots), C.byref(cnt))
+    assert rc < 0 and cnt.value == small
+    assert int((wc.bodies()["invMass"][1: 1 + n] != 0).sum()) == n - small

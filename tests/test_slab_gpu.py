@@ -18,3 +18,14 @@ def test_slab_two_gpus_matches_single():
            os.path.join(ROOT, "tools", "slab_check.py")]
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=540)
     assert out.returncode == 0 and "SLAB OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_slab_migration_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29518",
+           os.path.join(ROOT, "tools", "slab_migrate_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=540)
+    assert out.returncode == 0 and "MIGRATE OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
