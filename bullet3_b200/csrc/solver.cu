@@ -79,11 +79,14 @@ struct GridBarrier
 	{
 		if (threadIdx.x == 0)
 		{
+			// poll with relaxed loads and acquire ONCE at the end: an acquire load compiles to LD + CCTL.IVALL, i.e. every
+			// poll would throw away the SM's whole L1
 			unsigned int v = seen;
 			while ((int)(v - target) < 0)
 			{
-				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
 			}
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		}
 		__syncthreads();
 	}
@@ -98,8 +101,9 @@ struct GridBarrier
 			unsigned int v = old + 1;
 			while ((int)(v - target) < 0)
 			{
-				asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
 			}
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		}
 		__syncthreads();
 	}
