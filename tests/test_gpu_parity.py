@@ -990,7 +990,7 @@ def test_standalone_solver_entry_on_device_buffers_matches_world_solve():
         for f in ("linVel", "angVel"):
             if kind == capi.SOLVER_PGS:
                 assert np.array_equal(got[f].view(np.uint32), own[f].view(np.uint32)), f
-            else:  # the Jacobi kernels accumulate the split velocities with float atomics: equal up to summation order
+            else:  # a body's split slots are handed out with an atomic counter (like CountBodiesKernel): equal up to summation order
                 assert rel_close(got[f], own[f], 1e-4), f
         assert np.array_equal(got["pos"].view(np.uint32), start["pos"].view(np.uint32))
         # host pointers work too (cudaMemcpyDefault)
