@@ -94,6 +94,7 @@ struct World
 	float angularDamping = 0.99f;          // b3GpuRigidBodyPipeline.cpp:469
 	int solverKind = B3B200_SOLVER_PGS;
 	int solverIterations = 4;  // b3GpuPgsContactSolver.cpp:1049
+	int solverColouring = 1;  // batch assignment: 0 = Jones-Plassmann rounds (reproducible), 1 = single-pass first fit with atomics (solver.cu)
 	bool solverDataflow = false;  // true = barrier-free per-body dataflow kernel (solver.cu, experimental); false = grid-barrier kernel
 	float clipMinDist = -1e30f, clipMaxDist = 0.02f;  // satClipHullContacts.cl:916-917
 	int static0Index = -1;     // b3GpuNarrowPhase.cpp:861-864

@@ -143,6 +143,7 @@ struct SetupArgs
 	unsigned int* bar;
 	int numBodies;
 	int staticIdx;
+	int colouring;  // 0 = Jones-Plassmann rounds (reproducible for a given contact array), 1 = single-pass first fit with atomics
 	float dt, positionDrift, positionConstraintCoeff;
 };
 
@@ -343,6 +344,62 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 	return false;
 }
 
+// Single-pass colouring: every contact takes the lowest colour that is free on both of its dynamic bodies by setting the
+// colour's bit in the bodies' masks with atomicOr -- whoever flips a bit from 0 to 1 owns that (body, colour) -- and
+// retries with fresh masks when it loses a race.  The bodies are taken in index order, so two contacts can never hold
+// one bit each and wait for the other's (no livelock); a contact that loses on its second body gives the first bit back.
+// No rounds and no grid barrier: a body's contacts resolve their races in a few L2 round trips.  The colours depend on
+// the order in which the races resolve, i.e. they are not reproducible from run to run (the Jones-Plassmann path is).
+B3_D void colourFirstFit(const SetupArgs& s, int c)
+{
+	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
+	const int a = abs(ids.z), b = abs(ids.w);
+	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
+	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
+	int body[2];
+	int nb = 0;
+	if (!aStatic) body[nb++] = a;
+	if (!bStatic) body[nb++] = b;
+	if (nb == 2 && body[0] > body[1])
+	{
+		const int t = body[0];
+		body[0] = body[1];
+		body[1] = t;
+	}
+	int colour = 0;
+	for (;;)
+	{
+		unsigned long long m0 = 0ull, m1 = 0ull;
+		for (int k = 0; k < nb; k++)
+		{
+			m0 |= __ldcg(&s.bodyMask[2 * body[k]]);
+			m1 |= __ldcg(&s.bodyMask[2 * body[k] + 1]);
+		}
+		colour = -2;
+		if (~m0)
+			colour = __ffsll((long long)~m0) - 1;
+		else if (~m1)
+			colour = 64 + __ffsll((long long)~m1) - 1;
+		if (colour < 0)
+		{
+			// more than B3_MAX_NUM_BATCHES colours at one body (see colourTry)
+			s.contactColour[c] = -2;
+			atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+			return;
+		}
+		const unsigned long long bit = 1ull << (colour & 63);
+		const int word = colour >> 6;
+		int got = 0;
+		for (; got < nb; got++)
+			if (atomicOr(&s.bodyMask[2 * body[got] + word], bit) & bit) break;
+		if (got == nb) break;
+		for (int k = 0; k < got; k++) atomicAnd(&s.bodyMask[2 * body[k] + word], ~bit);
+	}
+	s.contactColour[c] = colour;
+	s.contacts[c].batchIdx = colour;
+	atomicAdd(&s.batchCount[colour], 1u);
+}
+
 #ifdef B3_SETUP_TIMING
 #define B3_PROBE(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); printf("setup %s %llu round %d\n", tag, t, round); } } while (0)
 #else
@@ -384,7 +441,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	const unsigned int* cur = nullptr;
 	const int lane = threadIdx.x & 31;
 	__shared__ unsigned int sNext;
-	for (; round < MAX_ROUNDS; round++)
+	if (s.colouring == 1)
+	{
+		for (int c = tid; c < nContacts; c += stride) colourFirstFit(s, c);
+		bar.sync();
+		count = 0;
+	}
+	for (; count > 0 && round < MAX_ROUNDS; round++)
 	{
 		for (int i = tid; i < count; i += stride) colourClaim(s, cur ? (int)__ldcg(&cur[i]) : i);
 		bar.sync();
@@ -962,6 +1025,7 @@ int launchSolverSetup(World* w)
 	s.bar = w->dGridBarrier.ptr;
 	s.numBodies = w->numBodies;
 	s.staticIdx = w->static0Index;
+	s.colouring = w->solverColouring;
 	s.dt = 1.f / 60.f;  // the reference solver ignores deltaTime (b3GpuPgsContactSolver.cpp:672)
 	s.positionDrift = 0.005f;
 	s.positionConstraintCoeff = 0.2f;

@@ -683,6 +683,12 @@ extern "C" int b3b200_set_solver_dataflow(b3b200_world* w, int enable)
 	w->solverDataflow = enable != 0;
 	return 0;
 }
+extern "C" int b3b200_set_colouring(b3b200_world* w, int mode)
+{
+	if (!w || mode < 0 || mode > 1) return B3B200_ERR_INVALID;
+	w->solverColouring = mode;
+	return 0;
+}
 extern "C" int b3b200_set_contact_clip(b3b200_world* w, float minDist, float maxDist)
 {
 	if (!w) return B3B200_ERR_INVALID;

@@ -131,6 +131,12 @@ int b3b200_set_broadphase(b3b200_world* w, int kind);
 /* PGS iteration kernel: 0 = one grid barrier per batch (default), 1 = barrier-free per-body dataflow ordering (experimental).
  * Both execute the same Gauss-Seidel order and give bit-identical velocities. */
 int b3b200_set_solver_dataflow(b3b200_world* w, int enable);
+/* how the PGS solver assigns contacts to batches (the reference: b3Solver::batchContacts / sortConstraintByBatch3; any
+ * assignment in which no two contacts of a batch share a dynamic body gives a valid Gauss-Seidel order):
+ * 1 (default) = one pass, every contact takes the lowest colour free on both bodies with atomics (fast, the colours
+ * depend on how the races resolve); 0 = Jones-Plassmann rounds by hashed priorities (reproducible for a given contact
+ * array, about 35 grid-wide rounds). */
+int b3b200_set_colouring(b3b200_world* w, int mode);
 /* clip window of the convex-convex clipper: the reference kernels use
  * (-1e30, 0.02) (satClipHullContacts.cl:916-917), the shared CPU header (-1, 0)
  * (b3ContactConvexConvexSAT.h:320-321).  Default = the kernel constants. */

@@ -130,10 +130,14 @@ def solve(constraints, batch_offsets, bodies, inertias, iterations):
     return bodies, cs
 
 
-def oracle_pgs_step_velocities(contacts, bodies, inertias, static_idx, iterations):
-    """colour -> sort by batch -> build rows -> solve, all on the CPU oracle"""
+def oracle_pgs_step_velocities(contacts, bodies, inertias, static_idx, iterations, colours=None):
+    """colour -> sort by batch -> build rows -> solve, all on the CPU oracle (colours: take this batch assignment instead)"""
     contacts = _arr(contacts, capi.contact4_t).copy()
-    nb, colours = colour_contacts(contacts, len(bodies), static_idx)
+    if colours is None:
+        nb, colours = colour_contacts(contacts, len(bodies), static_idx)
+    else:
+        colours = np.asarray(colours, np.int32)
+        nb = int(colours.max()) + 1 if len(colours) else 0
     contacts["batchIdx"] = colours
     order = np.argsort(colours, kind="stable")
     sorted_contacts = contacts[order]

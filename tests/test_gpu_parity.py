@@ -296,22 +296,31 @@ def test_contact_capacity_clamp():
 
 
 # ------------------------------------------------------------------ solver
+@pytest.mark.parametrize("colouring", [0, 1])
 @pytest.mark.parametrize("dataflow", [True, False])
 @pytest.mark.parametrize("seed,iters", [(0, 4), (1, 10)])
-def test_pgs_solver_matches_oracle(seed, iters, dataflow):
+def test_pgs_solver_matches_oracle(seed, iters, dataflow, colouring):
     w, sh, bodies, inertias = gpu_world(n_side=7, seed=seed)
     w.set_solver(capi.SOLVER_PGS, iters)
     w.set_solver_dataflow(dataflow)
+    w.set_colouring(colouring)
     w.update_aabbs()
     w.find_pairs()
     w.compute_contacts()
     contacts = w.contacts()
     assert len(contacts) > 200
     w.solver_setup()
-    # --- same batching: the device colouring equals the oracle's first-fit colouring
-    nb, colours = oa.colour_contacts(contacts, len(bodies), 0)
     g_contacts = w.contacts()
-    assert np.array_equal(g_contacts["batchIdx"], colours)
+    if colouring == 0:
+        # --- same batching: the device's Jones-Plassmann colouring equals the oracle's sequential restatement of it
+        nb, colours = oa.colour_contacts(contacts, len(bodies), 0)
+        assert np.array_equal(g_contacts["batchIdx"], colours)
+    else:
+        # --- the single-pass colouring depends on how its races resolve: take the device's batches as they are (their
+        # validity is checked below) and give the same ones to the oracle; at most a few colours more than the sequential one
+        colours = g_contacts["batchIdx"].astype(np.int32)
+        nb = int(colours.max()) + 1
+        assert colours.min() >= 0 and nb <= oa.colour_contacts(contacts, len(bodies), 0)[0] + 4
     off = w.batches()
     cs_all = w.constraints()
     assert len(off) - 1 == nb and off[-1] == len(cs_all) and (np.diff(off) % 32 == 0).all()
@@ -339,7 +348,7 @@ def test_pgs_solver_matches_oracle(seed, iters, dataflow):
     # --- velocities after the iterations
     w.solver_iterate()
     g_bodies = w.bodies()
-    o_bodies, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, iters)
+    o_bodies, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, iters, colours=colours)
     assert rel_close(g_bodies["linVel"][:, :3], o_bodies["linVel"][:, :3], 1e-4)
     assert rel_close(g_bodies["angVel"][:, :3], o_bodies["angVel"][:, :3], 1e-4)
     moved = np.abs(g_bodies["linVel"][:, :3] - bodies["linVel"][:, :3]).max()
@@ -390,6 +399,7 @@ def test_dataflow_and_barrier_kernels_bit_identical():
         w, sh, bodies, inertias = gpu_world(n_side=10, seed=7)
         w.set_solver(capi.SOLVER_PGS, 10)
         w.set_solver_dataflow(mode)
+        w.set_colouring(0)  # two worlds: the reproducible batch assignment
         w.update_aabbs()
         w.find_pairs()
         w.compute_contacts()
@@ -403,6 +413,7 @@ def test_full_step_matches_oracle_pipeline():
     """one whole b3b200_step == oracle stages chained on the CPU"""
     w, sh, bodies, inertias = gpu_world(n_side=6, seed=5)
     w.set_solver(capi.SOLVER_PGS, 4)
+    w.set_colouring(0)  # "same batching": the batch assignment the oracle restates
     w.step(1 / 60)
     g = w.bodies()
     aabbs = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
@@ -969,6 +980,7 @@ def test_standalone_solver_entry_on_device_buffers_matches_world_solve():
     for kind, iters in ((capi.SOLVER_PGS, 6), (capi.SOLVER_JACOBI, 7)):
         w, sh, bodies, inertias = gpu_world(n_side=8, seed=11)
         w.set_solver(kind, iters)
+        w.set_colouring(0)  # two worlds solve the same contacts: the reproducible batch assignment
         w.update_aabbs()
         w.find_pairs()
         w.compute_contacts()
@@ -985,6 +997,7 @@ def test_standalone_solver_entry_on_device_buffers_matches_world_solve():
             scratch.register_instance(1.0, (4.0 * i, 0, 0), scenes.IDENT, sphere)
         scratch.upload()
         scratch.set_solver(kind, iters)
+        scratch.set_colouring(0)
         scratch.solve_contacts_device(len(start), w.device_buffer(0), w.device_buffer(4), ncontacts, w.device_buffer(3), 0)
         got = w.bodies()
         for f in ("linVel", "angVel"):
