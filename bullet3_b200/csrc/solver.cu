@@ -350,7 +350,7 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 // one bit each and wait for the other's (no livelock); a contact that loses on its second body gives the first bit back.
 // No rounds and no grid barrier: a body's contacts resolve their races in a few L2 round trips.  The colours depend on
 // the order in which the races resolve, i.e. they are not reproducible from run to run (the Jones-Plassmann path is).
-B3_D void colourFirstFit(const SetupArgs& s, int c)
+B3_D int colourFirstFit(const SetupArgs& s, int c)
 {
 	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
 	const int a = abs(ids.z), b = abs(ids.w);
@@ -385,7 +385,7 @@ B3_D void colourFirstFit(const SetupArgs& s, int c)
 			// more than B3_MAX_NUM_BATCHES colours at one body (see colourTry)
 			s.contactColour[c] = -2;
 			atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-			return;
+			return -2;
 		}
 		const unsigned long long bit = 1ull << (colour & 63);
 		const int word = colour >> 6;
@@ -397,7 +397,19 @@ B3_D void colourFirstFit(const SetupArgs& s, int c)
 	}
 	s.contactColour[c] = colour;
 	s.contacts[c].batchIdx = colour;
-	atomicAdd(&s.batchCount[colour], 1u);
+	return colour;  // the caller counts it (warp-aggregated)
+}
+
+// counters[key] += 1 for every lane with key >= 0, one atomic per distinct key in the warp (a few hundred thousand contacts
+// share ~20 colours: one atomic each would serialise on ~20 addresses).  Returns the lane's own slot.  Whole warp calls.
+B3_D unsigned int warpCountByKey(unsigned int* counters, int key, int lane)
+{
+	const unsigned int peers = __match_any_sync(0xffffffffu, key);
+	unsigned int base = 0;
+	const int leader = __ffs(peers) - 1;
+	if (key >= 0 && lane == leader) base = atomicAdd(&counters[key], (unsigned int)__popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
 }
 
 #ifdef B3_SETUP_TIMING
@@ -443,7 +455,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 	__shared__ unsigned int sNext;
 	if (s.colouring == 1)
 	{
-		for (int c = tid; c < nContacts; c += stride) colourFirstFit(s, c);
+		for (int base = tid - lane; base < nContacts; base += stride)
+		{
+			const int c = base + lane;
+			const int colour = c < nContacts ? colourFirstFit(s, c) : -1;
+			__syncwarp();
+			warpCountByKey(s.batchCount, colour, lane);
+		}
 		bar.sync();
 		count = 0;
 	}
@@ -560,12 +578,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 			reinterpret_cast<int4*>(dw)[10] = tail;
 		}
 	}
-	for (int c = tid; c < nContacts; c += stride)
+	for (int base = tid - lane; base < nContacts; base += stride)
 	{
-		int colour = __ldcg(&s.contactColour[c]);
+		const int c = base + lane;
+		const int colour = c < nContacts ? __ldcg(&s.contactColour[c]) : -1;
+		const unsigned int rank = warpCountByKey(s.batchCursor, colour, lane);
 		if (colour < 0) continue;
-		unsigned int slot = __ldcg(&s.batchOffset[colour]) + atomicAdd(&s.batchCursor[colour], 1u);
-		buildConstraint(s, &s.contacts[c], colour, &s.constraints[slot]);
+		buildConstraint(s, &s.contacts[c], colour, &s.constraints[__ldcg(&s.batchOffset[colour]) + rank]);
 	}
 	B3_PROBE("built(block0 thread0 only)");
 }
