@@ -119,16 +119,31 @@ __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restric
 		qy += __shfl_xor_sync(0xffffffffu, qy, o);
 		qz += __shfl_xor_sync(0xffffffffu, qz, o);
 	}
-	if ((threadIdx.x & 31) == 0)
+	// one set of atomics per CTA (8 warps -> shared memory -> warp 0): the 7 scalars are global hot spots
+	__shared__ float part[8][7];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0)
 	{
-		atomicMax(&scal[SC_MAXEXT_BITS], __float_as_uint(ext));
+		part[warp][0] = ext;
+		part[warp][1] = sx;
+		part[warp][2] = sy;
+		part[warp][3] = sz;
+		part[warp][4] = qx;
+		part[warp][5] = qy;
+		part[warp][6] = qz;
+	}
+	__syncthreads();
+	if (threadIdx.x < 7)
+	{
+		float v = part[0][threadIdx.x];
+		for (int k = 1; k < 8; k++) v = threadIdx.x == 0 ? fmaxf(v, part[k][0]) : v + part[k][threadIdx.x];
 		float* f = reinterpret_cast<float*>(scal);
-		atomicAdd(&f[SC_SUM + 0], sx);
-		atomicAdd(&f[SC_SUM + 1], sy);
-		atomicAdd(&f[SC_SUM + 2], sz);
-		atomicAdd(&f[SC_SUM2 + 0], qx);
-		atomicAdd(&f[SC_SUM2 + 1], qy);
-		atomicAdd(&f[SC_SUM2 + 2], qz);
+		if (threadIdx.x == 0)
+			atomicMax(&scal[SC_MAXEXT_BITS], __float_as_uint(v));
+		else if (threadIdx.x <= 3)
+			atomicAdd(&f[SC_SUM + (threadIdx.x - 1)], v);
+		else
+			atomicAdd(&f[SC_SUM2 + (threadIdx.x - 4)], v);
 	}
 }
 
