@@ -70,9 +70,10 @@ struct GridBarrier
 		__syncthreads();
 		if (threadIdx.x == 0)
 		{
-			unsigned int old;
-			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
-			seen = old + 1;
+			// fire and forget: nobody needs the old value, and waiting for it would put one more L2 round trip in front of
+			// the first poll
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+			seen = target - 1u;
 		}
 	}
 	B3_D void wait()
@@ -96,9 +97,8 @@ struct GridBarrier
 		__syncthreads();
 		if (threadIdx.x == 0)
 		{
-			unsigned int old;
-			asm volatile("atom.add.release.gpu.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
-			unsigned int v = old + 1;
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+			unsigned int v = target - 1u;
 			while ((int)(v - target) < 0)
 			{
 				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
