@@ -321,6 +321,7 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 		// ("batchIdx>=B3_MAX_NUM_BATCHES", b3GpuPgsContactSolver.cpp:1497-1502); here the
 		// contact is left out of this step's solve and the overflow flag is raised.
 		s.contactColour[c] = -2;
+		s.contacts[c].batchIdx = -2;
 		if (!aStatic) s.bodyPrio[a] = 0ull;
 		if (!bStatic) s.bodyPrio[b] = 0ull;
 		atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
@@ -384,6 +385,8 @@ B3_D int colourFirstFit(const SetupArgs& s, int c)
 		{
 			// more than B3_MAX_NUM_BATCHES colours at one body (see colourTry)
 			s.contactColour[c] = -2;
+			s.contacts[c].batchIdx = -2;
+		s.contacts[c].batchIdx = -2;
 			atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
 			return -2;
 		}

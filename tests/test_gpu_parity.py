@@ -1092,3 +1092,49 @@ def test_halo_emigrate_adopt_between_two_worlds():
     rc = L.b3b200_halo_emigrate(wc.h, 0, C.c_float(-3.0e38), C.c_float(3.0e38), wc.num_bodies, 0, C.c_void_p(buf.data_ptr()), small, capi.ptr(slots), C.byref(cnt))
     assert rc < 0 and cnt.value == small
     assert int((wc.bodies()["invMass"][1: 1 + n] != 0).sum()) == n - small
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("colouring", [0, 1])
+@pytest.mark.parametrize("side,overflow", [(10, False), (12, True)])
+def test_high_degree_body_colouring(side, overflow, colouring):
+    """one dynamic plate carrying side^2 boxes: its contacts all need different batches.  Up to B3_MAX_NUM_BATCHES = 128
+    colours that works; beyond, the extra contacts are left out of the solve and the overflow flag is raised (the reference
+    errors out, b3GpuPgsContactSolver.cpp:1497-1502) -- in both batch-assignment modes, without hanging"""
+    w = capi.World(capi.default_config(1024))
+    scenes.add_ground_box(w, 50.0)
+    plate = w.register_convex_points(scenes.box_points(side * 0.6, 0.25, side * 0.6))
+    box = w.register_convex_points(scenes.box_points(0.5))
+    w.register_instance(50.0, (0, 0.25, 0), scenes.IDENT, plate)
+    for i in range(side):
+        for k in range(side):
+            w.register_instance(1.0, ((i - (side - 1) / 2) * 1.1, 0.5 + 0.5 - 0.005, (k - (side - 1) / 2) * 1.1), scenes.IDENT, box)
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, 4)
+    w.set_colouring(colouring)
+    w.update_aabbs()
+    w.find_pairs()
+    w.compute_contacts()
+    contacts = w.contacts()
+    on_plate = int(((np.abs(contacts["bodyA"]) == 1) | (np.abs(contacts["bodyB"]) == 1)).sum())
+    assert on_plate == side * side + 1  # every box + the ground
+    w.solver_setup()
+    flags = int(w.counters()[4])
+    cols = w.contacts()["batchIdx"]
+    if overflow:
+        assert flags & 4 and (cols < 0).sum() == on_plate - 128 and cols.max() == 127
+    else:
+        assert not (flags & 4) and cols.min() >= 0 and cols.max() + 1 >= on_plate
+    # valid batches: no dynamic body twice in a batch
+    b = w.bodies()
+    for c in np.unique(cols[cols >= 0]):
+        seg = contacts[cols == c]
+        ids = np.concatenate([np.abs(seg["bodyA"]), np.abs(seg["bodyB"])])
+        ids = ids[b["invMass"][ids] != 0]
+        assert len(ids) == len(np.unique(ids))
+    w.solver_iterate()
+    w.integrate(1 / 60)
+    assert np.isfinite(w.bodies()["pos"]).all()
+    for _ in range(5):
+        w.step(1 / 60)
+    assert np.isfinite(w.bodies()["pos"]).all()
