@@ -26,7 +26,8 @@ enum Counter
 	CTR_CURSOR_CLIP = 13,
 	CTR_CURSOR_CONCAVE = 14,
 	CTR_MESH_PAIRS = 15,  // broadphase pairs with a trimesh as A (listed by npCullKernel)
-	CTR_SMALL_ITEMS = 16,  // small x small hull items (thread-per-item kernel)
+	CTR_SMALL_ITEMS = 16,  // small x small hull items (thread-per-item kernel): box-like pairs, filled from the front of the list
+	CTR_SMALL_ITEMS_BACK = 17,  // the other small pairs, filled from the back of the same list (cleared together with 16)
 	CTR_COUNT = 24
 };
 enum OverflowBits

@@ -948,11 +948,16 @@ B3_D void smallPairThread(const NpArgs& a, const int4 it)
 	a.pairsOut[it.x].z = (int)slot;
 }
 
+// The list is filled from both ends: pairs of box-like hulls (<= 3 edge directions each: 6 + 6 + 9 axes) from the front, the
+// other small pairs (up to 44 axes) from the back, so that the lanes of a warp run loops of similar length.
 __global__ void __launch_bounds__(128) smallPairKernel(NpArgs a, const int4* __restrict__ smallItems)
 {
-	int numItems = (int)a.ctr[CTR_SMALL_ITEMS];
-	if (numItems > a.maxWorkItems) numItems = a.maxWorkItems;
-	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < numItems; s += gridDim.x * blockDim.x) smallPairThread(a, smallItems[s]);
+	int nFront = (int)a.ctr[CTR_SMALL_ITEMS], nBack = (int)a.ctr[CTR_SMALL_ITEMS_BACK];
+	if (nFront > a.maxWorkItems) nFront = a.maxWorkItems;
+	if (nBack > a.maxWorkItems - nFront) nBack = a.maxWorkItems - nFront;
+	const int numItems = nFront + nBack;
+	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < numItems; s += gridDim.x * blockDim.x)
+		smallPairThread(a, smallItems[s < nFront ? s : a.maxWorkItems - 1 - (s - nFront)]);
 }
 
 // ---------------------------------------------------------------- stage 1: quick reject
@@ -1015,24 +1020,42 @@ B3_D void pushItem(const NpArgs& a, int4* __restrict__ items, int p, int ca, int
 
 // warp-aggregated append of the kept items: small x small hull pairs go to the thread-per-item list, the rest to the
 // warp-per-item list
-B3_D void pushClassified(const NpArgs& a, bool keep, bool small, const int4& it, int4* __restrict__ items, int4* __restrict__ smallItems, int lane)
+B3_D void pushClassified(const NpArgs& a, bool keep, int small, const int4& it, int4* __restrict__ items, int4* __restrict__ smallItems, int lane)
 {
-	const unsigned int mg = __ballot_sync(FULL, keep && !small), ms = __ballot_sync(FULL, keep && small);
+	const unsigned int mg = __ballot_sync(FULL, keep && small == 0), mf = __ballot_sync(FULL, keep && small == 1), mb = __ballot_sync(FULL, keep && small == 2);
 	const unsigned int lt = (1u << lane) - 1u;
 	if (mg)
 	{
 		unsigned int slot = 0;
 		if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SURVIVORS], (unsigned int)__popc(mg));
 		slot = __shfl_sync(FULL, slot, 0) + __popc(mg & lt);
-		if (keep && !small && slot < (unsigned int)a.maxWorkItems) items[slot] = it;
+		if (keep && small == 0 && slot < (unsigned int)a.maxWorkItems) items[slot] = it;
 	}
-	if (ms)
+	if (mf | mb)
 	{
-		unsigned int slot = 0;
-		if (lane == 0) slot = atomicAdd(&a.ctr[CTR_SMALL_ITEMS], (unsigned int)__popc(ms));
-		slot = __shfl_sync(FULL, slot, 0) + __popc(ms & lt);
-		if (keep && small && slot < (unsigned int)a.maxWorkItems) smallItems[slot] = it;
+		// front and back cursors of the small-item list.  The ends cannot cross: every small item comes from a distinct
+		// broadphase pair or raw child item, and the list has room for all of those together (world.cu).
+		unsigned int sf = 0, sb = 0;
+		if (lane == 0)
+		{
+			if (mf) sf = atomicAdd(&a.ctr[CTR_SMALL_ITEMS], (unsigned int)__popc(mf));
+			if (mb) sb = atomicAdd(&a.ctr[CTR_SMALL_ITEMS_BACK], (unsigned int)__popc(mb));
+		}
+		sf = __shfl_sync(FULL, sf, 0) + __popc(mf & lt);
+		sb = __shfl_sync(FULL, sb, 0) + __popc(mb & lt);
+		if (keep && small == 1 && sf < (unsigned int)a.maxWorkItems) smallItems[sf] = it;
+		if (keep && small == 2 && sb < (unsigned int)a.maxWorkItems) smallItems[(unsigned int)a.maxWorkItems - 1u - sb] = it;
 	}
+}
+
+// 0 = not a pair of small hulls, 1 = both box-like (<= 3 edge directions), 2 = other small pair
+B3_D int smallClass(const NpArgs& a, int shapeA, int shapeB)
+{
+	const HullRef hA = loadHull(a.convex, shapeA), hB = loadHull(a.convex, shapeB);
+	const bool sm = hA.numVertices <= SMALL_VERTS && hA.numFaces <= SMALL_FACES && hA.numUniqueEdges <= SMALL_EDGES && hB.numVertices <= SMALL_VERTS &&
+					hB.numFaces <= SMALL_FACES && hB.numUniqueEdges <= SMALL_EDGES;
+	if (!sm) return 0;
+	return hA.numUniqueEdges <= 3 && hB.numUniqueEdges <= 3 ? 1 : 2;
 }
 
 // conservative world-space bounding sphere of one side: centre = hull centre, radius = circumscribed radius about it
@@ -1054,7 +1077,8 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 	for (int base = blockIdx.x * CULL_THREADS; base < numRaw; base += gridDim.x * CULL_THREADS)
 	{
 		const int r = base + threadIdx.x;
-		bool keep = false, small = false;
+		bool keep = false;
+		int small = 0;
 		int4 it = make_int4(0, 0, 0, 0);
 		if (r < numRaw)
 		{
@@ -1063,7 +1087,7 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 			if (resolveSide(a, a.pairs[it.x].x, it.y, A) && resolveSide(a, a.pairs[it.x].y, it.z, B))
 			{
 				keep = quickTest(a, A, B);
-				small = keep && isSmallHull(a, A.shape) && isSmallHull(a, B.shape);
+				small = keep ? smallClass(a, A.shape, B.shape) : 0;
 			}
 		}
 		pushClassified(a, keep, small, it, items, smallItems, lane);
@@ -1078,7 +1102,8 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 	for (int base = blockIdx.x * CULL_THREADS; base < numPairs; base += gridDim.x * CULL_THREADS)
 	{
 		const int p = base + threadIdx.x;
-		bool keep = false, small = false;
+		bool keep = false;
+		int small = 0;
 		if (p < numPairs)
 		{
 			const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
@@ -1097,7 +1122,7 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 						const float4 d = sub3(sA, sB);
 						const float rr = (rA + rB) * 1.001f + 1e-3f;
 						keep = dot3(d, d) <= rr * rr && quickTest(a, A, B);
-						small = keep && isSmallHull(a, A.shape) && isSmallHull(a, B.shape);
+						small = keep ? smallClass(a, A.shape, B.shape) : 0;
 					}
 				}
 				else if ((typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeA == B3B200_SHAPE_CONVEX_HULL) &&
@@ -1629,7 +1654,9 @@ __global__ void clampContactsKernel(unsigned int* ctr, int maxContacts, int maxW
 		ctr[CTR_OVERFLOW] |= OVF_CONTACTS;
 	}
 	// work items (child pairs of compounds + surviving pairs) beyond the queue capacity were dropped: say so
-	if (ctr[CTR_COMPOUND_PAIRS] > (unsigned int)maxWorkItems || ctr[CTR_SURVIVORS] > (unsigned int)maxWorkItems) ctr[CTR_OVERFLOW] |= OVF_COMPOUND;
+	if (ctr[CTR_COMPOUND_PAIRS] > (unsigned int)maxWorkItems || ctr[CTR_SURVIVORS] > (unsigned int)maxWorkItems ||
+		ctr[CTR_SMALL_ITEMS] + ctr[CTR_SMALL_ITEMS_BACK] > (unsigned int)maxWorkItems)
+		ctr[CTR_OVERFLOW] |= OVF_COMPOUND;
 }
 
 int launchNarrowphase(World* w)
@@ -1638,7 +1665,7 @@ int launchNarrowphase(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
-	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SMALL_ITEMS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SMALL_ITEMS], 0, 2 * sizeof(unsigned int), s));  // + CTR_SMALL_ITEMS_BACK
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 4 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors, CTR_MESH_PAIRS
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
