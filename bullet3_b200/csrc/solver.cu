@@ -285,9 +285,10 @@ B3_D void colourClaim(const SetupArgs& s, int c)
 	if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
 }
 
-// Step 2: the contact that is top on both of its bodies takes the lowest colour free on both.  Returns true when the
-// contact stays uncoloured for the next round.
-B3_D bool colourTry(const SetupArgs& s, int c)
+// Step 2: the contact that is top on both of its bodies takes the lowest colour free on both.  Returns the colour, -1 when
+// the contact stays uncoloured for the next round, -2 when it cannot be coloured at all (the caller counts the colours,
+// warp-aggregated).
+B3_D int colourTry(const SetupArgs& s, int c)
 {
 	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
 	const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
@@ -297,7 +298,7 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 	const unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
 	volatile unsigned long long* vp = s.bodyPrio;
 	const bool top = (aStatic || vp[a] == prio) && (bStatic || vp[b] == prio);
-	if (!top) return true;
+	if (!top) return -1;
 	// (masks written by other CTAs in earlier rounds: read through L2)
 	unsigned long long m0 = 0ull, m1 = 0ull;
 	if (!aStatic)
@@ -325,7 +326,7 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 		if (!aStatic) s.bodyPrio[a] = 0ull;
 		if (!bStatic) s.bodyPrio[b] = 0ull;
 		atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-		return false;
+		return -2;
 	}
 	const unsigned long long bit = 1ull << (colour & 63);
 	const int word = colour >> 6;
@@ -341,8 +342,7 @@ B3_D bool colourTry(const SetupArgs& s, int c)
 	}
 	s.contactColour[c] = colour;
 	s.contacts[c].batchIdx = colour;
-	atomicAdd(&s.batchCount[colour], 1u);
-	return false;
+	return colour;
 }
 
 // Single-pass colouring: every contact takes the lowest colour that is free on both of its dynamic bodies by setting the
@@ -477,7 +477,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 		{
 			const int i = base + lane;
 			const int c = i < count ? (cur ? (int)__ldcg(&cur[i]) : i) : 0;
-			const bool left = i < count && colourTry(s, c);
+			const int got = i < count ? colourTry(s, c) : -2;
+			const bool left = got == -1;
+			__syncwarp();
+			warpCountByKey(s.batchCount, got, lane);
 			// the still uncoloured contacts of this warp go to the next round's list
 			const unsigned int m = __ballot_sync(0xffffffffu, left);
 			if (m)
@@ -508,7 +511,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
 					{
 						const int i = base + lane;
 						const int c = i < count ? (int)__ldcg(&cur[i]) : 0;
-						const bool left = i < count && colourTry(s, c);
+						const int got = i < count ? colourTry(s, c) : -2;
+						const bool left = got == -1;
+						__syncwarp();
+						warpCountByKey(s.batchCount, got, lane);
 						const unsigned int m = __ballot_sync(0xffffffffu, left);
 						if (m)
 						{
