@@ -1099,12 +1099,14 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
 	const int lane = threadIdx.x & 31;
-	for (int base = blockIdx.x * CULL_THREADS; base < numPairs; base += gridDim.x * CULL_THREADS)
+	__shared__ int quickQueueAll[CULL_THREADS / 32][64];
+	int* quickQueue = quickQueueAll[threadIdx.x >> 5];
+	int qn = 0;  // warp-uniform
+	for (int base = blockIdx.x * CULL_THREADS; base < numPairs || qn > 0; base += gridDim.x * CULL_THREADS)
 	{
 		const int p = base + threadIdx.x;
-		bool keep = false;
-		int small = 0;
-		if (p < numPairs)
+		bool wantQuick = false;
+		if (base < numPairs && p < numPairs)
 		{
 			const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
 			const int cA = a.coll[bodyA], cB = a.coll[bodyB];
@@ -1116,13 +1118,13 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 					Side A, B;
 					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B))
 					{
-						// bounding spheres first (conservative, like the child pairs below), then the exact quick reject
+						// bounding spheres first (conservative, like the child pairs below); the exact quick reject runs below on
+						// the warp's queue of such pairs, 32 at a time, so that its lanes are not idled by the other pair types
 						float rA, rB;
 						const float4 sA = boundSphere(a, A, rA), sB = boundSphere(a, B, rB);
 						const float4 d = sub3(sA, sB);
 						const float rr = (rA + rB) * 1.001f + 1e-3f;
-						keep = dot3(d, d) <= rr * rr && quickTest(a, A, B);
-						small = keep ? smallClass(a, A.shape, B.shape) : 0;
+						wantQuick = dot3(d, d) <= rr * rr;
 					}
 				}
 				else if ((typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeA == B3B200_SHAPE_CONVEX_HULL) &&
@@ -1181,7 +1183,34 @@ __global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __r
 				}
 			}
 		}
-		pushClassified(a, keep, small, make_int4(p, -1, -1, 0), items, smallItems, lane);
+		{
+			const unsigned int m = __ballot_sync(FULL, wantQuick);
+			if (wantQuick) quickQueue[qn + __popc(m & ((1u << lane) - 1u))] = p;
+			qn += __popc(m);
+			__syncwarp();
+		}
+		// run the exact quick reject on a full warp's worth of queued convex pairs (or on what is left at the end)
+		const bool last = base + (int)(gridDim.x * CULL_THREADS) >= numPairs;
+		while (qn >= 32 || (last && qn > 0))
+		{
+			const int take = qn < 32 ? qn : 32;
+			bool keep = false;
+			int small = 0;
+			int q = -1;
+			if (lane < take)
+			{
+				q = quickQueue[qn - take + lane];
+				Side A, B;
+				if (resolveSide(a, a.pairs[q].x, -1, A) && resolveSide(a, a.pairs[q].y, -1, B))
+				{
+					keep = quickTest(a, A, B);
+					small = keep ? smallClass(a, A.shape, B.shape) : 0;
+				}
+			}
+			qn -= take;
+			__syncwarp();
+			pushClassified(a, keep, small, make_int4(q, -1, -1, 0), items, smallItems, lane);
+		}
 	}
 }
 
