@@ -240,7 +240,7 @@ B3_D bool resolveSide(const NpArgs& a, int body, int child, Side& s)
 // Part 1: b3FindSeparatingAxis.  Returns false when the hulls are separated; otherwise *sepOut is the
 // minimum-penetration axis (the reference's sepNormalWorldSpace).
 B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 ornA, float4 posB, float4 ornB,
-				  float4* bufA, float4* bufB, float4* sup, int* queue, int lane, float4* sepOut)
+				  float4* bufA, float4* bufB, float4* sup, int* queue, unsigned char* aliveA, unsigned char* aliveB, int lane, float4* sepOut)
 {
 	posA.w = 0.f;
 	posB.w = 0.f;
@@ -335,25 +335,41 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 	// of B, edge pairs) are filtered 32 at a time and compacted into a per-warp queue, so the
 	// expensive projection test always runs with (nearly) all 32 lanes busy.
 	int qn = 0;
-	int next = 0;
 	const unsigned int ltMask = (1u << lane) - 1u;
+	// Phase 0 generates the face candidates, phase 1 the edge x edge candidates; both feed the same queue.
+	// Edge pairs are pruned by rows and columns first: the cheap per-pair bound below drops (e0, e1) when
+	// (deltaC2 . (e0 x e1))^2 < 0.999 S^2 |e0 x e1|^2.  Since deltaC2 . (e0 x e1) = (deltaC2 x e0) . e1 and (deltaC2 x e0) is
+	// perpendicular to e0, the left side is at most |deltaC2 x e0|^2 |e0 x e1|^2 / |e0|^2: an edge e0 with
+	// |deltaC2 x e0|^2 < 0.99 S^2 |e0|^2 (the 1 % gap dwarfs the FP32 error of either side) loses EVERY pair it is part of, and
+	// likewise an edge e1.  Only the surviving rows x columns are enumerated; exactly the pairs that would have passed the
+	// per-pair bound reach the later tests, so the result is unchanged.  S is taken when the face candidates have all been
+	// generated (any earlier, larger curMin only prunes less).
+	int phase = 0, next = 0, limit = nF;
+	int nAA = nEA, nAB = nEB;
+	bool useLists = false;
+	float invNAB = invNEB;
 	for (;;)
 	{
-		while (qn < 32 && next < total)
+		while (qn < 32 && next < limit)
 		{
-			const int k = next + lane;
+			const int p = next + lane;
 			bool cand = false;
-			if (k < nF)
+			int k = p;
+			if (phase == 0)
 			{
-				const b3b200_face* f = k < nFA ? &a.faces[hA.faceOffset + k] : &a.faces[hB.faceOffset + (k - nFA)];
-				// a face whose normal is bitwise +-equal to an earlier face's gives the identical depth
-				// and can never win the strict "d < dmin" (flag set at registration, world.cu)
-				cand = __ldg(&f->pad1) == 0;
+				if (p < nF)
+				{
+					const b3b200_face* f = p < nFA ? &a.faces[hA.faceOffset + p] : &a.faces[hB.faceOffset + (p - nFA)];
+					// a face whose normal is bitwise +-equal to an earlier face's gives the identical depth
+					// and can never win the strict "d < dmin" (flag set at registration, world.cu)
+					cand = __ldg(&f->pad1) == 0;
+				}
 			}
-			else if (k < total)
+			else if (p < limit)
 			{
-				const int e = k - nF;
-				const int e0 = __float2int_rz(((float)e + 0.5f) * invNEB), e1 = e - e0 * nEB;  // == e / nEB (exact for these ranges), without the integer division
+				const int i0 = __float2int_rz(((float)p + 0.5f) * invNAB), i1 = p - i0 * nAB;  // == p / nAB (exact for these ranges), without the integer division
+				const int e0 = useLists ? (int)aliveA[i0] : i0, e1 = useLists ? (int)aliveB[i1] : i1;
+				k = nF + e0 * nEB + e1;
 				const float4 edge0 = staged ? bufA[e0] : quatRotate(ornA, __ldg(&a.uniqueEdges[hA.uniqueEdgesOffset + e0]));
 				const float4 edge1 = staged ? bufB[e1] : quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
 				const float4 cr = cross3(edge0, edge1);
@@ -388,9 +404,46 @@ B3_D bool satWarp(const NpArgs& a, int shapeA, int shapeB, float4 posA, float4 o
 			const unsigned int m = __ballot_sync(FULL, cand);
 			if (cand) queue[qn + __popc(m & ltMask)] = k;
 			qn += __popc(m);
-			// do not mix face and edge candidates of different rounds' bounds: nothing to do, bounds only tighten
 			next += 32;
 			__syncwarp();
+		}
+		if (phase == 0 && next >= limit && (qn < 32 || rsum - curMin > 0.f))
+		{
+			// all faces generated: switch to the edge pairs (unless no face has been projected yet -- then one round first, so
+			// that there is a bound to prune with)
+			if (!(qn > 0 && curMin == FLT_MAX))
+			{
+				const float S0 = rsum - curMin;
+				useLists = staged && S0 > 0.f && nEA * nEB >= 64;
+				if (useLists)
+				{
+					nAA = 0;
+					nAB = 0;
+					for (int base = 0; base < nEA + nEB; base += 32)
+					{
+						const int e = base + lane;
+						bool alive = false;
+						const bool onA = e < nEA;
+						if (e < nEA + nEB)
+						{
+							const float4 ed = onA ? bufA[e] : bufB[e - nEA];
+							const float4 u = cross3(deltaC2, ed);
+							alive = dot3(u, u) >= 0.99f * S0 * S0 * dot3(ed, ed);
+						}
+						const unsigned int mA = __ballot_sync(FULL, alive && onA), mB = __ballot_sync(FULL, alive && !onA);
+						if (alive && onA) aliveA[nAA + __popc(mA & ltMask)] = (unsigned char)e;
+						if (alive && !onA) aliveB[nAB + __popc(mB & ltMask)] = (unsigned char)(e - nEA);
+						nAA += __popc(mA);
+						nAB += __popc(mB);
+					}
+					__syncwarp();
+				}
+				phase = 1;
+				next = 0;
+				limit = nAA * nAB;
+				invNAB = 1.0f / (float)(nAB > 0 ? nAB : 1);
+				if (qn < 32 && limit > 0) continue;  // top the queue up with edge candidates before projecting
+			}
 		}
 		if (qn == 0) break;
 		const int take = qn < 32 ? qn : 32;
@@ -1223,6 +1276,7 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4*
 	__shared__ float4 bufAll[NP_WARPS][2][SAT_EDGES];
 	__shared__ float4 supAll[NP_WARPS][2 * SUP_K];
 	__shared__ int queueAll[NP_WARPS][64];
+	__shared__ unsigned char aliveAll[NP_WARPS][2][SAT_EDGES];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
@@ -1248,7 +1302,7 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4*
 			if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
 			{
 				float4 sep;
-				const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, sup, queue, lane, &sep);
+				const bool hit = satWarp(a, A.shape, B.shape, A.pos, A.orn, B.pos, B.orn, bufA, bufB, sup, queue, aliveAll[warp][0], aliveAll[warp][1], lane, &sep);
 				if (hit && lane == 0)
 				{
 					const unsigned int slot = atomicAdd(&a.ctr[CTR_OVERLAPS], 1u);
