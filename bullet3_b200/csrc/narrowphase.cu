@@ -787,6 +787,168 @@ B3_D int clipFaceSerial(const float4* in, int numIn, const float4& n, float eq, 
 	return numOut;
 }
 
+// b3ClipHullHullSingle + b3ReduceContacts + append for ONE item in one thread (the second half of the reference's
+// b3ContactConvexConvexSAT, in its statement order), given the separating axis.  Works for any hull as long as the two
+// chosen faces are small polygons (incident face + one vertex per clipping plane <= SMALL_POLY); returns 1 without touching
+// anything when they are not -- the caller then leaves the item to the warp-per-item clipKernel.
+B3_D int clipThread(const NpArgs& a, const int4 it, int bodyA, int bodyB, const Side& A, const Side& B, const HullRef& hA, const HullRef& hB, const float4& posA,
+					const float4& posB, const float4& ornA, const float4& ornB, const float4& sep)
+{
+	// ---- b3ClipHullHullSingle: orientations round-trip through b3Transform (:323-337)
+	const float4 ornA2 = quatFromMat(matFromQuat(ornA)), ornB2 = quatFromMat(matFromQuat(ornB));
+	float4 bufA[SMALL_POLY], bufB[SMALL_POLY];
+	// b3ClipHullAgainstHull: incident face of B
+	int closestFaceB = -1;
+	{
+		float dmax = -FLT_MAX;
+		for (int f = 0; f < hB.numFaces; f++)
+		{
+			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+			const float d = dot3(quatRotate(ornB2, normal), sep);
+			if (d > dmax)
+			{
+				dmax = d;
+				closestFaceB = f;
+			}
+		}
+	}
+	if (closestFaceB < 0) return 0;
+	int numVertsIn;
+	{
+		const b3b200_face* polyB = &a.faces[hB.faceOffset + closestFaceB];
+		const int idxOff = __ldg(&polyB->indexOffset);
+		numVertsIn = __ldg(&polyB->numIndices);
+		if (numVertsIn > SMALL_POLY) return 1;
+		for (int e = 0; e < numVertsIn; e++) bufA[e] = transformPoint(__ldg(&a.vertices[hB.vertexOffset + __ldg(&a.indices[idxOff + e])]), posB, ornB2);
+	}
+	// b3ClipFaceAgainstHull: reference face of A
+	int closestFaceA = -1;
+	{
+		float dm = FLT_MAX;
+		for (int f = 0; f < hA.numFaces; f++)
+		{
+			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
+			const float d = dot3(quatRotate(ornA2, mk4(normal.x, normal.y, normal.z)), sep);
+			if (d < dm)
+			{
+				dm = d;
+				closestFaceA = f;
+			}
+		}
+	}
+	if (closestFaceA < 0) return 0;
+	const b3b200_face* polyA = &a.faces[hA.faceOffset + closestFaceA];
+	const float4 planeA = __ldg(reinterpret_cast<const float4*>(&polyA->plane));
+	const int idxOffA = __ldg(&polyA->indexOffset);
+	const int numVerticesA = __ldg(&polyA->numIndices);
+	if (numVertsIn + numVerticesA > SMALL_POLY) return 1;  // every clipping plane can add one vertex
+	const float4 worldPlaneAnormal1 = quatRotate(ornA2, mk4(planeA.x, planeA.y, planeA.z));
+	float4* pIn = bufA;
+	float4* pOut = bufB;
+	for (int e0 = 0; e0 < numVerticesA; e0++)
+	{
+		const float4 va = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + e0])]);
+		const float4 vb = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + ((e0 + 1) % numVerticesA)])]);
+		const float4 worldEdge0 = quatRotate(ornA2, sub3(va, vb));
+		const float4 planeNormalWS = neg3(cross3(worldEdge0, worldPlaneAnormal1));
+		const float4 worldA1 = transformPoint(va, posA, ornA2);
+		const float planeEqWS = -dot3(worldA1, planeNormalWS);
+		const int numOut = clipFaceSerial(pIn, numVertsIn, planeNormalWS, planeEqWS, pOut);
+		float4* t = pOut;
+		pOut = pIn;
+		pIn = t;
+		numVertsIn = numOut;
+	}
+	int numContactsOut = 0;
+	{
+		const float planeEqWS = planeA.w - dot3(worldPlaneAnormal1, posA);
+		for (int i = 0; i < numVertsIn; i++)
+		{
+			float4 pt = pIn[i];
+			float depth = dot3(worldPlaneAnormal1, pt) + planeEqWS;
+			if (depth <= a.clipMin) depth = a.clipMin;
+			if (depth <= a.clipMax)
+			{
+				pt.w = depth;
+				pOut[numContactsOut++] = pt;
+			}
+		}
+	}
+	if (numContactsOut <= 0) return 0;
+	const float4* pts = pOut;
+
+	// ---- b3ReduceContacts
+	int idx[4] = {0, 1, 2, 3};
+	int numPoints = numContactsOut;
+	if (numContactsOut > 4)
+	{
+		const int nP = numContactsOut;
+		float4 center = mk4(0, 0, 0);
+		for (int i = 0; i < nP; i++) center = add3(center, pts[i]);
+		center = scale3(center, 1.0f / (float)nP);
+		const float4 aVector = sub3(pts[0], center);
+		float4 u = cross3(sep, aVector);
+		float4 v = cross3(sep, u);
+		u = normalized3(u);
+		v = normalized3(v);
+		float minW = FLT_MAX;
+		int minIndex = -1;
+		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
+		for (int ie = 0; ie < nP; ie++)
+		{
+			if (pts[ie].w < minW)
+			{
+				minW = pts[ie].w;
+				minIndex = ie;
+			}
+			const float4 r = sub3(pts[ie], center);
+			float f = dot3(u, r);
+			if (f < m0)
+			{
+				m0 = f;
+				idx[0] = ie;
+			}
+			f = dot3(neg3(u), r);
+			if (f < m1)
+			{
+				m1 = f;
+				idx[1] = ie;
+			}
+			f = dot3(v, r);
+			if (f < m2)
+			{
+				m2 = f;
+				idx[2] = ie;
+			}
+			f = dot3(neg3(v), r);
+			if (f < m3)
+			{
+				m3 = f;
+				idx[3] = ie;
+			}
+		}
+		if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
+		numPoints = 4;
+	}
+
+	// ---- append
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return 0;
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	for (int i = 0; i < 4; i++) cw[i] = i < numPoints ? pts[idx[i]] : mk4(0, 0, 0, 0);
+	cw[4] = mk4(sep.x, sep.y, sep.z, (float)numPoints);
+	int4 t;
+	t.x = (int)(0u | (45874u << 16));
+	t.y = 0;
+	t.z = A.invMass == 0.f ? -bodyA : bodyA;
+	t.w = B.invMass == 0.f ? -bodyB : bodyB;
+	reinterpret_cast<int4*>(c)[5] = t;
+	reinterpret_cast<int4*>(c)[6] = make_int4(it.y, it.z, 0, 0);
+	a.pairsOut[it.x].z = (int)slot;
+	return 0;
+}
+
 B3_D void smallPairThread(const NpArgs& a, const int4 it)
 {
 	const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
@@ -848,157 +1010,7 @@ B3_D void smallPairThread(const NpArgs& a, const int4 it)
 	}
 	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
 
-	// ---- b3ClipHullHullSingle: orientations round-trip through b3Transform (:323-337)
-	const float4 ornA2 = quatFromMat(matFromQuat(ornA)), ornB2 = quatFromMat(matFromQuat(ornB));
-	float4 bufA[SMALL_POLY], bufB[SMALL_POLY];
-	// b3ClipHullAgainstHull: incident face of B
-	int closestFaceB = -1;
-	{
-		float dmax = -FLT_MAX;
-		for (int f = 0; f < hB.numFaces; f++)
-		{
-			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
-			const float d = dot3(quatRotate(ornB2, normal), sep);
-			if (d > dmax)
-			{
-				dmax = d;
-				closestFaceB = f;
-			}
-		}
-	}
-	if (closestFaceB < 0) return;
-	int numVertsIn;
-	{
-		const b3b200_face* polyB = &a.faces[hB.faceOffset + closestFaceB];
-		const int idxOff = __ldg(&polyB->indexOffset);
-		numVertsIn = __ldg(&polyB->numIndices);
-		if (numVertsIn > SMALL_POLY) numVertsIn = SMALL_POLY;
-		for (int e = 0; e < numVertsIn; e++) bufA[e] = transformPoint(__ldg(&a.vertices[hB.vertexOffset + __ldg(&a.indices[idxOff + e])]), posB, ornB2);
-	}
-	// b3ClipFaceAgainstHull: reference face of A
-	int closestFaceA = -1;
-	{
-		float dm = FLT_MAX;
-		for (int f = 0; f < hA.numFaces; f++)
-		{
-			const float4 normal = __ldg(reinterpret_cast<const float4*>(&a.faces[hA.faceOffset + f].plane));
-			const float d = dot3(quatRotate(ornA2, mk4(normal.x, normal.y, normal.z)), sep);
-			if (d < dm)
-			{
-				dm = d;
-				closestFaceA = f;
-			}
-		}
-	}
-	if (closestFaceA < 0) return;
-	const b3b200_face* polyA = &a.faces[hA.faceOffset + closestFaceA];
-	const float4 planeA = __ldg(reinterpret_cast<const float4*>(&polyA->plane));
-	const int idxOffA = __ldg(&polyA->indexOffset);
-	const int numVerticesA = __ldg(&polyA->numIndices);
-	const float4 worldPlaneAnormal1 = quatRotate(ornA2, mk4(planeA.x, planeA.y, planeA.z));
-	float4* pIn = bufA;
-	float4* pOut = bufB;
-	for (int e0 = 0; e0 < numVerticesA; e0++)
-	{
-		const float4 va = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + e0])]);
-		const float4 vb = __ldg(&a.vertices[hA.vertexOffset + __ldg(&a.indices[idxOffA + ((e0 + 1) % numVerticesA)])]);
-		const float4 worldEdge0 = quatRotate(ornA2, sub3(va, vb));
-		const float4 planeNormalWS = neg3(cross3(worldEdge0, worldPlaneAnormal1));
-		const float4 worldA1 = transformPoint(va, posA, ornA2);
-		const float planeEqWS = -dot3(worldA1, planeNormalWS);
-		const int numOut = clipFaceSerial(pIn, numVertsIn, planeNormalWS, planeEqWS, pOut);
-		float4* t = pOut;
-		pOut = pIn;
-		pIn = t;
-		numVertsIn = numOut;
-	}
-	int numContactsOut = 0;
-	{
-		const float planeEqWS = planeA.w - dot3(worldPlaneAnormal1, posA);
-		for (int i = 0; i < numVertsIn; i++)
-		{
-			float4 pt = pIn[i];
-			float depth = dot3(worldPlaneAnormal1, pt) + planeEqWS;
-			if (depth <= a.clipMin) depth = a.clipMin;
-			if (depth <= a.clipMax)
-			{
-				pt.w = depth;
-				pOut[numContactsOut++] = pt;
-			}
-		}
-	}
-	if (numContactsOut <= 0) return;
-	const float4* pts = pOut;
-
-	// ---- b3ReduceContacts
-	int idx[4] = {0, 1, 2, 3};
-	int numPoints = numContactsOut;
-	if (numContactsOut > 4)
-	{
-		const int nP = numContactsOut;
-		float4 center = mk4(0, 0, 0);
-		for (int i = 0; i < nP; i++) center = add3(center, pts[i]);
-		center = scale3(center, 1.0f / (float)nP);
-		const float4 aVector = sub3(pts[0], center);
-		float4 u = cross3(sep, aVector);
-		float4 v = cross3(sep, u);
-		u = normalized3(u);
-		v = normalized3(v);
-		float minW = FLT_MAX;
-		int minIndex = -1;
-		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
-		for (int ie = 0; ie < nP; ie++)
-		{
-			if (pts[ie].w < minW)
-			{
-				minW = pts[ie].w;
-				minIndex = ie;
-			}
-			const float4 r = sub3(pts[ie], center);
-			float f = dot3(u, r);
-			if (f < m0)
-			{
-				m0 = f;
-				idx[0] = ie;
-			}
-			f = dot3(neg3(u), r);
-			if (f < m1)
-			{
-				m1 = f;
-				idx[1] = ie;
-			}
-			f = dot3(v, r);
-			if (f < m2)
-			{
-				m2 = f;
-				idx[2] = ie;
-			}
-			f = dot3(neg3(v), r);
-			if (f < m3)
-			{
-				m3 = f;
-				idx[3] = ie;
-			}
-		}
-		if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
-		numPoints = 4;
-	}
-
-	// ---- append
-	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
-	if (slot >= (unsigned int)a.maxContacts) return;
-	b3b200_contact4* c = &a.contacts[slot];
-	float4* cw = reinterpret_cast<float4*>(c);
-	for (int i = 0; i < 4; i++) cw[i] = i < numPoints ? pts[idx[i]] : mk4(0, 0, 0, 0);
-	cw[4] = mk4(sep.x, sep.y, sep.z, (float)numPoints);
-	int4 t;
-	t.x = (int)(0u | (45874u << 16));
-	t.y = 0;
-	t.z = A.invMass == 0.f ? -bodyA : bodyA;
-	t.w = B.invMass == 0.f ? -bodyB : bodyB;
-	reinterpret_cast<int4*>(c)[5] = t;
-	reinterpret_cast<int4*>(c)[6] = make_int4(it.y, it.z, 0, 0);
-	a.pairsOut[it.x].z = (int)slot;
+	clipThread(a, it, bodyA, bodyB, A, B, hA, hB, posA, posB, ornA, ornB, sep);
 }
 
 // The list is filled from both ends: pairs of box-like hulls (<= 3 edge directions each: 6 + 6 + 9 axes) from the front, the
@@ -1315,15 +1327,61 @@ __global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4*
 	}
 }
 
+// ---------------------------------------------------------------- stage 3a: clipping, one THREAD per overlapping item
+// The faces that get clipped are small polygons even for the large hulls (triangles, quads), so the warp-per-item clipKernel
+// runs its polygon steps on 1-6 lanes.  One thread per item does the same work serially (clipThread); the rare item whose
+// faces do not fit its 16-vertex polygon buffers is passed on to clipKernel through a fallback list.
+__global__ void __launch_bounds__(128) clipThreadKernel(NpArgs a, const int4* __restrict__ overlapItems, const float4* __restrict__ overlapSep,
+														  int4* __restrict__ fallbackItems, float4* __restrict__ fallbackSep)
+{
+	const int numOverlaps = (int)a.ctr[CTR_OVERLAPS];
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * blockDim.x; base < numOverlaps; base += gridDim.x * blockDim.x)
+	{
+		const int s = base + (int)threadIdx.x;
+		bool fallback = false;
+		int4 it = make_int4(0, 0, 0, 0);
+		float4 sep = mk4(0, 0, 0);
+		if (s < numOverlaps)
+		{
+			it = overlapItems[s];
+			sep = overlapSep[s];
+			const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+			Side A, B;
+			if (resolveSide(a, bodyA, it.y, A) && resolveSide(a, bodyB, it.z, B))
+			{
+				float4 posA = A.pos, posB = B.pos;
+				posA.w = 0.f;
+				posB.w = 0.f;
+				const HullRef hA = loadHull(a.convex, A.shape), hB = loadHull(a.convex, B.shape);
+				fallback = clipThread(a, it, bodyA, bodyB, A, B, hA, hB, posA, posB, A.orn, B.orn, mk4(sep.x, sep.y, sep.z)) != 0;
+			}
+		}
+		__syncwarp();
+		const unsigned int m = __ballot_sync(FULL, fallback);
+		if (m)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_CLIP_FALLBACK], (unsigned int)__popc(m));
+			slot = __shfl_sync(FULL, slot, 0) + __popc(m & ((1u << lane) - 1u));
+			if (fallback)
+			{
+				fallbackItems[slot] = it;
+				fallbackSep[slot] = sep;
+			}
+		}
+	}
+}
+
 // ---------------------------------------------------------------- stage 3: clipping + reduction + append
-__global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int4* __restrict__ overlapItems, const float4* __restrict__ overlapSep)
+__global__ void __launch_bounds__(NP_THREADS) clipKernel(NpArgs a, const int4* __restrict__ overlapItems, const float4* __restrict__ overlapSep, int countIndex)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][MAX_POLY];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
-	const int numOverlaps = (int)a.ctr[CTR_OVERLAPS];
+	const int numOverlaps = (int)a.ctr[countIndex];
 	for (;;)
 	{
 		int base = 0;
@@ -1748,7 +1806,7 @@ int launchNarrowphase(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONTACTS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SURVIVORS], 0, 2 * sizeof(unsigned int), s));  // + CTR_OVERLAPS
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_COMPOUND_PAIRS], 0, sizeof(unsigned int), s));
-	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SMALL_ITEMS], 0, 2 * sizeof(unsigned int), s));  // + CTR_SMALL_ITEMS_BACK
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_SMALL_ITEMS], 0, 3 * sizeof(unsigned int), s));  // + CTR_SMALL_ITEMS_BACK, CTR_CLIP_FALLBACK
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CURSOR_SAT], 0, 4 * sizeof(unsigned int), s));  // + CLIP, CONCAVE cursors, CTR_MESH_PAIRS
 	NpArgs a;
 	a.pairs = w->bp.pairs.ptr;
@@ -1813,7 +1871,17 @@ int launchNarrowphase(World* w)
 	satKernel<<<w->smCount * 12, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
 	B3_LAUNCH_CHECK();
 	if (w->timing) B3_CUDA_CHECK(cudaEventRecord(w->evSat[1], s));
-	clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr);
+	if (!fork)
+	{
+		// thread-per-item clip; what does not fit its buffers comes back in a fallback list.  The lists reuse buffers that are
+		// dead by now on this stream: the SAT work items and the small-pair items (not with forked branches: the small-pair
+		// kernel may still be reading its list)
+		clipThreadKernel<<<w->smCount * 16, 128, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr, w->dSurvivors.ptr, reinterpret_cast<float4*>(w->dSmallItems.ptr));
+		B3_LAUNCH_CHECK();
+		clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dSurvivors.ptr, reinterpret_cast<const float4*>(w->dSmallItems.ptr), (int)CTR_CLIP_FALLBACK);
+	}
+	else
+		clipKernel<<<w->smCount * 8, NP_THREADS, 0, s>>>(a, w->dOverlapPairs.ptr, w->dOverlapSep.ptr, (int)CTR_OVERLAPS);
 	B3_LAUNCH_CHECK();
 	if (w->hasConcave && !fork) B3_TRY(launchConcave(w, s));
 	if (fork)
