@@ -25,6 +25,9 @@ namespace
 constexpr int CC_THREADS = 128;
 constexpr int CC_WARPS = CC_THREADS / 32;
 constexpr int CC_MAX_POLY = 64;  // vertexFaceCapacity (b3ConvexHullContact.cpp:3481)
+// triangle x SMALL hull (boxes, tetrahedra, box children of compounds): one thread per item (concaveSmallKernel)
+constexpr int CCT_VERTS = 8, CCT_FACES = 6, CCT_EDGES = 6;
+constexpr int CCT_POLY = 16;  // a face of <= 8 vertices clipped by <= 3 planes
 #define FULL 0xffffffffu
 
 struct CcArgs
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* 
 	for (int base = blockIdx.x * blockDim.x; base < numRaw; base += gridDim.x * blockDim.x)
 	{
 		const int r = base + threadIdx.x;
-		bool keep = false;
+		bool keep = false, smallB = false;
 		int4 it = make_int4(0, 0, 0, 0);
 		if (r < numRaw)
 		{
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* 
 			else
 				shapeB = __ldg(&a.collidables[cB].shapeIndex);
 			const HullRef hB = loadHull(a.convex, shapeB);
+			smallB = hB.numVertices <= CCT_VERTS && hB.numFaces <= CCT_FACES && hB.numUniqueEdges <= CCT_EDGES;
 			float4 localCenter = add3(add3(vA[0], vA[1]), vA[2]);
 			localCenter = scale3(localCenter, 1.f / 3.f);
 			const float4 deltaC2 = sub3(transformPoint(localCenter, posA, ornA), transformPoint(hB.localCenter, posB, ornB));
@@ -594,16 +598,337 @@ __global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* 
 			}
 			}
 		}
-		const unsigned int m = __ballot_sync(FULL, keep);
-		if (m)
+		// survivors <= raw items <= capacity, so the two ends of the list cannot meet: items with a small hull B (thread-per-item
+		// kernel) from the front, the others (warp-per-item kernel) from the back
+		const unsigned int mf = __ballot_sync(FULL, keep && smallB), mb = __ballot_sync(FULL, keep && !smallB);
+		if (mf | mb)
 		{
-			unsigned int slot = 0;
-			if (lane == 0) slot = atomicAdd(&a.ctr[CTR_CONCAVE_SURVIVORS], (unsigned int)__popc(m));
-			slot = __shfl_sync(FULL, slot, 0);
-			slot += __popc(m & ((1u << lane) - 1u));
-			if (keep) items[slot] = it;  // survivors <= raw items <= capacity
+			unsigned int sf = 0, sb = 0;
+			if (lane == 0)
+			{
+				if (mf) sf = atomicAdd(&a.ctr[CTR_CONCAVE_SURVIVORS], (unsigned int)__popc(mf));
+				if (mb) sb = atomicAdd(&a.ctr[CTR_CONCAVE_SURVIVORS_BACK], (unsigned int)__popc(mb));
+			}
+			const unsigned int lt = (1u << lane) - 1u;
+			sf = __shfl_sync(FULL, sf, 0) + __popc(mf & lt);
+			sb = __shfl_sync(FULL, sb, 0) + __popc(mb & lt);
+			if (keep && smallB) items[sf] = it;
+			if (keep && !smallB) items[(unsigned int)a.maxItems - 1u - sb] = it;
 		}
 	}
+}
+
+// clipFaceGlobal (shared/b3ClipFaces.h:21-64), serial
+B3_D int clipFaceGlobalSerial(const float4* in, int numIn, const float4& n, float eq, float4* out)
+{
+	int numOut = 0;
+	for (int ve = 0; ve < numIn; ve++)
+	{
+		const float4 first = in[ve == 0 ? numIn - 1 : ve - 1];
+		const float4 end = in[ve];
+		const float ds = dot3(n, first) + eq;
+		const float de = dot3(n, end) + eq;
+		if (ds < 0)
+		{
+			if (de < 0)
+			{
+				if (numOut < CCT_POLY) out[numOut++] = end;
+			}
+			else if (numOut < CCT_POLY)
+				out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+		}
+		else if (de < 0)
+		{
+			if (numOut < CCT_POLY) out[numOut++] = lerp3(first, end, (ds * 1.f / (ds - de)));
+			if (numOut < CCT_POLY) out[numOut++] = end;
+		}
+	}
+	return numOut;
+}
+
+// Triangle x small hull, ONE THREAD per item: the same steps as concaveContactKernel (SAT over the 5-face triangle prism, the
+// faces of B and the 3 x E_B edge axes in the reference's order with its first-strict-minimum rule, b3FindClippingFaces,
+// clipFaceGlobal, b3ExtractManifoldSequentialGlobal, append), serially.  With at most 5 + 6 + 18 axes over 3 + 8 vertices a
+// warp per item keeps about 8 lanes busy; here 32 items share a warp.
+B3_D void concaveSmallThread(const CcArgs& a, const int4 it)
+{
+	const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
+	const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+	float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
+	const float4 ornA = a.pose[2 * bodyA + 1];
+	float4 ornB = a.pose[2 * bodyB + 1];
+	const float invMassA = posA.w, invMassB = posB.w;
+	posA.w = 0.f;
+	posB.w = 0.f;
+	const b3b200_convex_polyhedron* cvA = &a.convex[__ldg(&a.collidables[cA].shapeIndex)];
+	const b3b200_face* faceA = &a.faces[__ldg(&cvA->faceOffset) + it.y];
+	const float4 plane = __ldg(reinterpret_cast<const float4*>(&faceA->plane));
+	const int idxOffA = __ldg(&faceA->indexOffset), vOffA = __ldg(&cvA->vertexOffset);
+	float4 vA[3];
+#pragma unroll
+	for (int i = 0; i < 3; i++) vA[i] = __ldg(&a.vertices[vOffA + __ldg(&a.indices[idxOffA + i])]);
+	const float4 normal = mk4(plane.x, plane.y, plane.z);
+	float4 triN[5];
+	triN[0] = normal;
+	triN[1] = neg3(normal);
+	{
+		int prev = 2;
+#pragma unroll
+		for (int i = 0; i < 3; i++)
+		{
+			triN[2 + i] = normalized3(cross3(normal, sub3(vA[prev], vA[i])));
+			prev = i;
+		}
+	}
+	float4 localCenter = add3(add3(vA[0], vA[1]), vA[2]);
+	localCenter = scale3(localCenter, 1.f / 3.f);
+	int shapeB;
+	if (it.z >= 0)
+	{
+		const b3b200_child_shape* ch = &a.childShapes[it.z];
+		const float4 cp = __ldg(reinterpret_cast<const float4*>(&ch->childPosition));
+		const float4 co = __ldg(reinterpret_cast<const float4*>(&ch->childOrientation));
+		const float4 np = transformPoint(cp, posB, ornB);
+		ornB = quatMul(ornB, co);
+		posB = np;
+		shapeB = __ldg(&a.collidables[__ldg(&ch->shapeIndex)].shapeIndex);
+	}
+	else
+		shapeB = __ldg(&a.collidables[cB].shapeIndex);
+	const HullRef hB = loadHull(a.convex, shapeB);
+	const float4 c0 = transformPoint(localCenter, posA, ornA);
+	const float4 c1 = transformPoint(hB.localCenter, posB, ornB);
+	const float4 deltaC2 = sub3(c0, c1);
+
+	// ---- SAT, axes in the reference's order; "d < dmin" keeps the first strict minimum
+	const int nFB = hB.numFaces, nEB = hB.numUniqueEdges;
+	const int total = 5 + nFB + 3 * nEB;
+	float bestD = FLT_MAX;
+	float4 sep = mk4(0, 0, 0);
+	bool any = false;
+#pragma unroll 1
+	for (int k = 0; k < total; k++)
+	{
+		float4 axis;
+		if (k < 5)
+		{
+			if (k == 1) continue;  // -normal: same oriented axis and depth as face 0, never a strict minimum
+			axis = quatRotate(ornA, triN[k]);
+		}
+		else if (k < 5 + nFB)
+		{
+			const b3b200_face* f = &a.faces[hB.faceOffset + (k - 5)];
+			if (__ldg(&f->pad1) != 0) continue;  // bitwise +-duplicate of an earlier face normal
+			axis = quatRotate(ornB, __ldg(reinterpret_cast<const float4*>(&f->plane)));
+		}
+		else
+		{
+			const int e = k - 5 - nFB;
+			const int e0 = e / nEB, e1 = e - e0 * nEB;
+			const float4 edgeA = e0 == 0 ? sub3(vA[1], vA[0]) : (e0 == 1 ? sub3(vA[2], vA[1]) : sub3(vA[0], vA[2]));
+			const float4 edge0World = quatRotate(ornA, edgeA);
+			const float4 edge1World = quatRotate(ornB, __ldg(&a.uniqueEdges[hB.uniqueEdgesOffset + e1]));
+			const float4 cr = cross3(edge0World, edge1World);
+			if (almostZero(cr)) continue;
+			axis = normalized3(cr);
+		}
+		if (dot3(deltaC2, axis) < 0) axis = mk4(axis.x * -1.f, axis.y * -1.f, axis.z * -1.f);
+		float minT, maxT, minH, maxH;
+		projectTri(vA, posA, ornA, axis, minT, maxT);
+		projectHull(hB, posB, ornB, axis, a.vertices, minH, maxH);
+		if (maxT < minH || maxH < minT) return;
+		const float d0 = maxT - minH, d1 = maxH - minT;
+		const float d = d0 < d1 ? d0 : d1;
+		if (d < bestD)
+		{
+			bestD = d;
+			sep = axis;
+			any = true;
+		}
+	}
+	if (!any) return;
+	if (dot3(neg3(deltaC2), sep) > 0.0f) sep = neg3(sep);
+
+	// ---- b3FindClippingFaces: incident face of B (most aligned), reference face of the triangle prism (least aligned)
+	int closestFaceB = -1;
+	{
+		float dmax = -FLT_MAX;
+		for (int f = 0; f < nFB; f++)
+		{
+			const float4 n = __ldg(reinterpret_cast<const float4*>(&a.faces[hB.faceOffset + f].plane));
+			const float d = dot3(quatRotate(ornB, mk4(n.x, n.y, n.z)), sep);
+			if (d > dmax)
+			{
+				dmax = d;
+				closestFaceB = f;
+			}
+		}
+	}
+	if (closestFaceB < 0) return;
+	float4 bufA[CCT_POLY], bufB[CCT_POLY];
+	int numVertsIn;
+	{
+		const b3b200_face* polyB = &a.faces[hB.faceOffset + closestFaceB];
+		const int idxOff = __ldg(&polyB->indexOffset);
+		numVertsIn = __ldg(&polyB->numIndices);
+		if (numVertsIn > CCT_POLY) numVertsIn = CCT_POLY;  // (a small hull's face has at most CCT_VERTS vertices)
+		for (int e = 0; e < numVertsIn; e++) bufA[e] = transformPoint(__ldg(&a.vertices[hB.vertexOffset + __ldg(&a.indices[idxOff + e])]), posB, ornB);
+	}
+	int closestFaceA = 0;
+	float4 worldNormalA = mk4(0, 0, 0);
+	{
+		float dmin = FLT_MAX;
+#pragma unroll
+		for (int f = 0; f < 5; f++)
+		{
+			const float4 n = quatRotate(ornA, triN[f]);
+			const float d = dot3(n, sep);
+			if (d < dmin)
+			{
+				dmin = d;
+				closestFaceA = f;
+				worldNormalA = n;
+			}
+		}
+	}
+	// vertices of that face: front (0,1,2), back (2,1,0), edge plane i: (i, previous vertex)
+	const int numA = closestFaceA < 2 ? 3 : 2;
+	int ia0, ia1, ia2 = 0;
+	if (closestFaceA == 0)
+		ia0 = 0, ia1 = 1, ia2 = 2;
+	else if (closestFaceA == 1)
+		ia0 = 2, ia1 = 1, ia2 = 0;
+	else
+		ia0 = closestFaceA - 2, ia1 = (closestFaceA - 2 + 2) % 3;
+	float4 a1[3];
+	a1[0] = transformPoint(ia0 == 0 ? vA[0] : (ia0 == 1 ? vA[1] : vA[2]), posA, ornA);
+	a1[1] = transformPoint(ia1 == 0 ? vA[0] : (ia1 == 1 ? vA[1] : vA[2]), posA, ornA);
+	a1[2] = transformPoint(ia2 == 0 ? vA[0] : (ia2 == 1 ? vA[1] : vA[2]), posA, ornA);
+
+	// ---- clipFacesAndFindContactsKernel
+	float4* pIn = bufA;
+	float4* pOut = bufB;
+	for (int e0 = 0; e0 < numA; e0++)
+	{
+		const float4 aw = e0 == 0 ? a1[0] : (e0 == 1 ? a1[1] : a1[2]);
+		const int e1 = (e0 + 1) % numA;
+		const float4 bw = e1 == 0 ? a1[0] : (e1 == 1 ? a1[1] : a1[2]);
+		const float4 worldEdge0 = sub3(aw, bw);
+		const float4 planeNormalWS = neg3(cross3(worldEdge0, worldNormalA));
+		const float planeEqWS = -dot3(aw, planeNormalWS);
+		const int numOut = clipFaceGlobalSerial(pIn, numVertsIn, planeNormalWS, planeEqWS, pOut);
+		float4* t = pOut;
+		pOut = pIn;
+		pIn = t;
+		numVertsIn = numOut;
+	}
+	int numContactsOut = 0;
+	{
+		const float planeEqWS = -dot3(worldNormalA, a1[0]);
+		for (int i = 0; i < numVertsIn; i++)
+		{
+			float4 pt = pIn[i];
+			float depth = dot3(worldNormalA, pt) + planeEqWS;
+			if (depth <= -1e30f) depth = -1e30f;
+			if (depth <= 0.02f)
+			{
+				pt.w = depth;
+				pOut[numContactsOut++] = pt;
+			}
+		}
+	}
+	if (numContactsOut <= 0) return;
+	const float4* pts = pOut;
+
+	// ---- b3ExtractManifoldSequentialGlobal with nearNormal = -sep (b3NewContactReduction.h:10-91, 127)
+	int idx[4] = {0, 1, 2, 3};
+	int numPoints = numContactsOut;
+	if (numContactsOut > 4)
+	{
+		const float4 nearNormal = neg3(sep);
+		const int nPoints = numContactsOut;
+		float4 center = mk4(0, 0, 0);
+		for (int i = 0; i < nPoints; i++)
+		{
+			const float4 p = pts[i];
+			center.x += p.x;
+			center.y += p.y;
+			center.z += p.z;
+		}
+		{
+			const float sc = 1.0f / (float)nPoints;
+			center.x *= sc;
+			center.y *= sc;
+			center.z *= sc;
+		}
+		const float4 aVector = sub3(pts[0], center);
+		float4 u = cross3(nearNormal, aVector);
+		float4 v = cross3(nearNormal, u);
+		u = normalized3(u);
+		v = normalized3(v);
+		const float4 nu = neg3(u), nv = neg3(v);
+		float minW = FLT_MAX;
+		int minIndex = -1;
+		float m0 = FLT_MIN, m1 = FLT_MIN, m2 = FLT_MIN, m3 = FLT_MIN;
+		for (int ie = 0; ie < nPoints; ie++)
+		{
+			const float4 p = pts[ie];
+			if (p.w < minW)
+			{
+				minW = p.w;
+				minIndex = ie;
+			}
+			const float4 r = sub3(p, center);
+			float f = dot3(u, r);
+			if (f < m0)
+			{
+				m0 = f;
+				idx[0] = ie;
+			}
+			f = dot3(nu, r);
+			if (f < m1)
+			{
+				m1 = f;
+				idx[1] = ie;
+			}
+			f = dot3(v, r);
+			if (f < m2)
+			{
+				m2 = f;
+				idx[2] = ie;
+			}
+			f = dot3(nv, r);
+			if (f < m3)
+			{
+				m3 = f;
+				idx[3] = ie;
+			}
+		}
+		if (idx[0] != minIndex && idx[1] != minIndex && idx[2] != minIndex && idx[3] != minIndex) idx[0] = minIndex;
+		numPoints = 4;
+	}
+
+	// ---- append (b3NewContactReduction.h:129-166)
+	const unsigned int slot = atomicAdd(&a.ctr[CTR_CONTACTS], 1u);
+	if (slot >= (unsigned int)a.maxContacts) return;  // clamped afterwards, OVF_CONTACTS raised
+	b3b200_contact4* c = &a.contacts[slot];
+	float4* cw = reinterpret_cast<float4*>(c);
+	for (int i = 0; i < 4; i++) cw[i] = i < numPoints ? pts[idx[i]] : mk4(0, 0, 0, 0);
+	cw[4] = mk4(sep.x, sep.y, sep.z, (float)numPoints);
+	int4 t;
+	t.x = (int)(0u | (45874u << 16));  // restitution 0, friction (0.7f * 0xffff)
+	t.y = it.y;                         // the reference stores its concave-pair index; the triangle index is the stable equivalent
+	t.z = invMassA == 0.f ? -bodyA : bodyA;
+	t.w = invMassB == 0.f ? -bodyB : bodyB;
+	reinterpret_cast<int4*>(c)[5] = t;
+	reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);  // child indices are not recorded on this path (:143-144)
+}
+
+__global__ void __launch_bounds__(128) concaveSmallKernel(CcArgs a, const int4* __restrict__ items)
+{
+	int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
+	if (numItems > a.maxItems) numItems = a.maxItems;
+	for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < numItems; s += gridDim.x * blockDim.x) concaveSmallThread(a, items[s]);
 }
 
 __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, const int4* __restrict__ items)
@@ -613,14 +938,15 @@ __global__ void __launch_bounds__(CC_THREADS) concaveContactKernel(CcArgs a, con
 	const int warp = threadIdx.x >> 5;
 	float4* bufA = bufAll[warp][0];
 	float4* bufB = bufAll[warp][1];
-	const int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
+	int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS_BACK];  // the items with a larger hull B sit at the back end of the list
+	if (numItems > a.maxItems) numItems = a.maxItems;
 	// static striding: a dynamic cursor (as in satKernel) measured 2.7x slower here
 	const int warpsTotal = gridDim.x * CC_WARPS;
 	{
 	for (int s = blockIdx.x * CC_WARPS + warp; s < numItems; s += warpsTotal)
 	{
 		__syncwarp();
-		const int4 it = items[s];
+		const int4 it = items[a.maxItems - 1 - s];
 		const int bodyA = a.pairs[it.x].x, bodyB = a.pairs[it.x].y;
 		const int cA = a.coll[bodyA], cB = a.coll[bodyB];
 		float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
@@ -1017,6 +1343,7 @@ int launchConcave(World* w, cudaStream_t s)
 {
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_PAIRS], 0, sizeof(unsigned int), s));
 	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_SURVIVORS], 0, sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(&w->dCounters.ptr[CTR_CONCAVE_SURVIVORS_BACK], 0, sizeof(unsigned int), s));
 	CcArgs a;
 	a.pairs = w->bp.pairs.ptr;
 	a.ctr = w->dCounters.ptr;
@@ -1041,6 +1368,8 @@ int launchConcave(World* w, cudaStream_t s)
 	clampConcaveKernel<<<1, 1, 0, s>>>(w->dCounters.ptr, a.maxItems);
 	B3_LAUNCH_CHECK();
 	concaveQuickKernel<<<w->smCount * 4, 256, 0, s>>>(a, w->dConcavePairs.ptr, w->dConcaveSurvivors.ptr);
+	B3_LAUNCH_CHECK();
+	concaveSmallKernel<<<w->smCount * 8, 128, 0, s>>>(a, w->dConcaveSurvivors.ptr);
 	B3_LAUNCH_CHECK();
 	concaveContactKernel<<<w->smCount * 8, CC_THREADS, 0, s>>>(a, w->dConcaveSurvivors.ptr);
 	B3_LAUNCH_CHECK();

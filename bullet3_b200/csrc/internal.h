@@ -28,6 +28,7 @@ enum Counter
 	CTR_MESH_PAIRS = 15,  // broadphase pairs with a trimesh as A (listed by npCullKernel)
 	CTR_SMALL_ITEMS = 16,  // small x small hull items (thread-per-item kernel): box-like pairs, filled from the front of the list
 	CTR_SMALL_ITEMS_BACK = 17,  // the other small pairs, filled from the back of the same list (cleared together with 16)
+	CTR_CONCAVE_SURVIVORS_BACK = 19,  // trimesh items with a larger hull B (warp-per-item kernel), filled from the back of the survivor list
 	CTR_CLIP_FALLBACK = 18,  // overlapping items whose faces are too large for the thread-per-item clip (cleared together with 16)
 	CTR_COUNT = 24
 };

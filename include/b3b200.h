@@ -180,7 +180,7 @@ int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* nu
 int b3b200_get_counters(b3b200_world* w, int* dst8);
 /* the raw device counters of the last step (n <= 24) (diagnostics; no reference counterpart): [0..7] as above except [7] =
  * uncoloured contacts, [8] = SAT work items, [9] = overlapping items, [10] = halo records, [11] = triangle items that
- * passed the quick reject, [12..14] = work cursors, [15] = trimesh pairs, [16] = small x small hull items (box-like pairs), [17] = the other small pairs, [18] = overlapping items passed on to the warp-per-item clip */
+ * passed the quick reject, [12..14] = work cursors, [15] = trimesh pairs, [16] = small x small hull items (box-like pairs), [17] = the other small pairs, [18] = overlapping items passed on to the warp-per-item clip, [19] = triangle items with a larger hull B ([11] = those with a small hull B) */
 int b3b200_get_work_counters(b3b200_world* w, int* dst, int n);
 /* ms per stage of the last step when timing is enabled:
  * [0]=aabbs [1]=broadphase [2]=narrowphase [3]=solver setup [4]=solver iterations [5]=integrate [6]=total */

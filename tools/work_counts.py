@@ -19,4 +19,4 @@ c = w.work_counters()
 ct = w.contacts()
 mesh = int((np.abs(ct["bodyA"]) == 0).sum())
 print("pairs %d | compound raw child pairs %d | small items %d | SAT items %d -> overlapping %d -> contacts (non-mesh) %d | triangle raw items %d -> after quick reject %d -> mesh contacts %d" % (
-    c[0], c[5], c[16] + c[17], c[8], c[9], len(ct) - mesh, c[6], c[11], mesh))
+    c[0], c[5], c[16] + c[17], c[8], c[9], len(ct) - mesh, c[6], c[11] + c[19], mesh))
