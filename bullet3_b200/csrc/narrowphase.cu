@@ -750,12 +750,6 @@ B3_D void clipWarp(const NpArgs& a, int pairIndex, int bodyA, int bodyB, int sha
 constexpr int SMALL_VERTS = 8, SMALL_FACES = 6, SMALL_EDGES = 6;
 constexpr int SMALL_POLY = 16;  // a face of <= 8 vertices clipped by <= 8 planes
 
-B3_D bool isSmallHull(const NpArgs& a, int shape)
-{
-	const HullRef h = loadHull(a.convex, shape);
-	return h.numVertices <= SMALL_VERTS && h.numFaces <= SMALL_FACES && h.numUniqueEdges <= SMALL_EDGES;
-}
-
 // b3ClipFace (shared/b3ContactConvexConvexSAT.h:20-68)
 B3_D int clipFaceSerial(const float4* in, int numIn, const float4& n, float eq, float4* out)
 {
@@ -1075,12 +1069,6 @@ B3_D bool quickTest(const NpArgs& a, const Side& A, const Side& B)
 		if (!testSepAxis(hA, hB, A.pos, A.orn, B.pos, B.orn, axis, a.vertices, d)) return false;
 	}
 	return true;
-}
-
-B3_D void pushItem(const NpArgs& a, int4* __restrict__ items, int p, int ca, int cb)
-{
-	const unsigned int slot = atomicAdd(&a.ctr[CTR_SURVIVORS], 1u);
-	if (slot < (unsigned int)a.maxWorkItems) items[slot] = make_int4(p, ca, cb, 0);
 }
 
 // warp-aggregated append of the kept items: small x small hull pairs go to the thread-per-item list, the rest to the

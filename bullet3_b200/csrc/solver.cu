@@ -679,7 +679,7 @@ B3_D void loadRow(const IterArgs& s, const b3b200_constraint4* __restrict__ cs, 
 	r.ib2 = __ldg(IB + 2);
 }
 
-// solveContact<false> (b3Solver.cpp:187-266) on preloaded row data; same operation order as solveNormalRows
+// solveContact<false> (b3Solver.cpp:187-266) on preloaded row data; explicit FMAs (see fdot3)
 B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
 {
 	const int aIdx = r.aIdx, bIdx = r.bIdx;
@@ -929,9 +929,7 @@ B3_D unsigned int ldRelaxed(const unsigned int* p)
 	asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
 }
-B3_D void fenceAcqRel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 B3_D void stRelaxed(unsigned int* p, unsigned int v) { asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-B3_D void stRelease(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 B3_D void rankAndDegree(const unsigned long long* __restrict__ mask, int body, int colour, bool& dyn, unsigned int& rank, unsigned int& deg)
 {
