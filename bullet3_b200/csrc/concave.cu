@@ -494,7 +494,7 @@ B3_D void sphereTriangleThread(const CcArgs& a, const int4& it, int meshBody, in
 // stage 1b: exact quick reject, one THREAD per (pair, triangle, child) item.  Tests three members of the reference's
 // own axis list with its own arithmetic -- the triangle normal, the edge plane of the triangle that faces B most, and
 // the face of B that faces the triangle most -- so an item dropped here is one the full SAT would drop too.
-__global__ void __launch_bounds__(256) concaveQuickKernel(CcArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items)
+__global__ void __launch_bounds__(256, 4) concaveQuickKernel(CcArgs a, const int4* __restrict__ rawItems, int4* __restrict__ items)
 {
 	int numRaw = (int)a.ctr[CTR_CONCAVE_PAIRS];
 	if (numRaw > a.maxItems) numRaw = a.maxItems;
@@ -924,7 +924,7 @@ B3_D void concaveSmallThread(const CcArgs& a, const int4 it)
 	reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);  // child indices are not recorded on this path (:143-144)
 }
 
-__global__ void __launch_bounds__(128) concaveSmallKernel(CcArgs a, const int4* __restrict__ items)
+__global__ void __launch_bounds__(128, 6) concaveSmallKernel(CcArgs a, const int4* __restrict__ items)
 {
 	int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
 	if (numItems > a.maxItems) numItems = a.maxItems;

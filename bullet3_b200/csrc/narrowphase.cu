@@ -1009,7 +1009,7 @@ B3_D void smallPairThread(const NpArgs& a, const int4 it)
 
 // The list is filled from both ends: pairs of box-like hulls (<= 3 edge directions each: 6 + 6 + 9 axes) from the front, the
 // other small pairs (up to 44 axes) from the back, so that the lanes of a warp run loops of similar length.
-__global__ void __launch_bounds__(128) smallPairKernel(NpArgs a, const int4* __restrict__ smallItems)
+__global__ void __launch_bounds__(128, 6) smallPairKernel(NpArgs a, const int4* __restrict__ smallItems)
 {
 	int nFront = (int)a.ctr[CTR_SMALL_ITEMS], nBack = (int)a.ctr[CTR_SMALL_ITEMS_BACK];
 	if (nFront > a.maxWorkItems) nFront = a.maxWorkItems;
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 	}
 }
 
-__global__ void __launch_bounds__(CULL_THREADS) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems, int* __restrict__ meshPairs,
+__global__ void __launch_bounds__(CULL_THREADS, 4) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems, int* __restrict__ meshPairs,
 															 int maxMeshPairs, int4* __restrict__ smallItems)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
