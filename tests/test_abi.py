@@ -91,3 +91,46 @@ def test_capacity_errors_return_minus_one():
         w.register_instance(1.0, (0, 4, 0), scenes.IDENT, col)
     assert "exceeding" in str(e.value)
     w.close()
+
+
+def test_settings_and_state_errors_without_a_device(tmp_path):
+    """argument checking of the newer entry points on a host-only world: settings reject bad modes, everything that needs
+    device state reports a state error instead of touching a device (there is no CPU fallback)"""
+    from bullet3_b200 import scenes
+
+    L = capi.lib()
+    w = capi.World(capi.default_config(64), device=-1)
+    col = w.register_convex_points(scenes.box_points(0.5))
+    w.register_instance(1.0, (0, 1, 0), scenes.IDENT, col)
+    w.register_instance(1.0, (0, 3, 0), scenes.IDENT, col)
+    # settings: valid modes accepted, others refused
+    for mode, ok in ((0, True), (1, True), (2, False), (-1, False)):
+        assert (L.b3b200_set_colouring(w.h, mode) == 0) == ok
+    for mode, ok in ((-1, True), (0, True), (1, True), (2, False), (-2, False)):
+        assert (L.b3b200_set_ray_accel(w.h, mode) == 0) == ok
+    # joints live on the host until the first solve: creation / removal / query work without a device
+    uid = w.create_p2p_constraint(0, 1, (0, 1, 0), (0, -1, 0))
+    assert uid == 0 and w.num_constraints == 1
+    assert len(w.joints()) == 1 and w.joints()["rbB"][0] == 1
+    w.remove_constraint(uid)
+    assert w.num_constraints == 0
+    with pytest.raises(capi.B3Error):
+        w.create_p2p_constraint(0, 9, (0, 0, 0), (0, 0, 0))  # no such body
+    # device work is refused
+    with pytest.raises(capi.B3Error):
+        w.cast_rays(np.zeros((1, 3)), np.ones((1, 3)))
+    with pytest.raises(capi.B3Error):
+        w.checkpoint_save(tmp_path / "x.b3cp")
+    with pytest.raises(capi.B3Error):
+        w.checkpoint_load(tmp_path / "x.b3cp")
+    with pytest.raises(capi.B3Error):
+        w.solve_joints()
+    assert L.b3b200_copy_transforms(w.h, None, 0) != 0
+    assert L.b3b200_solve_contacts_device(w.h, 1, None, None, 0, None, -1) != 0
+    ids = np.zeros(2, np.int32)
+    assert L.b3b200_halo_set_ids(w.h, capi.ptr(ids), 2) != 0
+    assert L.b3b200_halo_adopt(w.h, None, 0, None) != 0
+    # null handles never crash
+    assert L.b3b200_set_colouring(None, 0) != 0 and L.b3b200_cast_rays(None, None, 0, None) != 0
+    assert L.b3b200_checkpoint_save(None, b"x") != 0 and L.b3b200_register_concave_obj(None, b"x", None, None) == -1
+    w.close()
