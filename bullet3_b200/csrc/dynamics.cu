@@ -149,6 +149,7 @@ int launchPackSoA(World* w)
 	packSoAKernel<<<divUp(n, DYN_THREADS), DYN_THREADS, 0, w->stream>>>(w->dBodiesAoS.ptr, n, w->dPose.ptr, w->dVel.ptr, w->dCollidableIdx.ptr);
 	B3_LAUNCH_CHECK();
 	w->soaDirty = false;
+	w->partValid = false;  // poses (and inverse masses) were replaced: the solver re-partitions the bodies
 	return 0;
 }
 

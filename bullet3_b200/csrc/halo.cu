@@ -218,6 +218,7 @@ extern "C" int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int co
 	}
 	w->aabbsValid = false;
 	w->soaDirty = true;
+	w->partValid = false;
 	return 0;
 }
 
@@ -270,6 +271,7 @@ extern "C" int b3b200_halo_emigrate(b3b200_world* w, int axis, float lo, float h
 	{
 		w->aabbsValid = false;
 		w->soaDirty = true;
+		w->partValid = false;
 	}
 	if ((int)n > capacity)
 	{
@@ -294,5 +296,6 @@ extern "C" int b3b200_halo_adopt(b3b200_world* w, const void* srcDevice, int cou
 	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));  // `slots` is the caller's host memory
 	w->aabbsValid = false;
 	w->soaDirty = true;
+	w->partValid = false;
 	return 0;
 }

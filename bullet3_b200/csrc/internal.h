@@ -97,8 +97,7 @@ struct World
 	float angularDamping = 0.99f;          // b3GpuRigidBodyPipeline.cpp:469
 	int solverKind = B3B200_SOLVER_PGS;
 	int solverIterations = 4;  // b3GpuPgsContactSolver.cpp:1049
-	int solverColouring = 1;  // batch assignment: 0 = Jones-Plassmann rounds (reproducible), 1 = single-pass first fit with atomics (solver.cu)
-	bool solverDataflow = false;  // true = barrier-free per-body dataflow kernel (solver.cu, experimental); false = grid-barrier kernel
+	int solverColouring = 1;  // batch assignment: 0 = priority rounds (reproducible for a given contact array), 1 = single-pass first fit with atomics (solver.cu)
 	float clipMinDist = -1e30f, clipMaxDist = 0.02f;  // satClipHullContacts.cl:916-917
 	int static0Index = -1;     // b3GpuNarrowPhase.cpp:861-864
 
@@ -175,15 +174,23 @@ struct World
 	DevBuf<int4> dOverlapPairs;  // work items with a penetrating SAT result
 	DevBuf<float4> dOverlapSep;  // their minimum-penetration axes
 
-	// solver
-	DevBuf<b3b200_constraint4> dConstraints;
-	DevBuf<unsigned long long> dBodyMask;  // colours used per body (2 words / body)
-	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body
-	DevBuf<int> dContactColour;           // colour per contact, -1 = none yet
-	DevBuf<unsigned int> dColourList;     // 2 x maxContacts: compacted uncoloured contacts (ping-pong)
-	DevBuf<unsigned int> dBatchCount;     // per colour (B3_MAX_BATCHES+1)
-	DevBuf<unsigned int> dBatchOffset;    // exclusive scan
-	DevBuf<unsigned int> dBatchCursor;
+	// solver (solver.cu): Morton-order partition of the dynamic bodies into blocks, per-step contact classification and
+	// colouring, rows as 32-row structure-of-arrays tiles
+	DevBuf<b3b200_constraint4> dConstraints;  // b3ContactConstraint4 rows in contact order (Jacobi solver only, allocated on first use)
+	DevBuf<int> dBodyLoc;                  // per body: (block << 12) | slot, -1 = static
+	DevBuf<unsigned int> dPartKeys, dPartVals, dPartBounds;  // Morton keys | bodies in Morton order | {min[3], max[3], numDynamic}
+	RadixSortTemp partSortTmp;
+	int partS = 0, partBlocksMax = 0, partAge = 0, partInterval = 8, partBodies = -1;
+	bool partValid = false;
+	DevBuf<unsigned long long> dBodyMask;  // colours of a body's cross contacts (2 words / body)
+	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body (reproducible colouring; 2 words / body)
+	DevBuf<int> dContactBlock, dContactColour;
+	DevBuf<unsigned int> dContactSlots, dBlockList, dCrossList;
+	DevBuf<unsigned int> dSolverScratch, dBlockStart, dBlockTileBase, dBlockTileOff, dCrossTileOff;
+	DevBuf<int> dBlockStatics;
+	DevBuf<float4> dTilesN, dTilesF;
+	unsigned int* solverMisc = nullptr;    // -> misc words of dSolverScratch once a setup has run
+	bool solverAttrSet = false;
 	DevBuf<unsigned int> dGridBarrier;    // software grid barrier state
 	// joints
 	DevBuf<b3b200_generic_constraint> dJoints;
@@ -203,7 +210,6 @@ struct World
 	DevBuf<unsigned int> dContactSlot;  // 2 per contact
 
 	int smCount = 148;
-	int coopBlocksPerSm = 1;
 
 	// timing
 	bool timing = false;
@@ -237,6 +243,7 @@ int launchSolveJoints(World* w);  // joints.cu
 int launchSolverSetup(World* w);
 int launchSolverIterate(World* w);
 int launchJacobi(World* w);
+int exportConstraints(World* w, std::vector<b3b200_constraint4>& out, std::vector<int>& batchOffsets);  // solver.cu
 
 }  // namespace b3b200
 

@@ -337,6 +337,8 @@ int launchJacobi(World* w)
 	const size_t splitCap = 2 * (size_t)std::max(w->cfg.maxContactCapacity, 1);
 	// Jacobi-only buffers are allocated on first use (0.27 GB at the default 16 contacts/body capacity)
 	B3_TRY(w->dBodyOffset.reserve(nb));
+	B3_TRY(w->dConstraints.reserve((size_t)std::max(w->cfg.maxContactCapacity, 1)));
+	s.constraints = w->dConstraints.ptr;
 	B3_TRY(w->dContactSlot.reserve(splitCap));
 	B3_TRY(w->dDeltaLin.reserve(splitCap));
 	B3_TRY(w->dDeltaAng.reserve(splitCap));

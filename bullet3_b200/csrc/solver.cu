@@ -1,77 +1,85 @@
-// solver.cu -- batched PGS contact solver.
+// solver.cu -- two-level batched PGS contact solver.
 //
-// Replaces b3GpuPgsContactSolver::solveContacts (b3GpuPgsContactSolver.cpp:568-1103):
-// 6 radix sorts + a serial per-cell batching thread (batchingKernelsNew.cl:144-231)
-// + contact->constraint + 2*I*8 launches of 32 work-groups, with host
-// synchronisation after every phase.  Here:
+// Replaces b3GpuPgsContactSolver::solveContacts (b3GpuPgsContactSolver.cpp:568-1103): 6 radix sorts, contacts binned
+// into 8 x 4 x 8 wrapped spatial cells, a serial batching thread per cell (batchingKernelsNew.cl:144-231), contact ->
+// constraint, then 2 * I * 8 launches in which one work-group walks the batches of one cell between local barriers
+// (solveContact.cl:397-482) with the body velocities in global memory.
 //
-//  setup    ONE persistent cooperative kernel:
-//           (1) graph colouring of the contact graph by priority rounds
-//               (Jones-Plassmann): every contact has a 64-bit priority that is a
-//               hash of (bodyA, bodyB, childA, childB); per round each uncoloured
-//               contact posts its priority on its dynamic bodies with atomicMax,
-//               and the contact that is top on both of its bodies takes the
-//               lowest colour not yet used on either body (two 64-bit colour
-//               masks per body = 128 colours = B3_MAX_NUM_BATCHES, b3Solver.h:39).
-//               The result equals a sequential first-fit colouring in
-//               descending priority order, i.e. it is deterministic whatever
-//               order the narrowphase appended the contacts in, and the CPU
-//               oracle reproduces it exactly ("same batching").
-//           (2) colour histogram -> batch offsets,
-//           (3) contact -> constraint rows (setConstraint4,
-//               b3ConvertConstraint4.h:62-148) written straight into batch order.
-//  iterate  ONE persistent cooperative kernel: for every iteration, every batch
-//           in order (grid barrier in between), all normal rows; then the same
-//           for friction -- the order of the reference's global-batch mode
-//           (gUseLargeBatches, solveContactConstraintBatchSizes,
-//           b3GpuPgsContactSolver.cpp:262-311) and of its host twin
-//           (solveContact<false>/solveFriction, b3Solver.cpp:187-329).
-//           Velocities live in the 32-byte-per-body SoA array (8 MB at 256k
-//           bodies: L2-resident across all 2*I*batches phases).
+// Same two-level idea, rebuilt around what a B200 SM can hold:
+//
+//  partition  (every few steps) the dynamic bodies are sorted along a Morton curve and cut into BLOCKS of S <= 2176
+//             bodies -- one block per CTA of the persistent iteration kernel, whose 96 bytes of solver state per body
+//             (velocities, position + inverse mass, world inverse inertia) live in that CTA's shared memory for the
+//             whole solve.
+//  setup      every contact is INTERIOR to a block (both dynamic bodies in it, or one dynamic + one static body) or
+//             CROSS (two blocks).  Interior contacts are coloured per block inside shared memory, cross contacts
+//             globally with one 128-bit colour mask per body; rows (setConstraint4, b3ConvertConstraint4.h:62-148)
+//             are written as 32-row structure-of-arrays tiles in solve order, so a warp streams a tile with 512-byte
+//             coalesced loads: 128 B per row and pass in the normal phase, 80 B in the friction phase, against 2 x 192 B
+//             for the 176-byte b3ContactConstraint4 rows.
+//  iterate    ONE persistent cooperative kernel.  Per iteration: the cross colours (global velocities through L2, a
+//             grid barrier per colour -- 5-10 of them), then every CTA runs all the colours of its block between
+//             __syncthreads() with the velocities in shared memory.  The batch index a contact reports (b3Contact4::
+//             m_batchIdx) is its position in that order: cross colour k -> k, interior colour m -> Kc + m (interior
+//             colours of different blocks share no dynamic body, so together they form one valid batch); solving
+//             the batches one after the other on the CPU gives the same Gauss-Seidel order ("same batching").
+//             Order of the phases = the reference's: all iterations of the normal rows, then all iterations of the
+//             friction rows (solveContact<false> / solveFriction, b3Solver.cpp:187-329).
 #include "internal.h"
 
 namespace b3b200
 {
-constexpr int SOLVER_THREADS = 512;
-constexpr int ITER_THREADS = 512;
-constexpr int TAIL_ROWS = ITER_THREADS;  // batches up to one row per thread are cheaper to solve in one CTA (measured 1.7 us
-                                           // per phase) than to pay a grid barrier for (3.5 us); two rows per thread cost 5.5 us
-constexpr int MAX_ROUNDS = 1024;
-constexpr int TAIL_COLOUR = 2048;  // colouring rounds with at most this many contacts left run in CTA 0 alone
+constexpr int ITER_THREADS = 256;
+constexpr int ITER_WARPS = ITER_THREADS / 32;
+constexpr int SETUP_THREADS = 512;
+constexpr int S_MAX = 2176;       // dynamic bodies per block: (S_MAX + NSTATIC) * 96 B = 215 KB of shared memory
+constexpr int S_MIN = 1024;       // below this a block is not worth a grid barrier
+constexpr int NSTATIC = 64;       // static bodies a block can keep in its own slots (more -> those contacts go the global way)
+constexpr int MAX_BLOCKS = 8192;  // block-start table of the scatter kernel lives in shared memory
+constexpr int JP_CONTACT_CAP = 16384;  // reproducible colouring keeps 5 B of state per interior contact in shared memory
+constexpr int NT_STRIDE = 8 * 32;  // float4 per normal tile: n|ids, 4 x (point | jacCoeffInv), b[4], lambda[4], {bodyA, bodyB, batch, contact}
+constexpr int FT_STRIDE = 2 * 32;  // float4 per friction tile: centre, {fJacCoeffInv[2], fLambda[2]}
+constexpr int TAIL_TILES = ITER_WARPS;  // cross colours this small are solved by CTA 0 alone (cheaper than a grid barrier)
+constexpr unsigned int INVALID_IDS = 0xffffffffu;
+
+// scratch layout (unsigned ints, zeroed before the setup kernels): [blockCount | blockCursor | crossHist | crossCursor | misc]
+enum
+{
+	MISC_CROSS_COUNT = 0,  // length of the cross list
+	MISC_TILE_CURSOR = 1,  // interior tiles handed out so far
+	MISC_MAX_KI = 2,       // largest number of interior colours of any block
+	MISC_KC = 3,           // number of cross colours
+	MISC_NUM = 16
+};
 
 // ---------------------------------------------------------------- grid barrier
-// One monotonically increasing arrival counter (zeroed by the host before the launch).
-// Thread 0 of every CTA arrives with a gpu-scope RELEASE add and spins with gpu-scope
-// ACQUIRE loads until all CTAs of this generation have arrived; bar.sync on either side
-// extends the ordering to the rest of the CTA (PTX memory model: causality order through
-// the CTA barrier, release/acquire are cumulative).  All CTAs are co-resident
-// (cooperative launch).
-// MEASURED CAVEAT: the acquire by thread 0 does not stop the OTHER threads' plain loads from hitting
-// stale lines in the SM's L1 (body colour masks read with ld.global gave invalid colourings in ~30 %
-// of the runs once the rounds became short).  Every value another CTA may have written during this
-// kernel is therefore read with ld.global.cg (__ldcg), volatile or an atomic -- never a plain load.
+// One monotonically increasing arrival counter (zeroed by the host before the launch).  Thread 0 of every CTA arrives
+// with a gpu-scope RELEASE add and spins with relaxed loads until all CTAs of this generation have arrived, then
+// fences; bar.sync on either side extends the ordering to the rest of the CTA.  All CTAs are co-resident (cooperative
+// launch).  MEASURED CAVEAT: the fence by thread 0 does not stop the OTHER threads' plain loads from hitting stale lines
+// in the SM's L1, so every value another CTA may have written during the kernel is read with ld.global.cg (__ldcg),
+// volatile or an atomic -- never a plain load.
 struct GridBarrier
 {
 	unsigned int* counter;
 	unsigned int numBlocks;
 	unsigned int target;
+	unsigned int seen;
 	B3_D void init(unsigned int* c, unsigned int nb)
 	{
 		counter = c;
 		numBlocks = nb;
 		target = 0;
+		seen = 0;
 	}
 	// split form: arrive() publishes this CTA's writes and signals, wait() blocks until every CTA has arrived;
 	// independent loads may be issued in between
-	unsigned int seen;
 	B3_D void arrive()
 	{
 		target += numBlocks;
 		__syncthreads();
 		if (threadIdx.x == 0)
 		{
-			// fire and forget: nobody needs the old value, and waiting for it would put one more L2 round trip in front of
-			// the first poll
 			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
 			seen = target - 1u;
 		}
@@ -80,8 +88,7 @@ struct GridBarrier
 	{
 		if (threadIdx.x == 0)
 		{
-			// poll with relaxed loads and acquire ONCE at the end: an acquire load compiles to LD + CCTL.IVALL, i.e. every
-			// poll would throw away the SM's whole L1
+			// poll with relaxed loads and fence ONCE at the end: an acquire load compiles to LD + CCTL.IVALL per poll
 			unsigned int v = seen;
 			while ((int)(v - target) < 0)
 			{
@@ -93,28 +100,13 @@ struct GridBarrier
 	}
 	B3_D void sync()
 	{
-		target += numBlocks;
-		__syncthreads();
-		if (threadIdx.x == 0)
-		{
-			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-			unsigned int v = target - 1u;
-			while ((int)(v - target) < 0)
-			{
-				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-			}
-			asm volatile("fence.acq_rel.gpu;" ::: "memory");
-		}
-		__syncthreads();
+		arrive();
+		wait();
 	}
 };
 
-B3_HD unsigned int hashContact(int a, int b, int ca, int cb)
+B3_HD unsigned int hashU32(unsigned int h)
 {
-	unsigned int h = (unsigned int)a * 0x9E3779B1u;
-	h ^= (unsigned int)b * 0x85EBCA77u + 0x165667B1u + (h << 6) + (h >> 2);
-	h ^= (unsigned int)ca * 0xC2B2AE3Du + (h << 6) + (h >> 2);
-	h ^= (unsigned int)cb * 0x27D4EB2Fu + (h << 6) + (h >> 2);
 	h ^= h >> 16;
 	h *= 0x85EBCA6Bu;
 	h ^= h >> 13;
@@ -123,34 +115,192 @@ B3_HD unsigned int hashContact(int a, int b, int ca, int cb)
 	return h;
 }
 
+// counters[key] += 1 for every lane with key >= 0, one atomic per distinct key in the warp.  Returns the lane's own slot.
+// Whole warp calls.
+B3_D unsigned int warpCountByKey(unsigned int* counters, int key, int lane)
+{
+	const unsigned int peers = __match_any_sync(0xffffffffu, key);
+	unsigned int base = 0;
+	const int leader = __ffs(peers) - 1;
+	if (key >= 0 && lane == leader) base = atomicAdd(&counters[key], (unsigned int)__popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	return base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+}
+
+// ================================================================ partition
+// float -> unsigned int whose order is the float order
+B3_D unsigned int orderedBits(float f)
+{
+	const unsigned int u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+B3_D float fromOrderedBits(unsigned int u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+__global__ void __launch_bounds__(256) partBoundsKernel(const float4* __restrict__ pose, int n, unsigned int* __restrict__ bounds)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float4 p = mk4(0, 0, 0, 0);
+	if (i < n) p = pose[2 * i];
+	const bool dyn = i < n && p.w != 0.f && isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+	unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+	if (dyn)
+	{
+		lo[0] = hi[0] = orderedBits(p.x);
+		lo[1] = hi[1] = orderedBits(p.y);
+		lo[2] = hi[2] = orderedBits(p.z);
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+		hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+	}
+	const unsigned int m = __ballot_sync(0xffffffffu, dyn);
+	if ((threadIdx.x & 31) == 0 && m)
+	{
+#pragma unroll
+		for (int k = 0; k < 3; k++)
+		{
+			atomicMin(&bounds[k], lo[k]);
+			atomicMax(&bounds[3 + k], hi[k]);
+		}
+		atomicAdd(&bounds[6], (unsigned int)__popc(m));
+	}
+}
+
+B3_D unsigned int spread10(unsigned int v)
+{
+	v &= 1023u;
+	v = (v | (v << 16)) & 0x030000FFu;
+	v = (v | (v << 8)) & 0x0300F00Fu;
+	v = (v | (v << 4)) & 0x030C30C3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+__global__ void __launch_bounds__(256) partKeysKernel(const float4* __restrict__ pose, int n, const unsigned int* __restrict__ bounds,
+													  unsigned int* __restrict__ keys, unsigned int* __restrict__ vals)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4 p = pose[2 * i];
+	unsigned int key = 0xffffffffu;  // static bodies sort last
+	if (p.w != 0.f)
+	{
+		key = 0x3fffffffu;  // a dynamic body at a non-finite position still gets a block
+		if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z))
+		{
+			const float mnx = fromOrderedBits(bounds[0]), mny = fromOrderedBits(bounds[1]), mnz = fromOrderedBits(bounds[2]);
+			const float ex = fromOrderedBits(bounds[3]) - mnx, ey = fromOrderedBits(bounds[4]) - mny, ez = fromOrderedBits(bounds[5]) - mnz;
+			// cubic cells: the same scale on the three axes, so that a key range is a compact region whatever the aspect of the scene
+			const float ext = fmaxf(fmaxf(ex, ey), fmaxf(ez, 1e-6f));
+			const float sc = 1023.f / ext;
+			const unsigned int qx = (unsigned int)fminf(fmaxf((p.x - mnx) * sc, 0.f), 1023.f);
+			const unsigned int qy = (unsigned int)fminf(fmaxf((p.y - mny) * sc, 0.f), 1023.f);
+			const unsigned int qz = (unsigned int)fminf(fmaxf((p.z - mnz) * sc, 0.f), 1023.f);
+			key = spread10(qx) | (spread10(qz) << 1) | (spread10(qy) << 2);
+		}
+	}
+	keys[i] = key;
+	vals[i] = (unsigned int)i;
+}
+
+// rank r in Morton order -> block r / S, slot r % S; statics (key 0xffffffff) -> -1
+__global__ void __launch_bounds__(256) partAssignKernel(const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals, int n, int S,
+														int* __restrict__ bodyLoc)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	const unsigned int body = vals[r];
+	bodyLoc[body] = keys[r] == 0xffffffffu ? -1 : (((r / S) << 12) | (r % S));
+}
+
+static int blockSizeFor(const World* w)
+{
+	const int n = std::max(w->numBodies, 1);
+	if (n <= S_MAX) return S_MAX;  // one block: the whole solve runs in one CTA without any grid barrier
+	int S = divUp(n, w->smCount);
+	S = std::max(S, S_MIN);
+	S = std::min(S, S_MAX);
+	return S;
+}
+
+static int ensurePartition(World* w)
+{
+	const int n = w->numBodies;
+	if (w->partValid && w->partAge < w->partInterval && w->partBodies == n)
+	{
+		w->partAge++;
+		return 0;
+	}
+	cudaStream_t s = w->stream;
+	w->partS = blockSizeFor(w);
+	w->partBlocksMax = std::max(divUp(std::max(n, 1), w->partS), 1);
+	if (w->partBlocksMax > MAX_BLOCKS)
+	{
+		setLastError("solver: %d bodies need more than %d blocks", n, MAX_BLOCKS);
+		return B3B200_ERR_INVALID;
+	}
+	const size_t nb = (size_t)std::max(n, 1);
+	B3_TRY(w->dBodyLoc.reserve(nb));
+	B3_TRY(w->dPartKeys.reserve(nb));
+	B3_TRY(w->dPartVals.reserve(nb));
+	B3_TRY(w->dPartBounds.reserve(8));
+	static const unsigned int init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
+	B3_CUDA_CHECK(cudaMemcpyAsync(w->dPartBounds.ptr, init, sizeof(init), cudaMemcpyHostToDevice, s));
+	if (n > 0)
+	{
+		partBoundsKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr);
+		B3_LAUNCH_CHECK();
+		partKeysKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr, w->dPartKeys.ptr, w->dPartVals.ptr);
+		B3_LAUNCH_CHECK();
+		B3_TRY(radixSortKV32(s, w->partSortTmp, w->dPartKeys.ptr, w->dPartVals.ptr, n, 32));
+		partAssignKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPartKeys.ptr, w->dPartVals.ptr, n, w->partS, w->dBodyLoc.ptr);
+		B3_LAUNCH_CHECK();
+	}
+	w->partValid = true;
+	w->partAge = 1;
+	w->partBodies = n;
+	return 0;
+}
+
+// ================================================================ setup
 struct SetupArgs
 {
 	b3b200_contact4* contacts;
 	unsigned int* ctr;
 	const float4* pose;
-	const float4* vel;
 	const b3b200_inertia* inertias;
-	b3b200_constraint4* constraints;
-	unsigned long long* bodyMask;  // 2 per body
-	unsigned long long* bodyPrio;  // 1 per body
-	int* contactColour;
-	unsigned int* batchCount;   // MAX_BATCHES
-	unsigned int* batchOffset;  // MAX_BATCHES + 1
-	unsigned int* batchCursor;  // MAX_BATCHES
-	unsigned int* remaining;    // MAX_ROUNDS
-	unsigned int* colourList;   // 2 x colourListStride: uncoloured contacts of the current / next round
-	int colourListStride;
-	unsigned int* bar;
+	const int* bodyLoc;
+	unsigned long long* bodyMask;  // 2 per body: colours of the body's CROSS contacts
+	unsigned long long* bodyPrio;  // 1 per body (reproducible cross colouring)
+	int* contactBlock;             // owner block, -1 = cross
+	unsigned int* contactSlots;    // slotA | slotB << 16 of an interior contact
+	int* contactColour;            // colour inside its class (cross colour / interior colour of its block), -2 = left out
+	unsigned int* blockCount;      // scratch, see the enum above
+	unsigned int* blockCursor;
+	unsigned int* crossHist;
+	unsigned int* crossCursor;
+	unsigned int* misc;
+	int* blockStatics;             // NSTATIC per block, -1 = free
+	unsigned int* blockStart;      // numBlocksMax + 1
+	unsigned int* blockList;       // interior contacts grouped by block
+	unsigned int* crossList;
+	unsigned int* blockTileBase;   // per block
+	unsigned int* blockTileOff;    // (MAX_BATCHES + 1) per block: first tile of every interior colour, relative to the base
+	unsigned int* crossTileOff;    // MAX_BATCHES + 1: first tile of every cross colour, relative to crossTileBase
+	float4* tilesN;
+	float4* tilesF;
+	unsigned int tileCap;          // tiles in the buffers; interior tiles grow from 0, cross tiles sit at the top
 	int numBodies;
+	int numBlocksMax;
+	int S;
 	int staticIdx;
-	int colouring;  // 0 = Jones-Plassmann rounds (reproducible for a given contact array), 1 = single-pass first fit with atomics
+	int colouring;  // 0 = reproducible (priority rounds), 1 = single pass first fit with atomics
 	float dt, positionDrift, positionConstraintCoeff;
 };
 
-B3_D float4 matRowMul(const float4& r0, const float4& r1, const float4& r2, const float4& v)
-{
-	return mk4(dot3(r0, v), dot3(r1, v), dot3(r2, v));
-}
+B3_D float4 matRowMul(const float4& r0, const float4& r1, const float4& r2, const float4& v) { return mk4(dot3(r0, v), dot3(r1, v), dot3(r2, v)); }
 
 // calcJacCoeff (b3ConvertConstraint4.h:50-60)
 B3_D float calcJacCoeff(const float4& angular0, const float4& angular1, float invMass0, const float4* I0, float invMass1, const float4* I1)
@@ -160,11 +310,6 @@ B3_D float calcJacCoeff(const float4& angular0, const float4& angular1, float in
 	float jmj2 = invMass1;
 	float jmj3 = dot3(matRowMul(I1[0], I1[1], I1[2], angular1), angular1);
 	return -1.f / (jmj0 + jmj1 + jmj2 + jmj3);
-}
-B3_D float calcRelVel(const float4& l0, const float4& l1, const float4& a0, const float4& a1, const float4& linVel0, const float4& angVel0,
-					  const float4& linVel1, const float4& angVel1)
-{
-	return dot3(l0, linVel0) + dot3(a0, angVel0) + dot3(l1, linVel1) + dot3(a1, angVel1);
 }
 // b3PlaneSpace1 (b3ConvertConstraint4.h:5-34)
 B3_D void planeSpace1(const float4& n, float4& p, float4& q)
@@ -185,17 +330,18 @@ B3_D void planeSpace1(const float4& n, float4& p, float4& q)
 	}
 }
 
-// setConstraint4 (b3ConvertConstraint4.h:62-148)
-B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict__ src, int colour, b3b200_constraint4* __restrict__ dst)
+// setConstraint4 (b3ConvertConstraint4.h:62-148) -> one row of a normal tile + one row of a friction tile.
+// `idsWord` goes into the w of the first field (slot pair of an interior row; unused by cross rows), `batch` is the global
+// batch index.  b = e * relVelN + ... with e = 0 in the reference: the velocities are not needed here.
+B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, float4* __restrict__ tn, float4* __restrict__ tf)
 {
+	const b3b200_contact4* src = &s.contacts[c];
 	const float4* cw = reinterpret_cast<const float4*>(src);
 	float4 wp[4] = {cw[0], cw[1], cw[2], cw[3]};
 	const float4 nrm = cw[4];
 	const int4 ids = reinterpret_cast<const int4*>(src)[5];
 	const int aIdx = abs(ids.z), bIdx = abs(ids.w);
 	const float4 posA = s.pose[2 * aIdx], posB = s.pose[2 * bIdx];
-	const float4 linVelA = s.vel[2 * aIdx], angVelA = s.vel[2 * aIdx + 1];
-	const float4 linVelB = s.vel[2 * bIdx], angVelB = s.vel[2 * bIdx + 1];
 	const float invMassA = posA.w, invMassB = posB.w;
 	// quirk kept from the reference: rows are built with the LOCAL initial inverse inertia
 	// (solverSetup.cl:254,260 / b3Solver.cpp:911,917), solved with the world one.
@@ -208,7 +354,6 @@ B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict_
 	const float npoints = nrm.w;
 	float jac[4], bb[4];
 	const float4 n = mk4(nrm.x, nrm.y, nrm.z);
-	const float4 nn = neg3(n);
 #pragma unroll
 	for (int ic = 0; ic < 4; ic++)
 	{
@@ -223,9 +368,7 @@ B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict_
 		float4 angular0 = cross3(r0, n);
 		float4 angular1 = neg3(cross3(r1, n));
 		jac[ic] = calcJacCoeff(angular0, angular1, invMassA, ia, invMassB, ib);
-		float relVelN = calcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB);
-		float e = 0.f;
-		float b = e * relVelN;
+		float b = 0.f;  // e * relVelN, e = 0
 		b += (wp[ic].w + s.positionDrift) * s.positionConstraintCoeff * dtInv;
 		bb[ic] = b;
 	}
@@ -255,368 +398,622 @@ B3_D void buildConstraint(const SetupArgs& s, const b3b200_contact4* __restrict_
 			fjac[1] = calcJacCoeff(a0, a1, invMassA, ia, invMassB, ib);
 		}
 	}
-	float4* dw = reinterpret_cast<float4*>(dst);
-	dw[0] = mk4(nrm.x, nrm.y, nrm.z, 0.7f);
+	tn[0] = mk4(nrm.x, nrm.y, nrm.z, __uint_as_float(idsWord));
 #pragma unroll
-	for (int i = 0; i < 4; i++) dw[1 + i] = ((float)i < npoints) ? wp[i] : mk4(0, 0, 0, 0);
-	dw[5] = center;
-	dw[6] = mk4(jac[0], jac[1], jac[2], jac[3]);
-	dw[7] = mk4(bb[0], bb[1], bb[2], bb[3]);
-	dw[8] = mk4(0, 0, 0, 0);              // appliedRambdaDt
-	dw[9] = mk4(fjac[0], fjac[1], 0, 0);  // fJacCoeffInv, fAppliedRambdaDt
+	for (int i = 0; i < 4; i++) tn[(1 + i) * 32] = ((float)i < npoints) ? mk4(wp[i].x, wp[i].y, wp[i].z, jac[i]) : mk4(0, 0, 0, 0);
+	tn[5 * 32] = mk4(bb[0], bb[1], bb[2], bb[3]);
+	tn[6 * 32] = mk4(0, 0, 0, 0);  // appliedRambdaDt
 	int4 tail;
 	tail.x = aIdx;
 	tail.y = bIdx;
-	tail.z = colour;
-	tail.w = 0;
-	reinterpret_cast<int4*>(dst)[10] = tail;
+	tail.z = batch;
+	tail.w = c;
+	reinterpret_cast<int4*>(tn)[7 * 32] = tail;
+	tf[0] = center;
+	tf[32] = mk4(fjac[0], fjac[1], 0, 0);  // fJacCoeffInv, fAppliedRambdaDt
 }
 
-// One colouring round, step 1: an uncoloured contact posts its priority on its dynamic bodies.
-B3_D void colourClaim(const SetupArgs& s, int c)
+B3_D void buildPadding(float4* __restrict__ tn, float4* __restrict__ tf)
+{
+	tn[0] = mk4(0, 0, 0, __uint_as_float(INVALID_IDS));
+#pragma unroll
+	for (int i = 1; i < 7; i++) tn[i * 32] = mk4(0, 0, 0, 0);
+	int4 tail;
+	tail.x = -1;
+	tail.y = -1;
+	tail.z = -1;
+	tail.w = -1;
+	reinterpret_cast<int4*>(tn)[7 * 32] = tail;
+	tf[0] = mk4(0, 0, 0, 0);
+	tf[32] = mk4(0, 0, 0, 0);
+}
+
+B3_D void contactBodies(const SetupArgs& s, int c, int& a, int& b, bool& aStatic, bool& bStatic, int& la, int& lb)
 {
 	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
-	const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
-	const int a = abs(ids.z), b = abs(ids.w);
-	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
-	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
-	const unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
-	if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
-	if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
+	a = abs(ids.z);
+	b = abs(ids.w);
+	la = s.bodyLoc[a];
+	lb = s.bodyLoc[b];
+	aStatic = ids.z < 0 || ids.z == s.staticIdx || la < 0;
+	bStatic = ids.w < 0 || ids.w == s.staticIdx || lb < 0;
 }
 
-// Step 2: the contact that is top on both of its bodies takes the lowest colour free on both.  Returns the colour, -1 when
-// the contact stays uncoloured for the next round, -2 when it cannot be coloured at all (the caller counts the colours,
-// warp-aggregated).
-B3_D int colourTry(const SetupArgs& s, int c)
+// ---- K1: classify every contact (interior to which block / cross), count per block, clear the cross masks
+__global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs s)
 {
-	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
-	const int4 ch = reinterpret_cast<const int4*>(&s.contacts[c])[6];
-	const int a = abs(ids.z), b = abs(ids.w);
-	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
-	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
-	const unsigned long long prio = ((unsigned long long)hashContact(a, b, ch.x, ch.y) << 32) | (unsigned long long)(c + 1);
-	volatile unsigned long long* vp = s.bodyPrio;
-	const bool top = (aStatic || vp[a] == prio) && (bStatic || vp[b] == prio);
-	if (!top) return -1;
-	// (masks written by other CTAs in earlier rounds: read through L2)
-	unsigned long long m0 = 0ull, m1 = 0ull;
-	if (!aStatic)
-	{
-		m0 |= __ldcg(&s.bodyMask[2 * a]);
-		m1 |= __ldcg(&s.bodyMask[2 * a + 1]);
-	}
-	if (!bStatic)
-	{
-		m0 |= __ldcg(&s.bodyMask[2 * b]);
-		m1 |= __ldcg(&s.bodyMask[2 * b + 1]);
-	}
-	int colour = -2;
-	if (~m0)
-		colour = __ffsll((long long)~m0) - 1;
-	else if (~m1)
-		colour = 64 + __ffsll((long long)~m1) - 1;
-	if (colour < 0)
-	{
-		// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
-		// ("batchIdx>=B3_MAX_NUM_BATCHES", b3GpuPgsContactSolver.cpp:1497-1502); here the
-		// contact is left out of this step's solve and the overflow flag is raised.
-		s.contactColour[c] = -2;
-		s.contacts[c].batchIdx = -2;
-		if (!aStatic) s.bodyPrio[a] = 0ull;
-		if (!bStatic) s.bodyPrio[b] = 0ull;
-		atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-		return -2;
-	}
-	const unsigned long long bit = 1ull << (colour & 63);
-	const int word = colour >> 6;
-	if (!aStatic)
-	{
-		__stcg(&s.bodyMask[2 * a + word], __ldcg(&s.bodyMask[2 * a + word]) | bit);
-		s.bodyPrio[a] = 0ull;
-	}
-	if (!bStatic)
-	{
-		__stcg(&s.bodyMask[2 * b + word], __ldcg(&s.bodyMask[2 * b + word]) | bit);
-		s.bodyPrio[b] = 0ull;
-	}
-	s.contactColour[c] = colour;
-	s.contacts[c].batchIdx = colour;
-	return colour;
-}
-
-// Single-pass colouring: every contact takes the lowest colour that is free on both of its dynamic bodies by setting the
-// colour's bit in the bodies' masks with atomicOr -- whoever flips a bit from 0 to 1 owns that (body, colour) -- and
-// retries with fresh masks when it loses a race.  The bodies are taken in index order, so two contacts can never hold
-// one bit each and wait for the other's (no livelock); a contact that loses on its second body gives the first bit back.
-// No rounds and no grid barrier: a body's contacts resolve their races in a few L2 round trips.  The colours depend on
-// the order in which the races resolve, i.e. they are not reproducible from run to run (the Jones-Plassmann path is).
-B3_D int colourFirstFit(const SetupArgs& s, int c)
-{
-	const int4 ids = reinterpret_cast<const int4*>(&s.contacts[c])[5];
-	const int a = abs(ids.z), b = abs(ids.w);
-	const bool aStatic = ids.z < 0 || ids.z == s.staticIdx;
-	const bool bStatic = ids.w < 0 || ids.w == s.staticIdx;
-	int body[2];
-	int nb = 0;
-	if (!aStatic) body[nb++] = a;
-	if (!bStatic) body[nb++] = b;
-	if (nb == 2 && body[0] > body[1])
-	{
-		const int t = body[0];
-		body[0] = body[1];
-		body[1] = t;
-	}
-	int colour = 0;
-	for (;;)
-	{
-		unsigned long long m0 = 0ull, m1 = 0ull;
-		for (int k = 0; k < nb; k++)
-		{
-			m0 |= __ldcg(&s.bodyMask[2 * body[k]]);
-			m1 |= __ldcg(&s.bodyMask[2 * body[k] + 1]);
-		}
-		colour = -2;
-		if (~m0)
-			colour = __ffsll((long long)~m0) - 1;
-		else if (~m1)
-			colour = 64 + __ffsll((long long)~m1) - 1;
-		if (colour < 0)
-		{
-			// more than B3_MAX_NUM_BATCHES colours at one body (see colourTry)
-			s.contactColour[c] = -2;
-			s.contacts[c].batchIdx = -2;
-		s.contacts[c].batchIdx = -2;
-			atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-			return -2;
-		}
-		const unsigned long long bit = 1ull << (colour & 63);
-		const int word = colour >> 6;
-		int got = 0;
-		for (; got < nb; got++)
-			if (atomicOr(&s.bodyMask[2 * body[got] + word], bit) & bit) break;
-		if (got == nb) break;
-		for (int k = 0; k < got; k++) atomicAnd(&s.bodyMask[2 * body[k] + word], ~bit);
-	}
-	s.contactColour[c] = colour;
-	s.contacts[c].batchIdx = colour;
-	return colour;  // the caller counts it (warp-aggregated)
-}
-
-// counters[key] += 1 for every lane with key >= 0, one atomic per distinct key in the warp (a few hundred thousand contacts
-// share ~20 colours: one atomic each would serialise on ~20 addresses).  Returns the lane's own slot.  Whole warp calls.
-B3_D unsigned int warpCountByKey(unsigned int* counters, int key, int lane)
-{
-	const unsigned int peers = __match_any_sync(0xffffffffu, key);
-	unsigned int base = 0;
-	const int leader = __ffs(peers) - 1;
-	if (key >= 0 && lane == leader) base = atomicAdd(&counters[key], (unsigned int)__popc(peers));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	return base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
-}
-
-#ifdef B3_SETUP_TIMING
-#define B3_PROBE(tag) do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); printf("setup %s %llu round %d\n", tag, t, round); } } while (0)
-#else
-#define B3_PROBE(tag)
-#endif
-__global__ void __launch_bounds__(SOLVER_THREADS) solverSetupKernel(SetupArgs s)
-{
-	GridBarrier bar;
-	bar.init(s.bar, gridDim.x);
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
+	const int lane = threadIdx.x & 31;
 	const int nContacts = (int)s.ctr[CTR_CONTACTS];
-	int round = 0;
-	B3_PROBE("start");
-
-	// ---- phase 0: clear
 	for (int i = tid; i < s.numBodies; i += stride)
 	{
 		s.bodyMask[2 * i] = 0ull;
 		s.bodyMask[2 * i + 1] = 0ull;
 		s.bodyPrio[i] = 0ull;
 	}
-	for (int i = tid; i < nContacts; i += stride) s.contactColour[i] = -1;
-	for (int i = tid; i < MAX_BATCHES; i += stride)
-	{
-		s.batchCount[i] = 0;
-		s.batchCursor[i] = 0;
-	}
-	for (int i = tid; i < MAX_ROUNDS; i += stride) s.remaining[i] = 0;
-	bar.sync();
-
-	B3_PROBE("cleared");
-	// ---- phase 1: colouring rounds
-	// Round 0 walks all contacts; every later round walks the compacted list of the contacts the previous round left
-	// uncoloured (ping-pong halves of colourList; remaining[round] is both the list length and the stop criterion).
-	// Once the list is short (<= TAIL_COLOUR) CTA 0 finishes the remaining rounds alone between __syncthreads():
-	// two grid barriers per round cost more than such a round.
-	int count = nContacts;
-	const unsigned int* cur = nullptr;
-	const int lane = threadIdx.x & 31;
-	__shared__ unsigned int sNext;
-	if (s.colouring == 1)
-	{
-		for (int base = tid - lane; base < nContacts; base += stride)
-		{
-			const int c = base + lane;
-			const int colour = c < nContacts ? colourFirstFit(s, c) : -1;
-			__syncwarp();
-			warpCountByKey(s.batchCount, colour, lane);
-		}
-		bar.sync();
-		count = 0;
-	}
-	for (; count > 0 && round < MAX_ROUNDS; round++)
-	{
-		for (int i = tid; i < count; i += stride) colourClaim(s, cur ? (int)__ldcg(&cur[i]) : i);
-		bar.sync();
-		unsigned int* nxt = s.colourList + (size_t)(round & 1) * (size_t)s.colourListStride;
-		for (int base = tid - lane; base < count; base += stride)
-		{
-			const int i = base + lane;
-			const int c = i < count ? (cur ? (int)__ldcg(&cur[i]) : i) : 0;
-			const int got = i < count ? colourTry(s, c) : -2;
-			const bool left = got == -1;
-			__syncwarp();
-			warpCountByKey(s.batchCount, got, lane);
-			// the still uncoloured contacts of this warp go to the next round's list
-			const unsigned int m = __ballot_sync(0xffffffffu, left);
-			if (m)
-			{
-				unsigned int slot = 0;
-				if (lane == 0) slot = atomicAdd(&s.remaining[round], (unsigned int)__popc(m));
-				slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
-				if (left) nxt[slot] = (unsigned int)c;
-			}
-		}
-		bar.sync();
-		volatile unsigned int* vr = s.remaining;
-		count = (int)vr[round];
-		cur = nxt;
-		if (count == 0) break;
-		if (count <= TAIL_COLOUR)
-		{
-			if (blockIdx.x == 0)
-			{
-				while (count > 0 && round + 1 < MAX_ROUNDS)
-				{
-					round++;
-					for (int i = threadIdx.x; i < count; i += blockDim.x) colourClaim(s, (int)__ldcg(&cur[i]));
-					if (threadIdx.x == 0) sNext = 0;
-					__syncthreads();
-					nxt = s.colourList + (size_t)(round & 1) * (size_t)s.colourListStride;
-					for (int base = (int)threadIdx.x - lane; base < count; base += blockDim.x)
-					{
-						const int i = base + lane;
-						const int c = i < count ? (int)__ldcg(&cur[i]) : 0;
-						const int got = i < count ? colourTry(s, c) : -2;
-						const bool left = got == -1;
-						__syncwarp();
-						warpCountByKey(s.batchCount, got, lane);
-						const unsigned int m = __ballot_sync(0xffffffffu, left);
-						if (m)
-						{
-							unsigned int slot = 0;
-							if (lane == 0) slot = atomicAdd(&sNext, (unsigned int)__popc(m));
-							slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
-							if (left) nxt[slot] = (unsigned int)c;
-						}
-					}
-					__syncthreads();
-					count = (int)sNext;
-					cur = nxt;
-					__syncthreads();
-				}
-			}
-			bar.sync();
-			break;
-		}
-	}
-
-	B3_PROBE("coloured");
-	// ---- phase 2: batch offsets (one warp)
-	if (blockIdx.x == 0 && threadIdx.x < 32)
-	{
-		unsigned int run = 0;
-		int numBatches = 0;
-		for (int base = 0; base < MAX_BATCHES; base += 32)
-		{
-			// every batch is padded to a multiple of 32 slots, so that a warp-row of the iteration
-			// kernels never straddles two batches (padding slots are marked invalid below)
-			const unsigned int raw = __ldcg(&s.batchCount[base + threadIdx.x]);  // cross-CTA data after a grid barrier: always through L2
-			unsigned int v = (raw + 31u) & ~31u;
-			unsigned int incl = v;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1)
-			{
-				unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-				if ((int)threadIdx.x >= o) incl += t;
-			}
-			s.batchOffset[base + threadIdx.x] = run + incl - v;
-			unsigned int nz = __ballot_sync(0xffffffffu, raw != 0);
-			if (nz) numBatches = base + 32 - __clz(nz);
-			run += __shfl_sync(0xffffffffu, incl, 31);
-		}
-		if (threadIdx.x == 0)
-		{
-			s.batchOffset[MAX_BATCHES] = run;
-			s.ctr[CTR_BATCHES] = (unsigned int)numBatches;
-			s.ctr[CTR_COLOUR_ROUNDS] = (unsigned int)(round + 1);
-		}
-	}
-	bar.sync();
-
-	B3_PROBE("offsets");
-	// ---- phase 3: contact -> constraint rows, written in batch order
-	for (int k = tid; k < MAX_BATCHES * 32; k += stride)
-	{
-		const int bch = k >> 5;
-		const unsigned int slot = __ldcg(&s.batchOffset[bch]) + __ldcg(&s.batchCount[bch]) + (unsigned int)(k & 31);
-		if (slot < __ldcg(&s.batchOffset[bch + 1]))
-		{
-			float4* dw = reinterpret_cast<float4*>(&s.constraints[slot]);
-			dw[6] = mk4(0, 0, 0, 0);
-			dw[9] = mk4(0, 0, 0, 0);
-			int4 tail;
-			tail.x = -1;  // bodyA = 0xffffffff marks a padding slot
-			tail.y = -1;
-			tail.z = -1;
-			tail.w = 0;
-			reinterpret_cast<int4*>(dw)[10] = tail;
-		}
-	}
 	for (int base = tid - lane; base < nContacts; base += stride)
 	{
 		const int c = base + lane;
-		const int colour = c < nContacts ? __ldcg(&s.contactColour[c]) : -1;
-		const unsigned int rank = warpCountByKey(s.batchCursor, colour, lane);
-		if (colour < 0) continue;
-		buildConstraint(s, &s.contacts[c], colour, &s.constraints[__ldcg(&s.batchOffset[colour]) + rank]);
+		int owner = -1;
+		if (c < nContacts)
+		{
+			int a, b, la, lb;
+			bool aStatic, bStatic;
+			contactBodies(s, c, a, b, aStatic, bStatic, la, lb);
+			if (aStatic != bStatic)
+				owner = (aStatic ? lb : la) >> 12;
+			else if (!aStatic && (la >> 12) == (lb >> 12))
+				owner = la >> 12;
+			s.contactBlock[c] = owner;
+		}
+		warpCountByKey(s.blockCount, owner, lane);
 	}
-	B3_PROBE("built(block0 thread0 only)");
 }
 
-// ---------------------------------------------------------------- iterations
+// lowest colour not in (m0, m1), -2 when all 128 are taken
+B3_D int lowestFree(unsigned long long m0, unsigned long long m1)
+{
+	if (~m0) return __ffsll((long long)~m0) - 1;
+	if (~m1) return 64 + __ffsll((long long)~m1) - 1;
+	return -2;
+}
+
+// Single-pass colouring: the contact takes the lowest colour free on its dynamic bodies by setting the colour's bit in
+// the bodies' masks with atomicOr -- whoever flips a bit from 0 to 1 owns that (body, colour) -- and retries with fresh
+// masks when it loses a race.  The bodies are taken in index order, so two contacts can never hold one bit each and wait
+// for the other's; a contact that loses on its second body gives the first bit back.  The colours depend on how the races
+// resolve (not reproducible from run to run).  MASKS: global (cross contacts) or shared (interior contacts of a block).
+template <typename LoadMask>
+B3_D int colourFirstFit(unsigned long long* masks, int i0, int i1, int nb, LoadMask ld)
+{
+	if (nb == 2 && i0 > i1)
+	{
+		const int t = i0;
+		i0 = i1;
+		i1 = t;
+	}
+	for (;;)
+	{
+		unsigned long long m0 = 0ull, m1 = 0ull;
+		if (nb > 0)
+		{
+			m0 |= ld(&masks[2 * i0]);
+			m1 |= ld(&masks[2 * i0 + 1]);
+		}
+		if (nb > 1)
+		{
+			m0 |= ld(&masks[2 * i1]);
+			m1 |= ld(&masks[2 * i1 + 1]);
+		}
+		const int colour = lowestFree(m0, m1);
+		if (colour < 0) return -2;
+		const unsigned long long bit = 1ull << (colour & 63);
+		const int word = colour >> 6;
+		if (nb > 0 && (atomicOr(&masks[2 * i0 + word], bit) & bit)) continue;
+		if (nb > 1 && (atomicOr(&masks[2 * i1 + word], bit) & bit))
+		{
+			atomicAnd(&masks[2 * i0 + word], ~bit);
+			continue;
+		}
+		return colour;
+	}
+}
+
+// ---- K2: interior contacts -> their block's list (+ slot pair); cross contacts -> cross list (+ first-fit colour)
+__global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s)
+{
+	extern __shared__ unsigned int sStart[];  // numBlocksMax + 1
+	__shared__ unsigned int sWarp[SETUP_THREADS / 32];
+	__shared__ unsigned int sCarry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	// exclusive scan of the block counts (every CTA computes its own copy; CTA 0 also publishes it)
+	if (threadIdx.x == 0) sCarry = 0;
+	__syncthreads();
+	for (int base = 0; base < s.numBlocksMax; base += SETUP_THREADS)
+	{
+		const int i = base + threadIdx.x;
+		const unsigned int v = i < s.numBlocksMax ? s.blockCount[i] : 0u;
+		unsigned int incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		if (lane == 31) sWarp[warp] = incl;
+		__syncthreads();
+		unsigned int before = sCarry;
+		for (int k = 0; k < warp; k++) before += sWarp[k];
+		if (i < s.numBlocksMax) sStart[i] = before + incl - v;
+		__syncthreads();
+		if (threadIdx.x == SETUP_THREADS - 1) sCarry = before + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) sStart[s.numBlocksMax] = sCarry;
+	__syncthreads();
+	if (blockIdx.x == 0)
+		for (int i = threadIdx.x; i <= s.numBlocksMax; i += SETUP_THREADS) s.blockStart[i] = sStart[i];
+
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+	const int nContacts = (int)s.ctr[CTR_CONTACTS];
+	const unsigned int contactCap = s.colouring == 0 ? (unsigned int)JP_CONTACT_CAP : 0xffffffffu;
+	for (int base = tid - lane; base < nContacts; base += stride)
+	{
+		const int c = base + lane;
+		bool cross = false;
+		int colour = -1;
+		if (c < nContacts)
+		{
+			int a, b, la, lb;
+			bool aStatic, bStatic;
+			contactBodies(s, c, a, b, aStatic, bStatic, la, lb);
+			int owner = s.contactBlock[c];
+			if (owner >= 0)
+			{
+				unsigned int sa = (unsigned int)(la & 4095), sb = (unsigned int)(lb & 4095);
+				if (aStatic != bStatic)
+				{
+					// the static body gets one of the block's own static slots (find or insert)
+					const int g = aStatic ? a : b;
+					int* table = s.blockStatics + (size_t)owner * NSTATIC;
+					int slot = -1;
+					for (int k = 0; k < NSTATIC; k++)
+					{
+						int v = *((volatile int*)&table[k]);
+						if (v == -1) v = atomicCAS(&table[k], -1, g), v = (v == -1) ? g : v;
+						if (v == g)
+						{
+							slot = k;
+							break;
+						}
+					}
+					if (slot < 0)
+						owner = -1;  // more than NSTATIC static bodies under one block: this contact goes the global way
+					else if (aStatic)
+						sa = (unsigned int)(s.S + slot);
+					else
+						sb = (unsigned int)(s.S + slot);
+				}
+				if (owner >= 0)
+				{
+					const unsigned int pos = atomicAdd(&s.blockCursor[owner], 1u);
+					if (pos >= contactCap)
+						owner = -1;
+					else
+					{
+						s.blockList[sStart[owner] + pos] = (unsigned int)c;
+						s.contactSlots[c] = sa | (sb << 16);
+					}
+				}
+				if (owner < 0) s.contactBlock[c] = -1;
+			}
+			if (owner < 0)
+			{
+				cross = true;
+				if (s.colouring == 1)
+				{
+					int i0 = 0, i1 = 0, nb = 0;
+					if (!aStatic) i0 = a, nb = 1;
+					if (!bStatic)
+					{
+						if (nb)
+							i1 = b;
+						else
+							i0 = b;
+						nb++;
+					}
+					colour = colourFirstFit(s.bodyMask, i0, i1, nb, [](const unsigned long long* p) { return __ldcg(p); });
+					s.contactColour[c] = colour;
+					if (colour < 0)
+					{
+						// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
+						// (b3GpuPgsContactSolver.cpp:1497-1502); here the contact is left out of this step's solve
+						s.contacts[c].batchIdx = -2;
+						atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+					}
+				}
+			}
+		}
+		__syncwarp();
+		warpCountByKey(s.crossHist, colour, lane);
+		const unsigned int m = __ballot_sync(0xffffffffu, cross);
+		if (m)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&s.misc[MISC_CROSS_COUNT], (unsigned int)__popc(m));
+			slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+			if (cross) s.crossList[slot] = (unsigned int)c;
+		}
+	}
+}
+
+// ---- K2b (reproducible mode only): the cross contacts are coloured by priority rounds (Jones-Plassmann) in ONE CTA:
+// per round every uncoloured contact posts its priority on its dynamic bodies, the contact that is top on all of them takes
+// the lowest colour free on them.  Equals the sequential first fit in descending priority order: a pure function of the
+// contact array.
+B3_D unsigned long long contactPrio(int c) { return ((unsigned long long)hashU32((unsigned int)c * 0x9E3779B1u + 0x7F4A7C15u) << 32) | (unsigned long long)(unsigned int)(c + 1); }
+
+__global__ void __launch_bounds__(1024) solverCrossColourKernel(SetupArgs s)
+{
+	__shared__ int sLeft;
+	const int n = (int)s.misc[MISC_CROSS_COUNT];
+	const int lane = threadIdx.x & 31;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) s.contactColour[s.crossList[i]] = -1;
+	__syncthreads();
+	for (int round = 0; round < 100000; round++)
+	{
+		if (threadIdx.x == 0) sLeft = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			const int c = (int)s.crossList[i];
+			if (s.contactColour[c] != -1) continue;  // own earlier write
+			int a, b, la, lb;
+			bool aStatic, bStatic;
+			contactBodies(s, c, a, b, aStatic, bStatic, la, lb);
+			const unsigned long long prio = contactPrio(c);
+			if (!aStatic) atomicMax(&s.bodyPrio[a], prio);
+			if (!bStatic) atomicMax(&s.bodyPrio[b], prio);
+		}
+		__syncthreads();
+		for (int base = (int)threadIdx.x - lane; base < n; base += blockDim.x)
+		{
+			const int i = base + lane;
+			int got = -1;
+			if (i < n)
+			{
+				const int c = (int)s.crossList[i];
+				if (s.contactColour[c] == -1)
+				{
+					int a, b, la, lb;
+					bool aStatic, bStatic;
+					contactBodies(s, c, a, b, aStatic, bStatic, la, lb);
+					const unsigned long long prio = contactPrio(c);
+					volatile unsigned long long* vp = s.bodyPrio;
+					if ((aStatic || vp[a] == prio) && (bStatic || vp[b] == prio))
+					{
+						unsigned long long m0 = 0ull, m1 = 0ull;
+						if (!aStatic) m0 |= __ldcg(&s.bodyMask[2 * a]), m1 |= __ldcg(&s.bodyMask[2 * a + 1]);
+						if (!bStatic) m0 |= __ldcg(&s.bodyMask[2 * b]), m1 |= __ldcg(&s.bodyMask[2 * b + 1]);
+						const int colour = lowestFree(m0, m1);
+						if (colour >= 0)
+						{
+							const unsigned long long bit = 1ull << (colour & 63);
+							const int word = colour >> 6;
+							if (!aStatic) __stcg(&s.bodyMask[2 * a + word], __ldcg(&s.bodyMask[2 * a + word]) | bit);
+							if (!bStatic) __stcg(&s.bodyMask[2 * b + word], __ldcg(&s.bodyMask[2 * b + word]) | bit);
+							got = colour;
+						}
+						else
+						{
+							s.contacts[c].batchIdx = -2;
+							atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+						}
+						s.contactColour[c] = colour;
+						if (!aStatic) vp[a] = 0ull;
+						if (!bStatic) vp[b] = 0ull;
+					}
+					else
+						sLeft = 1;
+				}
+			}
+			__syncwarp();
+			warpCountByKey(s.crossHist, got, lane);
+		}
+		__syncthreads();
+		const int left = sLeft;
+		__syncthreads();
+		if (!left) break;
+	}
+}
+
+// first tile of every colour (tiles of 32 rows) from the colour histogram; returns the number of colours in use
+B3_D int tileOffsetsFromHist(const unsigned int* hist, unsigned int* off, int lane)
+{
+	// one warp
+	unsigned int run = 0;
+	int numColours = 0;
+	for (int base = 0; base < MAX_BATCHES; base += 32)
+	{
+		const unsigned int raw = hist[base + lane];
+		const unsigned int v = (raw + 31u) >> 5;
+		unsigned int incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += t;
+		}
+		off[base + lane] = run + incl - v;
+		const unsigned int nz = __ballot_sync(0xffffffffu, raw != 0);
+		if (nz) numColours = base + 32 - __clz(nz);
+		run += __shfl_sync(0xffffffffu, incl, 31);
+	}
+	if (lane == 0) off[MAX_BATCHES] = run;
+	return numColours;
+}
+
+// ---- K3: one CTA per block: colour the block's interior contacts in shared memory, lay out its tiles, build its rows
+__global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArgs s)
+{
+	extern __shared__ unsigned long long sm64[];
+	__shared__ unsigned int sHist[MAX_BATCHES], sCursor[MAX_BATCHES], sOff[MAX_BATCHES + 1], sCrossHist[MAX_BATCHES];
+	__shared__ unsigned int sTileBase;
+	__shared__ int sKc, sKi, sLeft;
+	const int slots = s.S + NSTATIC;
+	unsigned long long* sMask = sm64;                  // 2 per slot
+	unsigned long long* sPrio = sm64 + 2 * slots;      // 1 per slot (reproducible mode)
+	unsigned int* sCSlots = reinterpret_cast<unsigned int*>(sPrio + slots);  // per contact (reproducible mode)
+	signed char* sCCol = reinterpret_cast<signed char*>(sCSlots + JP_CONTACT_CAP);
+	const int lane = threadIdx.x & 31;
+
+	// number of cross colours: interior colour m of any block is global batch Kc + m
+	if (threadIdx.x < MAX_BATCHES) sCrossHist[threadIdx.x] = s.crossHist[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x < 32)
+	{
+		int kc = 0;
+		for (int base = 0; base < MAX_BATCHES; base += 32)
+		{
+			const unsigned int nz = __ballot_sync(0xffffffffu, sCrossHist[base + lane] != 0);
+			if (nz) kc = base + 32 - __clz(nz);
+		}
+		if (lane == 0)
+		{
+			sKc = kc;
+			if (blockIdx.x == 0) s.misc[MISC_KC] = (unsigned int)kc;
+		}
+	}
+	__syncthreads();
+	const int Kc = sKc;
+
+	for (int blk = blockIdx.x; blk < s.numBlocksMax; blk += gridDim.x)
+	{
+		const unsigned int first = s.blockStart[blk];
+		unsigned int n = s.blockCursor[blk];
+		const unsigned int counted = s.blockStart[blk + 1] - first;
+		if (n > counted) n = counted;  // (cannot happen; the list segment is `counted` long)
+		if (s.colouring == 0 && n > (unsigned int)JP_CONTACT_CAP) n = JP_CONTACT_CAP;  // the scatter kernel sent the rest the global way
+		const unsigned int* list = s.blockList + first;
+		for (int i = threadIdx.x; i < 2 * slots; i += SETUP_THREADS) sMask[i] = 0ull;
+		if (threadIdx.x < MAX_BATCHES)
+		{
+			sHist[threadIdx.x] = 0;
+			sCursor[threadIdx.x] = 0;
+		}
+		__syncthreads();
+		// ---- colouring
+		if (s.colouring == 1)
+		{
+			for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
+			{
+				const int c = (int)list[i];
+				const unsigned int sl = s.contactSlots[c];
+				const int sa = (int)(sl & 0xffffu), sb = (int)(sl >> 16);
+				int i0 = 0, i1 = 0, nb = 0;
+				if (sa < s.S) i0 = sa, nb = 1;
+				if (sb < s.S)
+				{
+					if (nb)
+						i1 = sb;
+					else
+						i0 = sb;
+					nb++;
+				}
+				int colour = colourFirstFit(sMask, i0, i1, nb, [](const unsigned long long* p) { return *((volatile const unsigned long long*)p); });
+				if (colour >= 0 && Kc + colour >= MAX_BATCHES) colour = -2;  // (its mask bits stay set: harmless, the block only loses a colour)
+				s.contactColour[c] = colour;
+				if (colour >= 0) atomicAdd(&sHist[colour], 1u);
+			}
+		}
+		else
+		{
+			for (int i = threadIdx.x; i < slots; i += SETUP_THREADS) sPrio[i] = 0ull;
+			for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
+			{
+				sCSlots[i] = s.contactSlots[list[i]];
+				sCCol[i] = -1;
+			}
+			__syncthreads();
+			for (int round = 0; round < 100000; round++)
+			{
+				if (threadIdx.x == 0) sLeft = 0;
+				for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
+				{
+					if (sCCol[i] != -1) continue;
+					const unsigned int sl = sCSlots[i];
+					const int sa = (int)(sl & 0xffffu), sb = (int)(sl >> 16);
+					const unsigned long long prio = contactPrio((int)list[i]);
+					if (sa < s.S) atomicMax(&sPrio[sa], prio);
+					if (sb < s.S) atomicMax(&sPrio[sb], prio);
+				}
+				__syncthreads();
+				for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
+				{
+					if (sCCol[i] != -1) continue;
+					const unsigned int sl = sCSlots[i];
+					const int sa = (int)(sl & 0xffffu), sb = (int)(sl >> 16);
+					const unsigned long long prio = contactPrio((int)list[i]);
+					volatile unsigned long long* vp = sPrio;
+					const bool da = sa < s.S, db = sb < s.S;
+					if ((!da || vp[sa] == prio) && (!db || vp[sb] == prio))
+					{
+						unsigned long long m0 = 0ull, m1 = 0ull;
+						if (da) m0 |= sMask[2 * sa], m1 |= sMask[2 * sa + 1];
+						if (db) m0 |= sMask[2 * sb], m1 |= sMask[2 * sb + 1];
+						int colour = lowestFree(m0, m1);
+						if (colour >= 0)
+						{
+							const unsigned long long bit = 1ull << (colour & 63);
+							const int word = colour >> 6;
+							if (da) sMask[2 * sa + word] |= bit;
+							if (db) sMask[2 * sb + word] |= bit;
+							if (Kc + colour >= MAX_BATCHES) colour = -2;
+						}
+						sCCol[i] = (signed char)colour;
+						if (colour >= 0) atomicAdd(&sHist[colour], 1u);
+						if (da) vp[sa] = 0ull;
+						if (db) vp[sb] = 0ull;
+					}
+					else
+						sLeft = 1;
+				}
+				__syncthreads();
+				const int left = sLeft;
+				__syncthreads();
+				if (!left) break;
+			}
+			for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS) s.contactColour[list[i]] = (int)sCCol[i];
+		}
+		__syncthreads();
+		// ---- tile layout of the block
+		if (threadIdx.x < 32)
+		{
+			const int ki = tileOffsetsFromHist(sHist, sOff, lane);
+			__syncwarp();
+			if (lane == 0)
+			{
+				sKi = ki;
+				const unsigned int nTiles = sOff[MAX_BATCHES];
+				unsigned int base = atomicAdd(&s.misc[MISC_TILE_CURSOR], nTiles);
+				sTileBase = base;
+				s.blockTileBase[blk] = base;
+				atomicMax(&s.misc[MISC_MAX_KI], (unsigned int)ki);
+			}
+		}
+		__syncthreads();
+		for (int i = threadIdx.x; i <= MAX_BATCHES; i += SETUP_THREADS) s.blockTileOff[(size_t)blk * (MAX_BATCHES + 1) + i] = sOff[i];
+		const unsigned int tileBase = sTileBase;
+		// (capacity: interior + cross contacts <= contact capacity, and the buffers hold capacity / 32 + padding tiles)
+		// ---- rows
+		for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
+		{
+			const int c = (int)list[i];
+			const int colour = s.contactColour[c];  // this thread's own write
+			if (colour < 0)
+			{
+				s.contacts[c].batchIdx = -2;
+				atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
+				continue;
+			}
+			const unsigned int rank = atomicAdd(&sCursor[colour], 1u);
+			const unsigned int tile = tileBase + sOff[colour] + (rank >> 5);
+			const unsigned int row = rank & 31u;
+			s.contacts[c].batchIdx = Kc + colour;
+			buildRow(s, c, s.contactSlots[c], Kc + colour, s.tilesN + (size_t)tile * NT_STRIDE + row, s.tilesF + (size_t)tile * FT_STRIDE + row);
+		}
+		// padding rows of every colour's last tile
+		for (int k = threadIdx.x; k < MAX_BATCHES * 32; k += SETUP_THREADS)
+		{
+			const int colour = k >> 5;
+			const unsigned int cnt = sHist[colour];
+			const unsigned int rank = cnt + (unsigned int)(k & 31);
+			if (cnt != 0 && rank < ((cnt + 31u) & ~31u))
+			{
+				const unsigned int tile = tileBase + sOff[colour] + (rank >> 5);
+				buildPadding(s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// ---- K4: cross rows, at the top of the tile buffers in colour order
+__global__ void __launch_bounds__(SETUP_THREADS) solverCrossBuildKernel(SetupArgs s)
+{
+	__shared__ unsigned int sHist[MAX_BATCHES], sOff[MAX_BATCHES + 1];
+	const int lane = threadIdx.x & 31;
+	if (threadIdx.x < MAX_BATCHES) sHist[threadIdx.x] = s.crossHist[threadIdx.x];
+	__syncthreads();
+	if (threadIdx.x < 32)
+	{
+		const int kc = tileOffsetsFromHist(sHist, sOff, lane);
+		if (blockIdx.x == 0 && lane == 0)
+		{
+			s.ctr[CTR_BATCHES] = (unsigned int)kc + s.misc[MISC_MAX_KI];
+			s.ctr[CTR_COLOUR_ROUNDS] = (unsigned int)kc;  // diagnostics: number of cross colours = grid barriers per pass
+		}
+	}
+	__syncthreads();
+	const unsigned int crossTiles = sOff[MAX_BATCHES];
+	const unsigned int crossBase = s.tileCap - crossTiles;
+	if (blockIdx.x == 0)
+		for (int i = threadIdx.x; i <= MAX_BATCHES; i += SETUP_THREADS) s.crossTileOff[i] = sOff[i];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int stride = gridDim.x * blockDim.x;
+	const int n = (int)s.misc[MISC_CROSS_COUNT];
+	for (int base = tid - lane; base < n; base += stride)
+	{
+		const int i = base + lane;
+		const int c = i < n ? (int)s.crossList[i] : 0;
+		const int colour = i < n ? s.contactColour[c] : -1;
+		const unsigned int rank = warpCountByKey(s.crossCursor, colour, lane);
+		if (colour < 0) continue;
+		const unsigned int tile = crossBase + sOff[colour] + (rank >> 5);
+		s.contacts[c].batchIdx = colour;
+		buildRow(s, c, 0u, colour, s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
+	}
+	for (int k = tid; k < MAX_BATCHES * 32; k += stride)
+	{
+		const int colour = k >> 5;
+		const unsigned int cnt = sHist[colour];
+		const unsigned int rank = cnt + (unsigned int)(k & 31);
+		if (cnt != 0 && rank < ((cnt + 31u) & ~31u))
+		{
+			const unsigned int tile = crossBase + sOff[colour] + (rank >> 5);
+			buildPadding(s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
+		}
+	}
+}
+
+// ================================================================ iterations
 struct IterArgs
 {
-	b3b200_constraint4* constraints;
+	float4* tilesN;
+	float4* tilesF;
+	unsigned int tileCap;
 	const unsigned int* ctr;
 	const float4* pose;
 	float4* vel;
 	const b3b200_inertia* inertias;
-	const unsigned int* batchOffset;
+	const unsigned int* partVals;      // bodies in Morton order: block b, slot k = partVals[b * S + k]
+	const unsigned int* partBounds;    // [6] = number of dynamic bodies
+	const int* blockStatics;
+	const unsigned int* blockTileBase;
+	const unsigned int* blockTileOff;
+	const unsigned int* crossTileOff;
+	const unsigned int* misc;
+	const unsigned long long* bodyMask;  // != 0 -> the body has cross contacts
 	unsigned int* bar;
 	int iterations;
-	const unsigned long long* bodyMask;  // colours in use per body (from the setup kernel)
-	unsigned int* seq;                   // per-body progress counter (dataflow kernel)
+	int S;
+	int numBlocksMax;
 };
 
-// Iteration arithmetic: explicit FMAs.  This file is built with --fmad=false, so the only fused operations are the
-// ones written here and every kernel that inlines these helpers (barrier kernel, its one-CTA tail, dataflow kernel)
-// produces the same bits for the same Gauss-Seidel order.  (The oracle evaluates the reference's unfused expressions;
-// the bar for velocities is 1e-4 relative.)
+// Iteration arithmetic: explicit FMAs.  This file is built with --fmad=false, so the only fused operations are the ones
+// written here; the shared-memory path and the global path produce the same bits for the same Gauss-Seidel order.
+// (The oracle evaluates the reference's unfused expressions; the bar for velocities is 1e-4 relative.)
 B3_D float fdot3(const float4& a, const float4& b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, a.x * b.x)); }
 B3_D float4 fcross3(const float4& a, const float4& b)
 {
@@ -635,75 +1032,32 @@ B3_D float fcalcRelVel(const float4& l0, const float4& l1, const float4& a0, con
 	return fdot3(l0, linVel0) + fdot3(a0, angVel0) + fdot3(l1, linVel1) + fdot3(a1, angVel1);
 }
 
-struct RowData
+struct BodyConst
 {
-	float4 lin, wp0, wp1, wp2, wp3, center, jac, bias, applied, fr;
-	float4 posA, posB;
-	float4 ia0, ia1, ia2, ib0, ib1, ib2;
-	int aIdx, bIdx;
+	float4 pos;  // w = inverse mass
+	float4 i0, i1, i2;
 };
 
-template <int PHASE>
-B3_D void loadRow(const IterArgs& s, const b3b200_constraint4* __restrict__ cs, RowData& r)
+// solveContact<false> (b3Solver.cpp:187-266): the four points of one manifold.  p[i] = {point, jacCoeffInv}.
+B3_D void solveNormalCore(const float4& nId, const float4* p, const float4& bias, float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
+						  float4& angVelA, float4& linVelB, float4& angVelB)
 {
-	const float4* cw = reinterpret_cast<const float4*>(cs);
-	const int4 tail = reinterpret_cast<const int4*>(cs)[10];
-	r.aIdx = tail.x;
-	r.bIdx = tail.y;
-	r.lin = cw[0];
-	r.applied = cw[8];
-	if (PHASE == 0)
-	{
-		r.wp0 = cw[1];
-		r.wp1 = cw[2];
-		r.wp2 = cw[3];
-		r.wp3 = cw[4];
-		r.jac = cw[6];
-		r.bias = cw[7];
-	}
-	else
-	{
-		r.center = cw[5];
-		r.fr = cw[9];
-	}
-	if (r.aIdx < 0) return;  // padding slot
-	r.posA = s.pose[2 * r.aIdx];
-	r.posB = s.pose[2 * r.bIdx];
-	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[r.aIdx].invInertiaWorld);
-	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[r.bIdx].invInertiaWorld);
-	r.ia0 = __ldg(IA);
-	r.ia1 = __ldg(IA + 1);
-	r.ia2 = __ldg(IA + 2);
-	r.ib0 = __ldg(IB);
-	r.ib1 = __ldg(IB + 1);
-	r.ib2 = __ldg(IB + 2);
-}
-
-// solveContact<false> (b3Solver.cpp:187-266) on preloaded row data; explicit FMAs (see fdot3)
-B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
-{
-	const int aIdx = r.aIdx, bIdx = r.bIdx;
-	if (aIdx < 0) return;
-	const float invMassA = r.posA.w, invMassB = r.posB.w;
-	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
-	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
-	const float4 n = mk4(r.lin.x, r.lin.y, r.lin.z);
+	const float4 n = mk4(nId.x, nId.y, nId.z);
 	const float4 nn = neg3(n);
-	const float jacv[4] = {r.jac.x, r.jac.y, r.jac.z, r.jac.w};
-	const float bv[4] = {r.bias.x, r.bias.y, r.bias.z, r.bias.w};
-	float ap[4] = {r.applied.x, r.applied.y, r.applied.z, r.applied.w};
+	const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
+	float ap[4] = {applied.x, applied.y, applied.z, applied.w};
 #pragma unroll
 	for (int ic = 0; ic < 4; ic++)
 	{
-		if (jacv[ic] == 0.f) continue;
-		const float4 wp = ic == 0 ? r.wp0 : (ic == 1 ? r.wp1 : (ic == 2 ? r.wp2 : r.wp3));
-		float4 r0 = sub3(wp, r.posA), r1 = sub3(wp, r.posB);
-		float4 angular0 = fcross3(r0, n);
-		float4 angular1 = neg3(fcross3(r1, n));
+		const float jac = p[ic].w;
+		if (jac == 0.f) continue;
+		const float4 r0 = sub3(p[ic], A.pos), r1 = sub3(p[ic], B.pos);
+		const float4 angular0 = fcross3(r0, n);
+		const float4 angular1 = neg3(fcross3(r1, n));
 		float rambdaDt = fcalcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
-		rambdaDt *= jacv[ic];
+		rambdaDt *= jac;
 		{
-			float prevSum = ap[ic];
+			const float prevSum = ap[ic];
 			float updated = prevSum;
 			updated += rambdaDt;
 			updated = fmaxf(updated, 0.f);
@@ -711,47 +1065,33 @@ B3_D void solveNormalPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs,
 			rambdaDt = updated - prevSum;
 			ap[ic] = updated;
 		}
-		linVelA = faddScaled(linVelA, n, invMassA, rambdaDt);
-		angVelA = faddScaled1(angVelA, fmatRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
-		linVelB = faddScaled(linVelB, nn, invMassB, rambdaDt);
-		angVelB = faddScaled1(angVelB, fmatRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
+		linVelA = faddScaled(linVelA, n, A.pos.w, rambdaDt);
+		angVelA = faddScaled1(angVelA, fmatRowMul(A.i0, A.i1, A.i2, angular0), rambdaDt);
+		linVelB = faddScaled(linVelB, nn, B.pos.w, rambdaDt);
+		angVelB = faddScaled1(angVelB, fmatRowMul(B.i0, B.i1, B.i2, angular1), rambdaDt);
 	}
-	reinterpret_cast<float4*>(cs)[8] = mk4(ap[0], ap[1], ap[2], ap[3]);
-	if (invMassA != 0.f)
-	{
-		__stcg(&s.vel[2 * aIdx], linVelA);
-		__stcg(&s.vel[2 * aIdx + 1], angVelA);
-	}
-	if (invMassB != 0.f)
-	{
-		__stcg(&s.vel[2 * bIdx], linVelB);
-		__stcg(&s.vel[2 * bIdx + 1], angVelB);
-	}
+	applied = mk4(ap[0], ap[1], ap[2], ap[3]);
 }
 
-// solveFriction (b3Solver.cpp:268-329) on preloaded row data; explicit FMAs (see fdot3)
-B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ cs, const RowData& r)
+// solveFriction (b3Solver.cpp:268-329).  fr = {fJacCoeffInv[2], fAppliedRambdaDt[2]}; returns false when the row has no friction
+B3_D bool solveFrictionCore(const float4& nId, const float4& center, float4& fr, const float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
+							float4& angVelA, float4& linVelB, float4& angVelB)
 {
-	const float4 fr = r.fr;
-	if (fr.x == 0.f && fr.x == 0.f) return;
-	const int aIdx = r.aIdx, bIdx = r.bIdx;
-	const float4 posA = r.posA, posB = r.posB;
-	const float invMassA = posA.w, invMassB = posB.w;
-	float4 linVelA = __ldcg(&s.vel[2 * aIdx]), angVelA = __ldcg(&s.vel[2 * aIdx + 1]);
-	float4 linVelB = __ldcg(&s.vel[2 * bIdx]), angVelB = __ldcg(&s.vel[2 * bIdx + 1]);
+	if (fr.x == 0.f && fr.x == 0.f) return false;  // (sic, b3Solver.cpp:274)
+	const float invMassA = A.pos.w, invMassB = B.pos.w;
 	float sum = 0.f;
-	sum += r.applied.x;
-	sum += r.applied.y;
-	sum += r.applied.z;
-	sum += r.applied.w;
+	sum += applied.x;
+	sum += applied.y;
+	sum += applied.z;
+	sum += applied.w;
 	const float frictionCoeff = 0.7f;
 	const float maxR = frictionCoeff * sum;
 	const float minR = -maxR;
-	const float4 n = neg3(mk4(r.lin.x, r.lin.y, r.lin.z));
+	const float4 n = neg3(mk4(nId.x, nId.y, nId.z));
 	float4 tangent[2];
 	planeSpace1(n, tangent[0], tangent[1]);
-	const float4 r0 = sub3(r.center, posA), r1 = sub3(r.center, posB);
-	float fj[2] = {fr.x, fr.y};
+	const float4 r0 = sub3(center, A.pos), r1 = sub3(center, B.pos);
+	const float fj[2] = {fr.x, fr.y};
 	float fa[2] = {fr.z, fr.w};
 #pragma unroll
 	for (int i = 0; i < 2; i++)
@@ -762,7 +1102,7 @@ B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ c
 		float rambdaDt = fcalcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
 		rambdaDt *= fj[i];
 		{
-			float prevSum = fa[i];
+			const float prevSum = fa[i];
 			float updated = prevSum;
 			updated += rambdaDt;
 			updated = fmaxf(updated, minR);
@@ -771,325 +1111,603 @@ B3_D void solveFrictionPre(const IterArgs& s, b3b200_constraint4* __restrict__ c
 			fa[i] = updated;
 		}
 		linVelA = faddScaled(linVelA, t, invMassA, rambdaDt);
-		angVelA = faddScaled1(angVelA, fmatRowMul(r.ia0, r.ia1, r.ia2, angular0), rambdaDt);
+		angVelA = faddScaled1(angVelA, fmatRowMul(A.i0, A.i1, A.i2, angular0), rambdaDt);
 		linVelB = faddScaled(linVelB, neg3(t), invMassB, rambdaDt);
-		angVelB = faddScaled1(angVelB, fmatRowMul(r.ib0, r.ib1, r.ib2, angular1), rambdaDt);
+		angVelB = faddScaled1(angVelB, fmatRowMul(B.i0, B.i1, B.i2, angular1), rambdaDt);
 	}
 	{
 		// angular damping for point constraint (b3Solver.cpp:317-328)
-		float4 ab = normalized3(sub3(posB, posA));
-		float4 ac = normalized3(sub3(r.center, posA));
+		const float4 ab = normalized3(sub3(B.pos, A.pos));
+		const float4 ac = normalized3(sub3(center, A.pos));
 		if (fdot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
 		{
-			float angNA = fdot3(n, angVelA);
-			float angNB = fdot3(n, angVelB);
+			const float angNA = fdot3(n, angVelA);
+			const float angNB = fdot3(n, angVelB);
 			angVelA = faddScaled1(angVelA, n, -(angNA * 0.1f));
 			angVelB = faddScaled1(angVelB, n, -(angNB * 0.1f));
 		}
 	}
-	reinterpret_cast<float4*>(cs)[9] = mk4(fj[0], fj[1], fa[0], fa[1]);
-	if (invMassA != 0.f)
+	fr = mk4(fj[0], fj[1], fa[0], fa[1]);
+	return true;
+}
+
+// ---- rows as they sit in registers between the (early) load and the solve
+template <int PHASE>
+struct RowRegs
+{
+	float4 nId;
+	float4 p[PHASE == 0 ? 4 : 1];  // normal: the four points | friction: the centre
+	float4 bias;                   // normal: b[4] | friction: {fJacCoeffInv[2], fAppliedRambdaDt[2]}
+	float4 applied;
+};
+template <int PHASE>
+B3_D void loadRowRegs(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r)
+{
+	const float4* tn = s.tilesN + (size_t)tile * NT_STRIDE + lane;
+	r.nId = tn[0];
+	r.applied = tn[6 * 32];
+	if (PHASE == 0)
 	{
-		__stcg(&s.vel[2 * aIdx], linVelA);
-		__stcg(&s.vel[2 * aIdx + 1], angVelA);
+#pragma unroll
+		for (int i = 0; i < 4; i++) r.p[i] = tn[(1 + i) * 32];
+		r.bias = tn[5 * 32];
 	}
-	if (invMassB != 0.f)
+	else
 	{
-		__stcg(&s.vel[2 * bIdx], linVelB);
-		__stcg(&s.vel[2 * bIdx + 1], angVelB);
+		const float4* tf = s.tilesF + (size_t)tile * FT_STRIDE + lane;
+		r.p[0] = tf[0];
+		r.bias = tf[32];
 	}
 }
 
+// interior row: bodies are slots of the CTA's shared-memory state
 template <int PHASE>
-B3_D void iteratePhase(const IterArgs& s, GridBarrier& bar, int numBatches, int tailStart, int stride, int firstOffset)
+B3_D void solveRowShared(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r, float4* sVel, const float4* sPose, const float4* sIner)
 {
-	RowData pre;
-	bool havePre = false;
-	if (tailStart > 0)
+	const unsigned int ids = __float_as_uint(r.nId.w);
+	if (ids == INVALID_IDS) return;
+	const int sa = (int)(ids & 0xffffu), sb = (int)(ids >> 16);
+	BodyConst A, B;
+	A.pos = sPose[sa];
+	B.pos = sPose[sb];
+	A.i0 = sIner[3 * sa], A.i1 = sIner[3 * sa + 1], A.i2 = sIner[3 * sa + 2];
+	B.i0 = sIner[3 * sb], B.i1 = sIner[3 * sb + 1], B.i2 = sIner[3 * sb + 2];
+	float4 linVelA = sVel[2 * sa], angVelA = sVel[2 * sa + 1];
+	float4 linVelB = sVel[2 * sb], angVelB = sVel[2 * sb + 1];
+	if (PHASE == 0)
 	{
-		const int i0 = (int)s.batchOffset[0] + firstOffset;
-		if (i0 < (int)s.batchOffset[1])
+		solveNormalCore(r.nId, r.p, r.bias, r.applied, A, B, linVelA, angVelA, linVelB, angVelB);
+		s.tilesN[(size_t)tile * NT_STRIDE + 6 * 32 + lane] = r.applied;
+	}
+	else
+	{
+		if (!solveFrictionCore(r.nId, r.p[0], r.bias, r.applied, A, B, linVelA, angVelA, linVelB, angVelB)) return;
+		s.tilesF[(size_t)tile * FT_STRIDE + 32 + lane] = r.bias;
+	}
+	if (A.pos.w != 0.f)
+	{
+		sVel[2 * sa] = linVelA;
+		sVel[2 * sa + 1] = angVelA;
+	}
+	if (B.pos.w != 0.f)
+	{
+		sVel[2 * sb] = linVelB;
+		sVel[2 * sb + 1] = angVelB;
+	}
+}
+
+// cross row: bodies through global memory (L2)
+struct CrossPre
+{
+	int a, b;
+	BodyConst A, B;
+};
+B3_D void loadCrossPre(const IterArgs& s, unsigned int tile, int lane, CrossPre& c)
+{
+	const int4 tail = reinterpret_cast<const int4*>(s.tilesN)[(size_t)tile * NT_STRIDE + 7 * 32 + lane];
+	c.a = tail.x;
+	c.b = tail.y;
+	if (c.a < 0) return;
+	c.A.pos = s.pose[2 * c.a];
+	c.B.pos = s.pose[2 * c.b];
+	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[c.a].invInertiaWorld);
+	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[c.b].invInertiaWorld);
+	c.A.i0 = __ldg(IA), c.A.i1 = __ldg(IA + 1), c.A.i2 = __ldg(IA + 2);
+	c.B.i0 = __ldg(IB), c.B.i1 = __ldg(IB + 1), c.B.i2 = __ldg(IB + 2);
+}
+template <int PHASE>
+B3_D void solveRowGlobal(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r, const CrossPre& c)
+{
+	if (c.a < 0) return;
+	float4 linVelA = __ldcg(&s.vel[2 * c.a]), angVelA = __ldcg(&s.vel[2 * c.a + 1]);
+	float4 linVelB = __ldcg(&s.vel[2 * c.b]), angVelB = __ldcg(&s.vel[2 * c.b + 1]);
+	if (PHASE == 0)
+	{
+		solveNormalCore(r.nId, r.p, r.bias, r.applied, c.A, c.B, linVelA, angVelA, linVelB, angVelB);
+		s.tilesN[(size_t)tile * NT_STRIDE + 6 * 32 + lane] = r.applied;
+	}
+	else
+	{
+		if (!solveFrictionCore(r.nId, r.p[0], r.bias, r.applied, c.A, c.B, linVelA, angVelA, linVelB, angVelB)) return;
+		s.tilesF[(size_t)tile * FT_STRIDE + 32 + lane] = r.bias;
+	}
+	if (c.A.pos.w != 0.f)
+	{
+		__stcg(&s.vel[2 * c.a], linVelA);
+		__stcg(&s.vel[2 * c.a + 1], angVelA);
+	}
+	if (c.B.pos.w != 0.f)
+	{
+		__stcg(&s.vel[2 * c.b], linVelB);
+		__stcg(&s.vel[2 * c.b + 1], angVelB);
+	}
+}
+
+struct BlockView
+{
+	int blk;
+	int count;        // dynamic bodies in the block
+	unsigned int tileBase;
+	unsigned int numTiles;
+	int numColours;
+};
+
+// all colours of one block, velocities in shared memory.  Warp w owns the tiles w, w + 16, ... of the block's tile sequence
+// (the same warp every pass, so a tile's lambdas are read back by the thread that wrote them) and fetches its next tile
+// while it solves the current one.
+template <int PHASE>
+__device__ __noinline__ void solveBlockInterior(const IterArgs& s, const BlockView& v, const unsigned int* sTileOff, float4* sVel, const float4* sPose, const float4* sIner)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned int T = (unsigned int)warp;
+	RowRegs<PHASE> cur;
+	if (T < v.numTiles) loadRowRegs<PHASE>(s, v.tileBase + T, lane, cur);
+	for (int m = 0; m < v.numColours; m++)
+	{
+		const unsigned int end = sTileOff[m + 1];
+		while (T < end)
 		{
-			loadRow<PHASE>(s, &s.constraints[i0], pre);
+			RowRegs<PHASE> nxt;
+			const unsigned int T2 = T + ITER_WARPS;
+			if (T2 < v.numTiles) loadRowRegs<PHASE>(s, v.tileBase + T2, lane, nxt);
+			solveRowShared<PHASE>(s, v.tileBase + T, lane, cur, sVel, sPose, sIner);
+			cur = nxt;
+			T = T2;
+		}
+		__syncthreads();
+	}
+}
+
+// cross colours of one pass: global velocities, a grid barrier per colour; the next colour's rows are fetched while the
+// other CTAs arrive.  Trailing colours of at most TAIL_TILES tiles are solved by CTA 0 alone between __syncthreads().
+template <int PHASE>
+__device__ __noinline__ void solveCrossColours(const IterArgs& s, GridBarrier& bar, int Kc, int tailStart, const unsigned int* sCrossOff, unsigned int crossBase)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned int gw = (unsigned int)warp * gridDim.x + blockIdx.x;  // tiles are dealt round-robin to the CTAs
+	const unsigned int gstride = ITER_WARPS * gridDim.x;
+	RowRegs<PHASE> pre;
+	CrossPre cpre;
+	bool havePre = false;
+	if (tailStart > 0 && sCrossOff[0] + gw < sCrossOff[1])
+	{
+		loadRowRegs<PHASE>(s, crossBase + sCrossOff[0] + gw, lane, pre);
+		loadCrossPre(s, crossBase + sCrossOff[0] + gw, lane, cpre);
+		havePre = true;
+	}
+	bar.wait();  // (the caller arrived after publishing this CTA's velocities)
+	for (int k = 0; k < tailStart; k++)
+	{
+		for (unsigned int t = sCrossOff[k] + gw; t < sCrossOff[k + 1]; t += gstride)
+		{
+			if (!havePre)
+			{
+				loadRowRegs<PHASE>(s, crossBase + t, lane, pre);
+				loadCrossPre(s, crossBase + t, lane, cpre);
+			}
+			havePre = false;
+			solveRowGlobal<PHASE>(s, crossBase + t, lane, pre, cpre);
+		}
+		bar.arrive();
+		if (k + 1 < tailStart && sCrossOff[k + 1] + gw < sCrossOff[k + 2])
+		{
+			loadRowRegs<PHASE>(s, crossBase + sCrossOff[k + 1] + gw, lane, pre);
+			loadCrossPre(s, crossBase + sCrossOff[k + 1] + gw, lane, cpre);
 			havePre = true;
 		}
+		bar.wait();
 	}
-	for (int iter = 0; iter < s.iterations; iter++)
+	if (tailStart < Kc)
 	{
-		for (int b = 0; b < tailStart; b++)
+		if (blockIdx.x == 0)
 		{
-			// warp-rows are dealt round-robin to the CTAs so that a small batch still uses every SM
-			const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
-			for (int i = begin + firstOffset; i < end; i += stride)
+			for (int k = tailStart; k < Kc; k++)
 			{
-				if (!havePre) loadRow<PHASE>(s, &s.constraints[i], pre);
-				havePre = false;
-				if (PHASE == 0)
-					solveNormalPre(s, &s.constraints[i], pre);
-				else
-					solveFrictionPre(s, &s.constraints[i], pre);
-			}
-			bar.arrive();
-			// while the other CTAs arrive: fetch this thread's first row of the next grid-wide batch
-			{
-				int nb = b + 1;
-				bool more = true;
-				if (nb == tailStart)
+				const unsigned int t = sCrossOff[k] + (unsigned int)warp;
+				if (t < sCrossOff[k + 1])
 				{
-					nb = 0;
-					more = tailStart == numBatches && iter + 1 < s.iterations;  // with a tail, batch 0 is prefetched after it
+					loadRowRegs<PHASE>(s, crossBase + t, lane, pre);
+					loadCrossPre(s, crossBase + t, lane, cpre);
+					solveRowGlobal<PHASE>(s, crossBase + t, lane, pre, cpre);
 				}
-				if (more)
-				{
-					const int i2 = (int)s.batchOffset[nb] + firstOffset;
-					if (i2 < (int)s.batchOffset[nb + 1])
-					{
-						loadRow<PHASE>(s, &s.constraints[i2], pre);
-						havePre = true;
-					}
-				}
+				__syncthreads();
 			}
-			bar.wait();
 		}
-		if (tailStart < numBatches)
-		{
-			// The colouring leaves a long tail of small batches (a few hundred rows each).  A grid barrier costs more
-			// than solving one of them, so CTA 0 runs the whole tail alone, batch after batch in the same order,
-			// separated by __syncthreads(); everybody meets at ONE grid barrier afterwards.
-			if (blockIdx.x == 0)
+		bar.sync();
+	}
+}
+
+__global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs s)
+{
+	extern __shared__ float4 smem4[];
+	__shared__ unsigned int sTileOff[MAX_BATCHES + 1], sCrossOff[MAX_BATCHES + 1];
+	const int slots = s.S + NSTATIC;
+	float4* sVel = smem4;                // 2 per slot
+	float4* sPose = smem4 + 2 * slots;   // 1 per slot
+	float4* sIner = smem4 + 3 * slots;   // 3 per slot
+	GridBarrier bar;
+	bar.init(s.bar, gridDim.x);
+
+	const int numDyn = (int)s.partBounds[6];
+	const int numBlocks = (numDyn + s.S - 1) / s.S;
+	const int Kc = (int)s.misc[MISC_KC];
+	const bool resident = numBlocks <= (int)gridDim.x;
+	for (int i = threadIdx.x; i <= MAX_BATCHES; i += ITER_THREADS) sCrossOff[i] = s.crossTileOff[i];
+	__syncthreads();
+	const unsigned int crossBase = s.tileCap - sCrossOff[MAX_BATCHES];
+	int tailStart = Kc;
+	while (tailStart > 0 && sCrossOff[tailStart] - sCrossOff[tailStart - 1] <= (unsigned int)TAIL_TILES) tailStart--;
+
+	auto view = [&](int blk) {
+		BlockView v;
+		v.blk = blk;
+		v.count = min(s.S, numDyn - blk * s.S);
+		v.tileBase = s.blockTileBase[blk];
+		for (int i = threadIdx.x; i <= MAX_BATCHES; i += ITER_THREADS) sTileOff[i] = s.blockTileOff[(size_t)blk * (MAX_BATCHES + 1) + i];
+		__syncthreads();
+		v.numTiles = sTileOff[MAX_BATCHES];
+		int kc = 0;
+		// colours in use = last colour whose tile range is not empty
+		for (int m = MAX_BATCHES; m > 0; m--)
+			if (sTileOff[m] != sTileOff[m - 1])
 			{
-				for (int b = tailStart; b < numBatches; b++)
+				kc = m;
+				break;
+			}
+		v.numColours = kc;
+		return v;
+	};
+	// body of slot k of block blk (-1: none)
+	auto slotBody = [&](const BlockView& v, int k) -> int {
+		if (k < v.count) return (int)s.partVals[(size_t)v.blk * s.S + k];
+		if (k >= s.S && k < s.S + NSTATIC) return s.blockStatics[(size_t)v.blk * NSTATIC + (k - s.S)];
+		return -1;
+	};
+	auto loadBlock = [&](const BlockView& v, bool boundaryOnly) {
+		for (int k = threadIdx.x; k < slots; k += ITER_THREADS)
+		{
+			const int g = slotBody(v, k);
+			if (g < 0) continue;
+			if (boundaryOnly)
+			{
+				if (k >= s.S || (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) == 0ull) continue;
+			}
+			else
+			{
+				sPose[k] = s.pose[2 * g];
+				const float4* I = reinterpret_cast<const float4*>(&s.inertias[g].invInertiaWorld);
+				sIner[3 * k] = __ldg(I);
+				sIner[3 * k + 1] = __ldg(I + 1);
+				sIner[3 * k + 2] = __ldg(I + 2);
+			}
+			sVel[2 * k] = __ldcg(&s.vel[2 * g]);
+			sVel[2 * k + 1] = __ldcg(&s.vel[2 * g + 1]);
+		}
+	};
+	auto storeBlock = [&](const BlockView& v, bool boundaryOnly) {
+		for (int k = threadIdx.x; k < v.count; k += ITER_THREADS)
+		{
+			const int g = (int)s.partVals[(size_t)v.blk * s.S + k];
+			if (boundaryOnly && (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) == 0ull) continue;
+			if (sPose[k].w == 0.f) continue;
+			__stcg(&s.vel[2 * g], sVel[2 * k]);
+			__stcg(&s.vel[2 * g + 1], sVel[2 * k + 1]);
+		}
+	};
+
+	BlockView mine;
+	mine.blk = -1;
+	mine.count = 0;
+	mine.tileBase = 0;
+	mine.numTiles = 0;
+	mine.numColours = 0;
+	if (resident && (int)blockIdx.x < numBlocks)
+	{
+		mine = view((int)blockIdx.x);
+		loadBlock(mine, false);
+		__syncthreads();
+	}
+
+#pragma unroll 1
+	for (int phase = 0; phase < 2; phase++)
+	{
+#pragma unroll 1
+		for (int iter = 0; iter < s.iterations; iter++)
+		{
+			if (Kc > 0)
+			{
+				// the velocities the cross rows need are in global memory after this: resident blocks publish their boundary
+				// bodies (the others never left global memory)
+				if (mine.blk >= 0) storeBlock(mine, true);
+				bar.arrive();
+				if (phase == 0)
+					solveCrossColours<0>(s, bar, Kc, tailStart, sCrossOff, crossBase);
+				else
+					solveCrossColours<1>(s, bar, Kc, tailStart, sCrossOff, crossBase);
+				if (mine.blk >= 0)
 				{
-					const int begin = (int)s.batchOffset[b], end = (int)s.batchOffset[b + 1];
-					for (int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x)
-					{
-						RowData r;
-						loadRow<PHASE>(s, &s.constraints[i], r);
-						if (PHASE == 0)
-							solveNormalPre(s, &s.constraints[i], r);
-						else
-							solveFrictionPre(s, &s.constraints[i], r);
-					}
+					loadBlock(mine, true);
 					__syncthreads();
 				}
 			}
-			bar.arrive();
-			if (tailStart > 0 && iter + 1 < s.iterations)
+			if (resident)
 			{
-				const int i2 = (int)s.batchOffset[0] + firstOffset;
-				if (i2 < (int)s.batchOffset[1])
+				if (mine.blk >= 0)
 				{
-					loadRow<PHASE>(s, &s.constraints[i2], pre);
-					havePre = true;
+					if (phase == 0)
+						solveBlockInterior<0>(s, mine, sTileOff, sVel, sPose, sIner);
+					else
+						solveBlockInterior<1>(s, mine, sTileOff, sVel, sPose, sIner);
 				}
 			}
-			bar.wait();
+			else
+			{
+				for (int blk = blockIdx.x; blk < numBlocks; blk += gridDim.x)
+				{
+					__syncthreads();
+					const BlockView v = view(blk);
+					loadBlock(v, false);
+					__syncthreads();
+					if (phase == 0)
+						solveBlockInterior<0>(s, v, sTileOff, sVel, sPose, sIner);
+					else
+						solveBlockInterior<1>(s, v, sTileOff, sVel, sPose, sIner);
+					storeBlock(v, false);
+				}
+			}
 		}
 	}
-}
-
-template <int THREADS, int MIN_BLOCKS>
-B3_D void solverIterateBody(const IterArgs& s)
-{
-	GridBarrier bar;
-	bar.init(s.bar, gridDim.x);
-	const int stride = gridDim.x * blockDim.x;
-	const int numBatches = (int)s.ctr[CTR_BATCHES];
-	if (numBatches == 0) return;
-	const int firstOffset = (((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31);
-	// tail = the trailing run of batches with at most TAIL_ROWS rows each (solved by CTA 0 alone, see iteratePhase)
-	int tailStart = numBatches;
-	while (tailStart > 0 && (int)(s.batchOffset[tailStart] - s.batchOffset[tailStart - 1]) <= (int)blockDim.x) tailStart--;
-	iteratePhase<0>(s, bar, numBatches, tailStart, stride, firstOffset);
-	iteratePhase<1>(s, bar, numBatches, tailStart, stride, firstOffset);
-}
-
-__global__ void __launch_bounds__(ITER_THREADS) solverIterateKernel(IterArgs s) { solverIterateBody<ITER_THREADS, 1>(s); }
-// (measured: 2 CTAs per SM of 384 / 512 threads, i.e. 80 / 64 registers with part of the prefetched row spilled, take 2.74 /
-// 3.17 ms against 2.39 ms for this 128-register, one-CTA-per-SM version on the bench scene)
-
-// ---------------------------------------------------------------- dataflow iterations
-// Same Gauss-Seidel order as solverIterateKernel, no grid-wide barriers.  Within a body, the
-// constraints touching it are totally ordered by (round, batch); constraints that share no
-// dynamic body commute exactly.  So each constraint only has to wait for ITS two bodies:
-// every dynamic body carries a progress counter seq[b]; constraint c with colour k is the
-// rank(c,b) = popc(mask[b] & below(k))-th user of body b in every round, and may run in round r
-// when seq[b] == r * deg(b) + rank(c,b) for both bodies.  It then solves, publishes the new
-// velocities and bumps both counters (release/acquire at gpu scope).  Threads own constraints
-// i = tid, tid+T, ... of the batch-sorted array and visit them in ascending order each round,
-// which is consistent with the global (round, batch) order, so the earliest unfinished
-// constraint is always runnable: no deadlock as long as all threads are resident
-// (cooperative launch).  Ready lanes solve inside the polling loop, so lanes of one warp never
-// wait for each other at a reconvergence point.
-constexpr int DF_THREADS = 256;
-
-B3_D unsigned int ldRelaxed(const unsigned int* p)
-{
-	unsigned int v;
-	asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-B3_D void stRelaxed(unsigned int* p, unsigned int v) { asm volatile("st.relaxed.gpu.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-
-B3_D void rankAndDegree(const unsigned long long* __restrict__ mask, int body, int colour, bool& dyn, unsigned int& rank, unsigned int& deg)
-{
-	const unsigned long long m0 = __ldg(&mask[2 * body]), m1 = __ldg(&mask[2 * body + 1]);
-	const unsigned long long bit = 1ull << (colour & 63);
-	dyn = ((colour < 64 ? m0 : m1) & bit) != 0ull;
-	deg = __popcll(m0) + __popcll(m1);
-	rank = colour < 64 ? __popcll(m0 & (bit - 1ull)) : __popcll(m0) + __popcll(m1 & (bit - 1ull));
-}
-
-// One THREAD owns the slots i = tid, tid + T, ... of the batch-sorted array and walks them in ascending order every round.
-// A lane whose two bodies have reached its row's turn solves it at once, inside the polling loop; the other lanes of the
-// warp keep polling (independent thread scheduling), nobody waits at a reconvergence point.  The row, the positions and
-// the inertias are fetched when the thread moves on to the slot (only this thread ever writes the row), so when the
-// counters match only the velocities are still to be loaded.
-template <int PHASE>
-B3_D void dataflowRounds(const IterArgs& s, int tid, int T, int nSlots, int roundBegin, int roundEnd)
-{
-	int round = roundBegin, i = tid;
-	bool have = false, valid = false, dynA = false, dynB = false;
-	unsigned int expA = 0, expB = 0;
-	RowData pre;
-	while (round < roundEnd)
+	if (mine.blk >= 0)
 	{
-		if (!have)
-		{
-			loadRow<PHASE>(s, &s.constraints[i], pre);
-			valid = pre.aIdx >= 0;
-			if (valid)
-			{
-				const int colour = reinterpret_cast<const int4*>(&s.constraints[i])[10].z;
-				unsigned int rank, deg;
-				rankAndDegree(s.bodyMask, pre.aIdx, colour, dynA, rank, deg);
-				expA = (unsigned int)round * deg + rank;
-				rankAndDegree(s.bodyMask, pre.bIdx, colour, dynB, rank, deg);
-				expB = (unsigned int)round * deg + rank;
-			}
-			have = true;
-		}
-		bool ready = true;
-		if (valid)
-		{
-			if (dynA) ready = ldRelaxed(&s.seq[pre.aIdx]) == expA;
-			if (ready && dynB) ready = ldRelaxed(&s.seq[pre.bIdx]) == expB;
-		}
-		if (ready)
-		{
-			if (valid)
-			{
-				// No acquire fence here: it would invalidate the whole L1 (CCTL.IVALL) once per row.  Everything another
-				// thread writes (velocities, counters) is read with strong gpu-scope loads served by L2, and those loads
-				// are only issued once the branch on the counter values has resolved.
-				if (PHASE == 0)
-					solveNormalPre(s, &s.constraints[i], pre);
-				else
-					solveFrictionPre(s, &s.constraints[i], pre);
-				if (dynA || dynB) __threadfence();  // the velocity stores are performed before either counter moves
-				if (dynA) stRelaxed(&s.seq[pre.aIdx], expA + 1u);
-				if (dynB) stRelaxed(&s.seq[pre.bIdx], expB + 1u);
-			}
-			have = false;
-			i += T;
-			if (i >= nSlots)
-			{
-				i = tid;
-				round++;
-			}
-		}
+		__syncthreads();
+		storeBlock(mine, false);
 	}
 }
 
-__global__ void __launch_bounds__(DF_THREADS) solverIterateDataflowKernel(IterArgs s)
+// ================================================================ export (b3b200_get_constraints)
+// tiles -> b3ContactConstraint4 records (reference layout), compacted with one atomic cursor; the host sorts them by batch
+__global__ void __launch_bounds__(256) solverExportKernel(const float4* __restrict__ tilesN, const float4* __restrict__ tilesF, unsigned int tileCap,
+														  const unsigned int* __restrict__ misc, const unsigned int* __restrict__ crossTileOff,
+														  b3b200_constraint4* __restrict__ out, unsigned int* __restrict__ cursor, unsigned int capacity)
 {
-	const int T = gridDim.x * blockDim.x;
-	// consecutive lanes own consecutive slots; warps are dealt round-robin to the CTAs like in the barrier kernel
-	const int tid = (((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) << 5) + (threadIdx.x & 31);
-	const int nSlots = (int)s.batchOffset[MAX_BATCHES];  // batches are padded to multiples of 32
-	if (tid >= nSlots) return;
-	dataflowRounds<0>(s, tid, T, nSlots, 0, s.iterations);
-	dataflowRounds<1>(s, tid, T, nSlots, s.iterations, 2 * s.iterations);
-}
-
-static int coopLaunch(World* w, const void* fn, void* argStruct, int threads = SOLVER_THREADS)
-{
-	int perSm = 0;
-	B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, threads, 0));
-	if (perSm < 1)
+	const unsigned int interiorTiles = misc[MISC_TILE_CURSOR];
+	const unsigned int crossTiles = crossTileOff[MAX_BATCHES];
+	const unsigned int total = interiorTiles + crossTiles;
+	const int lane = threadIdx.x & 31;
+	for (unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += gridDim.x * (blockDim.x >> 5))
 	{
-		setLastError("solver kernel does not fit on an SM");
-		return B3B200_ERR_CUDA;
+		const unsigned int tile = t < interiorTiles ? t : tileCap - crossTiles + (t - interiorTiles);
+		const float4* tn = tilesN + (size_t)tile * NT_STRIDE + lane;
+		const float4* tf = tilesF + (size_t)tile * FT_STRIDE + lane;
+		const int4 tail = reinterpret_cast<const int4*>(tn)[7 * 32];
+		const bool valid = tail.x >= 0;
+		const unsigned int m = __ballot_sync(0xffffffffu, valid);
+		if (!m) continue;
+		unsigned int slot = 0;
+		if (lane == 0) slot = atomicAdd(cursor, (unsigned int)__popc(m));
+		slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+		if (!valid || slot >= capacity) continue;
+		float4* dw = reinterpret_cast<float4*>(&out[slot]);
+		const float4 nId = tn[0];
+		dw[0] = mk4(nId.x, nId.y, nId.z, 0.7f);
+		float jac[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++)
+		{
+			const float4 p = tn[(1 + i) * 32];
+			jac[i] = p.w;
+			dw[1 + i] = mk4(p.x, p.y, p.z, 0.f);
+		}
+		dw[5] = tf[0];
+		dw[6] = mk4(jac[0], jac[1], jac[2], jac[3]);
+		dw[7] = tn[5 * 32];
+		dw[8] = tn[6 * 32];
+		dw[9] = tf[32];
+		int4 o;
+		o.x = tail.x;
+		o.y = tail.y;
+		o.z = tail.z;
+		o.w = 0;
+		reinterpret_cast<int4*>(dw)[10] = o;
 	}
-	if (perSm > 2) perSm = 2;
-	dim3 grid(w->smCount * perSm), block(threads);
-	void* args[] = {argStruct};
-	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
-	B3_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, grid, block, args, 0, w->stream));
-	g_launchCount++;
-	return 0;
 }
 
-int launchSolverSetup(World* w)
+// ================================================================ launchers
+static size_t tileCapacity(const World* w, int blocksMax)
 {
-	SetupArgs s;
+	const size_t nc = (size_t)std::max(w->cfg.maxContactCapacity, 1);
+	return nc / 32 + std::min(nc, (size_t)blocksMax * MAX_BATCHES) + MAX_BATCHES + 2;
+}
+
+static int fillSetupArgs(World* w, SetupArgs& s)
+{
+	const int B = w->partBlocksMax;
+	const size_t nc = (size_t)std::max(w->cfg.maxContactCapacity, 1);
+	const size_t nb = (size_t)std::max(w->numBodies, 1);
+	const size_t tiles = tileCapacity(w, B);
+	B3_TRY(w->dTilesN.reserve(tiles * NT_STRIDE));
+	B3_TRY(w->dTilesF.reserve(tiles * FT_STRIDE));
+	B3_TRY(w->dContactBlock.reserve(nc));
+	B3_TRY(w->dContactSlots.reserve(nc));
+	B3_TRY(w->dContactColour.reserve(nc));
+	B3_TRY(w->dBlockList.reserve(nc));
+	B3_TRY(w->dCrossList.reserve(nc));
+	B3_TRY(w->dBodyMask.reserve(2 * nb));
+	B3_TRY(w->dBodyPrio.reserve(2 * nb));
+	B3_TRY(w->dSolverScratch.reserve((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM));
+	B3_TRY(w->dBlockStatics.reserve((size_t)B * NSTATIC));
+	B3_TRY(w->dBlockStart.reserve((size_t)B + 1));
+	B3_TRY(w->dBlockTileBase.reserve((size_t)B));
+	B3_TRY(w->dBlockTileOff.reserve((size_t)B * (MAX_BATCHES + 1)));
+	B3_TRY(w->dCrossTileOff.reserve(MAX_BATCHES + 1));
 	s.contacts = w->dContacts.ptr;
 	s.ctr = w->dCounters.ptr;
 	s.pose = w->dPose.ptr;
-	s.vel = w->dVel.ptr;
 	s.inertias = w->dInertias.ptr;
-	s.constraints = w->dConstraints.ptr;
+	s.bodyLoc = w->dBodyLoc.ptr;
 	s.bodyMask = w->dBodyMask.ptr;
 	s.bodyPrio = reinterpret_cast<unsigned long long*>(w->dBodyPrio.ptr);
+	s.contactBlock = w->dContactBlock.ptr;
+	s.contactSlots = w->dContactSlots.ptr;
 	s.contactColour = w->dContactColour.ptr;
-	s.batchCount = w->dBatchCount.ptr;
-	s.batchOffset = w->dBatchOffset.ptr;
-	s.batchCursor = w->dBatchCursor.ptr;
-	s.remaining = w->dBodyCount.ptr;  // MAX_ROUNDS words, see World::init
-	s.colourList = w->dColourList.ptr;
-	s.colourListStride = (int)(w->dColourList.cap / 2);
-	s.bar = w->dGridBarrier.ptr;
+	unsigned int* scr = w->dSolverScratch.ptr;
+	s.blockCount = scr;
+	s.blockCursor = scr + B;
+	s.crossHist = scr + 2 * B;
+	s.crossCursor = scr + 2 * B + MAX_BATCHES;
+	s.misc = scr + 2 * B + 2 * MAX_BATCHES;
+	s.blockStatics = w->dBlockStatics.ptr;
+	s.blockStart = w->dBlockStart.ptr;
+	s.blockList = w->dBlockList.ptr;
+	s.crossList = w->dCrossList.ptr;
+	s.blockTileBase = w->dBlockTileBase.ptr;
+	s.blockTileOff = w->dBlockTileOff.ptr;
+	s.crossTileOff = w->dCrossTileOff.ptr;
+	s.tilesN = w->dTilesN.ptr;
+	s.tilesF = w->dTilesF.ptr;
+	s.tileCap = (unsigned int)tiles;
 	s.numBodies = w->numBodies;
+	s.numBlocksMax = B;
+	s.S = w->partS;
 	s.staticIdx = w->static0Index;
 	s.colouring = w->solverColouring;
 	s.dt = 1.f / 60.f;  // the reference solver ignores deltaTime (b3GpuPgsContactSolver.cpp:672)
 	s.positionDrift = 0.005f;
 	s.positionConstraintCoeff = 0.2f;
-	return coopLaunch(w, (const void*)solverSetupKernel, &s);
+	return 0;
+}
+
+int launchSolverSetup(World* w)
+{
+	B3_TRY(ensurePartition(w));
+	SetupArgs s;
+	B3_TRY(fillSetupArgs(w, s));
+	cudaStream_t st = w->stream;
+	const int B = w->partBlocksMax;
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dSolverScratch.ptr, 0, sizeof(unsigned int) * ((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM), st));
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dBlockStatics.ptr, 0xff, sizeof(int) * (size_t)B * NSTATIC, st));
+	const int grid = w->smCount * 2;
+	solverClassifyKernel<<<grid, SETUP_THREADS, 0, st>>>(s);
+	B3_LAUNCH_CHECK();
+	solverScatterKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * ((size_t)B + 1), st>>>(s);
+	B3_LAUNCH_CHECK();
+	if (w->solverColouring == 0)
+	{
+		solverCrossColourKernel<<<1, 1024, 0, st>>>(s);
+		B3_LAUNCH_CHECK();
+	}
+	{
+		const int slots = w->partS + NSTATIC;
+		size_t smem = sizeof(unsigned long long) * 2 * (size_t)slots;
+		if (w->solverColouring == 0) smem += sizeof(unsigned long long) * (size_t)slots + (size_t)JP_CONTACT_CAP * 5 + 16;
+		if (!w->solverAttrSet)
+		{
+			B3_CUDA_CHECK(cudaFuncSetAttribute(solverBlockSetupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float4) * 6 * (S_MAX + NSTATIC))));
+			w->solverAttrSet = true;
+		}
+		solverBlockSetupKernel<<<std::min(B, w->smCount * 2), SETUP_THREADS, smem, st>>>(s);
+		B3_LAUNCH_CHECK();
+	}
+	solverCrossBuildKernel<<<grid, SETUP_THREADS, 0, st>>>(s);
+	B3_LAUNCH_CHECK();
+	w->solverMisc = s.misc;
+	return 0;
 }
 
 int launchSolverIterate(World* w)
 {
+	if (!w->partValid || !w->solverMisc)
+	{
+		setLastError("solver_iterate without solver_setup");
+		return B3B200_ERR_STATE;
+	}
 	IterArgs s;
-	s.constraints = w->dConstraints.ptr;
+	s.tilesN = w->dTilesN.ptr;
+	s.tilesF = w->dTilesF.ptr;
+	s.tileCap = (unsigned int)tileCapacity(w, w->partBlocksMax);
 	s.ctr = w->dCounters.ptr;
 	s.pose = w->dPose.ptr;
 	s.vel = w->dVel.ptr;
 	s.inertias = w->dInertias.ptr;
-	s.batchOffset = w->dBatchOffset.ptr;
+	s.partVals = w->dPartVals.ptr;
+	s.partBounds = w->dPartBounds.ptr;
+	s.blockStatics = w->dBlockStatics.ptr;
+	s.blockTileBase = w->dBlockTileBase.ptr;
+	s.blockTileOff = w->dBlockTileOff.ptr;
+	s.crossTileOff = w->dCrossTileOff.ptr;
+	s.misc = w->solverMisc;
+	s.bodyMask = w->dBodyMask.ptr;
 	s.bar = w->dGridBarrier.ptr;
 	s.iterations = w->solverIterations;
-	s.bodyMask = w->dBodyMask.ptr;
-	s.seq = w->dBodyCount.ptr;
+	s.S = w->partS;
+	s.numBlocksMax = w->partBlocksMax;
 	w->soaDirty = true;
-	if (w->solverDataflow)
-	{
-		// all threads must be co-resident: grid = SMs x occupancy, cooperative launch
-		int perSm = 0;
-		B3_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void*)solverIterateDataflowKernel, DF_THREADS, 0));
-		if (perSm < 1)
-		{
-			setLastError("solver kernel does not fit on an SM");
-			return B3B200_ERR_CUDA;
-		}
-		B3_CUDA_CHECK(cudaMemsetAsync(w->dBodyCount.ptr, 0, sizeof(unsigned int) * (size_t)std::max(w->numBodies, 1), w->stream));
-		dim3 grid(w->smCount * perSm), block(DF_THREADS);
-		void* args[] = {&s};
-		B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateDataflowKernel, grid, block, args, 0, w->stream));
-		g_launchCount++;
-		return 0;
-	}
-	return coopLaunch(w, (const void*)solverIterateKernel, &s, ITER_THREADS);
+	const size_t smem = sizeof(float4) * 6 * (size_t)(w->partS + NSTATIC);
+	// one CTA per SM at most (cooperative: all CTAs co-resident); small worlds use as many CTAs as they have blocks
+	const int grid = std::max(1, std::min(w->smCount, w->partBlocksMax));
+	dim3 g(grid), b(ITER_THREADS);
+	void* args[] = {&s};
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
+	B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateKernel, g, b, args, smem, w->stream));
+	g_launchCount++;
+	return 0;
+}
+
+// b3b200_get_constraints: rows in the reference layout, sorted by batch on the host
+int exportConstraints(World* w, std::vector<b3b200_constraint4>& out, std::vector<int>& batchOffsets)
+{
+	out.clear();
+	batchOffsets.assign(1, 0);
+	if (!w->solverMisc) return 0;
+	unsigned int nContacts = 0;
+	B3_CUDA_CHECK(cudaMemcpyAsync(&nContacts, &w->dCounters.ptr[CTR_CONTACTS], sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	if (nContacts == 0) return 0;
+	DevBuf<b3b200_constraint4> tmp;
+	DevBuf<unsigned int> cursor;
+	B3_TRY(tmp.reserve(nContacts));
+	B3_TRY(cursor.reserve(1));
+	B3_CUDA_CHECK(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned int), w->stream));
+	solverExportKernel<<<w->smCount * 4, 256, 0, w->stream>>>(w->dTilesN.ptr, w->dTilesF.ptr, (unsigned int)tileCapacity(w, w->partBlocksMax), w->solverMisc,
+															 w->dCrossTileOff.ptr, tmp.ptr, cursor.ptr, nContacts);
+	B3_LAUNCH_CHECK();
+	unsigned int n = 0;
+	B3_CUDA_CHECK(cudaMemcpyAsync(&n, cursor.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	n = std::min(n, nContacts);
+	std::vector<b3b200_constraint4> raw(n);
+	if (n) B3_CUDA_CHECK(cudaMemcpy(raw.data(), tmp.ptr, sizeof(b3b200_constraint4) * n, cudaMemcpyDeviceToHost));
+	int nb = 0;
+	for (unsigned int i = 0; i < n; i++) nb = std::max(nb, raw[i].batchIdx + 1);
+	std::vector<int> count(nb + 1, 0);
+	for (unsigned int i = 0; i < n; i++) count[raw[i].batchIdx + 1]++;
+	for (int b = 0; b < nb; b++) count[b + 1] += count[b];
+	batchOffsets.assign(count.begin(), count.end());
+	out.resize(n);
+	std::vector<int> cur(count.begin(), count.end() - 1);
+	for (unsigned int i = 0; i < n; i++) out[cur[raw[i].batchIdx]++] = raw[i];
+	return 0;
 }
 
 }  // namespace b3b200

@@ -390,6 +390,8 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->static0Index = -1;
 	w->uploaded = false;
 	w->aabbsValid = false;
+	w->partValid = false;
+	w->solverMisc = nullptr;
 	w->bp.reset();
 	return 0;
 }
@@ -638,14 +640,6 @@ extern "C" int b3b200_upload(b3b200_world* w)
 		B3_TRY(w->dConcavePairs.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
 		B3_TRY(w->dConcaveSurvivors.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
 	}
-	B3_TRY(w->dConstraints.reserve(nc + 32 * MAX_BATCHES));  // batches are padded to multiples of 32
-	B3_TRY(w->dContactColour.reserve(nc));
-	B3_TRY(w->dColourList.reserve(2 * nc));
-	B3_TRY(w->dBodyMask.reserve(2 * nb));
-	B3_TRY(w->dBodyPrio.reserve(2 * nb));
-	B3_TRY(w->dBatchCount.reserve(MAX_BATCHES + 1));
-	B3_TRY(w->dBatchOffset.reserve(MAX_BATCHES + 1));
-	B3_TRY(w->dBatchCursor.reserve(MAX_BATCHES + 1));
 	B3_TRY(w->dBodyCount.reserve(std::max(nb, (size_t)1024)));
 	B3_TRY(w->bp.writeAabbs());
 	B3_TRY(launchPackSoA(w));
@@ -675,12 +669,6 @@ extern "C" int b3b200_set_broadphase(b3b200_world* w, int kind)
 {
 	if (!w || (kind != B3B200_BP_SAP && kind != B3B200_BP_GRID)) return B3B200_ERR_INVALID;
 	w->bp.kind = kind;
-	return 0;
-}
-extern "C" int b3b200_set_solver_dataflow(b3b200_world* w, int enable)
-{
-	if (!w) return B3B200_ERR_INVALID;
-	w->solverDataflow = enable != 0;
 	return 0;
 }
 extern "C" int b3b200_set_colouring(b3b200_world* w, int mode)
@@ -902,32 +890,25 @@ extern "C" int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, 
 {
 	W_UPLOADED(w);
 	if (!numConstraints || capacity < 0) return B3B200_ERR_INVALID;
-	unsigned int off[MAX_BATCHES + 1];
-	B3_CUDA_CHECK(cudaMemcpyAsync(off, w->dBatchOffset.ptr, sizeof(off), cudaMemcpyDeviceToHost, w->stream));
-	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
-	int n = (int)off[MAX_BATCHES];
-	*numConstraints = n;
-	int m = std::min(n, capacity);
-	if (m > 0 && dst)
-	{
-		B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dConstraints.ptr, sizeof(b3b200_constraint4) * m, cudaMemcpyDeviceToHost, w->stream));
-		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
-	}
+	std::vector<b3b200_constraint4> rows;
+	std::vector<int> off;
+	B3_TRY(exportConstraints(w, rows, off));
+	*numConstraints = (int)rows.size();
+	const int m = std::min((int)rows.size(), capacity);
+	if (m > 0 && dst) memcpy(dst, rows.data(), sizeof(b3b200_constraint4) * (size_t)m);
 	return 0;
 }
 extern "C" int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches)
 {
 	W_UPLOADED(w);
 	if (!numBatches || capacity < 0) return B3B200_ERR_INVALID;
-	unsigned int c[CTR_COUNT];
-	B3_TRY(readCounters(w, c));
-	unsigned int off[MAX_BATCHES + 1];
-	B3_CUDA_CHECK(cudaMemcpyAsync(off, w->dBatchOffset.ptr, sizeof(off), cudaMemcpyDeviceToHost, w->stream));
-	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
-	int nb = (int)c[CTR_BATCHES];
+	std::vector<b3b200_constraint4> rows;
+	std::vector<int> off;
+	B3_TRY(exportConstraints(w, rows, off));
+	const int nb = (int)off.size() - 1;
 	*numBatches = nb;
 	if (batchOffsets)
-		for (int i = 0; i <= nb && i < capacity; i++) batchOffsets[i] = (i == nb) ? (int)off[MAX_BATCHES] : (int)off[i];
+		for (int i = 0; i <= nb && i < capacity; i++) batchOffsets[i] = off[i];
 	return 0;
 }
 extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)

@@ -128,14 +128,13 @@ int b3b200_set_ray_accel(b3b200_world* w, int mode);
 int b3b200_set_gravity(b3b200_world* w, const float* gravity3);
 int b3b200_set_solver(b3b200_world* w, int kind, int iterations);
 int b3b200_set_broadphase(b3b200_world* w, int kind);
-/* PGS iteration kernel: 0 = one grid barrier per batch (default), 1 = barrier-free per-body dataflow ordering (experimental).
- * Both execute the same Gauss-Seidel order and give bit-identical velocities. */
-int b3b200_set_solver_dataflow(b3b200_world* w, int enable);
 /* how the PGS solver assigns contacts to batches (the reference: b3Solver::batchContacts / sortConstraintByBatch3; any
- * assignment in which no two contacts of a batch share a dynamic body gives a valid Gauss-Seidel order):
- * 1 (default) = one pass, every contact takes the lowest colour free on both bodies with atomics (fast, the colours
- * depend on how the races resolve); 0 = Jones-Plassmann rounds by hashed priorities (reproducible for a given contact
- * array, about 35 grid-wide rounds). */
+ * assignment in which no two contacts of a batch share a dynamic body gives a valid Gauss-Seidel order).  Two levels, like the
+ * reference's cells: the dynamic bodies are cut into spatial blocks (one per SM); contacts inside a block are coloured by the
+ * block's CTA in shared memory, contacts between blocks globally.  b3Contact4::m_batchIdx = position in the solve order.
+ * 1 (default) = every contact takes the lowest colour free on both bodies with atomics (one pass; the colours depend on how
+ * the races resolve); 0 = priority rounds (reproducible for a given contact array; the cross contacts in one CTA: slow
+ * on large scenes). */
 int b3b200_set_colouring(b3b200_world* w, int mode);
 /* clip window of the convex-convex clipper: the reference kernels use
  * (-1e30, 0.02) (satClipHullContacts.cl:916-917), the shared CPU header (-1, 0)
@@ -171,8 +170,8 @@ int b3b200_get_aabbs(b3b200_world* w, b3b200_aabb* dst, int n);
 int b3b200_get_pairs(b3b200_world* w, b3b200_int4* dst, int capacity, int* numPairs);
 int b3b200_get_contacts(b3b200_world* w, b3b200_contact4* dst, int capacity, int* numContacts);
 int b3b200_set_contacts(b3b200_world* w, const b3b200_contact4* src, int numContacts);
-/* constraints in solve order (sorted by batch); batchOffsets has numBatches+1 entries.  Every batch is
- * padded to a multiple of 32 slots; padding slots have batchIdx == -1 and bodyA == 0xffffffff. */
+/* the solver rows as b3ContactConstraint4 records in solve order (sorted by batch; inside a batch the order is free);
+ * batchOffsets has numBatches+1 entries.  (Converted on request from the solver's own 32-row tiles.) */
 int b3b200_get_constraints(b3b200_world* w, b3b200_constraint4* dst, int capacity, int* numConstraints);
 int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capacity, int* numBatches);
 /* counters of the last step: [0]=pairs [1]=contacts [2]=batches [3]=colouring rounds

@@ -296,13 +296,22 @@ def test_contact_capacity_clamp():
 
 
 # ------------------------------------------------------------------ solver
+def check_batches(contacts, colours, bodies):
+    """the reference's batch invariant: no two contacts of a batch share a dynamic body"""
+    for b in np.unique(colours[colours >= 0]):
+        seg = contacts[colours == b]
+        ids = np.concatenate([np.abs(seg["bodyA"]), np.abs(seg["bodyB"])])
+        ids = ids[bodies["invMass"][ids] != 0]
+        assert len(ids) == len(np.unique(ids)), b
+
+
 @pytest.mark.parametrize("colouring", [0, 1])
-@pytest.mark.parametrize("dataflow", [True, False])
-@pytest.mark.parametrize("seed,iters", [(0, 4), (1, 10)])
-def test_pgs_solver_matches_oracle(seed, iters, dataflow, colouring):
-    w, sh, bodies, inertias = gpu_world(n_side=7, seed=seed)
+@pytest.mark.parametrize("seed,iters,n_side", [(0, 4, 7), (1, 10, 7), (2, 6, 14)])
+def test_pgs_solver_matches_oracle(seed, iters, n_side, colouring):
+    """two-level batching (blocks of bodies in shared memory + coloured contacts between blocks); n_side 14 = 2 745 bodies
+    -> several blocks, i.e. the cross-block colours and their grid barriers run too"""
+    w, sh, bodies, inertias = gpu_world(n_side=n_side, seed=seed)
     w.set_solver(capi.SOLVER_PGS, iters)
-    w.set_solver_dataflow(dataflow)
     w.set_colouring(colouring)
     w.update_aabbs()
     w.find_pairs()
@@ -311,40 +320,30 @@ def test_pgs_solver_matches_oracle(seed, iters, dataflow, colouring):
     assert len(contacts) > 200
     w.solver_setup()
     g_contacts = w.contacts()
-    if colouring == 0:
-        # --- same batching: the device's Jones-Plassmann colouring equals the oracle's sequential restatement of it
-        nb, colours = oa.colour_contacts(contacts, len(bodies), 0)
-        assert np.array_equal(g_contacts["batchIdx"], colours)
-    else:
-        # --- the single-pass colouring depends on how its races resolve: take the device's batches as they are (their
-        # validity is checked below) and give the same ones to the oracle; at most a few colours more than the sequential one
-        colours = g_contacts["batchIdx"].astype(np.int32)
-        nb = int(colours.max()) + 1
-        assert colours.min() >= 0 and nb <= oa.colour_contacts(contacts, len(bodies), 0)[0] + 4
+    # --- "same batching": the device's batch assignment is taken as it is (its validity is checked here) and given to the oracle
+    colours = g_contacts["batchIdx"].astype(np.int32)
+    nb = int(colours.max()) + 1
+    ctr = w.counters()
+    assert colours.min() >= 0 and nb == ctr[2]
+    if n_side >= 14:
+        assert ctr[3] > 0  # there are contacts between blocks
+    assert nb <= oa.colour_contacts(contacts, len(bodies), 0)[0] + 12
+    check_batches(g_contacts, colours, bodies)
     off = w.batches()
     cs_all = w.constraints()
-    assert len(off) - 1 == nb and off[-1] == len(cs_all) and (np.diff(off) % 32 == 0).all()
-    counts = np.array([(cs_all[off[b]: off[b + 1]]["batchIdx"] >= 0).sum() for b in range(nb)])
-    assert np.array_equal(counts, np.bincount(colours, minlength=nb)) and counts.sum() == len(contacts)
-    # no two constraints of a batch share a dynamic body
+    assert len(off) - 1 == nb and off[-1] == len(cs_all) == len(contacts)
     for b in range(nb):
-        seg = cs_all[off[b]: off[b + 1]]
-        seg = seg[seg["batchIdx"] >= 0]  # drop the padding slots
-        assert (seg["batchIdx"] == b).all()
-        ids = np.concatenate([seg["bodyA"], seg["bodyB"]])
-        ids = ids[bodies["invMass"][ids] != 0]
-        assert len(ids) == len(np.unique(ids))
+        assert (cs_all[off[b]: off[b + 1]]["batchIdx"] == b).all()
+    assert np.array_equal(np.diff(off), np.bincount(colours, minlength=nb))
     # --- constraint rows equal the oracle's (order inside a batch is free -> sort by body ids)
-    g_contacts["batchIdx"] = colours
     o_cs = oa.build_constraints(oa.oracle(), "orc_", g_contacts, bodies, inertias)
 
     def key(c):
         return np.lexsort((c["bodyB"], c["bodyA"], c["batchIdx"]))
 
-    cs = cs_all[cs_all["batchIdx"] >= 0]
-    gs, os_ = cs[key(cs)], o_cs[key(o_cs)]
+    gs, os_ = cs_all[key(cs_all)], o_cs[key(o_cs)]
     for f in ("linear", "worldPos", "center", "jacCoeffInv", "b", "fJacCoeffInv"):
-        assert rel_close(gs[f], os_[f], 1e-5), f
+        assert rel_close(gs[f][..., :3] if f in ("worldPos", "center") else gs[f], os_[f][..., :3] if f in ("worldPos", "center") else os_[f], 1e-5), f
     # --- velocities after the iterations
     w.solver_iterate()
     g_bodies = w.bodies()
@@ -353,6 +352,28 @@ def test_pgs_solver_matches_oracle(seed, iters, dataflow, colouring):
     assert rel_close(g_bodies["angVel"][:, :3], o_bodies["angVel"][:, :3], 1e-4)
     moved = np.abs(g_bodies["linVel"][:, :3] - bodies["linVel"][:, :3]).max()
     assert moved > 0.1  # the solver did something
+    # the applied impulses come back with the rows
+    assert np.abs(w.constraints()["appliedRambdaDt"]).max() > 0
+
+
+def test_pgs_reproducible_colouring_is_bit_identical_between_worlds():
+    """colouring mode 0: the batch assignment (and with it every bit of the result) is a function of the contact array"""
+    out = []
+    for _ in range(2):
+        w, sh, bodies, inertias = gpu_world(n_side=14, seed=7)
+        w.set_solver(capi.SOLVER_PGS, 10)
+        w.set_colouring(0)
+        w.update_aabbs()
+        w.find_pairs()
+        w.compute_contacts()
+        if out:
+            w.set_contacts(out[0][1])  # the narrowphase appends with atomics: give both worlds the same contact ARRAY
+        contacts = w.contacts()
+        w.solve_contacts()
+        out.append((w.bodies(), contacts, w.contacts()["batchIdx"].copy()))
+    assert np.array_equal(out[0][2], out[1][2])
+    for f in ("linVel", "angVel"):
+        assert np.array_equal(out[0][0][f].view(np.uint32), out[1][0][f].view(np.uint32)), f
 
 
 @pytest.mark.parametrize("seed,iters", [(0, 7), (3, 8)])
@@ -392,35 +413,38 @@ def test_jacobi_box_plane_scene_settles():
     assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 0.5
 
 
-def test_dataflow_and_barrier_kernels_bit_identical():
-    """the two iteration kernels execute the same Gauss-Seidel order"""
-    out = []
-    for mode in (True, False):
-        w, sh, bodies, inertias = gpu_world(n_side=10, seed=7)
-        w.set_solver(capi.SOLVER_PGS, 10)
-        w.set_solver_dataflow(mode)
-        w.set_colouring(0)  # two worlds: the reproducible batch assignment
-        w.update_aabbs()
-        w.find_pairs()
-        w.compute_contacts()
-        w.solve_contacts()
-        out.append(w.bodies())
-    for f in ("linVel", "angVel"):
-        assert np.array_equal(out[0][f].view(np.uint32), out[1][f].view(np.uint32)), f
+def transfer_batches(device_contacts, oracle_contacts):
+    """batch index of every oracle contact = that of the device contact with the same bytes (everything but batchIdx)"""
+    def canon(c):
+        c = c.copy()
+        c["batchIdx"] = 0
+        return c.view(np.uint8).reshape(len(c), -1)
+
+    d, o = canon(device_contacts), canon(oracle_contacts)
+    do = np.lexsort(d.T[::-1])
+    oo = np.lexsort(o.T[::-1])
+    assert np.array_equal(d[do], o[oo]), "contact sets differ"
+    out = np.zeros(len(o), np.int32)
+    out[oo] = device_contacts["batchIdx"][do]
+    return out
 
 
-def test_full_step_matches_oracle_pipeline():
-    """one whole b3b200_step == oracle stages chained on the CPU"""
-    w, sh, bodies, inertias = gpu_world(n_side=6, seed=5)
+@pytest.mark.parametrize("colouring,n_side", [(1, 6), (1, 14), (0, 6)])
+def test_full_step_matches_oracle_pipeline(colouring, n_side):
+    """one whole b3b200_step == oracle stages chained on the CPU, in the DEFAULT configuration too: the oracle computes its own
+    AABBs, pairs and contacts and solves them with the device's batch assignment ("same batching")"""
+    w, sh, bodies, inertias = gpu_world(n_side=n_side, seed=5)
     w.set_solver(capi.SOLVER_PGS, 4)
-    w.set_colouring(0)  # "same batching": the batch assignment the oracle restates
+    w.set_colouring(colouring)
     w.step(1 / 60)
     g = w.bodies()
     aabbs = oa.update_aabbs(oa.oracle(), "orc_", bodies, sh)
     small, large = small_large(bodies)
     _, pairs = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 1 << 22)
     contacts, _ = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
-    solved, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, 4)
+    colours = transfer_batches(w.contacts(), contacts)
+    check_batches(contacts, colours, bodies)
+    solved, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, 4, colours=colours)
     o = oa.integrate(oa.oracle(), "orc_", solved, 1 / 60, 0.99, G)
     for f in ("pos", "quat", "linVel", "angVel"):
         assert rel_close(g[f][:, :3], o[f][:, :3], 1e-4), f
