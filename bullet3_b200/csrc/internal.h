@@ -191,6 +191,7 @@ struct World
 	DevBuf<float4> dTilesN, dTilesF;
 	unsigned int* solverMisc = nullptr;    // -> misc words of dSolverScratch once a setup has run
 	bool solverAttrSet = false;
+	DevBuf<unsigned long long> dSolverProbe;  // development aid (b3b200_debug_solver_probe)
 	DevBuf<unsigned int> dGridBarrier;    // software grid barrier state
 	// joints
 	DevBuf<b3b200_generic_constraint> dJoints;

@@ -32,15 +32,24 @@ namespace b3b200
 constexpr int ITER_THREADS = 256;
 constexpr int ITER_WARPS = ITER_THREADS / 32;
 constexpr int SETUP_THREADS = 512;
-constexpr int S_MAX = 2176;       // dynamic bodies per block: (S_MAX + NSTATIC) * 96 B = 215 KB of shared memory
+constexpr int S_MAX = 2560;       // dynamic bodies per block: (S_MAX + NSTATIC) * (80 + 6) B = 220 KB of shared memory
 constexpr int S_MIN = 1024;       // below this a block is not worth a grid barrier
 constexpr int NSTATIC = 64;       // static bodies a block can keep in its own slots (more -> those contacts go the global way)
 constexpr int MAX_BLOCKS = 8192;  // block-start table of the scatter kernel lives in shared memory
 constexpr int JP_CONTACT_CAP = 16384;  // reproducible colouring keeps 5 B of state per interior contact in shared memory
-constexpr int NT_STRIDE = 8 * 32;  // float4 per normal tile: n|ids, 4 x (point | jacCoeffInv), b[4], lambda[4], {bodyA, bodyB, batch, contact}
-constexpr int FT_STRIDE = 2 * 32;  // float4 per friction tile: centre, {fJacCoeffInv[2], fLambda[2]}
+// normal tile, 11 float4 per row: {n, slot pair} | 4 x ({r0 x n, jacCoeffInv}, {-(r1 x n), b}) | lambda[4] | {bodyA, bodyB, batch, contact}
+// (the angular Jacobians are constants of the step -- positions do not move during the solve -- so they are built once
+// here instead of in each of the 2 * I passes like solveContact does: the row solve is a chain of dependent FP32
+// operations, and this halves its length)
+constexpr int NT_FIELDS = 11, NT_LAMBDA = 9, NT_TAIL = 10;
+constexpr int NT_STRIDE = NT_FIELDS * 32;
+// friction tile, 4 float4 per row: {centre, damping flag} | {t0, fJacCoeffInv[0]} | {t1, fJacCoeffInv[1]} | {fLambda[2], -, -}
+constexpr int FT_FIELDS = 4, FT_LAMBDA = 3;
+constexpr int FT_STRIDE = FT_FIELDS * 32;
 constexpr int TAIL_TILES = ITER_WARPS;  // cross colours this small are solved by CTA 0 alone (cheaper than a grid barrier)
 constexpr unsigned int INVALID_IDS = 0xffffffffu;
+constexpr int ITER_SMEM_PER_SLOT = (int)(sizeof(float4) * 5 + sizeof(int) + sizeof(unsigned short));
+constexpr int ITER_SMEM_MAX = ITER_SMEM_PER_SLOT * (S_MAX + NSTATIC);
 
 // scratch layout (unsigned ints, zeroed before the setup kernels): [blockCount | blockCursor | crossHist | crossCursor | misc]
 enum
@@ -88,13 +97,15 @@ struct GridBarrier
 	{
 		if (threadIdx.x == 0)
 		{
-			// poll with relaxed loads and fence ONCE at the end: an acquire load compiles to LD + CCTL.IVALL per poll
+			// Poll with relaxed loads.  No acquire fence afterwards: it costs 0.15-0.3 us per barrier (MEMBAR + CCTL.IVALL, measured
+			// with tools/cu/barrier_bench.cu) and buys nothing here, because every datum another CTA writes during the kernel is
+			// read with L2-only loads (ld.cg / volatile / atomics) that are issued after this loop has seen the last arrival, and the
+			// arriving side has made its stores visible at L2 before its arrival (release).
 			unsigned int v = seen;
 			while ((int)(v - target) < 0)
 			{
 				asm volatile("ld.relaxed.gpu.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
 			}
-			asm volatile("fence.acq_rel.gpu;" ::: "memory");
 		}
 		__syncthreads();
 	}
@@ -353,12 +364,14 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 	const float dtInv = 1.f / s.dt;
 	const float npoints = nrm.w;
 	float jac[4], bb[4];
+	float4 ang0[4], ang1[4];
 	const float4 n = mk4(nrm.x, nrm.y, nrm.z);
 #pragma unroll
 	for (int ic = 0; ic < 4; ic++)
 	{
 		float4 r0 = sub3(wp[ic], posA);
 		float4 r1 = sub3(wp[ic], posB);
+		ang0[ic] = ang1[ic] = mk4(0, 0, 0);
 		if ((float)ic >= npoints)
 		{
 			jac[ic] = 0.f;
@@ -367,6 +380,8 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 		}
 		float4 angular0 = cross3(r0, n);
 		float4 angular1 = neg3(cross3(r1, n));
+		ang0[ic] = angular0;
+		ang1[ic] = angular1;
 		jac[ic] = calcJacCoeff(angular0, angular1, invMassA, ia, invMassB, ib);
 		float b = 0.f;  // e * relVelN, e = 0
 		b += (wp[ic].w + s.positionDrift) * s.positionConstraintCoeff * dtInv;
@@ -374,6 +389,7 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 	}
 	float fjac[2] = {0.f, 0.f};
 	float4 center = mk4(0, 0, 0);
+	float4 t0 = mk4(0, 0, 0), t1 = mk4(0, 0, 0);
 	if (npoints > 0)
 	{
 		for (int i = 0; (float)i < npoints && i < 4; i++)
@@ -386,8 +402,7 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 		center.x *= inv;
 		center.y *= inv;
 		center.z *= inv;
-		float4 t0, t1;
-		planeSpace1(n, t0, t1);
+		planeSpace1(neg3(n), t0, t1);  // the tangents solveFriction uses (of -linear, b3Solver.cpp:278-282)
 		float4 r0 = sub3(center, posA), r1 = sub3(center, posB);
 		{
 			float4 a0 = cross3(r0, t0), a1 = neg3(cross3(r1, t0));
@@ -400,32 +415,45 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 	}
 	tn[0] = mk4(nrm.x, nrm.y, nrm.z, __uint_as_float(idsWord));
 #pragma unroll
-	for (int i = 0; i < 4; i++) tn[(1 + i) * 32] = ((float)i < npoints) ? mk4(wp[i].x, wp[i].y, wp[i].z, jac[i]) : mk4(0, 0, 0, 0);
-	tn[5 * 32] = mk4(bb[0], bb[1], bb[2], bb[3]);
-	tn[6 * 32] = mk4(0, 0, 0, 0);  // appliedRambdaDt
+	for (int i = 0; i < 4; i++)
+	{
+		const bool on = (float)i < npoints;
+		tn[(1 + 2 * i) * 32] = on ? mk4(ang0[i].x, ang0[i].y, ang0[i].z, jac[i]) : mk4(0, 0, 0, 0);
+		tn[(2 + 2 * i) * 32] = on ? mk4(ang1[i].x, ang1[i].y, ang1[i].z, bb[i]) : mk4(0, 0, 0, 0);
+	}
+	tn[NT_LAMBDA * 32] = mk4(0, 0, 0, 0);  // appliedRambdaDt
 	int4 tail;
 	tail.x = aIdx;
 	tail.y = bIdx;
 	tail.z = batch;
 	tail.w = c;
-	reinterpret_cast<int4*>(tn)[7 * 32] = tail;
-	tf[0] = center;
-	tf[32] = mk4(fjac[0], fjac[1], 0, 0);  // fJacCoeffInv, fAppliedRambdaDt
+	reinterpret_cast<int4*>(tn)[NT_TAIL * 32] = tail;
+	// angular damping of solveFriction (b3Solver.cpp:317-328): its condition only depends on positions
+	float damp = 0.f;
+	{
+		const float4 ab = normalized3(sub3(posB, posA));
+		const float4 ac = normalized3(sub3(center, posA));
+		if (dot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f)) damp = 1.f;
+	}
+	tf[0] = mk4(center.x, center.y, center.z, damp);
+	tf[32] = mk4(t0.x, t0.y, t0.z, fjac[0]);
+	tf[64] = mk4(t1.x, t1.y, t1.z, fjac[1]);
+	tf[FT_LAMBDA * 32] = mk4(0, 0, 0, 0);  // fAppliedRambdaDt
 }
 
 B3_D void buildPadding(float4* __restrict__ tn, float4* __restrict__ tf)
 {
 	tn[0] = mk4(0, 0, 0, __uint_as_float(INVALID_IDS));
 #pragma unroll
-	for (int i = 1; i < 7; i++) tn[i * 32] = mk4(0, 0, 0, 0);
+	for (int i = 1; i < NT_TAIL; i++) tn[i * 32] = mk4(0, 0, 0, 0);
 	int4 tail;
 	tail.x = -1;
 	tail.y = -1;
 	tail.z = -1;
 	tail.w = -1;
-	reinterpret_cast<int4*>(tn)[7 * 32] = tail;
-	tf[0] = mk4(0, 0, 0, 0);
-	tf[32] = mk4(0, 0, 0, 0);
+	reinterpret_cast<int4*>(tn)[NT_TAIL * 32] = tail;
+#pragma unroll
+	for (int i = 0; i < FT_FIELDS; i++) tf[i * 32] = mk4(0, 0, 0, 0);
 }
 
 B3_D void contactBodies(const SetupArgs& s, int c, int& a, int& b, bool& aStatic, bool& bStatic, int& la, int& lb)
@@ -1009,6 +1037,7 @@ struct IterArgs
 	int iterations;
 	int S;
 	int numBlocksMax;
+	unsigned long long* probe;  // development aid: globaltimer stamps of CTA 0 (nullptr = off)
 };
 
 // Iteration arithmetic: explicit FMAs.  This file is built with --fmad=false, so the only fused operations are the ones
@@ -1038,23 +1067,24 @@ struct BodyConst
 	float4 i0, i1, i2;
 };
 
-// solveContact<false> (b3Solver.cpp:187-266): the four points of one manifold.  p[i] = {point, jacCoeffInv}.
-B3_D void solveNormalCore(const float4& nId, const float4* p, const float4& bias, float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
+// solveContact<false> (b3Solver.cpp:187-266): the four points of one manifold, with the angular Jacobians of the row.
+// j0[i] = {r0 x n, jacCoeffInv}, j1[i] = {-(r1 x n), b}.
+B3_D void solveNormalCore(const float4& nId, const float4* j0, const float4* j1, float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
 						  float4& angVelA, float4& linVelB, float4& angVelB)
 {
 	const float4 n = mk4(nId.x, nId.y, nId.z);
 	const float4 nn = neg3(n);
-	const float bv[4] = {bias.x, bias.y, bias.z, bias.w};
 	float ap[4] = {applied.x, applied.y, applied.z, applied.w};
+	// what an impulse of 1 does to the four velocities (independent of the velocities: off the dependency chain)
+	const float4 dLinA = scale3(n, A.pos.w), dLinB = scale3(nn, B.pos.w);
 #pragma unroll
 	for (int ic = 0; ic < 4; ic++)
 	{
-		const float jac = p[ic].w;
+		const float jac = j0[ic].w;
 		if (jac == 0.f) continue;
-		const float4 r0 = sub3(p[ic], A.pos), r1 = sub3(p[ic], B.pos);
-		const float4 angular0 = fcross3(r0, n);
-		const float4 angular1 = neg3(fcross3(r1, n));
-		float rambdaDt = fcalcRelVel(n, nn, angular0, angular1, linVelA, angVelA, linVelB, angVelB) + bv[ic];
+		const float4 dAngA = fmatRowMul(A.i0, A.i1, A.i2, j0[ic]);
+		const float4 dAngB = fmatRowMul(B.i0, B.i1, B.i2, j1[ic]);
+		float rambdaDt = fcalcRelVel(n, nn, j0[ic], j1[ic], linVelA, angVelA, linVelB, angVelB) + j1[ic].w;
 		rambdaDt *= jac;
 		{
 			const float prevSum = ap[ic];
@@ -1065,19 +1095,20 @@ B3_D void solveNormalCore(const float4& nId, const float4* p, const float4& bias
 			rambdaDt = updated - prevSum;
 			ap[ic] = updated;
 		}
-		linVelA = faddScaled(linVelA, n, A.pos.w, rambdaDt);
-		angVelA = faddScaled1(angVelA, fmatRowMul(A.i0, A.i1, A.i2, angular0), rambdaDt);
-		linVelB = faddScaled(linVelB, nn, B.pos.w, rambdaDt);
-		angVelB = faddScaled1(angVelB, fmatRowMul(B.i0, B.i1, B.i2, angular1), rambdaDt);
+		linVelA = faddScaled1(linVelA, dLinA, rambdaDt);
+		angVelA = faddScaled1(angVelA, dAngA, rambdaDt);
+		linVelB = faddScaled1(linVelB, dLinB, rambdaDt);
+		angVelB = faddScaled1(angVelB, dAngB, rambdaDt);
 	}
 	applied = mk4(ap[0], ap[1], ap[2], ap[3]);
 }
 
-// solveFriction (b3Solver.cpp:268-329).  fr = {fJacCoeffInv[2], fAppliedRambdaDt[2]}; returns false when the row has no friction
-B3_D bool solveFrictionCore(const float4& nId, const float4& center, float4& fr, const float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
-							float4& angVelA, float4& linVelB, float4& angVelB)
+// solveFriction (b3Solver.cpp:268-329).  cf = {centre, damping flag}, t0 / t1 = {tangent, fJacCoeffInv}, fl = fAppliedRambdaDt;
+// returns false when the row has no friction
+B3_D bool solveFrictionCore(const float4& nId, const float4& cf, const float4& t0, const float4& t1, float4& fl, const float4& applied, const BodyConst& A,
+							const BodyConst& B, float4& linVelA, float4& angVelA, float4& linVelB, float4& angVelB)
 {
-	if (fr.x == 0.f && fr.x == 0.f) return false;  // (sic, b3Solver.cpp:274)
+	if (t0.w == 0.f && t0.w == 0.f) return false;  // (sic, b3Solver.cpp:274)
 	const float invMassA = A.pos.w, invMassB = B.pos.w;
 	float sum = 0.f;
 	sum += applied.x;
@@ -1088,17 +1119,17 @@ B3_D bool solveFrictionCore(const float4& nId, const float4& center, float4& fr,
 	const float maxR = frictionCoeff * sum;
 	const float minR = -maxR;
 	const float4 n = neg3(mk4(nId.x, nId.y, nId.z));
-	float4 tangent[2];
-	planeSpace1(n, tangent[0], tangent[1]);
-	const float4 r0 = sub3(center, A.pos), r1 = sub3(center, B.pos);
-	const float fj[2] = {fr.x, fr.y};
-	float fa[2] = {fr.z, fr.w};
+	const float4 r0 = sub3(cf, A.pos), r1 = sub3(cf, B.pos);
+	const float fj[2] = {t0.w, t1.w};
+	float fa[2] = {fl.x, fl.y};
 #pragma unroll
 	for (int i = 0; i < 2; i++)
 	{
-		const float4 t = tangent[i];
+		const float4 t = i == 0 ? mk4(t0.x, t0.y, t0.z) : mk4(t1.x, t1.y, t1.z);
 		const float4 angular0 = fcross3(r0, t);
 		const float4 angular1 = neg3(fcross3(r1, t));
+		const float4 dAngA = fmatRowMul(A.i0, A.i1, A.i2, angular0);
+		const float4 dAngB = fmatRowMul(B.i0, B.i1, B.i2, angular1);
 		float rambdaDt = fcalcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
 		rambdaDt *= fj[i];
 		{
@@ -1111,23 +1142,19 @@ B3_D bool solveFrictionCore(const float4& nId, const float4& center, float4& fr,
 			fa[i] = updated;
 		}
 		linVelA = faddScaled(linVelA, t, invMassA, rambdaDt);
-		angVelA = faddScaled1(angVelA, fmatRowMul(A.i0, A.i1, A.i2, angular0), rambdaDt);
+		angVelA = faddScaled1(angVelA, dAngA, rambdaDt);
 		linVelB = faddScaled(linVelB, neg3(t), invMassB, rambdaDt);
-		angVelB = faddScaled1(angVelB, fmatRowMul(B.i0, B.i1, B.i2, angular1), rambdaDt);
+		angVelB = faddScaled1(angVelB, dAngB, rambdaDt);
 	}
+	if (cf.w != 0.f)
 	{
-		// angular damping for point constraint (b3Solver.cpp:317-328)
-		const float4 ab = normalized3(sub3(B.pos, A.pos));
-		const float4 ac = normalized3(sub3(center, A.pos));
-		if (fdot3(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
-		{
-			const float angNA = fdot3(n, angVelA);
-			const float angNB = fdot3(n, angVelB);
-			angVelA = faddScaled1(angVelA, n, -(angNA * 0.1f));
-			angVelB = faddScaled1(angVelB, n, -(angNB * 0.1f));
-		}
+		// angular damping for point constraint (b3Solver.cpp:317-328); the condition was evaluated by the setup
+		const float angNA = fdot3(n, angVelA);
+		const float angNB = fdot3(n, angVelB);
+		angVelA = faddScaled1(angVelA, n, -(angNA * 0.1f));
+		angVelB = faddScaled1(angVelB, n, -(angNB * 0.1f));
 	}
-	fr = mk4(fj[0], fj[1], fa[0], fa[1]);
+	fl = mk4(fa[0], fa[1], 0.f, 0.f);
 	return true;
 }
 
@@ -1136,112 +1163,139 @@ template <int PHASE>
 struct RowRegs
 {
 	float4 nId;
-	float4 p[PHASE == 0 ? 4 : 1];  // normal: the four points | friction: the centre
-	float4 bias;                   // normal: b[4] | friction: {fJacCoeffInv[2], fAppliedRambdaDt[2]}
-	float4 applied;
+	float4 j0[PHASE == 0 ? 4 : 1];  // normal: {r0 x n, jacCoeffInv} per point | friction: {centre, damping flag}
+	float4 j1[PHASE == 0 ? 4 : 2];  // normal: {-(r1 x n), b} per point      | friction: {t0, fJacCoeffInv[0]}, {t1, fJacCoeffInv[1]}
+	float4 applied;                 // lambda[4] of the normal rows
+	float4 fl;                      // friction: fLambda[2]
 };
 template <int PHASE>
-B3_D void loadRowRegs(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r)
+B3_D void loadRowRegs(const float4* __restrict__ tilesN, const float4* __restrict__ tilesF, unsigned int tile, int lane, RowRegs<PHASE>& r)
 {
-	const float4* tn = s.tilesN + (size_t)tile * NT_STRIDE + lane;
+	const float4* tn = tilesN + (size_t)tile * NT_STRIDE + lane;
 	r.nId = tn[0];
-	r.applied = tn[6 * 32];
+	r.applied = tn[NT_LAMBDA * 32];
 	if (PHASE == 0)
 	{
 #pragma unroll
-		for (int i = 0; i < 4; i++) r.p[i] = tn[(1 + i) * 32];
-		r.bias = tn[5 * 32];
+		for (int i = 0; i < 4; i++)
+		{
+			r.j0[i] = tn[(1 + 2 * i) * 32];
+			r.j1[i] = tn[(2 + 2 * i) * 32];
+		}
 	}
 	else
 	{
-		const float4* tf = s.tilesF + (size_t)tile * FT_STRIDE + lane;
-		r.p[0] = tf[0];
-		r.bias = tf[32];
+		const float4* tf = tilesF + (size_t)tile * FT_STRIDE + lane;
+		r.j0[0] = tf[0];
+		r.j1[0] = tf[32];
+		r.j1[1] = tf[64];
+		r.fl = tf[FT_LAMBDA * 32];
 	}
 }
+template <int PHASE>
+B3_D bool solveRowCore(RowRegs<PHASE>& r, const BodyConst& A, const BodyConst& B, float4& linVelA, float4& angVelA, float4& linVelB, float4& angVelB)
+{
+	if (PHASE == 0)
+	{
+		solveNormalCore(r.nId, r.j0, r.j1, r.applied, A, B, linVelA, angVelA, linVelB, angVelB);
+		return true;
+	}
+	return solveFrictionCore(r.nId, r.j0[0], r.j1[0], r.j1[PHASE == 0 ? 0 : 1], r.fl, r.applied, A, B, linVelA, angVelA, linVelB, angVelB);
+}
+template <int PHASE>
+B3_D void storeRowLambda(float4* tilesN, float4* tilesF, unsigned int tile, int lane, const RowRegs<PHASE>& r)
+{
+	if (PHASE == 0)
+		tilesN[(size_t)tile * NT_STRIDE + NT_LAMBDA * 32 + lane] = r.applied;
+	else
+		tilesF[(size_t)tile * FT_STRIDE + FT_LAMBDA * 32 + lane] = r.fl;
+}
 
+// The CTA's shared-memory state: one 16-byte array per quantity (a warp gathers 32 random slots per load: with 16-byte
+// strides the eight lanes of a quarter-warp can hit all 32 banks, with the 32-byte {lin, ang} records of the global
+// array only half of them -- shared-memory wavefronts are what bounds the interior loop).  The world inverse inertia is
+// kept as its upper triangle (R diag R^T is symmetric up to rounding): 2 loads per body instead of 4 with the position.
+struct SharedBodies
+{
+	float4* lin;        // linear velocity
+	float4* ang;        // angular velocity
+	float4* inerA;      // {Ixx, Ixy, Ixz, Iyy}
+	float4* inerB;      // {Iyz, Izz, inverse mass, -}
+	float4* pos;        // position (friction rows: r = centre - pos)
+};
 // interior row: bodies are slots of the CTA's shared-memory state
 template <int PHASE>
-B3_D void solveRowShared(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r, float4* sVel, const float4* sPose, const float4* sIner)
+B3_D void solveRowShared(float4* tilesN, float4* tilesF, unsigned int tile, int lane, RowRegs<PHASE>& r, const SharedBodies& sb_)
 {
 	const unsigned int ids = __float_as_uint(r.nId.w);
 	if (ids == INVALID_IDS) return;
 	const int sa = (int)(ids & 0xffffu), sb = (int)(ids >> 16);
 	BodyConst A, B;
-	A.pos = sPose[sa];
-	B.pos = sPose[sb];
-	A.i0 = sIner[3 * sa], A.i1 = sIner[3 * sa + 1], A.i2 = sIner[3 * sa + 2];
-	B.i0 = sIner[3 * sb], B.i1 = sIner[3 * sb + 1], B.i2 = sIner[3 * sb + 2];
-	float4 linVelA = sVel[2 * sa], angVelA = sVel[2 * sa + 1];
-	float4 linVelB = sVel[2 * sb], angVelB = sVel[2 * sb + 1];
-	if (PHASE == 0)
 	{
-		solveNormalCore(r.nId, r.p, r.bias, r.applied, A, B, linVelA, angVelA, linVelB, angVelB);
-		s.tilesN[(size_t)tile * NT_STRIDE + 6 * 32 + lane] = r.applied;
+		const float4 a0 = sb_.inerA[sa], a1 = sb_.inerB[sa], b0 = sb_.inerA[sb], b1 = sb_.inerB[sb];
+		A.i0 = mk4(a0.x, a0.y, a0.z), A.i1 = mk4(a0.y, a0.w, a1.x), A.i2 = mk4(a0.z, a1.x, a1.y);
+		B.i0 = mk4(b0.x, b0.y, b0.z), B.i1 = mk4(b0.y, b0.w, b1.x), B.i2 = mk4(b0.z, b1.x, b1.y);
+		A.pos = mk4(0, 0, 0, a1.z);
+		B.pos = mk4(0, 0, 0, b1.z);
+		if (PHASE == 1)
+		{
+			const float4 pa = sb_.pos[sa], pb = sb_.pos[sb];
+			A.pos = mk4(pa.x, pa.y, pa.z, a1.z);
+			B.pos = mk4(pb.x, pb.y, pb.z, b1.z);
+		}
 	}
-	else
-	{
-		if (!solveFrictionCore(r.nId, r.p[0], r.bias, r.applied, A, B, linVelA, angVelA, linVelB, angVelB)) return;
-		s.tilesF[(size_t)tile * FT_STRIDE + 32 + lane] = r.bias;
-	}
+	float4 linVelA = sb_.lin[sa], angVelA = sb_.ang[sa];
+	float4 linVelB = sb_.lin[sb], angVelB = sb_.ang[sb];
+	if (!solveRowCore<PHASE>(r, A, B, linVelA, angVelA, linVelB, angVelB)) return;
+	storeRowLambda<PHASE>(tilesN, tilesF, tile, lane, r);
 	if (A.pos.w != 0.f)
 	{
-		sVel[2 * sa] = linVelA;
-		sVel[2 * sa + 1] = angVelA;
+		sb_.lin[sa] = linVelA;
+		sb_.ang[sa] = angVelA;
 	}
 	if (B.pos.w != 0.f)
 	{
-		sVel[2 * sb] = linVelB;
-		sVel[2 * sb + 1] = angVelB;
+		sb_.lin[sb] = linVelB;
+		sb_.ang[sb] = angVelB;
 	}
 }
 
-// cross row: bodies through global memory (L2)
-struct CrossPre
+// cross row: bodies through global memory (L2).  Everything but the row itself is fetched AFTER the grid barrier: the
+// velocities have to be (one L2 round trip), and the constants of the two bodies ride along in the same round trip.
+struct CrossBodies
 {
-	int a, b;
-	BodyConst A, B;
+	const float4* pose;
+	float4* vel;
+	const b3b200_inertia* inertias;
 };
-B3_D void loadCrossPre(const IterArgs& s, unsigned int tile, int lane, CrossPre& c)
-{
-	const int4 tail = reinterpret_cast<const int4*>(s.tilesN)[(size_t)tile * NT_STRIDE + 7 * 32 + lane];
-	c.a = tail.x;
-	c.b = tail.y;
-	if (c.a < 0) return;
-	c.A.pos = s.pose[2 * c.a];
-	c.B.pos = s.pose[2 * c.b];
-	const float4* IA = reinterpret_cast<const float4*>(&s.inertias[c.a].invInertiaWorld);
-	const float4* IB = reinterpret_cast<const float4*>(&s.inertias[c.b].invInertiaWorld);
-	c.A.i0 = __ldg(IA), c.A.i1 = __ldg(IA + 1), c.A.i2 = __ldg(IA + 2);
-	c.B.i0 = __ldg(IB), c.B.i1 = __ldg(IB + 1), c.B.i2 = __ldg(IB + 2);
-}
 template <int PHASE>
-B3_D void solveRowGlobal(const IterArgs& s, unsigned int tile, int lane, RowRegs<PHASE>& r, const CrossPre& c)
+B3_D void solveRowGlobal(float4* tilesN, float4* tilesF, const CrossBodies& cb, unsigned int tile, int lane, RowRegs<PHASE>& r, const int4& tail)
 {
-	if (c.a < 0) return;
-	float4 linVelA = __ldcg(&s.vel[2 * c.a]), angVelA = __ldcg(&s.vel[2 * c.a + 1]);
-	float4 linVelB = __ldcg(&s.vel[2 * c.b]), angVelB = __ldcg(&s.vel[2 * c.b + 1]);
-	if (PHASE == 0)
+	const int a = tail.x, b = tail.y;
+	if (a < 0) return;
+	BodyConst A, B;
+	float4 linVelA = __ldcg(&cb.vel[2 * a]), angVelA = __ldcg(&cb.vel[2 * a + 1]);
+	float4 linVelB = __ldcg(&cb.vel[2 * b]), angVelB = __ldcg(&cb.vel[2 * b + 1]);
+	A.pos = __ldg(&cb.pose[2 * a]);
+	B.pos = __ldg(&cb.pose[2 * b]);
+	const float4* IA = reinterpret_cast<const float4*>(&cb.inertias[a].invInertiaWorld);
+	const float4* IB = reinterpret_cast<const float4*>(&cb.inertias[b].invInertiaWorld);
+	A.i0 = __ldg(IA), A.i1 = __ldg(IA + 1), A.i2 = __ldg(IA + 2);
+	B.i0 = __ldg(IB), B.i1 = __ldg(IB + 1), B.i2 = __ldg(IB + 2);
+	if (!solveRowCore<PHASE>(r, A, B, linVelA, angVelA, linVelB, angVelB)) return;
+	storeRowLambda<PHASE>(tilesN, tilesF, tile, lane, r);
+	if (A.pos.w != 0.f)
 	{
-		solveNormalCore(r.nId, r.p, r.bias, r.applied, c.A, c.B, linVelA, angVelA, linVelB, angVelB);
-		s.tilesN[(size_t)tile * NT_STRIDE + 6 * 32 + lane] = r.applied;
+		__stcg(&cb.vel[2 * a], linVelA);
+		__stcg(&cb.vel[2 * a + 1], angVelA);
 	}
-	else
+	if (B.pos.w != 0.f)
 	{
-		if (!solveFrictionCore(r.nId, r.p[0], r.bias, r.applied, c.A, c.B, linVelA, angVelA, linVelB, angVelB)) return;
-		s.tilesF[(size_t)tile * FT_STRIDE + 32 + lane] = r.bias;
-	}
-	if (c.A.pos.w != 0.f)
-	{
-		__stcg(&s.vel[2 * c.a], linVelA);
-		__stcg(&s.vel[2 * c.a + 1], angVelA);
-	}
-	if (c.B.pos.w != 0.f)
-	{
-		__stcg(&s.vel[2 * c.b], linVelB);
-		__stcg(&s.vel[2 * c.b + 1], angVelB);
+		__stcg(&cb.vel[2 * b], linVelB);
+		__stcg(&cb.vel[2 * b + 1], angVelB);
 	}
 }
+B3_D int4 loadTail(const float4* tilesN, unsigned int tile, int lane) { return reinterpret_cast<const int4*>(tilesN)[(size_t)tile * NT_STRIDE + NT_TAIL * 32 + lane]; }
 
 struct BlockView
 {
@@ -1252,68 +1306,101 @@ struct BlockView
 	int numColours;
 };
 
-// all colours of one block, velocities in shared memory.  Warp w owns the tiles w, w + 16, ... of the block's tile sequence
-// (the same warp every pass, so a tile's lambdas are read back by the thread that wrote them) and fetches its next tile
-// while it solves the current one.
+// all colours of one block, velocities in shared memory.  Warp w owns the tiles w, w + ITER_WARPS, ... of the block's tile
+// sequence (the same warp every pass, so a tile's lambdas are read back by the thread that wrote them) and fetches its
+// next tile into a second register set while it solves the current one; one __syncthreads() per colour.
 template <int PHASE>
-__device__ __noinline__ void solveBlockInterior(const IterArgs& s, const BlockView& v, const unsigned int* sTileOff, float4* sVel, const float4* sPose, const float4* sIner)
+__device__ __noinline__ void solveBlockInterior(float4* tilesN, float4* tilesF, unsigned int tileBase, unsigned int numTiles, int numColours,
+												const unsigned int* sTileOff, SharedBodies sb_, unsigned long long* probe)
 {
+	int probeN = 256;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	unsigned int T = (unsigned int)warp;
-	RowRegs<PHASE> cur;
-	if (T < v.numTiles) loadRowRegs<PHASE>(s, v.tileBase + T, lane, cur);
-	for (int m = 0; m < v.numColours; m++)
+	int m = 0;
+	RowRegs<PHASE> ra, rb;
+	if (T < numTiles) loadRowRegs<PHASE>(tilesN, tilesF, tileBase + T, lane, ra);
+	while (T < numTiles)
 	{
-		const unsigned int end = sTileOff[m + 1];
-		while (T < end)
+		unsigned int T2 = T + ITER_WARPS;
+		if (T2 < numTiles) loadRowRegs<PHASE>(tilesN, tilesF, tileBase + T2, lane, rb);
+
+		while (T >= sTileOff[m + 1])
 		{
-			RowRegs<PHASE> nxt;
-			const unsigned int T2 = T + ITER_WARPS;
-			if (T2 < v.numTiles) loadRowRegs<PHASE>(s, v.tileBase + T2, lane, nxt);
-			solveRowShared<PHASE>(s, v.tileBase + T, lane, cur, sVel, sPose, sIner);
-			cur = nxt;
-			T = T2;
+			__syncthreads();
+			m++;
+			if (probe && threadIdx.x == 0 && probeN < 500)
+			{
+				unsigned long long t_;
+				asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+				probe[probeN++] = (t_ << 8) | (unsigned long long)m;
+			}
 		}
-		__syncthreads();
+		if (probe && threadIdx.x == 0 && probeN < 500)
+		{
+			unsigned long long t_;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+			probe[probeN++] = (t_ << 8) | 200ull;
+		}
+		solveRowShared<PHASE>(tilesN, tilesF, tileBase + T, lane, ra, sb_);
+		if (probe && threadIdx.x == 0 && probeN < 500)
+		{
+			unsigned long long t_;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+			probe[probeN++] = (t_ << 8) | 201ull;
+		}
+		T = T2;
+		if (T >= numTiles) break;
+		T2 = T + ITER_WARPS;
+		if (T2 < numTiles) loadRowRegs<PHASE>(tilesN, tilesF, tileBase + T2, lane, ra);
+		while (T >= sTileOff[m + 1])
+		{
+			__syncthreads();
+			m++;
+		}
+		solveRowShared<PHASE>(tilesN, tilesF, tileBase + T, lane, rb, sb_);
+		T = T2;
 	}
+	for (; m < numColours; m++) __syncthreads();
 }
 
 // cross colours of one pass: global velocities, a grid barrier per colour; the next colour's rows are fetched while the
 // other CTAs arrive.  Trailing colours of at most TAIL_TILES tiles are solved by CTA 0 alone between __syncthreads().
 template <int PHASE>
-__device__ __noinline__ void solveCrossColours(const IterArgs& s, GridBarrier& bar, int Kc, int tailStart, const unsigned int* sCrossOff, unsigned int crossBase)
+__device__ __noinline__ void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, GridBarrier& bar, int Kc, int tailStart,
+											   const unsigned int* sCrossOff, unsigned int crossBase)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned int gw = (unsigned int)warp * gridDim.x + blockIdx.x;  // tiles are dealt round-robin to the CTAs
 	const unsigned int gstride = ITER_WARPS * gridDim.x;
 	RowRegs<PHASE> pre;
-	CrossPre cpre;
-	bool havePre = false;
-	if (tailStart > 0 && sCrossOff[0] + gw < sCrossOff[1])
+	int4 tail;
+	// this warp's first tile of colour 0, fetched while the other CTAs arrive
+	unsigned int t = sCrossOff[0] + gw;
+	if (tailStart > 0 && t < sCrossOff[1])
 	{
-		loadRowRegs<PHASE>(s, crossBase + sCrossOff[0] + gw, lane, pre);
-		loadCrossPre(s, crossBase + sCrossOff[0] + gw, lane, cpre);
-		havePre = true;
+		loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
+		tail = loadTail(tilesN, crossBase + t, lane);
 	}
 	bar.wait();  // (the caller arrived after publishing this CTA's velocities)
 	for (int k = 0; k < tailStart; k++)
 	{
-		for (unsigned int t = sCrossOff[k] + gw; t < sCrossOff[k + 1]; t += gstride)
+		if (t < sCrossOff[k + 1])
 		{
-			if (!havePre)
+			solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
+			// (a colour with more tiles than the grid has warps: the rest without the early fetch)
+			for (t += gstride; t < sCrossOff[k + 1]; t += gstride)
 			{
-				loadRowRegs<PHASE>(s, crossBase + t, lane, pre);
-				loadCrossPre(s, crossBase + t, lane, cpre);
+				loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
+				tail = loadTail(tilesN, crossBase + t, lane);
+				solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
 			}
-			havePre = false;
-			solveRowGlobal<PHASE>(s, crossBase + t, lane, pre, cpre);
 		}
 		bar.arrive();
-		if (k + 1 < tailStart && sCrossOff[k + 1] + gw < sCrossOff[k + 2])
+		t = sCrossOff[k + 1] + gw;
+		if (k + 1 < tailStart && t < sCrossOff[k + 2])
 		{
-			loadRowRegs<PHASE>(s, crossBase + sCrossOff[k + 1] + gw, lane, pre);
-			loadCrossPre(s, crossBase + sCrossOff[k + 1] + gw, lane, cpre);
-			havePre = true;
+			loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
+			tail = loadTail(tilesN, crossBase + t, lane);
 		}
 		bar.wait();
 	}
@@ -1323,12 +1410,12 @@ __device__ __noinline__ void solveCrossColours(const IterArgs& s, GridBarrier& b
 		{
 			for (int k = tailStart; k < Kc; k++)
 			{
-				const unsigned int t = sCrossOff[k] + (unsigned int)warp;
+				t = sCrossOff[k] + (unsigned int)warp;
 				if (t < sCrossOff[k + 1])
 				{
-					loadRowRegs<PHASE>(s, crossBase + t, lane, pre);
-					loadCrossPre(s, crossBase + t, lane, cpre);
-					solveRowGlobal<PHASE>(s, crossBase + t, lane, pre, cpre);
+					loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
+					tail = loadTail(tilesN, crossBase + t, lane);
+					solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
 				}
 				__syncthreads();
 			}
@@ -1337,14 +1424,31 @@ __device__ __noinline__ void solveCrossColours(const IterArgs& s, GridBarrier& b
 	}
 }
 
+#define B3_PROBE(i)                                                              \
+	do                                                                           \
+	{                                                                            \
+		if (s.probe && blockIdx.x == 0 && threadIdx.x == 0 && probeN < 512)      \
+		{                                                                        \
+			unsigned long long t_;                                               \
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));               \
+			s.probe[probeN++] = (t_ << 4) | (unsigned long long)(i);             \
+		}                                                                        \
+	} while (0)
 __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs s)
 {
+	int probeN = 0;
 	extern __shared__ float4 smem4[];
 	__shared__ unsigned int sTileOff[MAX_BATCHES + 1], sCrossOff[MAX_BATCHES + 1];
+	__shared__ int sNumBoundary;
 	const int slots = s.S + NSTATIC;
-	float4* sVel = smem4;                // 2 per slot
-	float4* sPose = smem4 + 2 * slots;   // 1 per slot
-	float4* sIner = smem4 + 3 * slots;   // 3 per slot
+	SharedBodies sb_;
+	sb_.lin = smem4;
+	sb_.ang = smem4 + slots;
+	sb_.inerA = smem4 + 2 * slots;
+	sb_.inerB = smem4 + 3 * slots;
+	sb_.pos = smem4 + 4 * slots;
+	int* sSlotBody = reinterpret_cast<int*>(smem4 + 5 * slots);                 // body of every slot, -1 = none
+	unsigned short* sBoundary = reinterpret_cast<unsigned short*>(sSlotBody + slots);  // slots of the bodies that have cross contacts
 	GridBarrier bar;
 	bar.init(s.bar, gridDim.x);
 
@@ -1353,10 +1457,15 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 	const int Kc = (int)s.misc[MISC_KC];
 	const bool resident = numBlocks <= (int)gridDim.x;
 	for (int i = threadIdx.x; i <= MAX_BATCHES; i += ITER_THREADS) sCrossOff[i] = s.crossTileOff[i];
+	if (threadIdx.x == 0) sNumBoundary = 0;
 	__syncthreads();
 	const unsigned int crossBase = s.tileCap - sCrossOff[MAX_BATCHES];
 	int tailStart = Kc;
 	while (tailStart > 0 && sCrossOff[tailStart] - sCrossOff[tailStart - 1] <= (unsigned int)TAIL_TILES) tailStart--;
+	CrossBodies cb;
+	cb.pose = s.pose;
+	cb.vel = s.vel;
+	cb.inertias = s.inertias;
 
 	auto view = [&](int blk) {
 		BlockView v;
@@ -1377,44 +1486,39 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 		v.numColours = kc;
 		return v;
 	};
-	// body of slot k of block blk (-1: none)
-	auto slotBody = [&](const BlockView& v, int k) -> int {
-		if (k < v.count) return (int)s.partVals[(size_t)v.blk * s.S + k];
-		if (k >= s.S && k < s.S + NSTATIC) return s.blockStatics[(size_t)v.blk * NSTATIC + (k - s.S)];
-		return -1;
-	};
-	auto loadBlock = [&](const BlockView& v, bool boundaryOnly) {
+	// everything of the block: bodies of the slots, their constants and velocities; lists the boundary slots
+	auto loadBlock = [&](const BlockView& v, bool listBoundary) {
 		for (int k = threadIdx.x; k < slots; k += ITER_THREADS)
 		{
-			const int g = slotBody(v, k);
+			int g = -1;
+			if (k < v.count)
+				g = (int)s.partVals[(size_t)v.blk * s.S + k];
+			else if (k >= s.S)
+				g = s.blockStatics[(size_t)v.blk * NSTATIC + (k - s.S)];
+			sSlotBody[k] = g;
 			if (g < 0) continue;
-			if (boundaryOnly)
-			{
-				if (k >= s.S || (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) == 0ull) continue;
-			}
-			else
-			{
-				sPose[k] = s.pose[2 * g];
-				const float4* I = reinterpret_cast<const float4*>(&s.inertias[g].invInertiaWorld);
-				sIner[3 * k] = __ldg(I);
-				sIner[3 * k + 1] = __ldg(I + 1);
-				sIner[3 * k + 2] = __ldg(I + 2);
-			}
-			sVel[2 * k] = __ldcg(&s.vel[2 * g]);
-			sVel[2 * k + 1] = __ldcg(&s.vel[2 * g + 1]);
+			const float4 ps = s.pose[2 * g];
+			const float4* I = reinterpret_cast<const float4*>(&s.inertias[g].invInertiaWorld);
+			const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+			sb_.pos[k] = ps;
+			sb_.inerA[k] = mk4(r0.x, r0.y, r0.z, r1.y);
+			sb_.inerB[k] = mk4(r1.z, r2.z, ps.w, 0.f);
+			sb_.lin[k] = __ldcg(&s.vel[2 * g]);
+			sb_.ang[k] = __ldcg(&s.vel[2 * g + 1]);
+			if (listBoundary && k < v.count && (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) != 0ull) sBoundary[atomicAdd(&sNumBoundary, 1)] = (unsigned short)k;
 		}
 	};
-	auto storeBlock = [&](const BlockView& v, bool boundaryOnly) {
+	auto storeBlock = [&](const BlockView& v) {
 		for (int k = threadIdx.x; k < v.count; k += ITER_THREADS)
 		{
-			const int g = (int)s.partVals[(size_t)v.blk * s.S + k];
-			if (boundaryOnly && (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) == 0ull) continue;
-			if (sPose[k].w == 0.f) continue;
-			__stcg(&s.vel[2 * g], sVel[2 * k]);
-			__stcg(&s.vel[2 * g + 1], sVel[2 * k + 1]);
+			const int g = sSlotBody[k];
+			if (sb_.inerB[k].z == 0.f) continue;
+			__stcg(&s.vel[2 * g], sb_.lin[k]);
+			__stcg(&s.vel[2 * g + 1], sb_.ang[k]);
 		}
 	};
 
+	B3_PROBE(0);
 	BlockView mine;
 	mine.blk = -1;
 	mine.count = 0;
@@ -1424,7 +1528,7 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 	if (resident && (int)blockIdx.x < numBlocks)
 	{
 		mine = view((int)blockIdx.x);
-		loadBlock(mine, false);
+		loadBlock(mine, true);
 		__syncthreads();
 	}
 
@@ -1438,26 +1542,47 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 			{
 				// the velocities the cross rows need are in global memory after this: resident blocks publish their boundary
 				// bodies (the others never left global memory)
-				if (mine.blk >= 0) storeBlock(mine, true);
-				bar.arrive();
-				if (phase == 0)
-					solveCrossColours<0>(s, bar, Kc, tailStart, sCrossOff, crossBase);
-				else
-					solveCrossColours<1>(s, bar, Kc, tailStart, sCrossOff, crossBase);
+				B3_PROBE(1);
 				if (mine.blk >= 0)
 				{
-					loadBlock(mine, true);
+					const int nB = sNumBoundary;
+					for (int i = threadIdx.x; i < nB; i += ITER_THREADS)
+					{
+						const int k = sBoundary[i];
+						const int g = sSlotBody[k];
+						__stcg(&s.vel[2 * g], sb_.lin[k]);
+						__stcg(&s.vel[2 * g + 1], sb_.ang[k]);
+					}
+				}
+				B3_PROBE(2);
+				bar.arrive();
+				if (phase == 0)
+					solveCrossColours<0>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
+				else
+					solveCrossColours<1>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
+				B3_PROBE(3);
+				if (mine.blk >= 0)
+				{
+					const int nB = sNumBoundary;
+					for (int i = threadIdx.x; i < nB; i += ITER_THREADS)
+					{
+						const int k = sBoundary[i];
+						const int g = sSlotBody[k];
+						sb_.lin[k] = __ldcg(&s.vel[2 * g]);
+						sb_.ang[k] = __ldcg(&s.vel[2 * g + 1]);
+					}
 					__syncthreads();
 				}
+				B3_PROBE(4);
 			}
 			if (resident)
 			{
 				if (mine.blk >= 0)
 				{
 					if (phase == 0)
-						solveBlockInterior<0>(s, mine, sTileOff, sVel, sPose, sIner);
+						solveBlockInterior<0>(s.tilesN, s.tilesF, mine.tileBase, mine.numTiles, mine.numColours, sTileOff, sb_, (blockIdx.x == 0 && iter == 1) ? s.probe : nullptr);
 					else
-						solveBlockInterior<1>(s, mine, sTileOff, sVel, sPose, sIner);
+						solveBlockInterior<1>(s.tilesN, s.tilesF, mine.tileBase, mine.numTiles, mine.numColours, sTileOff, sb_, nullptr);
 				}
 			}
 			else
@@ -1469,26 +1594,29 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 					loadBlock(v, false);
 					__syncthreads();
 					if (phase == 0)
-						solveBlockInterior<0>(s, v, sTileOff, sVel, sPose, sIner);
+						solveBlockInterior<0>(s.tilesN, s.tilesF, v.tileBase, v.numTiles, v.numColours, sTileOff, sb_, nullptr);
 					else
-						solveBlockInterior<1>(s, v, sTileOff, sVel, sPose, sIner);
-					storeBlock(v, false);
+						solveBlockInterior<1>(s.tilesN, s.tilesF, v.tileBase, v.numTiles, v.numColours, sTileOff, sb_, nullptr);
+					storeBlock(v);
 				}
 			}
 		}
 	}
+	B3_PROBE(5);
 	if (mine.blk >= 0)
 	{
 		__syncthreads();
-		storeBlock(mine, false);
+		storeBlock(mine);
 	}
+	B3_PROBE(6);
 }
 
 // ================================================================ export (b3b200_get_constraints)
 // tiles -> b3ContactConstraint4 records (reference layout), compacted with one atomic cursor; the host sorts them by batch
 __global__ void __launch_bounds__(256) solverExportKernel(const float4* __restrict__ tilesN, const float4* __restrict__ tilesF, unsigned int tileCap,
 														  const unsigned int* __restrict__ misc, const unsigned int* __restrict__ crossTileOff,
-														  b3b200_constraint4* __restrict__ out, unsigned int* __restrict__ cursor, unsigned int capacity)
+														  const b3b200_contact4* __restrict__ contacts, b3b200_constraint4* __restrict__ out,
+														  unsigned int* __restrict__ cursor, unsigned int capacity)
 {
 	const unsigned int interiorTiles = misc[MISC_TILE_CURSOR];
 	const unsigned int crossTiles = crossTileOff[MAX_BATCHES];
@@ -1499,7 +1627,7 @@ __global__ void __launch_bounds__(256) solverExportKernel(const float4* __restri
 		const unsigned int tile = t < interiorTiles ? t : tileCap - crossTiles + (t - interiorTiles);
 		const float4* tn = tilesN + (size_t)tile * NT_STRIDE + lane;
 		const float4* tf = tilesF + (size_t)tile * FT_STRIDE + lane;
-		const int4 tail = reinterpret_cast<const int4*>(tn)[7 * 32];
+		const int4 tail = reinterpret_cast<const int4*>(tn)[NT_TAIL * 32];
 		const bool valid = tail.x >= 0;
 		const unsigned int m = __ballot_sync(0xffffffffu, valid);
 		if (!m) continue;
@@ -1510,19 +1638,24 @@ __global__ void __launch_bounds__(256) solverExportKernel(const float4* __restri
 		float4* dw = reinterpret_cast<float4*>(&out[slot]);
 		const float4 nId = tn[0];
 		dw[0] = mk4(nId.x, nId.y, nId.z, 0.7f);
-		float jac[4];
+		// m_worldPos: the points of the contact the row was built from (the tiles keep the angular Jacobians instead)
+		const float4* cw = reinterpret_cast<const float4*>(&contacts[tail.w]);
+		const float npoints = cw[4].w;
+		float jac[4], bb[4];
 #pragma unroll
 		for (int i = 0; i < 4; i++)
 		{
-			const float4 p = tn[(1 + i) * 32];
-			jac[i] = p.w;
-			dw[1 + i] = mk4(p.x, p.y, p.z, 0.f);
+			jac[i] = tn[(1 + 2 * i) * 32].w;
+			bb[i] = tn[(2 + 2 * i) * 32].w;
+			const float4 p = cw[i];
+			dw[1 + i] = ((float)i < npoints) ? mk4(p.x, p.y, p.z, 0.f) : mk4(0, 0, 0, 0);
 		}
-		dw[5] = tf[0];
+		const float4 cf = tf[0], t0 = tf[32], t1 = tf[64], fl = tf[FT_LAMBDA * 32];
+		dw[5] = mk4(cf.x, cf.y, cf.z, 0.f);
 		dw[6] = mk4(jac[0], jac[1], jac[2], jac[3]);
-		dw[7] = tn[5 * 32];
-		dw[8] = tn[6 * 32];
-		dw[9] = tf[32];
+		dw[7] = mk4(bb[0], bb[1], bb[2], bb[3]);
+		dw[8] = tn[NT_LAMBDA * 32];
+		dw[9] = mk4(t0.w, t1.w, fl.x, fl.y);
 		int4 o;
 		o.x = tail.x;
 		o.y = tail.y;
@@ -1623,7 +1756,7 @@ int launchSolverSetup(World* w)
 		if (!w->solverAttrSet)
 		{
 			B3_CUDA_CHECK(cudaFuncSetAttribute(solverBlockSetupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float4) * 6 * (S_MAX + NSTATIC))));
+			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITER_SMEM_MAX)));
 			w->solverAttrSet = true;
 		}
 		solverBlockSetupKernel<<<std::min(B, w->smCount * 2), SETUP_THREADS, smem, st>>>(s);
@@ -1662,8 +1795,9 @@ int launchSolverIterate(World* w)
 	s.iterations = w->solverIterations;
 	s.S = w->partS;
 	s.numBlocksMax = w->partBlocksMax;
+	s.probe = w->dSolverProbe.ptr;  // nullptr unless b3b200_debug_solver_probe armed it
 	w->soaDirty = true;
-	const size_t smem = sizeof(float4) * 6 * (size_t)(w->partS + NSTATIC);
+	const size_t smem = (size_t)ITER_SMEM_PER_SLOT * (size_t)(w->partS + NSTATIC);
 	// one CTA per SM at most (cooperative: all CTAs co-resident); small worlds use as many CTAs as they have blocks
 	const int grid = std::max(1, std::min(w->smCount, w->partBlocksMax));
 	dim3 g(grid), b(ITER_THREADS);
@@ -1690,7 +1824,7 @@ int exportConstraints(World* w, std::vector<b3b200_constraint4>& out, std::vecto
 	B3_TRY(cursor.reserve(1));
 	B3_CUDA_CHECK(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned int), w->stream));
 	solverExportKernel<<<w->smCount * 4, 256, 0, w->stream>>>(w->dTilesN.ptr, w->dTilesF.ptr, (unsigned int)tileCapacity(w, w->partBlocksMax), w->solverMisc,
-															 w->dCrossTileOff.ptr, tmp.ptr, cursor.ptr, nContacts);
+															 w->dCrossTileOff.ptr, w->dContacts.ptr, tmp.ptr, cursor.ptr, nContacts);
 	B3_LAUNCH_CHECK();
 	unsigned int n = 0;
 	B3_CUDA_CHECK(cudaMemcpyAsync(&n, cursor.ptr, sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));

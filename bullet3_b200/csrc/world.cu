@@ -930,6 +930,21 @@ extern "C" int b3b200_get_work_counters(b3b200_world* w, int* dst, int n)
 	for (int i = 0; i < n; i++) dst[i] = (int)c[i];
 	return 0;
 }
+// development aid (not part of include/b3b200.h): arm (dst == nullptr) or read back the solver kernel's globaltimer stamps
+extern "C" int b3b200_debug_solver_probe(b3b200_world* w, unsigned long long* dst, int n)
+{
+	W_CHECK(w);
+	if (!dst)
+	{
+		B3_TRY(w->dSolverProbe.reserve(512));
+		B3_CUDA_CHECK(cudaMemsetAsync(w->dSolverProbe.ptr, 0, 512 * sizeof(unsigned long long), w->stream));
+		return 0;
+	}
+	if (!w->dSolverProbe.ptr || n > 512) return B3B200_ERR_STATE;
+	B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dSolverProbe.ptr, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
 extern "C" int b3b200_enable_stage_timing(b3b200_world* w, int enable)
 {
 	if (!w) return B3B200_ERR_INVALID;
