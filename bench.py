@@ -30,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DT = 1.0 / 60.0
 ITERS = 10
+METRIC = "bodies*steps/s (256k convex scene)"  # one string for both arms: the driver divides lines with equal metrics
 SETTLE_STEPS = 250  # untimed: the 16-layer lattice drops and comes to rest (contacts/body plateaus) before anything is measured
 LAYERS = 16
 
@@ -41,7 +42,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bodies-side", type=int, default=64, help="scene is side^3 bodies (64 -> 262 144)")
-    ap.add_argument("--cpu-sample-side", type=int, default=16, help="side of the bounded CPU-baseline sample scene")
+    ap.add_argument("--ref-bodies", type=int, default=8192, help="--impl reference: bodies of the scene region one reference step simulates")
+    ap.add_argument("--bt2-bodies", type=int, default=65536, help="bodies of the scene region the Bullet 2 MT baseline steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -101,85 +103,192 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------- CPU arms
-def cpu_pipeline_step(oa, lib, prefix, bodies, sh, inertias, iters):
-    """one step of the path on the CPU: AABBs -> pairs -> SAT/clip contacts -> PGS -> integrate.
-    `lib/prefix` select the compiled reference (ref_) or the oracle port (orc_) where both exist."""
-    aabbs = oa.update_aabbs(lib, prefix, bodies, sh)
-    small = np.nonzero(bodies["invMass"] != 0)[0].astype(np.int32)
-    large = np.nonzero(bodies["invMass"] == 0)[0].astype(np.int32)
-    # pair finding: sort-and-sweep port (the reference's host twin is O(N^2) brute force)
-    _, pairs = oa.brute_force_pairs(oa.oracle(), "orc_", aabbs, small, large, 16 * len(bodies), fn="sweep_pairs")
-    cap = 24 * len(bodies)
-    if prefix == "ref_":
-        # convex x convex through the compiled reference header path; compound children and the trimesh through the port
-        hull = sh.collidables["shapeType"][bodies["collidableIdx"]] == 3
-        both = hull[pairs["x"]] & hull[pairs["y"]]
-        c1, _ = oa.convex_contacts_ref(pairs[both], bodies, sh, cap)
-        c2 = oa.contacts_oracle(pairs[~both], bodies, sh, -1e30, 0.02, cap)
-    else:
-        c1 = oa.contacts_oracle(pairs, bodies, sh, -1e30, 0.02, cap)
-        c2 = c1[:0]
-    c3, _ = oa.concave_contacts_oracle(pairs, bodies, sh, aabbs, cap)
-    contacts = np.concatenate([c1, c2, c3])
-    solved, _, _, _ = oa.oracle_pgs_step_velocities(contacts, bodies, inertias, 0, iters)
-    return oa.integrate(lib, prefix, solved, DT, 0.99, (0.0, -9.8, 0.0)), len(pairs), len(contacts)
+def settled_state(side):
+    """(full-lattice body array, True) after SETTLE_STEPS steps on the GPU when there is one -- state PREPARATION for the
+    CPU arms, outside every timed region -- else (None, False): the CPU arms then start from the unsettled lattice"""
+    try:
+        dev = os.environ.get("B3B200_SETTLED_NPY")  # development aid: a state saved by tools/dump_settled.py
+        if dev and os.path.exists(dev):
+            return np.load(dev), True
+        import torch
 
+        if not torch.cuda.is_available():
+            return None, False
+        from bullet3_b200 import capi, scenes
 
-def make_cpu_sample(side, settle_on_gpu):
-    """the bench scene recipe at side^3 bodies; state after SETTLE_STEPS steps when a GPU is there"""
-    from bullet3_b200 import capi, scenes
-    import oracle_api as oa
-
-    dev = 0 if settle_on_gpu else -1
-    w = capi.World(bench_config(capi, side), device=dev)
-    scenes.bench_config4_scene(w, *scene_dims(side))
-    t = w.tables()
-    bodies = t["bodies"]
-    if settle_on_gpu:
+        w = capi.World(bench_config(capi, side))
+        scenes.bench_config4_scene(w, *scene_dims(side))
         w.upload()
         w.set_solver(capi.SOLVER_PGS, ITERS)
         w.step_n(DT, SETTLE_STEPS)
         bodies = w.bodies()
-    w.close()
-    return bodies, oa.Shapes(t), t["inertias"]
+        w.close()
+        return bodies, True
+    except Exception:
+        return None, False
 
 
-def run_cpu_arm(side, threads, steps, warmup, use_ref, settle_on_gpu):
-    """`threads` independent sample worlds stepped concurrently (the path shards by world);
-    returns (bodies*steps/s, ms per step of one sample world, description)"""
+def region_of(side, bodies, target):
+    """indices (into the lattice bodies, 0-based without the mesh) of a square x-z window around the centre of the pile that
+    holds about `target` bodies: one connected piece of the real scene, all 16 layers"""
+    nx, ny, nz = scene_dims(side)
+    n = nx * ny * nz
+    if target >= n:
+        return np.arange(n)
+    if bodies is not None:
+        x, z = bodies["pos"][1:, 0], bodies["pos"][1:, 2]
+    else:
+        i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+        x, z = (2.2 * i).reshape(-1).astype(np.float32), (2.2 * k).reshape(-1).astype(np.float32)
+    cx, cz = np.median(x), np.median(z)
+    d = np.maximum(np.abs(x - cx), np.abs(z - cz))
+    half = np.sort(d)[target - 1]
+    return np.nonzero(d <= half)[0]
+
+
+def build_region_world(world, side, bodies, keep):
+    """register the bench scene recipe restricted to `keep` (same shapes, same mesh) with the poses of `bodies` (or the lattice)"""
+    from bullet3_b200 import scenes
+
+    poses = None
+    if bodies is not None:
+        pos = np.ascontiguousarray(bodies["pos"][1:]).copy()
+        pos[:, 3] = 0.0
+        poses = (pos, np.ascontiguousarray(bodies["quat"][1:]))
+    scenes.bench_config4_scene(world, *scene_dims(side), keep=keep, poses=poses)
+
+
+def run_reference_arm(side, steps, warmup, target_bodies):
+    """the reference's own b3GpuRigidBodyPipeline::stepSimulation, UNMODIFIED, with every host-twin switch on (oracle/_ref/
+    libb3refcl.so: gCalcWorldSpaceAabbOnCpu, gUseDbvt, CHECK_ON_HOST contact loop + concave host twins, the gCpu* solver stages,
+    gIntegrateOnCpu), stepping one connected region of the settled scene.  Returns (value, ms/step, description, cores)."""
     import oracle_api as oa
 
-    use_ref = use_ref and oa.ref_available()
-    lib, prefix = (oa.ref(), "ref_") if use_ref else (oa.oracle(), "orc_")
-    bodies0, sh, inertias = make_cpu_sample(side, settle_on_gpu)
-    n = len(bodies0)
-    state = [bodies0.copy() for _ in range(threads)]
-    stats = [None] * threads
+    if not oa.refcl_available():
+        raise SystemExit("oracle/_ref/libb3refcl.so is missing (built by __graft_entry__.build() where /root/reference exists)")
+    from bullet3_b200 import capi
 
-    def work(i, k):
-        b = state[i]
-        for _ in range(k):
-            b, npairs, ncontacts = cpu_pipeline_step(oa, lib, prefix, b, sh, inertias, ITERS)
-            stats[i] = (npairs, ncontacts)
-        state[i] = b
+    bodies, settled = settled_state(side)
+    keep = region_of(side, bodies, target_bodies)
+    w = oa.RefPipeline(bench_config(capi, side))
+    build_region_world(w, side, bodies, keep)
+    w.upload()
+    if bodies is not None:
+        state = w.bodies()
+        for f in ("linVel", "angVel"):
+            state[f][1:] = bodies[f][1:][keep]
+        w.set_bodies(state)
+    n = w.num_bodies
+    out = w.step(DT, warmup) if warmup else [0, 0, 0]
+    w.profile_zones()
+    t0 = time.perf_counter()
+    out = w.step(DT, steps)
+    el = time.perf_counter() - t0
+    zones = w.profile_zones()
+    w.close()
+    desc = ("UNMODIFIED reference b3GpuRigidBodyPipeline::stepSimulation with every host-twin flag on (oracle/_ref/libb3refcl.so over a host-memory "
+            "fake OpenCL): AABBs on CPU, b3DynamicBvhBroadphase, CHECK_ON_HOST contacts (hulls, compounds, trimesh), b3GpuPgsContactSolver host "
+            "stages -> b3Solver::solveContactConstraintHost (its hard-coded 4 iterations), integrate on CPU; single-threaded by construction; "
+            "one world = a connected %d-body region (all 16 layers, %s) of the %d-body scene on the full mesh, %d warm-up + %d timed steps; "
+            "%d DBVT pairs / %d contacts in the last step.  The full 262 145-body world takes 44 s per step through this path even before it "
+            "has settled (measured; its host batching scans all bodies per cell and batch), so the region is the bounded sample" %
+            (n, "settled state of the GPU run" if settled else "UNSETTLED lattice: no GPU for state preparation", side ** 3 + 1, warmup, steps, out[0], out[1]))
+    top = sorted(zones.items(), key=lambda kv: -kv[1])[:8]
+    desc += ".  Its own B3_PROFILE zones, ms per step (inclusive): " + ", ".join("%s %.0f" % (k, v / steps * 1e3) for k, v in top)
+    return n * steps / el, el / steps * 1e3, desc, 1
 
-    def run(k):
-        ts = [threading.Thread(target=work, args=(i, k)) for i in range(threads)]
-        t0 = time.perf_counter()
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        return time.perf_counter() - t0
 
-    run(warmup)
-    el = run(steps)
-    value = n * steps * threads / el
-    desc = ("%s: %d independent %d-body sample worlds of the bench recipe (one per thread), %d steps each: "
-            "AABBs, sweep pair finding, SAT+clip contacts (hulls, compound children, trimesh), coloured PGS %d it., integrate; %d pairs / %d contacts per world" %
-            ("compiled reference (oracle/_ref: b3UpdateAabbs/b3ContactConvexConvexSAT/b3IntegrateTransforms) + oracle-port compound/trimesh contacts and solver" if use_ref
-             else "oracle port", threads, n, steps, ITERS, stats[0][0], stats[0][1]))
-    return value, el / steps * 1e3, desc, ("reference" if use_ref else "port")
+def dump_bt2_scene(path, tables, bodies):
+    """scene file of oracle/bt2/bt2mt_bench.cpp: the collidables as point clouds / compounds of them / one triangle mesh"""
+    col, convex, verts = tables["collidables"], tables["convex"], tables["vertices"]
+    faces, indices, children = tables["faces"], tables["indices"], tables["child_shapes"]
+    mesh_v, mesh_i = np.zeros((0, 3), np.float32), np.zeros(0, np.int32)
+    with open(path, "wb") as f:
+        f.write(np.array([0x62743273, len(col), len(bodies), 0, 0], np.int32).tobytes())  # header patched below
+        for c in col:
+            st, si = int(c["shapeType"]), int(c["shapeIndex"])
+            if st == 3:  # SHAPE_CONVEX_HULL
+                cv = convex[si]
+                pts = np.ascontiguousarray(verts[cv["vertexOffset"]: cv["vertexOffset"] + cv["numVertices"]]).view(np.float32).reshape(-1, 4)[:, :3]
+                f.write(np.array([0, len(pts)], np.int32).tobytes())
+                f.write(np.ascontiguousarray(pts, np.float32).tobytes())
+            elif st == 6:  # SHAPE_COMPOUND_OF_CONVEX_HULLS: numChildShapes / first child ride in the collidable's unions
+                nch, first = int(c["numChildShapes"]), si
+                f.write(np.array([1, nch], np.int32).tobytes())
+                for ch in children[first: first + nch]:
+                    f.write(np.array([int(ch["shapeIndex"])], np.int32).tobytes())
+                    f.write(np.concatenate([np.asarray(ch["childPosition"], np.float32).reshape(-1)[:3],
+                                            np.asarray(ch["childOrientation"], np.float32).reshape(-1)[:4]]).astype(np.float32).tobytes())
+            else:
+                f.write(np.array([0, 0], np.int32).tobytes())
+                if st == 5:  # SHAPE_CONCAVE_TRIMESH: one convex-table entry whose faces are the triangles
+                    cv = convex[si]
+                    mesh_v = np.ascontiguousarray(verts[cv["vertexOffset"]: cv["vertexOffset"] + cv["numVertices"]]).view(np.float32).reshape(-1, 4)[:, :3]
+                    fs = faces[cv["faceOffset"]: cv["faceOffset"] + cv["numFaces"]]
+                    mesh_i = np.concatenate([indices[o: o + 3] for o in fs["indexOffset"]]).astype(np.int32) if len(fs) else mesh_i
+        f.write(np.ascontiguousarray(mesh_v, np.float32).tobytes())
+        f.write(np.ascontiguousarray(mesh_i, np.int32).tobytes())
+        shape_type = col["shapeType"][bodies["collidableIdx"]]
+        rec = np.zeros(len(bodies), np.dtype([("shape", np.int32), ("v", np.float32, 14)]))
+        rec["shape"] = np.where(shape_type == 5, -1, bodies["collidableIdx"])
+        rec["v"][:, 0] = np.where(bodies["invMass"] != 0, 1.0 / np.where(bodies["invMass"] != 0, bodies["invMass"], 1.0), 0.0)
+        rec["v"][:, 1:4] = bodies["pos"][:, :3]
+        rec["v"][:, 4:8] = bodies["quat"]
+        rec["v"][:, 8:11] = bodies["linVel"][:, :3]
+        rec["v"][:, 11:14] = bodies["angVel"][:, :3]
+        f.write(rec.tobytes())
+        f.seek(0)
+        f.write(np.array([0x62743273, len(col), len(bodies), len(mesh_v), len(mesh_i)], np.int32).tobytes())
+
+
+def run_bt2mt(tables, bodies, warmup, steps, threads=0):
+    """Bullet 2 btDiscreteDynamicsWorldMt + btDbvtBroadphase + btCollisionDispatcherMt + btSequentialImpulseConstraintSolverMt assembled like
+    examples/MultiThreadedDemo/CommonRigidBodyMTBase.cpp:518-567, from the unmodified reference sources (oracle/_ref/bt2mt_bench)"""
+    exe = os.path.join(ROOT, "oracle", "_ref", "bt2mt_bench")
+    if not os.path.exists(exe):
+        return None
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "scene.bin")
+        dump_bt2_scene(path, tables, bodies)
+        r = subprocess.run([exe, path, str(warmup), str(steps), str(ITERS), str(threads)], capture_output=True, text=True, timeout=900)
+    if r.returncode != 0:
+        return None
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def run_cpu_pipeline_config1(steps=600):
+    """BASELINE configs[0]: 1 000 unit boxes (10 x 10 x 10) on a static 400-box through the reference's b3CpuRigidBodyPipeline
+    (+ b3CpuNarrowPhase + b3DynamicBvhBroadphase; it has no contact solver), 600 steps at 1/60 s, single thread by construction"""
+    import oracle_api as oa
+    from bullet3_b200 import capi, scenes
+
+    if not oa.ref_available():
+        return None
+    w = oa.RefCpuPipeline(capi.default_config(2048))
+    scenes.box_stack(w, 10, 10, 10)
+    n = w.num_bodies
+    t0 = time.perf_counter()
+    w.step(DT, steps)
+    el = time.perf_counter() - t0
+    w.close()
+    return {"value": n * steps / el, "unit": "bodies*steps/s", "cores": 1, "kind": "reference", "ms_per_step": el / steps * 1e3,
+            "sample": "BASELINE configs[0]: %d bodies (10x10x10 unit boxes + static ground box), b3CpuRigidBodyPipeline::stepSimulation x %d "
+                      "(AABBs, b3DynamicBvhBroadphase, b3CpuNarrowPhase SAT contacts, integrate; the reference's CPU pipeline has no solver)" % (n, steps)}
+
+
+def ncu_traffic(kernel):
+    """dram bytes read + written per launch of `kernel` from the committed ncu --set full summary of the CURRENT build
+    (profiles/r02_solver_ncu_summary.txt, written by tools/ncu_summary.py from the .ncu-rep); None when the file has no such line"""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r02_solver_ncu_summary.txt")):
+            p = line.split()
+            if len(p) >= 3 and p[0] == "traffic" and p[1] == kernel:
+                return float(p[2])
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------- main
@@ -193,16 +302,13 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        import torch
-
-        settle = torch.cuda.is_available()
-        value, ms, desc, kind = run_cpu_arm(a.cpu_sample_side, cores, max(1, a.steps // 10), max(1, a.warmup // 5), True, settle)
+        value, ms, desc, used = run_reference_arm(a.bodies_side, a.steps, a.warmup, a.ref_bodies)
         print(json.dumps({
-            "impl": "reference", "metric": "bodies*steps/s (256k convex scene recipe)", "value": value, "unit": "bodies*steps/s",
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "bodies*steps/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, world_size),
-            "cpu_baseline": {"value": value, "unit": "bodies*steps/s", "cores": cores, "kind": kind, "sample": desc},
+            "cpu_baseline": {"value": value, "unit": "bodies*steps/s", "cores": used, "kind": "reference", "sample": desc, "host_cores": cores},
             "e2e": {"value": value, "unit": "bodies*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -249,7 +355,7 @@ def main():
     # ---- per-stage timing + counters (separate pass, CUDA events between stages on the same stream)
     w.enable_stage_timing(True)
     stage = np.zeros(8)
-    nst = 10
+    nst = 16
     for _ in range(nst):
         w.step(DT)
         stage += w.stage_timings()
@@ -303,27 +409,27 @@ def main():
                       "frac_of_hbm_peak": stage_bytes[k] / (stage_ms[k] * 1e-3) / 1e9 / peak if stage_ms[k] > 0 else 0.0} for k in stage_ms}
         # dominant KERNEL: the SAT kernel (timed alone by its own pair of events) or the solver iteration kernel (a
         # single-kernel stage).  Algorithmic bytes per launch: SAT = 112 B per work item (16 B item +
-        # two 32-B pose records + 32 B appended item and axis); iterations = 2*I*192*C + 96*N.
-        # `traffic` = dram bytes read + written by that kernel in the ncu --set full capture of this scene
-        # (profiles/r01_np_config4_ncu_summary.txt), per launch.
+        # two 32-B pose records + 32 B appended item and axis); iterations = 2*I*192*C + 96*N (SURVEY 8(d)).
+        # `traffic` = dram bytes read + written per launch of that kernel, parsed from the committed ncu --set full summary
+        # of this build (profiles/r02_solver_ncu_summary.txt); null when the summary has no line for the kernel.
         sat_items = int(ctr[7])
-        kern = {"satKernel": {"ms": float(stage[7]), "alg_bytes": 112.0 * sat_items, "traffic": 64.1e6,
-                              "note": "FP32-issue bound, not HBM bound: ncu sm__throughput 78 % of peak issue rate, L1 hit 94 %"},
-                "solverIterateKernel": {"ms": float(stage[4]), "alg_bytes": stage_bytes["solver_iterate"], "traffic": 397.4e6,
-                                        "note": "grid-barrier latency bound: 2*I*batches phases"}}
+        kern = {"satKernel": {"ms": float(stage[7]), "alg_bytes": 112.0 * sat_items,
+                              "note": "FP32-issue bound, not HBM bound (ncu: sm__throughput 78 % of peak issue rate, L1 hit 94 %)"},
+                "solverIterateKernel": {"ms": float(stage[4]), "alg_bytes": stage_bytes["solver_iterate"],
+                                        "note": "latency bound: per pass %d grid barriers (batches of contacts between blocks) + the per-block batch loop in shared memory" % int(ctr[3])}}
         domk = max(kern, key=lambda k: kern[k]["ms"])
         dk = kern[domk]
         dk_gbs = dk["alg_bytes"] / (dk["ms"] * 1e-3) / 1e9 if dk["ms"] > 0 else 0.0
         out = {
-            "metric": "bodies*steps/s (256k convex scene)", "value": value, "unit": "bodies*steps/s", "n_gpus": world_size, "steps": a.steps,
+            "metric": METRIC, "value": value, "unit": "bodies*steps/s", "n_gpus": world_size, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(a, world_size),
-            "counts": {"bodies": nbodies, "pairs": P, "contacts": Cn, "batches": nb, "colour_rounds": int(ctr[3]), "overflow_flags": int(ctr[4])},
+            "counts": {"bodies": nbodies, "pairs": P, "contacts": Cn, "batches": nb, "cross_block_batches": int(ctr[3]), "overflow_flags": int(ctr[4])},
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": domk, "achieved": dk_gbs, "peak": peak, "unit": "GB/s", "frac": dk_gbs / peak,
-                         "traffic": dk["traffic"], "peak_source": peak_src, "kernel_ms": dk["ms"], "alg_bytes_per_launch": dk["alg_bytes"],
+                         "traffic": ncu_traffic(domk), "peak_source": peak_src, "kernel_ms": dk["ms"], "alg_bytes_per_launch": dk["alg_bytes"],
                          "note": "dominant kernel, timed live with CUDA events on the world's stream; " + dk["note"],
-                         "other_kernel": {k: {"ms": v["ms"], "gbs": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0}
+                         "other_kernel": {k: {"ms": v["ms"], "gbs": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0, "traffic": ncu_traffic(k)}
                                           for k, v in kern.items() if k != domk}},
             "e2e": {"value": e2e_value, "unit": "bodies*steps/s", "h2d_bytes_per_step": int(host_bodies.nbytes) * world_size,
                     "d2h_bytes_per_step": int(host_bodies.nbytes) * world_size, "ms_per_step": e2e_s / e2e_steps * 1e3,
@@ -331,8 +437,25 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not a.no_cpu_baseline and world_size == 1:
-            v, ms, desc, kind = run_cpu_arm(a.cpu_sample_side, 1, 2, 1, False, True)
-            out["cpu_baseline"] = {"value": v, "unit": "bodies*steps/s", "cores": 1, "kind": kind, "sample": desc, "ms_per_step_sample": ms}
+            # the CPU baselines north_star names, on this box's host cores, bounded samples (reported, not a target)
+            tables = w.tables()
+            keep = region_of(side, host_bodies, a.bt2_bodies)
+            sel = np.concatenate([[0], keep + 1])
+            bt = run_bt2mt(tables, host_bodies[sel], 2, 5, 0)
+            extra = []
+            if bt:
+                out["cpu_baseline"] = {"value": bt["bodies"] * 1e3 / bt["ms_per_step"], "unit": "bodies*steps/s", "cores": bt["threads"], "kind": "reference",
+                                       "ms_per_step_sample": bt["ms_per_step"],
+                                       "sample": "Bullet 2 btDiscreteDynamicsWorldMt + btDbvtBroadphase + btCollisionDispatcherMt(40) + btConstraintSolverPoolMt + "
+                                                 "btSequentialImpulseConstraintSolverMt (CommonRigidBodyMTBase.cpp:518-567; unmodified reference sources, -DBT_THREADSAFE=1, "
+                                                 "oracle/_ref/bt2mt_bench), %d threads, %d iterations, no sleeping: a connected %d-body region (all layers) of the settled "
+                                                 "scene on the full mesh, 2 warm-up + %d timed steps, %d manifolds" % (bt["threads"], bt["iterations"], bt["bodies"], bt["steps"], bt["manifolds"])}
+            c1 = run_cpu_pipeline_config1(600)
+            if c1:
+                extra.append(dict(c1, name="b3CpuRigidBodyPipeline, BASELINE configs[0]"))
+                if "cpu_baseline" not in out:
+                    out["cpu_baseline"] = c1
+            out["cpu_baselines_other"] = extra
         print(json.dumps(out))
     if world_size > 1:
         dist.destroy_process_group()

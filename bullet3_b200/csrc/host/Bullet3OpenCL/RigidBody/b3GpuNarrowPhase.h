@@ -22,6 +22,7 @@ protected:
 	int m_device;
 	int m_static0Index;
 	mutable b3AlignedObjectArray<b3RigidBodyData> m_bodiesCPU;
+	mutable bool m_cpuEdited = false;  // m_bodiesCPU holds setObject*Cpu edits that writeAllBodiesToGpu has to send
 	mutable b3AlignedObjectArray<b3Collidable> m_collidablesCPU;
 	mutable b3AlignedObjectArray<b3SapAabb> m_localAabbsCPU;
 	mutable b3AlignedObjectArray<b3Contact4Data> m_contactsCPU;

@@ -252,7 +252,17 @@ int b3GpuNarrowPhase::registerRigidBody(int collidableIndex, float mass, const f
 	if (r == 0 && mass == 0.f) m_static0Index = 0;
 	return r;
 }
-void b3GpuNarrowPhase::writeAllBodiesToGpu() { checked(b3b200_upload(m_world), "writeAllBodiesToGpu"); }
+void b3GpuNarrowPhase::writeAllBodiesToGpu()
+{
+	// b3GpuNarrowPhase::writeAllBodiesToGpu (b3GpuNarrowPhase.cpp:970-979) sends m_bodyBufferCPU: the wrapper's CPU copy is the
+	// authority for the bodies it holds (setObjectTransformCpu / setObjectVelocityCpu edit it), the world's upload only adds
+	// what was registered since (b3b200_upload keeps the device state of the bodies that are already there)
+	checked(b3b200_upload(m_world), "writeAllBodiesToGpu");
+	const int n = b3b200_num_bodies(m_world);
+	if (m_cpuEdited && m_bodiesCPU.size() == n && n > 0)
+		checked(b3b200_write_bodies(m_world, (const b3b200_rigid_body*)&m_bodiesCPU[0], n), "writeAllBodiesToGpu");
+	m_cpuEdited = false;
+}
 void b3GpuNarrowPhase::reset()
 {
 	b3b200_reset(m_world);
@@ -263,14 +273,20 @@ void b3GpuNarrowPhase::readbackAllBodiesToCpu()
 	int n = b3b200_num_bodies(m_world);
 	m_bodiesCPU.resize(n);
 	if (n) checked(b3b200_readback_bodies(m_world, (b3b200_rigid_body*)&m_bodiesCPU[0], n), "readbackAllBodiesToCpu");
+	m_cpuEdited = false;
 }
 const b3RigidBodyData* b3GpuNarrowPhase::getBodiesCpu() const
 {
 	if (m_bodiesCPU.size() != b3b200_num_bodies(m_world))
 	{
+		// first use, or bodies were registered since: the world's table = the current device state of the uploaded bodies +
+		// the registration state of the new ones (b3b200_get_table refreshes it from the device)
 		int n = b3b200_num_bodies(m_world);
-		m_bodiesCPU.resize(n);
-		if (n) b3b200_get_table(m_world, B3B200_TBL_BODIES, &m_bodiesCPU[0], n, &n);
+		b3AlignedObjectArray<b3RigidBodyData> fresh;
+		fresh.resize(n);
+		if (n) b3b200_get_table(m_world, B3B200_TBL_BODIES, &fresh[0], n, &n);
+		for (int i = 0; i < m_bodiesCPU.size() && i < n && m_cpuEdited; i++) fresh[i] = m_bodiesCPU[i];  // keep pending edits
+		m_bodiesCPU = fresh;
 	}
 	return m_bodiesCPU.size() ? &m_bodiesCPU[0] : 0;
 }
@@ -302,6 +318,7 @@ void b3GpuNarrowPhase::setObjectTransformCpu(float* position, float* orientation
 	}
 	m_bodiesCPU[bodyIndex].m_pos = b3MakeVector3(position[0], position[1], position[2]);
 	m_bodiesCPU[bodyIndex].m_quat.setValue(orientation[0], orientation[1], orientation[2], orientation[3]);
+	m_cpuEdited = true;
 }
 void b3GpuNarrowPhase::setObjectVelocityCpu(float* linVel, float* angVel, int bodyIndex)
 {
@@ -313,12 +330,27 @@ void b3GpuNarrowPhase::setObjectVelocityCpu(float* linVel, float* angVel, int bo
 	}
 	m_bodiesCPU[bodyIndex].m_linVel = b3MakeVector3(linVel[0], linVel[1], linVel[2]);
 	m_bodiesCPU[bodyIndex].m_angVel = b3MakeVector3(angVel[0], angVel[1], angVel[2]);
+	m_cpuEdited = true;
 }
 void b3GpuNarrowPhase::setObjectTransform(const float* position, const float* orientation, int bodyIndex)
 {
-	// b3GpuNarrowPhase.cpp:946-963: CPU copy + immediate write of that body to the device
-	setObjectTransformCpu((float*)position, (float*)orientation, bodyIndex);
-	if (m_bodiesCPU.size()) checked(b3b200_write_bodies(m_world, (const b3b200_rigid_body*)&m_bodiesCPU[0], m_bodiesCPU.size()), "setObjectTransform");
+	// b3GpuNarrowPhase::setObjectTransform: the CPU copy of THAT body + an immediate write of that one body to the device
+	// (the other bodies keep their device state: the CPU copy may be older than the simulation)
+	if (bodyIndex < 0 || bodyIndex >= b3b200_num_bodies(m_world))
+	{
+		b3Warning("setObjectTransform out of range.\n");
+		return;
+	}
+	b3RigidBodyData one;
+	checked(b3b200_read_body(m_world, bodyIndex, (b3b200_rigid_body*)&one), "setObjectTransform");
+	one.m_pos = b3MakeVector3(position[0], position[1], position[2]);
+	one.m_quat.setValue(orientation[0], orientation[1], orientation[2], orientation[3]);
+	checked(b3b200_write_body(m_world, bodyIndex, (const b3b200_rigid_body*)&one), "setObjectTransform");
+	if (bodyIndex < m_bodiesCPU.size())
+	{
+		m_bodiesCPU[bodyIndex].m_pos = one.m_pos;
+		m_bodiesCPU[bodyIndex].m_quat = one.m_quat;
+	}
 }
 void b3GpuNarrowPhase::computeContacts(cl_mem, int, cl_mem, int) { checked(b3b200_compute_contacts(m_world), "computeContacts"); }
 cl_mem b3GpuNarrowPhase::getBodiesGpu()

@@ -90,6 +90,7 @@ struct World
 	cudaStream_t stream = 0;
 	bool ownStream = false;
 	bool uploaded = false;
+	bool everUploaded = false;  // bodies [0, numBodies) have device state that an upload must not rewind
 	bool aabbsValid = false;  // world AABBs on device match the current poses
 
 	// settings

@@ -389,6 +389,7 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->numBodies = 0;
 	w->static0Index = -1;
 	w->uploaded = false;
+	w->everUploaded = false;
 	w->aabbsValid = false;
 	w->partValid = false;
 	w->solverMisc = nullptr;
@@ -569,11 +570,13 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	W_CHECK(w);
 	cudaStream_t s = w->stream;
 	B3_CUDA_CHECK(cudaStreamSynchronize(s));
-	if (w->hostBodiesStale && w->numBodies > 0 && w->dBodiesAoS.ptr)
+	if (w->everUploaded && w->numBodies > 0 && w->dBodiesAoS.ptr)
 	{
-		// bodies written with b3b200_write_bodies live on the device only: bring them back before the tables are re-sent
+		// the bodies that are already on the device have been stepped / written / solved there: their state comes back into the
+		// host mirror before the tables are re-sent, so that an upload after registering one more body does not rewind them
 		if (w->soaDirty) B3_TRY(launchUnpackSoA(w));
 		B3_CUDA_CHECK(cudaMemcpyAsync(w->bodies.data(), w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * (size_t)w->numBodies, cudaMemcpyDeviceToHost, s));
+		B3_CUDA_CHECK(cudaMemcpyAsync(w->inertias.data(), w->dInertias.ptr, sizeof(b3b200_inertia) * (size_t)w->numBodies, cudaMemcpyDeviceToHost, s));  // (checkpoint / halo paths write them on the device)
 		B3_CUDA_CHECK(cudaStreamSynchronize(s));
 	}
 	w->hostBodiesStale = false;
@@ -645,6 +648,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 	B3_TRY(launchPackSoA(w));
 	B3_CUDA_CHECK(cudaStreamSynchronize(s));
 	w->uploaded = true;
+	w->everUploaded = true;
 	w->aabbsValid = false;
 	w->soaDirty = false;
 	return 0;
@@ -710,6 +714,27 @@ extern "C" int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, i
 	if (!dst || n < 0 || n > w->numBodies) return B3B200_ERR_INVALID;
 	B3_TRY(syncAoS(w));
 	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * n, cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+extern "C" int b3b200_write_body(b3b200_world* w, int bodyIndex, const b3b200_rigid_body* src)
+{
+	W_UPLOADED(w);
+	if (!src || bodyIndex < 0 || bodyIndex >= w->numBodies) return B3B200_ERR_INVALID;
+	B3_TRY(syncAoS(w));
+	B3_CUDA_CHECK(cudaMemcpyAsync(&w->dBodiesAoS.ptr[bodyIndex], src, sizeof(b3b200_rigid_body), cudaMemcpyHostToDevice, w->stream));
+	B3_TRY(launchPackSoA(w));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	w->hostBodiesStale = true;
+	w->aabbsValid = false;
+	return 0;
+}
+extern "C" int b3b200_read_body(b3b200_world* w, int bodyIndex, b3b200_rigid_body* dst)
+{
+	W_UPLOADED(w);
+	if (!dst || bodyIndex < 0 || bodyIndex >= w->numBodies) return B3B200_ERR_INVALID;
+	B3_TRY(syncAoS(w));
+	B3_CUDA_CHECK(cudaMemcpyAsync(dst, &w->dBodiesAoS.ptr[bodyIndex], sizeof(b3b200_rigid_body), cudaMemcpyDeviceToHost, w->stream));
 	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
 	return 0;
 }
@@ -1019,12 +1044,12 @@ extern "C" int b3b200_get_table(b3b200_world* w, int which, void* dst, int capac
 		case B3B200_TBL_BVH_SUBTREES:
 			return copyTable(w->bvhSubtrees, dst, capacity, count);
 		case B3B200_TBL_BODIES:
-			if (w->hostBodiesStale && w->device >= 0 && w->uploaded)
+			if (w->device >= 0 && w->uploaded && w->numBodies > 0)
 			{
 				// "last written": the AoS buffer as b3b200_write_bodies left it is not kept on the host any more
 				B3_CUDA_CHECK(cudaSetDevice(w->device));
 				B3_TRY(syncAoS(w));
-				B3_CUDA_CHECK(cudaMemcpyAsync(w->bodies.data(), w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * w->bodies.size(), cudaMemcpyDeviceToHost, w->stream));
+				B3_CUDA_CHECK(cudaMemcpyAsync(w->bodies.data(), w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * (size_t)w->numBodies, cudaMemcpyDeviceToHost, w->stream));
 				B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
 				w->hostBodiesStale = false;
 			}

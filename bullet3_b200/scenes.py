@@ -152,12 +152,15 @@ def heightfield_mesh(nx, nz, cell=1.0, amplitude=2.0, freq=0.1, x0=None, z0=None
     return verts, tris.astype(np.int32).reshape(-1)
 
 
-def bench_config4_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, hull_verts=(8, 32), spacing=(2.2, 2.0, 2.2), mesh_quads=None):
+def bench_config4_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, hull_verts=(8, 32), spacing=(2.2, 2.0, 2.2), mesh_quads=None, keep=None, poses=None):
     """BASELINE.json config 4: a pile of nx*ny*nz bodies -- 1/4 boxes, 1/4 tetrahedra, 1/4 seeded random hulls
     (`hull_verts` vertices on a sphere), 1/4 three-box "L" compounds -- with seeded random orientations on the config-3
     lattice, dropped on a synthetic concave heightfield trimesh h = 2 sin(0.1 x) cos(0.1 z) that extends 10 % beyond the
     pile (256 x 256 quads = 131 072 triangles at bench size).  Body 0 is the mesh (it has to be the lower body index of
-    its pairs, b3BvhTraversal.h:35).  Returns the list of collidables."""
+    its pairs, b3BvhTraversal.h:35).  Returns the list of collidables.
+    keep: optional index array into the nx*ny*nz lattice bodies -- only those are registered (a sub-region of the scene with the
+    same shapes and the same mesh); poses: optional (positions n x 4, orientations n x 4) replacing the lattice poses (e.g. a
+    settled state), indexed like the full lattice."""
     rng = np.random.default_rng(seed)
     wx, wz = spacing[0] * nx, spacing[2] * nz
     if mesh_quads is None:
@@ -186,5 +189,11 @@ def bench_config4_scene(world, nx, ny, nz, seed=1234, num_hull_shapes=8, hull_ve
     kind = rng.integers(0, 4, n)
     hull = np.asarray(hulls, np.int32)[rng.integers(0, num_hull_shapes, n)]
     col = np.where(kind == 0, box, np.where(kind == 1, tet, np.where(kind == 2, hull, ell))).astype(np.int32)
-    world.register_instances(np.ones(n, np.float32), pos, q.astype(np.float32), col)
+    q = q.astype(np.float32)
+    if poses is not None:
+        pos, q = np.ascontiguousarray(poses[0], np.float32).reshape(n, 4), np.ascontiguousarray(poses[1], np.float32).reshape(n, 4)
+    if keep is not None:
+        keep = np.asarray(keep, np.int64)
+        pos, q, col = np.ascontiguousarray(pos[keep]), np.ascontiguousarray(q[keep]), np.ascontiguousarray(col[keep])
+    world.register_instances(np.ones(len(col), np.float32), pos, q, col)
     return [mesh, box, tet] + hulls + [small_box, ell]

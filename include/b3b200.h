@@ -99,7 +99,9 @@ int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const
 /* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
 int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4,
 							  const float* orientations4, const int* collidableIndices);
-/* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150) */
+/* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150).  Bodies that are already on the
+ * device keep their device state (poses, velocities): only the shape tables and the bodies registered since the last
+ * upload are sent, like the reference's copyFromHostPointer(&body, 1, bodyIndex) per new body. */
 int b3b200_upload(b3b200_world* w);
 
 /* ---- joints: b3GpuRigidBodyPipeline::createPoint2PointConstraint / createFixedConstraint / removeConstraintByUid /
@@ -147,6 +149,10 @@ int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src, int n);
 /* b3GpuNarrowPhase::readbackAllBodiesToCpu + getBodiesCpu (b3GpuNarrowPhase.cpp:965-968, 676-679) */
 int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, int n);
 int b3b200_readback_inertias(b3b200_world* w, b3b200_inertia* dst, int n);
+/* one body: copyFromHostPointer(&body, 1, bodyIndex) / the matching read (b3GpuNarrowPhase::setObjectTransform, b3GpuNarrowPhase.cpp:946-963;
+ * the pick-and-drag flow of GpuRigidBodyDemo.cpp:457-463) */
+int b3b200_write_body(b3b200_world* w, int bodyIndex, const b3b200_rigid_body* src);
+int b3b200_read_body(b3b200_world* w, int bodyIndex, b3b200_rigid_body* dst);
 int b3b200_num_bodies(b3b200_world* w);
 
 /* ---- the step: b3GpuRigidBodyPipeline::stepSimulation (b3GpuRigidBodyPipeline.cpp:221-463) ---- */

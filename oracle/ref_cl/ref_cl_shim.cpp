@@ -271,3 +271,155 @@ void refcl_cast_rays_host(void* h, const b3b200_rigid_body* bodies, int numBodie
 	if (numRays) memcpy(hits, &out[0], sizeof(b3RayHit) * (size_t)numRays);
 }
 }
+
+// ------------------------------------------------------------------ the whole step: b3GpuRigidBodyPipeline::stepSimulation
+// (b3GpuRigidBodyPipeline.cpp:221-463), UNMODIFIED, with every host-twin switch of the reference turned on, so that each
+// stage runs the reference's own CPU code under the fake OpenCL:
+//   world AABBs   gCalcWorldSpaceAabbOnCpu            (b3GpuRigidBodyPipeline.cpp:508-533)
+//   pairs         gUseDbvt -> b3DynamicBvhBroadphase  (:231-251; the brute-force calculateOverlappingPairsHost is O(N^2))
+//   contacts      -DCHECK_ON_HOST contact loop + the concave host twins (b3ConvexHullContact.cpp:2595-2748, 20-24)
+//   solver        gCpuSortContactsDeterminism, gCpuSetSortData, gCpuRadixSort, gUseScanHost, gReorderContactsOnCpu,
+//                 gUseCpuCopyConstraints, gCpuBatchContacts, gConvertConstraintOnCpu, gCpuSolveConstraint
+//                 (b3GpuPgsContactSolver.cpp:568-1103 -> b3Solver::solveContactConstraintHost, b3Solver.cpp:468-637)
+//   integrate     gIntegrateOnCpu                     (b3GpuRigidBodyPipeline.cpp:471-486)
+// This is what bench.py --impl reference times.  Single-threaded by construction.
+#include <unistd.h>
+#include <fcntl.h>
+#include "Bullet3OpenCL/RigidBody/b3GpuRigidBodyPipeline.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuPgsContactSolver.h"
+#include "Bullet3Collision/BroadPhaseCollision/b3DynamicBvhBroadphase.h"
+extern bool gUseDbvt, gCalcWorldSpaceAabbOnCpu, gIntegrateOnCpu, gClearPairsOnGpu, gUseJacobi;
+extern bool gCpuBatchContacts, gCpuSolveConstraint, gCpuRadixSort, gCpuSetSortData, gCpuSortContactsDeterminism, gUseCpuCopyConstraints, gUseScanHost,
+	gReorderContactsOnCpu, gUseLargeBatches;
+
+// the reference's own B3_PROFILE zones (b3Logging.h:21-63), summed per zone name: where its step spends the time
+#include <chrono>
+#include <map>
+#include <string>
+#include <vector>
+#include "Bullet3Common/b3Logging.h"
+static std::map<std::string, double> g_zoneSeconds;
+static std::vector<std::pair<const char*, std::chrono::steady_clock::time_point> > g_zoneStack;
+static void zoneEnter(const char* name) { g_zoneStack.push_back(std::make_pair(name, std::chrono::steady_clock::now())); }
+static void zoneLeave()
+{
+	if (g_zoneStack.empty()) return;
+	g_zoneSeconds[g_zoneStack.back().first] += std::chrono::duration<double>(std::chrono::steady_clock::now() - g_zoneStack.back().second).count();
+	g_zoneStack.pop_back();
+}
+
+struct RefPipeline
+{
+	RefNp np;  // first member: a RefPipeline* is also a valid refcl_np_* handle for the shape registration calls
+	b3GpuSapBroadphase* sap;
+	b3DynamicBvhBroadphase* dbvt;
+	b3GpuRigidBodyPipeline* pipe;
+};
+
+extern "C" {
+void* refcl_pipeline_create(const b3b200_config* cfg)
+{
+	init();
+	RefPipeline* r = new RefPipeline;
+	memcpy(&r->np.cfg, cfg, sizeof(b3Config));
+	r->np.np = new b3GpuNarrowPhase(CTX, DEV, Q, r->np.cfg);
+	r->sap = new b3GpuSapBroadphase(CTX, DEV, Q);
+	r->dbvt = new b3DynamicBvhBroadphase(r->np.cfg.m_maxConvexBodies);
+	r->pipe = new b3GpuRigidBodyPipeline(CTX, DEV, Q, r->np.np, r->sap, r->dbvt, r->np.cfg);
+	gUseDbvt = true;
+	gCalcWorldSpaceAabbOnCpu = true;
+	gIntegrateOnCpu = true;
+	gClearPairsOnGpu = false;
+	gUseJacobi = false;
+	gCpuBatchContacts = gCpuSolveConstraint = gCpuRadixSort = gCpuSetSortData = gCpuSortContactsDeterminism = true;
+	gUseCpuCopyConstraints = gUseScanHost = gReorderContactsOnCpu = true;
+	gConvertConstraintOnCpu = true;
+	gUseLargeBatches = false;
+	refcl_concave_host_twins(1);
+	b3SetCustomEnterProfileZoneFunc(zoneEnter);
+	b3SetCustomLeaveProfileZoneFunc(zoneLeave);
+	return r;
+}
+void refcl_pipeline_destroy(void* h)
+{
+	RefPipeline* r = (RefPipeline*)h;
+	delete r->pipe;
+	delete r->np.np;
+	delete r->sap;
+	delete r->dbvt;
+	delete r;
+}
+int refcl_pipeline_register_instance(void* h, float mass, const float* pos4, const float* orn4, int collidable, int userIndex)
+{
+	return ((RefPipeline*)h)->pipe->registerPhysicsInstance(mass, pos4, orn4, collidable, userIndex, false);
+}
+// writeAllInstancesToGpu (GpuRigidBodyDemo.cpp:148-150)
+void refcl_pipeline_upload(void* h)
+{
+	RefPipeline* r = (RefPipeline*)h;
+	r->np.np->writeAllBodiesToGpu();
+	r->sap->writeAabbsToGpu();
+	r->pipe->writeAllInstancesToGpu();
+}
+// overwrite the body state (poses, velocities) with the caller's
+void refcl_pipeline_set_bodies(void* h, const b3b200_rigid_body* bodies, int n)
+{
+	RefPipeline* r = (RefPipeline*)h;
+	b3GpuNarrowPhaseInternalData* d = r->np.np->getInternalData();
+	for (int i = 0; i < n && i < d->m_bodyBufferCPU->size(); i++) memcpy(&d->m_bodyBufferCPU->at(i), &bodies[i], sizeof(b3RigidBodyData));
+	r->np.np->writeAllBodiesToGpu();
+}
+void refcl_pipeline_get_bodies(void* h, b3b200_rigid_body* bodies, int n)
+{
+	RefPipeline* r = (RefPipeline*)h;
+	r->np.np->readbackAllBodiesToCpu();
+	b3GpuNarrowPhaseInternalData* d = r->np.np->getInternalData();
+	for (int i = 0; i < n && i < d->m_bodyBufferCPU->size(); i++) memcpy(&bodies[i], &d->m_bodyBufferCPU->at(i), sizeof(b3RigidBodyData));
+}
+// `steps` x stepSimulation(dt).  The contact solver runs the 4 iterations b3GpuPgsContactSolver::solveContacts hard-codes
+// (b3GpuPgsContactSolver.cpp:1049-1051: `int numIter = 4`; b3Config has no iteration count) -- `iterations` is ignored.
+// out3 = {broadphase pairs, contacts, device kernel launches that were skipped} of the last step.
+int refcl_pipeline_step(void* h, float dt, int steps, int iterations, int* out3)
+{
+	RefPipeline* r = (RefPipeline*)h;
+	// (the narrowphase still enqueues its device kernels after the CHECK_ON_HOST loop, see fake_cl.cpp)
+	g_fakeClLaunchIsNoop = 1;
+	g_fakeClLaunches = 0;
+	(void)iterations;
+	// the host twins printf diagnostics every step ("maxNumAabbChecks=..."): keep them off the caller's stdout
+	fflush(stdout);
+	const int saved = dup(1), devnull = open("/dev/null", O_WRONLY);
+	if (saved >= 0 && devnull >= 0) dup2(devnull, 1);
+	for (int i = 0; i < steps; i++) r->pipe->stepSimulation(dt);
+	fflush(stdout);
+	if (saved >= 0 && devnull >= 0) dup2(saved, 1);
+	if (saved >= 0) close(saved);
+	if (devnull >= 0) close(devnull);
+	g_fakeClLaunchIsNoop = 0;
+	if (out3)
+	{
+		out3[0] = r->dbvt->getOverlappingPairCache()->getNumOverlappingPairs();
+		out3[1] = r->np.np->getNumContactsGpu();
+		out3[2] = g_fakeClLaunches;
+	}
+	return 0;
+}
+// seconds per B3_PROFILE zone since the last call, as "name=seconds;..." (inclusive times; zones nest)
+int refcl_profile_zones(char* dst, int cap)
+{
+	std::string out;
+	for (std::map<std::string, double>::iterator it = g_zoneSeconds.begin(); it != g_zoneSeconds.end(); ++it)
+	{
+		char buf[256];
+		snprintf(buf, sizeof(buf), "%s=%.6f;", it->first.c_str(), it->second);
+		out += buf;
+	}
+	g_zoneSeconds.clear();
+	if (dst && cap > 0)
+	{
+		strncpy(dst, out.c_str(), (size_t)cap - 1);
+		dst[cap - 1] = 0;
+	}
+	return (int)out.size();
+}
+}

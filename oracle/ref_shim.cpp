@@ -244,3 +244,162 @@ int ref_solve_joints_p2p(b3b200_rigid_body* bodies, b3b200_inertia* inertias, in
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ the reference's CPU pipeline itself
+// b3CpuRigidBodyPipeline (src/Bullet3Dynamics/b3CpuRigidBodyPipeline.cpp) + b3CpuNarrowPhase + b3DynamicBvhBroadphase,
+// instantiated and stepped as they are: BASELINE configs[0] ("1,000 unit boxes ... b3CpuRigidBodyPipeline on CPU, 600 steps")
+// and the CPU baseline north_star names.  stepSimulation = AABBs + DBVT pairs + contacts + integrate (it has no solver,
+// b3CpuRigidBodyPipeline.cpp:75-90).  The per-stage getters exist for the per-step parity test of SURVEY 8(d) config 1.
+#include <unistd.h>
+#include <fcntl.h>
+#include "Bullet3Dynamics/b3CpuRigidBodyPipeline.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3CpuNarrowPhase.h"
+#include "Bullet3Collision/NarrowPhaseCollision/b3Config.h"
+#include "Bullet3Collision/BroadPhaseCollision/b3DynamicBvhBroadphase.h"
+#include "Bullet3Dynamics/shared/b3Inertia.h"
+// layout mirror of the pipeline's private data (b3CpuRigidBodyPipeline.cpp:14-23), to read the world AABBs and to re-seed the bodies
+struct b3CpuRigidBodyPipelineInternalData
+{
+	b3AlignedObjectArray<b3RigidBodyData> m_rigidBodies;
+	b3AlignedObjectArray<b3Inertia> m_inertias;
+	b3AlignedObjectArray<b3Aabb> m_aabbWorldSpace;
+	b3DynamicBvhBroadphase* m_bp;
+	b3CpuNarrowPhase* m_np;
+	b3Config m_config;
+};
+struct RefCpuPipe : public b3CpuRigidBodyPipeline
+{
+	RefCpuPipe(b3CpuNarrowPhase* np, b3DynamicBvhBroadphase* bp, const b3Config& c) : b3CpuRigidBodyPipeline(np, bp, c) {}
+	b3CpuRigidBodyPipelineInternalData* data() { return m_data; }
+};
+struct RefCpu
+{
+	b3Config cfg;
+	b3CpuNarrowPhase* np;
+	b3DynamicBvhBroadphase* bp;
+	RefCpuPipe* pipe;
+};
+struct Quiet  // the pipeline printf()s "numPairs=..." every step
+{
+	int saved, devnull;
+	Quiet()
+	{
+		fflush(stdout);
+		saved = dup(1);
+		devnull = open("/dev/null", O_WRONLY);
+		if (saved >= 0 && devnull >= 0) dup2(devnull, 1);
+	}
+	~Quiet()
+	{
+		fflush(stdout);
+		if (saved >= 0 && devnull >= 0) dup2(saved, 1);
+		if (saved >= 0) close(saved);
+		if (devnull >= 0) close(devnull);
+	}
+};
+
+extern "C" {
+void* ref_cpu_create(const b3b200_config* cfg)
+{
+	RefCpu* r = new RefCpu;
+	memcpy(&r->cfg, cfg, sizeof(b3Config));
+	r->np = new b3CpuNarrowPhase(r->cfg);
+	r->bp = new b3DynamicBvhBroadphase(r->cfg.m_maxConvexBodies);
+	r->pipe = new RefCpuPipe(r->np, r->bp, r->cfg);
+	return r;
+}
+void ref_cpu_destroy(void* h)
+{
+	RefCpu* r = (RefCpu*)h;
+	delete r->pipe;
+	delete r->np;
+	delete r->bp;
+	delete r;
+}
+int ref_cpu_register_convex_points(void* h, const float* pts, int n, const float* scaling) { return ((RefCpu*)h)->np->registerConvexHullShape(pts, 12, n, scaling); }
+int ref_cpu_register_instance(void* h, float mass, const float* pos4, const float* orn4, int collidable, int userIndex)
+{
+	return ((RefCpu*)h)->pipe->registerPhysicsInstance(mass, pos4, orn4, collidable, userIndex);
+}
+// (b3CpuRigidBodyPipeline::setGravity is declared but never defined: the pipeline integrates with its built-in (0,-9,0), b3CpuRigidBodyPipeline.cpp:365)
+int ref_cpu_num_bodies(void* h) { return ((RefCpu*)h)->pipe->getNumBodies(); }
+void ref_cpu_step(void* h, float dt, int steps)
+{
+	Quiet q;
+	for (int i = 0; i < steps; i++) ((RefCpu*)h)->pipe->stepSimulation(dt);
+}
+// one stage: 0 updateAabbWorldSpace, 1 computeOverlappingPairs, 2 computeContactPoints, 3 integrate
+void ref_cpu_stage(void* h, int which, float dt)
+{
+	Quiet q;
+	RefCpuPipe* p = ((RefCpu*)h)->pipe;
+	if (which == 0) p->updateAabbWorldSpace();
+	if (which == 1) p->computeOverlappingPairs();
+	if (which == 2) p->computeContactPoints();
+	if (which == 3) p->integrate(dt);
+}
+void ref_cpu_get_bodies(void* h, b3b200_rigid_body* out, int n)
+{
+	RefCpu* r = (RefCpu*)h;
+	const b3RigidBodyData* b = r->pipe->getBodyBuffer();
+	for (int i = 0; i < n && i < r->pipe->getNumBodies(); i++) memcpy(&out[i], &b[i], sizeof(b3RigidBodyData));
+}
+void ref_cpu_set_bodies(void* h, const b3b200_rigid_body* in, int n)
+{
+	b3CpuRigidBodyPipelineInternalData* d = ((RefCpu*)h)->pipe->data();
+	for (int i = 0; i < n && i < d->m_rigidBodies.size(); i++) memcpy(&d->m_rigidBodies[i], &in[i], sizeof(b3RigidBodyData));
+}
+int ref_cpu_get_aabbs(void* h, b3b200_aabb* out, int n)
+{
+	b3CpuRigidBodyPipelineInternalData* d = ((RefCpu*)h)->pipe->data();
+	for (int i = 0; i < n && i < d->m_aabbWorldSpace.size(); i++) memcpy(&out[i], &d->m_aabbWorldSpace[i], sizeof(b3Aabb));
+	return d->m_aabbWorldSpace.size();
+}
+int ref_cpu_get_pairs(void* h, b3b200_int4* out, int cap)
+{
+	b3AlignedObjectArray<b3Int4>& p = ((RefCpu*)h)->bp->getOverlappingPairCache()->getOverlappingPairArray();
+	for (int i = 0; i < p.size() && i < cap; i++) memcpy(&out[i], &p[i], sizeof(b3Int4));
+	return p.size();
+}
+int ref_cpu_get_contacts(void* h, b3b200_contact4* out, int cap)
+{
+	const b3AlignedObjectArray<b3Contact4Data>& c = ((RefCpu*)h)->np->getContacts();
+	for (int i = 0; i < c.size() && i < cap; i++) memcpy(&out[i], &c[i], sizeof(b3Contact4Data));
+	return c.size();
+}
+// the shape tables b3CpuNarrowPhase built (b3ConvexUtility hulls): 0 collidables, 2 convex polyhedra, 3 vertices, 4 unique edges, 5 faces, 6 indices
+int ref_cpu_get_table(void* h, int which, void* dst, int capacity, int* count)
+{
+	// layout mirror of b3CpuNarrowPhaseInternalData (b3CpuNarrowPhase.cpp:8-24)
+	struct NpData
+	{
+		b3AlignedObjectArray<b3Aabb> m_localShapeAABBCPU;
+		b3AlignedObjectArray<b3Collidable> m_collidablesCPU;
+		b3AlignedObjectArray<b3ConvexUtility*> m_convexData;
+		b3Config m_config;
+		b3AlignedObjectArray<b3ConvexPolyhedronData> m_convexPolyhedra;
+		b3AlignedObjectArray<b3Vector3> m_uniqueEdges;
+		b3AlignedObjectArray<b3Vector3> m_convexVertices;
+		b3AlignedObjectArray<int> m_convexIndices;
+		b3AlignedObjectArray<b3GpuFace> m_convexFaces;
+	};
+	const NpData* d = (const NpData*)((RefCpu*)h)->np->getInternalData();
+	const void* src = 0;
+	int n = 0, sz = 0;
+	switch (which)
+	{
+		case 0: n = d->m_collidablesCPU.size(); sz = sizeof(b3Collidable); src = n ? &d->m_collidablesCPU[0] : 0; break;
+		case 1: n = d->m_localShapeAABBCPU.size(); sz = sizeof(b3Aabb); src = n ? &d->m_localShapeAABBCPU[0] : 0; break;
+		case 2: n = d->m_convexPolyhedra.size(); sz = sizeof(b3ConvexPolyhedronData); src = n ? &d->m_convexPolyhedra[0] : 0; break;
+		case 3: n = d->m_convexVertices.size(); sz = 16; src = n ? &d->m_convexVertices[0] : 0; break;
+		case 4: n = d->m_uniqueEdges.size(); sz = 16; src = n ? &d->m_uniqueEdges[0] : 0; break;
+		case 5: n = d->m_convexFaces.size(); sz = sizeof(b3GpuFace); src = n ? &d->m_convexFaces[0] : 0; break;
+		case 6: n = d->m_convexIndices.size(); sz = 4; src = n ? &d->m_convexIndices[0] : 0; break;
+		default: return -1;
+	}
+	*count = n;
+	const int m = n < capacity ? n : capacity;
+	if (dst && m > 0 && src) memcpy(dst, src, (size_t)sz * m);
+	return 0;
+}
+}

@@ -196,8 +196,23 @@ int main(int argc, char** argv)
 	for (int pass = 0; pass < 2; pass++)
 	{
 		float down[3] = {0, -1, 0}, zero[3] = {0, 0, 0};
+		np->readbackAllBodiesToCpu();  // the CPU copy = the stepped state
+		b3AlignedObjectArray<b3RigidBodyData> before;
+		before.resize(pipe->getNumBodies());
+		for (int i = 0; i < pipe->getNumBodies(); i++) before[i] = np->getBodiesCpu()[i];
 		for (int i = 1; i < pipe->getNumBodies(); i++) np->setObjectVelocityCpu(down, zero, i);
 		np->writeAllBodiesToGpu();
+		{
+			// the edit arrived on the device and nothing else moved (the pick flow of GpuRigidBodyDemo.cpp:457-463)
+			np->readbackAllBodiesToCpu();
+			const b3RigidBodyData* now = np->getBodiesCpu();
+			bool arrived = true;
+			for (int i = 1; i < pipe->getNumBodies(); i++)
+				arrived = arrived && now[i].m_linVel.y == -1.f && now[i].m_pos.x == before[i].m_pos.x && now[i].m_pos.y == before[i].m_pos.y &&
+						  now[i].m_pos.z == before[i].m_pos.z && now[i].m_quat.w == before[i].m_quat.w;
+			printf("edit on CPU -> writeAllBodiesToGpu -> device: %s\n", arrived ? "arrived" : "LOST");
+			ok = ok && arrived;
+		}
 		if (pass == 0)
 		{
 			b3GpuPgsContactSolver pgs(ctx, dev, q, config.m_maxBroadphasePairs);
@@ -221,7 +236,7 @@ int main(int argc, char** argv)
 		}
 		const double meanVy = sumVy / (pipe->getNumBodies() - 1);
 		printf("standalone %s solver: mean vertical velocity %.3f after the solve (was -1)\n", pass == 0 ? "PGS" : "Jacobi", meanVy);
-		ok = ok && finite && meanVy > -0.5;
+		ok = ok && finite && meanVy > -0.5 && meanVy < -1e-4;  // the solver stopped most of the push (and did act: not exactly 0 either)
 	}
 
 	delete pipe;

@@ -345,3 +345,151 @@ def _ref_cast_rays(self, ray_from, ray_to, bodies, max_fraction=1.0):
 
 
 RefNarrowphase.cast_rays = _ref_cast_rays
+
+
+class RefPipeline(RefNarrowphase):
+    """the reference's own b3GpuRigidBodyPipeline (unmodified, every host-twin switch on, fake OpenCL) behind the method names
+    bullet3_b200.scenes uses, so that one scene recipe builds both worlds.  bench.py --impl reference times its step()."""
+
+    def __init__(self, cfg):
+        self.L = refcl()
+        self.L.refcl_pipeline_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.refcl_pipeline_create(P(cfg)))
+        self.num_bodies = 0
+
+    def close(self):
+        if self.h:
+            self.L.refcl_pipeline_destroy(self.h)
+            self.h = None
+
+    def register_instance(self, mass, pos, orn, collidable, user_index=0):
+        f = lambda v, n: (C.c_float * n)(*[float(x) for x in list(v)[:n]])
+        r = self.L.refcl_pipeline_register_instance(self.h, C.c_float(mass), f(list(pos) + [0.0], 4), f(orn, 4), int(collidable), int(user_index))
+        self.num_bodies += 1
+        return r
+
+    def register_instances(self, masses, positions4, orientations4, collidables):
+        positions4 = _arr(positions4, np.float32).reshape(-1, 4)
+        orientations4 = _arr(orientations4, np.float32).reshape(-1, 4)
+        first = self.num_bodies
+        for i in range(len(masses)):
+            self.L.refcl_pipeline_register_instance(self.h, C.c_float(float(masses[i])), P(positions4[i]), P(orientations4[i]), int(collidables[i]), 0)
+        self.num_bodies += len(masses)
+        return first
+
+    def upload(self):
+        self.L.refcl_pipeline_upload(self.h)
+
+    def set_bodies(self, bodies):
+        bodies = _arr(bodies, capi.rigid_body_t)
+        self.L.refcl_pipeline_set_bodies(self.h, P(bodies), len(bodies))
+
+    def bodies(self):
+        out = np.zeros(self.num_bodies, capi.rigid_body_t)
+        self.L.refcl_pipeline_get_bodies(self.h, P(out), len(out))
+        return out
+
+    def step(self, dt, steps=1):
+        out = (C.c_int * 3)()
+        self.L.refcl_pipeline_step(self.h, C.c_float(dt), int(steps), 4, out)
+        return list(out)
+
+    def profile_zones(self):
+        """seconds per B3_PROFILE zone of the reference (inclusive) since the last call"""
+        buf = C.create_string_buffer(1 << 16)
+        self.L.refcl_profile_zones(buf, len(buf))
+        return {k: float(v) for k, v in (kv.split("=") for kv in buf.value.decode().split(";") if "=" in kv)}
+
+
+class RefCpuPipeline:
+    """the reference's b3CpuRigidBodyPipeline + b3CpuNarrowPhase + b3DynamicBvhBroadphase, instantiated as they are
+    (BASELINE configs[0]); per-stage access for the per-step parity test of SURVEY 8(d) config 1"""
+
+    def __init__(self, cfg):
+        self.L = ref()
+        self.L.ref_cpu_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.ref_cpu_create(P(cfg)))
+
+    def close(self):
+        if self.h:
+            self.L.ref_cpu_destroy(self.h)
+            self.h = None
+
+    def register_convex_points(self, pts, scaling=(1.0, 1.0, 1.0)):
+        pts = _arr(pts, np.float32).reshape(-1, 3)
+        sc = (C.c_float * 4)(*[float(x) for x in scaling], 1.0)
+        return self.L.ref_cpu_register_convex_points(self.h, P(pts), len(pts), sc)
+
+    def register_instance(self, mass, pos, orn, collidable, user_index=0):
+        f = lambda v, n: (C.c_float * n)(*[float(x) for x in list(v)[:n]])
+        return self.L.ref_cpu_register_instance(self.h, C.c_float(mass), f(list(pos) + [0.0], 4), f(orn, 4), int(collidable), int(user_index))
+
+    @property
+    def num_bodies(self):
+        return self.L.ref_cpu_num_bodies(self.h)
+
+    def step(self, dt, steps=1):
+        self.L.ref_cpu_step(self.h, C.c_float(dt), int(steps))
+
+    def stage(self, which, dt=0.0):
+        self.L.ref_cpu_stage(self.h, int(which), C.c_float(dt))
+
+    def bodies(self):
+        out = np.zeros(self.num_bodies, capi.rigid_body_t)
+        self.L.ref_cpu_get_bodies(self.h, P(out), len(out))
+        return out
+
+    def set_bodies(self, bodies):
+        bodies = _arr(bodies, capi.rigid_body_t)
+        self.L.ref_cpu_set_bodies(self.h, P(bodies), len(bodies))
+
+    def aabbs(self):
+        out = np.zeros(self.num_bodies, capi.aabb_t)
+        self.L.ref_cpu_get_aabbs(self.h, P(out), len(out))
+        return out
+
+    def pairs(self):
+        n = self.L.ref_cpu_get_pairs(self.h, None, 0)
+        out = np.zeros(max(n, 1), capi.int4_t)
+        self.L.ref_cpu_get_pairs(self.h, P(out), n)
+        return out[:n]
+
+    def contacts(self):
+        n = self.L.ref_cpu_get_contacts(self.h, None, 0)
+        out = np.zeros(max(n, 1), capi.contact4_t)
+        self.L.ref_cpu_get_contacts(self.h, P(out), n)
+        return out[:n]
+
+
+def _refcpu_table(self, which, dt):
+    n = C.c_int(0)
+    self.L.ref_cpu_get_table(self.h, which, None, 0, C.byref(n))
+    out = np.zeros(n.value, dt)
+    if n.value:
+        self.L.ref_cpu_get_table(self.h, which, P(out), n.value, C.byref(n))
+    return out
+
+
+def _refcpu_register_shapes_into(self, world):
+    """register the reference's own hull tables (b3ConvexUtility output) in a b3b200 world through b3b200_register_convex --
+    the registerConvexHullShape(b3ConvexUtility*) route of the drop-in boundary -- so both sides work on identical shape data"""
+    col = _refcpu_table(self, 0, capi.collidable_t)
+    convex = _refcpu_table(self, 2, capi.convex_t)
+    verts = _refcpu_table(self, 3, np.dtype(("f4", 4)))
+    edges = _refcpu_table(self, 4, np.dtype(("f4", 4)))
+    faces = _refcpu_table(self, 5, capi.face_t)
+    idx = _refcpu_table(self, 6, np.dtype("i4"))
+    out = []
+    for c in col:
+        cv = convex[int(c["shapeIndex"])]
+        f = faces[cv["faceOffset"]: cv["faceOffset"] + cv["numFaces"]].copy()
+        lo = int(f["indexOffset"].min())
+        hi = int((f["indexOffset"] + f["numIndices"]).max())
+        f["indexOffset"] -= lo
+        out.append(world.register_convex(verts[cv["vertexOffset"]: cv["vertexOffset"] + cv["numVertices"]], f, idx[lo:hi],
+                                         edges[cv["uniqueEdgesOffset"]: cv["uniqueEdgesOffset"] + cv["numUniqueEdges"]], np.array([cv])))
+    return out
+
+
+RefCpuPipeline.table = _refcpu_table
+RefCpuPipeline.register_shapes_into = _refcpu_register_shapes_into

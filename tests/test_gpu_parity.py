@@ -1162,3 +1162,47 @@ def test_high_degree_body_colouring(side, overflow, colouring):
     for _ in range(5):
         w.step(1 / 60)
     assert np.isfinite(w.bodies()["pos"]).all()
+
+
+# ------------------------------------------------------------------ body edits and uploads after stepping
+def test_upload_after_stepping_keeps_the_device_state():
+    """registering one more body mid-simulation and uploading must not rewind the bodies that are already on the device
+    (the reference copies only the new body: copyFromHostPointer(&body, 1, bodyIndex), b3GpuNarrowPhase.cpp:903-907)"""
+    w = capi.World(capi.default_config(1024))
+    scenes.add_ground_box(w, 50.0)
+    box = w.register_convex_points(scenes.box_points(0.5))
+    for i in range(50):
+        w.register_instance(1.0, (1.5 * (i % 10), 0.5 + 1.2 * (i // 10), 0.0), scenes.IDENT, box)
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, 4)
+    for _ in range(20):
+        w.step(1 / 60)
+    before = w.bodies()
+    assert np.abs(before["linVel"][1:, 1]).max() > 0.01 or np.abs(before["pos"][1:, 1] - 0.5).max() > 1e-3  # it did move
+    new = w.register_instance(1.0, (0.0, 30.0, 5.0), scenes.IDENT, box)
+    w.upload()
+    after = w.bodies()
+    assert len(after) == len(before) + 1 and new == len(before)
+    for f in ("pos", "quat", "linVel", "angVel"):
+        assert np.array_equal(after[f][:-1].view(np.uint32), before[f].view(np.uint32)), f
+    assert tuple(after["pos"][-1][:3]) == (0.0, 30.0, 5.0)
+    w.step(1 / 60)
+    assert np.isfinite(w.bodies()["pos"]).all()
+
+
+def test_write_body_and_read_body_touch_one_body():
+    w, sh, bodies, inertias = gpu_world(n_side=4, seed=3)
+    L = capi.lib()
+    w.step(1 / 60)
+    before = w.bodies()
+    one = np.zeros(1, capi.rigid_body_t)
+    capi.check(L.b3b200_read_body(w.h, 7, capi.ptr(one)), "read_body")
+    assert one.tobytes() == before[7:8].tobytes()
+    one["pos"][0][:3] = (1.0, 9.0, -2.0)
+    one["linVel"][0][:3] = (0.0, 0.0, 3.0)
+    capi.check(L.b3b200_write_body(w.h, 7, capi.ptr(one)), "write_body")
+    after = w.bodies()
+    assert after[7:8].tobytes() == one.tobytes()
+    keep = np.arange(len(after)) != 7
+    assert after[keep].tobytes() == before[keep].tobytes()
+    assert L.b3b200_write_body(w.h, len(after), capi.ptr(one)) != 0 and L.b3b200_read_body(w.h, -1, capi.ptr(one)) != 0
