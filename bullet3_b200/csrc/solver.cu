@@ -1069,42 +1069,65 @@ struct BodyConst
 
 // solveContact<false> (b3Solver.cpp:187-266): the four points of one manifold, with the angular Jacobians of the row.
 // j0[i] = {r0 x n, jacCoeffInv}, j1[i] = {-(r1 x n), b}.
+//
+// The reference walks the points one after the other, each reading the velocities the previous one wrote: a chain of
+// ~50 dependent FP32 operations per point, ~1 us per row on one warp -- and every colour of every pass waits for one such
+// row.  The same sequence is evaluated here through its linear structure: with J_i the 12-component Jacobian of point i
+// and D_i the velocity change per unit impulse, relVel_i = J_i . v0 + sum_{j<i} (J_i . D_j) dLambda_j.  J_i . v0 (4 dot
+// products), the couplings J_i . D_j (6 scalars) and D_i depend on nothing the chain produces, so they issue back to back;
+// what stays sequential is one FMA + the clamp per point, and the velocities are updated once at the end.  Same
+// Gauss-Seidel order, same clamping; the results differ from the point-by-point evaluation by reassociation only
+// (~1e-7 relative; the parity bar of the velocities is 1e-4).
 B3_D void solveNormalCore(const float4& nId, const float4* j0, const float4* j1, float4& applied, const BodyConst& A, const BodyConst& B, float4& linVelA,
 						  float4& angVelA, float4& linVelB, float4& angVelB)
 {
 	const float4 n = mk4(nId.x, nId.y, nId.z);
-	const float4 nn = neg3(n);
-	float ap[4] = {applied.x, applied.y, applied.z, applied.w};
-	// what an impulse of 1 does to the four velocities (independent of the velocities: off the dependency chain)
-	const float4 dLinA = scale3(n, A.pos.w), dLinB = scale3(nn, B.pos.w);
+	const float invMassA = A.pos.w, invMassB = B.pos.w;
+	float4 dAngA[4], dAngB[4];
+	float rv[4];
+	// (n . n)(invMassA + invMassB): the linear part of every coupling J_i . D_j
+	const float linCoupling = fdot3(n, n) * (invMassA + invMassB);
+	const float relLin = fdot3(n, linVelA) - fdot3(n, linVelB);
 #pragma unroll
-	for (int ic = 0; ic < 4; ic++)
+	for (int i = 0; i < 4; i++)
 	{
-		const float jac = j0[ic].w;
-		if (jac == 0.f) continue;
-		const float4 dAngA = fmatRowMul(A.i0, A.i1, A.i2, j0[ic]);
-		const float4 dAngB = fmatRowMul(B.i0, B.i1, B.i2, j1[ic]);
-		float rambdaDt = fcalcRelVel(n, nn, j0[ic], j1[ic], linVelA, angVelA, linVelB, angVelB) + j1[ic].w;
-		rambdaDt *= jac;
-		{
-			const float prevSum = ap[ic];
-			float updated = prevSum;
-			updated += rambdaDt;
-			updated = fmaxf(updated, 0.f);
-			updated = fminf(updated, FLT_MAX);
-			rambdaDt = updated - prevSum;
-			ap[ic] = updated;
-		}
-		linVelA = faddScaled1(linVelA, dLinA, rambdaDt);
-		angVelA = faddScaled1(angVelA, dAngA, rambdaDt);
-		linVelB = faddScaled1(linVelB, dLinB, rambdaDt);
-		angVelB = faddScaled1(angVelB, dAngB, rambdaDt);
+		dAngA[i] = fmatRowMul(A.i0, A.i1, A.i2, j0[i]);
+		dAngB[i] = fmatRowMul(B.i0, B.i1, B.i2, j1[i]);
+		rv[i] = (relLin + fdot3(j0[i], angVelA)) + (fdot3(j1[i], angVelB) + j1[i].w);
 	}
-	applied = mk4(ap[0], ap[1], ap[2], ap[3]);
+	const float lam[4] = {applied.x, applied.y, applied.z, applied.w};
+	float d[4], out[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		float r = rv[i];
+#pragma unroll
+		for (int j = 0; j < i; j++)
+		{
+			const float c = (linCoupling + fdot3(j0[i], dAngA[j])) + fdot3(j1[i], dAngB[j]);  // J_i . D_j (independent of the chain)
+			r = __fmaf_rn(c, d[j], r);
+		}
+		const float jac = j0[i].w;
+		float updated = __fmaf_rn(r, jac, lam[i]);
+		updated = fmaxf(updated, 0.f);
+		updated = fminf(updated, FLT_MAX);
+		d[i] = jac == 0.f ? 0.f : updated - lam[i];  // (a point the manifold does not have: solveContact skips it)
+		out[i] = jac == 0.f ? lam[i] : updated;
+	}
+	applied = mk4(out[0], out[1], out[2], out[3]);
+	const float dsum = (d[0] + d[1]) + (d[2] + d[3]);
+	linVelA = faddScaled1(linVelA, n, invMassA * dsum);
+	linVelB = faddScaled1(linVelB, n, -(invMassB * dsum));
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+	{
+		angVelA = faddScaled1(angVelA, dAngA[i], d[i]);
+		angVelB = faddScaled1(angVelB, dAngB[i], d[i]);
+	}
 }
 
-// solveFriction (b3Solver.cpp:268-329).  cf = {centre, damping flag}, t0 / t1 = {tangent, fJacCoeffInv}, fl = fAppliedRambdaDt;
-// returns false when the row has no friction
+// solveFriction (b3Solver.cpp:268-329), the two tangent directions through the same linear structure.  cf = {centre, damping
+// flag}, t0 / t1 = {tangent, fJacCoeffInv}, fl = fAppliedRambdaDt; returns false when the row has no friction
 B3_D bool solveFrictionCore(const float4& nId, const float4& cf, const float4& t0, const float4& t1, float4& fl, const float4& applied, const BodyConst& A,
 							const BodyConst& B, float4& linVelA, float4& angVelA, float4& linVelB, float4& angVelB)
 {
@@ -1120,32 +1143,25 @@ B3_D bool solveFrictionCore(const float4& nId, const float4& cf, const float4& t
 	const float minR = -maxR;
 	const float4 n = neg3(mk4(nId.x, nId.y, nId.z));
 	const float4 r0 = sub3(cf, A.pos), r1 = sub3(cf, B.pos);
-	const float fj[2] = {t0.w, t1.w};
-	float fa[2] = {fl.x, fl.y};
-#pragma unroll
-	for (int i = 0; i < 2; i++)
-	{
-		const float4 t = i == 0 ? mk4(t0.x, t0.y, t0.z) : mk4(t1.x, t1.y, t1.z);
-		const float4 angular0 = fcross3(r0, t);
-		const float4 angular1 = neg3(fcross3(r1, t));
-		const float4 dAngA = fmatRowMul(A.i0, A.i1, A.i2, angular0);
-		const float4 dAngB = fmatRowMul(B.i0, B.i1, B.i2, angular1);
-		float rambdaDt = fcalcRelVel(t, neg3(t), angular0, angular1, linVelA, angVelA, linVelB, angVelB);
-		rambdaDt *= fj[i];
-		{
-			const float prevSum = fa[i];
-			float updated = prevSum;
-			updated += rambdaDt;
-			updated = fmaxf(updated, minR);
-			updated = fminf(updated, maxR);
-			rambdaDt = updated - prevSum;
-			fa[i] = updated;
-		}
-		linVelA = faddScaled(linVelA, t, invMassA, rambdaDt);
-		angVelA = faddScaled1(angVelA, dAngA, rambdaDt);
-		linVelB = faddScaled(linVelB, neg3(t), invMassB, rambdaDt);
-		angVelB = faddScaled1(angVelB, dAngB, rambdaDt);
-	}
+	const float4 ta = mk4(t0.x, t0.y, t0.z), tb = mk4(t1.x, t1.y, t1.z);
+	const float4 a0 = fcross3(r0, ta), a1 = neg3(fcross3(r1, ta));
+	const float4 b0 = fcross3(r0, tb), b1 = neg3(fcross3(r1, tb));
+	const float4 dA0 = fmatRowMul(A.i0, A.i1, A.i2, a0), dB0 = fmatRowMul(B.i0, B.i1, B.i2, a1);
+	const float4 dA1 = fmatRowMul(A.i0, A.i1, A.i2, b0), dB1 = fmatRowMul(B.i0, B.i1, B.i2, b1);
+	const float4 relV = sub3(linVelA, linVelB);
+	const float rv0 = (fdot3(ta, relV) + fdot3(a0, angVelA)) + fdot3(a1, angVelB);
+	const float rv1 = (fdot3(tb, relV) + fdot3(b0, angVelA)) + fdot3(b1, angVelB);
+	const float c10 = (fdot3(tb, ta) * (invMassA + invMassB) + fdot3(b0, dA0)) + fdot3(b1, dB0);
+	float u0 = __fmaf_rn(rv0, t0.w, fl.x);
+	u0 = fminf(fmaxf(u0, minR), maxR);
+	const float d0 = u0 - fl.x;
+	float u1 = __fmaf_rn(__fmaf_rn(c10, d0, rv1), t1.w, fl.y);
+	u1 = fminf(fmaxf(u1, minR), maxR);
+	const float d1 = u1 - fl.y;
+	linVelA = faddScaled1(faddScaled1(linVelA, ta, invMassA * d0), tb, invMassA * d1);
+	linVelB = faddScaled1(faddScaled1(linVelB, ta, -(invMassB * d0)), tb, -(invMassB * d1));
+	angVelA = faddScaled1(faddScaled1(angVelA, dA0, d0), dA1, d1);
+	angVelB = faddScaled1(faddScaled1(angVelB, dB0, d0), dB1, d1);
 	if (cf.w != 0.f)
 	{
 		// angular damping for point constraint (b3Solver.cpp:317-328); the condition was evaluated by the setup
@@ -1154,7 +1170,7 @@ B3_D bool solveFrictionCore(const float4& nId, const float4& cf, const float4& t
 		angVelA = faddScaled1(angVelA, n, -(angNA * 0.1f));
 		angVelB = faddScaled1(angVelB, n, -(angNB * 0.1f));
 	}
-	fl = mk4(fa[0], fa[1], 0.f, 0.f);
+	fl = mk4(u0, u1, 0.f, 0.f);
 	return true;
 }
 

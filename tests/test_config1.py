@@ -98,7 +98,7 @@ def test_config1_600_steps_against_the_reference_cpu_pipeline():
         assert np.array_equal(ga["max"][:, :3].view(np.uint32), ra["max"][:, :3].view(np.uint32)), step
         gp = oa.sorted_pair_set(g.pairs())
         if step % 10 == 0:  # the exact pair set (brute force over the reference's AABBs), bit-exact
-            assert np.array_equal(gp, oa.sorted_pair_set(exact_pairs(ra, state))), step
+            assert np.array_equal(gp, oa.sorted_pair_set(exact_pairs(ga, state))), step  # (ga == ra bit for bit, and carries the body ids in w)
         fat = oa.sorted_pair_set(ref.pairs())  # the DBVT tests fat leaf volumes: a superset
         assert len(np.setdiff1d(gp.view([("a", gp.dtype), ("b", gp.dtype)]), fat.view([("a", fat.dtype), ("b", fat.dtype)]))) == 0, step
         gc, rc = contact_table(g.contacts()), contact_table(ref.contacts())
