@@ -187,6 +187,8 @@ struct World
 	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body (reproducible colouring; 2 words / body)
 	DevBuf<int> dContactBlock, dContactColour;
 	DevBuf<unsigned int> dContactSlots, dBlockList, dCrossList;
+	DevBuf<int2> dContactPair;
+	DevBuf<int> dTileSrc;
 	DevBuf<unsigned int> dSolverScratch, dBlockStart, dBlockTileBase, dBlockTileOff, dCrossTileOff;
 	DevBuf<int> dBlockStatics;
 	DevBuf<float4> dTilesN, dTilesF;

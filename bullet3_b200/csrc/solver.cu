@@ -288,6 +288,8 @@ struct SetupArgs
 	int* contactBlock;             // owner block, -1 = cross
 	unsigned int* contactSlots;    // slotA | slotB << 16 of an interior contact
 	int* contactColour;            // colour inside its class (cross colour / interior colour of its block), -2 = left out
+	int2* contactPair;             // dynamic bodies of the contact (-1 = that side is static): what the colouring needs, 8 coalesced bytes
+	int* tileSrc;                  // per row slot of every tile: the contact it is built from, -1 = padding
 	unsigned int* blockCount;      // scratch, see the enum above
 	unsigned int* blockCursor;
 	unsigned int* crossHist;
@@ -467,7 +469,9 @@ B3_D void contactBodies(const SetupArgs& s, int c, int& a, int& b, bool& aStatic
 	bStatic = ids.w < 0 || ids.w == s.staticIdx || lb < 0;
 }
 
-// ---- K1: classify every contact (interior to which block / cross), count per block, clear the cross masks
+// ---- K1: classify every contact (interior to which block / cross), count per block, clear the cross masks.  This is the
+// only setup kernel that reads the body ids out of the 112-byte contact records (one 32-byte sector each) and looks the
+// bodies up in the partition; the kernels after it work on the packed per-contact words it leaves.
 __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs s)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -493,7 +497,33 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs 
 				owner = (aStatic ? lb : la) >> 12;
 			else if (!aStatic && (la >> 12) == (lb >> 12))
 				owner = la >> 12;
+			unsigned int sa = (unsigned int)(la & 4095), sb = (unsigned int)(lb & 4095);
+			if (owner >= 0 && aStatic != bStatic)
+			{
+				// the static body gets one of the block's own static slots (find or insert)
+				const int g = aStatic ? a : b;
+				int* table = s.blockStatics + (size_t)owner * NSTATIC;
+				int slot = -1;
+				for (int k = 0; k < NSTATIC; k++)
+				{
+					int v = *((volatile int*)&table[k]);
+					if (v == -1) v = atomicCAS(&table[k], -1, g), v = (v == -1) ? g : v;
+					if (v == g)
+					{
+						slot = k;
+						break;
+					}
+				}
+				if (slot < 0)
+					owner = -1;  // more than NSTATIC static bodies under one block: this contact goes the global way
+				else if (aStatic)
+					sa = (unsigned int)(s.S + slot);
+				else
+					sb = (unsigned int)(s.S + slot);
+			}
 			s.contactBlock[c] = owner;
+			s.contactSlots[c] = sa | (sb << 16);
+			s.contactPair[c] = make_int2(aStatic ? -1 : a, bStatic ? -1 : b);
 		}
 		warpCountByKey(s.blockCount, owner, lane);
 	}
@@ -548,7 +578,7 @@ B3_D int colourFirstFit(unsigned long long* masks, int i0, int i1, int nb, LoadM
 	}
 }
 
-// ---- K2: interior contacts -> their block's list (+ slot pair); cross contacts -> cross list (+ first-fit colour)
+// ---- K2: interior contacts -> their block's list; cross contacts -> cross list (+ first-fit colour)
 __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s)
 {
 	extern __shared__ unsigned int sStart[];  // numBlocksMax + 1
@@ -590,78 +620,42 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 	for (int base = tid - lane; base < nContacts; base += stride)
 	{
 		const int c = base + lane;
-		bool cross = false;
-		int colour = -1;
-		if (c < nContacts)
+		int owner = c < nContacts ? s.contactBlock[c] : -1;
+		// interior: a place in the block's list (one atomic per distinct block in the warp)
+		const unsigned int pos = warpCountByKey(s.blockCursor, owner, lane);
+		if (owner >= 0)
 		{
-			int a, b, la, lb;
-			bool aStatic, bStatic;
-			contactBodies(s, c, a, b, aStatic, bStatic, la, lb);
-			int owner = s.contactBlock[c];
-			if (owner >= 0)
+			if (pos >= contactCap)
 			{
-				unsigned int sa = (unsigned int)(la & 4095), sb = (unsigned int)(lb & 4095);
-				if (aStatic != bStatic)
-				{
-					// the static body gets one of the block's own static slots (find or insert)
-					const int g = aStatic ? a : b;
-					int* table = s.blockStatics + (size_t)owner * NSTATIC;
-					int slot = -1;
-					for (int k = 0; k < NSTATIC; k++)
-					{
-						int v = *((volatile int*)&table[k]);
-						if (v == -1) v = atomicCAS(&table[k], -1, g), v = (v == -1) ? g : v;
-						if (v == g)
-						{
-							slot = k;
-							break;
-						}
-					}
-					if (slot < 0)
-						owner = -1;  // more than NSTATIC static bodies under one block: this contact goes the global way
-					else if (aStatic)
-						sa = (unsigned int)(s.S + slot);
-					else
-						sb = (unsigned int)(s.S + slot);
-				}
-				if (owner >= 0)
-				{
-					const unsigned int pos = atomicAdd(&s.blockCursor[owner], 1u);
-					if (pos >= contactCap)
-						owner = -1;
-					else
-					{
-						s.blockList[sStart[owner] + pos] = (unsigned int)c;
-						s.contactSlots[c] = sa | (sb << 16);
-					}
-				}
-				if (owner < 0) s.contactBlock[c] = -1;
+				owner = -1;
+				s.contactBlock[c] = -1;
 			}
-			if (owner < 0)
+			else
+				s.blockList[sStart[owner] + pos] = (unsigned int)c;
+		}
+		const bool cross = c < nContacts && owner < 0;
+		int colour = -1;
+		if (cross && s.colouring == 1)
+		{
+			const int2 pr = s.contactPair[c];
+			int i0 = 0, i1 = 0, nb = 0;
+			if (pr.x >= 0) i0 = pr.x, nb = 1;
+			if (pr.y >= 0)
 			{
-				cross = true;
-				if (s.colouring == 1)
-				{
-					int i0 = 0, i1 = 0, nb = 0;
-					if (!aStatic) i0 = a, nb = 1;
-					if (!bStatic)
-					{
-						if (nb)
-							i1 = b;
-						else
-							i0 = b;
-						nb++;
-					}
-					colour = colourFirstFit(s.bodyMask, i0, i1, nb, [](const unsigned long long* p) { return __ldcg(p); });
-					s.contactColour[c] = colour;
-					if (colour < 0)
-					{
-						// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
-						// (b3GpuPgsContactSolver.cpp:1497-1502); here the contact is left out of this step's solve
-						s.contacts[c].batchIdx = -2;
-						atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
-					}
-				}
+				if (nb)
+					i1 = pr.y;
+				else
+					i0 = pr.y;
+				nb++;
+			}
+			colour = colourFirstFit(s.bodyMask, i0, i1, nb, [](const unsigned long long* p) { return __ldcg(p); });
+			s.contactColour[c] = colour;
+			if (colour < 0)
+			{
+				// more than B3_MAX_NUM_BATCHES colours at one body: the reference errors out
+				// (b3GpuPgsContactSolver.cpp:1497-1502); here the contact is left out of this step's solve
+				s.contacts[c].batchIdx = -2;
+				atomicOr(&s.ctr[CTR_OVERFLOW], (unsigned int)OVF_BATCHES);
 			}
 		}
 		__syncwarp();
@@ -815,6 +809,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 	}
 	__syncthreads();
 	const int Kc = sKc;
+	{
+		// the row slots of the cross tiles (top of the buffers) start out as padding; solverCrossBuildKernel fills them
+		unsigned int crossTiles = 0;
+		for (int k = 0; k < MAX_BATCHES; k++) crossTiles += (sCrossHist[k] + 31u) >> 5;
+		const size_t first = (size_t)(s.tileCap - crossTiles) * 32u;
+		for (size_t k = (size_t)blockIdx.x * SETUP_THREADS + threadIdx.x; k < (size_t)crossTiles * 32u; k += (size_t)gridDim.x * SETUP_THREADS) s.tileSrc[first + k] = -1;
+	}
 
 	for (int blk = blockIdx.x; blk < s.numBlocksMax; blk += gridDim.x)
 	{
@@ -934,7 +935,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 		for (int i = threadIdx.x; i <= MAX_BATCHES; i += SETUP_THREADS) s.blockTileOff[(size_t)blk * (MAX_BATCHES + 1) + i] = sOff[i];
 		const unsigned int tileBase = sTileBase;
 		// (capacity: interior + cross contacts <= contact capacity, and the buffers hold capacity / 32 + padding tiles)
-		// ---- rows
+		// ---- which contact every row slot of the block's tiles is built from (the rows themselves are built by
+		// solverBuildRowsKernel, a warp per tile at full occupancy: this CTA's 512 threads cannot hide the latency of its
+		// block's ~4 000 contact / pose / inertia gathers)
+		{
+			const unsigned int nSlots = sOff[MAX_BATCHES] * 32u;
+			for (unsigned int k = threadIdx.x; k < nSlots; k += SETUP_THREADS) s.tileSrc[(size_t)tileBase * 32u + k] = -1;
+		}
+		__syncthreads();
 		for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
 		{
 			const int c = (int)list[i];
@@ -947,27 +955,14 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 			}
 			const unsigned int rank = atomicAdd(&sCursor[colour], 1u);
 			const unsigned int tile = tileBase + sOff[colour] + (rank >> 5);
-			const unsigned int row = rank & 31u;
 			s.contacts[c].batchIdx = Kc + colour;
-			buildRow(s, c, s.contactSlots[c], Kc + colour, s.tilesN + (size_t)tile * NT_STRIDE + row, s.tilesF + (size_t)tile * FT_STRIDE + row);
-		}
-		// padding rows of every colour's last tile
-		for (int k = threadIdx.x; k < MAX_BATCHES * 32; k += SETUP_THREADS)
-		{
-			const int colour = k >> 5;
-			const unsigned int cnt = sHist[colour];
-			const unsigned int rank = cnt + (unsigned int)(k & 31);
-			if (cnt != 0 && rank < ((cnt + 31u) & ~31u))
-			{
-				const unsigned int tile = tileBase + sOff[colour] + (rank >> 5);
-				buildPadding(s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
-			}
+			s.tileSrc[(size_t)tile * 32u + (rank & 31u)] = c;
 		}
 		__syncthreads();
 	}
 }
 
-// ---- K4: cross rows, at the top of the tile buffers in colour order
+// ---- K4: where the cross rows go: the top of the tile buffers, in colour order
 __global__ void __launch_bounds__(SETUP_THREADS) solverCrossBuildKernel(SetupArgs s)
 {
 	__shared__ unsigned int sHist[MAX_BATCHES], sOff[MAX_BATCHES + 1];
@@ -1000,18 +995,29 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverCrossBuildKernel(SetupArg
 		if (colour < 0) continue;
 		const unsigned int tile = crossBase + sOff[colour] + (rank >> 5);
 		s.contacts[c].batchIdx = colour;
-		buildRow(s, c, 0u, colour, s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
+		s.tileSrc[(size_t)tile * 32u + (rank & 31u)] = c;
 	}
-	for (int k = tid; k < MAX_BATCHES * 32; k += stride)
+}
+
+// ---- K5: the rows, a warp per tile: lane r builds row r from the contact the layout kernels put there (scattered reads of
+// whole 112-byte contact records, coalesced 512-byte stores of the row fields)
+__global__ void __launch_bounds__(256, 2) solverBuildRowsKernel(SetupArgs s)
+{
+	const unsigned int interiorTiles = s.misc[MISC_TILE_CURSOR];
+	const unsigned int crossTiles = s.crossTileOff[MAX_BATCHES];
+	const unsigned int total = interiorTiles + crossTiles;
+	const int lane = threadIdx.x & 31;
+	for (unsigned int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < total; t += gridDim.x * (blockDim.x >> 5))
 	{
-		const int colour = k >> 5;
-		const unsigned int cnt = sHist[colour];
-		const unsigned int rank = cnt + (unsigned int)(k & 31);
-		if (cnt != 0 && rank < ((cnt + 31u) & ~31u))
-		{
-			const unsigned int tile = crossBase + sOff[colour] + (rank >> 5);
-			buildPadding(s.tilesN + (size_t)tile * NT_STRIDE + (rank & 31u), s.tilesF + (size_t)tile * FT_STRIDE + (rank & 31u));
-		}
+		const bool interior = t < interiorTiles;
+		const unsigned int tile = interior ? t : s.tileCap - crossTiles + (t - interiorTiles);
+		const int c = s.tileSrc[(size_t)tile * 32u + lane];
+		float4* tn = s.tilesN + (size_t)tile * NT_STRIDE + lane;
+		float4* tf = s.tilesF + (size_t)tile * FT_STRIDE + lane;
+		if (c < 0)
+			buildPadding(tn, tf);
+		else
+			buildRow(s, c, interior ? s.contactSlots[c] : 0u, s.contacts[c].batchIdx, tn, tf);
 	}
 }
 
@@ -1699,6 +1705,8 @@ static int fillSetupArgs(World* w, SetupArgs& s)
 	B3_TRY(w->dContactBlock.reserve(nc));
 	B3_TRY(w->dContactSlots.reserve(nc));
 	B3_TRY(w->dContactColour.reserve(nc));
+	B3_TRY(w->dContactPair.reserve(nc));
+	B3_TRY(w->dTileSrc.reserve(tiles * 32));
 	B3_TRY(w->dBlockList.reserve(nc));
 	B3_TRY(w->dCrossList.reserve(nc));
 	B3_TRY(w->dBodyMask.reserve(2 * nb));
@@ -1719,6 +1727,8 @@ static int fillSetupArgs(World* w, SetupArgs& s)
 	s.contactBlock = w->dContactBlock.ptr;
 	s.contactSlots = w->dContactSlots.ptr;
 	s.contactColour = w->dContactColour.ptr;
+	s.contactPair = w->dContactPair.ptr;
+	s.tileSrc = w->dTileSrc.ptr;
 	unsigned int* scr = w->dSolverScratch.ptr;
 	s.blockCount = scr;
 	s.blockCursor = scr + B;
@@ -1755,7 +1765,7 @@ int launchSolverSetup(World* w)
 	const int B = w->partBlocksMax;
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dSolverScratch.ptr, 0, sizeof(unsigned int) * ((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM), st));
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dBlockStatics.ptr, 0xff, sizeof(int) * (size_t)B * NSTATIC, st));
-	const int grid = w->smCount * 2;
+	const int grid = w->smCount * 4;
 	solverClassifyKernel<<<grid, SETUP_THREADS, 0, st>>>(s);
 	B3_LAUNCH_CHECK();
 	solverScatterKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * ((size_t)B + 1), st>>>(s);
@@ -1779,6 +1789,8 @@ int launchSolverSetup(World* w)
 		B3_LAUNCH_CHECK();
 	}
 	solverCrossBuildKernel<<<grid, SETUP_THREADS, 0, st>>>(s);
+	B3_LAUNCH_CHECK();
+	solverBuildRowsKernel<<<w->smCount * 6, 256, 0, st>>>(s);
 	B3_LAUNCH_CHECK();
 	w->solverMisc = s.misc;
 	return 0;

@@ -18,7 +18,7 @@ data = []
 tot = 0.0
 agg = {}
 for k, r in enumerate(rows[hdr + 1:]):
-    if len(r) <= isamp or not r[0]:
+    if len(r) <= isamp or not r[0] or r[0] == "Address":
         continue
     v = f(r[isamp])
     tot += v
