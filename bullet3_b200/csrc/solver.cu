@@ -29,8 +29,9 @@
 
 namespace b3b200
 {
-constexpr int ITER_THREADS = 256;
-constexpr int ITER_WARPS = ITER_THREADS / 32;
+// threads of the iteration kernels, per phase (normal rows: 44 registers of row data per tile in flight; friction: 20):
+// as many warps as keep the row solve free of spills -- more warps = fewer tiles per warp and colour
+constexpr int ITER_THREADS_NORMAL = 256, ITER_THREADS_FRICTION = 256;
 constexpr int SETUP_THREADS = 512;
 constexpr int S_MAX = 2560;       // dynamic bodies per block: (S_MAX + NSTATIC) * (80 + 6) B = 220 KB of shared memory
 constexpr int S_MIN = 1024;       // below this a block is not worth a grid barrier
@@ -46,7 +47,6 @@ constexpr int NT_STRIDE = NT_FIELDS * 32;
 // friction tile, 4 float4 per row: {centre, damping flag} | {t0, fJacCoeffInv[0]} | {t1, fJacCoeffInv[1]} | {fLambda[2], -, -}
 constexpr int FT_FIELDS = 4, FT_LAMBDA = 3;
 constexpr int FT_STRIDE = FT_FIELDS * 32;
-constexpr int TAIL_TILES = ITER_WARPS;  // cross colours this small are solved by CTA 0 alone (cheaper than a grid barrier)
 constexpr unsigned int INVALID_IDS = 0xffffffffu;
 constexpr int ITER_SMEM_PER_SLOT = (int)(sizeof(float4) * 5 + sizeof(int) + sizeof(unsigned short));
 constexpr int ITER_SMEM_MAX = ITER_SMEM_PER_SLOT * (S_MAX + NSTATIC);
@@ -1319,6 +1319,25 @@ B3_D void solveRowGlobal(float4* tilesN, float4* tilesF, const CrossBodies& cb, 
 }
 B3_D int4 loadTail(const float4* tilesN, unsigned int tile, int lane) { return reinterpret_cast<const int4*>(tilesN)[(size_t)tile * NT_STRIDE + NT_TAIL * 32 + lane]; }
 
+// The rows of a step (~150 MB on the bench scene) do not stay in L2 between passes, and a warp holds only one tile ahead in
+// registers: with the row solve down to a few hundred cycles, a tile's HBM latency would be exposed at every tile.  One
+// lane asks for the whole tile (one contiguous range) to be pulled into L2 a few tiles ahead; the register loads then hit L2.
+B3_D void prefetchL2(const void* p, unsigned int bytes) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory"); }
+template <int PHASE>
+B3_D void prefetchTile(const float4* tilesN, const float4* tilesF, unsigned int tile)
+{
+	const float4* tn = tilesN + (size_t)tile * NT_STRIDE;
+	if (PHASE == 0)
+		prefetchL2(tn, NT_TAIL * 512);
+	else
+	{
+		prefetchL2(tn, 512);
+		prefetchL2(tn + NT_LAMBDA * 32, 512);
+		prefetchL2(tilesF + (size_t)tile * FT_STRIDE, FT_FIELDS * 512);
+	}
+}
+constexpr int PF_AHEAD = 4;  // tiles (of the same warp) between the L2 prefetch and the solve
+
 struct BlockView
 {
 	int blk;
@@ -1331,8 +1350,8 @@ struct BlockView
 // all colours of one block, velocities in shared memory.  Warp w owns the tiles w, w + ITER_WARPS, ... of the block's tile
 // sequence (the same warp every pass, so a tile's lambdas are read back by the thread that wrote them) and fetches its
 // next tile into a second register set while it solves the current one; one __syncthreads() per colour.
-template <int PHASE>
-__device__ __noinline__ void solveBlockInterior(float4* tilesN, float4* tilesF, unsigned int tileBase, unsigned int numTiles, int numColours,
+template <int PHASE, int ITER_WARPS>
+B3_D void solveBlockInterior(float4* tilesN, float4* tilesF, unsigned int tileBase, unsigned int numTiles, int numColours,
 												const unsigned int* sTileOff, SharedBodies sb_, unsigned long long* probe)
 {
 	int probeN = 256;
@@ -1340,11 +1359,19 @@ __device__ __noinline__ void solveBlockInterior(float4* tilesN, float4* tilesF, 
 	unsigned int T = (unsigned int)warp;
 	int m = 0;
 	RowRegs<PHASE> ra, rb;
+	if (lane == 0)
+		for (int j = 2; j < PF_AHEAD; j++)
+			if (T + j * ITER_WARPS < numTiles) prefetchTile<PHASE>(tilesN, tilesF, tileBase + T + j * ITER_WARPS);
 	if (T < numTiles) loadRowRegs<PHASE>(tilesN, tilesF, tileBase + T, lane, ra);
 	while (T < numTiles)
 	{
 		unsigned int T2 = T + ITER_WARPS;
 		if (T2 < numTiles) loadRowRegs<PHASE>(tilesN, tilesF, tileBase + T2, lane, rb);
+		if (lane == 0)
+		{
+			if (T + PF_AHEAD * ITER_WARPS < numTiles) prefetchTile<PHASE>(tilesN, tilesF, tileBase + T + PF_AHEAD * ITER_WARPS);
+			if (T + (PF_AHEAD + 1) * ITER_WARPS < numTiles) prefetchTile<PHASE>(tilesN, tilesF, tileBase + T + (PF_AHEAD + 1) * ITER_WARPS);
+		}
 
 		while (T >= sTileOff[m + 1])
 		{
@@ -1386,9 +1413,9 @@ __device__ __noinline__ void solveBlockInterior(float4* tilesN, float4* tilesF, 
 }
 
 // cross colours of one pass: global velocities, a grid barrier per colour; the next colour's rows are fetched while the
-// other CTAs arrive.  Trailing colours of at most TAIL_TILES tiles are solved by CTA 0 alone between __syncthreads().
-template <int PHASE>
-__device__ __noinline__ void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, GridBarrier& bar, int Kc, int tailStart,
+// other CTAs arrive.  Trailing colours of at most one tile per warp of a CTA are solved by CTA 0 alone between __syncthreads().
+template <int PHASE, int ITER_WARPS>
+B3_D void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, GridBarrier& bar, int Kc, int tailStart,
 											   const unsigned int* sCrossOff, unsigned int crossBase)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1449,16 +1476,22 @@ __device__ __noinline__ void solveCrossColours(float4* tilesN, float4* tilesF, C
 #define B3_PROBE(i)                                                              \
 	do                                                                           \
 	{                                                                            \
-		if (s.probe && blockIdx.x == 0 && threadIdx.x == 0 && probeN < 512)      \
+		if (s.probe && blockIdx.x == 0 && threadIdx.x == 0 && probeN < 250)      \
 		{                                                                        \
 			unsigned long long t_;                                               \
 			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));               \
 			s.probe[probeN++] = (t_ << 4) | (unsigned long long)(i);             \
 		}                                                                        \
 	} while (0)
+// One launch per phase (all iterations of the normal rows, then all iterations of the friction rows): a kernel that holds only
+// one phase's code keeps its row registers without spilling -- with ~6 KB of L1 left beside the block state, every spill
+// is an L2 round trip on the critical path.
+template <int PHASE, int ITER_THREADS>
 __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs s)
 {
-	int probeN = 0;
+	constexpr int ITER_WARPS = ITER_THREADS / 32;
+	constexpr int TAIL_TILES = ITER_WARPS;  // cross colours this small are solved by CTA 0 alone (cheaper than a grid barrier)
+	int probeN = PHASE * 100;
 	extern __shared__ float4 smem4[];
 	__shared__ unsigned int sTileOff[MAX_BATCHES + 1], sCrossOff[MAX_BATCHES + 1];
 	__shared__ int sNumBoundary;
@@ -1554,8 +1587,6 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 		__syncthreads();
 	}
 
-#pragma unroll 1
-	for (int phase = 0; phase < 2; phase++)
 	{
 #pragma unroll 1
 		for (int iter = 0; iter < s.iterations; iter++)
@@ -1578,10 +1609,7 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 				}
 				B3_PROBE(2);
 				bar.arrive();
-				if (phase == 0)
-					solveCrossColours<0>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
-				else
-					solveCrossColours<1>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
+				solveCrossColours<PHASE, ITER_WARPS>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
 				B3_PROBE(3);
 				if (mine.blk >= 0)
 				{
@@ -1601,10 +1629,7 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 			{
 				if (mine.blk >= 0)
 				{
-					if (phase == 0)
-						solveBlockInterior<0>(s.tilesN, s.tilesF, mine.tileBase, mine.numTiles, mine.numColours, sTileOff, sb_, (blockIdx.x == 0 && iter == 1) ? s.probe : nullptr);
-					else
-						solveBlockInterior<1>(s.tilesN, s.tilesF, mine.tileBase, mine.numTiles, mine.numColours, sTileOff, sb_, nullptr);
+					solveBlockInterior<PHASE, ITER_WARPS>(s.tilesN, s.tilesF, mine.tileBase, mine.numTiles, mine.numColours, sTileOff, sb_, (PHASE == 0 && blockIdx.x == 0 && iter == 1) ? s.probe : nullptr);
 				}
 			}
 			else
@@ -1615,10 +1640,7 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 					const BlockView v = view(blk);
 					loadBlock(v, false);
 					__syncthreads();
-					if (phase == 0)
-						solveBlockInterior<0>(s.tilesN, s.tilesF, v.tileBase, v.numTiles, v.numColours, sTileOff, sb_, nullptr);
-					else
-						solveBlockInterior<1>(s.tilesN, s.tilesF, v.tileBase, v.numTiles, v.numColours, sTileOff, sb_, nullptr);
+					solveBlockInterior<PHASE, ITER_WARPS>(s.tilesN, s.tilesF, v.tileBase, v.numTiles, v.numColours, sTileOff, sb_, nullptr);
 					storeBlock(v);
 				}
 			}
@@ -1782,7 +1804,8 @@ int launchSolverSetup(World* w)
 		if (!w->solverAttrSet)
 		{
 			B3_CUDA_CHECK(cudaFuncSetAttribute(solverBlockSetupKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITER_SMEM_MAX)));
+			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel<0, ITER_THREADS_NORMAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITER_SMEM_MAX)));
+			B3_CUDA_CHECK(cudaFuncSetAttribute(solverIterateKernel<1, ITER_THREADS_FRICTION>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ITER_SMEM_MAX)));
 			w->solverAttrSet = true;
 		}
 		solverBlockSetupKernel<<<std::min(B, w->smCount * 2), SETUP_THREADS, smem, st>>>(s);
@@ -1828,10 +1851,13 @@ int launchSolverIterate(World* w)
 	const size_t smem = (size_t)ITER_SMEM_PER_SLOT * (size_t)(w->partS + NSTATIC);
 	// one CTA per SM at most (cooperative: all CTAs co-resident); small worlds use as many CTAs as they have blocks
 	const int grid = std::max(1, std::min(w->smCount, w->partBlocksMax));
-	dim3 g(grid), b(ITER_THREADS);
+	dim3 g(grid), b0(ITER_THREADS_NORMAL), b1(ITER_THREADS_FRICTION);
 	void* args[] = {&s};
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
-	B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateKernel, g, b, args, smem, w->stream));
+	B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateKernel<0, ITER_THREADS_NORMAL>, g, b0, args, smem, w->stream));
+	g_launchCount++;
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
+	B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateKernel<1, ITER_THREADS_FRICTION>, g, b1, args, smem, w->stream));
 	g_launchCount++;
 	return 0;
 }
