@@ -227,6 +227,71 @@ __global__ void boundCountKernel(const b3b200_sort_data* __restrict__ sorted, in
 	if (i == 0 || sorted[i - 1].key != k) lower[k] = i;
 	if (i == n - 1 || sorted[i + 1].key != k) upper[k] = i + 1;
 }
+// b3BoundSearchCL BOUND_LOWER / BOUND_UPPER (b3BoundSearchCL.cpp:74-110, host twin :139-172): dst[k] = first index holding key k /
+// one past the last; entries of keys that do not occur are left as the caller passed them
+__global__ void boundLowerUpperKernel(const b3b200_sort_data* __restrict__ sorted, int n, unsigned int* __restrict__ dst, int numBuckets, int upper)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned int k = sorted[i].key;
+	if (k >= (unsigned int)numBuckets) return;
+	if (!upper && (i == 0 || sorted[i - 1].key != k)) dst[k] = i;
+	if (upper && (i == n - 1 || sorted[i + 1].key != k)) dst[k] = i + 1;
+}
+
+// b3PrefixScanFloat4CL (b3PrefixScanFloat4CL.cpp:12-120): exclusive scan of the xyz of float4 values (w is not summed, like
+// b3Vector3::operator+=), one CTA, warp-shuffle scans
+constexpr int SCAN4_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN4_THREADS) scanFloat4Kernel(const float4* __restrict__ src, float4* __restrict__ dst, int n)
+{
+	__shared__ float4 warpSums[32];
+	__shared__ float4 carry;
+	if (threadIdx.x == 0) carry = make_float4(0.f, 0.f, 0.f, 0.f);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int base = 0; base < n; base += SCAN4_THREADS)
+	{
+		const int i = base + threadIdx.x;
+		float4 v = i < n ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+		float4 incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const float tx = __shfl_up_sync(0xffffffffu, incl.x, o), ty = __shfl_up_sync(0xffffffffu, incl.y, o), tz = __shfl_up_sync(0xffffffffu, incl.z, o);
+			if (lane >= o)
+			{
+				incl.x += tx;
+				incl.y += ty;
+				incl.z += tz;
+			}
+		}
+		if (lane == 31) warpSums[warp] = incl;
+		__syncthreads();
+		if (warp == 0)
+		{
+			float4 w = warpSums[lane], wi = w;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const float tx = __shfl_up_sync(0xffffffffu, wi.x, o), ty = __shfl_up_sync(0xffffffffu, wi.y, o), tz = __shfl_up_sync(0xffffffffu, wi.z, o);
+				if (lane >= o)
+				{
+					wi.x += tx;
+					wi.y += ty;
+					wi.z += tz;
+				}
+			}
+			warpSums[lane] = make_float4(wi.x - w.x, wi.y - w.y, wi.z - w.z, 0.f);  // exclusive
+		}
+		__syncthreads();
+		const float4 c = carry, ws = warpSums[warp];
+		if (i < n) dst[i] = make_float4(c.x + ws.x + (incl.x - v.x), c.y + ws.y + (incl.y - v.y), c.z + ws.z + (incl.z - v.z), 0.f);
+		__syncthreads();
+		if (threadIdx.x == SCAN4_THREADS - 1) carry = make_float4(c.x + ws.x + incl.x, c.y + ws.y + incl.y, c.z + ws.z + incl.z, 0.f);
+		__syncthreads();
+	}
+}
+
 __global__ void subKernel(const unsigned int* lower, const unsigned int* upper, unsigned int* counts, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,5 +412,45 @@ extern "C" int b3b200_fill_u32(int device, unsigned int* dst, unsigned int value
 	fillKernel<<<divUp(n, 256), 256>>>(d.ptr, value, n, offset);
 	B3_LAUNCH_CHECK();
 	B3_CUDA_CHECK(cudaMemcpy(dst, d.ptr, sizeof(unsigned int) * ((size_t)n + offset), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// b3BoundSearchCL::execute with BOUND_LOWER (0) / BOUND_UPPER (1) / COUNT (2) (b3BoundSearchCL.cpp:74-137).  `dst` comes in with
+// the caller's initial values (the reference only writes the entries of keys that occur) and goes out with the result.
+extern "C" int b3b200_bound_search(int device, const b3b200_sort_data* sorted, int n, unsigned int* dst, int numBuckets, int option)
+{
+	if (option == 2) return b3b200_bound_search_count(device, sorted, n, dst, numBuckets);
+	if (n < 0 || numBuckets <= 0 || !dst || (n > 0 && !sorted) || option < 0 || option > 2) return B3B200_ERR_INVALID;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<b3b200_sort_data> d;
+	DevBuf<unsigned int> out;
+	B3_TRY(out.reserve(numBuckets));
+	B3_CUDA_CHECK(cudaMemcpy(out.ptr, dst, sizeof(unsigned int) * numBuckets, cudaMemcpyHostToDevice));
+	if (n > 0)
+	{
+		B3_TRY(d.reserve(n));
+		B3_CUDA_CHECK(cudaMemcpy(d.ptr, sorted, sizeof(b3b200_sort_data) * n, cudaMemcpyHostToDevice));
+		boundLowerUpperKernel<<<divUp(n, 256), 256>>>(d.ptr, n, out.ptr, numBuckets, option);
+		B3_LAUNCH_CHECK();
+	}
+	B3_CUDA_CHECK(cudaMemcpy(dst, out.ptr, sizeof(unsigned int) * numBuckets, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+// b3PrefixScanFloat4CL::execute (b3PrefixScanFloat4CL.cpp:44-93): exclusive scan of xyz; `sum` = the LAST OUTPUT element like the
+// reference returns it (dst[n-1], not the grand total: b3PrefixScanFloat4CL.cpp:116-119)
+extern "C" int b3b200_prefix_scan_float4(int device, const b3b200_float4* src, b3b200_float4* dst, int n, b3b200_float4* sum)
+{
+	if (n < 0 || (n > 0 && (!src || !dst))) return B3B200_ERR_INVALID;
+	if (n == 0) return 0;
+	B3_CUDA_CHECK(cudaSetDevice(device));
+	DevBuf<float4> a, b;
+	B3_TRY(a.reserve(n));
+	B3_TRY(b.reserve(n));
+	B3_CUDA_CHECK(cudaMemcpy(a.ptr, src, sizeof(float4) * n, cudaMemcpyHostToDevice));
+	scanFloat4Kernel<<<1, SCAN4_THREADS>>>(a.ptr, b.ptr, n);
+	B3_LAUNCH_CHECK();
+	B3_CUDA_CHECK(cudaMemcpy(dst, b.ptr, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+	if (sum) *sum = dst[n - 1];
 	return 0;
 }

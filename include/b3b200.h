@@ -289,6 +289,10 @@ int b3b200_radix_sort_keys(int device, unsigned int* keys, int n);
 int b3b200_prefix_scan_u32(int device, const unsigned int* src, unsigned int* dst, int n, unsigned int* sum);
 int b3b200_bound_search_count(int device, const b3b200_sort_data* sorted, int n, unsigned int* counts, int numBuckets);
 int b3b200_fill_u32(int device, unsigned int* dst, unsigned int value, int n, int offset);
+/* b3BoundSearchCL::execute, option BOUND_LOWER 0 / BOUND_UPPER 1 / COUNT 2 (b3BoundSearchCL.h:28-33, .cpp:74-137); dst is in/out */
+int b3b200_bound_search(int device, const b3b200_sort_data* sorted, int n, unsigned int* dst, int numBuckets, int option);
+/* b3PrefixScanFloat4CL::execute (b3PrefixScanFloat4CL.cpp:44-93): exclusive scan of xyz, sum = dst[n-1] like the reference */
+int b3b200_prefix_scan_float4(int device, const b3b200_float4* src, b3b200_float4* dst, int n, b3b200_float4* sum);
 
 #ifdef __cplusplus
 }

@@ -1636,8 +1636,19 @@ void orc_solve(b3b200_constraint4* cs, const int* batchOffsets, int numBatches, 
 //  SolveContactJacobiKernel :527-651, AverageVelocitiesKernel :428-456,
 //  SolveFrictionJacobiKernel :654-811, UpdateBodyVelocitiesKernel :815-833.)
 // Split slots are handed out in contact-index order (the reference's atomic order is arbitrary).
+// hostOrder = 0: the order of the GPU path (solveContacts, :788-855): per iteration contacts, average, friction, average.
+// hostOrder = 1: the order of the reference's host twin solveGroupHost (:462-697): all contact iterations, then all friction
+// iterations -- the variant that is pinned bit for bit against the compiled reference (tests/test_oracle_vs_refcl.py); the two
+// differ in nothing but this loop nest.
+void orc_jacobi_solve_ordered(const b3b200_contact4* contacts, int n, b3b200_rigid_body* bodies, int numBodies, const b3b200_inertia* inertias, int staticIdx,
+							  int iterations, float dt, float positionDrift, float positionConstraintCoeff, int hostOrder);
 void orc_jacobi_solve(const b3b200_contact4* contacts, int n, b3b200_rigid_body* bodies, int numBodies, const b3b200_inertia* inertias, int staticIdx,
 					  int iterations, float dt, float positionDrift, float positionConstraintCoeff)
+{
+	orc_jacobi_solve_ordered(contacts, n, bodies, numBodies, inertias, staticIdx, iterations, dt, positionDrift, positionConstraintCoeff, 0);
+}
+void orc_jacobi_solve_ordered(const b3b200_contact4* contacts, int n, b3b200_rigid_body* bodies, int numBodies, const b3b200_inertia* inertias, int staticIdx,
+							  int iterations, float dt, float positionDrift, float positionConstraintCoeff, int hostOrder)
 {
 	std::vector<unsigned int> bodyCount(numBodies, 0), bodyOffset(numBodies, 0);
 	std::vector<int> slotA(n, 0), slotB(n, 0);
@@ -1720,10 +1731,11 @@ void orc_jacobi_solve(const b3b200_contact4* contacts, int n, b3b200_rigid_body*
 			}
 		}
 	};
-	for (int iter = 0; iter < iterations; iter++)
+	// sweep = (iteration, phase) in the order of the chosen variant
+	for (int sweep = 0; sweep < 2 * iterations; sweep++)
 	{
-		for (int phase = 0; phase < 2; phase++)
 		{
+			const int phase = hostOrder ? (sweep >= iterations ? 1 : 0) : (sweep & 1);
 			for (int i = 0; i < n; i++)
 			{
 				b3b200_constraint4& c = cs[i];
@@ -1783,10 +1795,16 @@ void orc_jacobi_solve(const b3b200_contact4* contacts, int n, b3b200_rigid_body*
 					V3 t[2];
 					planeSpace1(nn, t[0], t[1]);
 					V3 r0 = sub(center, posA), r1 = sub(center, posB);
+					// The reference's host twin (solveFriction, b3GpuJacobiContactSolver.cpp:239-312) sums velocity + delta ONCE before the two
+					// tangent directions and damps with that sum, and only touches the deltas of dynamic bodies; the kernel
+					// (solveFrictionConstraint, solverUtils.cl:654-790) re-evaluates the sum per direction and damps with the body's own
+					// angular velocity.  hostOrder selects the twin's form -- the only other difference between the two variants.
+					const V3 sumLA = add(linVelA, dLA), sumAA = add(angVelA, dAA), sumLB = add(linVelB, dLB), sumAB = add(angVelB, dAB);
 					for (int k = 0; k < 2; k++)
 					{
 						V3 a0 = cross(r0, t[k]), a1 = neg(cross(r1, t[k]));
-						float rambdaDt = calcRelVel(t[k], neg(t[k]), a0, a1, add(linVelA, dLA), add(angVelA, dAA), add(linVelB, dLB), add(angVelB, dAB));
+						float rambdaDt = hostOrder ? calcRelVel(t[k], neg(t[k]), a0, a1, sumLA, sumAA, sumLB, sumAB)
+												   : calcRelVel(t[k], neg(t[k]), a0, a1, add(linVelA, dLA), add(angVelA, dAA), add(linVelB, dLB), add(angVelB, dAB));
 						rambdaDt *= c.fJacCoeffInv[k];
 						float prevSum = c.fAppliedRambdaDt[k];
 						float updated = prevSum + rambdaDt;
@@ -1794,17 +1812,23 @@ void orc_jacobi_solve(const b3b200_contact4* contacts, int n, b3b200_rigid_body*
 						updated = std::min(updated, maxR);
 						rambdaDt = updated - prevSum;
 						c.fAppliedRambdaDt[k] = updated;
-						dLA = add(dLA, mul(mul(t[k], invMassA), rambdaDt));
-						dLB = add(dLB, mul(mul(neg(t[k]), invMassB), rambdaDt));
-						dAA = add(dAA, mul(matMul(IA, a0), rambdaDt));
-						dAB = add(dAB, mul(matMul(IB, a1), rambdaDt));
+						if (!hostOrder || invMassA)
+						{
+							dLA = add(dLA, mul(mul(t[k], invMassA), rambdaDt));
+							dAA = add(dAA, mul(matMul(IA, a0), rambdaDt));
+						}
+						if (!hostOrder || invMassB)
+						{
+							dLB = add(dLB, mul(mul(neg(t[k]), invMassB), rambdaDt));
+							dAB = add(dAB, mul(matMul(IB, a1), rambdaDt));
+						}
 					}
 					V3 ab = normalized(sub(posB, posA)), ac = normalized(sub(center, posA));
 					if (dot(ab, ac) > 0.95f || (invMassA == 0.f || invMassB == 0.f))
 					{
-						float angNA = dot(nn, angVelA), angNB = dot(nn, angVelB);
-						dAA = sub(dAA, mul(nn, angNA * 0.1f));
-						dAB = sub(dAB, mul(nn, angNB * 0.1f));
+						float angNA = dot(nn, hostOrder ? sumAA : angVelA), angNB = dot(nn, hostOrder ? sumAB : angVelB);
+						if (!hostOrder || invMassA) dAA = sub(dAA, mul(nn, angNA * 0.1f));
+						if (!hostOrder || invMassB) dAB = sub(dAB, mul(nn, angNB * 0.1f));
 					}
 				}
 				if (invMassA)

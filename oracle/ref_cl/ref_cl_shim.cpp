@@ -18,6 +18,9 @@
 #include "Bullet3OpenCL/ParallelPrimitives/b3BoundSearchCL.h"
 #include "Bullet3OpenCL/BroadphaseCollision/b3GpuSapBroadphase.h"
 #include "Bullet3OpenCL/RigidBody/b3Solver.h"
+#include "Bullet3OpenCL/RigidBody/b3GpuJacobiContactSolver.h"
+#include <unistd.h>
+#include <fcntl.h>
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhase.h"
 #include "Bullet3OpenCL/RigidBody/b3GpuNarrowPhaseInternalData.h"
 #include "Bullet3OpenCL/Raycast/b3GpuRaycast.h"
@@ -144,6 +147,44 @@ void refcl_bound_search_count(const b3b200_sort_data* sorted, int n, unsigned in
 	for (int i = 0; i < numBuckets; i++) c[i] = 0;
 	search.executeHost(a, n, c, numBuckets, b3BoundSearchCL::COUNT);
 	memcpy(counts, &c[0], 4 * (size_t)numBuckets);
+}
+
+// b3BoundSearchCL::executeHost with BOUND_LOWER (0) / BOUND_UPPER (1) / COUNT (2); dst is in/out
+void refcl_bound_search(const b3b200_sort_data* sorted, int n, unsigned int* dst, int numBuckets, int option)
+{
+	init();
+	b3BoundSearchCL search(CTX, DEV, Q, numBuckets);
+	b3AlignedObjectArray<b3SortData> a;
+	b3AlignedObjectArray<unsigned int> c;
+	a.resize(n);
+	c.resize(numBuckets);
+	if (n) memcpy(&a[0], sorted, sizeof(b3SortData) * (size_t)n);
+	memcpy(&c[0], dst, 4 * (size_t)numBuckets);
+	search.executeHost(a, n, c, numBuckets, option == 0 ? b3BoundSearchCL::BOUND_LOWER : (option == 1 ? b3BoundSearchCL::BOUND_UPPER : b3BoundSearchCL::COUNT));
+	memcpy(dst, &c[0], 4 * (size_t)numBuckets);
+}
+
+// b3GpuJacobiContactSolver::solveGroupHost (b3GpuJacobiContactSolver.cpp:462-697): the reference's host twin of the mass-splitting
+// Jacobi solver; bodies are updated in place
+void refcl_jacobi_solve_host(b3b200_contact4* contacts, int n, b3b200_rigid_body* bodies, int numBodies, b3b200_inertia* inertias, int staticIdx, int iterations,
+							 float dt, float positionDrift, float positionConstraintCoeff)
+{
+	init();
+	b3GpuJacobiContactSolver solver(CTX, DEV, Q, n > 512 ? n : 512);
+	b3JacobiSolverInfo info;
+	info.m_fixedBodyIndex = staticIdx;
+	info.m_deltaTime = dt;
+	info.m_positionDrift = positionDrift;
+	info.m_positionConstraintCoeff = positionConstraintCoeff;
+	info.m_numIterations = iterations;
+	fflush(stdout);
+	const int saved = dup(1), devnull = open("/dev/null", O_WRONLY);  // it printf()s totalNumSplitBodies
+	if (saved >= 0 && devnull >= 0) dup2(devnull, 1);
+	solver.solveGroupHost((b3RigidBodyData*)bodies, (b3InertiaData*)inertias, numBodies, (b3Contact4*)contacts, n, info);
+	fflush(stdout);
+	if (saved >= 0 && devnull >= 0) dup2(saved, 1);
+	if (saved >= 0) close(saved);
+	if (devnull >= 0) close(devnull);
 }
 
 // ------------------------------------------------------------------ narrowphase (CHECK_ON_HOST build)

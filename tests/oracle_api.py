@@ -160,12 +160,24 @@ def sorted_pair_set(pairs):
     return xy[order]
 
 
-def jacobi_solve(contacts, bodies, inertias, static_idx, iterations, dt=1.0 / 60.0, drift=0.005, coeff=0.99):
+def jacobi_solve(contacts, bodies, inertias, static_idx, iterations, dt=1.0 / 60.0, drift=0.005, coeff=0.99, host_order=False):
+    """host_order=False: the GPU path's order (contacts, average, friction, average per iteration); True: the order of the reference's
+    host twin solveGroupHost (all contact iterations, then all friction iterations) -- same code, one switch"""
     contacts = _arr(contacts, capi.contact4_t)
     bodies = _arr(bodies, capi.rigid_body_t).copy()
     inertias = _arr(inertias, capi.inertia_t)
-    oracle().orc_jacobi_solve(P(contacts), len(contacts), P(bodies), len(bodies), P(inertias), int(static_idx), int(iterations),
-                              C.c_float(dt), C.c_float(drift), C.c_float(coeff))
+    oracle().orc_jacobi_solve_ordered(P(contacts), len(contacts), P(bodies), len(bodies), P(inertias), int(static_idx), int(iterations),
+                                      C.c_float(dt), C.c_float(drift), C.c_float(coeff), int(bool(host_order)))
+    return bodies
+
+
+def refcl_jacobi_solve_host(contacts, bodies, inertias, static_idx, iterations, dt=1.0 / 60.0, drift=0.005, coeff=0.99):
+    """b3GpuJacobiContactSolver::solveGroupHost of the compiled reference"""
+    contacts = _arr(contacts, capi.contact4_t).copy()
+    bodies = _arr(bodies, capi.rigid_body_t).copy()
+    inertias = _arr(inertias, capi.inertia_t).copy()
+    refcl().refcl_jacobi_solve_host(P(contacts), len(contacts), P(bodies), len(bodies), P(inertias), int(static_idx), int(iterations),
+                                    C.c_float(dt), C.c_float(drift), C.c_float(coeff))
     return bodies
 
 

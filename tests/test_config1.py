@@ -114,3 +114,62 @@ def test_config1_600_steps_against_the_reference_cpu_pipeline():
         total_contacts += len(rc)
         ref.stage(3, DT)
     assert total_contacts > 600 * 1000
+
+
+# ------------------------------------------------------------------ long trajectories: statistics against the reference's own run
+def pile_statistics(bodies, contacts, ground_top=0.0):
+    """what north_star asks to compare for chaotic long runs: kinetic + potential energy per body, rest height of the pile,
+    speed distribution and penetration-depth statistics of the contact points"""
+    dyn = bodies["invMass"] != 0
+    v = bodies["linVel"][dyn, :3].astype(np.float64)
+    w = bodies["angVel"][dyn, :3].astype(np.float64)
+    y = bodies["pos"][dyn, 1].astype(np.float64)
+    depth = np.concatenate([contacts["worldPosB"][contacts["worldNormalOnB"][:, 3] > k, k, 3] for k in range(4)]).astype(np.float64) if len(contacts) else np.zeros(1)
+    return {"kinetic": float(0.5 * (v * v).sum(1).mean() + 0.5 * 0.2 * (w * w).sum(1).mean()), "potential": float(9.8 * y.mean()), "mean_y": float(y.mean()),
+            "min_y": float(y.min()), "max_y": float(y.max()), "median_speed": float(np.median(np.linalg.norm(v, axis=1))),
+            "depth_mean": float(depth.mean()), "depth_p01": float(np.percentile(depth, 1)), "depth_min": float(depth.min()), "contacts": len(contacts)}
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(not oa.refcl_available(), reason="compiled reference host twins (oracle/_ref/libb3refcl.so) not built")
+def test_trajectory_statistics_match_the_reference_run():
+    """the same 8 x 6 x 8 box pile stepped 240 times by this library and by the reference's own b3GpuRigidBodyPipeline (unmodified,
+    host twins): the dynamics are chaotic (and the batch orders differ), so energies, rest heights and penetration statistics
+    are compared, not states.  Both solve with the reference's 4 PGS iterations."""
+    steps = 240
+    g = capi.World(capi.default_config(4096))
+    scenes.box_plane_scene(g, 8, 6, 8)
+    g.upload()
+    g.set_solver(capi.SOLVER_PGS, 4)
+    ref = oa.RefPipeline(capi.default_config(4096))
+    scenes.box_plane_scene(ref, 8, 6, 8)
+    ref.upload()
+    for _ in range(steps):
+        g.step(1 / 60)
+    ref.step(1 / 60, steps)
+    gb, rb = g.bodies(), ref.bodies()
+    assert np.isfinite(gb["pos"]).all() and np.isfinite(rb["pos"]).all()
+    # contacts of the final states through one narrowphase (this library's, checked bit-exact elsewhere): same measuring stick
+    g.compute_contacts()
+    gs = pile_statistics(gb, g.contacts())
+    g.write_bodies(rb)
+    g.update_aabbs()
+    g.find_pairs()
+    g.compute_contacts()
+    rs = pile_statistics(rb, g.contacts())
+    print("b3b200   ", gs)
+    print("reference", rs)
+    # both piles came to rest on the ground at the same height, nothing fell through or flew off
+    assert gs["min_y"] > 0.9 and rs["min_y"] > 0.9
+    assert abs(gs["mean_y"] - rs["mean_y"]) < 0.02 * rs["mean_y"]
+    assert abs(gs["max_y"] - rs["max_y"]) < 0.05 * rs["max_y"]
+    assert abs(gs["potential"] - rs["potential"]) < 0.02 * rs["potential"]
+    # residual motion: both settled (kinetic energy per body far below the 0.5 * (g * 0.5 s)^2 of the initial drop)
+    assert gs["kinetic"] < 0.2 and rs["kinetic"] < 0.2
+    assert gs["median_speed"] < 0.5 and rs["median_speed"] < 0.5
+    # penetration: same contact population and the same depth distribution (positional drift 0.005 allowed by the solver's ERP)
+    assert abs(gs["contacts"] - rs["contacts"]) < 0.1 * rs["contacts"]
+    assert abs(gs["depth_mean"] - rs["depth_mean"]) < 0.01
+    assert abs(gs["depth_p01"] - rs["depth_p01"]) < 0.03
+    assert gs["depth_min"] > -0.25 and rs["depth_min"] > -0.25

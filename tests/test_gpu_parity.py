@@ -75,6 +75,38 @@ def test_bound_search_count_and_fill():
     assert (a[50:150] == 7).all() and a[49] == 49 and a[150] == 150
 
 
+@pytest.mark.parametrize("option", [0, 1, 2])
+def test_bound_search_lower_upper_count_match_host_twin(option):
+    """b3BoundSearchCL BOUND_LOWER / BOUND_UPPER / COUNT against its executeHost twin (b3BoundSearchCL.cpp:139-203)"""
+    rng = np.random.default_rng(5 + option)
+    nb = 300
+    keys = np.sort(rng.choice(np.arange(nb), size=4000, p=None)).astype(np.uint32)
+    keys = keys[(keys % 7) != 3]  # some buckets stay empty: their entries must be left untouched
+    data = np.zeros(len(keys), capi.sort_data_t)
+    data["key"] = keys
+    data["value"] = rng.integers(0, 1 << 30, len(keys))
+    init = rng.integers(0, 1000, nb).astype(np.uint32) if option < 2 else np.zeros(nb, np.uint32)
+    g, r = init.copy(), init.copy()
+    capi.check(capi.lib().b3b200_bound_search(0, capi.ptr(data), len(data), capi.ptr(g), nb, option), "bound_search")
+    oa.refcl().refcl_bound_search(capi.ptr(data), len(data), capi.ptr(r), nb, option)
+    assert np.array_equal(g, r)
+
+
+@pytest.mark.parametrize("n", [1, 33, 1024, 1025, 5000])
+def test_prefix_scan_float4_matches_host_twin(n):
+    """b3PrefixScanFloat4CL (exclusive, xyz) against executeHost (b3PrefixScanFloat4CL.cpp:95-120); the host twin adds left to
+    right, the device scans in a tree: equal to FP32 summation-order tolerance"""
+    rng = np.random.default_rng(n)
+    src = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+    g, r = np.zeros_like(src), np.zeros_like(src)
+    gs, rs = np.zeros(4, np.float32), np.zeros(4, np.float32)
+    capi.check(capi.lib().b3b200_prefix_scan_float4(0, capi.ptr(src), capi.ptr(g), n, capi.ptr(gs)), "scan4")
+    oa.refcl().refcl_prefix_scan_float4(capi.ptr(src), capi.ptr(r), n, capi.ptr(rs))
+    assert np.allclose(g[:, :3], r[:, :3], rtol=1e-5, atol=2e-5 * np.sqrt(n))
+    assert np.allclose(gs[:3], rs[:3], rtol=1e-5, atol=2e-5 * np.sqrt(n))
+    assert (g[:, 3] == 0).all()
+
+
 # ------------------------------------------------------------------ scene helpers
 def gpu_world(n_side=6, seed=0, rotate=True, spacing=1.6, shapes="mixed", max_bodies=8192):
     rng = np.random.default_rng(seed)

@@ -70,3 +70,27 @@ def test_primitives_match_executeHost(n):
     oa.oracle().orc_bound_search_count(capi.ptr(s), n, capi.ptr(c1), buckets)
     oa.refcl().refcl_bound_search_count(capi.ptr(s), n, capi.ptr(c2), buckets)
     assert np.array_equal(c1, c2)
+
+
+@pytest.mark.parametrize("seed,iters", [(0, 7), (3, 8)])
+def test_jacobi_matches_solveGroupHost(seed, iters):
+    """pins the oracle's mass-splitting Jacobi solver: run in the loop order of the reference's host twin
+    (b3GpuJacobiContactSolver::solveGroupHost, b3GpuJacobiContactSolver.cpp:462-697) it must equal that twin; the GPU path's
+    variant (what the CUDA kernels are compared with, `host_order=False`) is the same code with the kernels' loop nest and the
+    kernels' form of the friction step (solverUtils.cl:654-790 re-evaluates velocity + delta per tangent direction)"""
+    w, sh, bodies, inertias = make_world(seed=seed, n_side=6)
+    _, _, _, pairs = all_pairs(bodies, sh)
+    contacts, _ = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 16)
+    assert len(contacts) > 150
+    ref_bodies = oa.refcl_jacobi_solve_host(contacts, bodies, inertias, 0, iters)
+    o_bodies = oa.jacobi_solve(contacts, bodies, inertias, 0, iters, host_order=True)
+    moved = np.abs(ref_bodies["linVel"][:, :3] - bodies["linVel"][:, :3]).max()
+    assert moved > 0.1
+    for f in ("linVel", "angVel"):
+        a, b = o_bodies[f][:, :3], ref_bodies[f][:, :3]
+        err = np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))
+        print(f, "max rel err", err, "bit-equal", np.array_equal(a.view(np.uint32), b.view(np.uint32)))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (f, err)  # bit for bit
+    # the two loop orders really differ (so the switch is not a no-op)
+    g_bodies = oa.jacobi_solve(contacts, bodies, inertias, 0, iters, host_order=False)
+    assert np.abs(g_bodies["linVel"][:, :3] - o_bodies["linVel"][:, :3]).max() > 1e-4
