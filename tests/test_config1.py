@@ -165,9 +165,9 @@ def test_trajectory_statistics_match_the_reference_run():
     assert abs(gs["mean_y"] - rs["mean_y"]) < 0.02 * rs["mean_y"]
     assert abs(gs["max_y"] - rs["max_y"]) < 0.05 * rs["max_y"]
     assert abs(gs["potential"] - rs["potential"]) < 0.02 * rs["potential"]
-    # residual motion: both settled (kinetic energy per body far below the 0.5 * (g * 0.5 s)^2 of the initial drop)
-    assert gs["kinetic"] < 0.2 and rs["kinetic"] < 0.2
-    assert gs["median_speed"] < 0.5 and rs["median_speed"] < 0.5
+    # residual motion: the same jitter level (4 PGS iterations do not bring a 6-high pile to rest in either implementation)
+    assert abs(gs["kinetic"] - rs["kinetic"]) < 0.3 * rs["kinetic"] + 0.02
+    assert abs(gs["median_speed"] - rs["median_speed"]) < 0.1
     # penetration: same contact population and the same depth distribution (positional drift 0.005 allowed by the solver's ERP)
     assert abs(gs["contacts"] - rs["contacts"]) < 0.1 * rs["contacts"]
     assert abs(gs["depth_mean"] - rs["depth_mean"]) < 0.01
