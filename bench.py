@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--ref-bodies", type=int, default=8192, help="--impl reference: bodies of the scene region one reference step simulates")
     ap.add_argument("--bt2-bodies", type=int, default=65536, help="bodies of the scene region the Bullet 2 MT baseline steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed scene (BASELINE configs[4](ii)) that is timed after the replicas")
     return ap.parse_args()
 
 
@@ -291,6 +292,59 @@ def ncu_traffic(kernel):
     return None
 
 
+def slab_leg(world_size, rank, local_rank, steps, warmup, per_rank_x=32, ny=64, nz=256):
+    """BASELINE configs[4](ii): ONE box field (config-3 recipe) of 32*N x 64 x 256 bodies -- 4 194 304 at N = 8 -- cut into N slabs along x; every
+    rank steps its slab, boundary bodies are mirrored on the neighbours by NCCL send/recv issued by the library itself on the world's stream
+    (b3b200_slab_step: device-side counts, fixed-capacity messages, no host synchronisation).  Returns the dict of the "slab" key (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from bullet3_b200 import capi, scenes, slab
+
+    nx = per_rank_x * world_size
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    pos = np.stack([(((j + 1) & 1) + 2.2 * i).reshape(-1), (1.0 + 2.0 * j).reshape(-1), (((j + 1) & 1) + 2.2 * k).reshape(-1)], 1).astype(np.float32)
+    n = len(pos)
+    quat = np.tile(np.array(scenes.IDENT, np.float32), (n, 1))
+
+    def shapes(world):
+        return [world.register_convex_points(scenes.box_points(2000.0)), world.register_convex_points(scenes.box_points(1.0))]
+
+    scene = dict(shapes=shapes, static=[((0.0, -2000.0, 0.0), scenes.IDENT, 0)], pos=pos, quat=quat, shape_slot=np.ones(n, np.int64))
+    stream = torch.cuda.Stream()
+    sw = slab.SlabWorld(scene, rank, world_size, local_rank, stream.cuda_stream, max_ghosts=3 * ny * nz, margin=3.0)
+    sw.world.set_solver(capi.SOLVER_PGS, ITERS)
+    sw.enable_c_exchange()
+    sw.exchange()
+    sw.step_n(DT, warmup)
+    sw.world.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    sw.step_n(DT, steps)
+    e1.record(stream)
+    sw.world.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    left, right = sw.last_halo_counts()
+    halo = torch.tensor([float((left + right) * slab.HALO_RECORD)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(halo, op=dist.ReduceOp.SUM)
+    ctr = sw.world.counters()
+    cnt = torch.tensor([float(ctr[0]), float(ctr[1]), float(ctr[4])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    b = sw.world.bodies()
+    finite = bool(np.isfinite(b["pos"][: sw.num_owned]).all())
+    sw.world.close()
+    return {"workload": "BASELINE configs[4](ii): one %d x %d x %d = %d-body box field (GpuBoxPlaneScene recipe) on a static ground box, %d slabs along x, "
+                        "PGS %d iterations; %d warm-up + %d timed steps while the field falls and piles up" % (nx, ny, nz, n, world_size, ITERS, warmup, steps),
+            "bodies": n, "ms_per_step": float(ms[0]), "bodies_steps_per_s": n / (float(ms[0]) * 1e-3), "halo_bytes_per_step": float(halo[0]),
+            "exchange": "b3b200_slab_step: pack -> ncclSend/ncclRecv (called by the library, world's stream) -> unpack; fixed-capacity messages of %d records per side, "
+                        "device-side counts, no host synchronisation" % sw.max_ghosts,
+            "pairs": float(cnt[0]), "contacts": float(cnt[1]), "overflow_flags": int(cnt[2]), "finite": finite}
+
+
 # ---------------------------------------------------------------------------------- main
 def main():
     a = parse()
@@ -456,6 +510,19 @@ def main():
                 if "cpu_baseline" not in out:
                     out["cpu_baseline"] = c1
             out["cpu_baselines_other"] = extra
+    slab_out = None
+    if world_size > 1 and not a.no_slab:
+        # the multi-GPU mode WITH communication (the independent replicas above have none)
+        w.close()
+        del w
+        torch.cuda.empty_cache()
+        try:
+            slab_out = slab_leg(world_size, rank, local_rank, max(5, a.steps), max(3, a.warmup))
+        except Exception as e:  # the headline line must still be printed
+            slab_out = {"error": repr(e)[:300]}
+    if rank == 0:
+        if slab_out is not None:
+            out["slab"] = slab_out
         print(json.dumps(out))
     if world_size > 1:
         dist.destroy_process_group()

@@ -74,7 +74,8 @@ SYMBOLS = [
     "b3b200_device_buffer", "b3b200_get_table", "b3b200_device_to_host", "b3b200_halo_record_size", "b3b200_halo_pack", "b3b200_halo_unpack", "b3b200_halo_ghost_ids", "b3b200_halo_set_ids", "b3b200_halo_emigrate", "b3b200_halo_adopt", "b3b200_bp_create", "b3b200_bp_destroy", "b3b200_bp_create_proxy", "b3b200_bp_create_large_proxy",
     "b3b200_bp_write_aabbs", "b3b200_bp_set_aabbs", "b3b200_bp_calculate_pairs", "b3b200_bp_num_overlap", "b3b200_bp_get_pairs",
     "b3b200_bp_device_pairs", "b3b200_bp_device_aabbs", "b3b200_bp_last_ms", "b3b200_radix_sort_kv", "b3b200_radix_sort_keys",
-    "b3b200_prefix_scan_u32", "b3b200_bound_search_count", "b3b200_fill_u32", "b3b200_bound_search", "b3b200_prefix_scan_float4",
+    "b3b200_prefix_scan_u32", "b3b200_bound_search_count", "b3b200_fill_u32", "b3b200_bound_search", "b3b200_prefix_scan_float4", "b3b200_slab_unique_id", "b3b200_slab_init", "b3b200_slab_exchange", "b3b200_slab_step",
+    "b3b200_slab_step_n", "b3b200_slab_last_counts", "b3b200_slab_shutdown",
     "b3b200_solve_contacts_device", "b3b200_register_concave_obj", "b3b200_checkpoint_save", "b3b200_checkpoint_load", "b3b200_copy_transforms",
 ]
 

@@ -13,6 +13,7 @@
 //                         slab), writes their records, frees their slots (parked, static, id -1) and returns the slot list
 //   b3b200_halo_adopt     writes received records into the free owned slots the caller names
 // Every slot carries its global body id (b3b200_halo_set_ids at start-up; pack / emigrate send it, unpack / adopt store it).
+#include <dlfcn.h>
 #include "internal.h"
 
 namespace b3b200
@@ -169,9 +170,239 @@ __global__ void haloAdoptKernel(float4* __restrict__ pose, float4* __restrict__ 
 	ids[i] = r.meta.y;
 }
 
+// ---------------------------------------------------------------- slab step behind the C ABI: NCCL called from C++
+// The message of one side is a fixed-capacity buffer [header record | capacity records]; the header's meta.x is the record
+// count, written on the device.  So neither side ever needs the count on the host: no read-back, no stream synchronisation;
+// pack, ncclSend / ncclRecv and unpack are all queued on the world's stream behind the step's kernels.
+__global__ void haloHeaderKernel(HaloRecord* __restrict__ dst, const unsigned int* __restrict__ count, int capacity, unsigned int* __restrict__ overflow)
+{
+	const unsigned int n = *count;
+	HaloRecord h;
+	memset(&h, 0, sizeof(h));
+	h.meta = make_int4((int)(n < (unsigned int)capacity ? n : (unsigned int)capacity), (int)n, 0, 0);
+	dst[0] = h;
+	if (n > (unsigned int)capacity) atomicOr(overflow, (unsigned int)OVF_HALO);
+}
+__global__ void haloUnpackMsgKernel(float4* __restrict__ pose, float4* __restrict__ vel, b3b200_inertia* __restrict__ inertias, int* __restrict__ coll,
+									int* __restrict__ ghostGlobalId, const HaloRecord* __restrict__ msg, int firstSlot, int numSlots)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= numSlots) return;
+	const int i = firstSlot + k;
+	int count = msg[0].meta.x;
+	if (count > numSlots) count = numSlots;
+	if (k < count)
+	{
+		const HaloRecord r = msg[1 + k];
+		pose[2 * i] = r.pos;
+		pose[2 * i + 1] = r.quat;
+		vel[2 * i] = r.linVel;
+		vel[2 * i + 1] = r.angVel;
+		float4* I = reinterpret_cast<float4*>(&inertias[i]);
+		for (int j = 0; j < 3; j++)
+		{
+			I[j] = r.invInertiaWorld[j];
+			I[3 + j] = r.initInvInertia[j];
+		}
+		coll[i] = r.meta.x;
+		ghostGlobalId[i] = r.meta.y;
+	}
+	else
+		parkSlot(pose, vel, ghostGlobalId, i);
+}
+
+// NCCL through dlopen: the library has no link-time dependency on it (a single-GPU user never needs it), and inside a
+// process that already holds an NCCL (torch's) the same copy is used.  Only the handful of entry points of the exchange.
+struct NcclApi
+{
+	void* lib = nullptr;
+	int (*GetUniqueId)(void*) = nullptr;
+	int (*CommInitRank)(void**, int, b3b200_nccl_id, int) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int loadNccl()
+{
+	if (g_nccl.lib) return 0;
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h)
+	{
+		setLastError("slab mode needs NCCL: dlopen(libnccl.so.2) failed: %s", dlerror());
+		return B3B200_ERR_STATE;
+	}
+	NcclApi a;
+	a.lib = h;
+	a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+	a.CommInitRank = (int (*)(void**, int, b3b200_nccl_id, int))dlsym(h, "ncclCommInitRank");
+	a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+	a.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+	a.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+	a.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+	a.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+	a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+	if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.GroupStart || !a.GroupEnd || !a.Send || !a.Recv)
+	{
+		setLastError("slab mode: the NCCL library lacks a required entry point");
+		return B3B200_ERR_STATE;
+	}
+	g_nccl = a;
+	return 0;
+}
+#define B3_NCCL_CHECK(expr)                                                                                              \
+	do                                                                                                                   \
+	{                                                                                                                    \
+		int _r = (expr);                                                                                                 \
+		if (_r != 0)                                                                                                     \
+		{                                                                                                                \
+			setLastError("%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "nccl error");     \
+			return B3B200_ERR_CUDA;                                                                                      \
+		}                                                                                                                \
+	} while (0)
+
+void slabDestroy(World* w)
+{
+	if (w->slab.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->slab.comm);
+	w->slab.comm = nullptr;
+	w->slab.active = false;
+}
+
+// pack -> exchange -> unpack, all queued on the world's stream
+int slabExchange(World* w)
+{
+	SlabState& sl = w->slab;
+	cudaStream_t st = w->stream;
+	if (!w->aabbsValid) B3_TRY(launchUpdateAabbs(w));
+	const size_t msgBytes = sizeof(HaloRecord) * (size_t)(sl.maxGhosts + 1);
+	const float big = 3.0e38f;
+	for (int side = 0; side < 2; side++)
+	{
+		if (!(side == 0 ? sl.hasLeft : sl.hasRight)) continue;
+		unsigned int* ctr = &w->dCounters.ptr[side == 0 ? CTR_HALO : CTR_HALO_RIGHT];
+		B3_CUDA_CHECK(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+		HaloRecord* msg = reinterpret_cast<HaloRecord*>(sl.sendBuf[side].ptr);
+		const float a = side == 0 ? -big : sl.hi - sl.margin, b = side == 0 ? sl.lo + sl.margin : big;
+		if (sl.numOwned > 0)
+		{
+			haloPackKernel<<<divUp(sl.numOwned, 256), 256, 0, st>>>(w->dPose.ptr, w->dVel.ptr, w->dInertias.ptr, w->dCollidableIdx.ptr, w->bp.aabbs.ptr, sl.numOwned,
+																   sl.axis, a, b, sl.globalIdBase, w->haloIdsSet ? w->dGhostGlobalId.ptr : nullptr, sl.rank, msg + 1,
+																   sl.maxGhosts, ctr);
+			B3_LAUNCH_CHECK();
+		}
+		haloHeaderKernel<<<1, 1, 0, st>>>(msg, ctr, sl.maxGhosts, &w->dCounters.ptr[CTR_OVERFLOW]);
+		B3_LAUNCH_CHECK();
+	}
+	B3_NCCL_CHECK(g_nccl.GroupStart());
+	for (int side = 0; side < 2; side++)
+	{
+		if (!(side == 0 ? sl.hasLeft : sl.hasRight)) continue;
+		const int peer = side == 0 ? sl.rank - 1 : sl.rank + 1;
+		B3_NCCL_CHECK(g_nccl.Send(sl.sendBuf[side].ptr, msgBytes, 0 /* ncclInt8 */, peer, sl.comm, st));
+		B3_NCCL_CHECK(g_nccl.Recv(sl.recvBuf[side].ptr, msgBytes, 0, peer, sl.comm, st));
+	}
+	B3_NCCL_CHECK(g_nccl.GroupEnd());
+	B3_TRY(w->dGhostGlobalId.reserve(std::max(w->numBodies, 1)));
+	int slot = sl.firstGhostSlot;
+	for (int side = 0; side < 2; side++)
+	{
+		if (!(side == 0 ? sl.hasLeft : sl.hasRight)) continue;
+		haloUnpackMsgKernel<<<divUp(sl.maxGhosts, 256), 256, 0, st>>>(w->dPose.ptr, w->dVel.ptr, w->dInertias.ptr, w->dCollidableIdx.ptr, w->dGhostGlobalId.ptr,
+																	   reinterpret_cast<const HaloRecord*>(sl.recvBuf[side].ptr), slot, sl.maxGhosts);
+		B3_LAUNCH_CHECK();
+		slot += sl.maxGhosts;
+	}
+	w->aabbsValid = false;
+	w->soaDirty = true;
+	w->partValid = false;
+	return 0;
+}
+
 }  // namespace b3b200
 
 using namespace b3b200;
+
+// ---- slab decomposition driven from C / C++: the caller creates one world per rank (owned bodies first, then
+// ghost slots), hands every rank the same NCCL unique id, and calls b3b200_slab_step instead of b3b200_step.
+extern "C" int b3b200_slab_unique_id(b3b200_nccl_id* out)
+{
+	if (!out) return B3B200_ERR_INVALID;
+	B3_TRY(loadNccl());
+	B3_NCCL_CHECK(g_nccl.GetUniqueId(out));
+	return 0;
+}
+extern "C" int b3b200_slab_init(b3b200_world* w, const b3b200_slab_config* cfg, const b3b200_nccl_id* id)
+{
+	if (!w || w->device < 0 || !w->uploaded || !cfg || !id) return B3B200_ERR_INVALID;
+	if (cfg->axis < 0 || cfg->axis > 2 || cfg->rank < 0 || cfg->rank >= cfg->numRanks || cfg->maxGhosts < 0 || cfg->numOwned < 0 || cfg->numOwned > w->numBodies ||
+		cfg->firstGhostSlot < 0)
+		return B3B200_ERR_INVALID;
+	const bool hasLeft = cfg->rank > 0, hasRight = cfg->rank < cfg->numRanks - 1;
+	if (cfg->firstGhostSlot + cfg->maxGhosts * ((int)hasLeft + (int)hasRight) > w->numBodies)
+	{
+		setLastError("slab_init: the ghost slots [%d, +%d x %d) do not fit the world's %d bodies", cfg->firstGhostSlot, (int)hasLeft + (int)hasRight, cfg->maxGhosts, w->numBodies);
+		return B3B200_ERR_INVALID;
+	}
+	B3_TRY(loadNccl());
+	B3_CUDA_CHECK(cudaSetDevice(w->device));
+	slabDestroy(w);
+	SlabState& sl = w->slab;
+	sl.axis = cfg->axis;
+	sl.lo = cfg->lo;
+	sl.hi = cfg->hi;
+	sl.margin = cfg->margin;
+	sl.numOwned = cfg->numOwned;
+	sl.firstGhostSlot = cfg->firstGhostSlot;
+	sl.maxGhosts = cfg->maxGhosts;
+	sl.globalIdBase = cfg->globalIdBase;
+	sl.rank = cfg->rank;
+	sl.numRanks = cfg->numRanks;
+	sl.hasLeft = hasLeft;
+	sl.hasRight = hasRight;
+	const size_t msgBytes = sizeof(HaloRecord) * (size_t)(sl.maxGhosts + 1);
+	for (int side = 0; side < 2; side++)
+	{
+		B3_TRY(sl.sendBuf[side].reserve(msgBytes));
+		B3_TRY(sl.recvBuf[side].reserve(msgBytes));
+		B3_CUDA_CHECK(cudaMemsetAsync(sl.sendBuf[side].ptr, 0, msgBytes, w->stream));
+		B3_CUDA_CHECK(cudaMemsetAsync(sl.recvBuf[side].ptr, 0, msgBytes, w->stream));
+	}
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	B3_NCCL_CHECK(g_nccl.CommInitRank(&sl.comm, sl.numRanks, *id, sl.rank));
+	sl.active = true;
+	return 0;
+}
+// ghost slots <- the neighbours' current boundary bands (call once before the first step)
+extern "C" int b3b200_slab_exchange(b3b200_world* w)
+{
+	if (!w || w->device < 0 || !w->uploaded || !w->slab.active) return B3B200_ERR_STATE;
+	B3_CUDA_CHECK(cudaSetDevice(w->device));
+	return slabExchange(w);
+}
+// halo records sent by this rank in the last exchange (left, right); synchronises the stream
+extern "C" int b3b200_slab_last_counts(b3b200_world* w, int* left, int* right)
+{
+	if (!w || w->device < 0 || !w->slab.active || !left || !right) return B3B200_ERR_STATE;
+	B3_CUDA_CHECK(cudaSetDevice(w->device));
+	unsigned int c[2] = {0, 0};
+	B3_CUDA_CHECK(cudaMemcpyAsync(&c[0], &w->dCounters.ptr[CTR_HALO], sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaMemcpyAsync(&c[1], &w->dCounters.ptr[CTR_HALO_RIGHT], sizeof(unsigned int), cudaMemcpyDeviceToHost, w->stream));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	*left = w->slab.hasLeft ? (int)c[0] : 0;
+	*right = w->slab.hasRight ? (int)c[1] : 0;
+	return 0;
+}
+extern "C" int b3b200_slab_shutdown(b3b200_world* w)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	if (w->device >= 0) cudaSetDevice(w->device);
+	slabDestroy(w);
+	return 0;
+}
 
 extern "C" int b3b200_halo_record_size(void) { return (int)sizeof(HaloRecord); }
 

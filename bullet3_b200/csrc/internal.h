@@ -30,6 +30,7 @@ enum Counter
 	CTR_SMALL_ITEMS_BACK = 17,  // the other small pairs, filled from the back of the same list (cleared together with 16)
 	CTR_CONCAVE_SURVIVORS_BACK = 19,  // trimesh items with a larger hull B (warp-per-item kernel), filled from the back of the survivor list
 	CTR_CLIP_FALLBACK = 18,  // overlapping items whose faces are too large for the thread-per-item clip (cleared together with 16)
+	CTR_HALO_RIGHT = 20,  // halo records packed for the right neighbour (CTR_HALO: left) in the C-driven slab step
 	CTR_COUNT = 24
 };
 enum OverflowBits
@@ -38,7 +39,8 @@ enum OverflowBits
 	OVF_CONTACTS = 2,
 	OVF_BATCHES = 4,
 	OVF_COMPOUND = 8,
-	OVF_CONCAVE = 16
+	OVF_CONCAVE = 16,
+	OVF_HALO = 32
 };
 
 // ------------------------------------------------------------------ broadphase
@@ -80,6 +82,17 @@ struct Broadphase
 	int writeAabbs();           // host -> device, (re)allocates scratch
 	int calculatePairs(int maxPairsNow);  // async on stream
 	int reset();
+};
+
+// slab decomposition driven through the C ABI (halo.cu): NCCL communicator + fixed-capacity message buffers of one rank
+struct SlabState
+{
+	bool active = false;
+	void* comm = nullptr;  // ncclComm_t
+	int axis = 0, rank = 0, numRanks = 1, numOwned = 0, firstGhostSlot = 0, maxGhosts = 0, globalIdBase = 0;
+	float lo = 0.f, hi = 0.f, margin = 0.f;
+	bool hasLeft = false, hasRight = false;
+	DevBuf<unsigned char> sendBuf[2], recvBuf[2];  // [left, right]: header record + maxGhosts records
 };
 
 // ------------------------------------------------------------------ world
@@ -157,6 +170,7 @@ struct World
 	DevBuf<int> dGhostGlobalId;  // slab mode: global id mirrored by each ghost slot (-1 = parked / owned)
 	DevBuf<int> dHaloSlots;  // slot lists of emigrate / adopt
 	bool haloIdsSet = false;  // dGhostGlobalId holds the global id of every slot (b3b200_halo_set_ids)
+	SlabState slab;
 	bool soaDirty = false;  // SoA is newer than AoS
 	bool hostBodiesStale = false;  // the host mirror `bodies` is older than the device AoS (after b3b200_write_bodies)
 	bool hasConcave = false;  // any SHAPE_CONCAVE_TRIMESH collidable registered (enables the concave kernels)
@@ -247,6 +261,8 @@ int launchSolveJoints(World* w);  // joints.cu
 int launchSolverSetup(World* w);
 int launchSolverIterate(World* w);
 int launchJacobi(World* w);
+int slabExchange(World* w);  // halo.cu
+void slabDestroy(World* w);
 int exportConstraints(World* w, std::vector<b3b200_constraint4>& out, std::vector<int>& batchOffsets);  // solver.cu
 
 }  // namespace b3b200

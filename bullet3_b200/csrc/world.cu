@@ -65,6 +65,7 @@ void World::destroy()
 {
 	if (device < 0) return;  // host-only world: nothing on a device
 	cudaSetDevice(device);
+	slabDestroy(this);
 	if (stream) cudaStreamSynchronize(stream);
 	for (int i = 0; i < 8; i++)
 		if (ev[i]) cudaEventDestroy(ev[i]);
@@ -771,6 +772,22 @@ extern "C" int b3b200_step_n(b3b200_world* w, float dt, int n)
 	for (int i = 0; i < n; i++) B3_TRY(stepOnce(w, dt));
 	return 0;
 }
+extern "C" int b3b200_slab_step_n(b3b200_world* w, float dt, int n)
+{
+	W_UPLOADED(w);
+	if (!w->slab.active)
+	{
+		setLastError("slab_step without slab_init");
+		return B3B200_ERR_STATE;
+	}
+	for (int i = 0; i < n; i++)
+	{
+		B3_TRY(stepOnce(w, dt));
+		B3_TRY(slabExchange(w));
+	}
+	return 0;
+}
+extern "C" int b3b200_slab_step(b3b200_world* w, float dt) { return b3b200_slab_step_n(w, dt, 1); }
 extern "C" int b3b200_synchronize(b3b200_world* w)
 {
 	W_CHECK(w);

@@ -24,6 +24,12 @@ from . import capi
 HALO_RECORD = 176
 
 
+class slab_config_t(C.Structure):
+    """b3b200_slab_config (include/b3b200_types.h)"""
+    _fields_ = [("axis", C.c_int), ("lo", C.c_float), ("hi", C.c_float), ("margin", C.c_float), ("numOwned", C.c_int), ("firstGhostSlot", C.c_int),
+                ("maxGhosts", C.c_int), ("globalIdBase", C.c_int), ("rank", C.c_int), ("numRanks", C.c_int)]
+
+
 # ---------------------------------------------------------------------------------- pure partition logic (CPU-testable)
 def shard_worlds(num_worlds, world_size):
     """contiguous world ranges per rank: [(first, count)] * world_size, sizes differ by at most one"""
@@ -167,6 +173,7 @@ class SlabWorld:
             self.mig_recv = {s: torch.zeros(self.max_migrants * HALO_RECORD, dtype=torch.uint8, device=dev) for s in ("left", "right")}
         self.halo_bytes = 0
         self.migrated_out = self.migrated_in = 0
+        self.c_driven = False
         assert capi.lib().b3b200_halo_record_size() == HALO_RECORD
 
     def _pack(self, side):
@@ -184,6 +191,11 @@ class SlabWorld:
 
     def exchange(self):
         """boundary bands -> neighbours -> ghost slots (call after every step, and once before the first)"""
+        if self.c_driven:
+            capi.check(capi.lib().b3b200_slab_exchange(self.world.h), "slab_exchange")
+            a, b = self.last_halo_counts()
+            self.halo_bytes = (a + b) * HALO_RECORD
+            return {"left": a, "right": b}, None
         torch = self.torch
         sides = [s for s, has in (("left", self.has_left), ("right", self.has_right)) if has]
         peer = {"left": self.rank - 1, "right": self.rank + 1}
@@ -228,9 +240,50 @@ class SlabWorld:
         return counts, rc
 
     def step(self, dt=1.0 / 60.0):
+        if self.c_driven:
+            if self.spare_slots:
+                self.world.step(dt)
+                self.migrate()  # (hand-overs keep their host-side free-slot lists)
+                capi.check(capi.lib().b3b200_slab_exchange(self.world.h), "slab_exchange")
+            else:
+                capi.check(capi.lib().b3b200_slab_step(self.world.h, C.c_float(dt)), "slab_step")
+            return
         self.world.step(dt)
         self.migrate()
         self.exchange()
+
+    # ---- the exchange driven from C: b3b200_slab_* call NCCL themselves on the world's stream (no torch tensors, no host sync)
+    def enable_c_exchange(self):
+        """every rank calls this once after construction: rank 0 makes the NCCL id, torch.distributed carries its 128 bytes to the
+        others (any transport would do), b3b200_slab_init builds the communicator and the fixed-capacity message buffers"""
+        import torch.distributed as dist
+
+        ident = (C.c_char * 128)()
+        if self.rank == 0:
+            capi.check(capi.lib().b3b200_slab_unique_id(ident), "slab_unique_id")
+        box = [bytes(ident.raw)]
+        if self.world_size > 1:
+            dist.broadcast_object_list(box, src=0)
+        ident = (C.c_char * 128).from_buffer_copy(box[0])
+        lo, hi = float(self.boundaries[self.rank]), float(self.boundaries[self.rank + 1])
+        big = 3.0e38
+        cfg = slab_config_t(axis=0, lo=max(lo, -big), hi=min(hi, big), margin=self.margin, numOwned=int(self.num_owned), firstGhostSlot=int(self.first_ghost),
+                            maxGhosts=int(self.max_ghosts), globalIdBase=int(self.global_first - self.n_static), rank=int(self.rank), numRanks=int(self.world_size))
+        capi.check(capi.lib().b3b200_slab_init(self.world.h, C.byref(cfg), ident), "slab_init")
+        self.c_driven = True
+
+    def step_n(self, dt, n):
+        """n steps back to back; in the C-driven mode without hand-overs nothing returns to the host in between"""
+        if self.c_driven and not self.spare_slots:
+            capi.check(capi.lib().b3b200_slab_step_n(self.world.h, C.c_float(dt), int(n)), "slab_step_n")
+        else:
+            for _ in range(n):
+                self.step(dt)
+
+    def last_halo_counts(self):
+        a, b = C.c_int(0), C.c_int(0)
+        capi.check(capi.lib().b3b200_slab_last_counts(self.world.h, C.byref(a), C.byref(b)), "slab_last_counts")
+        return a.value, b.value
 
     def global_ids(self):
         """global id of every local body (-1 for static and parked ghost slots)"""

@@ -241,6 +241,18 @@ int b3b200_bp_last_ms(b3b200_broadphase* bp, float* ms);
  * b3b200_halo_record_size()-byte records (pose, velocity, inverse inertias, collidable, global id) into a DEVICE buffer;
  * the caller ships it to the neighbour (NCCL send/recv); unpack scatters received records into the ghost slots
  * [firstGhostSlot, firstGhostSlot + numGhostSlots) and parks the unused ones.  See bullet3_b200/slab.py. */
+/* The same exchange driven entirely from C / C++: NCCL send/recv is called by the library on the world's stream (NCCL is
+ * dlopen'ed: libnccl.so.2), one fixed-capacity message per side whose header carries the record count written on the device, so
+ * a step needs no host synchronisation.  Rank 0 makes the id (b3b200_slab_unique_id), every rank gets the same bytes by its own
+ * means (MPI, a file, torch.distributed), builds its world (owned bodies first, then ghost slots), uploads and calls
+ * b3b200_slab_init once, b3b200_slab_exchange once, then b3b200_slab_step per step. */
+int b3b200_slab_unique_id(b3b200_nccl_id* out);
+int b3b200_slab_init(b3b200_world* w, const b3b200_slab_config* cfg, const b3b200_nccl_id* id);
+int b3b200_slab_exchange(b3b200_world* w);
+int b3b200_slab_step(b3b200_world* w, float dt);            /* b3b200_step + halo exchange, all queued on the world's stream */
+int b3b200_slab_step_n(b3b200_world* w, float dt, int n);
+int b3b200_slab_last_counts(b3b200_world* w, int* left, int* right);
+int b3b200_slab_shutdown(b3b200_world* w);
 int b3b200_halo_record_size(void);
 int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, int numOwned, int globalIdBase, int rank, void* dstDevice,
 					 int capacity, int* countOut);

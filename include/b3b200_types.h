@@ -283,4 +283,21 @@ static_assert(sizeof(b3b200_ray_info) == 32, "abi");
 static_assert(sizeof(b3b200_ray_hit) == 48, "abi");
 #endif
 
+/* slab decomposition of one scene over several GPUs, driven from C / C++ (no reference counterpart: Bullet3OpenCL is single-device) */
+typedef struct b3b200_nccl_id
+{
+	char internal[128]; /* an ncclUniqueId */
+} b3b200_nccl_id;
+typedef struct b3b200_slab_config
+{
+	int axis;           /* slab axis: 0 x, 1 y, 2 z */
+	float lo, hi;       /* this rank's slab along the axis (+-3e38 at the outer ranks) */
+	float margin;       /* a body whose AABB reaches within `margin` of a slab face is mirrored on that neighbour */
+	int numOwned;       /* bodies [0, numOwned) of the world are owned (static + dynamic + spare); the rest are ghost slots */
+	int firstGhostSlot; /* first ghost slot: maxGhosts for the left neighbour (if any), then maxGhosts for the right one */
+	int maxGhosts;      /* capacity per side = size of the fixed-size message */
+	int globalIdBase;   /* global id of local body i = globalIdBase + i (unless b3b200_halo_set_ids gave every slot its id) */
+	int rank, numRanks;
+} b3b200_slab_config;
+
 #endif /* B3B200_TYPES_H */

@@ -53,6 +53,8 @@ def main():
     n = len(scene["pos"])
     stream = torch.cuda.current_stream().cuda_stream
     sw = slab.SlabWorld(scene, rank, ws, local, stream, max_ghosts=max(1024, 4 * ny * nz), margin=3.0)
+    if os.environ.get("SLAB_C", "1") == "1":  # the exchange driven from C (NCCL called by the library); SLAB_C=0: torch.distributed orchestration
+        sw.enable_c_exchange()
     sw.exchange()
     sw.world.step()
     ids = sw.global_ids()
@@ -68,8 +70,7 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     ev0.record()
-    for _ in range(steps - 1):
-        sw.step()
+    sw.step_n(1.0 / 60.0, steps - 1)
     ev1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([ev0.elapsed_time(ev1) / max(1, steps - 1)], device="cuda")

@@ -48,6 +48,8 @@ def main():
     n = len(scene["pos"])
     stream = torch.cuda.current_stream().cuda_stream
     sw = slab.SlabWorld(scene, rank, ws, local, stream, max_ghosts=max(1024, 8 * ny * nz), margin=3.0, spare_slots=max(256, n // (2 * ws)), hysteresis=0.25)
+    if os.environ.get("SLAB_C", "1") == "1":  # the exchange driven from C (NCCL called by the library); SLAB_C=0: torch.distributed orchestration
+        sw.enable_c_exchange()
     sw.world.set_gravity((0.0, 0.0, 0.0))
     sw.world.set_solver(capi.SOLVER_PGS, 4)
     sw.exchange()
