@@ -175,15 +175,21 @@ __global__ void bpParamsKernel(unsigned int* scal, int n)
 B3_D int3 cellOf(const float4& mn, const float4& mx, float invCell)
 {
 	float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
-	return make_int3((int)floorf(cx * invCell), (int)floorf(cy * invCell), (int)floorf(cz * invCell));
+	// (clamped before the conversion: a far-away or non-finite centre must not overflow the int, and c.x + 1 must not either)
+	const float lim = 1.0e9f;
+	return make_int3((int)fminf(fmaxf(floorf(cx * invCell), -lim), lim), (int)fminf(fmaxf(floorf(cy * invCell), -lim), lim), (int)fminf(fmaxf(floorf(cz * invCell), -lim), lim));
 }
 B3_D unsigned int cellKey(int x, int y, int z)
 {
 	return ((unsigned int)(z & (GRID_DIM - 1)) << 14) | ((unsigned int)(y & (GRID_DIM - 1)) << 7) | (unsigned int)(x & (GRID_DIM - 1));
 }
 
-__global__ void __launch_bounds__(256) gridHashKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
-													  const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals)
+// Counting sort by cell (the keys ARE small integers: no radix passes): count with the rank inside the cell as a by-product,
+// dense exclusive scan over the 128^3 cells, scatter.  The dense table gives the sorted range of ANY run of cells -- also of
+// empty ones -- with two loads, which is what the pair kernel needs.
+__global__ void __launch_bounds__(256) gridCountKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
+													   const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ rankInCell,
+													   unsigned int* __restrict__ cellCount)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -191,11 +197,26 @@ __global__ void __launch_bounds__(256) gridHashKernel(const b3b200_aabb* __restr
 	int idx = smallMap[i];
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[idx]);
 	int3 c = cellOf(__ldg(p), __ldg(p + 1), invCell);
-	keys[i] = cellKey(c.x, c.y, c.z);
-	vals[i] = (unsigned int)idx;
+	const unsigned int key = cellKey(c.x, c.y, c.z);
+	keys[i] = key;
+	rankInCell[i] = atomicAdd(&cellCount[key], 1u);
 }
 
-// gather AABBs into sorted order (coalesced 2x128-bit per proxy) and mark cell starts
+// AABBs into cell order (the order inside a cell is the order of the atomics: the pair SET does not depend on it)
+__global__ void __launch_bounds__(256) gridScatterKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
+														 const unsigned int* __restrict__ keys, const unsigned int* __restrict__ rankInCell,
+														 const unsigned int* __restrict__ cellStart, b3b200_aabb* __restrict__ sorted)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
+	const float4 mn = __ldg(p), mx = __ldg(p + 1);
+	float4* q = reinterpret_cast<float4*>(&sorted[cellStart[keys[i]] + rankInCell[i]]);
+	q[0] = mn;
+	q[1] = mx;
+}
+
+// gather AABBs into sorted order (coalesced 2x128-bit per proxy) -- SAP path
 __global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restrict__ aabbs, const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals,
 													int n, b3b200_aabb* __restrict__ sorted, int* __restrict__ cellStart)
 {
@@ -206,18 +227,22 @@ __global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restric
 	float4* q = reinterpret_cast<float4*>(&sorted[i]);
 	q[0] = mn;
 	q[1] = mx;
-	if (cellStart)
-	{
-		unsigned int k = keys[i];
-		if (i == 0 || keys[i - 1] != k) cellStart[k] = i;
-	}
+	(void)cellStart;
 }
 
-__global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_aabb* __restrict__ sorted, const unsigned int* __restrict__ keys, const int* __restrict__ cellStart,
-																  int n, const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+// One thread per AABB (in cell order).  Its candidates are the 3 x 3 x 3 cells around its own: per (y, z) row the cells x-1..x+1
+// are ONE contiguous range of the sorted array, [cellStart[key(x-1)], cellStart[key(x+1) + 1]) -- two loads per row, all rows'
+// loads independent of each other (the first version walked 27 cells with a dependent cellStart -> key -> AABB chain each).
+// A pair is emitted by the body with the lower sorted index; rows whose keys are all smaller than the body's own cannot
+// hold a higher index, so away from the wrap-around of the 128^3 hash only 5 of the 9 rows are visited.  Consecutive threads
+// are neighbours in space: their candidate ranges overlap and are served by L1.
+constexpr int GRID_ROWS = 27;
+__global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_aabb* __restrict__ sorted, const unsigned int* __restrict__ cellStart, int n,
+																  const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
 {
 	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
-	const int lane = threadIdx.x & 31;
+	__shared__ int2 sRange[GRID_ROWS][BP_THREADS];
+	const int lane = threadIdx.x & 31, t = threadIdx.x;
 	int2* stage = stageAll[threadIdx.x >> 5];
 	int count = 0;
 	const float invCell = __uint_as_float(scal[SC_INVCELL]);
@@ -225,44 +250,65 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 	bool valid = i < n;
 	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
 	int idA = 0;
-	int3 c = make_int3(0, 0, 0);
+	int nr = 0;
 	if (valid)
 	{
 		const float4* p = reinterpret_cast<const float4*>(&sorted[i]);
 		mnA = p[0];
 		mxA = p[1];
 		idA = __float_as_int(mnA.w);
-		c = cellOf(mnA, mxA, invCell);
+		const int3 c = cellOf(mnA, mxA, invCell);
+		const int xw = c.x & (GRID_DIM - 1), yw = c.y & (GRID_DIM - 1), zw = c.z & (GRID_DIM - 1);
+		const bool inner = yw >= 1 && yw <= GRID_DIM - 2 && zw >= 1 && zw <= GRID_DIM - 2;  // no (y, z) wrap: key order == (z, y, x) order
+		const bool xInner = xw >= 1 && xw <= GRID_DIM - 2;
+#pragma unroll
+		for (int r = 0; r < 9; r++)
+		{
+			const int dz = r / 3 - 1, dy = r % 3 - 1;
+			if (inner && (dz < 0 || (dz == 0 && dy < 0))) continue;  // all of that row sorts before this body
+			if (xInner)
+			{
+				const unsigned int k0 = cellKey(c.x - 1, c.y + dy, c.z + dz);
+				const int lo = (int)__ldg(&cellStart[k0]), hi = (int)__ldg(&cellStart[k0 + 3]);
+				if (hi > lo) sRange[nr++][t] = make_int2(lo, hi);
+			}
+			else
+			{
+				for (int dx = -1; dx <= 1; dx++)
+				{
+					const unsigned int k = cellKey(c.x + dx, c.y + dy, c.z + dz);
+					const int lo = (int)__ldg(&cellStart[k]), hi = (int)__ldg(&cellStart[k + 1]);
+					if (hi > lo) sRange[nr++][t] = make_int2(lo, hi);
+				}
+			}
+		}
 	}
-	int nb = 0;
-	int j = -1;
-	unsigned int curKey = 0;
+	int r = 0, j = 0, jend = 0;
+	if (valid && nr > 0)
+	{
+		const int2 rg = sRange[0][t];
+		j = rg.x;
+		jend = rg.y;
+	}
+	else
+		valid = false;
 	for (;;)
 	{
 		bool have = false;
 		if (valid)
 		{
-			for (;;)
+			while (j >= jend)
 			{
-				if (j >= 0)
-				{
-					if (j < n && keys[j] == curKey)
-					{
-						have = true;
-						break;
-					}
-					j = -1;
-				}
-				if (nb >= 27)
+				if (++r >= nr)
 				{
 					valid = false;
 					break;
 				}
-				int dz = nb / 9 - 1, dy = (nb / 3) % 3 - 1, dx = nb % 3 - 1;
-				curKey = cellKey(c.x + dx, c.y + dy, c.z + dz);
-				nb++;
-				j = cellStart[curKey];
+				const int2 rg = sRange[r][t];
+				j = rg.x;
+				jend = rg.y;
 			}
+			have = valid;
 		}
 		bool hit = false;
 		int idB = 0;
@@ -271,7 +317,7 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 			if (j > i)
 			{
 				const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
-				float4 mnB = p[0], mxB = p[1];
+				const float4 mnB = __ldg(p), mxB = __ldg(p + 1);
 				idB = __float_as_int(mnB.w);
 				hit = aabbOverlap(mnA, mxA, mnB, mxB);
 			}
@@ -442,6 +488,8 @@ void Broadphase::destroy()
 	vals.release();
 	sortedAabbs.release();
 	cellStart.release();
+	cellCnt.release();
+	scanTotals.release();
 	scalars.release();
 }
 
@@ -488,7 +536,9 @@ int Broadphase::writeAabbs()
 	B3_TRY(keys.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(vals.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(sortedAabbs.reserve(numSmall > 0 ? numSmall : 1));
-	B3_TRY(cellStart.reserve(GRID_CELLS));
+	B3_TRY(cellStart.reserve(GRID_CELLS + 4));
+	B3_TRY(cellCnt.reserve(GRID_CELLS + 4));
+	B3_TRY(scanTotals.reserve((size_t)largeScanChunks(GRID_CELLS + 4)));
 	B3_TRY(sortTmp.keysAlt.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(sortTmp.valsAlt.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(sortTmp.blockHist.reserve((size_t)256 * divUp(numSmall > 0 ? numSmall : 1, 2048)));
@@ -517,13 +567,16 @@ int Broadphase::calculatePairs(int maxPairsNow)
 		const unsigned int* scal = reinterpret_cast<const unsigned int*>(scalars.ptr);
 		if (kind == B3B200_BP_GRID)
 		{
-			gridHashKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr);
+			unsigned int* cellCount = reinterpret_cast<unsigned int*>(cellCnt.ptr);
+			unsigned int* cellBegin = reinterpret_cast<unsigned int*>(cellStart.ptr);
+			B3_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(unsigned int) * (GRID_CELLS + 4), s));
+			gridCountKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr, cellCount);
 			B3_LAUNCH_CHECK();
-			B3_TRY(radixSortKV32(s, sortTmp, keys.ptr, vals.ptr, numSmall, 21));
-			B3_CUDA_CHECK(cudaMemsetAsync(cellStart.ptr, 0xff, sizeof(int) * GRID_CELLS, s));
-			gatherKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, keys.ptr, vals.ptr, numSmall, sortedAabbs.ptr, cellStart.ptr);
+			// GRID_CELLS + 4 entries: cellStart[key + 3] of the last cells reads the total
+			B3_TRY(exclusiveScanLargeU32(s, cellCount, cellBegin, GRID_CELLS + 4, scanTotals.ptr, nullptr));
+			gridScatterKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, keys.ptr, vals.ptr, cellBegin, sortedAabbs.ptr);
 			B3_LAUNCH_CHECK();
-			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, keys.ptr, cellStart.ptr, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
+			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, cellBegin, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
 			B3_LAUNCH_CHECK();
 		}
 		else

@@ -70,7 +70,9 @@ struct Broadphase
 	// scratch
 	DevBuf<unsigned int> keys, vals;
 	DevBuf<b3b200_aabb> sortedAabbs;
-	DevBuf<int> cellStart;         // 128^3
+	DevBuf<int> cellStart;         // 128^3 + 4: first sorted index of every cell (dense exclusive scan of the counts)
+	DevBuf<int> cellCnt;           // bodies per cell
+	DevBuf<unsigned int> scanTotals;  // scratch of the multi-CTA scan
 	DevBuf<float> scalars;         // [0]=maxExtent bits/cellSize ... see broadphase.cu
 	RadixSortTemp sortTmp;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -22,6 +22,9 @@ int radixSortKeys32(cudaStream_t s, RadixSortTemp& tmp, unsigned int* keys, int 
 int radixSortKV64(cudaStream_t s, RadixSortTemp& tmp, unsigned long long* keys, unsigned int* vals, int n, int numBits);
 
 // exclusive scan of n u32; if total != nullptr the grand total is written there (device pointer)
+// the same for large n over many CTAs; chunkTotals: scratch of largeScanChunks(n) words
+int exclusiveScanLargeU32(cudaStream_t s, const unsigned int* src, unsigned int* dst, int n, unsigned int* chunkTotals, unsigned int* totalDevice);
+int largeScanChunks(int n);
 int exclusiveScanU32(cudaStream_t s, const unsigned int* src, unsigned int* dst, int n, unsigned int* totalDevice);
 
 }  // namespace b3b200
