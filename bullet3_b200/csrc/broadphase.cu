@@ -26,7 +26,7 @@ namespace b3b200
 constexpr int BP_THREADS = 128;
 constexpr int GRID_DIM = 128;
 constexpr int GRID_CELLS = GRID_DIM * GRID_DIM * GRID_DIM;
-constexpr int STAGE_CAP = 96;  // per-warp staging: flush at >= 64
+constexpr int STAGE_CAP = 96;  // per-warp staging: flush at >= 64 (larger stages were measured: no gain, the one pair counter is not the bottleneck)
 
 // scalars layout (32-bit words)
 enum
@@ -237,11 +237,12 @@ __global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restric
 // hold a higher index, so away from the wrap-around of the 128^3 hash only 5 of the 9 rows are visited.  Consecutive threads
 // are neighbours in space: their candidate ranges overlap and are served by L1.
 constexpr int GRID_ROWS = 27;
+constexpr int GRID_UNROLL = 4;
 __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_aabb* __restrict__ sorted, const unsigned int* __restrict__ cellStart, int n,
 																  const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
 {
 	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
-	__shared__ int2 sRange[GRID_ROWS][BP_THREADS];
+	__shared__ int2 sRange[GRID_ROWS][BP_THREADS];  // [first, end) per row of cells (9 rows, or 27 single cells next to the wrap-around)
 	const int lane = threadIdx.x & 31, t = threadIdx.x;
 	int2* stage = stageAll[threadIdx.x >> 5];
 	int count = 0;
@@ -261,6 +262,11 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 		const int xw = c.x & (GRID_DIM - 1), yw = c.y & (GRID_DIM - 1), zw = c.z & (GRID_DIM - 1);
 		const bool inner = yw >= 1 && yw <= GRID_DIM - 2 && zw >= 1 && zw <= GRID_DIM - 2;  // no (y, z) wrap: key order == (z, y, x) order
 		const bool xInner = xw >= 1 && xw <= GRID_DIM - 2;
+		auto add = [&](int lo, int hi) {
+			if (inner && hi <= i + 1) return;   // nothing behind this body in the range
+			if (inner && lo <= i) lo = i + 1;   // (own row: start right behind the body itself)
+			if (hi > lo) sRange[nr++][t] = make_int2(lo, hi);
+		};
 #pragma unroll
 		for (int r = 0; r < 9; r++)
 		{
@@ -269,61 +275,65 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 			if (xInner)
 			{
 				const unsigned int k0 = cellKey(c.x - 1, c.y + dy, c.z + dz);
-				const int lo = (int)__ldg(&cellStart[k0]), hi = (int)__ldg(&cellStart[k0 + 3]);
-				if (hi > lo) sRange[nr++][t] = make_int2(lo, hi);
+				add((int)__ldg(&cellStart[k0]), (int)__ldg(&cellStart[k0 + 3]));
 			}
 			else
 			{
 				for (int dx = -1; dx <= 1; dx++)
 				{
 					const unsigned int k = cellKey(c.x + dx, c.y + dy, c.z + dz);
-					const int lo = (int)__ldg(&cellStart[k]), hi = (int)__ldg(&cellStart[k + 1]);
-					if (hi > lo) sRange[nr++][t] = make_int2(lo, hi);
+					add((int)__ldg(&cellStart[k]), (int)__ldg(&cellStart[k + 1]));
 				}
 			}
 		}
 	}
-	int r = 0, j = 0, jend = 0;
-	if (valid && nr > 0)
-	{
-		const int2 rg = sRange[0][t];
-		j = rg.x;
-		jend = rg.y;
-	}
-	else
-		valid = false;
+	int r = -1, j = 0, jend = 0;
+	if (nr == 0) valid = false;
 	for (;;)
 	{
-		bool have = false;
+		// GRID_UNROLL candidates per lane and round: their loads are issued together (one dependent load per candidate was the
+		// kernel's critical path)
+		int jj[GRID_UNROLL];
+#pragma unroll
+		for (int k = 0; k < GRID_UNROLL; k++) jj[k] = -1;
 		if (valid)
 		{
-			while (j >= jend)
+#pragma unroll
+			for (int k = 0; k < GRID_UNROLL; k++)
 			{
-				if (++r >= nr)
+				while (valid && j >= jend)
 				{
-					valid = false;
-					break;
+					if (++r < nr)
+					{
+						const int2 rg = sRange[r][t];
+						j = rg.x;
+						jend = rg.y;
+					}
+					else
+						valid = false;
 				}
-				const int2 rg = sRange[r][t];
-				j = rg.x;
-				jend = rg.y;
+				if (valid) jj[k] = j++;
 			}
-			have = valid;
 		}
-		bool hit = false;
-		int idB = 0;
-		if (have)
+		float4 mnB[GRID_UNROLL], mxB[GRID_UNROLL];
+#pragma unroll
+		for (int k = 0; k < GRID_UNROLL; k++)
 		{
-			if (j > i)
+			mnB[k] = mk4(0, 0, 0);
+			mxB[k] = mnB[k];
+			if (jj[k] > i)
 			{
-				const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
-				const float4 mnB = __ldg(p), mxB = __ldg(p + 1);
-				idB = __float_as_int(mnB.w);
-				hit = aabbOverlap(mnA, mxA, mnB, mxB);
+				const float4* p = reinterpret_cast<const float4*>(&sorted[jj[k]]);
+				mnB[k] = __ldg(p);
+				mxB[k] = __ldg(p + 1);
 			}
-			j++;
 		}
-		stagePush(hit, idA, idB, stage, count, lane, pairs, ctr, maxPairs);
+#pragma unroll
+		for (int k = 0; k < GRID_UNROLL; k++)
+		{
+			const bool hit = jj[k] > i && aabbOverlap(mnA, mxA, mnB[k], mxB[k]);
+			stagePush(hit, idA, __float_as_int(mnB[k].w), stage, count, lane, pairs, ctr, maxPairs);
+		}
 		if (!__any_sync(0xffffffffu, valid)) break;
 	}
 	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
