@@ -230,7 +230,9 @@ static int blockSizeFor(const World* w)
 {
 	const int n = std::max(w->numBodies, 1);
 	if (n <= S_MAX) return S_MAX;  // one block: the whole solve runs in one CTA without any grid barrier
-	int S = divUp(n, w->smCount);
+	// k blocks per CTA (k = 1: the block state stays in shared memory for the whole solve), all CTAs equally loaded
+	const int k = divUp(n, w->smCount * S_MAX);
+	int S = divUp(n, w->smCount * k);
 	S = std::max(S, S_MIN);
 	S = std::min(S, S_MAX);
 	return S;
