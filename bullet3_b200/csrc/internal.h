@@ -208,6 +208,8 @@ struct World
 	DevBuf<unsigned int> dSolverScratch, dBlockStart, dBlockTileBase, dBlockTileOff, dCrossTileOff;
 	DevBuf<int> dBlockStatics;
 	DevBuf<float4> dTilesN, dTilesF;
+	DevBuf<float4> dSortedState;          // body state in block order: lin | ang | inertia (upper triangle, 2 float4) | pos
+	DevBuf<unsigned char> dSortedBoundary;
 	unsigned int* solverMisc = nullptr;    // -> misc words of dSolverScratch once a setup has run
 	bool solverAttrSet = false;
 	DevBuf<unsigned long long> dSolverProbe;  // development aid (b3b200_debug_solver_probe)

@@ -33,7 +33,7 @@ namespace b3b200
 // as many warps as keep the row solve free of spills -- more warps = fewer tiles per warp and colour
 constexpr int ITER_THREADS_NORMAL = 256, ITER_THREADS_FRICTION = 256;
 constexpr int SETUP_THREADS = 512;
-constexpr int S_MAX = 2560;       // dynamic bodies per block: (S_MAX + NSTATIC) * (80 + 6) B = 220 KB of shared memory
+constexpr int S_MAX = 2688;       // dynamic bodies per block: (S_MAX + NSTATIC) * (80 + 2) B = 220 KB of shared memory
 constexpr int S_MIN = 1024;       // below this a block is not worth a grid barrier
 constexpr int NSTATIC = 64;       // static bodies a block can keep in its own slots (more -> those contacts go the global way)
 constexpr int MAX_BLOCKS = 8192;  // block-start table of the scatter kernel lives in shared memory
@@ -48,7 +48,7 @@ constexpr int NT_STRIDE = NT_FIELDS * 32;
 constexpr int FT_FIELDS = 4, FT_LAMBDA = 3;
 constexpr int FT_STRIDE = FT_FIELDS * 32;
 constexpr unsigned int INVALID_IDS = 0xffffffffu;
-constexpr int ITER_SMEM_PER_SLOT = (int)(sizeof(float4) * 5 + sizeof(int) + sizeof(unsigned short));
+constexpr int ITER_SMEM_PER_SLOT = (int)(sizeof(float4) * 5 + sizeof(unsigned short));
 constexpr int ITER_SMEM_MAX = ITER_SMEM_PER_SLOT * (S_MAX + NSTATIC);
 
 // scratch layout (unsigned ints, zeroed before the setup kernels): [blockCount | blockCursor | crossHist | crossCursor | misc]
@@ -292,6 +292,12 @@ struct SetupArgs
 	int* contactColour;            // colour inside its class (cross colour / interior colour of its block), -2 = left out
 	int2* contactPair;             // dynamic bodies of the contact (-1 = that side is static): what the colouring needs, 8 coalesced bytes
 	int* tileSrc;                  // per row slot of every tile: the contact it is built from, -1 = padding
+	// body state in BLOCK ORDER (rank r = block * S + slot): what the iteration kernels read and write; filled by solverGatherKernel
+	float4 *gLin, *gAng, *gInerA, *gInerB, *gPos;
+	unsigned char* gBoundary;      // rank has cross contacts
+	const unsigned int* partVals;  // rank -> body
+	const unsigned int* partBounds;
+	const float4* vel;
 	unsigned int* blockCount;      // scratch, see the enum above
 	unsigned int* blockCursor;
 	unsigned int* crossHist;
@@ -426,9 +432,11 @@ B3_D void buildRow(const SetupArgs& s, int c, unsigned int idsWord, int batch, f
 		tn[(2 + 2 * i) * 32] = on ? mk4(ang1[i].x, ang1[i].y, ang1[i].z, bb[i]) : mk4(0, 0, 0, 0);
 	}
 	tn[NT_LAMBDA * 32] = mk4(0, 0, 0, 0);  // appliedRambdaDt
+	// the two bodies as the iteration kernels address them: rank in block order, or -(body + 2) for a body without a rank (static)
+	const int la = s.bodyLoc[aIdx], lb = s.bodyLoc[bIdx];
 	int4 tail;
-	tail.x = aIdx;
-	tail.y = bIdx;
+	tail.x = la >= 0 ? (la >> 12) * s.S + (la & 4095) : -(aIdx + 2);
+	tail.y = lb >= 0 ? (lb >> 12) * s.S + (lb & 4095) : -(bIdx + 2);
 	tail.z = batch;
 	tail.w = c;
 	reinterpret_cast<int4*>(tn)[NT_TAIL * 32] = tail;
@@ -451,10 +459,10 @@ B3_D void buildPadding(float4* __restrict__ tn, float4* __restrict__ tf)
 #pragma unroll
 	for (int i = 1; i < NT_TAIL; i++) tn[i * 32] = mk4(0, 0, 0, 0);
 	int4 tail;
-	tail.x = -1;
-	tail.y = -1;
+	tail.x = 0;
+	tail.y = 0;
 	tail.z = -1;
-	tail.w = -1;
+	tail.w = -1;  // no contact: padding
 	reinterpret_cast<int4*>(tn)[NT_TAIL * 32] = tail;
 #pragma unroll
 	for (int i = 0; i < FT_FIELDS; i++) tf[i * 32] = mk4(0, 0, 0, 0);
@@ -1023,6 +1031,46 @@ __global__ void __launch_bounds__(256, 2) solverBuildRowsKernel(SetupArgs s)
 	}
 }
 
+// ---- K6: body state into block order.  The iteration kernels then load / store a block with coalesced copies, and the cross rows
+// address their bodies by rank (no indirection through the partition on the critical path of a pass).
+__global__ void __launch_bounds__(256) solverGatherKernel(SetupArgs s, int numRanks)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= numRanks) return;
+	const int numDyn = (int)s.partBounds[6];
+	float4 lin = mk4(0, 0, 0), ang = lin, ia = lin, ib = lin, pos = lin;
+	unsigned char boundary = 0;
+	if (r < numDyn)
+	{
+		const int g = (int)s.partVals[r];
+		const float4 ps = s.pose[2 * g];
+		const float4* I = reinterpret_cast<const float4*>(&s.inertias[g].invInertiaWorld);
+		const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
+		lin = s.vel[2 * g];
+		ang = s.vel[2 * g + 1];
+		pos = ps;
+		ia = mk4(r0.x, r0.y, r0.z, r1.y);
+		ib = mk4(r1.z, r2.z, ps.w, 0.f);
+		boundary = (s.bodyMask[2 * g] | s.bodyMask[2 * g + 1]) != 0ull;
+	}
+	s.gLin[r] = lin;
+	s.gAng[r] = ang;
+	s.gInerA[r] = ia;
+	s.gInerB[r] = ib;
+	s.gPos[r] = pos;
+	s.gBoundary[r] = boundary;
+}
+__global__ void __launch_bounds__(256) solverScatterBackKernel(const float4* __restrict__ gLin, const float4* __restrict__ gAng, const float4* __restrict__ gInerB,
+															  const unsigned int* __restrict__ partVals, const unsigned int* __restrict__ partBounds, float4* __restrict__ vel)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= (int)partBounds[6]) return;
+	if (gInerB[r].z == 0.f) return;  // (no longer dynamic)
+	const int g = (int)partVals[r];
+	vel[2 * g] = gLin[r];
+	vel[2 * g + 1] = gAng[r];
+}
+
 // ================================================================ iterations
 struct IterArgs
 {
@@ -1033,7 +1081,9 @@ struct IterArgs
 	const float4* pose;
 	float4* vel;
 	const b3b200_inertia* inertias;
-	const unsigned int* partVals;      // bodies in Morton order: block b, slot k = partVals[b * S + k]
+	float4 *gLin, *gAng;               // velocities in block order (rank = block * S + slot): the cross rows' global memory
+	const float4 *gInerA, *gInerB, *gPos;
+	const unsigned char* gBoundary;
 	const unsigned int* partBounds;    // [6] = number of dynamic bodies
 	const int* blockStatics;
 	const unsigned int* blockTileBase;
@@ -1288,35 +1338,60 @@ B3_D void solveRowShared(float4* tilesN, float4* tilesF, unsigned int tile, int 
 // velocities have to be (one L2 round trip), and the constants of the two bodies ride along in the same round trip.
 struct CrossBodies
 {
-	const float4* pose;
-	float4* vel;
+	float4 *gLin, *gAng;
+	const float4 *gInerA, *gInerB;
+	const float4* pose;  // bodies without a rank (static): original arrays
+	const float4* vel;
 	const b3b200_inertia* inertias;
 };
+B3_D void loadCrossBody(const CrossBodies& cb, int id, BodyConst& C, float4& lin, float4& ang)
+{
+	if (id >= 0)
+	{
+		lin = __ldcg(&cb.gLin[id]);
+		ang = __ldcg(&cb.gAng[id]);
+		const float4 a0 = __ldg(&cb.gInerA[id]), a1 = __ldg(&cb.gInerB[id]);
+		C.i0 = mk4(a0.x, a0.y, a0.z), C.i1 = mk4(a0.y, a0.w, a1.x), C.i2 = mk4(a0.z, a1.x, a1.y);
+		C.pos = mk4(0, 0, 0, a1.z);
+	}
+	else
+	{
+		const int g = -id - 2;
+		lin = cb.vel[2 * g];
+		ang = cb.vel[2 * g + 1];
+		C.pos = cb.pose[2 * g];
+		const float4* I = reinterpret_cast<const float4*>(&cb.inertias[g].invInertiaWorld);
+		C.i0 = __ldg(I), C.i1 = __ldg(I + 1), C.i2 = __ldg(I + 2);
+		C.pos.w = 0.f;  // never written back
+	}
+}
 template <int PHASE>
-B3_D void solveRowGlobal(float4* tilesN, float4* tilesF, const CrossBodies& cb, unsigned int tile, int lane, RowRegs<PHASE>& r, const int4& tail)
+B3_D void solveRowGlobal(float4* tilesN, float4* tilesF, const CrossBodies& cb, const float4* gPos, unsigned int tile, int lane, RowRegs<PHASE>& r, const int4& tail)
 {
 	const int a = tail.x, b = tail.y;
-	if (a < 0) return;
+	if (tail.w < 0) return;  // padding
 	BodyConst A, B;
-	float4 linVelA = __ldcg(&cb.vel[2 * a]), angVelA = __ldcg(&cb.vel[2 * a + 1]);
-	float4 linVelB = __ldcg(&cb.vel[2 * b]), angVelB = __ldcg(&cb.vel[2 * b + 1]);
-	A.pos = __ldg(&cb.pose[2 * a]);
-	B.pos = __ldg(&cb.pose[2 * b]);
-	const float4* IA = reinterpret_cast<const float4*>(&cb.inertias[a].invInertiaWorld);
-	const float4* IB = reinterpret_cast<const float4*>(&cb.inertias[b].invInertiaWorld);
-	A.i0 = __ldg(IA), A.i1 = __ldg(IA + 1), A.i2 = __ldg(IA + 2);
-	B.i0 = __ldg(IB), B.i1 = __ldg(IB + 1), B.i2 = __ldg(IB + 2);
+	float4 linVelA, angVelA, linVelB, angVelB;
+	loadCrossBody(cb, a, A, linVelA, angVelA);
+	loadCrossBody(cb, b, B, linVelB, angVelB);
+	if (PHASE == 1)
+	{
+		// friction rows need the positions (r = centre - pos)
+		const float4 pa = a >= 0 ? __ldg(&gPos[a]) : cb.pose[2 * (-a - 2)], pb = b >= 0 ? __ldg(&gPos[b]) : cb.pose[2 * (-b - 2)];
+		A.pos = mk4(pa.x, pa.y, pa.z, A.pos.w);
+		B.pos = mk4(pb.x, pb.y, pb.z, B.pos.w);
+	}
 	if (!solveRowCore<PHASE>(r, A, B, linVelA, angVelA, linVelB, angVelB)) return;
 	storeRowLambda<PHASE>(tilesN, tilesF, tile, lane, r);
 	if (A.pos.w != 0.f)
 	{
-		__stcg(&cb.vel[2 * a], linVelA);
-		__stcg(&cb.vel[2 * a + 1], angVelA);
+		__stcg(&cb.gLin[a], linVelA);
+		__stcg(&cb.gAng[a], angVelA);
 	}
 	if (B.pos.w != 0.f)
 	{
-		__stcg(&cb.vel[2 * b], linVelB);
-		__stcg(&cb.vel[2 * b + 1], angVelB);
+		__stcg(&cb.gLin[b], linVelB);
+		__stcg(&cb.gAng[b], angVelB);
 	}
 }
 B3_D int4 loadTail(const float4* tilesN, unsigned int tile, int lane) { return reinterpret_cast<const int4*>(tilesN)[(size_t)tile * NT_STRIDE + NT_TAIL * 32 + lane]; }
@@ -1417,7 +1492,7 @@ B3_D void solveBlockInterior(float4* tilesN, float4* tilesF, unsigned int tileBa
 // cross colours of one pass: global velocities, a grid barrier per colour; the next colour's rows are fetched while the
 // other CTAs arrive.  Trailing colours of at most one tile per warp of a CTA are solved by CTA 0 alone between __syncthreads().
 template <int PHASE, int ITER_WARPS>
-B3_D void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, GridBarrier& bar, int Kc, int tailStart,
+B3_D void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, const float4* gPos, GridBarrier& bar, int Kc, int tailStart,
 											   const unsigned int* sCrossOff, unsigned int crossBase)
 {
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1437,13 +1512,13 @@ B3_D void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, Grid
 	{
 		if (t < sCrossOff[k + 1])
 		{
-			solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
+			solveRowGlobal<PHASE>(tilesN, tilesF, cb, gPos, crossBase + t, lane, pre, tail);
 			// (a colour with more tiles than the grid has warps: the rest without the early fetch)
 			for (t += gstride; t < sCrossOff[k + 1]; t += gstride)
 			{
 				loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
 				tail = loadTail(tilesN, crossBase + t, lane);
-				solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
+				solveRowGlobal<PHASE>(tilesN, tilesF, cb, gPos, crossBase + t, lane, pre, tail);
 			}
 		}
 		bar.arrive();
@@ -1466,7 +1541,7 @@ B3_D void solveCrossColours(float4* tilesN, float4* tilesF, CrossBodies cb, Grid
 				{
 					loadRowRegs<PHASE>(tilesN, tilesF, crossBase + t, lane, pre);
 					tail = loadTail(tilesN, crossBase + t, lane);
-					solveRowGlobal<PHASE>(tilesN, tilesF, cb, crossBase + t, lane, pre, tail);
+					solveRowGlobal<PHASE>(tilesN, tilesF, cb, gPos, crossBase + t, lane, pre, tail);
 				}
 				__syncthreads();
 			}
@@ -1504,8 +1579,7 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 	sb_.inerA = smem4 + 2 * slots;
 	sb_.inerB = smem4 + 3 * slots;
 	sb_.pos = smem4 + 4 * slots;
-	int* sSlotBody = reinterpret_cast<int*>(smem4 + 5 * slots);                 // body of every slot, -1 = none
-	unsigned short* sBoundary = reinterpret_cast<unsigned short*>(sSlotBody + slots);  // slots of the bodies that have cross contacts
+	unsigned short* sBoundary = reinterpret_cast<unsigned short*>(smem4 + 5 * slots);  // slots of the bodies that have cross contacts
 	GridBarrier bar;
 	bar.init(s.bar, gridDim.x);
 
@@ -1520,6 +1594,10 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 	int tailStart = Kc;
 	while (tailStart > 0 && sCrossOff[tailStart] - sCrossOff[tailStart - 1] <= (unsigned int)TAIL_TILES) tailStart--;
 	CrossBodies cb;
+	cb.gLin = s.gLin;
+	cb.gAng = s.gAng;
+	cb.gInerA = s.gInerA;
+	cb.gInerB = s.gInerB;
 	cb.pose = s.pose;
 	cb.vel = s.vel;
 	cb.inertias = s.inertias;
@@ -1543,35 +1621,39 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 		v.numColours = kc;
 		return v;
 	};
-	// everything of the block: bodies of the slots, their constants and velocities; lists the boundary slots
+	// the block's state: coalesced copies out of the block-ordered arrays (+ the few static bodies the block refers to, from the
+	// body arrays); lists the boundary slots
 	auto loadBlock = [&](const BlockView& v, bool listBoundary) {
-		for (int k = threadIdx.x; k < slots; k += ITER_THREADS)
+		const size_t first = (size_t)v.blk * s.S;
+		for (int k = threadIdx.x; k < v.count; k += ITER_THREADS)
 		{
-			int g = -1;
-			if (k < v.count)
-				g = (int)s.partVals[(size_t)v.blk * s.S + k];
-			else if (k >= s.S)
-				g = s.blockStatics[(size_t)v.blk * NSTATIC + (k - s.S)];
-			sSlotBody[k] = g;
+			sb_.lin[k] = __ldcg(&s.gLin[first + k]);
+			sb_.ang[k] = __ldcg(&s.gAng[first + k]);
+			sb_.inerA[k] = __ldg(&s.gInerA[first + k]);
+			sb_.inerB[k] = __ldg(&s.gInerB[first + k]);
+			sb_.pos[k] = __ldg(&s.gPos[first + k]);
+			if (listBoundary && s.gBoundary[first + k]) sBoundary[atomicAdd(&sNumBoundary, 1)] = (unsigned short)k;
+		}
+		for (int k = threadIdx.x; k < NSTATIC; k += ITER_THREADS)
+		{
+			const int g = s.blockStatics[(size_t)v.blk * NSTATIC + k];
 			if (g < 0) continue;
 			const float4 ps = s.pose[2 * g];
 			const float4* I = reinterpret_cast<const float4*>(&s.inertias[g].invInertiaWorld);
 			const float4 r0 = __ldg(I), r1 = __ldg(I + 1), r2 = __ldg(I + 2);
-			sb_.pos[k] = ps;
-			sb_.inerA[k] = mk4(r0.x, r0.y, r0.z, r1.y);
-			sb_.inerB[k] = mk4(r1.z, r2.z, ps.w, 0.f);
-			sb_.lin[k] = __ldcg(&s.vel[2 * g]);
-			sb_.ang[k] = __ldcg(&s.vel[2 * g + 1]);
-			if (listBoundary && k < v.count && (__ldg(&s.bodyMask[2 * g]) | __ldg(&s.bodyMask[2 * g + 1])) != 0ull) sBoundary[atomicAdd(&sNumBoundary, 1)] = (unsigned short)k;
+			sb_.pos[s.S + k] = ps;
+			sb_.inerA[s.S + k] = mk4(r0.x, r0.y, r0.z, r1.y);
+			sb_.inerB[s.S + k] = mk4(r1.z, r2.z, 0.f, 0.f);  // a static slot is never written back
+			sb_.lin[s.S + k] = s.vel[2 * g];
+			sb_.ang[s.S + k] = s.vel[2 * g + 1];
 		}
 	};
 	auto storeBlock = [&](const BlockView& v) {
+		const size_t first = (size_t)v.blk * s.S;
 		for (int k = threadIdx.x; k < v.count; k += ITER_THREADS)
 		{
-			const int g = sSlotBody[k];
-			if (sb_.inerB[k].z == 0.f) continue;
-			__stcg(&s.vel[2 * g], sb_.lin[k]);
-			__stcg(&s.vel[2 * g + 1], sb_.ang[k]);
+			__stcg(&s.gLin[first + k], sb_.lin[k]);
+			__stcg(&s.gAng[first + k], sb_.ang[k]);
 		}
 	};
 
@@ -1604,14 +1686,13 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 					for (int i = threadIdx.x; i < nB; i += ITER_THREADS)
 					{
 						const int k = sBoundary[i];
-						const int g = sSlotBody[k];
-						__stcg(&s.vel[2 * g], sb_.lin[k]);
-						__stcg(&s.vel[2 * g + 1], sb_.ang[k]);
+						__stcg(&s.gLin[(size_t)mine.blk * s.S + k], sb_.lin[k]);
+						__stcg(&s.gAng[(size_t)mine.blk * s.S + k], sb_.ang[k]);
 					}
 				}
 				B3_PROBE(2);
 				bar.arrive();
-				solveCrossColours<PHASE, ITER_WARPS>(s.tilesN, s.tilesF, cb, bar, Kc, tailStart, sCrossOff, crossBase);
+				solveCrossColours<PHASE, ITER_WARPS>(s.tilesN, s.tilesF, cb, s.gPos, bar, Kc, tailStart, sCrossOff, crossBase);
 				B3_PROBE(3);
 				if (mine.blk >= 0)
 				{
@@ -1619,9 +1700,8 @@ __global__ void __launch_bounds__(ITER_THREADS, 1) solverIterateKernel(IterArgs 
 					for (int i = threadIdx.x; i < nB; i += ITER_THREADS)
 					{
 						const int k = sBoundary[i];
-						const int g = sSlotBody[k];
-						sb_.lin[k] = __ldcg(&s.vel[2 * g]);
-						sb_.ang[k] = __ldcg(&s.vel[2 * g + 1]);
+						sb_.lin[k] = __ldcg(&s.gLin[(size_t)mine.blk * s.S + k]);
+						sb_.ang[k] = __ldcg(&s.gAng[(size_t)mine.blk * s.S + k]);
 					}
 					__syncthreads();
 				}
@@ -1674,7 +1754,7 @@ __global__ void __launch_bounds__(256) solverExportKernel(const float4* __restri
 		const float4* tn = tilesN + (size_t)tile * NT_STRIDE + lane;
 		const float4* tf = tilesF + (size_t)tile * FT_STRIDE + lane;
 		const int4 tail = reinterpret_cast<const int4*>(tn)[NT_TAIL * 32];
-		const bool valid = tail.x >= 0;
+		const bool valid = tail.w >= 0;
 		const unsigned int m = __ballot_sync(0xffffffffu, valid);
 		if (!m) continue;
 		unsigned int slot = 0;
@@ -1702,9 +1782,10 @@ __global__ void __launch_bounds__(256) solverExportKernel(const float4* __restri
 		dw[7] = mk4(bb[0], bb[1], bb[2], bb[3]);
 		dw[8] = tn[NT_LAMBDA * 32];
 		dw[9] = mk4(t0.w, t1.w, fl.x, fl.y);
+		const int4 cids = reinterpret_cast<const int4*>(&contacts[tail.w])[5];
 		int4 o;
-		o.x = tail.x;
-		o.y = tail.y;
+		o.x = abs(cids.z);  // (the tiles address the bodies by their rank in block order)
+		o.y = abs(cids.w);
 		o.z = tail.z;
 		o.w = 0;
 		reinterpret_cast<int4*>(dw)[10] = o;
@@ -1752,6 +1833,20 @@ static int fillSetupArgs(World* w, SetupArgs& s)
 	s.contactSlots = w->dContactSlots.ptr;
 	s.contactColour = w->dContactColour.ptr;
 	s.contactPair = w->dContactPair.ptr;
+	{
+		const size_t ranks = (size_t)B * (size_t)w->partS;
+		B3_TRY(w->dSortedState.reserve(5 * ranks));
+		B3_TRY(w->dSortedBoundary.reserve(ranks));
+		s.gLin = w->dSortedState.ptr;
+		s.gAng = s.gLin + ranks;
+		s.gInerA = s.gAng + ranks;
+		s.gInerB = s.gInerA + ranks;
+		s.gPos = s.gInerB + ranks;
+		s.gBoundary = w->dSortedBoundary.ptr;
+	}
+	s.partVals = w->dPartVals.ptr;
+	s.partBounds = w->dPartBounds.ptr;
+	s.vel = w->dVel.ptr;
 	s.tileSrc = w->dTileSrc.ptr;
 	unsigned int* scr = w->dSolverScratch.ptr;
 	s.blockCount = scr;
@@ -1817,6 +1912,11 @@ int launchSolverSetup(World* w)
 	B3_LAUNCH_CHECK();
 	solverBuildRowsKernel<<<w->smCount * 6, 256, 0, st>>>(s);
 	B3_LAUNCH_CHECK();
+	{
+		const int numRanks = B * w->partS;
+		solverGatherKernel<<<divUp(numRanks, 256), 256, 0, st>>>(s, numRanks);
+		B3_LAUNCH_CHECK();
+	}
 	w->solverMisc = s.misc;
 	return 0;
 }
@@ -1836,7 +1936,15 @@ int launchSolverIterate(World* w)
 	s.pose = w->dPose.ptr;
 	s.vel = w->dVel.ptr;
 	s.inertias = w->dInertias.ptr;
-	s.partVals = w->dPartVals.ptr;
+	{
+		const size_t ranks = (size_t)w->partBlocksMax * (size_t)w->partS;
+		s.gLin = w->dSortedState.ptr;
+		s.gAng = s.gLin + ranks;
+		s.gInerA = s.gAng + ranks;
+		s.gInerB = s.gInerA + ranks;
+		s.gPos = s.gInerB + ranks;
+		s.gBoundary = w->dSortedBoundary.ptr;
+	}
 	s.partBounds = w->dPartBounds.ptr;
 	s.blockStatics = w->dBlockStatics.ptr;
 	s.blockTileBase = w->dBlockTileBase.ptr;
@@ -1861,6 +1969,11 @@ int launchSolverIterate(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dGridBarrier.ptr, 0, sizeof(unsigned int) * 4, w->stream));
 	B3_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)solverIterateKernel<1, ITER_THREADS_FRICTION>, g, b1, args, smem, w->stream));
 	g_launchCount++;
+	{
+		const int n = std::max(w->numBodies, 1);
+		solverScatterBackKernel<<<divUp(n, 256), 256, 0, w->stream>>>(s.gLin, s.gAng, s.gInerB, w->dPartVals.ptr, w->dPartBounds.ptr, w->dVel.ptr);
+		B3_LAUNCH_CHECK();
+	}
 	return 0;
 }
 
