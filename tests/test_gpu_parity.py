@@ -299,6 +299,50 @@ def test_convex_contacts_match_oracle(clip, seed, rotate, shapes, n_side):
     assert np.array_equal(pz >= 0, pci >= 0)
 
 
+def _large_hull_pile(seed, n_side, verts, settle):
+    """a pile of larger seeded hulls (and a few boxes / tetrahedra) settled on a ground box: resting face / edge / vertex
+    contacts between hulls with up to 32 vertices -- the items whose edge x edge axes satKernel prunes hardest"""
+    rng = np.random.default_rng(seed)
+    w = capi.World(capi.default_config(8192))
+    scenes.add_ground_box(w, 60.0)
+    cols = [w.register_convex_points(scenes.box_points(0.6)), w.register_convex_points(scenes.tetra_points(1.0))]
+    for nv in verts:
+        cols.append(w.register_convex_points(scenes.random_hull_points(rng, nv, 0.6, 1.1)))
+    for i in range(n_side):
+        for j in range(n_side):
+            for k in range(n_side):
+                p = np.array([i, j, k], np.float64) * 1.7 + rng.uniform(-0.2, 0.2, 3)
+                p[1] += 1.2
+                pick = int(rng.integers(2, len(cols))) if rng.uniform() < 0.8 else int(rng.integers(0, 2))
+                w.register_instance(1.0, tuple(p), scenes.random_quat(rng), cols[pick])
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, 6)
+    w.step_n(1 / 60, settle)
+    return w
+
+
+@pytest.mark.parametrize("seed,n_side,verts,settle", [(0, 8, (16, 24, 32, 32), 90), (1, 7, (32, 32, 28), 200), (2, 9, (10, 20, 32), 30)])
+def test_large_hull_pile_contacts_bit_exact(seed, n_side, verts, settle):
+    w = _large_hull_pile(seed, n_side, verts, settle)
+    t = w.tables()
+    sh = oa.Shapes(t)
+    for _ in range(3):  # three consecutive states of the same pile
+        bodies = w.bodies()
+        w.write_bodies(bodies)
+        w.update_aabbs()
+        w.find_pairs()
+        pairs = w.pairs()
+        w.compute_contacts()
+        g = w.contacts()
+        o, pci = oa.convex_contacts_oracle(pairs, bodies, sh, -1e30, 0.02, 1 << 18)
+        assert len(o) > 300
+        assert assert_contacts_match(g, o), "contact points are expected to be bit-exact"
+        assert np.array_equal(contact_table(g)["worldNormalOnB"].view(np.uint32), contact_table(o)["worldNormalOnB"].view(np.uint32))
+        assert np.array_equal(w.pairs()["z"] >= 0, pci >= 0)
+        w.step_n(1 / 60, 7)
+    w.close()
+
+
 def test_resting_stack_contacts_ties():
     w = capi.World(capi.default_config(2048))
     scenes.box_stack(w, 6, 6, 6)

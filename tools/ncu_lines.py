@@ -12,6 +12,7 @@ import tempfile
 
 rep, kern, obj = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sect_re = sys.argv[5] if len(sys.argv) > 5 else kern  # regex for the mangled name in the object (template instances)
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
@@ -34,7 +35,7 @@ for line in out.splitlines():
     m = re.search(r'//## File "([^"]+)", line (\d+)', line)
     if m:
         cur = os.path.basename(m.group(1)) + ":" + m.group(2)
-    if re.search(kern, sect) and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+    if re.search(sect_re, sect) and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
         lines.append(cur)
 print("sass in report: %d, in object: %d" % (len(sass), len(lines)))
 n = min(len(sass), len(lines))
