@@ -21,6 +21,7 @@ namespace b3b200
 // ---------------------------------------------------------------- errors
 void setLastError(const char* fmt, ...);
 extern long long g_launchCount;
+extern long long g_allocEpoch;  // bumped by every device (re)allocation: a captured step graph that saw one is discarded
 
 #define B3_CUDA_CHECK(expr)                                                                 \
 	do                                                                                      \
@@ -76,6 +77,7 @@ struct DevBuf
 		if (n <= cap) return 0;
 		release();
 		if (n == 0) return 0;
+		g_allocEpoch++;
 		cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
 		if (e != cudaSuccess)
 		{

@@ -337,6 +337,7 @@ extern "C" int b3b200_slab_unique_id(b3b200_nccl_id* out)
 }
 extern "C" int b3b200_slab_init(b3b200_world* w, const b3b200_slab_config* cfg, const b3b200_nccl_id* id)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded || !cfg || !id) return B3B200_ERR_INVALID;
 	if (cfg->axis < 0 || cfg->axis > 2 || cfg->rank < 0 || cfg->rank >= cfg->numRanks || cfg->maxGhosts < 0 || cfg->numOwned < 0 || cfg->numOwned > w->numBodies ||
 		cfg->firstGhostSlot < 0)
@@ -398,6 +399,7 @@ extern "C" int b3b200_slab_last_counts(b3b200_world* w, int* left, int* right)
 }
 extern "C" int b3b200_slab_shutdown(b3b200_world* w)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w) return B3B200_ERR_INVALID;
 	if (w->device >= 0) cudaSetDevice(w->device);
 	slabDestroy(w);
@@ -436,6 +438,7 @@ extern "C" int b3b200_halo_pack(b3b200_world* w, int axis, float lo, float hi, i
 
 extern "C" int b3b200_halo_unpack(b3b200_world* w, const void* srcDevice, int count, int firstGhostSlot, int numGhostSlots)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded || count < 0 || firstGhostSlot < 0 || numGhostSlots < 0 || firstGhostSlot + numGhostSlots > w->numBodies ||
 		count > numGhostSlots || (count > 0 && !srcDevice))
 		return B3B200_ERR_INVALID;
@@ -466,6 +469,7 @@ extern "C" int b3b200_halo_ghost_ids(b3b200_world* w, int* dst, int n)
 // global id of every body slot (-1 = none); from then on pack sends these instead of globalIdBase + slot
 extern "C" int b3b200_halo_set_ids(b3b200_world* w, const int* ids, int n)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded || !ids || n != w->numBodies) return B3B200_ERR_INVALID;
 	B3_CUDA_CHECK(cudaSetDevice(w->device));
 	B3_TRY(w->dGhostGlobalId.reserve(std::max(w->numBodies, 1)));
@@ -478,6 +482,7 @@ extern "C" int b3b200_halo_set_ids(b3b200_world* w, const int* ids, int n)
 extern "C" int b3b200_halo_emigrate(b3b200_world* w, int axis, float lo, float hi, int numOwned, int rank, void* dstDevice, int capacity, int* slotsOut,
 									int* countOut)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded || !w->haloIdsSet || axis < 0 || axis > 2 || numOwned < 0 || numOwned > w->numBodies || !dstDevice || capacity < 0 ||
 		!slotsOut || !countOut)
 		return B3B200_ERR_INVALID;
@@ -514,6 +519,7 @@ extern "C" int b3b200_halo_emigrate(b3b200_world* w, int axis, float lo, float h
 
 extern "C" int b3b200_halo_adopt(b3b200_world* w, const void* srcDevice, int count, const int* slots)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded || !w->haloIdsSet || count < 0 || (count > 0 && (!srcDevice || !slots))) return B3B200_ERR_INVALID;
 	if (count == 0) return 0;
 	for (int k = 0; k < count; k++)

@@ -165,6 +165,7 @@ extern "C" int b3b200_checkpoint_save(b3b200_world* w, const char* path)
 // re-registered by the caller); body state, inertias and the joint set are replaced.
 extern "C" int b3b200_checkpoint_load(b3b200_world* w, const char* path)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || !path) return B3B200_ERR_INVALID;
 	if (w->device < 0 || !w->uploaded) return B3B200_ERR_STATE;
 	FILE* f = fopen(path, "rb");

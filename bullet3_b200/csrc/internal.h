@@ -233,6 +233,22 @@ struct World
 
 	int smCount = 148;
 
+	// CUDA graphs of one whole step (world.cu, stepGraphed): the launch sequence of a step depends on the host only through
+	// (world AABBs valid?, partition due?), so there is one captured graph per such key.  Any API call that can change launch
+	// parameters (registration, upload, settings, stand-alone stage calls ...) drops them (graphEpoch); a step whose capture saw
+	// a device (re)allocation is not kept.  state: 0 = this key has not run yet (run eagerly: sizes the buffers), 1 = ran
+	// eagerly (capture next), 2 = graph ready
+	struct StepGraph
+	{
+		int state = 0;
+		cudaGraphExec_t exec = nullptr;
+		long long launches = 0;
+		float dt = 0.f;
+	};
+	StepGraph stepGraphs[4];
+	int useGraphs = 1;  // B3B200_GRAPHS=0 / b3b200_set_step_graphs(w, 0): every step launches its kernels one by one
+	void dropStepGraphs();
+
 	// timing
 	bool timing = false;
 	cudaEvent_t ev[8] = {nullptr};

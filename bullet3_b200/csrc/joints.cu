@@ -464,6 +464,7 @@ extern "C" int b3b200_get_joints(b3b200_world* w, b3b200_generic_constraint* dst
 
 extern "C" int b3b200_solve_joints(b3b200_world* w)
 {
+	if (w) w->dropStepGraphs();  // may change what a step launches
 	if (!w || w->device < 0 || !w->uploaded) return B3B200_ERR_STATE;
 	B3_CUDA_CHECK(cudaSetDevice(w->device));
 	return launchSolveJoints(w);

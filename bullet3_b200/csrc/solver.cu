@@ -259,8 +259,9 @@ static int ensurePartition(World* w)
 	B3_TRY(w->dPartKeys.reserve(nb));
 	B3_TRY(w->dPartVals.reserve(nb));
 	B3_TRY(w->dPartBounds.reserve(8));
-	static const unsigned int init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u, 0u};
-	B3_CUDA_CHECK(cudaMemcpyAsync(w->dPartBounds.ptr, init, sizeof(init), cudaMemcpyHostToDevice, s));
+	// {min.xyz = 0xffffffff, max.xyz = 0, 0, 0} (memsets: capturable into the step graph, unlike a copy from pageable memory)
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dPartBounds.ptr, 0xff, 3 * sizeof(unsigned int), s));
+	B3_CUDA_CHECK(cudaMemsetAsync(w->dPartBounds.ptr + 3, 0, 5 * sizeof(unsigned int), s));
 	if (n > 0)
 	{
 		partBoundsKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr);

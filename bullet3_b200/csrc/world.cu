@@ -9,6 +9,7 @@ namespace b3b200
 {
 static thread_local char g_lastError[512] = "";
 long long g_launchCount = 0;
+long long g_allocEpoch = 0;
 
 void setLastError(const char* fmt, ...)
 {
@@ -58,7 +59,17 @@ int World::init(const b3b200_config* c, int dev, cudaStream_t st)
 	for (int i = 0; i < 2; i++) B3_CUDA_CHECK(cudaEventCreateWithFlags(&evNpFork[i], cudaEventDisableTiming));
 	for (int i = 0; i < 3; i++) B3_CUDA_CHECK(cudaEventCreateWithFlags(&evNpJoin[i], cudaEventDisableTiming));
 	if (const char* e = getenv("B3B200_NP_OVERLAP")) npOverlap = atoi(e) != 0;
+	if (const char* e = getenv("B3B200_GRAPHS")) useGraphs = atoi(e);
 	return 0;
+}
+
+void World::dropStepGraphs()
+{
+	for (StepGraph& g : stepGraphs)
+	{
+		if (g.exec) cudaGraphExecDestroy(g.exec);
+		g = StepGraph();
+	}
 }
 
 void World::destroy()
@@ -67,6 +78,7 @@ void World::destroy()
 	cudaSetDevice(device);
 	slabDestroy(this);
 	if (stream) cudaStreamSynchronize(stream);
+	dropStepGraphs();
 	for (int i = 0; i < 8; i++)
 		if (ev[i]) cudaEventDestroy(ev[i]);
 	for (int i = 0; i < 2; i++)
@@ -280,11 +292,88 @@ static int stepOnce(World* w, float dt)
 	return 0;
 }
 
+// One step through a captured CUDA graph (one cudaGraphLaunch instead of ~35 kernel launches + memsets: what a small world's
+// step costs is launch latency).  The reference has nothing like it (7..15 clFinish per step).
+static int stepGraphed(World* w, float dt)
+{
+	const bool partDue = !(w->partValid && w->partAge < w->partInterval && w->partBodies == w->numBodies);
+	const bool eligible = w->useGraphs && !w->timing && w->joints.empty() && !w->npOverlap && w->solverKind == B3B200_SOLVER_PGS && w->dSolverProbe.ptr == nullptr;
+	if (!eligible) return stepOnce(w, dt);
+	World::StepGraph& g = w->stepGraphs[(w->aabbsValid ? 1 : 0) | (partDue ? 2 : 0)];
+	if (g.state == 2 && g.dt != dt)
+	{
+		cudaGraphExecDestroy(g.exec);
+		g = World::StepGraph();
+		g.state = 1;
+	}
+	if (g.state == 0)
+	{
+		g.state = 1;
+		return stepOnce(w, dt);
+	}
+	if (g.state == 1)
+	{
+		const long long epoch = g_allocEpoch, launches0 = g_launchCount;
+		B3_CUDA_CHECK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeRelaxed));
+		const int rc = stepOnce(w, dt);  // also advances the host-side state exactly like an eager step
+		cudaGraph_t graph = nullptr;
+		const cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
+		if (rc < 0 || e != cudaSuccess || !graph)
+		{
+			if (graph) cudaGraphDestroy(graph);
+			cudaGetLastError();
+			w->useGraphs = 0;  // capture is not possible here (e.g. a caller-owned stream that is already capturing): stay eager
+			if (rc < 0) return rc;
+			setLastError("step graph capture failed: %s", cudaGetErrorString(e));
+			return B3B200_ERR_CUDA;
+		}
+		cudaGraphExec_t exec = nullptr;
+		const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+		cudaGraphDestroy(graph);
+		if (ei != cudaSuccess)
+		{
+			cudaGetLastError();
+			w->useGraphs = 0;
+			setLastError("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+			return B3B200_ERR_CUDA;
+		}
+		const long long launches = g_launchCount - launches0;
+		B3_CUDA_CHECK(cudaGraphLaunch(exec, w->stream));
+		if (g_allocEpoch != epoch)
+		{
+			// a buffer grew while capturing: this graph may hold a freed pointer after the next growth; use it once, then re-capture
+			B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+			cudaGraphExecDestroy(exec);
+			return 0;
+		}
+		g.exec = exec;
+		g.launches = launches;
+		g.dt = dt;
+		g.state = 2;
+		return 0;
+	}
+	B3_CUDA_CHECK(cudaGraphLaunch(g.exec, w->stream));
+	g_launchCount += g.launches;
+	// the host-side state an eager step leaves behind (solver.cu ensurePartition, launchSolverIterate, dynamics.cu launchIntegrate)
+	if (partDue)
+	{
+		w->partValid = true;
+		w->partAge = 1;
+		w->partBodies = w->numBodies;
+	}
+	else
+		w->partAge++;
+	w->soaDirty = true;
+	w->aabbsValid = true;
+	return 0;
+}
+
 }  // namespace b3b200
 
 using namespace b3b200;
 
-#define W_CHECK(w)                                                              \
+// every API entry point that is not a plain step / copy drops the captured step graphs (it may change what a step launches)
+#define W_CHECK_KEEP(w)                                                         \
 	if (!(w)) return B3B200_ERR_INVALID;                                        \
 	if ((w)->device < 0)                                                        \
 	{                                                                           \
@@ -292,13 +381,19 @@ using namespace b3b200;
 		return B3B200_ERR_STATE;                                                \
 	}                                                                           \
 	B3_CUDA_CHECK(cudaSetDevice((w)->device))
-#define W_UPLOADED(w)                                          \
-	W_CHECK(w);                                                \
+#define W_CHECK(w)   \
+	W_CHECK_KEEP(w); \
+	(w)->dropStepGraphs()
+#define W_UPLOADED_KEEP(w)                                     \
+	W_CHECK_KEEP(w);                                           \
 	if (!(w)->uploaded)                                        \
 	{                                                          \
 		setLastError("world not uploaded (call b3b200_upload)"); \
 		return B3B200_ERR_STATE;                               \
 	}
+#define W_UPLOADED(w)   \
+	W_UPLOADED_KEEP(w); \
+	(w)->dropStepGraphs()
 
 extern "C" const char* b3b200_last_error(void) { return g_lastError; }
 extern "C" int b3b200_version(void) { return 100; }
@@ -658,6 +753,7 @@ extern "C" int b3b200_upload(b3b200_world* w)
 extern "C" int b3b200_set_gravity(b3b200_world* w, const float* g)
 {
 	if (!w || !g) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->gravity[0] = g[0];
 	w->gravity[1] = g[1];
 	w->gravity[2] = g[2];
@@ -666,6 +762,7 @@ extern "C" int b3b200_set_gravity(b3b200_world* w, const float* g)
 extern "C" int b3b200_set_solver(b3b200_world* w, int kind, int iterations)
 {
 	if (!w || iterations < 0 || (kind != B3B200_SOLVER_PGS && kind != B3B200_SOLVER_JACOBI)) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->solverKind = kind;
 	w->solverIterations = iterations;
 	return 0;
@@ -673,18 +770,28 @@ extern "C" int b3b200_set_solver(b3b200_world* w, int kind, int iterations)
 extern "C" int b3b200_set_broadphase(b3b200_world* w, int kind)
 {
 	if (!w || (kind != B3B200_BP_SAP && kind != B3B200_BP_GRID)) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->bp.kind = kind;
+	return 0;
+}
+extern "C" int b3b200_set_step_graphs(b3b200_world* w, int on)
+{
+	if (!w) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();
+	w->useGraphs = on ? 1 : 0;
 	return 0;
 }
 extern "C" int b3b200_set_colouring(b3b200_world* w, int mode)
 {
 	if (!w || mode < 0 || mode > 1) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->solverColouring = mode;
 	return 0;
 }
 extern "C" int b3b200_set_contact_clip(b3b200_world* w, float minDist, float maxDist)
 {
 	if (!w) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->clipMinDist = minDist;
 	w->clipMaxDist = maxDist;
 	return 0;
@@ -692,13 +799,14 @@ extern "C" int b3b200_set_contact_clip(b3b200_world* w, float minDist, float max
 extern "C" int b3b200_set_angular_damping(b3b200_world* w, float d)
 {
 	if (!w) return B3B200_ERR_INVALID;
+	w->dropStepGraphs();  // a captured step holds the old value
 	w->angularDamping = d;
 	return 0;
 }
 
 extern "C" int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src, int n)
 {
-	W_UPLOADED(w);
+	W_UPLOADED_KEEP(w);
 	if (!src || n != w->numBodies) return B3B200_ERR_INVALID;
 	// the host mirror (get_table) is refreshed lazily: copying 80 B x N on the host here cost more than the transfer
 	w->hostBodiesStale = true;
@@ -711,7 +819,7 @@ extern "C" int b3b200_write_bodies(b3b200_world* w, const b3b200_rigid_body* src
 
 extern "C" int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, int n)
 {
-	W_UPLOADED(w);
+	W_UPLOADED_KEEP(w);
 	if (!dst || n < 0 || n > w->numBodies) return B3B200_ERR_INVALID;
 	B3_TRY(syncAoS(w));
 	if (n) B3_CUDA_CHECK(cudaMemcpyAsync(dst, w->dBodiesAoS.ptr, sizeof(b3b200_rigid_body) * n, cudaMemcpyDeviceToHost, w->stream));
@@ -720,7 +828,7 @@ extern "C" int b3b200_readback_bodies(b3b200_world* w, b3b200_rigid_body* dst, i
 }
 extern "C" int b3b200_write_body(b3b200_world* w, int bodyIndex, const b3b200_rigid_body* src)
 {
-	W_UPLOADED(w);
+	W_UPLOADED_KEEP(w);
 	if (!src || bodyIndex < 0 || bodyIndex >= w->numBodies) return B3B200_ERR_INVALID;
 	B3_TRY(syncAoS(w));
 	B3_CUDA_CHECK(cudaMemcpyAsync(&w->dBodiesAoS.ptr[bodyIndex], src, sizeof(b3b200_rigid_body), cudaMemcpyHostToDevice, w->stream));
@@ -732,7 +840,7 @@ extern "C" int b3b200_write_body(b3b200_world* w, int bodyIndex, const b3b200_ri
 }
 extern "C" int b3b200_read_body(b3b200_world* w, int bodyIndex, b3b200_rigid_body* dst)
 {
-	W_UPLOADED(w);
+	W_UPLOADED_KEEP(w);
 	if (!dst || bodyIndex < 0 || bodyIndex >= w->numBodies) return B3B200_ERR_INVALID;
 	B3_TRY(syncAoS(w));
 	B3_CUDA_CHECK(cudaMemcpyAsync(dst, &w->dBodiesAoS.ptr[bodyIndex], sizeof(b3b200_rigid_body), cudaMemcpyDeviceToHost, w->stream));
@@ -751,8 +859,8 @@ extern "C" int b3b200_num_bodies(b3b200_world* w) { return w ? (int)w->bodies.si
 
 extern "C" int b3b200_step(b3b200_world* w, float dt)
 {
-	W_UPLOADED(w);
-	B3_TRY(stepOnce(w, dt));
+	W_UPLOADED_KEEP(w);
+	B3_TRY(stepGraphed(w, dt));
 	if (w->timing)
 	{
 		B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
@@ -768,8 +876,8 @@ extern "C" int b3b200_step(b3b200_world* w, float dt)
 }
 extern "C" int b3b200_step_n(b3b200_world* w, float dt, int n)
 {
-	W_UPLOADED(w);
-	for (int i = 0; i < n; i++) B3_TRY(stepOnce(w, dt));
+	W_UPLOADED_KEEP(w);
+	for (int i = 0; i < n; i++) B3_TRY(stepGraphed(w, dt));
 	return 0;
 }
 extern "C" int b3b200_slab_step_n(b3b200_world* w, float dt, int n)
@@ -790,7 +898,7 @@ extern "C" int b3b200_slab_step_n(b3b200_world* w, float dt, int n)
 extern "C" int b3b200_slab_step(b3b200_world* w, float dt) { return b3b200_slab_step_n(w, dt, 1); }
 extern "C" int b3b200_synchronize(b3b200_world* w)
 {
-	W_CHECK(w);
+	W_CHECK_KEEP(w);
 	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
 	return 0;
 }
@@ -955,7 +1063,7 @@ extern "C" int b3b200_get_batches(b3b200_world* w, int* batchOffsets, int capaci
 }
 extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)
 {
-	W_CHECK(w);
+	W_CHECK_KEEP(w);
 	if (!dst8) return B3B200_ERR_INVALID;
 	unsigned int c[CTR_COUNT];
 	B3_TRY(readCounters(w, c));
@@ -965,7 +1073,7 @@ extern "C" int b3b200_get_counters(b3b200_world* w, int* dst8)
 }
 extern "C" int b3b200_get_work_counters(b3b200_world* w, int* dst, int n)
 {
-	W_CHECK(w);
+	W_CHECK_KEEP(w);
 	if (!dst || n < 0 || n > CTR_COUNT) return B3B200_ERR_INVALID;
 	unsigned int c[CTR_COUNT];
 	B3_TRY(readCounters(w, c));

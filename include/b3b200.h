@@ -138,6 +138,10 @@ int b3b200_set_broadphase(b3b200_world* w, int kind);
  * the races resolve); 0 = priority rounds (reproducible for a given contact array; the cross contacts in one CTA: slow
  * on large scenes). */
 int b3b200_set_colouring(b3b200_world* w, int mode);
+/* 1 (default): b3b200_step / b3b200_step_n replay the whole step as ONE captured CUDA graph (the reference issues each of its
+ * ~40 kernels with a clFinish in between, b3GpuRigidBodyPipeline.cpp:221-463); 0: kernel by kernel.  Same kernels, same
+ * results; worlds with joints, the Jacobi solver or stage timing enabled always step kernel by kernel. */
+int b3b200_set_step_graphs(b3b200_world* w, int on);
 /* clip window of the convex-convex clipper: the reference kernels use
  * (-1e30, 0.02) (satClipHullContacts.cl:916-917), the shared CPU header (-1, 0)
  * (b3ContactConvexConvexSAT.h:320-321).  Default = the kernel constants. */

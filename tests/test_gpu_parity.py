@@ -1282,3 +1282,45 @@ def test_write_body_and_read_body_touch_one_body():
     keep = np.arange(len(after)) != 7
     assert after[keep].tobytes() == before[keep].tobytes()
     assert L.b3b200_write_body(w.h, len(after), capi.ptr(one)) != 0 and L.b3b200_read_body(w.h, -1, capi.ptr(one)) != 0
+
+
+# ------------------------------------------------------------------ whole-step CUDA graphs
+def test_step_graph_replays_match_kernel_by_kernel_steps():
+    """b3b200_step / step_n through captured graphs (one per (AABBs valid, partition due) key) against the same steps launched
+    kernel by kernel.  The scene is order independent (every box touches only the ground, so the order in which the narrowphase's
+    atomics append the contacts cannot change a bit), which lets the two worlds be compared bit for bit over 60 steps that
+    include re-partitions, a settings call that drops the graphs and a body upload that invalidates the AABBs."""
+    def build(graphs):
+        w = capi.World(capi.default_config(4096))
+        scenes.add_ground_box(w, 80.0)
+        col = w.register_convex_points(scenes.box_points(0.5))
+        rng = np.random.default_rng(5)
+        for i in range(20):
+            for k in range(20):
+                w.register_instance(1.0, (i * 3.0 - 30, 0.7 + 0.3 * rng.uniform(), k * 3.0 - 30), scenes.random_quat(rng), col)
+        w.upload()
+        w.set_solver(capi.SOLVER_PGS, 6)
+        w.set_step_graphs(graphs)
+        return w
+
+    a, b = build(False), build(True)
+    l0 = capi.lib().b3b200_launch_count()
+    a.step_n(1 / 60, 25)
+    la = capi.lib().b3b200_launch_count() - l0
+    b.step_n(1 / 60, 25)
+    lb = capi.lib().b3b200_launch_count() - l0 - la
+    assert la == lb and la > 25 * 20, (la, lb)  # replays count the kernels they contain
+    for w in (a, b):
+        w.set_gravity((0.0, -9.8, 0.5))  # any settings call drops the graphs
+        w.step_n(1 / 60, 10)
+        st = w.bodies()
+        st["linVel"][1:, 1] += 1.0
+        w.write_bodies(st)  # AABBs invalid -> the next step is a different graph
+        for _ in range(25):
+            w.step(1 / 60)
+    ba, bb = a.bodies(), b.bodies()
+    assert a.counters()[1] == b.counters()[1] > 300
+    for f in ("pos", "quat", "linVel", "angVel"):
+        assert np.array_equal(ba[f].view(np.uint32), bb[f].view(np.uint32)), f
+    a.close()
+    b.close()
