@@ -179,6 +179,14 @@ B3_D int3 cellOf(const float4& mn, const float4& mx, float invCell)
 	const float lim = 1.0e9f;
 	return make_int3((int)fminf(fmaxf(floorf(cx * invCell), -lim), lim), (int)fminf(fmaxf(floorf(cy * invCell), -lim), lim), (int)fminf(fmaxf(floorf(cz * invCell), -lim), lim));
 }
+// Batched independent worlds ("key = (worldId << k) + cell"): every world gets its own 8 x 8 x 8 block of the 128^3
+// cell table (4096 blocks, then they repeat), i.e. its cell coordinates are shifted before the wrap.  Worlds that stand at the
+// same coordinates therefore do not pile into the same cells, neighbouring cells stay neighbours, and exactness never depends
+// on the shift: the pair test compares the world ids.
+B3_D int3 worldCellShift(int world)
+{
+	return make_int3((world & 15) << 3, ((world >> 4) & 15) << 3, ((world >> 8) & 15) << 3);
+}
 B3_D unsigned int cellKey(int x, int y, int z)
 {
 	return ((unsigned int)(z & (GRID_DIM - 1)) << 14) | ((unsigned int)(y & (GRID_DIM - 1)) << 7) | (unsigned int)(x & (GRID_DIM - 1));
@@ -189,7 +197,7 @@ B3_D unsigned int cellKey(int x, int y, int z)
 // empty ones -- with two loads, which is what the pair kernel needs.
 __global__ void __launch_bounds__(256) gridCountKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
 													   const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ rankInCell,
-													   unsigned int* __restrict__ cellCount)
+													   unsigned int* __restrict__ cellCount, const int* __restrict__ worldOf)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -197,6 +205,13 @@ __global__ void __launch_bounds__(256) gridCountKernel(const b3b200_aabb* __rest
 	int idx = smallMap[i];
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[idx]);
 	int3 c = cellOf(__ldg(p), __ldg(p + 1), invCell);
+	if (worldOf)
+	{
+		const int3 sh = worldCellShift(__ldg(&worldOf[idx]));
+		c.x += sh.x;
+		c.y += sh.y;
+		c.z += sh.z;
+	}
 	const unsigned int key = cellKey(c.x, c.y, c.z);
 	keys[i] = key;
 	rankInCell[i] = atomicAdd(&cellCount[key], 1u);
@@ -205,12 +220,14 @@ __global__ void __launch_bounds__(256) gridCountKernel(const b3b200_aabb* __rest
 // AABBs into cell order (the order inside a cell is the order of the atomics: the pair SET does not depend on it)
 __global__ void __launch_bounds__(256) gridScatterKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
 														 const unsigned int* __restrict__ keys, const unsigned int* __restrict__ rankInCell,
-														 const unsigned int* __restrict__ cellStart, b3b200_aabb* __restrict__ sorted)
+														 const unsigned int* __restrict__ cellStart, b3b200_aabb* __restrict__ sorted, const int* __restrict__ worldOf)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
-	const float4 mn = __ldg(p), mx = __ldg(p + 1);
+	const float4 mn = __ldg(p);
+	float4 mx = __ldg(p + 1);
+	if (worldOf) mx.w = __int_as_float(__ldg(&worldOf[smallMap[i]]));  // the sorted copy carries the world id for the pair kernel
 	float4* q = reinterpret_cast<float4*>(&sorted[cellStart[keys[i]] + rankInCell[i]]);
 	q[0] = mn;
 	q[1] = mx;
@@ -218,16 +235,16 @@ __global__ void __launch_bounds__(256) gridScatterKernel(const b3b200_aabb* __re
 
 // gather AABBs into sorted order (coalesced 2x128-bit per proxy) -- SAP path
 __global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restrict__ aabbs, const unsigned int* __restrict__ keys, const unsigned int* __restrict__ vals,
-													int n, b3b200_aabb* __restrict__ sorted, int* __restrict__ cellStart)
+													int n, b3b200_aabb* __restrict__ sorted, const int* __restrict__ worldOf)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[vals[i]]);
 	float4 mn = __ldg(p), mx = __ldg(p + 1);
+	if (worldOf) mx.w = __int_as_float(__ldg(&worldOf[vals[i]]));
 	float4* q = reinterpret_cast<float4*>(&sorted[i]);
 	q[0] = mn;
 	q[1] = mx;
-	(void)cellStart;
 }
 
 // One thread per AABB (in cell order).  Its candidates are the 3 x 3 x 3 cells around its own: per (y, z) row the cells x-1..x+1
@@ -239,7 +256,8 @@ __global__ void __launch_bounds__(256) gatherKernel(const b3b200_aabb* __restric
 constexpr int GRID_ROWS = 27;
 constexpr int GRID_UNROLL = 4;
 __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_aabb* __restrict__ sorted, const unsigned int* __restrict__ cellStart, int n,
-																  const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+																  const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs,
+																  int hasWorlds)
 {
 	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
 	__shared__ int2 sRange[GRID_ROWS][BP_THREADS];  // [first, end) per row of cells (9 rows, or 27 single cells next to the wrap-around)
@@ -258,7 +276,14 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 		mnA = p[0];
 		mxA = p[1];
 		idA = __float_as_int(mnA.w);
-		const int3 c = cellOf(mnA, mxA, invCell);
+		int3 c = cellOf(mnA, mxA, invCell);
+		if (hasWorlds)
+		{
+			const int3 sh = worldCellShift(__float_as_int(mxA.w));
+			c.x += sh.x;
+			c.y += sh.y;
+			c.z += sh.z;
+		}
 		const int xw = c.x & (GRID_DIM - 1), yw = c.y & (GRID_DIM - 1), zw = c.z & (GRID_DIM - 1);
 		const bool inner = yw >= 1 && yw <= GRID_DIM - 2 && zw >= 1 && zw <= GRID_DIM - 2;  // no (y, z) wrap: key order == (z, y, x) order
 		const bool xInner = xw >= 1 && xw <= GRID_DIM - 2;
@@ -331,7 +356,7 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 #pragma unroll
 		for (int k = 0; k < GRID_UNROLL; k++)
 		{
-			const bool hit = jj[k] > i && aabbOverlap(mnA, mxA, mnB[k], mxB[k]);
+			const bool hit = jj[k] > i && aabbOverlap(mnA, mxA, mnB[k], mxB[k]) && (!hasWorlds || __float_as_int(mxB[k].w) == __float_as_int(mxA.w));
 			stagePush(hit, idA, __float_as_int(mnB[k].w), stage, count, lane, pairs, ctr, maxPairs);
 		}
 		if (!__any_sync(0xffffffffu, valid)) break;
@@ -362,7 +387,7 @@ __global__ void __launch_bounds__(256) sapKeyKernel(const b3b200_aabb* __restric
 }
 
 __global__ void __launch_bounds__(BP_THREADS) sapSweepKernel(const b3b200_aabb* __restrict__ sorted, int n, const unsigned int* __restrict__ scal,
-															 b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+															 b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs, int hasWorlds)
 {
 	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
 	const int lane = threadIdx.x & 31;
@@ -400,7 +425,7 @@ __global__ void __launch_bounds__(BP_THREADS) sapSweepKernel(const b3b200_aabb* 
 				{
 					float4 mxB = p[1];
 					idB = __float_as_int(mnB.w);
-					hit = aabbOverlap(mnA, mxA, mnB, mxB);
+					hit = aabbOverlap(mnA, mxA, mnB, mxB) && (!hasWorlds || __float_as_int(mxB.w) == __float_as_int(mxA.w));
 					j++;
 				}
 			}
@@ -416,7 +441,8 @@ __global__ void __launch_bounds__(BP_THREADS) sapSweepKernel(const b3b200_aabb* 
 // ---------------------------------------------------------------- large x small
 __global__ void __launch_bounds__(BP_THREADS) largeSmallKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int nSmall,
 															   const int* __restrict__ largeMap, int nLarge,
-															   b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs)
+															   b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs,
+															   const int* __restrict__ worldOf, const int* __restrict__ largeStart)
 {
 	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
 	const int lane = threadIdx.x & 31;
@@ -433,12 +459,31 @@ __global__ void __launch_bounds__(BP_THREADS) largeSmallKernel(const b3b200_aabb
 		mxA = __ldg(p + 1);
 		idA = __float_as_int(mnA.w);
 	}
-	for (int l = 0; l < nLarge; l++)
+	// batched worlds: largeMap is grouped by world and a body only meets the large proxies of its own world
+	int first = 0, num = nLarge;
+	if (worldOf)
 	{
-		const float4* p = reinterpret_cast<const float4*>(&aabbs[largeMap[l]]);
-		float4 mnB = __ldg(p), mxB = __ldg(p + 1);
-		bool hit = valid && aabbOverlap(mnA, mxA, mnB, mxB);
-		stagePush(hit, idA, __float_as_int(mnB.w), stage, count, lane, pairs, ctr, maxPairs);
+		first = num = 0;
+		if (valid)
+		{
+			const int wd = __ldg(&worldOf[smallMap[i]]);
+			first = __ldg(&largeStart[wd]);
+			num = __ldg(&largeStart[wd + 1]) - first;
+		}
+	}
+	const int numMax = worldOf ? __reduce_max_sync(0xffffffffu, num) : nLarge;
+	for (int l = 0; l < numMax; l++)
+	{
+		bool hit = false;
+		int idB = 0;
+		if (l < num)
+		{
+			const float4* p = reinterpret_cast<const float4*>(&aabbs[largeMap[first + l]]);
+			float4 mnB = __ldg(p), mxB = __ldg(p + 1);
+			hit = valid && aabbOverlap(mnA, mxA, mnB, mxB);
+			idB = __float_as_int(mnB.w);
+		}
+		stagePush(hit, idA, idB, stage, count, lane, pairs, ctr, maxPairs);
 	}
 	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
 }
@@ -580,13 +625,13 @@ int Broadphase::calculatePairs(int maxPairsNow)
 			unsigned int* cellCount = reinterpret_cast<unsigned int*>(cellCnt.ptr);
 			unsigned int* cellBegin = reinterpret_cast<unsigned int*>(cellStart.ptr);
 			B3_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(unsigned int) * (GRID_CELLS + 4), s));
-			gridCountKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr, cellCount);
+			gridCountKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr, cellCount, worldOf);
 			B3_LAUNCH_CHECK();
 			// GRID_CELLS + 4 entries: cellStart[key + 3] of the last cells reads the total
 			B3_TRY(exclusiveScanLargeU32(s, cellCount, cellBegin, GRID_CELLS + 4, scanTotals.ptr, nullptr));
-			gridScatterKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, keys.ptr, vals.ptr, cellBegin, sortedAabbs.ptr);
+			gridScatterKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, keys.ptr, vals.ptr, cellBegin, sortedAabbs.ptr, worldOf);
 			B3_LAUNCH_CHECK();
-			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, cellBegin, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
+			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, cellBegin, numSmall, scal, pairs.ptr, ctr, maxPairsNow, worldOf ? 1 : 0);
 			B3_LAUNCH_CHECK();
 		}
 		else
@@ -594,14 +639,15 @@ int Broadphase::calculatePairs(int maxPairsNow)
 			sapKeyKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr);
 			B3_LAUNCH_CHECK();
 			B3_TRY(radixSortKV32(s, sortTmp, keys.ptr, vals.ptr, numSmall, 32));
-			gatherKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, keys.ptr, vals.ptr, numSmall, sortedAabbs.ptr, nullptr);
+			gatherKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, keys.ptr, vals.ptr, numSmall, sortedAabbs.ptr, worldOf);
 			B3_LAUNCH_CHECK();
-			sapSweepKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, numSmall, scal, pairs.ptr, ctr, maxPairsNow);
+			sapSweepKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, numSmall, scal, pairs.ptr, ctr, maxPairsNow, worldOf ? 1 : 0);
 			B3_LAUNCH_CHECK();
 		}
 		if (numLarge > 0)
 		{
-			largeSmallKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, largeMap.ptr, numLarge, pairs.ptr, ctr, maxPairsNow);
+			largeSmallKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, largeMap.ptr, numLarge, pairs.ptr, ctr, maxPairsNow, worldOf,
+																				worldOf ? largeStart.ptr : nullptr);
 			B3_LAUNCH_CHECK();
 		}
 	}

@@ -62,6 +62,10 @@ struct Broadphase
 	DevBuf<b3b200_aabb> aabbs;
 	DevBuf<int> smallMap, largeMap;
 	int numSmall = 0, numLarge = 0, numAabbs = 0;
+	// batched independent worlds (set by the owning World at upload; nullptr = one world): world id per proxy, and the large
+	// proxies grouped by world (largeMap) with their first index per world
+	const int* worldOf = nullptr;
+	DevBuf<int> largeStart;
 
 	DevBuf<b3b200_int4> pairs;
 	DevBuf<unsigned int> counters;  // CTR_COUNT (own copy when stand-alone; world shares its own)
@@ -107,6 +111,12 @@ struct World
 	bool uploaded = false;
 	bool everUploaded = false;  // bodies [0, numBodies) have device state that an upload must not rewind
 	bool aabbsValid = false;  // world AABBs on device match the current poses
+
+	// batched independent worlds (b3b200_set_current_world): bodies only collide inside their own world
+	int currentWorld = 0, numWorlds = 1;
+	std::vector<int> bodyWorld;  // per body
+	DevBuf<int> dBodyWorld;
+	int worldDynBodies = 0;  // > 0: every world has exactly this many dynamic bodies (solver blocks then hold whole worlds)
 
 	// settings
 	float gravity[3] = {0.f, -9.8f, 0.f};  // b3GpuRigidBodyPipeline.cpp:92

@@ -190,7 +190,7 @@ B3_D unsigned int spread10(unsigned int v)
 }
 
 __global__ void __launch_bounds__(256) partKeysKernel(const float4* __restrict__ pose, int n, const unsigned int* __restrict__ bounds,
-													  unsigned int* __restrict__ keys, unsigned int* __restrict__ vals)
+													  unsigned int* __restrict__ keys, unsigned int* __restrict__ vals, const int* __restrict__ worldOf, int worldShift)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(256) partKeysKernel(const float4* __restrict__
 			const unsigned int qz = (unsigned int)fminf(fmaxf((p.z - mnz) * sc, 0.f), 1023.f);
 			key = spread10(qx) | (spread10(qz) << 1) | (spread10(qy) << 2);
 		}
+		// batched independent worlds: world-major order (the top bits of the Morton key inside a world), so that a block of
+		// consecutive ranks holds whole worlds and no contact crosses blocks when the block size is a multiple of a world
+		if (worldOf) key = ((unsigned int)worldOf[i] << worldShift) | (key >> (30 - worldShift));
 	}
 	keys[i] = key;
 	vals[i] = (unsigned int)i;
@@ -235,6 +238,15 @@ static int blockSizeFor(const World* w)
 	int S = divUp(n, w->smCount * k);
 	S = std::max(S, S_MIN);
 	S = std::min(S, S_MAX);
+	// batched worlds of equal size: a block holds whole worlds (the ranks are world-major), so every contact is interior to a
+	// block and the iteration kernels never meet a grid barrier
+	const int D = w->worldDynBodies;
+	if (w->numWorlds > 1 && D > 0 && D <= S_MAX)
+	{
+		int m = divUp(S, D);
+		if (m * D > S_MAX) m = S_MAX / D;
+		S = std::max(m, 1) * D;
+	}
 	return S;
 }
 
@@ -266,7 +278,16 @@ static int ensurePartition(World* w)
 	{
 		partBoundsKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr);
 		B3_LAUNCH_CHECK();
-		partKeysKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr, w->dPartKeys.ptr, w->dPartVals.ptr);
+		int worldShift = 30;
+		if (w->numWorlds > 1)
+		{
+			int wbits = 1;
+			while ((1 << wbits) < w->numWorlds) wbits++;
+			worldShift = std::max(31 - wbits, 1);  // keys stay below 0x80000000 (statics: 0xffffffff)
+			if (worldShift > 30) worldShift = 30;
+		}
+		partKeysKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPose.ptr, n, w->dPartBounds.ptr, w->dPartKeys.ptr, w->dPartVals.ptr,
+													 w->numWorlds > 1 ? w->dBodyWorld.ptr : nullptr, worldShift);
 		B3_LAUNCH_CHECK();
 		B3_TRY(radixSortKV32(s, w->partSortTmp, w->dPartKeys.ptr, w->dPartVals.ptr, n, 32));
 		partAssignKernel<<<divUp(n, 256), 256, 0, s>>>(w->dPartKeys.ptr, w->dPartVals.ptr, n, w->partS, w->dBodyLoc.ptr);

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <math.h>
 #include "internal.h"
+#include <algorithm>
 
 namespace b3b200
 {
@@ -490,6 +491,11 @@ extern "C" int b3b200_reset(b3b200_world* w)
 	w->partValid = false;
 	w->solverMisc = nullptr;
 	w->bp.reset();
+	w->bp.worldOf = nullptr;
+	w->bodyWorld.clear();
+	w->currentWorld = 0;
+	w->numWorlds = 1;
+	w->worldDynBodies = 0;
 	return 0;
 }
 
@@ -619,7 +625,23 @@ static int registerBodyCommon(b3b200_world* w, float mass, const float* position
 		return -1;
 	}
 	w->uploaded = false;
+	w->bodyWorld.push_back(w->currentWorld);
+	if (w->currentWorld + 1 > w->numWorlds) w->numWorlds = w->currentWorld + 1;
 	return bodyIndex;
+}
+
+extern "C" int b3b200_set_current_world(b3b200_world* w, int worldIndex)
+{
+	if (!w || worldIndex < 0 || worldIndex >= (1 << 20)) return B3B200_ERR_INVALID;
+	w->currentWorld = worldIndex;
+	return 0;
+}
+extern "C" int b3b200_num_worlds(b3b200_world* w) { return w ? w->numWorlds : B3B200_ERR_INVALID; }
+extern "C" int b3b200_get_body_worlds(b3b200_world* w, int* dst, int n)
+{
+	if (!w || !dst || n < 0 || n > (int)w->bodyWorld.size()) return B3B200_ERR_INVALID;
+	for (int i = 0; i < n; i++) dst[i] = w->bodyWorld[i];
+	return 0;
 }
 
 extern "C" int b3b200_register_instance(b3b200_world* w, float mass, const float* position, const float* orientation, int collidableIndex, int userIndex)
@@ -740,6 +762,25 @@ extern "C" int b3b200_upload(b3b200_world* w)
 		B3_TRY(w->dConcaveSurvivors.reserve((size_t)std::max(w->cfg.maxTriConvexPairCapacity, 1)));
 	}
 	B3_TRY(w->dBodyCount.reserve(std::max(nb, (size_t)1024)));
+	w->bp.worldOf = nullptr;
+	w->worldDynBodies = 0;
+	if (w->numWorlds > 1)
+	{
+		// batched independent worlds: world id per body (= per proxy: one proxy per body, in creation order), the large proxies
+		// grouped by world, and -- when every world has the same number of dynamic bodies -- that number (solver.cu blockSizeFor)
+		B3_TRY(uploadVec(w->dBodyWorld, w->bodyWorld, 0, s));
+		w->bp.worldOf = w->dBodyWorld.ptr;
+		std::stable_sort(w->bp.largeIdx.begin(), w->bp.largeIdx.end(), [&](int a, int b) { return w->bodyWorld[a] < w->bodyWorld[b]; });
+		std::vector<int> start((size_t)w->numWorlds + 1, 0), dyn((size_t)w->numWorlds, 0);
+		for (int idx : w->bp.largeIdx) start[(size_t)w->bodyWorld[idx] + 1]++;
+		for (int k = 0; k < w->numWorlds; k++) start[k + 1] += start[k];
+		B3_TRY(uploadVec(w->bp.largeStart, start, 0, s));
+		for (int i = 0; i < w->numBodies; i++)
+			if (w->bodies[i].invMass != 0.f) dyn[w->bodyWorld[i]]++;
+		bool uniform = true;
+		for (int k = 1; k < w->numWorlds; k++) uniform = uniform && dyn[k] == dyn[0];
+		if (uniform && dyn[0] > 0) w->worldDynBodies = dyn[0];
+	}
 	B3_TRY(w->bp.writeAabbs());
 	B3_TRY(launchPackSoA(w));
 	B3_CUDA_CHECK(cudaStreamSynchronize(s));

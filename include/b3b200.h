@@ -97,6 +97,16 @@ int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
 int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const float* position, const float* orientation,
 						 const float* aabbMin3, const float* aabbMax3);
 /* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
+/* Batched independent worlds (no counterpart in the reference, which steps one world per b3GpuRigidBodyPipeline):
+ * bodies registered after b3b200_set_current_world(w, k) belong to world k (default 0).  Bodies of different worlds never
+ * collide, wherever they stand; every world sees exactly the pairs and contacts it would see alone.  One broadphase pass,
+ * one narrowphase, one solve for all worlds: the world id is part of the grid broadphase's cell key and of the solver's block
+ * order (blocks hold whole worlds when the worlds have equally many dynamic bodies: no cross-block contacts, no grid
+ * barriers).  Static bodies belong to a world like any other body.  With the SAP broadphase the result is the same but the
+ * sweep sees all worlds interleaved (slow): use the grid. */
+int b3b200_set_current_world(b3b200_world* w, int worldIndex);
+int b3b200_num_worlds(b3b200_world* w);
+int b3b200_get_body_worlds(b3b200_world* w, int* dst, int n);
 int b3b200_register_instances(b3b200_world* w, int n, const float* masses, const float* positions4,
 							  const float* orientations4, const int* collidableIndices);
 /* writeAllInstancesToGpu + writeAllBodiesToGpu + writeAabbsToGpu (GpuRigidBodyDemo.cpp:148-150).  Bodies that are already on the

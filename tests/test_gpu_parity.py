@@ -1324,3 +1324,134 @@ def test_step_graph_replays_match_kernel_by_kernel_steps():
         assert np.array_equal(ba[f].view(np.uint32), bb[f].view(np.uint32)), f
     a.close()
     b.close()
+
+
+# ------------------------------------------------------------------ batched independent worlds
+def _pile_world(w, rng, nx, ny, nz, cols, ground_col):
+    w.register_instance(0.0, (0.0, -50.0, 0.0), scenes.IDENT, ground_col)
+    for i in range(nx):
+        for j in range(ny):
+            for k in range(nz):
+                p = np.array([i, j, k], np.float64) * 1.5 + rng.uniform(-0.15, 0.15, 3)
+                p[1] += 0.9
+                w.register_instance(1.0, tuple(p), scenes.random_quat(rng), cols[int(rng.integers(0, len(cols)))])
+
+
+@pytest.mark.parametrize("kind", [capi.BP_GRID, capi.BP_SAP])
+def test_batched_worlds_see_exactly_their_own_pairs_and_contacts(kind):
+    """b3b200_set_current_world: 7 different piles registered at the SAME coordinates as 7 worlds of one b3b200 world, against
+    each pile alone in a world of its own: per world the sorted pair set and the contacts (points, normals, depths) are
+    bit-identical, no pair joins two worlds, and after stepping the batch every world still rests on its own ground."""
+    n_worlds = 7
+    def shapes(w):
+        cols = [w.register_convex_points(scenes.box_points(0.5)), w.register_convex_points(scenes.tetra_points(0.9))]
+        r = np.random.default_rng(99)
+        cols.append(w.register_convex_points(scenes.random_hull_points(r, 12, 0.5, 0.8)))
+        ground = w.register_convex_points(scenes.box_points(50.0))
+        return cols, ground
+
+    batch = capi.World(capi.default_config(8192))
+    cols, ground = shapes(batch)
+    for k in range(n_worlds):
+        batch.set_current_world(k)
+        _pile_world(batch, np.random.default_rng(100 + k), 4, 3 + k % 3, 4, cols, ground)
+    batch.upload()
+    assert batch.num_worlds() == n_worlds
+    batch.set_broadphase(kind)
+    world_of = batch.body_worlds()
+    first = [int(np.nonzero(world_of == k)[0][0]) for k in range(n_worlds)]
+    batch.update_aabbs()
+    batch.find_pairs()
+    bp = batch.pairs()
+    batch.compute_contacts()
+    bc = batch.contacts()
+    assert np.array_equal(world_of[bp["x"]], world_of[bp["y"]]), "a pair between two worlds"
+    for k in range(n_worlds):
+        single = capi.World(capi.default_config(1024))
+        cs, gs = shapes(single)
+        _pile_world(single, np.random.default_rng(100 + k), 4, 3 + k % 3, 4, cs, gs)
+        single.upload()
+        single.set_broadphase(kind)
+        single.update_aabbs()
+        single.find_pairs()
+        sp = single.pairs()
+        single.compute_contacts()
+        sc = single.contacts()
+        mine = bp[world_of[bp["x"]] == k].copy()
+        mine["x"] -= first[k]
+        mine["y"] -= first[k]
+        got, want = oa.sorted_pair_set(mine), oa.sorted_pair_set(sp)
+        assert len(want) > 50 and np.array_equal(got, want), k
+        cm = bc[world_of[np.abs(bc["bodyA"])] == k].copy()
+        cm["bodyA"] = np.sign(cm["bodyA"]) * (np.abs(cm["bodyA"]) - first[k])
+        cm["bodyB"] = np.sign(cm["bodyB"]) * (np.abs(cm["bodyB"]) - first[k])
+        # (body 0 of a stand-alone world is its static ground: -0 == 0, compare magnitudes + the static flag through invMass)
+        a, b = contact_table(cm), contact_table(sc)
+        assert len(a) == len(b) > 10
+        assert np.array_equal(np.abs(a["bodyA"]), np.abs(b["bodyA"])) and np.array_equal(np.abs(a["bodyB"]), np.abs(b["bodyB"]))
+        assert np.array_equal(a["worldNormalOnB"].view(np.uint32), b["worldNormalOnB"].view(np.uint32))
+        assert np.array_equal(a["worldPosB"].view(np.uint32), b["worldPosB"].view(np.uint32))
+        single.close()
+    batch.set_solver(capi.SOLVER_PGS, 6)
+    batch.step_n(1 / 60, 150)
+    b = batch.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all() and (b["pos"][dyn, 1] > 0.1).all() and (b["pos"][dyn, 1] < 12).all()
+    assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 0.5
+    batch.close()
+
+
+def test_batched_identical_worlds_have_no_cross_block_contacts_and_agree_with_a_single_world():
+    """config 5(i) in small: 40 copies of one 8 x 4 x 8 box pile as 40 worlds.  Blocks hold whole worlds (equal dynamic body
+    counts), so the solver has no cross-block batch; after 120 steps every world's kinetic / potential energy agrees with the
+    same pile stepped alone (the solve ORDER differs between the two, so the comparison is statistical)."""
+    def pile(w):
+        col = w.register_convex_points(scenes.box_points(0.5))
+        ground = w.register_convex_points(scenes.box_points(50.0))
+        return col, ground
+
+    def add(w, col, ground):
+        w.register_instance(0.0, (0.0, -50.0, 0.0), scenes.IDENT, ground)
+        for i in range(8):
+            for j in range(4):
+                for k in range(8):
+                    w.register_instance(1.0, (((j + 1) & 1) * 0.3 + 1.1 * i, 0.6 + 1.05 * j, ((j + 1) & 1) * 0.3 + 1.1 * k), scenes.IDENT, col)
+
+    n_worlds = 40
+    batch = capi.World(capi.default_config(16384))
+    col, ground = pile(batch)
+    for k in range(n_worlds):
+        batch.set_current_world(k)
+        add(batch, col, ground)
+    batch.upload()
+    batch.set_solver(capi.SOLVER_PGS, 10)
+    single = capi.World(capi.default_config(1024))
+    c1, g1 = pile(single)
+    add(single, c1, g1)
+    single.upload()
+    single.set_solver(capi.SOLVER_PGS, 10)
+    batch.step_n(1 / 60, 120)
+    single.step_n(1 / 60, 120)
+    b, s = batch.bodies(), single.bodies()
+    world_of = batch.body_worlds()
+    assert batch.counters()[1] > 30 * n_worlds * 10
+
+    def energy(x):
+        d = x["invMass"] != 0
+        return 0.5 * (x["linVel"][d, :3] ** 2).sum(), 9.8 * x["pos"][d, 1].sum()
+
+    ks, ps = energy(s)
+    for k in range(n_worlds):
+        kb, pb = energy(b[world_of == k])
+        assert abs(pb - ps) < 0.02 * ps, (k, pb, ps)
+        assert kb < max(4 * ks, 2.0), (k, kb, ks)
+    # the batch keeps the reference's invariant and has no cross-block colour
+    batch.update_aabbs()
+    batch.find_pairs()
+    batch.compute_contacts()
+    batch.solver_setup()
+    cs = batch.constraints()
+    assert len(cs) > 0
+    assert batch.counters()[3] == 0, "cross-block colours in a batch of equal worlds"
+    batch.close()
+    single.close()
