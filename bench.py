@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--ref-bodies", type=int, default=8192, help="--impl reference: bodies of the scene region one reference step simulates")
     ap.add_argument("--bt2-bodies", type=int, default=65536, help="bodies of the scene region the Bullet 2 MT baseline steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-batched", action="store_true", help="skip the batched independent worlds (BASELINE configs[4](i)) that are timed after the headline scene")
+    ap.add_argument("--worlds-per-gpu", type=int, default=1024, help="independent 256-box worlds batched into one b3b200 world per GPU")
     ap.add_argument("--no-slab", action="store_true", help="N > 1: skip the slab-decomposed scene (BASELINE configs[4](ii)) that is timed after the replicas")
     return ap.parse_args()
 
@@ -345,6 +347,47 @@ def slab_leg(world_size, rank, local_rank, steps, warmup, per_rank_x=32, ny=64, 
             "pairs": float(cnt[0]), "contacts": float(cnt[1]), "overflow_flags": int(cnt[2]), "finite": finite}
 
 
+def batched_worlds_leg(world_size, local_rank, steps, warmup, worlds_per_gpu):
+    """BASELINE configs[4](i): independent 256-box worlds batched into ONE b3b200 world per GPU (b3b200_set_current_world): one
+    broadphase / narrowphase / solve for all of them, no communication between ranks"""
+    import torch
+    import torch.distributed as dist
+    from bullet3_b200 import capi, scenes
+
+    per_world = 257
+    cfg = capi.default_config(worlds_per_gpu * per_world + 64)
+    stream = torch.cuda.Stream()
+    w = capi.World(cfg, device=local_rank, stream=stream.cuda_stream)
+    scenes.batched_box_worlds(w, worlds_per_gpu)
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, ITERS)
+    settle = 180
+    w.step_n(DT, settle + warmup)
+    w.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    w.step_n(DT, steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ctr = w.counters()
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    ok = bool(np.isfinite(b["pos"]).all() and (b["pos"][dyn, 1] > 0.5).all())
+    n = worlds_per_gpu * per_world
+    w.close()
+    return {"workload": "BASELINE configs[4](i): %d independent worlds per GPU (8 x 4 x 8 cubes, GpuBoxPlaneScene recipe, + 1 static ground box each, all at the same "
+                        "coordinates) batched into one b3b200 world per GPU; PGS %d iterations; settled %d steps" % (worlds_per_gpu, ITERS, settle),
+            "worlds": worlds_per_gpu * world_size, "bodies": n * world_size, "ms_per_step": float(ms[0]), "bodies_steps_per_s": n * world_size / (float(ms[0]) * 1e-3),
+            "world_steps_per_s": worlds_per_gpu * world_size / (float(ms[0]) * 1e-3), "pairs_per_gpu": int(ctr[0]), "contacts_per_gpu": int(ctr[1]),
+            "batches": int(ctr[2]), "cross_block_batches": int(ctr[3]), "overflow_flags": int(ctr[4]), "resting_on_their_grounds": ok}
+
+
 # ---------------------------------------------------------------------------------- main
 def main():
     a = parse()
@@ -510,6 +553,12 @@ def main():
                 if "cpu_baseline" not in out:
                     out["cpu_baseline"] = c1
             out["cpu_baselines_other"] = extra
+    batched_out = None
+    if not a.no_batched:
+        try:
+            batched_out = batched_worlds_leg(world_size, local_rank, max(5, a.steps), max(3, a.warmup), a.worlds_per_gpu)
+        except Exception as e:  # the headline line must still be printed
+            batched_out = {"error": repr(e)[:300]}
     slab_out = None
     if world_size > 1 and not a.no_slab:
         # the multi-GPU mode WITH communication (the independent replicas above have none)
@@ -521,6 +570,8 @@ def main():
         except Exception as e:  # the headline line must still be printed
             slab_out = {"error": repr(e)[:300]}
     if rank == 0:
+        if batched_out is not None:
+            out["batched_worlds"] = batched_out
         if slab_out is not None:
             out["slab"] = slab_out
         print(json.dumps(out))

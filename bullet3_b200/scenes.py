@@ -52,6 +52,30 @@ def box_stack(world, nx, ny, nz, half=0.5, spacing=1.0, y0=0.5, mass=1.0, ground
     return col
 
 
+def batched_box_worlds(world, num_worlds, nx=8, ny=4, nz=8):
+    """BASELINE configs[4](i) / SURVEY 8(d) config 5(i): `num_worlds` independent worlds, each an nx x ny x nz pile of cubes
+    (GpuBoxPlaneScene recipe) on its own static ground box, all at the SAME coordinates (b3b200_set_current_world)"""
+    ground = world.register_convex_points(box_points(400.0))
+    col = world.register_convex_points(box_points(1.0))
+    n = nx * ny * nz + 1
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    i, j, k = i.ravel(), j.ravel(), k.ravel()
+    pos = np.zeros((n, 3), np.float32)
+    pos[0] = (0.0, -400.0, 0.0)
+    pos[1:, 0] = ((j + 1) & 1) + 2.2 * i
+    pos[1:, 1] = 1.0 + 2.0 * j
+    pos[1:, 2] = ((j + 1) & 1) + 2.2 * k
+    masses = np.ones(n, np.float32)
+    masses[0] = 0.0
+    quats = np.tile(np.asarray(IDENT, np.float32), (n, 1))
+    cols = np.full(n, col, np.int32)
+    cols[0] = ground
+    for wd in range(num_worlds):
+        world.set_current_world(wd)
+        world.register_instances(masses, pos, quats, cols)
+    return n
+
+
 def box_plane_scene(world, nx, ny, nz, ground=True):
     """config 3: GpuBoxPlaneScene recipe (GpuConvexScene.cpp:163-278): cubes of half-extent 1,
     pos = (((j+1)&1) + 2.2 i, 1 + 2 j, ((j+1)&1) + 2.2 k)"""
