@@ -65,7 +65,7 @@ SYMBOLS = [
     "b3b200_last_error", "b3b200_version", "b3b200_launch_count", "b3b200_config_default", "b3b200_create", "b3b200_destroy",
     "b3b200_reset", "b3b200_register_convex", "b3b200_register_convex_points", "b3b200_register_plane", "b3b200_register_sphere",
     "b3b200_register_compound", "b3b200_register_concave", "b3b200_register_instance", "b3b200_register_body", "b3b200_register_instances", "b3b200_upload", "b3b200_set_gravity",
-    "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_colouring", "b3b200_set_step_graphs", "b3b200_set_current_world", "b3b200_num_worlds", "b3b200_get_body_worlds", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
+    "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_colouring", "b3b200_set_step_graphs", "b3b200_set_current_world", "b3b200_step_host_async", "b3b200_step_host_wait", "b3b200_num_worlds", "b3b200_get_body_worlds", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_write_body", "b3b200_read_body", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
     "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solve_joints", "b3b200_create_p2p_constraint", "b3b200_create_fixed_constraint", "b3b200_remove_constraint",
     "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_set_ray_accel", "b3b200_solver_setup",
@@ -242,6 +242,14 @@ class World:
 
     def set_broadphase(self, kind):
         check(self.L.b3b200_set_broadphase(self.h, int(kind)), "set_broadphase")
+
+    def step_host_async(self, dt, host_in, host_out):
+        """host_in / host_out: rigid_body_t arrays in page-locked memory (or None)"""
+        n = len(host_in) if host_in is not None else len(host_out)
+        check(self.L.b3b200_step_host_async(self.h, C.c_float(dt), ptr(host_in) if host_in is not None else None, ptr(host_out) if host_out is not None else None, n), "step_host_async")
+
+    def step_host_wait(self):
+        check(self.L.b3b200_step_host_wait(self.h), "step_host_wait")
 
     def set_current_world(self, k):
         check(self.L.b3b200_set_current_world(self.h, int(k)), "set_current_world")

@@ -153,6 +153,28 @@ int launchPackSoA(World* w)
 	return 0;
 }
 
+// pipelined host stepping (world.cu, b3b200_step_host_async): body records come from / go to a staging buffer instead of the
+// world's own AoS array
+int launchPackSoAFrom(World* w, const b3b200_rigid_body* src)
+{
+	int n = w->numBodies;
+	if (n == 0) return 0;
+	packSoAKernel<<<divUp(n, DYN_THREADS), DYN_THREADS, 0, w->stream>>>(src, n, w->dPose.ptr, w->dVel.ptr, w->dCollidableIdx.ptr);
+	B3_LAUNCH_CHECK();
+	w->soaDirty = true;    // the world's own AoS array does not hold this state
+	w->partValid = false;  // poses (and inverse masses) were replaced: the solver re-partitions the bodies
+	w->aabbsValid = false;
+	return 0;
+}
+int launchUnpackSoATo(World* w, b3b200_rigid_body* dst)
+{
+	int n = w->numBodies;
+	if (n == 0) return 0;
+	unpackSoAKernel<<<divUp(n, DYN_THREADS), DYN_THREADS, 0, w->stream>>>(dst, n, w->dPose.ptr, w->dVel.ptr, w->dCollidableIdx.ptr);
+	B3_LAUNCH_CHECK();
+	return 0;
+}
+
 int launchUnpackSoA(World* w)
 {
 	int n = w->numBodies;

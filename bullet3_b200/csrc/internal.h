@@ -256,6 +256,16 @@ struct World
 		float dt = 0.f;
 	};
 	StepGraph stepGraphs[4];
+
+	// pipelined host stepping (b3b200_step_host_async): two staging slots, an upload and a download stream of their own
+	struct HostPipe
+	{
+		cudaStream_t h2d = nullptr, d2h = nullptr;
+		DevBuf<b3b200_rigid_body> stage[2];
+		cudaEvent_t inReady[2] = {nullptr, nullptr}, stepDone[2] = {nullptr, nullptr}, outDone[2] = {nullptr, nullptr};
+		bool stepRecorded[2] = {false, false}, outPending[2] = {false, false};
+		unsigned long long calls = 0;
+	} pipe;
 	int useGraphs = 1;  // B3B200_GRAPHS=0 / b3b200_set_step_graphs(w, 0): every step launches its kernels one by one
 	void dropStepGraphs();
 
@@ -283,6 +293,8 @@ int allocateCollidable(World* w);
 // stage launchers (each async on w->stream)
 int launchPackSoA(World* w);    // AoS -> SoA
 int launchUnpackSoA(World* w);  // SoA -> AoS
+int launchPackSoAFrom(World* w, const b3b200_rigid_body* src);
+int launchUnpackSoATo(World* w, b3b200_rigid_body* dst);
 int launchUpdateAabbs(World* w);
 int launchIntegrate(World* w, float dt, bool alsoAabbs);
 int launchNarrowphase(World* w);

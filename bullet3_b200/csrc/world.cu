@@ -80,6 +80,20 @@ void World::destroy()
 	slabDestroy(this);
 	if (stream) cudaStreamSynchronize(stream);
 	dropStepGraphs();
+	if (pipe.h2d)
+	{
+		cudaStreamSynchronize(pipe.h2d);
+		cudaStreamSynchronize(pipe.d2h);
+		cudaStreamDestroy(pipe.h2d);
+		cudaStreamDestroy(pipe.d2h);
+		for (int i = 0; i < 2; i++)
+		{
+			cudaEventDestroy(pipe.inReady[i]);
+			cudaEventDestroy(pipe.stepDone[i]);
+			cudaEventDestroy(pipe.outDone[i]);
+		}
+		pipe.h2d = pipe.d2h = nullptr;
+	}
 	for (int i = 0; i < 8; i++)
 		if (ev[i]) cudaEventDestroy(ev[i]);
 	for (int i = 0; i < 2; i++)
@@ -921,6 +935,81 @@ extern "C" int b3b200_step_n(b3b200_world* w, float dt, int n)
 	for (int i = 0; i < n; i++) B3_TRY(stepGraphed(w, dt));
 	return 0;
 }
+// ---------------------------------------------------------------- pipelined stepping from / to host memory
+// The reference's host loop is writeAllBodiesToGpu -> stepSimulation -> readbackAllBodiesToCpu, each blocking
+// (b3GpuRigidBodyPipeline.cpp:221-463, b3GpuNarrowPhase.cpp:1020-1040).  Here the three overlap ACROSS calls: call c uploads into
+// staging slot c & 1 on an upload stream while call c - 1 still computes, and its result leaves on a download stream while
+// call c + 1 computes.  Nothing blocks the host; b3b200_step_host_wait drains the pipe.
+static int ensureHostPipe(World* w)
+{
+	World::HostPipe& p = w->pipe;
+	if (!p.h2d)
+	{
+		B3_CUDA_CHECK(cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+		B3_CUDA_CHECK(cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+		for (int i = 0; i < 2; i++)
+		{
+			B3_CUDA_CHECK(cudaEventCreateWithFlags(&p.inReady[i], cudaEventDisableTiming));
+			B3_CUDA_CHECK(cudaEventCreateWithFlags(&p.stepDone[i], cudaEventDisableTiming));
+			B3_CUDA_CHECK(cudaEventCreateWithFlags(&p.outDone[i], cudaEventDisableTiming));
+		}
+	}
+	for (int i = 0; i < 2; i++) B3_TRY(p.stage[i].reserve((size_t)std::max(w->numBodies, 1)));
+	return 0;
+}
+
+extern "C" int b3b200_step_host_async(b3b200_world* w, float dt, const b3b200_rigid_body* hostIn, b3b200_rigid_body* hostOut, int n)
+{
+	W_UPLOADED_KEEP(w);
+	if (n != w->numBodies || (!hostIn && !hostOut)) return B3B200_ERR_INVALID;
+	B3_TRY(ensureHostPipe(w));
+	World::HostPipe& p = w->pipe;
+	const int slot = (int)(p.calls++ & 1);
+	const size_t bytes = sizeof(b3b200_rigid_body) * (size_t)n;
+	if (hostIn)
+	{
+		// the slot is free once the step that used it two calls ago has consumed it and its result has left
+		if (p.stepRecorded[slot]) B3_CUDA_CHECK(cudaStreamWaitEvent(p.h2d, p.stepDone[slot], 0));
+		if (p.outPending[slot]) B3_CUDA_CHECK(cudaStreamWaitEvent(p.h2d, p.outDone[slot], 0));
+		B3_CUDA_CHECK(cudaMemcpyAsync(p.stage[slot].ptr, hostIn, bytes, cudaMemcpyHostToDevice, p.h2d));
+		B3_CUDA_CHECK(cudaEventRecord(p.inReady[slot], p.h2d));
+		B3_CUDA_CHECK(cudaStreamWaitEvent(w->stream, p.inReady[slot], 0));
+		B3_TRY(launchPackSoAFrom(w, p.stage[slot].ptr));
+		w->hostBodiesStale = true;
+	}
+	B3_TRY(stepGraphed(w, dt));
+	if (hostOut)
+	{
+		if (!hostIn)
+		{
+			// chained stepping: the records' other fields come from the world's own array
+			if (p.outPending[slot]) B3_CUDA_CHECK(cudaStreamWaitEvent(w->stream, p.outDone[slot], 0));
+			B3_TRY(syncAoS(w));
+			B3_CUDA_CHECK(cudaMemcpyAsync(p.stage[slot].ptr, w->dBodiesAoS.ptr, bytes, cudaMemcpyDeviceToDevice, w->stream));
+		}
+		else
+			B3_TRY(launchUnpackSoATo(w, p.stage[slot].ptr));
+	}
+	B3_CUDA_CHECK(cudaEventRecord(p.stepDone[slot], w->stream));
+	p.stepRecorded[slot] = true;
+	p.outPending[slot] = false;
+	if (hostOut)
+	{
+		B3_CUDA_CHECK(cudaStreamWaitEvent(p.d2h, p.stepDone[slot], 0));
+		B3_CUDA_CHECK(cudaMemcpyAsync(hostOut, p.stage[slot].ptr, bytes, cudaMemcpyDeviceToHost, p.d2h));
+		B3_CUDA_CHECK(cudaEventRecord(p.outDone[slot], p.d2h));
+		p.outPending[slot] = true;
+	}
+	return 0;
+}
+extern "C" int b3b200_step_host_wait(b3b200_world* w)
+{
+	W_CHECK_KEEP(w);
+	if (w->pipe.d2h) B3_CUDA_CHECK(cudaStreamSynchronize(w->pipe.d2h));
+	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	return 0;
+}
+
 extern "C" int b3b200_slab_step_n(b3b200_world* w, float dt, int n)
 {
 	W_UPLOADED(w);

@@ -97,6 +97,14 @@ int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
 int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const float* position, const float* orientation,
 						 const float* aabbMin3, const float* aabbMax3);
 /* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
+/* Pipelined stepping from / to HOST memory: upload `hostIn` (all bodies; NULL = keep stepping the state on the device), step,
+ * download the stepped bodies into `hostOut` (NULL = no download) -- all asynchronously: the upload of call c overlaps the
+ * step of call c - 1 and the download overlaps the step of call c + 1 (two staging slots, separate copy streams).  The host
+ * buffers must be page-locked (cudaHostAlloc / cudaHostRegister) for the overlap and must stay untouched until
+ * b3b200_step_host_wait returns.  The blocking reference loop it replaces: writeAllBodiesToGpu -> stepSimulation ->
+ * readbackAllBodiesToCpu (b3GpuNarrowPhase.cpp:1020-1040, b3GpuRigidBodyPipeline.cpp:221-463). */
+int b3b200_step_host_async(b3b200_world* w, float dt, const b3b200_rigid_body* hostIn, b3b200_rigid_body* hostOut, int numBodies);
+int b3b200_step_host_wait(b3b200_world* w);
 /* Batched independent worlds (no counterpart in the reference, which steps one world per b3GpuRigidBodyPipeline):
  * bodies registered after b3b200_set_current_world(w, k) belong to world k (default 0).  Bodies of different worlds never
  * collide, wherever they stand; every world sees exactly the pairs and contacts it would see alone.  One broadphase pass,

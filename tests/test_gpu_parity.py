@@ -1455,3 +1455,62 @@ def test_batched_identical_worlds_have_no_cross_block_contacts_and_agree_with_a_
     assert batch.counters()[3] == 0, "cross-block colours in a batch of equal worlds"
     batch.close()
     single.close()
+
+
+def test_pipelined_host_stepping_matches_blocking_write_step_readback():
+    """b3b200_step_host_async (upload / step / download overlapped across calls) against b3b200_write_bodies -> b3b200_step ->
+    b3b200_readback_bodies on the same inputs, bit for bit (order-independent scene: every box touches only the ground)"""
+    import torch
+
+    def build():
+        w = capi.World(capi.default_config(4096))
+        scenes.add_ground_box(w, 80.0)
+        col = w.register_convex_points(scenes.box_points(0.5))
+        rng = np.random.default_rng(11)
+        for i in range(24):
+            for k in range(24):
+                w.register_instance(1.0, (i * 3.0 - 36, 0.6 + 0.2 * rng.uniform(), k * 3.0 - 36), scenes.random_quat(rng), col)
+        w.upload()
+        w.set_solver(capi.SOLVER_PGS, 5)
+        return w
+
+    a, b = build(), build()
+    a.step_n(1 / 60, 30)
+    base = a.bodies()
+    n = len(base)
+    rng = np.random.default_rng(3)
+    inputs = []
+    for k in range(7):
+        s = base.copy()
+        s["linVel"][1:, :3] += rng.normal(size=(n - 1, 3)).astype(np.float32) * 0.3
+        s["pos"][1:, 1] += 0.01 * k
+        inputs.append(s)
+    want = []
+    for s in inputs:
+        a.write_bodies(s)
+        a.step(1 / 60)
+        want.append(a.bodies())
+    pins = [torch.empty(base.nbytes, dtype=torch.uint8).pin_memory() for _ in range(2 * len(inputs))]
+    hin = [np.frombuffer(p.numpy(), dtype=capi.rigid_body_t) for p in pins[: len(inputs)]]
+    hout = [np.frombuffer(p.numpy(), dtype=capi.rigid_body_t) for p in pins[len(inputs):]]
+    for h, s in zip(hin, inputs):
+        h[:] = s
+    for h, o in zip(hin, hout):
+        b.step_host_async(1 / 60, h, o)
+    b.step_host_wait()
+    for k in range(len(inputs)):
+        for f in ("pos", "quat", "linVel", "angVel", "invMass", "collidableIdx"):
+            assert np.array_equal(hout[k][f].view(np.uint32), want[k][f].view(np.uint32)), (k, f)
+    # chained: no upload, the device state keeps stepping, every state comes back
+    b.write_bodies(inputs[0])
+    a.write_bodies(inputs[0])
+    for k in range(3):
+        b.step_host_async(1 / 60, None, hout[k])
+        a.step(1 / 60)
+        want[k] = a.bodies()
+    b.step_host_wait()
+    for k in range(3):
+        assert np.array_equal(hout[k]["pos"].view(np.uint32), want[k]["pos"].view(np.uint32)), k
+    assert np.array_equal(b.bodies()["linVel"].view(np.uint32), a.bodies()["linVel"].view(np.uint32))
+    a.close()
+    b.close()
