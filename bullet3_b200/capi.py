@@ -29,6 +29,7 @@ convex_t = np.dtype([("localCenter", *F4), ("extents", *F4), ("mC", *F4), ("mE",
                      ("uniqueEdgesOffset", "i4"), ("numUniqueEdges", "i4"), ("unused", "i4")])
 aabb_t = np.dtype([("min", "f4", 3), ("minIndex", "i4"), ("max", "f4", 3), ("maxIndex", "i4")])
 int4_t = np.dtype([("x", "i4"), ("y", "i4"), ("z", "i4"), ("w", "i4")])
+mpr_result_t = np.dtype([("result", "i4"), ("depth", "f4"), ("dir", "f4", 3), ("pos", "f4", 3)])
 contact4_t = np.dtype([("worldPosB", "f4", (4, 4)), ("worldNormalOnB", *F4), ("restitutionCmp", "u2"), ("frictionCmp", "u2"),
                        ("batchIdx", "i4"), ("bodyA", "i4"), ("bodyB", "i4"), ("childA", "i4"), ("childB", "i4"),
                        ("unused1", "i4"), ("unused2", "i4")])
@@ -65,7 +66,7 @@ SYMBOLS = [
     "b3b200_last_error", "b3b200_version", "b3b200_launch_count", "b3b200_config_default", "b3b200_create", "b3b200_destroy",
     "b3b200_reset", "b3b200_register_convex", "b3b200_register_convex_points", "b3b200_register_plane", "b3b200_register_sphere",
     "b3b200_register_compound", "b3b200_register_concave", "b3b200_register_instance", "b3b200_register_body", "b3b200_register_instances", "b3b200_upload", "b3b200_set_gravity",
-    "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_colouring", "b3b200_set_step_graphs", "b3b200_set_current_world", "b3b200_step_host_async", "b3b200_step_host_wait", "b3b200_num_worlds", "b3b200_get_body_worlds", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
+    "b3b200_set_solver", "b3b200_set_broadphase", "b3b200_set_colouring", "b3b200_set_step_graphs", "b3b200_set_current_world", "b3b200_mpr_penetration", "b3b200_step_host_async", "b3b200_step_host_wait", "b3b200_num_worlds", "b3b200_get_body_worlds", "b3b200_set_contact_clip", "b3b200_set_angular_damping", "b3b200_write_bodies",
     "b3b200_readback_bodies", "b3b200_write_body", "b3b200_read_body", "b3b200_readback_inertias", "b3b200_num_bodies", "b3b200_step", "b3b200_step_n", "b3b200_synchronize",
     "b3b200_update_aabbs", "b3b200_find_pairs", "b3b200_compute_contacts", "b3b200_solve_contacts", "b3b200_solve_joints", "b3b200_create_p2p_constraint", "b3b200_create_fixed_constraint", "b3b200_remove_constraint",
     "b3b200_num_constraints", "b3b200_get_joints", "b3b200_cast_rays", "b3b200_set_ray_accel", "b3b200_solver_setup",
@@ -525,3 +526,19 @@ class Broadphase:
         ms = C.c_float(0)
         check(self.L.b3b200_bp_last_ms(self.h, C.byref(ms)), "bp_last_ms")
         return ms.value
+
+
+def mpr_penetration(pairs, bodies, collidables, convex, vertices, sep_normals, has_sep_axis, capacity, count0=0, device=0):
+    """mprPenetrationKernel on host arrays (b3b200_mpr_penetration).  Returns (pairs, sep_normals, has_sep_axis, contacts[:total], total, results)"""
+    L = lib()
+    pairs = np.ascontiguousarray(pairs.copy())
+    sep = np.ascontiguousarray(sep_normals, np.float32).copy()
+    has = np.ascontiguousarray(has_sep_axis, np.int32).copy()
+    contacts = np.zeros(max(capacity, 1), contact4_t)
+    n = C.c_int(int(count0))
+    res = np.zeros(len(pairs), mpr_result_t)
+    bodies, collidables, convex = np.ascontiguousarray(bodies), np.ascontiguousarray(collidables), np.ascontiguousarray(convex)
+    vertices = np.ascontiguousarray(vertices, np.float32)
+    check(L.b3b200_mpr_penetration(int(device), ptr(pairs), len(pairs), ptr(bodies), len(bodies), ptr(collidables), len(collidables), ptr(convex), len(convex),
+                                   ptr(vertices), len(vertices), ptr(sep), ptr(has), ptr(contacts), int(capacity), C.byref(n), ptr(res)), "mpr_penetration")
+    return pairs, sep, has, contacts[: min(n.value, capacity)], n.value, res

@@ -97,6 +97,16 @@ int b3b200_register_instance(b3b200_world* w, float mass, const float* position,
 int b3b200_register_body(b3b200_world* w, int collidableIndex, float mass, const float* position, const float* orientation,
 						 const float* aabbMin3, const float* aabbMax3);
 /* the same for n instances in one call (positions/orientations: n x 4 floats); returns the first body index */
+/* The MPR stage of the reference's GPU narrowphase as a stand-alone kernel: mprPenetrationKernel (kernels/mpr.cl:14-89, launched
+ * by b3ConvexHullContact.cpp:2817-2850 when useMprGpu is set) = b3MprPenetration (shared/b3MprPenetration.h:825-888) per convex x
+ * convex pair; a penetrating pair gets pairs[i].z = its contact, a ONE-point contact (portal position, normal = -direction,
+ * depth = -distance) appended at *numContacts, hasSepAxis[i] = 1 and sepNormals[i] = -direction.  All arrays are HOST arrays
+ * in the layout of the reference kernel's buffers (this is the call the reference's serialized test launches replay,
+ * test/OpenCL/AllBullet3Kernels/testExecuteBullet3NarrowphaseKernels.cpp:382-420). */
+int b3b200_mpr_penetration(int device, b3b200_int4* pairs, int numPairs, const b3b200_rigid_body* bodies, int numBodies,
+						   const b3b200_collidable* collidables, int numCollidables, const b3b200_convex_polyhedron* convex, int numConvex,
+						   const b3b200_float4* vertices, int numVertices, b3b200_float4* sepNormals, int* hasSepAxis,
+						   b3b200_contact4* contactsOut, int contactCapacity, int* numContacts, b3b200_mpr_result* results);
 /* Pipelined stepping from / to HOST memory: upload `hostIn` (all bodies; NULL = keep stepping the state on the device), step,
  * download the stepped bodies into `hostOut` (NULL = no download) -- all asynchronously: the upload of call c overlaps the
  * step of call c - 1 and the download overlaps the step of call c + 1 (two staging slots, separate copy streams).  The host

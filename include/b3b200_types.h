@@ -146,6 +146,15 @@ typedef struct B3B200_ALIGN16 b3b200_aabb
 	};
 } b3b200_aabb;
 
+/* per-pair output of b3b200_mpr_penetration: what b3MprPenetration (shared/b3MprPenetration.h:825-888) returned for the pair */
+typedef struct b3b200_mpr_result
+{
+	int result; /* 0 = penetrating (depth / dir / pos valid), -1 = not, -2 = pair skipped (not two hulls, or both static) */
+	float depth;
+	float dir[3];
+	float pos[3];
+} b3b200_mpr_result;
+
 typedef struct B3B200_ALIGN16 b3b200_contact4
 {
 	b3b200_float4 worldPosB[4]; /* xyz = point on B, w = depth */

@@ -21,6 +21,7 @@
 #include "Bullet3Collision/NarrowPhaseCollision/shared/b3UpdateAabbs.h"
 #include "Bullet3Collision/NarrowPhaseCollision/b3ConvexUtility.h"
 #include "Bullet3Collision/BroadPhaseCollision/shared/b3Aabb.h"
+#include "Bullet3Collision/NarrowPhaseCollision/shared/b3MprPenetration.h"
 #include "Bullet3Dynamics/shared/b3IntegrateTransforms.h"
 #include "Bullet3Dynamics/shared/b3ConvertConstraint4.h"
 
@@ -400,6 +401,66 @@ int ref_cpu_get_table(void* h, int which, void* dst, int capacity, int* count)
 	*count = n;
 	const int m = n < capacity ? n : capacity;
 	if (dst && m > 0 && src) memcpy(dst, src, (size_t)sz * m);
+	return 0;
+}
+
+// mprPenetrationKernel (src/Bullet3OpenCL/NarrowphaseCollision/kernels/mpr.cl:14-89) as a host loop around the reference's own
+// b3MprPenetration (shared/b3MprPenetration.h:825-888): the kernel body is 30 lines of bookkeeping, restated here because the .cl
+// file cannot be compiled by g++; everything numeric is the header's.  res[i] = what b3MprPenetration returned (-2: skipped).
+int ref_mpr_kernel(b3b200_int4* pairs, int numPairs, const b3b200_rigid_body* bodies, const b3b200_collidable* collidables, const b3b200_convex_polyhedron* convex,
+				   const b3b200_float4* vertices, b3b200_float4* sepNormals, int* hasSepAxis, b3b200_contact4* contactsOut, int contactCapacity, int* numContacts,
+				   b3b200_mpr_result* res)
+{
+	const b3RigidBodyData* rb = (const b3RigidBodyData*)bodies;
+	const b3Collidable* col = (const b3Collidable*)collidables;
+	const b3ConvexPolyhedronData* cv = (const b3ConvexPolyhedronData*)convex;
+	const b3Vector3* vtx = (const b3Vector3*)vertices;
+	b3Vector3* sep = (b3Vector3*)sepNormals;
+	b3Contact4Data* out = (b3Contact4Data*)contactsOut;
+	for (int i = 0; i < numPairs; i++)
+	{
+		const int bodyIndexA = pairs[i].x, bodyIndexB = pairs[i].y;
+		if (res)
+		{
+			res[i].result = -2;
+			res[i].depth = 0.f;
+		}
+		if (rb[bodyIndexA].m_invMass == 0 && rb[bodyIndexB].m_invMass == 0) continue;
+		if (col[rb[bodyIndexA].m_collidableIdx].m_shapeType != SHAPE_CONVEX_HULL || col[rb[bodyIndexB].m_collidableIdx].m_shapeType != SHAPE_CONVEX_HULL) continue;
+		float depthOut = 0.f;
+		b3Float4 dirOut = b3MakeFloat4(0, 0, 0, 0), posOut = b3MakeFloat4(0, 0, 0, 0);
+		int r = b3MprPenetration(i, bodyIndexA, bodyIndexB, rb, cv, col, vtx, sep, hasSepAxis, &depthOut, &dirOut, &posOut);
+		if (res)
+		{
+			res[i].result = r;
+			res[i].depth = depthOut;
+			for (int k = 0; k < 3; k++)
+			{
+				res[i].dir[k] = dirOut[k];
+				res[i].pos[k] = posOut[k];
+			}
+		}
+		if (r == 0)
+		{
+			int dstIdx = (*numContacts)++;
+			if (dstIdx < contactCapacity)
+			{
+				pairs[i].z = dstIdx;
+				b3Contact4Data* c = out + dstIdx;
+				c->m_worldNormalOnB = -dirOut;
+				c->m_restituitionCoeffCmp = (0.f * 0xffff);
+				c->m_frictionCoeffCmp = (0.7f * 0xffff);
+				c->m_batchIdx = i;
+				c->m_bodyAPtrAndSignBit = rb[bodyIndexA].m_invMass == 0 ? -bodyIndexA : bodyIndexA;
+				c->m_bodyBPtrAndSignBit = rb[bodyIndexB].m_invMass == 0 ? -bodyIndexB : bodyIndexB;
+				c->m_childIndexA = -1;
+				c->m_childIndexB = -1;
+				posOut.w = -depthOut;
+				c->m_worldPosB[0] = posOut;
+				c->m_worldNormalOnB.w = 1.f;  // GET_NPOINTS(*c) = 1
+			}
+		}
+	}
 	return 0;
 }
 }
