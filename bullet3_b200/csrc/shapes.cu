@@ -64,6 +64,207 @@ extern "C" int b3b200_register_sphere(b3b200_world* w, float radius)
 	return ci;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The reference's quantized BVH tables (b3QuantizedBvhNodeData 16 B, b3BvhSubtreeInfoData 32 B) for a set of leaf boxes, as
+// b3QuantizedBvh::buildInternal produces them (b3QuantizedBvh.cpp:34-62, 79-88, 99-176, 178-208, 210-261, 263-290; helpers
+// b3QuantizedBvh.h:189-268, 314-341, 389-398): 16-bit boxes inside the padded shape box (margin 1, 65533 steps; minima rounded
+// down to even, maxima rounded up to odd), leaves reordered in place by the mean split along the axis of largest variance of
+// the UNQUANTIZED-again leaf centres (with the reference's fallback to the middle when a side gets < 1/3), nodes in depth-first
+// order with escape indices (-subtree size on internal nodes), 2 * leaves slots (the last one stays zero), and a subtree
+// header for every child subtree of <= 128 nodes whose parent is larger (or one header for a tree that small).
+// This build's own narrowphase walks different structures (float trees, bounding-sphere child culls); the tables exist so that
+// getStatic / serialisation consumers of b3GpuNarrowPhase see what the reference would hand them.
+namespace
+{
+struct QuantizedBvhBuilder
+{
+	float bvhMin[3], bvhMax[3], quant[3];
+	std::vector<b3b200_bvh_node> leaves, nodes;
+	std::vector<b3b200_bvh_subtree> headers;
+	int cur = 0;
+
+	void setQuantizationValues(const float* mn, const float* mx)
+	{
+		for (int k = 0; k < 3; k++)
+		{
+			bvhMin[k] = mn[k] - 1.0f;
+			bvhMax[k] = mx[k] + 1.0f;
+			quant[k] = 65533.0f / (bvhMax[k] - bvhMin[k]);
+		}
+	}
+	void quantize(unsigned short* out, const float* p, int isMax) const
+	{
+		for (int k = 0; k < 3; k++)
+		{
+			const float v = (p[k] - bvhMin[k]) * quant[k];
+			out[k] = isMax ? (unsigned short)(((unsigned short)(int)(v + 1.0f)) | 1) : (unsigned short)(((unsigned short)(int)v) & 0xfffe);
+		}
+	}
+	void unQuantize(const unsigned short* in, float* out) const
+	{
+		for (int k = 0; k < 3; k++) out[k] = (float)in[k] / quant[k] + bvhMin[k];
+	}
+	void addLeaf(const float* mn, const float* mx, int index)
+	{
+		b3b200_bvh_node n;
+		quantize(n.quantizedAabbMin, mn, 0);
+		quantize(n.quantizedAabbMax, mx, 1);
+		n.escapeIndexOrTriangleIndex = index;  // part 0
+		leaves.push_back(n);
+	}
+	void centre(int i, float* c) const
+	{
+		float mn[3], mx[3];
+		unQuantize(leaves[i].quantizedAabbMin, mn);
+		unQuantize(leaves[i].quantizedAabbMax, mx);
+		for (int k = 0; k < 3; k++) c[k] = 0.5f * (mx[k] + mn[k]);
+	}
+	int calcSplittingAxis(int start, int end) const
+	{
+		float means[3] = {0.f, 0.f, 0.f}, variance[3] = {0.f, 0.f, 0.f};
+		const int num = end - start;
+		for (int i = start; i < end; i++)
+		{
+			float c[3];
+			centre(i, c);
+			for (int k = 0; k < 3; k++) means[k] += c[k];
+		}
+		const float inv = 1.0f / (float)num;
+		for (int k = 0; k < 3; k++) means[k] *= inv;
+		for (int i = start; i < end; i++)
+		{
+			float c[3];
+			centre(i, c);
+			for (int k = 0; k < 3; k++)
+			{
+				const float d = c[k] - means[k];
+				variance[k] += d * d;
+			}
+		}
+		const float invv = 1.0f / ((float)num - 1);
+		for (int k = 0; k < 3; k++) variance[k] *= invv;
+		// b3Vector3::maxAxis
+		return variance[0] < variance[1] ? (variance[1] < variance[2] ? 2 : 1) : (variance[0] < variance[2] ? 2 : 0);
+	}
+	int sortAndCalcSplittingIndex(int start, int end, int axis)
+	{
+		int split = start;
+		const int num = end - start;
+		float means[3] = {0.f, 0.f, 0.f};
+		for (int i = start; i < end; i++)
+		{
+			float c[3];
+			centre(i, c);
+			for (int k = 0; k < 3; k++) means[k] += c[k];
+		}
+		const float inv = 1.0f / (float)num;
+		for (int k = 0; k < 3; k++) means[k] *= inv;
+		const float splitValue = means[axis];
+		for (int i = start; i < end; i++)
+		{
+			float c[3];
+			centre(i, c);
+			if (c[axis] > splitValue)
+			{
+				std::swap(leaves[i], leaves[split]);
+				split++;
+			}
+		}
+		const int range = num / 3;
+		if (split <= start + range || split >= end - 1 - range) split = start + (num >> 1);
+		return split;
+	}
+	void header(int nodeIndex)
+	{
+		const b3b200_bvh_node& n = nodes[nodeIndex];
+		b3b200_bvh_subtree h;
+		memset(&h, 0, sizeof(h));
+		for (int k = 0; k < 3; k++)
+		{
+			h.quantizedAabbMin[k] = n.quantizedAabbMin[k];
+			h.quantizedAabbMax[k] = n.quantizedAabbMax[k];
+		}
+		h.rootNodeIndex = nodeIndex;
+		h.subtreeSize = n.escapeIndexOrTriangleIndex >= 0 ? 1 : -n.escapeIndexOrTriangleIndex;
+		headers.push_back(h);
+	}
+	void buildTree(int start, int end)
+	{
+		const int num = end - start, curIndex = cur;
+		if (num == 1)
+		{
+			nodes[cur++] = leaves[start];
+			return;
+		}
+		const int axis = calcSplittingAxis(start, end);
+		const int split = sortAndCalcSplittingIndex(start, end, axis);
+		const int internal = cur;
+		quantize(nodes[internal].quantizedAabbMin, bvhMax, 0);
+		quantize(nodes[internal].quantizedAabbMax, bvhMin, 1);
+		for (int i = start; i < end; i++)
+		{
+			// mergeInternalNodeAabb takes the leaf's UNQUANTIZED box and quantizes it again
+			float mn[3], mx[3];
+			unQuantize(leaves[i].quantizedAabbMin, mn);
+			unQuantize(leaves[i].quantizedAabbMax, mx);
+			unsigned short qmn[3], qmx[3];
+			quantize(qmn, mn, 0);
+			quantize(qmx, mx, 1);
+			for (int k = 0; k < 3; k++)
+			{
+				if (nodes[internal].quantizedAabbMin[k] > qmn[k]) nodes[internal].quantizedAabbMin[k] = qmn[k];
+				if (nodes[internal].quantizedAabbMax[k] < qmx[k]) nodes[internal].quantizedAabbMax[k] = qmx[k];
+			}
+		}
+		cur++;
+		const int left = cur;
+		buildTree(start, split);
+		const int right = cur;
+		buildTree(split, end);
+		const int escape = cur - curIndex;
+		if (escape * (int)sizeof(b3b200_bvh_node) > 2048)  // MAX_SUBTREE_SIZE_IN_BYTES
+		{
+			const int ls = nodes[left].escapeIndexOrTriangleIndex >= 0 ? 1 : -nodes[left].escapeIndexOrTriangleIndex;
+			const int rs = nodes[right].escapeIndexOrTriangleIndex >= 0 ? 1 : -nodes[right].escapeIndexOrTriangleIndex;
+			if (ls * (int)sizeof(b3b200_bvh_node) <= 2048) header(left);
+			if (rs * (int)sizeof(b3b200_bvh_node) <= 2048) header(right);
+		}
+		nodes[internal].escapeIndexOrTriangleIndex = -escape;
+	}
+	void build()
+	{
+		b3b200_bvh_node zero;
+		memset(&zero, 0, sizeof(zero));
+		nodes.assign(2 * leaves.size(), zero);
+		cur = 0;
+		if (!leaves.empty()) buildTree(0, (int)leaves.size());
+		if (headers.empty() && !nodes.empty()) header(0);
+	}
+	// appends the tables to the world's and returns the b3BvhInfo (b3GpuNarrowPhase.cpp:575-603)
+	b3b200_bvh_info append(World* w)
+	{
+		b3b200_bvh_info info;
+		memset(&info, 0, sizeof(info));
+		info.aabbMin.x = bvhMin[0];
+		info.aabbMin.y = bvhMin[1];
+		info.aabbMin.z = bvhMin[2];
+		info.aabbMax.x = bvhMax[0];
+		info.aabbMax.y = bvhMax[1];
+		info.aabbMax.z = bvhMax[2];
+		info.quantization.x = quant[0];
+		info.quantization.y = quant[1];
+		info.quantization.z = quant[2];
+		info.numNodes = (int)nodes.size();
+		info.numSubTrees = (int)headers.size();
+		info.nodeOffset = (int)w->bvhNodes.size();
+		info.subTreeOffset = (int)w->bvhSubtrees.size();
+		w->bvhNodes.insert(w->bvhNodes.end(), nodes.begin(), nodes.end());
+		w->bvhSubtrees.insert(w->bvhSubtrees.end(), headers.begin(), headers.end());
+		return info;
+	}
+};
+}  // namespace
+
 extern "C" int b3b200_register_compound(b3b200_world* w, const b3b200_child_shape* children, int numChildren)
 {
 	if (!w || !children || numChildren <= 0)
@@ -90,10 +291,11 @@ extern "C" int b3b200_register_compound(b3b200_world* w, const b3b200_child_shap
 	b3b200_collidable& col = w->collidables[ci];
 	col.shapeType = B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
 	col.shapeIndex = (int)w->childShapes.size();
-	// The reference builds a quantized BVH over the children here (:432-474).  This build culls child
-	// pairs by their world AABBs directly (see narrowphase.cu), which yields the same contacts.
-	col.compoundBvhIndex = -1;
+	// The reference builds a quantized BVH over the children (:439-490): the tables are produced below for its consumers; this
+	// build's narrowphase culls child pairs by bounding spheres instead (narrowphase.cu), which yields the same contacts.
+	col.compoundBvhIndex = (int)w->bvhInfos.size();
 	float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+	std::vector<float> childBoxes((size_t)numChildren * 6);
 	for (int i = 0; i < numChildren; i++)
 	{
 		b3b200_child_shape ch = children[i];
@@ -108,7 +310,18 @@ extern "C" int b3b200_register_compound(b3b200_world* w, const b3b200_child_shap
 		{
 			if (amn[k] < mn[k]) mn[k] = amn[k];
 			if (amx[k] > mx[k]) mx[k] = amx[k];
+			childBoxes[(size_t)i * 6 + k] = amn[k];
+			childBoxes[(size_t)i * 6 + 3 + k] = amx[k];
 		}
+	}
+	{
+		QuantizedBvhBuilder qb;
+		qb.setQuantizationValues(mn, mx);
+		for (int i = 0; i < numChildren; i++) qb.addLeaf(&childBoxes[(size_t)i * 6], &childBoxes[(size_t)i * 6 + 3], i);
+		qb.build();
+		b3b200_bvh_info info = qb.append(w);
+		info.numNodes = numChildren;  // the reference stores the number of CHILDREN here (:442, :470) while it appends all 2 n node slots
+		w->bvhInfos.push_back(info);
 	}
 	// NB: `col` may dangle after push_backs on other vectors only; collidables was not resized since
 	w->collidables[ci].numChildShapes = numChildren;
@@ -285,21 +498,35 @@ extern "C" int b3b200_register_concave(b3b200_world* w, const float* vertices, i
 	}
 	a.minIndices[3] = 0;
 	a.signedMaxIndices[3] = 0;
-	// b3BvhInfo header as the reference computes it (b3QuantizedBvh::setQuantizationValues, margin 1); the quantized
-	// node / subtree tables themselves are not produced (numNodes = numSubTrees = 0)
-	b3b200_bvh_info info;
-	memset(&info, 0, sizeof(info));
-	const float lo[3] = {mn[0] - 1.f, mn[1] - 1.f, mn[2] - 1.f}, hi[3] = {mx[0] + 1.f, mx[1] + 1.f, mx[2] + 1.f};
-	info.aabbMin.x = lo[0];
-	info.aabbMin.y = lo[1];
-	info.aabbMin.z = lo[2];
-	info.aabbMax.x = hi[0];
-	info.aabbMax.y = hi[1];
-	info.aabbMax.z = hi[2];
-	info.quantization.x = 65533.f / (hi[0] - lo[0]);
-	info.quantization.y = 65533.f / (hi[1] - lo[1]);
-	info.quantization.z = 65533.f / (hi[2] - lo[2]);
-	w->bvhInfos.push_back(info);
+	// the reference's b3OptimizedBvh tables (b3OptimizedBvh.cpp:27-190): quantization box = the SCALED mesh box padded by 1, leaves =
+	// the boxes of the UNSCALED triangles (b3GpuNarrowPhase.cpp:562-573 hands the tree the caller's vertices), each widened to at
+	// least 0.002 per axis, leaf index = triangle index
+	{
+		QuantizedBvhBuilder qb;
+		qb.setQuantizationValues(mn, mx);
+		for (int f = 0; f < numTris; f++)
+		{
+			float tmn[3] = {1e18f, 1e18f, 1e18f}, tmx[3] = {-1e18f, -1e18f, -1e18f};  // B3_LARGE_FLOAT
+			for (int c = 0; c < 3; c++)
+			{
+				const float* v = &vertices[3 * triIndices[3 * f + c]];
+				for (int k = 0; k < 3; k++)
+				{
+					tmn[k] = std::min(tmn[k], v[k]);
+					tmx[k] = std::max(tmx[k], v[k]);
+				}
+			}
+			for (int k = 0; k < 3; k++)
+				if (tmx[k] - tmn[k] < 0.002f)
+				{
+					tmx[k] = tmx[k] + 0.001f;
+					tmn[k] = tmn[k] - 0.001f;
+				}
+			qb.addLeaf(tmn, tmx, f);
+		}
+		qb.build();
+		w->bvhInfos.push_back(qb.append(w));
+	}
 	b3b200_int4 mi;
 	mi.x = (int)(w->meshNodes.size() / 2);
 	mi.z = (int)w->meshTris.size();

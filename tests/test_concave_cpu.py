@@ -90,12 +90,44 @@ def test_mesh_tables_match_reference(seed):
     assert cr["shapeType"] == cm["shapeType"] == capi.SHAPE_CONCAVE_TRIMESH and cr["shapeIndex"] == cm["shapeIndex"]
     ar, am = r.table(1, capi.aabb_t)[0], sh.local_aabbs[0]
     assert np.array_equal(ar["min"][:3].view(np.uint32), am["min"][:3].view(np.uint32)) and np.array_equal(ar["max"][:3].view(np.uint32), am["max"][:3].view(np.uint32))
-    # the b3BvhInfo header (quantization box) is reproduced even though the quantized nodes are not
-    ir = r.table(8, capi.bvh_info_t)[0]
-    im = w.table("bvh_infos")[0] if hasattr(w, "table") else None
-    if im is not None:
-        for f in ("aabbMin", "aabbMax", "quantization"):
-            assert np.allclose(np.asarray(ir[f])[:3], np.asarray(im[f])[:3], rtol=1e-6), f
+    # the quantized BVH tables of every shape registered so far (the trimesh's b3OptimizedBvh, the compounds' b3QuantizedBvh):
+    # headers, 16-byte nodes and subtree headers equal the reference's byte for byte
+    assert_bvh_tables_equal(w, r)
+
+
+def assert_bvh_tables_equal(w, r):
+    ir, im = r.table(8, capi.bvh_info_t), w.table("bvh_infos")
+    assert len(ir) == len(im) >= 1
+    for f in ("aabbMin", "aabbMax", "quantization"):
+        assert np.array_equal(np.asarray(ir[f])[:, :3].view(np.uint32), np.asarray(im[f])[:, :3].view(np.uint32)), f
+    for f in ("numNodes", "numSubTrees", "nodeOffset", "subTreeOffset"):
+        assert np.array_equal(ir[f], im[f]), f
+    nr, nm = r.table(9, capi.bvh_node_t), w.table("bvh_nodes")
+    assert len(nr) == len(nm) >= int(ir["numNodes"].sum())  # (a compound's header counts its children, its table has 2 n slots)
+    for f in ("qmin", "qmax", "escapeIndexOrTriangleIndex"):
+        assert np.array_equal(nr[f], nm[f]), f
+    sr, sm = r.table(10, capi.bvh_subtree_t), w.table("bvh_subtrees")
+    assert len(sr) == len(sm) == int(ir["numSubTrees"].sum())
+    for f in ("qmin", "qmax", "rootNodeIndex", "subtreeSize"):
+        assert np.array_equal(sr[f], sm[f]), f
+
+
+@pytest.mark.parametrize("nx,nz,amp", [(1, 1, 0.0), (3, 2, 0.5), (40, 40, 2.0), (64, 33, 1.0)])
+def test_quantized_bvh_tables_of_trimeshes_equal_the_reference(nx, nz, amp):
+    """b3OptimizedBvh::build through registerConcaveMesh (b3GpuNarrowPhase.cpp:521-605) for meshes from 2 triangles (one leaf
+    pair, one subtree header) to 5 120 triangles (many subtree headers), and two meshes in one world (offsets)"""
+    cfg = capi.default_config(64)
+    w = capi.World(cfg, device=-1)
+    r = oa.RefNarrowphase(cfg)
+    verts, tris = scenes.heightfield_mesh(nx, nz, cell=0.7, amplitude=amp, freq=0.9)
+    assert w.register_concave(verts, tris) == r.register_concave(verts, tris)
+    verts2, tris2 = scenes.heightfield_mesh(5, 7, cell=1.3, amplitude=0.3, freq=0.4)
+    assert w.register_concave(verts2, tris2) == r.register_concave(verts2, tris2)
+    assert_bvh_tables_equal(w, r)
+    n = w.table("bvh_infos")
+    assert n["numNodes"][0] == 2 * (len(tris) // 3)
+    if len(tris) // 3 > 200:
+        assert n["numSubTrees"][0] > 4
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
@@ -121,3 +153,32 @@ def test_concave_contacts_bit_exact_vs_host_twins(seed):
         assert np.array_equal(a["worldPosB"][m, k].view(np.uint32), b["worldPosB"][m, k].view(np.uint32)), k
     assert np.array_equal(a["frictionCmp"], b["frictionCmp"])
     assert np.all(a["childA"] == -1) and np.all(a["childB"] == -1) and np.all(b["childB"] == -1)
+
+
+@pytest.mark.parametrize("counts", [(1,), (2, 3), (7, 90, 5), (200,)])
+def test_quantized_bvh_tables_of_compounds_equal_the_reference(counts):
+    """b3QuantizedBvh::buildInternal through registerCompoundShape (b3GpuNarrowPhase.cpp:370-515): compounds from one child (a
+    single leaf) to 200 children (400 node slots: subtree headers), several per world"""
+    cfg = capi.default_config(64)
+    cfg["maxCompoundChildShapes"] = 4096
+    w = capi.World(cfg, device=-1)
+    r = oa.RefNarrowphase(cfg)
+    rc = r.register_convex_points(scenes.box_points(0.4))
+    cv = r.table(2, capi.convex_t)[-1]
+    vv = r.table(3, np.dtype(("f4", 4)))[cv["vertexOffset"]: cv["vertexOffset"] + cv["numVertices"]]
+    faces = r.table(5, capi.face_t)[cv["faceOffset"]: cv["faceOffset"] + cv["numFaces"]].copy()
+    idx = r.table(6, np.dtype("i4"))
+    edges = r.table(4, np.dtype(("f4", 4)))[cv["uniqueEdgesOffset"]: cv["uniqueEdgesOffset"] + cv["numUniqueEdges"]]
+    poly = np.zeros(1, capi.convex_t)
+    poly[0] = cv
+    wc = w.register_convex(vv, faces, idx[: int((faces["indexOffset"] + faces["numIndices"]).max())], edges, poly)
+    rng = np.random.default_rng(len(counts))
+    for k in counts:
+        offs = rng.uniform(-6, 6, (k, 3))
+        orns = [scenes.random_quat(rng) for _ in range(k)]
+        a = w.register_compound(scenes.compound_children(wc, offs, orns))
+        b = r.register_compound(scenes.compound_children(rc, offs, orns))
+        assert a == b
+    assert_bvh_tables_equal(w, r)
+    if max(counts) >= 90:
+        assert w.table("bvh_infos")["numSubTrees"].max() >= 2
