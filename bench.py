@@ -282,10 +282,11 @@ def run_cpu_pipeline_config1(steps=600):
 
 
 def ncu_traffic(kernel):
-    """dram bytes read + written per launch of `kernel` from the committed ncu --set full summary of the CURRENT build
-    (profiles/r02_solver_ncu_summary.txt, written by tools/ncu_summary.py from the .ncu-rep); None when the file has no such line"""
+    """dram bytes read + written per step by `kernel` (one launch; solverIterateKernel: its two phase launches together) from the
+    committed ncu --set full summary of the CURRENT build (profiles/r02s2_ncu_summary.txt, written by tools/ncu_summary.py from
+    gpurun_out/r02s2_full.ncu-rep); None when the file has no such line"""
     try:
-        for line in open(os.path.join(ROOT, "profiles", "r02_solver_ncu_summary.txt")):
+        for line in open(os.path.join(ROOT, "profiles", "r02s2_ncu_summary.txt")):
             p = line.split()
             if len(p) >= 3 and p[0] == "traffic" and p[1] == kernel:
                 return float(p[2])
@@ -527,10 +528,10 @@ def main():
         # single-kernel stage).  Algorithmic bytes per launch: SAT = 112 B per work item (16 B item +
         # two 32-B pose records + 32 B appended item and axis); iterations = 2*I*192*C + 96*N.
         # `traffic` = dram bytes read + written per launch of that kernel, parsed from the committed ncu --set full summary
-        # of this build (profiles/r02_solver_ncu_summary.txt); null when the summary has no line for the kernel.
+        # of this build (profiles/r02s2_ncu_summary.txt); null when the summary has no line for the kernel.
         sat_items = int(ctr[7])
         kern = {"satKernel": {"ms": float(stage[7]), "alg_bytes": 112.0 * sat_items,
-                              "note": "FP32-issue bound, not HBM bound (ncu: sm__throughput 78 % of peak issue rate, L1 hit 94 %)"},
+                              "note": "FP32-issue bound, not HBM bound (ncu: sm__throughput 72 % of peak issue rate, L1 hit 97 %, 36 MB of DRAM traffic)"},
                 "solverIterateKernel": {"ms": float(stage[4]), "alg_bytes": stage_bytes["solver_iterate"],
                                         "note": "latency bound: per pass %d grid barriers (batches of contacts between blocks) + the per-block batch loop in shared memory" % int(ctr[3])}}
         domk = max(kern, key=lambda k: kern[k]["ms"])

@@ -31,7 +31,10 @@ for rep in reps:
     for r in rows[2:]:
         name = r[col["Kernel Name"]].split("(")[0]
         rd, wr = val(r, "dram__bytes_read.sum", "bytes"), val(r, "dram__bytes_write.sum", "bytes")
-        traffic[name] = rd + wr
+        # machine-readable name: no "void ", no template arguments, no anonymous-namespace prefix; template instances of one
+        # kernel (the two phases of solverIterateKernel) add up: bytes per STEP of that kernel
+        key = name.replace("void ", "").split("<")[0].split("::")[-1].strip()
+        traffic[key] = traffic.get(key, 0.0) + rd + wr
         stalls = sorted(((val(r, n), n.split("issue_stalled_")[1].split("_per")[0]) for n in hdr
                          if n.startswith("smsp__average_warps_issue_stalled_") and n.endswith("_per_issue_active.ratio")), reverse=True)[:4]
         lines.append("%-28s %9.1f us  dram rd %8.1f MB wr %8.1f MB  L2 hit %5.1f%%  L1 hit %5.1f%%  sm throughput %5.1f%%  regs %3d  lanes/inst %4.1f  stalls: %s" % (
