@@ -14,14 +14,15 @@
 #include <float.h>
 #include <stdio.h>
 #include <string>
+#include <atomic>
 #include "../../include/b3b200.h"
 
 namespace b3b200
 {
 // ---------------------------------------------------------------- errors
 void setLastError(const char* fmt, ...);
-extern long long g_launchCount;
-extern long long g_allocEpoch;  // bumped by every device (re)allocation: a captured step graph that saw one is discarded
+extern std::atomic<long long> g_launchCount;  // process-wide statistic (worlds may be stepped from several threads)
+extern thread_local long long g_allocEpoch;   // bumped by every device (re)allocation of THIS thread: a step graph whose capture saw one is discarded
 
 #define B3_CUDA_CHECK(expr)                                                                 \
 	do                                                                                      \

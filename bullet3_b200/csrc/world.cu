@@ -9,8 +9,8 @@
 namespace b3b200
 {
 static thread_local char g_lastError[512] = "";
-long long g_launchCount = 0;
-long long g_allocEpoch = 0;
+std::atomic<long long> g_launchCount{0};
+thread_local long long g_allocEpoch = 0;
 
 void setLastError(const char* fmt, ...)
 {
@@ -412,7 +412,7 @@ using namespace b3b200;
 
 extern "C" const char* b3b200_last_error(void) { return g_lastError; }
 extern "C" int b3b200_version(void) { return 100; }
-extern "C" long long b3b200_launch_count(void) { return g_launchCount; }
+extern "C" long long b3b200_launch_count(void) { return g_launchCount.load(); }
 
 extern "C" int b3b200_config_default(b3b200_config* c)
 {

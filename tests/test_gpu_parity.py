@@ -1514,3 +1514,48 @@ def test_pipelined_host_stepping_matches_blocking_write_step_readback():
     assert np.array_equal(b.bodies()["linVel"].view(np.uint32), a.bodies()["linVel"].view(np.uint32))
     a.close()
     b.close()
+
+
+def test_two_worlds_stepped_from_two_threads():
+    """SURVEY 8(b) threading: worlds are independent objects; two of them stepped concurrently from two host threads (ctypes drops
+    the GIL; each world has its own stream, graphs and error slot) end bit-identical to a world stepped alone"""
+    import threading
+
+    def build():
+        w = capi.World(capi.default_config(4096))
+        scenes.add_ground_box(w, 80.0)
+        col = w.register_convex_points(scenes.box_points(0.5))
+        rng = np.random.default_rng(21)
+        for i in range(16):
+            for k in range(16):
+                w.register_instance(1.0, (i * 3.0 - 24, 0.6 + 0.2 * rng.uniform(), k * 3.0 - 24), scenes.random_quat(rng), col)
+        w.upload()
+        w.set_solver(capi.SOLVER_PGS, 5)
+        return w
+
+    alone = build()
+    alone.step_n(1 / 60, 80)
+    want = alone.bodies()
+    ws = [build(), build()]
+    errs = []
+
+    def run(w):
+        try:
+            for _ in range(40):
+                w.step_n(1 / 60, 2)
+            w.synchronize()
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=run, args=(w,)) for w in ws]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs
+    for w in ws:
+        b = w.bodies()
+        for f in ("pos", "quat", "linVel", "angVel"):
+            assert np.array_equal(b[f].view(np.uint32), want[f].view(np.uint32)), f
+        w.close()
+    alone.close()
