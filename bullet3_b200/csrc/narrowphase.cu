@@ -1147,18 +1147,36 @@ __global__ void __launch_bounds__(CULL_THREADS) npChildCullKernel(NpArgs a, cons
 	}
 }
 
+// Per-warp queues keep the three kinds of work apart, so that each runs with (nearly) full lanes instead of idling the lanes
+// that hold another kind of pair: convex pairs of two small hulls (6 faces / 8 vertices: short loops), convex pairs with a larger
+// hull (up to 60 faces / 32 vertices), and pairs with a compound, whose child pairs are enumerated one per LANE
+// (ncu before: the child loops ran at 4-6 of 32 lanes, the quick reject's face search at 6).
+constexpr int CULL_WARPS = CULL_THREADS / 32;
+constexpr int CQ_TAKE = 16;  // compound pairs expanded together
+
+struct CullCompound
+{
+	int pair, firstA, nA, firstB, nB;  // first child shape (-1: a lone hull), number of children
+};
+
 __global__ void __launch_bounds__(CULL_THREADS, 4) npCullKernel(NpArgs a, int4* __restrict__ items, int4* __restrict__ rawItems, int* __restrict__ meshPairs,
 															 int maxMeshPairs, int4* __restrict__ smallItems)
 {
 	const int numPairs = (int)a.ctr[CTR_PAIRS];
-	const int lane = threadIdx.x & 31;
-	__shared__ int quickQueueAll[CULL_THREADS / 32][64];
-	int* quickQueue = quickQueueAll[threadIdx.x >> 5];
-	int qn = 0;  // warp-uniform
-	for (int base = blockIdx.x * CULL_THREADS; base < numPairs || qn > 0; base += gridDim.x * CULL_THREADS)
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__shared__ int queueAll[CULL_WARPS][3][64];          // 0: small convex pairs, 1: convex pairs with a larger hull, 2: pairs with a compound
+	__shared__ CullCompound compAll[CULL_WARPS][CQ_TAKE];
+	__shared__ float4 frameAll[CULL_WARPS][CQ_TAKE][2][5];  // per queued compound pair and side: rotation rows, position, lone sphere
+	__shared__ int offAll[CULL_WARPS][CQ_TAKE + 1];
+	int(*queue)[64] = queueAll[warp];
+	CullCompound* comp = compAll[warp];
+	int* off = offAll[warp];
+	int qn0 = 0, qn1 = 0, qn2 = 0;  // warp-uniform
+	const unsigned int lt = (1u << lane) - 1u;
+	for (int base = blockIdx.x * CULL_THREADS; base < numPairs || (qn0 | qn1 | qn2) > 0; base += gridDim.x * CULL_THREADS)
 	{
 		const int p = base + threadIdx.x;
-		bool wantQuick = false;
+		int kind = -1;
 		if (base < numPairs && p < numPairs)
 		{
 			const int bodyA = a.pairs[p].x, bodyB = a.pairs[p].y;
@@ -1172,59 +1190,26 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) npCullKernel(NpArgs a, int4* 
 					if (resolveSide(a, bodyA, -1, A) && resolveSide(a, bodyB, -1, B))
 					{
 						// bounding spheres first (conservative, like the child pairs below); the exact quick reject runs below on
-						// the warp's queue of such pairs, 32 at a time, so that its lanes are not idled by the other pair types
+						// the warp's queues of such pairs, 32 at a time
 						float rA, rB;
 						const float4 sA = boundSphere(a, A, rA), sB = boundSphere(a, B, rB);
 						const float4 d = sub3(sA, sB);
 						const float rr = (rA + rB) * 1.001f + 1e-3f;
-						wantQuick = dot3(d, d) <= rr * rr;
+						if (dot3(d, d) <= rr * rr)
+						{
+							const b3b200_convex_polyhedron *hA = &a.convex[A.shape], *hB = &a.convex[B.shape];
+							kind = __ldg(&hA->numVertices) <= SMALL_VERTS && __ldg(&hA->numFaces) <= SMALL_FACES && __ldg(&hB->numVertices) <= SMALL_VERTS &&
+										   __ldg(&hB->numFaces) <= SMALL_FACES
+									   ? 0
+									   : 1;
+						}
 					}
 				}
 				else if ((typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeA == B3B200_SHAPE_CONVEX_HULL) &&
 						 (typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeB == B3B200_SHAPE_CONVEX_HULL))
 				{
-					// at least one compound: expand to child pairs (two static bodies never collide, sat.cl:975-978)
-					if (!(a.pose[2 * bodyA].w == 0.f && a.pose[2 * bodyB].w == 0.f))
-					{
-						const bool compA = typeA == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS, compB = typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
-						const int firstA = compA ? __ldg(&a.collidables[cA].shapeIndex) : -1, nA = compA ? __ldg(&a.collidables[cA].numChildShapes) : 1;
-						const int firstB = compB ? __ldg(&a.collidables[cB].shapeIndex) : -1, nB = compB ? __ldg(&a.collidables[cB].numChildShapes) : 1;
-						// child pairs whose bounding spheres touch go to the raw child-item queue; npChildCullKernel runs the exact
-						// quick reject on them, one thread each.  The spheres come from a per-child table in the compound's
-						// frame (world.cu), so a child costs one matrix-vector product here instead of a composed transform.
-						const float4 posA = a.pose[2 * bodyA], posB = a.pose[2 * bodyB];
-						const Mat3 mA = matFromQuat(a.pose[2 * bodyA + 1]), mB = matFromQuat(a.pose[2 * bodyB + 1]);
-						float4 loneA = mk4(0, 0, 0, -1.f), loneB = mk4(0, 0, 0, -1.f);
-						if (!compA)
-						{
-							const b3b200_convex_polyhedron* h = &a.convex[__ldg(&a.collidables[cA].shapeIndex)];
-							loneA = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
-							loneA.w = __int_as_float(__ldg(&h->unused));
-						}
-						if (!compB)
-						{
-							const b3b200_convex_polyhedron* h = &a.convex[__ldg(&a.collidables[cB].shapeIndex)];
-							loneB = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
-							loneB.w = __int_as_float(__ldg(&h->unused));
-						}
-						for (int i = 0; i < nA; i++)
-						{
-							const float4 lA = compA ? __ldg(&a.childSpheres[firstA + i]) : loneA;
-							if (lA.w < 0.f) continue;
-							const float4 sA = add3(matMulVec(mA, lA), posA);
-							for (int j = 0; j < nB; j++)
-							{
-								const float4 lB = compB ? __ldg(&a.childSpheres[firstB + j]) : loneB;
-								if (lB.w < 0.f) continue;
-								const float4 sB = add3(matMulVec(mB, lB), posB);
-								const float4 d = sub3(sA, sB);
-								const float rr = (lA.w + lB.w) * 1.001f + 2e-3f;
-								if (dot3(d, d) > rr * rr) continue;
-								const unsigned int slot = atomicAdd(&a.ctr[CTR_COMPOUND_PAIRS], 1u);
-								if (slot < (unsigned int)a.maxWorkItems) rawItems[slot] = make_int4(p, compA ? firstA + i : -1, compB ? firstB + j : -1, 0);
-							}
-						}
-					}
+					// at least one compound: its child pairs are expanded below (two static bodies never collide, sat.cl:975-978)
+					if (!(a.pose[2 * bodyA].w == 0.f && a.pose[2 * bodyB].w == 0.f)) kind = 2;
 				}
 				else if (meshPairs && typeA == B3B200_SHAPE_CONCAVE_TRIMESH &&
 						 (typeB == B3B200_SHAPE_CONVEX_HULL || typeB == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS || typeB == B3B200_SHAPE_SPHERE))
@@ -1237,32 +1222,143 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) npCullKernel(NpArgs a, int4* 
 			}
 		}
 		{
-			const unsigned int m = __ballot_sync(FULL, wantQuick);
-			if (wantQuick) quickQueue[qn + __popc(m & ((1u << lane) - 1u))] = p;
-			qn += __popc(m);
+			const unsigned int m0 = __ballot_sync(FULL, kind == 0), m1 = __ballot_sync(FULL, kind == 1), m2 = __ballot_sync(FULL, kind == 2);
+			if (kind == 0) queue[0][qn0 + __popc(m0 & lt)] = p;
+			if (kind == 1) queue[1][qn1 + __popc(m1 & lt)] = p;
+			if (kind == 2) queue[2][qn2 + __popc(m2 & lt)] = p;
+			qn0 += __popc(m0);
+			qn1 += __popc(m1);
+			qn2 += __popc(m2);
 			__syncwarp();
 		}
-		// run the exact quick reject on a full warp's worth of queued convex pairs (or on what is left at the end)
 		const bool last = base + (int)(gridDim.x * CULL_THREADS) >= numPairs;
-		while (qn >= 32 || (last && qn > 0))
+		// ---- the exact quick reject on a full warp's worth of queued convex pairs of one kind (or on what is left at the end)
+#pragma unroll 1
+		for (int k = 0; k < 2; k++)
 		{
-			const int take = qn < 32 ? qn : 32;
-			bool keep = false;
-			int small = 0;
-			int q = -1;
+			int qn = k ? qn1 : qn0;
+			while (qn >= 32 || (last && qn > 0))
+			{
+				const int take = qn < 32 ? qn : 32;
+				bool keep = false;
+				int small = 0;
+				int q = -1;
+				if (lane < take)
+				{
+					q = queue[k][qn - take + lane];
+					Side A, B;
+					if (resolveSide(a, a.pairs[q].x, -1, A) && resolveSide(a, a.pairs[q].y, -1, B))
+					{
+						keep = quickTest(a, A, B);
+						small = keep ? smallClass(a, A.shape, B.shape) : 0;
+					}
+				}
+				qn -= take;
+				__syncwarp();
+				pushClassified(a, keep, small, make_int4(q, -1, -1, 0), items, smallItems, lane);
+			}
+			if (k)
+				qn1 = qn;
+			else
+				qn0 = qn;
+		}
+		// ---- child pairs of the queued compound pairs, one per lane.  Child pairs whose bounding spheres touch go to the raw
+		// child-item queue; npChildCullKernel runs the exact quick reject on them.  The spheres come from a per-child table in the
+		// compound's frame (world.cu), so a child costs one matrix-vector product here instead of a composed transform.
+		while (qn2 >= CQ_TAKE || (last && qn2 > 0))
+		{
+			const int take = qn2 < CQ_TAKE ? qn2 : CQ_TAKE;
+			int cnt = 0;
 			if (lane < take)
 			{
-				q = quickQueue[qn - take + lane];
-				Side A, B;
-				if (resolveSide(a, a.pairs[q].x, -1, A) && resolveSide(a, a.pairs[q].y, -1, B))
+				const int q = queue[2][qn2 - take + lane];
+				const int bodyA = a.pairs[q].x, bodyB = a.pairs[q].y;
+				const int cA = a.coll[bodyA], cB = a.coll[bodyB];
+				const bool compA = __ldg(&a.collidables[cA].shapeType) == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS,
+						   compB = __ldg(&a.collidables[cB].shapeType) == B3B200_SHAPE_COMPOUND_OF_CONVEX_HULLS;
+				CullCompound c;
+				c.pair = q;
+				c.firstA = compA ? __ldg(&a.collidables[cA].shapeIndex) : -1;
+				c.nA = compA ? __ldg(&a.collidables[cA].numChildShapes) : 1;
+				c.firstB = compB ? __ldg(&a.collidables[cB].shapeIndex) : -1;
+				c.nB = compB ? __ldg(&a.collidables[cB].numChildShapes) : 1;
+				comp[lane] = c;
+				cnt = c.nA * c.nB;
+#pragma unroll
+				for (int side = 0; side < 2; side++)
 				{
-					keep = quickTest(a, A, B);
-					small = keep ? smallClass(a, A.shape, B.shape) : 0;
+					const int body = side ? bodyB : bodyA, cc = side ? cB : cA;
+					const Mat3 m = matFromQuat(a.pose[2 * body + 1]);
+					float4* f = frameAll[warp][lane][side];
+					f[0] = m.r0;
+					f[1] = m.r1;
+					f[2] = m.r2;
+					f[3] = a.pose[2 * body];
+					float4 lone = mk4(0, 0, 0, -1.f);
+					if (!(side ? compB : compA))
+					{
+						const b3b200_convex_polyhedron* h = &a.convex[__ldg(&a.collidables[cc].shapeIndex)];
+						lone = __ldg(reinterpret_cast<const float4*>(&h->localCenter));
+						lone.w = __int_as_float(__ldg(&h->unused));
+					}
+					f[4] = lone;
 				}
 			}
-			qn -= take;
+			// exclusive scan of the child-pair counts
+			int incl = cnt;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const int t = __shfl_up_sync(FULL, incl, o);
+				if (lane >= o) incl += t;
+			}
+			if (lane < take) off[lane] = incl - cnt;
+			const int total = __shfl_sync(FULL, incl, take - 1);
+			if (lane == 0) off[take] = total;
+			qn2 -= take;
 			__syncwarp();
-			pushClassified(a, keep, small, make_int4(q, -1, -1, 0), items, smallItems, lane);
+			for (int cb = 0; cb < total; cb += 32)
+			{
+				const int c = cb + lane;
+				bool hit = false;
+				int4 it = make_int4(0, 0, 0, 0);
+				if (c < total)
+				{
+					int sl = 0;
+					while (off[sl + 1] <= c) sl++;  // (<= CQ_TAKE entries)
+					const CullCompound cc = comp[sl];
+					const int r = c - off[sl];
+					const int i = r / cc.nB, j = r - i * cc.nB;
+					const float4* fA = frameAll[warp][sl][0];
+					const float4* fB = frameAll[warp][sl][1];
+					const float4 lA = cc.firstA >= 0 ? __ldg(&a.childSpheres[cc.firstA + i]) : fA[4];
+					const float4 lB = cc.firstB >= 0 ? __ldg(&a.childSpheres[cc.firstB + j]) : fB[4];
+					if (lA.w >= 0.f && lB.w >= 0.f)
+					{
+						Mat3 mA, mB;
+						mA.r0 = fA[0];
+						mA.r1 = fA[1];
+						mA.r2 = fA[2];
+						mB.r0 = fB[0];
+						mB.r1 = fB[1];
+						mB.r2 = fB[2];
+						const float4 sA = add3(matMulVec(mA, lA), fA[3]), sB = add3(matMulVec(mB, lB), fB[3]);
+						const float4 d = sub3(sA, sB);
+						const float rr = (lA.w + lB.w) * 1.001f + 2e-3f;
+						hit = dot3(d, d) <= rr * rr;
+						it = make_int4(cc.pair, cc.firstA >= 0 ? cc.firstA + i : -1, cc.firstB >= 0 ? cc.firstB + j : -1, 0);
+					}
+				}
+				const unsigned int m = __ballot_sync(FULL, hit);
+				if (m)
+				{
+					unsigned int slot = 0;
+					if (lane == 0) slot = atomicAdd(&a.ctr[CTR_COMPOUND_PAIRS], (unsigned int)__popc(m));
+					slot = __shfl_sync(FULL, slot, 0) + __popc(m & lt);
+					if (hit && slot < (unsigned int)a.maxWorkItems) rawItems[slot] = it;
+				}
+			}
+			__syncwarp();
 		}
 	}
 }
