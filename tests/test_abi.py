@@ -134,3 +134,37 @@ def test_settings_and_state_errors_without_a_device(tmp_path):
     assert L.b3b200_set_colouring(None, 0) != 0 and L.b3b200_cast_rays(None, None, 0, None) != 0
     assert L.b3b200_checkpoint_save(None, b"x") != 0 and L.b3b200_register_concave_obj(None, b"x", None, None) == -1
     w.close()
+
+
+def test_round2_entry_points_without_a_device():
+    """argument / state checking of the entry points added in round 2, on a host-only world (no GPU work happens)"""
+    from bullet3_b200 import scenes
+
+    L = capi.lib()
+    w = capi.World(capi.default_config(64), device=-1)
+    col = w.register_convex_points(scenes.box_points(0.5))
+    # batched worlds: ids are recorded at registration
+    assert w.num_worlds() == 1
+    w.register_instance(1.0, (0, 1, 0), scenes.IDENT, col)
+    w.set_current_world(3)
+    w.register_instance(1.0, (0, 1, 0), scenes.IDENT, col)
+    w.register_instance(0.0, (0, -1, 0), scenes.IDENT, col)
+    assert w.num_worlds() == 4 and w.body_worlds().tolist() == [0, 3, 3]
+    assert L.b3b200_set_current_world(w.h, -1) != 0 and L.b3b200_set_current_world(None, 0) != 0 and L.b3b200_num_worlds(None) < 0
+    # step graphs are a setting; stepping itself needs a device
+    assert L.b3b200_set_step_graphs(w.h, 0) == 0 and L.b3b200_set_step_graphs(w.h, 1) == 0 and L.b3b200_set_step_graphs(None, 1) != 0
+    buf = np.zeros(3, capi.rigid_body_t)
+    assert L.b3b200_step_host_async(w.h, C.c_float(1 / 60), capi.ptr(buf), capi.ptr(buf), 3) != 0  # host-only world
+    assert L.b3b200_step_host_async(None, C.c_float(1 / 60), capi.ptr(buf), capi.ptr(buf), 3) != 0
+    assert L.b3b200_step_host_wait(w.h) != 0
+    # the MPR stage checks its arguments before touching a device
+    n = C.c_int(0)
+    assert L.b3b200_mpr_penetration(0, None, 5, None, 0, None, 0, None, 0, None, 0, None, None, None, 0, C.byref(n), None) != 0
+    assert L.b3b200_mpr_penetration(0, None, -1, None, 0, None, 0, None, 0, None, 0, None, None, None, 0, C.byref(n), None) != 0
+    assert L.b3b200_mpr_penetration(0, None, 0, None, 0, None, 0, None, 0, None, 0, None, None, None, 0, None, None) != 0
+    # quantized BVH tables are host tables: available without a device
+    ch = scenes.compound_children(col, [(0, 0, 0), (1, 0, 0), (0, 1, 0)])
+    w.register_compound(ch)
+    info = w.table("bvh_infos")
+    assert len(info) == 1 and info["numNodes"][0] == 3 and info["numSubTrees"][0] == 1 and len(w.table("bvh_nodes")) == 6
+    w.close()
