@@ -924,7 +924,7 @@ B3_D void concaveSmallThread(const CcArgs& a, const int4 it)
 	reinterpret_cast<int4*>(c)[6] = make_int4(-1, -1, 0, 0);  // child indices are not recorded on this path (:143-144)
 }
 
-__global__ void __launch_bounds__(128, 6) concaveSmallKernel(CcArgs a, const int4* __restrict__ items)
+__global__ void __launch_bounds__(128, 5) concaveSmallKernel(CcArgs a, const int4* __restrict__ items)
 {
 	int numItems = (int)a.ctr[CTR_CONCAVE_SURVIVORS];
 	if (numItems > a.maxItems) numItems = a.maxItems;

@@ -1366,7 +1366,7 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) npCullKernel(NpArgs a, int4* 
 // ---------------------------------------------------------------- stage 2: SAT, one warp per work item
 // Small, hot kernel (fits the instruction cache, ~85 registers): finds the minimum-penetration axis
 // and appends (item, axis) to the overlap list.
-__global__ void __launch_bounds__(NP_THREADS, 6) satKernel(NpArgs a, const int4* __restrict__ items, int4* __restrict__ overlapItems,
+__global__ void __launch_bounds__(NP_THREADS, 5) satKernel(NpArgs a, const int4* __restrict__ items, int4* __restrict__ overlapItems,
 															   float4* __restrict__ overlapSep)
 {
 	__shared__ float4 bufAll[NP_WARPS][2][SAT_EDGES];
