@@ -329,7 +329,13 @@ static int stepGraphed(World* w, float dt)
 	if (g.state == 1)
 	{
 		const long long epoch = g_allocEpoch, launches0 = g_launchCount;
-		B3_CUDA_CHECK(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeRelaxed));
+		if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+		{
+			// e.g. a caller-owned stream that is being captured by the caller already: step kernel by kernel from now on
+			cudaGetLastError();
+			w->useGraphs = 0;
+			return stepOnce(w, dt);
+		}
 		const int rc = stepOnce(w, dt);  // also advances the host-side state exactly like an eager step
 		cudaGraph_t graph = nullptr;
 		const cudaError_t e = cudaStreamEndCapture(w->stream, &graph);
