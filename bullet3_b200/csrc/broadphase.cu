@@ -386,56 +386,99 @@ __global__ void __launch_bounds__(256) sapKeyKernel(const b3b200_aabb* __restric
 	vals[i] = (unsigned int)idx;
 }
 
+// Warp-cooperative sweep with a shared-memory window (the role of the LDS window of computePairsKernelLocalSharedMemory,
+// sap.cl:231-300): a warp owns 32 consecutive bodies of the sorted order; the candidates behind them are loaded ONCE per warp,
+// 32 at a time and coalesced, into shared memory, and every lane tests the 32 staged candidates against its own body.  A lane
+// stops for good at the first candidate whose minimum lies beyond its maximum on the sweep axis (the reference's break test);
+// the warp stops when all its lanes have.  Hits are kept as one bit per (lane, candidate); after each window the warp
+// reserves room for all of them with one atomic and the lanes write their pairs.  Same pair set as one thread per body.
 __global__ void __launch_bounds__(BP_THREADS) sapSweepKernel(const b3b200_aabb* __restrict__ sorted, int n, const unsigned int* __restrict__ scal,
 															 b3b200_int4* __restrict__ pairs, unsigned int* __restrict__ ctr, int maxPairs, int hasWorlds)
 {
-	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
+	__shared__ float4 winAll[BP_THREADS / 32][2][32];
 	const int lane = threadIdx.x & 31;
-	int2* stage = stageAll[threadIdx.x >> 5];
-	int count = 0;
+	float4* wmn = winAll[threadIdx.x >> 5][0];
+	float4* wmx = winAll[threadIdx.x >> 5][1];
 	const int axis = (int)scal[SC_AXIS];
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	bool valid = i < n;
+	const int base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31;
+	if (base >= n) return;
+	const int i = base + lane;
+	bool active = i < n;
 	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
-	int idA = 0;
 	float limit = 0.f;
-	if (valid)
+	if (active)
 	{
 		const float4* p = reinterpret_cast<const float4*>(&sorted[i]);
 		mnA = p[0];
 		mxA = p[1];
-		idA = __float_as_int(mnA.w);
 		limit = axisOf(mxA, axis);
 	}
-	int j = i + 1;
-	for (;;)
+	const int idA = __float_as_int(mnA.w);
+	for (int start = base + 1; start < n; start += 32)
 	{
-		bool hit = false;
-		int idB = 0;
-		if (valid)
+		const int j = start + lane;
+		if (j < n)
 		{
-			if (j < n)
+			const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
+			wmn[lane] = __ldg(p);
+			wmx[lane] = __ldg(p + 1);
+		}
+		__syncwarp();
+		const int cnt = n - start < 32 ? n - start : 32;
+		unsigned int hits = 0u;
+		if (active)
+		{
+			// candidates [start, start + cnt); this lane's own successors start at i + 1
+			int t = i + 1 - start;
+			if (t < 0) t = 0;
+			for (; t < cnt; t++)
 			{
-				const float4* p = reinterpret_cast<const float4*>(&sorted[j]);
-				float4 mnB = p[0];
+				const float4 mnB = wmn[t];
 				// computePairsKernelLocalSharedMemory break test (sap.cl:231-300)
 				if (limit < axisOf(mnB, axis))
-					valid = false;
-				else
 				{
-					float4 mxB = p[1];
-					idB = __float_as_int(mnB.w);
-					hit = aabbOverlap(mnA, mxA, mnB, mxB) && (!hasWorlds || __float_as_int(mxB.w) == __float_as_int(mxA.w));
-					j++;
+					active = false;
+					break;
 				}
+				const float4 mxB = wmx[t];
+				if (aabbOverlap(mnA, mxA, mnB, mxB) && (!hasWorlds || __float_as_int(mxB.w) == __float_as_int(mxA.w))) hits |= 1u << t;
 			}
-			else
-				valid = false;
 		}
-		stagePush(hit, idA, idB, stage, count, lane, pairs, ctr, maxPairs);
-		if (!__any_sync(0xffffffffu, valid)) break;
+		// emit: one reservation per warp and window
+		const int mine = __popc(hits);
+		int incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const int v = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) incl += v;
+		}
+		const int total = __shfl_sync(0xffffffffu, incl, 31);
+		if (total)
+		{
+			unsigned int slot = 0;
+			if (lane == 0) slot = atomicAdd(&ctr[CTR_PAIRS], (unsigned int)total);
+			slot = __shfl_sync(0xffffffffu, slot, 0) + (unsigned int)(incl - mine);
+			while (hits)
+			{
+				const int t = __ffs(hits) - 1;
+				hits &= hits - 1;
+				if (slot < (unsigned int)maxPairs)
+				{
+					const int idB = __float_as_int(wmn[t].w);
+					b3b200_int4 o;
+					o.x = idA < idB ? idA : idB;
+					o.y = idA < idB ? idB : idA;
+					o.z = -1;  // clearOverlappingPairsKernel (updateAabbsKernel.cl:15) folded in
+					o.w = -1;
+					pairs[slot] = o;
+				}
+				slot++;
+			}
+		}
+		if (!__any_sync(0xffffffffu, active)) break;
+		__syncwarp();
 	}
-	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
 }
 
 // ---------------------------------------------------------------- large x small

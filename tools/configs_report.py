@@ -84,26 +84,17 @@ st, wall = timed_steps(w, 100, 20)
 report("           same scene, batched PGS 8 it., grid", w, st, wall)
 w.close()
 
-# config 5 (i), one GPU's share: 1 024 independent 256-box worlds (8x4x8 piles, config-3 recipe) in one world object,
-# 64 units apart on a shared plane (no pair ever crosses a world boundary: checked)
+# config 5 (i), one GPU's share: 1 024 independent worlds (8x4x8 cubes + their own static ground box each, config-3 recipe), all at
+# the SAME coordinates, batched into one b3b200 world (b3b200_set_current_world)
 nw = 1024
-w = capi.World(capi.default_config(nw * 256 + 16))
-w.register_instance(0.0, (0, 0, 0), scenes.IDENT, w.register_plane((0, 1, 0), 0.0))
-col = w.register_convex_points(scenes.box_points(1.0))
-i, j, k = np.meshgrid(np.arange(8), np.arange(4), np.arange(8), indexing="ij")
-local = np.stack([(((j + 1) & 1) + 2.2 * i).reshape(-1), (1.0 + 2.0 * j).reshape(-1), (((j + 1) & 1) + 2.2 * k).reshape(-1)], 1).astype(np.float32)
-gx, gz = np.meshgrid(np.arange(32), np.arange(32), indexing="ij")
-off = np.stack([gx.reshape(-1) * 64.0, np.zeros(nw), gz.reshape(-1) * 64.0], 1).astype(np.float32)
-pos = (off[:, None, :] + local[None, :, :]).reshape(-1, 3)
-q = np.tile(np.array(scenes.IDENT, np.float32), (len(pos), 1))
-w.register_instances(np.ones(len(pos), np.float32), pos, q, np.full(len(pos), col, np.int32))
+w = capi.World(capi.default_config(nw * 257 + 64))
+scenes.batched_box_worlds(w, nw)
 w.upload()
 w.set_solver(capi.SOLVER_PGS, 10)
 st, wall = timed_steps(w, 100, 200)
 p = w.pairs()
-world_of = np.concatenate([[-1], np.repeat(np.arange(nw), 256)])
-wa, wb = world_of[p["x"]], world_of[p["y"]]
-cross = int(((wa != wb) & (wa >= 0) & (wb >= 0)).sum())
-report("configs[4](i) 1 024 worlds x 256 boxes in one launch stream", w, st, wall)
-print("           pairs that cross a world boundary: %d" % cross)
+world_of = w.body_worlds()
+cross = int((world_of[p["x"]] != world_of[p["y"]]).sum())
+report("configs[4](i) 1 024 batched worlds x 257 bodies, PGS 10 it.", w, st, wall)
+print("           pairs that join two worlds: %d; cross-block batches %d" % (cross, w.counters()[3]))
 w.close()
