@@ -506,6 +506,11 @@ B3_D void contactBodies(const SetupArgs& s, int c, int& a, int& b, bool& aStatic
 // bodies up in the partition; the kernels after it work on the packed per-contact words it leaves.
 __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs s)
 {
+	// the per-block contact counts are gathered per CTA in shared memory and added to the global table once at the end (a few
+	// hundred hot addresses hit by every warp were what bounded this kernel)
+	extern __shared__ unsigned int sCount[];  // numBlocksMax
+	for (int i = threadIdx.x; i < s.numBlocksMax; i += blockDim.x) sCount[i] = 0u;
+	__syncthreads();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
 	const int lane = threadIdx.x & 31;
@@ -557,8 +562,11 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs 
 			s.contactSlots[c] = sa | (sb << 16);
 			s.contactPair[c] = make_int2(aStatic ? -1 : a, bStatic ? -1 : b);
 		}
-		warpCountByKey(s.blockCount, owner, lane);
+		warpCountByKey(sCount, owner, lane);
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < s.numBlocksMax; i += blockDim.x)
+		if (sCount[i]) atomicAdd(&s.blockCount[i], sCount[i]);
 }
 
 // lowest colour not in (m0, m1), -2 when all 128 are taken
@@ -616,6 +624,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 	extern __shared__ unsigned int sStart[];  // numBlocksMax + 1
 	__shared__ unsigned int sWarp[SETUP_THREADS / 32];
 	__shared__ unsigned int sCarry;
+	__shared__ unsigned int sCrossHist[MAX_BATCHES];  // cross colours of this CTA's contacts, added to the global histogram at the end
+	for (int i = threadIdx.x; i < MAX_BATCHES; i += blockDim.x) sCrossHist[i] = 0u;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	// exclusive scan of the block counts (every CTA computes its own copy; CTA 0 also publishes it)
 	if (threadIdx.x == 0) sCarry = 0;
@@ -691,7 +701,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 			}
 		}
 		__syncwarp();
-		warpCountByKey(s.crossHist, colour, lane);
+		warpCountByKey(sCrossHist, colour, lane);
 		const unsigned int m = __ballot_sync(0xffffffffu, cross);
 		if (m)
 		{
@@ -701,6 +711,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 			if (cross) s.crossList[slot] = (unsigned int)c;
 		}
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < MAX_BATCHES; i += blockDim.x)
+		if (sCrossHist[i]) atomicAdd(&s.crossHist[i], sCrossHist[i]);
 }
 
 // ---- K2b (reproducible mode only): the cross contacts are coloured by priority rounds (Jones-Plassmann) in ONE CTA:
@@ -1907,7 +1920,7 @@ int launchSolverSetup(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dSolverScratch.ptr, 0, sizeof(unsigned int) * ((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM), st));
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dBlockStatics.ptr, 0xff, sizeof(int) * (size_t)B * NSTATIC, st));
 	const int grid = w->smCount * 4;
-	solverClassifyKernel<<<grid, SETUP_THREADS, 0, st>>>(s);
+	solverClassifyKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * (size_t)B, st>>>(s);
 	B3_LAUNCH_CHECK();
 	solverScatterKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * ((size_t)B + 1), st>>>(s);
 	B3_LAUNCH_CHECK();
