@@ -210,6 +210,7 @@ struct World
 	int partS = 0, partBlocksMax = 0, partAge = 0, partInterval = 8, partBodies = -1;
 	bool partValid = false;
 	DevBuf<unsigned long long> dBodyMask;  // colours of a body's cross contacts (2 words / body)
+	DevBuf<unsigned int> dCtaBase;        // per setup CTA and block: start of the CTA's contacts inside the block's list (classify -> scatter)
 	DevBuf<unsigned int> dBodyPrio;       // max pending priority per body (reproducible colouring; 2 words / body)
 	DevBuf<int> dContactBlock, dContactColour;
 	DevBuf<unsigned int> dContactSlots, dBlockList, dCrossList;

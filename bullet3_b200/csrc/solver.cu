@@ -323,6 +323,7 @@ struct SetupArgs
 	unsigned int* blockCount;      // scratch, see the enum above
 	unsigned int* blockCursor;
 	unsigned int* crossHist;
+	unsigned int* ctaBase;  // [setup grid][numBlocksMax + 1]: where each CTA's contacts go inside every block's list (+ in the cross list)
 	unsigned int* crossCursor;
 	unsigned int* misc;
 	int* blockStatics;             // NSTATIC per block, -1 = free
@@ -508,8 +509,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs 
 {
 	// the per-block contact counts are gathered per CTA in shared memory and added to the global table once at the end (a few
 	// hundred hot addresses hit by every warp were what bounded this kernel)
-	extern __shared__ unsigned int sCount[];  // numBlocksMax
-	for (int i = threadIdx.x; i < s.numBlocksMax; i += blockDim.x) sCount[i] = 0u;
+	extern __shared__ unsigned int sCount[];  // numBlocksMax + 1
+	for (int i = threadIdx.x; i <= s.numBlocksMax; i += blockDim.x) sCount[i] = 0u;
 	__syncthreads();
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int stride = gridDim.x * blockDim.x;
@@ -563,10 +564,19 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverClassifyKernel(SetupArgs 
 			s.contactPair[c] = make_int2(aStatic ? -1 : a, bStatic ? -1 : b);
 		}
 		warpCountByKey(sCount, owner, lane);
+		// (cross contacts are counted under the extra key numBlocksMax)
+		warpCountByKey(sCount, c < nContacts && owner < 0 ? s.numBlocksMax : -1, lane);
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < s.numBlocksMax; i += blockDim.x)
-		if (sCount[i]) atomicAdd(&s.blockCount[i], sCount[i]);
+	// one atomic per (CTA, block): the returned base is where THIS CTA's contacts of that block go in the block's list.  The
+	// scatter kernel (same grid, same contact -> CTA mapping) then needs shared-memory cursors only.
+	unsigned int* mine = s.ctaBase + (size_t)blockIdx.x * (s.numBlocksMax + 1);
+	for (int i = threadIdx.x; i <= s.numBlocksMax; i += blockDim.x)
+	{
+		const unsigned int cnt = sCount[i];
+		unsigned int* dst = i < s.numBlocksMax ? &s.blockCount[i] : &s.misc[MISC_CROSS_COUNT];
+		mine[i] = cnt ? atomicAdd(dst, cnt) : 0u;
+	}
 }
 
 // lowest colour not in (m0, m1), -2 when all 128 are taken
@@ -626,6 +636,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 	__shared__ unsigned int sCarry;
 	__shared__ unsigned int sCrossHist[MAX_BATCHES];  // cross colours of this CTA's contacts, added to the global histogram at the end
 	for (int i = threadIdx.x; i < MAX_BATCHES; i += blockDim.x) sCrossHist[i] = 0u;
+	// this CTA's cursors into the blocks' lists and into the cross list, from the ranges the classify kernel reserved
+	unsigned int* sCursor = sStart + s.numBlocksMax + 1;  // numBlocksMax + 1
+	for (int i = threadIdx.x; i <= s.numBlocksMax; i += blockDim.x) sCursor[i] = s.ctaBase[(size_t)blockIdx.x * (s.numBlocksMax + 1) + i];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	// exclusive scan of the block counts (every CTA computes its own copy; CTA 0 also publishes it)
 	if (threadIdx.x == 0) sCarry = 0;
@@ -664,7 +677,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 		const int c = base + lane;
 		int owner = c < nContacts ? s.contactBlock[c] : -1;
 		// interior: a place in the block's list (one atomic per distinct block in the warp)
-		const unsigned int pos = warpCountByKey(s.blockCursor, owner, lane);
+		const bool wasCross = c < nContacts && owner < 0;
+		const unsigned int pos = warpCountByKey(sCursor, owner, lane);
 		if (owner >= 0)
 		{
 			if (pos >= contactCap)
@@ -702,14 +716,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverScatterKernel(SetupArgs s
 		}
 		__syncwarp();
 		warpCountByKey(sCrossHist, colour, lane);
-		const unsigned int m = __ballot_sync(0xffffffffu, cross);
-		if (m)
-		{
-			unsigned int slot = 0;
-			if (lane == 0) slot = atomicAdd(&s.misc[MISC_CROSS_COUNT], (unsigned int)__popc(m));
-			slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
-			if (cross) s.crossList[slot] = (unsigned int)c;
-		}
+		// cross list: the contacts the classify kernel counted go to this CTA's reserved range; the few that overflowed their
+		// block's cap just now take a slot behind all reserved ranges
+		const unsigned int slotR = warpCountByKey(sCursor, wasCross ? s.numBlocksMax : -1, lane);
+		if (wasCross)
+			s.crossList[slotR] = (unsigned int)c;
+		else if (cross)
+			s.crossList[atomicAdd(&s.misc[MISC_CROSS_COUNT], 1u)] = (unsigned int)c;
 	}
 	__syncthreads();
 	for (int i = threadIdx.x; i < MAX_BATCHES; i += blockDim.x)
@@ -865,9 +878,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 	for (int blk = blockIdx.x; blk < s.numBlocksMax; blk += gridDim.x)
 	{
 		const unsigned int first = s.blockStart[blk];
-		unsigned int n = s.blockCursor[blk];
 		const unsigned int counted = s.blockStart[blk + 1] - first;
-		if (n > counted) n = counted;  // (cannot happen; the list segment is `counted` long)
+		unsigned int n = counted;  // (every position of the segment was handed to exactly one contact)
 		if (s.colouring == 0 && n > (unsigned int)JP_CONTACT_CAP) n = JP_CONTACT_CAP;  // the scatter kernel sent the rest the global way
 		const unsigned int* list = s.blockList + first;
 		for (int i = threadIdx.x; i < 2 * slots; i += SETUP_THREADS) sMask[i] = 0ull;
@@ -1852,6 +1864,7 @@ static int fillSetupArgs(World* w, SetupArgs& s)
 	B3_TRY(w->dBodyMask.reserve(2 * nb));
 	B3_TRY(w->dBodyPrio.reserve(2 * nb));
 	B3_TRY(w->dSolverScratch.reserve((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM));
+	B3_TRY(w->dCtaBase.reserve((size_t)w->smCount * 4 * ((size_t)B + 1)));  // (smCount * 4 = the grid of the classify / scatter kernels)
 	B3_TRY(w->dBlockStatics.reserve((size_t)B * NSTATIC));
 	B3_TRY(w->dBlockStart.reserve((size_t)B + 1));
 	B3_TRY(w->dBlockTileBase.reserve((size_t)B));
@@ -1887,6 +1900,7 @@ static int fillSetupArgs(World* w, SetupArgs& s)
 	s.blockCount = scr;
 	s.blockCursor = scr + B;
 	s.crossHist = scr + 2 * B;
+	s.ctaBase = w->dCtaBase.ptr;
 	s.crossCursor = scr + 2 * B + MAX_BATCHES;
 	s.misc = scr + 2 * B + 2 * MAX_BATCHES;
 	s.blockStatics = w->dBlockStatics.ptr;
@@ -1920,9 +1934,9 @@ int launchSolverSetup(World* w)
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dSolverScratch.ptr, 0, sizeof(unsigned int) * ((size_t)2 * B + 2 * MAX_BATCHES + MISC_NUM), st));
 	B3_CUDA_CHECK(cudaMemsetAsync(w->dBlockStatics.ptr, 0xff, sizeof(int) * (size_t)B * NSTATIC, st));
 	const int grid = w->smCount * 4;
-	solverClassifyKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * (size_t)B, st>>>(s);
+	solverClassifyKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * ((size_t)B + 1), st>>>(s);
 	B3_LAUNCH_CHECK();
-	solverScatterKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * ((size_t)B + 1), st>>>(s);
+	solverScatterKernel<<<grid, SETUP_THREADS, sizeof(unsigned int) * 2 * ((size_t)B + 1), st>>>(s);
 	B3_LAUNCH_CHECK();
 	if (w->solverColouring == 0)
 	{
