@@ -168,3 +168,18 @@ def test_round2_entry_points_without_a_device():
     info = w.table("bvh_infos")
     assert len(info) == 1 and info["numNodes"][0] == 3 and info["numSubTrees"][0] == 1 and len(w.table("bvh_nodes")) == 6
     w.close()
+
+
+def test_batched_box_worlds_scene_on_a_host_only_world():
+    """BASELINE configs[4](i) recipe: every world is 8 x 4 x 8 cubes + its own static ground box, all worlds at the same coordinates"""
+    from bullet3_b200 import scenes
+
+    w = capi.World(capi.default_config(5 * 257 + 8), device=-1)
+    per_world = scenes.batched_box_worlds(w, 5)
+    assert per_world == 257 and w.num_bodies == 5 * 257 and w.num_worlds() == 5
+    wid = w.body_worlds()
+    assert np.array_equal(wid, np.repeat(np.arange(5), 257))
+    b = w.table("bodies")
+    assert (b["invMass"][wid == 3] == 0).sum() == 1 and b["invMass"][257 * 3] == 0  # the ground box comes first in its world
+    assert np.array_equal(b["pos"][:257], b["pos"][257 * 4:])  # same coordinates in every world
+    w.close()
