@@ -295,6 +295,17 @@ def ncu_traffic(kernel):
     return None
 
 
+def ncu_sm_throughput(kernel):
+    """sm__throughput (% of the peak issue rate) of `kernel` from the same committed ncu summary; None when absent"""
+    try:
+        for line in open(os.path.join(ROOT, "profiles", "r02s2_ncu_summary.txt")):
+            if line.startswith(kernel + " ") and "sm throughput" in line:
+                return float(line.split("sm throughput")[1].split("%")[0])
+    except Exception:
+        pass
+    return None
+
+
 def slab_leg(world_size, rank, local_rank, steps, warmup, per_rank_x=32, ny=64, nz=256):
     """BASELINE configs[4](ii): ONE box field (config-3 recipe) of 32*N x 64 x 256 bodies -- 4 194 304 at N = 8 -- cut into N slabs along x; every
     rank steps its slab, boundary bodies are mirrored on the neighbours by NCCL send/recv issued by the library itself on the world's stream
@@ -544,7 +555,7 @@ def main():
             "counts": {"bodies": nbodies, "pairs": P, "contacts": Cn, "batches": nb, "cross_block_batches": int(ctr[3]), "overflow_flags": int(ctr[4])},
             "stages": stages,
             "roofline": {"bound": "hbm", "kernel": domk, "achieved": dk_gbs, "peak": peak, "unit": "GB/s", "frac": dk_gbs / peak,
-                         "traffic": ncu_traffic(domk), "peak_source": peak_src, "kernel_ms": dk["ms"], "alg_bytes_per_launch": dk["alg_bytes"],
+                         "traffic": ncu_traffic(domk), "sm_throughput_pct_ncu": ncu_sm_throughput(domk), "peak_source": peak_src, "kernel_ms": dk["ms"], "alg_bytes_per_launch": dk["alg_bytes"],
                          "note": "dominant kernel, timed live with CUDA events on the world's stream; " + dk["note"],
                          "other_kernel": {k: {"ms": v["ms"], "gbs": v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else 0.0, "traffic": ncu_traffic(k)}
                                           for k, v in kern.items() if k != domk}},
