@@ -342,6 +342,11 @@ extern "C" int b3b200_slab_init(b3b200_world* w, const b3b200_slab_config* cfg, 
 	if (cfg->axis < 0 || cfg->axis > 2 || cfg->rank < 0 || cfg->rank >= cfg->numRanks || cfg->maxGhosts < 0 || cfg->numOwned < 0 || cfg->numOwned > w->numBodies ||
 		cfg->firstGhostSlot < 0)
 		return B3B200_ERR_INVALID;
+	if (w->numWorlds > 1)
+	{
+		setLastError("slab_init: a world that batches independent worlds (b3b200_set_current_world) cannot be slab-decomposed; shard the worlds across ranks instead");
+		return B3B200_ERR_STATE;
+	}
 	const bool hasLeft = cfg->rank > 0, hasRight = cfg->rank < cfg->numRanks - 1;
 	if (cfg->firstGhostSlot + cfg->maxGhosts * ((int)hasLeft + (int)hasRight) > w->numBodies)
 	{
