@@ -1559,3 +1559,42 @@ def test_two_worlds_stepped_from_two_threads():
             assert np.array_equal(b[f].view(np.uint32), want[f].view(np.uint32)), f
         w.close()
     alone.close()
+
+
+def test_batched_worlds_with_gaps_and_unequal_sizes():
+    """world ids need not be dense or equally filled: worlds 0, 3 and 9 (1-8 otherwise empty) with 40 / 1 / 150 dynamic bodies, one of
+    them without any static body -- pairs stay inside their worlds, the lone body of world 3 falls freely through the others"""
+    w = capi.World(capi.default_config(1024))
+    col = w.register_convex_points(scenes.box_points(0.5))
+    ground = w.register_convex_points(scenes.box_points(30.0))
+    rng = np.random.default_rng(2)
+
+    def pile(n, with_ground):
+        if with_ground:
+            w.register_instance(0.0, (0.0, -30.0, 0.0), scenes.IDENT, ground)
+        for _ in range(n):
+            w.register_instance(1.0, tuple(rng.uniform((-3, 0.6, -3), (3, 6, 3))), scenes.random_quat(rng), col)
+
+    w.set_current_world(0)
+    pile(40, True)
+    w.set_current_world(3)
+    pile(1, False)
+    w.set_current_world(9)
+    pile(150, True)
+    w.upload()
+    assert w.num_worlds() == 10
+    wid = w.body_worlds()
+    w.set_solver(capi.SOLVER_PGS, 6)
+    lone = int(np.nonzero(wid == 3)[0][0])
+    y0 = w.bodies()["pos"][lone, 1]
+    for _ in range(30):
+        w.step(1 / 60)
+        p = w.pairs()
+        assert np.array_equal(wid[p["x"]], wid[p["y"]])
+    b = w.bodies()
+    assert w.counters()[1] > 20 and w.counters()[4] == 0
+    fall = 0.5 * 9.8 * (30 / 60) ** 2
+    assert abs((y0 - b["pos"][lone, 1]) - fall) < 0.15 * fall  # free fall: nothing of the other worlds touched it
+    dyn = (b["invMass"] != 0) & (wid != 3)
+    assert (b["pos"][dyn, 1] > 0.2).all()
+    w.close()
