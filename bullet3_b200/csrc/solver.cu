@@ -925,6 +925,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 			for (int round = 0; round < 100000; round++)
 			{
 				if (threadIdx.x == 0) sLeft = 0;
+				// (the priorities are cleared between the rounds, not by the winners while the others still compare: no thread then
+				// reads a word another one writes in the same phase)
+				if (round > 0)
+				{
+					for (int i = threadIdx.x; i < slots; i += SETUP_THREADS) sPrio[i] = 0ull;
+					__syncthreads();
+				}
 				for (unsigned int i = threadIdx.x; i < n; i += SETUP_THREADS)
 				{
 					if (sCCol[i] != -1) continue;
@@ -959,8 +966,6 @@ __global__ void __launch_bounds__(SETUP_THREADS) solverBlockSetupKernel(SetupArg
 						}
 						sCCol[i] = (signed char)colour;
 						if (colour >= 0) atomicAdd(&sHist[colour], 1u);
-						if (da) vp[sa] = 0ull;
-						if (db) vp[sb] = 0ull;
 					}
 					else
 						sLeft = 1;
