@@ -37,6 +37,9 @@ enum
 	SC_AXIS = 3,
 	SC_SUM = 4,   // 3 floats
 	SC_SUM2 = 7,  // 3 floats
+	SC_EXTSUM = 10,       // float: sum of the small AABBs' widest extents
+	SC_WIDE_THRESH = 11,  // float: a small AABB wider than this is "wide" (kept out of the grid); FLT_MAX when there is none
+	SC_WIDE_COUNT = 12,   // number of wide AABBs this step
 	SC_COUNT = 16
 };
 
@@ -93,13 +96,15 @@ B3_D void stagePush(bool hit, int a, int b, int2* stage, int& count, int lane, b
 // ---------------------------------------------------------------- parameters
 __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n, unsigned int* __restrict__ scal)
 {
-	float ext = 0.f;
+	float ext = 0.f, es = 0.f;
 	float sx = 0.f, sy = 0.f, sz = 0.f, qx = 0.f, qy = 0.f, qz = 0.f;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
 		const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
 		float4 mn = __ldg(p), mx = __ldg(p + 1);
-		ext = fmaxf(ext, fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z)));
+		const float e = fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z));
+		ext = fmaxf(ext, e);
+		if (e < 1e30f) es += e;
 		float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
 		sx += cx;
 		sy += cy;
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restric
 	for (int o = 16; o > 0; o >>= 1)
 	{
 		ext = fmaxf(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+		es += __shfl_xor_sync(0xffffffffu, es, o);
 		sx += __shfl_xor_sync(0xffffffffu, sx, o);
 		sy += __shfl_xor_sync(0xffffffffu, sy, o);
 		sz += __shfl_xor_sync(0xffffffffu, sz, o);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restric
 		qz += __shfl_xor_sync(0xffffffffu, qz, o);
 	}
 	// one set of atomics per CTA (8 warps -> shared memory -> warp 0): the 7 scalars are global hot spots
-	__shared__ float part[8][7];
+	__shared__ float part[8][8];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (lane == 0)
 	{
@@ -131,9 +137,10 @@ __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restric
 		part[warp][4] = qx;
 		part[warp][5] = qy;
 		part[warp][6] = qz;
+		part[warp][7] = es;
 	}
 	__syncthreads();
-	if (threadIdx.x < 7)
+	if (threadIdx.x < 8)
 	{
 		float v = part[0][threadIdx.x];
 		for (int k = 1; k < 8; k++) v = threadIdx.x == 0 ? fmaxf(v, part[k][0]) : v + part[k][threadIdx.x];
@@ -142,8 +149,10 @@ __global__ void __launch_bounds__(256) bpPrepKernel(const b3b200_aabb* __restric
 			atomicMax(&scal[SC_MAXEXT_BITS], __float_as_uint(v));
 		else if (threadIdx.x <= 3)
 			atomicAdd(&f[SC_SUM + (threadIdx.x - 1)], v);
-		else
+		else if (threadIdx.x <= 6)
 			atomicAdd(&f[SC_SUM2 + (threadIdx.x - 4)], v);
+		else
+			atomicAdd(&f[SC_EXTSUM], v);
 	}
 }
 
@@ -151,7 +160,18 @@ __global__ void bpParamsKernel(unsigned int* scal, int n)
 {
 	float* f = reinterpret_cast<float*>(scal);
 	float ext = __uint_as_float(scal[SC_MAXEXT_BITS]);
-	// the cell edge must be >= the widest small AABB for the 27-cell scan to be exact
+	// the cell edge must be >= the widest AABB IN THE GRID for the 27-cell scan to be exact.  Normally that is the widest small
+	// AABB; but one long body among many small ones would blow every cell up (and the pair kernel towards O(n^2)), so AABBs
+	// wider than 4 x the mean extent are kept out of the grid when they exist -- gridCountKernel lists them, wideSmallKernel
+	// tests them against everything, like the static "large" proxies -- and the cell is sized for the rest.
+	const float robust = 4.0f * f[SC_EXTSUM] / fmaxf((float)n, 1.0f);
+	float thresh = FLT_MAX;
+	if (n >= 64 && ext > robust && robust > 0.f)
+	{
+		thresh = robust;
+		ext = robust;
+	}
+	f[SC_WIDE_THRESH] = thresh;
 	float cell = fmaxf(ext * 1.01f + 1e-6f, 1e-3f);
 	f[SC_CELL] = cell;
 	f[SC_INVCELL] = 1.0f / cell;
@@ -196,14 +216,25 @@ B3_D unsigned int cellKey(int x, int y, int z)
 // dense exclusive scan over the 128^3 cells, scatter.  The dense table gives the sorted range of ANY run of cells -- also of
 // empty ones -- with two loads, which is what the pair kernel needs.
 __global__ void __launch_bounds__(256) gridCountKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int n,
-													   const unsigned int* __restrict__ scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ rankInCell,
-													   unsigned int* __restrict__ cellCount, const int* __restrict__ worldOf)
+													   const unsigned int* scal, unsigned int* __restrict__ keys, unsigned int* __restrict__ rankInCell,
+													   unsigned int* __restrict__ cellCount, const int* __restrict__ worldOf, unsigned int* wideCount,
+													   int* __restrict__ wideList)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	float invCell = __uint_as_float(scal[SC_INVCELL]);
 	int idx = smallMap[i];
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[idx]);
+	{
+		const float4 mn = __ldg(p), mx = __ldg(p + 1);
+		if (fmaxf(mx.x - mn.x, fmaxf(mx.y - mn.y, mx.z - mn.z)) > __uint_as_float(scal[SC_WIDE_THRESH]))
+		{
+			// a wide AABB: not in the grid (its key marks it for the scatter kernel), listed for wideSmallKernel
+			wideList[atomicAdd(wideCount, 1u)] = idx;
+			keys[i] = 0xffffffffu;
+			return;
+		}
+	}
 	int3 c = cellOf(__ldg(p), __ldg(p + 1), invCell);
 	if (worldOf)
 	{
@@ -224,6 +255,7 @@ __global__ void __launch_bounds__(256) gridScatterKernel(const b3b200_aabb* __re
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
+	if (keys[i] == 0xffffffffu) return;  // a wide AABB (gridCountKernel)
 	const float4* p = reinterpret_cast<const float4*>(&aabbs[smallMap[i]]);
 	const float4 mn = __ldg(p);
 	float4 mx = __ldg(p + 1);
@@ -266,6 +298,7 @@ __global__ void __launch_bounds__(BP_THREADS) gridFindPairsKernel(const b3b200_a
 	int count = 0;
 	const float invCell = __uint_as_float(scal[SC_INVCELL]);
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	n = (int)__ldg(&cellStart[GRID_CELLS]);  // bodies in the grid (all small AABBs but the wide ones)
 	bool valid = i < n;
 	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
 	int idA = 0;
@@ -531,6 +564,45 @@ __global__ void __launch_bounds__(BP_THREADS) largeSmallKernel(const b3b200_aabb
 	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
 }
 
+// wide x everything: the AABBs gridCountKernel kept out of the grid against every small AABB (a pair of two wide ones is
+// emitted by the one with the lower index).  Usually there is none and every thread leaves after one load.
+__global__ void __launch_bounds__(BP_THREADS) wideSmallKernel(const b3b200_aabb* __restrict__ aabbs, const int* __restrict__ smallMap, int nSmall,
+															  const int* __restrict__ wideList, const unsigned int* __restrict__ scal, b3b200_int4* __restrict__ pairs,
+															  unsigned int* __restrict__ ctr, int maxPairs, const int* __restrict__ worldOf)
+{
+	const int nWide = (int)scal[SC_WIDE_COUNT];
+	if (nWide == 0) return;
+	__shared__ int2 stageAll[BP_THREADS / 32][STAGE_CAP];
+	const int lane = threadIdx.x & 31;
+	int2* stage = stageAll[threadIdx.x >> 5];
+	int count = 0;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = i < nSmall;
+	float4 mnA = mk4(0, 0, 0), mxA = mk4(0, 0, 0);
+	int idxA = -1, wA = 0;
+	bool wideA = false;
+	if (valid)
+	{
+		idxA = smallMap[i];
+		const float4* p = reinterpret_cast<const float4*>(&aabbs[idxA]);
+		mnA = __ldg(p);
+		mxA = __ldg(p + 1);
+		wideA = fmaxf(mxA.x - mnA.x, fmaxf(mxA.y - mnA.y, mxA.z - mnA.z)) > __uint_as_float(scal[SC_WIDE_THRESH]);
+		if (worldOf) wA = __ldg(&worldOf[idxA]);
+	}
+	const int idA = __float_as_int(mnA.w);
+	for (int l = 0; l < nWide; l++)
+	{
+		const int idxB = __ldg(&wideList[l]);
+		const float4* p = reinterpret_cast<const float4*>(&aabbs[idxB]);
+		const float4 mnB = __ldg(p), mxB = __ldg(p + 1);
+		bool hit = valid && idxB != idxA && !(wideA && idxB < idxA) && aabbOverlap(mnA, mxA, mnB, mxB);
+		if (hit && worldOf) hit = __ldg(&worldOf[idxB]) == wA;
+		stagePush(hit, idA, __float_as_int(mnB.w), stage, count, lane, pairs, ctr, maxPairs);
+	}
+	if (count) stageFlush(stage, count, lane, pairs, ctr, maxPairs);
+}
+
 __global__ void clampPairsKernel(unsigned int* ctr, int maxPairs)
 {
 	if (ctr[CTR_PAIRS] > (unsigned int)maxPairs)
@@ -634,6 +706,7 @@ int Broadphase::writeAabbs()
 	B3_TRY(keys.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(vals.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(sortedAabbs.reserve(numSmall > 0 ? numSmall : 1));
+	B3_TRY(wideList.reserve(numSmall > 0 ? numSmall : 1));
 	B3_TRY(cellStart.reserve(GRID_CELLS + 4));
 	B3_TRY(cellCnt.reserve(GRID_CELLS + 4));
 	B3_TRY(scanTotals.reserve((size_t)largeScanChunks(GRID_CELLS + 4)));
@@ -668,13 +741,16 @@ int Broadphase::calculatePairs(int maxPairsNow)
 			unsigned int* cellCount = reinterpret_cast<unsigned int*>(cellCnt.ptr);
 			unsigned int* cellBegin = reinterpret_cast<unsigned int*>(cellStart.ptr);
 			B3_CUDA_CHECK(cudaMemsetAsync(cellCount, 0, sizeof(unsigned int) * (GRID_CELLS + 4), s));
-			gridCountKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr, cellCount, worldOf);
+			gridCountKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, scal, keys.ptr, vals.ptr, cellCount, worldOf,
+																 reinterpret_cast<unsigned int*>(scalars.ptr) + SC_WIDE_COUNT, wideList.ptr);
 			B3_LAUNCH_CHECK();
 			// GRID_CELLS + 4 entries: cellStart[key + 3] of the last cells reads the total
 			B3_TRY(exclusiveScanLargeU32(s, cellCount, cellBegin, GRID_CELLS + 4, scanTotals.ptr, nullptr));
 			gridScatterKernel<<<divUp(numSmall, 256), 256, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, keys.ptr, vals.ptr, cellBegin, sortedAabbs.ptr, worldOf);
 			B3_LAUNCH_CHECK();
 			gridFindPairsKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(sortedAabbs.ptr, cellBegin, numSmall, scal, pairs.ptr, ctr, maxPairsNow, worldOf ? 1 : 0);
+			B3_LAUNCH_CHECK();
+			wideSmallKernel<<<divUp(numSmall, BP_THREADS), BP_THREADS, 0, s>>>(aabbs.ptr, smallMap.ptr, numSmall, wideList.ptr, scal, pairs.ptr, ctr, maxPairsNow, worldOf);
 			B3_LAUNCH_CHECK();
 		}
 		else

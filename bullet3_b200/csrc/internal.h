@@ -74,6 +74,7 @@ struct Broadphase
 	// scratch
 	DevBuf<unsigned int> keys, vals;
 	DevBuf<b3b200_aabb> sortedAabbs;
+	DevBuf<int> wideList;          // small AABBs much wider than the rest: kept out of the grid, tested against everything (broadphase.cu)
 	DevBuf<int> cellStart;         // 128^3 + 4: first sorted index of every cell (dense exclusive scan of the counts)
 	DevBuf<int> cellCnt;           // bodies per cell
 	DevBuf<unsigned int> scanTotals;  // scratch of the multi-CTA scan

@@ -1598,3 +1598,31 @@ def test_batched_worlds_with_gaps_and_unequal_sizes():
     dyn = (b["invMass"] != 0) & (wid != 3)
     assert (b["pos"][dyn, 1] > 0.2).all()
     w.close()
+
+
+def test_grid_broadphase_keeps_a_few_long_bodies_out_of_the_cells():
+    """a few long dynamic AABBs among 30 000 small ones: the grid cell is sized for the small ones, the long ones are listed and tested
+    against everything (the cell used to be the widest AABB: every cell then held hundreds of bodies).  Exact pair set, and the
+    time of calculateOverlappingPairs stays near that of the scene without the long bodies"""
+    rng = np.random.default_rng(4)
+    n = 30000
+    a = np.zeros(n, capi.aabb_t)
+    c = rng.uniform(-60, 60, (n, 3)).astype(np.float32)
+    h = rng.uniform(0.3, 0.6, (n, 3)).astype(np.float32)
+    a["min"][:, :3], a["max"][:, :3] = c - h, c + h
+    a["minIndex"] = np.arange(n)
+    small, large = np.arange(n, dtype=np.int32), np.zeros(0, np.int32)
+    bp = run_standalone_bp(capi.BP_GRID, a, small, large, 1 << 20)
+    base_ms = bp.last_ms()
+    base_pairs = bp.num_overlap()
+    for k, (lo, hi) in enumerate([((-55, -1, -1), (55, 1, 1)), ((-1, -58, -1), (1, 58, 1)), ((-50, -50, 3), (50, 50, 4))]):
+        a["min"][7 + k, :3], a["max"][7 + k, :3] = lo, hi
+    _, o = oa.brute_force_pairs(oa.oracle(), "orc_", a, small, large, 1 << 20)
+    bp = run_standalone_bp(capi.BP_GRID, a, small, large, 1 << 20)
+    assert bp.num_overlap() > base_pairs + 200
+    assert np.array_equal(oa.sorted_pair_set(bp.pairs()), oa.sorted_pair_set(o))
+    ms = []
+    for _ in range(5):
+        bp.calculate_pairs(1 << 20)
+        ms.append(bp.last_ms())
+    assert min(ms) < 5 * max(base_ms, 0.05), (ms, base_ms)
