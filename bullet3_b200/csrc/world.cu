@@ -1036,6 +1036,17 @@ extern "C" int b3b200_synchronize(b3b200_world* w)
 {
 	W_CHECK_KEEP(w);
 	B3_CUDA_CHECK(cudaStreamSynchronize(w->stream));
+	// the steps themselves never look at their counters (no host round trip); this is where a capacity overrun becomes visible
+	// without asking for the counters: the call still succeeds (the buffers were clamped, like the reference's b3Error + clamp),
+	// b3b200_last_error() says which capacity was hit
+	if (w->dCounters.ptr)
+	{
+		unsigned int ovf = 0;
+		if (cudaMemcpy(&ovf, &w->dCounters.ptr[CTR_OVERFLOW], sizeof(ovf), cudaMemcpyDeviceToHost) == cudaSuccess && ovf)
+			setLastError("capacity overrun in the last steps (flags 0x%x:%s%s%s%s%s%s): results were clamped", ovf, (ovf & OVF_PAIRS) ? " pairs" : "",
+						 (ovf & OVF_CONTACTS) ? " contacts" : "", (ovf & OVF_BATCHES) ? " batches" : "", (ovf & OVF_COMPOUND) ? " work-items" : "",
+						 (ovf & OVF_CONCAVE) ? " triangle-pairs" : "", (ovf & OVF_HALO) ? " halo" : "");
+	}
 	return 0;
 }
 

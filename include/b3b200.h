@@ -191,6 +191,8 @@ int b3b200_num_bodies(b3b200_world* w);
 int b3b200_step(b3b200_world* w, float dt);
 /* run `n` steps back to back with no host synchronisation in between */
 int b3b200_step_n(b3b200_world* w, float dt, int n);
+/* waits for the world's stream.  A capacity overrun of the steps since (pairs, contacts, batches, work items: the buffers were clamped,
+ * b3b200_get_counters()[4] holds the flags) is reported here through b3b200_last_error(); the call itself still returns 0. */
 int b3b200_synchronize(b3b200_world* w);
 
 /* per-stage entry points (parity tests call these one at a time) */

@@ -369,6 +369,10 @@ def test_contact_capacity_clamp():
     w.compute_contacts()
     c = w.counters()
     assert c[1] == 50 and (c[4] & 2)
+    # a plain step never reads its counters back; b3b200_synchronize is where the overrun is reported (the call itself succeeds)
+    w.step(1 / 60)
+    w.synchronize()
+    assert "contacts" in capi.last_error() and "overrun" in capi.last_error()
 
 
 # ------------------------------------------------------------------ solver
