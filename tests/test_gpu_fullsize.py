@@ -129,3 +129,52 @@ def test_full_size_keeps_stepping(full_world):
     assert np.median(np.linalg.norm(b["linVel"][dyn, :3], axis=1)) < 2.0
     # the pile rests on the heightfield: hardly any body below the lowest point of the mesh (h >= -2)
     assert (b["pos"][dyn, 1] < -3.0).mean() < 0.01
+
+
+@pytest.mark.timeout(600)
+def test_full_size_batched_worlds_are_isolated_and_identical_at_the_start():
+    """BASELINE configs[4](i) at full per-GPU size: 1 024 identical 257-body worlds at the same coordinates in one b3b200 world.
+    Before any step every world must see exactly world 0's pairs and contacts (same local indices, same bits: the
+    narrowphase is a pure function of a pair's two bodies); after stepping, no pair joins two worlds, the solver has no cross-block
+    batch (blocks hold whole worlds) and every pile rests on its own ground."""
+    nw = 1024
+    w = capi.World(capi.default_config(nw * 257 + 64))
+    per = scenes.batched_box_worlds(w, nw)
+    w.upload()
+    w.set_solver(capi.SOLVER_PGS, 10)
+    # a few steps first so that the piles touch their grounds (all worlds still evolve identically only in exact arithmetic of
+    # the same ORDER, so compare at the start, where no solve has happened yet)
+    w.update_aabbs()
+    w.find_pairs()
+    p = w.pairs()
+    w.compute_contacts()
+    c = w.contacts()
+    wid = w.body_worlds()
+    assert np.array_equal(wid[p["x"]], wid[p["y"]])
+    lx, ly = p["x"] - wid[p["x"]] * per, p["y"] - wid[p["y"]] * per
+    key = np.minimum(lx, ly).astype(np.int64) * per + np.maximum(lx, ly)
+    order = np.lexsort((key, wid[p["x"]]))
+    kw, ww = key[order], wid[p["x"]][order]
+    n0 = int((ww == 0).sum())
+    assert n0 > 200 and len(kw) == n0 * nw
+    assert np.array_equal(kw.reshape(nw, n0), np.tile(kw[:n0], (nw, 1)))
+    ca, cb = np.abs(c["bodyA"]), np.abs(c["bodyB"])
+    cw = wid[ca]
+    assert np.array_equal(cw, wid[cb])
+    ckey = (ca - cw * per).astype(np.int64) * per + (cb - cw * per)
+    order = np.lexsort((ckey, cw))
+    cs = c[order]
+    m0 = int((cw == 0).sum())
+    assert m0 > 50 and len(cs) == m0 * nw
+    for f in ("worldPosB", "worldNormalOnB"):
+        v = cs[f].view(np.uint32).reshape(nw, -1)
+        assert np.array_equal(v, np.tile(v[0], (nw, 1))), f
+    w.step_n(1 / 60, 120)
+    p = w.pairs()
+    assert np.array_equal(wid[p["x"]], wid[p["y"]])
+    ctr = w.counters()
+    assert ctr[4] == 0 and ctr[3] == 0 and ctr[1] > 500 * nw
+    b = w.bodies()
+    dyn = b["invMass"] != 0
+    assert np.isfinite(b["pos"]).all() and (b["pos"][dyn, 1] > 0.5).all()
+    w.close()
