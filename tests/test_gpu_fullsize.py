@@ -119,6 +119,41 @@ def test_full_size_pairs_contacts_and_batches(full_world):
 
 
 @pytest.mark.timeout(600)
+def test_full_size_sap_equals_grid_and_the_narrowphase_is_idempotent(full_world):
+    """two independent pair finders on the full scene give the same sorted pair set (uniform grid vs 1-axis sweep), and the
+    narrowphase run twice on the same state gives the same contacts bit for bit (sorted: the append order is not fixed)"""
+    w = full_world
+    bodies = w.bodies()
+    w.write_bodies(bodies)
+    w.update_aabbs()
+
+    def pair_keys():
+        w.find_pairs()
+        p = w.pairs()
+        a, b = p["x"].astype(np.int64), p["y"].astype(np.int64)
+        return np.sort(np.minimum(a, b) * len(bodies) + np.maximum(a, b))
+
+    w.set_broadphase(capi.BP_GRID)
+    grid = pair_keys()
+    w.set_broadphase(capi.BP_SAP)
+    sap = pair_keys()
+    w.set_broadphase(capi.BP_GRID)
+    assert len(grid) > 1_000_000 and np.array_equal(grid, sap)
+
+    def contact_rows():
+        w.find_pairs()
+        w.compute_contacts()
+        c = w.contacts()
+        rows = np.concatenate([c["worldPosB"].view(np.uint32).reshape(len(c), -1), c["worldNormalOnB"].view(np.uint32).reshape(len(c), -1),
+                               np.abs(c["bodyA"]).astype(np.uint32)[:, None], np.abs(c["bodyB"]).astype(np.uint32)[:, None],
+                               c["childA"].astype(np.uint32)[:, None], c["childB"].astype(np.uint32)[:, None]], axis=1)
+        return rows[np.lexsort(rows.T[::-1])]
+
+    first, second = contact_rows(), contact_rows()
+    assert len(first) > 200_000 and np.array_equal(first, second)
+
+
+@pytest.mark.timeout(600)
 def test_full_size_keeps_stepping(full_world):
     w = full_world
     w.step_n(1 / 60, 60)
